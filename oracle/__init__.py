@@ -1,0 +1,244 @@
+"""ORACLE — test infrastructure, not product code.
+
+ctypes front end for the CPU restatement of the reference hot path (``oracle/*_oracle.cpp``).
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package.  The product package
+``orb_slam3_rgbl_b200`` never imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "build" / "liborb_oracle.so"
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def build(force: bool = False) -> Path:
+    """Compile the oracle with the committed Makefile (g++ only)."""
+    srcs = list(_HERE.glob("*_oracle.cpp")) + [_HERE / "orb_pattern_31.inc", _HERE / "Makefile"]
+    stale = (not _LIB_PATH.exists()) or any(s.stat().st_mtime > _LIB_PATH.stat().st_mtime for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", str(_HERE)] + (["-B"] if force else []), check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists() or os.environ.get("ORACLE_REBUILD"):
+            build()
+        else:
+            try:
+                build()
+            except Exception:
+                pass  # prebuilt .so travels to the GPU box; make may be unnecessary there
+        _lib = C.CDLL(str(_LIB_PATH))
+        _declare(_lib)
+    return _lib
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
+                ("ini_th", C.c_int), ("min_th", C.c_int), ("lap0", C.c_int), ("lap1", C.c_int)]
+
+
+def _p(a, t=None):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _declare(L):
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    L.orc_resize_linear_u8.argtypes = [vp, i, i, i, vp, i, i, i]
+    L.orc_gaussian_blur7_u8.argtypes = [vp, i, i, i, vp, i]
+    L.orc_fast_window.argtypes = [vp, i, i, i, i, vp, i]
+    L.orc_fast_window.restype = i
+    L.orc_fast_atan2.argtypes = [f, f]
+    L.orc_fast_atan2.restype = f
+    L.orc_distribute_quadtree.argtypes = [vp, i, i, i, i, i, i, vp, i]
+    L.orc_distribute_quadtree.restype = i
+    L.orc_extractor_create.argtypes = [C.POINTER(OrbParams)]
+    L.orc_extractor_create.restype = vp
+    L.orc_extractor_destroy.argtypes = [vp]
+    L.orc_extractor_tables.argtypes = [vp, vp, vp, vp, vp]
+    L.orc_extract.argtypes = [vp, vp, i, i, i, i, i, vp, vp, i, C.POINTER(i)]
+    L.orc_extract.restype = i
+    L.orc_level_size.argtypes = [vp, i, C.POINTER(i), C.POINTER(i)]
+    L.orc_level_ptr.argtypes = [vp, i]
+    L.orc_level_ptr.restype = vp
+    L.orc_level_candidates.argtypes = [vp, i, vp, i]
+    L.orc_level_candidates.restype = i
+    L.orc_level_keypoints.argtypes = [vp, i, vp, i]
+    L.orc_level_keypoints.restype = i
+    L.orc_descriptor.argtypes = [vp, vp, i, vp]
+    L.orc_depth_project.argtypes = [vp, i, vp, i, i, f, f, vp]
+    L.orc_depth_inverse_dilation.argtypes = [vp, i, i, f, f, vp, i, i, vp]
+    L.orc_depth_average_filter.argtypes = [vp, i, i, i, vp]
+    L.orc_depth_gather.argtypes = [vp, i, vp, vp, i, f, vp, vp]
+    L.orc_depth_from_pcd.argtypes = [vp, i, vp, i, i, f, f, vp, i, i, f, vp, vp, i, vp, vp, vp, vp]
+    for name, (args, res) in _LATE.items():
+        if hasattr(L, name):
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = res
+
+
+_LATE: dict = {}
+
+# ------------------------------------------------------------------------------------------------
+# primitives
+# ------------------------------------------------------------------------------------------------
+
+def resize_linear(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def gaussian_blur7(src: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().orc_gaussian_blur7_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0])
+    return dst
+
+
+def fast_window(win: np.ndarray, th: int) -> np.ndarray:
+    """cv::FAST(win, th, nonmax=True) -> int32 [n,3] rows (x, y, score), row-major order."""
+    win = np.ascontiguousarray(win, np.uint8)
+    cap = win.size
+    out = np.empty((cap, 3), np.int32)
+    n = lib().orc_fast_window(_p(win), win.shape[1], win.shape[0], win.strides[0], th, _p(out), cap)
+    return out[:n].copy()
+
+
+def fast_atan2(y: float, x: float) -> float:
+    return float(lib().orc_fast_atan2(float(y), float(x)))
+
+
+def distribute_quadtree(kps: np.ndarray, min_x, max_x, min_y, max_y, n_desired) -> np.ndarray:
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    out = np.empty(len(kps) + 8, KP_DTYPE)
+    m = lib().orc_distribute_quadtree(_p(kps), len(kps), min_x, max_x, min_y, max_y, n_desired, _p(out), len(out))
+    return out[:m].copy()
+
+
+class Extractor:
+    """Mirror of ORB_SLAM3::ORBextractor (include/ORBextractor.h:45-108)."""
+
+    def __init__(self, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=12, min_th=7):
+        self.params = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th, 0, 0)
+        self.h = lib().orc_extractor_create(C.byref(self.params))
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        sc = np.empty(nlevels, np.float32); inv = np.empty(nlevels, np.float32)
+        q = np.empty(nlevels, np.int32); um = np.empty(16, np.int32)
+        lib().orc_extractor_tables(self.h, _p(sc), _p(inv), _p(q), _p(um))
+        self.scale_factors, self.inv_scale_factors, self.features_per_level, self.umax = sc, inv, q, um
+
+    def __del__(self):
+        try:
+            lib().orc_extractor_destroy(self.h)
+        except Exception:
+            pass
+
+    def __call__(self, img: np.ndarray, lapping=(0, 0)):
+        """-> (keypoints[KP_DTYPE], descriptors[N,32] u8, mono_index)"""
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.nfeatures + 64
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = C.c_int(0)
+        mono = lib().orc_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0],
+                                 int(lapping[0]), int(lapping[1]), _p(kps), _p(desc), cap, C.byref(n))
+        if mono < 0:
+            raise RuntimeError(f"orc_extract failed: {mono}")
+        return kps[:n.value].copy(), desc[:n.value].copy(), mono
+
+    def level_image(self, l: int) -> np.ndarray:
+        w, h = C.c_int(), C.c_int()
+        lib().orc_level_size(self.h, l, C.byref(w), C.byref(h))
+        ptr = lib().orc_level_ptr(self.h, l)
+        buf = (C.c_uint8 * (w.value * h.value)).from_address(ptr)
+        return np.frombuffer(buf, np.uint8).reshape(h.value, w.value).copy()
+
+    def level_candidates(self, l: int) -> np.ndarray:
+        cap = 1 << 18
+        out = np.empty((cap, 3), np.int32)
+        n = lib().orc_level_candidates(self.h, l, _p(out), cap)
+        return out[:n].copy()
+
+    def level_keypoints(self, l: int) -> np.ndarray:
+        out = np.empty(self.nfeatures + 64, KP_DTYPE)
+        n = lib().orc_level_keypoints(self.h, l, _p(out), len(out))
+        return out[:n].copy()
+
+
+def descriptor(kp, blurred: np.ndarray) -> np.ndarray:
+    k = np.zeros(1, KP_DTYPE); k[0] = kp
+    d = np.empty(32, np.uint8)
+    blurred = np.ascontiguousarray(blurred)
+    lib().orc_descriptor(_p(k), _p(blurred), blurred.strides[0], _p(d))
+    return d
+
+
+# ------------------------------------------------------------------------------------------------
+# DepthModule
+# ------------------------------------------------------------------------------------------------
+
+def depth_project(pts4xn: np.ndarray, P: np.ndarray, W: int, H: int, min_d=5.0, max_d=200.0) -> np.ndarray:
+    pts = np.ascontiguousarray(pts4xn, np.float32)
+    assert pts.shape[0] == 4
+    P = np.ascontiguousarray(P, np.float32).reshape(12)
+    raw = np.empty((H, W), np.float32)
+    lib().orc_depth_project(_p(pts), pts.shape[1], _p(P), W, H, min_d, max_d, _p(raw))
+    return raw
+
+
+def depth_inverse_dilation(raw: np.ndarray, mask: np.ndarray, max_d=200.0, scale=1.0) -> np.ndarray:
+    raw = np.ascontiguousarray(raw, np.float32)
+    mask = np.ascontiguousarray(mask, np.uint8)
+    out = np.empty_like(raw)
+    lib().orc_depth_inverse_dilation(_p(raw), raw.shape[1], raw.shape[0], max_d, scale, _p(mask),
+                                     mask.shape[1], mask.shape[0], _p(out))
+    return out
+
+
+def depth_average_filter(raw: np.ndarray, k: int) -> np.ndarray:
+    raw = np.ascontiguousarray(raw, np.float32)
+    out = np.empty_like(raw)
+    lib().orc_depth_average_filter(_p(raw), raw.shape[1], raw.shape[0], k, _p(out))
+    return out
+
+
+def depth_gather(dmap: np.ndarray, kps: np.ndarray, kps_un: np.ndarray, bf: float):
+    dmap = np.ascontiguousarray(dmap, np.float32)
+    kps = np.ascontiguousarray(kps, KP_DTYPE); kps_un = np.ascontiguousarray(kps_un, KP_DTYPE)
+    d = np.empty(len(kps), np.float32); u = np.empty(len(kps), np.float32)
+    lib().orc_depth_gather(_p(dmap), dmap.shape[1], _p(kps), _p(kps_un), len(kps), bf, _p(d), _p(u))
+    return d, u
+
+
+def depth_from_pcd(pts4xn, P, W, H, mask, bf, kps, kps_un, min_d=5.0, max_d=200.0):
+    pts = np.ascontiguousarray(pts4xn, np.float32)
+    P = np.ascontiguousarray(P, np.float32).reshape(12)
+    mask = np.ascontiguousarray(mask, np.uint8)
+    kps = np.ascontiguousarray(kps, KP_DTYPE); kps_un = np.ascontiguousarray(kps_un, KP_DTYPE)
+    n = len(kps)
+    d = np.empty(n, np.float32); u = np.empty(n, np.float32)
+    raw = np.empty((H, W), np.float32); proc = np.empty((H, W), np.float32)
+    lib().orc_depth_from_pcd(_p(pts), pts.shape[1], _p(P), W, H, min_d, max_d, _p(mask), mask.shape[1], mask.shape[0],
+                             bf, _p(kps), _p(kps_un), n, _p(d), _p(u), _p(raw), _p(proc))
+    return d, u, raw, proc

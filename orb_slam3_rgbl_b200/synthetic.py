@@ -1,0 +1,134 @@
+"""Seeded synthetic KITTI-like inputs; KITTI itself is not available offline.
+
+Everything is numpy-only and deterministic given the seed, so the CPU box and the GPU box
+generate identical bytes.  Formats follow the reference's example driver:
+  * image: uint8 gray H x W (``cv::imread`` + cvtColor, src/Tracking.cc:1567-1580)
+  * point cloud: float32 4 x N planar rows (x, y, z, 1) (Examples/RGB-L/rgbl_kitti.cc:168-177)
+  * calibration: Examples/RGB-L/KITTI00-02.yaml
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# Examples/RGB-L/KITTI00-02.yaml:9-12,29,44-55,63-64
+KITTI_FX = 718.856
+KITTI_FY = 718.856
+KITTI_CX = 607.1928
+KITTI_CY = 185.2157
+KITTI_BF = 100.0
+KITTI_W, KITTI_H = 1241, 376
+KITTI_TR = np.array([[4.276802385584e-04, -9.999672484946e-01, -8.084491683471e-03, -1.198459927713e-02],
+                     [-7.210626507497e-03, 8.081198471645e-03, -9.999413164504e-01, -5.403984729748e-02],
+                     [9.999738645903e-01, 4.859485810390e-04, -7.206933692422e-03, -2.921968648686e-01]], np.float64)
+LIDAR_MIN_DIST, LIDAR_MAX_DIST = 5.0, 200.0
+
+
+def camera_matrix(fx=KITTI_FX, fy=KITTI_FY, cx=KITTI_CX, cy=KITTI_CY) -> np.ndarray:
+    return np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+
+
+def lidar_projection_matrix(K: np.ndarray | None = None, Tr: np.ndarray | None = None) -> np.ndarray:
+    """3x4 float32 P = K[3x3|0] * [Tr;0001] (src/DepthModule.cc:434 builds it once on the host).
+
+    NOTE: the reference's product is evaluated by OpenCV's small-matrix path; callers that need the
+    reference's exact 12 floats must pass them across the ABI.  Here (synthetic calibration) the
+    float32(float64 product) is the definition.
+    """
+    K = camera_matrix() if K is None else K
+    Tr = KITTI_TR if Tr is None else Tr
+    return (K.astype(np.float64) @ Tr.astype(np.float64)).astype(np.float32)
+
+
+def _upsample_bilinear(a: np.ndarray, H: int, W: int) -> np.ndarray:
+    h, w = a.shape
+    ys = np.linspace(0, h - 1, H); xs = np.linspace(0, w - 1, W)
+    y0 = np.floor(ys).astype(int); x0 = np.floor(xs).astype(int)
+    y1 = np.minimum(y0 + 1, h - 1); x1 = np.minimum(x0 + 1, w - 1)
+    fy = (ys - y0)[:, None]; fx = (xs - x0)[None, :]
+    top = a[y0][:, x0] * (1 - fx) + a[y0][:, x1] * fx
+    bot = a[y1][:, x0] * (1 - fx) + a[y1][:, x1] * fx
+    return top * (1 - fy) + bot * fy
+
+
+def make_image(seed: int, W: int = KITTI_W, H: int = KITTI_H, n_rects: int = 350) -> np.ndarray:
+    """Multi-octave value noise plus random rectangles (real corners); ~10-20k FAST candidates at 1241x376."""
+    rng = np.random.default_rng(seed)
+    img = np.zeros((H, W), np.float64)
+    for div, amp in ((32, 70.0), (8, 35.0), (2, 10.0)):
+        h, w = max(2, H // div + 2), max(2, W // div + 2)
+        img += amp * _upsample_bilinear(rng.random((h, w)), H, W)
+    img += 40.0
+    scale = np.sqrt(W * H / float(KITTI_W * KITTI_H))
+    for _ in range(int(n_rects * scale * scale)):
+        rw = int(rng.integers(6, 70)); rh = int(rng.integers(6, 50))
+        x = int(rng.integers(0, W - 1)); y = int(rng.integers(0, H - 1))
+        delta = float(rng.integers(25, 90)) * (1 if rng.random() < 0.5 else -1)
+        img[y:y + rh, x:x + rw] += delta
+    img += rng.normal(0.0, 1.5, (H, W))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def make_pointcloud(seed: int, n_rings: int = 64, n_azimuth: int = 1875, W: int = KITTI_W, H: int = KITTI_H) -> np.ndarray:
+    """Velodyne-like sweep, ring-major azimuth order, float32 4 x N planar (x, y, z, 1).
+
+    Range comes from a ground plane (sensor 1.73 m above ground) plus random boxes (5-80 m), 2 cm noise.
+    Roughly 15-20 % of the points land in a KITTI image.
+    """
+    rng = np.random.default_rng(seed ^ 0x5EED)
+    elev = np.deg2rad(np.linspace(2.0, -24.8, n_rings))[:, None]
+    azim = np.linspace(-np.pi, np.pi, n_azimuth, endpoint=False)[None, :]
+    ce, se = np.cos(elev), np.sin(elev)
+    # ground plane range
+    with np.errstate(divide="ignore"):
+        r_ground = np.where(se < -1e-3, 1.73 / -se, 120.0)
+    r = np.minimum(r_ground, 120.0) * np.ones_like(azim)
+    # random "boxes": azimuth sectors at closer range
+    for _ in range(40):
+        a0 = rng.uniform(-np.pi, np.pi); aw = rng.uniform(0.03, 0.35)
+        dist = rng.uniform(5.0, 80.0)
+        top = rng.uniform(-0.02, 0.04)
+        sel = (np.abs(((azim - a0 + np.pi) % (2 * np.pi)) - np.pi) < aw)
+        hit = sel & (elev < top) & (r * ce > dist)
+        r = np.where(hit, dist / np.maximum(ce, 1e-3), r)
+    r = r + rng.normal(0.0, 0.02, r.shape)
+    x = (r * ce * np.cos(azim)).ravel(); y = (r * ce * np.sin(azim)).ravel(); z = (r * se).ravel()
+    pts = np.stack([x, y, z, np.ones_like(x)]).astype(np.float32)
+    return np.ascontiguousarray(pts)
+
+
+def make_frame(seed: int, W: int = KITTI_W, H: int = KITTI_H, n_azimuth: int = 1875):
+    return make_image(seed, W, H), make_pointcloud(seed, 64, n_azimuth, W, H)
+
+
+def structuring_element(kind: str, ku: int, kv: int | None = None) -> np.ndarray:
+    """0/1 uint8 mask [kv, ku] for DepthModule::Upsample_InverseDilation (src/DepthModule.cc:234-260).
+
+    'Diamond' follows include/DepthModule.h:138-161 (|dx|+|dy| <= r); 'Rectangle'/'Cross'/'Ellipse'
+    follow cv::getStructuringElement.
+    """
+    kv = ku if kv is None else kv
+    kind = kind.lower()
+    m = np.zeros((kv, ku), np.uint8)
+    if kind == "rectangle":
+        m[:] = 1
+    elif kind == "cross":
+        m[kv // 2, :] = 1; m[:, ku // 2] = 1
+    elif kind == "diamond":
+        if ku not in (3, 5, 7, 9):
+            raise ValueError("invalid kernel size for diamond kernel")   # DepthModule.cc:250-253
+        r = ku // 2
+        m = np.zeros((ku, ku), np.uint8)
+        for j in range(ku):
+            for i in range(ku):
+                m[j, i] = 1 if abs(i - r) + abs(j - r) <= r else 0
+    elif kind == "ellipse":
+        r, c = kv // 2, ku // 2
+        inv_r2 = 1.0 / (r * r) if r else 0.0
+        for i in range(kv):
+            dy = i - r
+            if abs(dy) <= r:
+                dx = int(np.rint(c * np.sqrt((r * r - dy * dy) * inv_r2)))
+                m[i, max(c - dx, 0):min(c + dx + 1, ku)] = 1
+    else:
+        raise ValueError(f"invalid kernel type: {kind}")
+    return m

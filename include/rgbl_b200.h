@@ -1,0 +1,148 @@
+/*
+ * rgbl_b200 — C ABI of the B200-native per-frame front end for ORB-SLAM3-RGBL.
+ *
+ * The reference has no FFI; its boundary is four C++ classes.  Each entry point
+ * below names the reference method it replaces (paths relative to the reference root).  A thin C++
+ * shim with the reference's class signatures (shim/) marshals cv::Mat /
+ * std::vector<cv::KeyPoint> to these flat buffers.
+ *
+ * Conventions: plain C types; caller-allocated outputs with explicit capacities; return 0 on
+ * success, negative rgbl_status on error (rgbl_last_error() gives the text); all pointers are HOST
+ * pointers unless the name ends in _dev; a context is bound to one CUDA device and owns its
+ * streams; calls on one context are serialised by the caller (one context per tracking thread /
+ * per camera, as the reference uses one ORBextractor per camera: src/Frame.cc:122-125).
+ * There is NO CPU fallback: without a usable CUDA device rgbl_create fails with RGBL_E_CUDA.
+ */
+#ifndef RGBL_B200_H
+#define RGBL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGBL_MAX_LEVELS 16
+#define RGBL_DESC_BYTES 32
+
+typedef enum {
+    RGBL_OK = 0,
+    RGBL_E_INVALID = -1,     /* bad argument */
+    RGBL_E_CUDA = -2,        /* CUDA runtime/driver error (no device, launch failure, ...) */
+    RGBL_E_CAPACITY = -3,    /* an output or internal buffer was too small; nothing silently dropped */
+    RGBL_E_EMPTY = -4,       /* empty image: ORBextractor::operator() returns -1 (src/ORBextractor.cc:1090) */
+    RGBL_E_UNSUPPORTED = -5
+} rgbl_status;
+
+typedef struct rgbl_ctx rgbl_ctx;
+
+/* cv::KeyPoint memory layout (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id. */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} rgbl_keypoint;
+
+/* ORBextractor constructor arguments, include/ORBextractor.h:51-52, src/ORBextractor.cc:409-469. */
+typedef struct {
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+} rgbl_orb_params;
+
+/* DepthModule parameters parsed from the YAML, src/DepthModule.cc:281-601. */
+typedef enum {
+    RGBL_DEPTH_NONE = 0,
+    RGBL_DEPTH_NEAREST_NEIGHBOR_PIXEL = 1,
+    RGBL_DEPTH_AVERAGE_FILTERING = 2,
+    RGBL_DEPTH_INVERSE_DILATION = 3
+} rgbl_depth_method;                          /* include/DepthModule.h:33-39 */
+
+typedef struct {
+    int32_t method;                            /* rgbl_depth_method */
+    float min_dist, max_dist;                  /* LiDAR.min_dist / LiDAR.max_dist */
+    float bf;                                  /* Camera.bf */
+    float inv_dilation_scale;                  /* ParamUpsampling_InverseDilation_ScaleFactor (1.0) */
+    int32_t ku, kv;                            /* structuring element size (u = columns, v = rows) */
+    uint8_t mask[81];                          /* 0/1 structuring element, row-major kv x ku (<= 9x9) */
+    int32_t avg_kernel;                        /* AverageFiltering kernel size */
+    float nn_search_radius;                    /* NearestNeighborPixel search distance */
+} rgbl_depth_params;
+
+typedef struct {
+    int32_t device;          /* CUDA device ordinal */
+    int32_t width, height;   /* image size all frames of this context share */
+    int32_t max_batch;       /* frames processed per batched call (>= 1) */
+    int32_t max_points;      /* LiDAR points per frame capacity */
+    int32_t max_candidates;  /* FAST candidates per frame capacity; 0 = default */
+    rgbl_orb_params orb;
+} rgbl_config;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int rgbl_create(const rgbl_config* cfg, rgbl_ctx** out);
+void rgbl_destroy(rgbl_ctx* ctx);
+const char* rgbl_last_error(const rgbl_ctx* ctx);     /* ctx may be NULL: error of the last failed rgbl_create */
+int rgbl_abi_version(void);
+
+/* Tables computed by ORBextractor::ORBextractor (src/ORBextractor.cc:409-469) and exposed through
+ * GetScaleFactors()/GetInverseScaleFactors()/... (include/ORBextractor.h:61-81).  Host-only. */
+int rgbl_orb_tables(const rgbl_orb_params* p, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                    int32_t* features_per_level, int32_t* umax16);
+
+/* ---- ORBextractor::operator() (include/ORBextractor.h:57-59, src/ORBextractor.cc:1086-1168) ---- *
+ * gray: CV_8UC1 host image.  kps/desc: capacity `cap` entries (cap >= nfeatures + 2*nlevels is
+ * always sufficient).  lap0/lap1 = vLappingArea.  *mono_index = the return value of
+ * the reference operator().  Returns RGBL_E_EMPTY for an empty image.                               */
+int rgbl_orb_extract(rgbl_ctx* ctx, const uint8_t* gray, int width, int height, int stride, int lap0, int lap1,
+                     rgbl_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_index);
+
+/* Batched form: n_frames images of identical size (offline sequences / several cameras); outputs
+ * are [n_frames][cap] and n_out/mono_index[n_frames].  gray[i] are host pointers.               */
+int rgbl_orb_extract_batch(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
+                           int lap0, int lap1, rgbl_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_index);
+
+/* mvImagePyramid[level] of frame slot `frame` of the last extract call, WITH the 19 px REFLECT_101
+ * border (src/ORBextractor.cc:1170-1195).  dst is (w+38) x (h+38), row stride dst_stride.        */
+int rgbl_orb_get_pyramid(rgbl_ctx* ctx, int frame, int level, uint8_t* dst, int dst_stride, int* w_out, int* h_out);
+
+/* Stage introspection for parity tests (valid after an extract call). */
+int rgbl_orb_get_level(rgbl_ctx* ctx, int frame, int level, uint8_t* dst, int dst_stride, int* w_out, int* h_out);
+int rgbl_orb_get_blurred_level(rgbl_ctx* ctx, int frame, int level, uint8_t* dst, int dst_stride);
+int rgbl_orb_get_candidates(rgbl_ctx* ctx, int frame, int level, int32_t* xys /* n x 3 */, int cap, int* n_out);
+
+/* ---- DepthModule::CalculateDepthFromPcd (include/DepthModule.h:62, src/DepthModule.cc:50-79) ---- *
+ * pts4xn: 4 x n planar float rows x,y,z,1 (Examples/RGB-L/rgbl_kitti.cc:168-177).  P: the 12 floats
+ * of LidarProjectionMatrix (row-major 3x4), passed through unchanged.  kps = mvKeys,
+ * kps_un = mvKeysUn.  depth/uright = mvDepth/mvuRight.  raw_map/processed_map (H x W float, nullable)
+ * = RawDepthMap / ProcessedDepthMap.                                                              */
+int rgbl_depth_from_pcd(rgbl_ctx* ctx, const float* pts4xn, int n_pts, const float P[12], int width, int height,
+                        const rgbl_depth_params* prm, const rgbl_keypoint* kps, const rgbl_keypoint* kps_un, int n_kp,
+                        float* depth, float* uright, float* raw_map, float* processed_map);
+
+/* Structuring element for Upsample_InverseDilation (src/DepthModule.cc:234-260): kind = "Rectangle",
+ * "Cross", "Ellipse" (cv::getStructuringElement) or "Diamond" (include/DepthModule.h:138-161).   */
+int rgbl_depth_structuring_element(const char* kind, int ku, int kv, uint8_t* mask /* kv*ku */);
+
+/* ---- fused RGB-L frame construction, src/Frame.cc:289-377 (ExtractORB + CalculateDepthFromPcd) ---- *
+ * n_frames frames: image i + point cloud i -> keypoints, descriptors, mvDepth, mvuRight.  KITTI has
+ * k1 == 0, so mvKeysUn == mvKeys (src/Frame.cc:837-843); distorted cameras use the two-call form.   */
+int rgbl_frame_rgbl_batch(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
+                          const float* const* pts4xn, const int* n_pts, const float P[12], const rgbl_depth_params* prm,
+                          rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out);
+
+/* ---- ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2058-2074).  Host-only helper. ---- */
+int rgbl_descriptor_distance(const uint8_t a[32], const uint8_t b[32]);
+
+/* ---- host-only pieces exported for tests (no GPU needed) ---- */
+/* DistributeOctTree (src/ORBextractor.cc:555-779) on candidates given relative to (minX,minY).
+ * xys: n x 3 int32 (x, y, score) in reference order.  out_idx: indices into the input, in the
+ * reference's output order.  Returns the number selected (<= N + 3).                             */
+int rgbl_quadtree_select(const int32_t* xys, int n, int min_x, int max_x, int min_y, int max_y, int n_desired,
+                         int32_t* out_idx, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGBL_B200_H */

@@ -1,0 +1,103 @@
+"""ctypes binding of librgbl_b200.so (the C ABI in include/rgbl_b200.h).
+
+The library is the product: if it is missing or cannot create a CUDA context the callers fail
+loudly — there is no Python/CPU fallback path in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "librgbl_b200.so"
+CSRC = _PKG / "csrc"
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+
+RGBL_OK, RGBL_E_INVALID, RGBL_E_CUDA, RGBL_E_CAPACITY, RGBL_E_EMPTY, RGBL_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+DEPTH_NONE, DEPTH_NEAREST_NEIGHBOR_PIXEL, DEPTH_AVERAGE_FILTERING, DEPTH_INVERSE_DILATION = 0, 1, 2, 3
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
+
+
+class DepthParams(C.Structure):
+    _fields_ = [("method", C.c_int32), ("min_dist", C.c_float), ("max_dist", C.c_float), ("bf", C.c_float),
+                ("inv_dilation_scale", C.c_float), ("ku", C.c_int32), ("kv", C.c_int32),
+                ("mask", C.c_uint8 * 81), ("avg_kernel", C.c_int32), ("nn_search_radius", C.c_float)]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("max_batch", C.c_int32),
+                ("max_points", C.c_int32), ("max_candidates", C.c_int32), ("orb", OrbParams)]
+
+
+def build(force: bool = False) -> Path:
+    """Compile librgbl_b200.so in-tree with nvcc for sm_100a (see csrc/Makefile)."""
+    cmd = ["make", "-C", str(CSRC)] + (["-B"] if force else [])
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building librgbl_b200.so failed:\n" + r.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/rgbl_b200.h declares must be listed here
+_vp, _i, _f = C.c_void_p, C.c_int, C.c_float
+_ip = C.POINTER(C.c_int)
+SYMBOLS = {
+    "rgbl_create": (_i, [C.POINTER(Config), C.POINTER(_vp)]),
+    "rgbl_destroy": (None, [_vp]),
+    "rgbl_last_error": (C.c_char_p, [_vp]),
+    "rgbl_abi_version": (_i, []),
+    "rgbl_orb_tables": (_i, [C.POINTER(OrbParams), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rgbl_orb_extract": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _ip, _ip]),
+    "rgbl_orb_extract_batch": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "rgbl_orb_get_pyramid": (_i, [_vp, _i, _i, _vp, _i, _ip, _ip]),
+    "rgbl_orb_get_level": (_i, [_vp, _i, _i, _vp, _i, _ip, _ip]),
+    "rgbl_orb_get_blurred_level": (_i, [_vp, _i, _i, _vp, _i]),
+    "rgbl_orb_get_candidates": (_i, [_vp, _i, _i, _vp, _i, _ip]),
+    "rgbl_depth_from_pcd": (_i, [_vp, _vp, _i, _vp, _i, _i, C.POINTER(DepthParams), _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "rgbl_depth_structuring_element": (_i, [C.c_char_p, _i, _i, _vp]),
+    "rgbl_frame_rgbl_batch": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(DepthParams), _vp, _vp, _vp, _vp, _i, _vp]),
+    "rgbl_descriptor_distance": (_i, [_vp, _vp]),
+    "rgbl_quadtree_select": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i]),
+}
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)          # AttributeError if the ABI lost a symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class RgblError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rgbl error {code}: {msg}")
+        self.code = code
+
+
+def check(rc: int, ctx=None):
+    if rc != 0:
+        msg = lib().rgbl_last_error(ctx)
+        raise RgblError(rc, msg.decode() if msg else "")

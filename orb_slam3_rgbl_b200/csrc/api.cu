@@ -1,0 +1,512 @@
+// Context, memory plan and the C ABI entry points of librgbl_b200.so (see include/rgbl_b200.h).
+// There is no CPU fallback anywhere in this file: every compute entry point needs the CUDA device
+// the context was created on and reports RGBL_E_CUDA otherwise.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "rgbl_kernels.h"
+
+namespace rgbl {
+
+static thread_local std::string g_create_error;
+
+struct Ctx {
+    rgbl_config cfg{};
+    OrbTables tab{};
+    std::vector<LevelGeom> levels;
+    std::vector<CellInfo> cells;
+    std::vector<LinCoef> coefs;
+    size_t frame_bytes = 0;
+    int n_cells = 0;
+    int cap_kp = 0;              // keypoints per frame capacity (nfeatures + 3 per level)
+    int dense_cap = 0;           // candidates per batch capacity
+    std::string err;
+
+    cudaStream_t st = nullptr, st_aux = nullptr;
+    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
+
+    // device
+    LevelGeom* d_levels = nullptr;
+    CellInfo* d_cells = nullptr;
+    LinCoef* d_coefs = nullptr;
+    uint8_t *d_pyr = nullptr, *d_blur = nullptr;
+    uint32_t* d_slots = nullptr;
+    int *d_counts = nullptr, *d_cell_off = nullptr, *d_level_cnt = nullptr, *d_frame_total = nullptr, *d_overflow = nullptr;
+    uint32_t* d_dense = nullptr;
+    SelKp* d_sel = nullptr;
+    int* d_n_sel = nullptr;
+    rgbl_keypoint *d_kps = nullptr, *d_kps_un = nullptr, *d_kps_in = nullptr;
+    int* d_n_kp_in = nullptr;
+    uint8_t* d_desc = nullptr;
+    float* d_pts = nullptr;
+    int* d_n_pts = nullptr;
+    uint32_t* d_idx_map = nullptr;
+    float *d_raw = nullptr, *d_processed = nullptr, *d_depth = nullptr, *d_uright = nullptr;
+    uint8_t* d_scratch = nullptr;   // padded-level export
+    size_t scratch_bytes = 0;
+    uint32_t stamp = 0;
+
+    // pinned host
+    int *h_level_cnt = nullptr, *h_frame_total = nullptr, *h_overflow = nullptr, *h_n_sel = nullptr, *h_n_pts = nullptr;
+    uint32_t* h_dense = nullptr;
+    SelKp* h_sel = nullptr;
+
+    int last_frames = 0;         // frames valid in the device buffers
+    bool blur_valid = false;
+};
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return RGBL_E_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+template <class T>
+static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+template <class T>
+static cudaError_t hmalloc(T** p, size_t n) { return cudaMallocHost((void**)p, n * sizeof(T)); }
+
+static void release(Ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    void* dev[] = {c->d_levels, c->d_cells, c->d_coefs, c->d_pyr, c->d_blur, c->d_slots, c->d_counts, c->d_cell_off,
+                   c->d_level_cnt, c->d_frame_total, c->d_overflow, c->d_dense, c->d_sel, c->d_n_sel, c->d_kps,
+                   c->d_kps_un, c->d_desc, c->d_pts, c->d_n_pts, c->d_idx_map, c->d_raw, c->d_processed, c->d_depth,
+                   c->d_uright, c->d_scratch, c->d_kps_in, c->d_n_kp_in};
+    for (void* p : dev) if (p) cudaFree(p);
+    void* host[] = {c->h_level_cnt, c->h_frame_total, c->h_overflow, c->h_n_sel, c->h_n_pts, c->h_dense, c->h_sel};
+    for (void* p : host) if (p) cudaFreeHost(p);
+    if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
+    if (c->ev_blur) cudaEventDestroy(c->ev_blur);
+    if (c->st) cudaStreamDestroy(c->st);
+    if (c->st_aux) cudaStreamDestroy(c->st_aux);
+    delete c;
+}
+
+static int create(const rgbl_config* cfg, Ctx** out) {
+    Ctx* c = new Ctx();
+    c->cfg = *cfg;
+    auto fail = [&](int rc) { g_create_error = c->err; release(c); return rc; };
+    if (cfg->width < 1 || cfg->height < 1 || cfg->max_batch < 1 || cfg->max_points < 0) { c->err = "invalid configuration"; return fail(RGBL_E_INVALID); }
+    if (cfg->max_points >= (1 << 22) - 1) { c->err = "max_points must be < 4194303"; return fail(RGBL_E_UNSUPPORTED); }
+    int rc = compute_orb_tables(cfg->orb, c->tab);
+    if (rc) { c->err = "invalid ORB parameters"; return fail(rc); }
+    rc = build_geometry(cfg->width, cfg->height, c->tab, c->levels, c->cells, c->coefs, c->frame_bytes, c->err);
+    if (rc) return fail(rc);
+    c->n_cells = (int)c->cells.size();
+    c->cap_kp = cfg->orb.nfeatures + 3 * cfg->orb.nlevels;
+    const int B = cfg->max_batch;
+    const int per_frame_cand = cfg->max_candidates > 0 ? cfg->max_candidates : std::max(32768, cfg->width * cfg->height / 8);
+    c->dense_cap = per_frame_cand * B;
+
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { c->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e) + " (librgbl_b200 has no CPU fallback)"; return fail(RGBL_E_CUDA); }
+    const int nl = c->tab.nlevels;
+    const size_t WH = (size_t)cfg->width * cfg->height;
+#define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { c->err = std::string(#call) + ": " + cudaGetErrorString(e_); return fail(RGBL_E_CUDA); } } while (0)
+    CUF(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CUF(cudaStreamCreateWithFlags(&c->st_aux, cudaStreamNonBlocking));
+    CUF(cudaEventCreateWithFlags(&c->ev_pyr, cudaEventDisableTiming));
+    CUF(cudaEventCreateWithFlags(&c->ev_blur, cudaEventDisableTiming));
+    CUF(dmalloc(&c->d_levels, nl));
+    CUF(dmalloc(&c->d_cells, c->cells.size()));
+    CUF(dmalloc(&c->d_coefs, std::max<size_t>(c->coefs.size(), 1)));
+    CUF(cudaMemcpy(c->d_levels, c->levels.data(), nl * sizeof(LevelGeom), cudaMemcpyHostToDevice));
+    CUF(cudaMemcpy(c->d_cells, c->cells.data(), c->cells.size() * sizeof(CellInfo), cudaMemcpyHostToDevice));
+    if (!c->coefs.empty()) CUF(cudaMemcpy(c->d_coefs, c->coefs.data(), c->coefs.size() * sizeof(LinCoef), cudaMemcpyHostToDevice));
+    CUF(dmalloc(&c->d_pyr, c->frame_bytes * B));
+    CUF(dmalloc(&c->d_blur, c->frame_bytes * B));
+    CUF(cudaMemset(c->d_pyr, 0, c->frame_bytes * B));
+    CUF(cudaMemset(c->d_blur, 0, c->frame_bytes * B));
+    CUF(dmalloc(&c->d_slots, (size_t)B * c->n_cells * kCellCap));
+    CUF(dmalloc(&c->d_counts, (size_t)B * c->n_cells));
+    CUF(dmalloc(&c->d_cell_off, (size_t)B * c->n_cells));
+    CUF(dmalloc(&c->d_level_cnt, (size_t)B * RGBL_MAX_LEVELS));
+    CUF(dmalloc(&c->d_frame_total, (size_t)B));
+    CUF(dmalloc(&c->d_overflow, 1));
+    CUF(cudaMemset(c->d_overflow, 0, sizeof(int)));
+    CUF(dmalloc(&c->d_dense, (size_t)c->dense_cap));
+    CUF(dmalloc(&c->d_sel, (size_t)B * c->cap_kp));
+    CUF(dmalloc(&c->d_n_sel, (size_t)B));
+    CUF(dmalloc(&c->d_kps, (size_t)B * c->cap_kp));
+    CUF(dmalloc(&c->d_kps_un, (size_t)c->cap_kp));
+    CUF(dmalloc(&c->d_kps_in, (size_t)c->cap_kp));
+    CUF(dmalloc(&c->d_n_kp_in, 1));
+    CUF(dmalloc(&c->d_desc, (size_t)B * c->cap_kp * 32));
+    CUF(dmalloc(&c->d_depth, (size_t)B * c->cap_kp));
+    CUF(dmalloc(&c->d_uright, (size_t)B * c->cap_kp));
+    if (cfg->max_points > 0) {
+        CUF(dmalloc(&c->d_pts, (size_t)B * 4 * cfg->max_points));
+        CUF(dmalloc(&c->d_n_pts, (size_t)B));
+        CUF(dmalloc(&c->d_idx_map, (size_t)B * WH));
+        CUF(cudaMemset(c->d_idx_map, 0, (size_t)B * WH * sizeof(uint32_t)));
+        CUF(dmalloc(&c->d_raw, (size_t)B * WH));
+        CUF(dmalloc(&c->d_processed, (size_t)B * WH));
+        CUF(hmalloc(&c->h_n_pts, (size_t)B));
+    }
+    c->scratch_bytes = (size_t)(cfg->width + 2 * kEdgeThreshold + 64) * (cfg->height + 2 * kEdgeThreshold);
+    CUF(dmalloc(&c->d_scratch, c->scratch_bytes));
+    CUF(hmalloc(&c->h_level_cnt, (size_t)B * RGBL_MAX_LEVELS));
+    CUF(hmalloc(&c->h_frame_total, (size_t)B));
+    CUF(hmalloc(&c->h_overflow, 1));
+    CUF(hmalloc(&c->h_n_sel, (size_t)B));
+    CUF(hmalloc(&c->h_dense, (size_t)c->dense_cap));
+    CUF(hmalloc(&c->h_sel, (size_t)B * c->cap_kp));
+#undef CUF
+    *out = c;
+    return RGBL_OK;
+}
+
+// ---- extraction pipeline -----------------------------------------------------------------------
+// Stage 1 (device): upload, pyramid, FAST + compaction; blur on the aux stream.
+// Stage 2 (host):   quad-tree per (frame, level) on worker threads -> SelKp lists.
+// Stage 3 (device): describe.  Results stay in d_kps / d_desc (and are copied out by the callers).
+static int run_extract(Ctx* c, int n_frames, const uint8_t* const* gray, int stride) {
+    const int W = c->cfg.width, H = c->cfg.height, nl = c->tab.nlevels;
+    const LevelGeom& l0 = c->levels[0];
+    for (int f = 0; f < n_frames; ++f)
+        CU(cudaMemcpy2DAsync(c->d_pyr + (size_t)f * c->frame_bytes + l0.off, l0.pitch, gray[f], stride, W, H,
+                             cudaMemcpyHostToDevice, c->st));
+    launch_pyramid(c->st, c->d_pyr, c->frame_bytes, c->levels.data(), nl, c->d_coefs, n_frames);
+    CU(cudaEventRecord(c->ev_pyr, c->st));
+    CU(cudaStreamWaitEvent(c->st_aux, c->ev_pyr, 0));
+    launch_blur(c->st_aux, c->d_pyr, c->d_blur, c->frame_bytes, c->levels.data(), nl, n_frames);
+    CU(cudaEventRecord(c->ev_blur, c->st_aux));
+    launch_fast(c->st, c->d_pyr, c->frame_bytes, c->d_levels, nl, c->d_cells, c->n_cells, c->cfg.orb.ini_th_fast,
+                c->cfg.orb.min_th_fast, c->d_slots, c->d_counts, c->d_cell_off, c->d_level_cnt, c->d_frame_total,
+                c->d_dense, c->dense_cap, c->d_overflow, n_frames);
+    CU(cudaMemcpyAsync(c->h_level_cnt, c->d_level_cnt, (size_t)n_frames * RGBL_MAX_LEVELS * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(c->h_frame_total, c->d_frame_total, (size_t)n_frames * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (*c->h_overflow) {
+        cudaMemsetAsync(c->d_overflow, 0, sizeof(int), c->st);
+        c->err = (*c->h_overflow == 1) ? "FAST cell slot overflow (>256 survivors in one cell)" : "candidate buffer overflow: raise max_candidates";
+        return RGBL_E_CAPACITY;
+    }
+    size_t total = 0;
+    std::vector<size_t> fbase(n_frames + 1, 0);
+    for (int f = 0; f < n_frames; ++f) { total += c->h_frame_total[f]; fbase[f + 1] = total; }
+    if (total > (size_t)c->dense_cap) { c->err = "candidate buffer overflow: raise max_candidates"; return RGBL_E_CAPACITY; }
+    if (total) CU(cudaMemcpyAsync(c->h_dense, c->d_dense, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+
+    // host quad-tree: tasks = (frame, level)
+    std::vector<int> sel_count((size_t)n_frames * nl, 0);
+    std::vector<std::vector<SelKp>> sel_lists((size_t)n_frames * nl);
+    std::atomic<int> next{0};
+    std::atomic<int> status{0};
+    const int n_tasks = n_frames * nl;
+    auto worker = [&]() {
+        std::vector<int32_t> xys, idx;
+        for (;;) {
+            const int t = next.fetch_add(1);
+            if (t >= n_tasks) break;
+            const int f = t / nl, l = t % nl;
+            size_t off = fbase[f];
+            for (int k = 0; k < l; ++k) off += c->h_level_cnt[f * RGBL_MAX_LEVELS + k];
+            const int n = c->h_level_cnt[f * RGBL_MAX_LEVELS + l];
+            const LevelGeom& lg = c->levels[l];
+            xys.resize((size_t)n * 3);
+            for (int k = 0; k < n; ++k) {
+                const uint32_t p = c->h_dense[off + k];
+                xys[3 * k] = (int)(p & 0xfff); xys[3 * k + 1] = (int)((p >> 12) & 0xfff); xys[3 * k + 2] = (int)(p >> 24);
+            }
+            idx.resize((size_t)lg.quota + 8);
+            int m = quadtree_select(xys.data(), n, lg.min_bx, lg.max_bx, lg.min_by, lg.max_by, lg.quota, idx.data(), (int)idx.size());
+            if (m < 0) { status.store(m); continue; }
+            std::vector<SelKp>& out = sel_lists[t];
+            out.resize(m);
+            for (int k = 0; k < m; ++k) {
+                const int q = idx[k];
+                out[k].x = (uint16_t)(xys[3 * q] + lg.min_bx);
+                out[k].y = (uint16_t)(xys[3 * q + 1] + lg.min_by);
+                out[k].level = (uint8_t)l; out[k].score = (uint8_t)xys[3 * q + 2]; out[k].pad = 0;
+            }
+        }
+    };
+    int n_threads = (int)std::thread::hardware_concurrency();
+    n_threads = std::max(1, std::min(std::min(n_threads, 32), n_tasks));
+    if (n_threads == 1) worker();
+    else {
+        std::vector<std::thread> pool;
+        for (int i = 0; i < n_threads; ++i) pool.emplace_back(worker);
+        for (auto& th : pool) th.join();
+    }
+    if (status.load()) { c->err = "quad-tree selection failed"; return status.load(); }
+    int max_n = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        int n = 0;
+        for (int l = 0; l < nl; ++l) {
+            const std::vector<SelKp>& s = sel_lists[(size_t)f * nl + l];
+            if (n + (int)s.size() > c->cap_kp) { c->err = "keypoint capacity exceeded"; return RGBL_E_CAPACITY; }
+            if (!s.empty()) std::memcpy(c->h_sel + (size_t)f * c->cap_kp + n, s.data(), s.size() * sizeof(SelKp));
+            n += (int)s.size();
+        }
+        c->h_n_sel[f] = n;
+        max_n = std::max(max_n, n);
+    }
+    CU(cudaMemcpyAsync(c->d_sel, c->h_sel, (size_t)n_frames * c->cap_kp * sizeof(SelKp), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(c->d_n_sel, c->h_n_sel, (size_t)n_frames * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CU(cudaStreamWaitEvent(c->st, c->ev_blur, 0));
+    launch_describe(c->st, c->d_pyr, c->d_blur, c->frame_bytes, c->d_levels, c->d_sel, c->d_n_sel, c->cap_kp, max_n,
+                    c->tab.umax, c->d_kps, c->d_desc, n_frames);
+    CU(cudaGetLastError());
+    c->last_frames = n_frames;
+    c->blur_valid = true;
+    return max_n;
+}
+
+static int setup_depth(Ctx* c, const float P[12], const rgbl_depth_params* prm, DepthDev& dd) {
+    if (!c->d_pts) { c->err = "context was created with max_points == 0"; return RGBL_E_INVALID; }
+    if (prm->method != RGBL_DEPTH_INVERSE_DILATION) { c->err = "only LiDAR.Method InverseDilation is implemented on the device"; return RGBL_E_UNSUPPORTED; }
+    if (prm->ku < 1 || prm->kv < 1 || prm->ku > 9 || prm->kv > 9) { c->err = "structuring element must be 1..9"; return RGBL_E_INVALID; }
+    std::memcpy(dd.P, P, sizeof(float) * 12);
+    dd.min_dist = prm->min_dist; dd.max_dist = prm->max_dist; dd.bf = prm->bf;
+    dd.inv_scale_m = prm->max_dist * prm->inv_dilation_scale;
+    dd.ku = prm->ku; dd.kv = prm->kv;
+    std::memcpy(dd.mask, prm->mask, 81);
+    if (++c->stamp >= 1023u) {
+        // stamp wrap: clear the index map once every 1022 calls
+        if (cudaMemsetAsync(c->d_idx_map, 0, (size_t)c->cfg.max_batch * c->cfg.width * c->cfg.height * sizeof(uint32_t), c->st) != cudaSuccess) {
+            c->err = "cudaMemsetAsync(idx_map) failed"; return RGBL_E_CUDA;
+        }
+        c->stamp = 1;
+    }
+    return RGBL_OK;
+}
+
+}  // namespace rgbl
+
+using namespace rgbl;
+
+extern "C" {
+
+int rgbl_create(const rgbl_config* cfg, rgbl_ctx** out) {
+    if (!cfg || !out) return RGBL_E_INVALID;
+    *out = nullptr;
+    Ctx* c = nullptr;
+    int rc = create(cfg, &c);
+    if (rc) return rc;
+    *out = reinterpret_cast<rgbl_ctx*>(c);
+    return RGBL_OK;
+}
+
+void rgbl_destroy(rgbl_ctx* ctx) { release(reinterpret_cast<Ctx*>(ctx)); }
+
+const char* rgbl_last_error(const rgbl_ctx* ctx) {
+    if (!ctx) return g_create_error.c_str();
+    return reinterpret_cast<const Ctx*>(ctx)->err.c_str();
+}
+
+int rgbl_orb_extract_batch(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
+                           int lap0, int lap1, rgbl_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_index) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!gray || n_frames < 1 || !kps || !desc || !n_out) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (width <= 0 || height <= 0) { c->err = "empty image"; return RGBL_E_EMPTY; }
+    for (int f = 0; f < n_frames; ++f) if (!gray[f]) { c->err = "empty image"; return RGBL_E_EMPTY; }
+    if (width != c->cfg.width || height != c->cfg.height || stride < width) { c->err = "image size does not match the context"; return RGBL_E_INVALID; }
+    if (n_frames > c->cfg.max_batch) { c->err = "n_frames exceeds max_batch"; return RGBL_E_CAPACITY; }
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = run_extract(c, n_frames, gray, stride);
+    if (rc < 0) return rc;
+    for (int f = 0; f < n_frames; ++f) {
+        const int n = c->h_n_sel[f];
+        n_out[f] = n;
+        if (n > cap) { c->err = "output capacity too small"; return RGBL_E_CAPACITY; }
+        if (n) {
+            CU(cudaMemcpyAsync(kps + (size_t)f * cap, c->d_kps + (size_t)f * c->cap_kp, (size_t)n * sizeof(rgbl_keypoint), cudaMemcpyDeviceToHost, c->st));
+            CU(cudaMemcpyAsync(desc + (size_t)f * cap * 32, c->d_desc + (size_t)f * c->cap_kp * 32, (size_t)n * 32, cudaMemcpyDeviceToHost, c->st));
+        }
+    }
+    CU(cudaStreamSynchronize(c->st));
+    // vLappingArea placement (src/ORBextractor.cc:1153-1162): lapping keypoints fill the back.
+    for (int f = 0; f < n_frames; ++f) {
+        const int n = n_out[f];
+        int mono = n;
+        if (!(lap0 == 0 && lap1 == 0)) {
+            rgbl_keypoint* k = kps + (size_t)f * cap;
+            uint8_t* d = desc + (size_t)f * cap * 32;
+            std::vector<rgbl_keypoint> k2(n);
+            std::vector<uint8_t> d2((size_t)n * 32);
+            int mi = 0, si = n - 1;
+            for (int i = 0; i < n; ++i) {
+                const bool lapping = k[i].x >= (float)lap0 && k[i].x <= (float)lap1;
+                const int slot = lapping ? si-- : mi++;
+                k2[slot] = k[i];
+                std::memcpy(&d2[(size_t)slot * 32], d + (size_t)i * 32, 32);
+            }
+            std::memcpy(k, k2.data(), (size_t)n * sizeof(rgbl_keypoint));
+            std::memcpy(d, d2.data(), (size_t)n * 32);
+            mono = mi;
+        }
+        if (mono_index) mono_index[f] = mono;
+    }
+    return RGBL_OK;
+}
+
+int rgbl_orb_extract(rgbl_ctx* ctx, const uint8_t* gray, int width, int height, int stride, int lap0, int lap1,
+                     rgbl_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_index) {
+    const uint8_t* g[1] = {gray};
+    return rgbl_orb_extract_batch(ctx, 1, g, width, height, stride, lap0, lap1, kps, desc, cap, n_out, mono_index);
+}
+
+static int check_frame_level(Ctx* c, int frame, int level) {
+    if (frame < 0 || frame >= c->last_frames || level < 0 || level >= c->tab.nlevels) { c->err = "frame/level out of range (no extraction yet?)"; return RGBL_E_INVALID; }
+    return RGBL_OK;
+}
+
+int rgbl_orb_get_pyramid(rgbl_ctx* ctx, int frame, int level, uint8_t* dst, int dst_stride, int* w_out, int* h_out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !dst) return RGBL_E_INVALID;
+    int rc = check_frame_level(c, frame, level); if (rc) return rc;
+    const LevelGeom& lg = c->levels[level];
+    const int W = lg.w + 2 * kEdgeThreshold, H = lg.h + 2 * kEdgeThreshold;
+    if (dst_stride < W) { c->err = "dst_stride too small"; return RGBL_E_INVALID; }
+    CU(cudaSetDevice(c->cfg.device));
+    const int pitch = (W + 63) & ~63;
+    launch_padded_level(c->st, c->d_pyr, c->frame_bytes, frame, lg, c->d_scratch, pitch);
+    CU(cudaMemcpy2DAsync(dst, dst_stride, c->d_scratch, pitch, W, H, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (w_out) *w_out = lg.w;
+    if (h_out) *h_out = lg.h;
+    return RGBL_OK;
+}
+
+static int get_plane(Ctx* c, const uint8_t* base, int frame, int level, uint8_t* dst, int dst_stride, int* w_out, int* h_out) {
+    int rc = check_frame_level(c, frame, level); if (rc) return rc;
+    const LevelGeom& lg = c->levels[level];
+    if (dst_stride < lg.w) { c->err = "dst_stride too small"; return RGBL_E_INVALID; }
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaMemcpy2DAsync(dst, dst_stride, base + (size_t)frame * c->frame_bytes + lg.off, lg.pitch, lg.w, lg.h, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (w_out) *w_out = lg.w;
+    if (h_out) *h_out = lg.h;
+    return RGBL_OK;
+}
+
+int rgbl_orb_get_level(rgbl_ctx* ctx, int frame, int level, uint8_t* dst, int dst_stride, int* w_out, int* h_out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !dst) return RGBL_E_INVALID;
+    return get_plane(c, c->d_pyr, frame, level, dst, dst_stride, w_out, h_out);
+}
+
+int rgbl_orb_get_blurred_level(rgbl_ctx* ctx, int frame, int level, uint8_t* dst, int dst_stride) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !dst) return RGBL_E_INVALID;
+    if (!c->blur_valid) { c->err = "no extraction yet"; return RGBL_E_INVALID; }
+    CU(cudaStreamSynchronize(c->st_aux));
+    return get_plane(c, c->d_blur, frame, level, dst, dst_stride, nullptr, nullptr);
+}
+
+int rgbl_orb_get_candidates(rgbl_ctx* ctx, int frame, int level, int32_t* xys, int cap, int* n_out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !xys || !n_out) return RGBL_E_INVALID;
+    int rc = check_frame_level(c, frame, level); if (rc) return rc;
+    size_t off = 0;
+    for (int f = 0; f < frame; ++f) off += c->h_frame_total[f];
+    for (int l = 0; l < level; ++l) off += c->h_level_cnt[frame * RGBL_MAX_LEVELS + l];
+    const int n = c->h_level_cnt[frame * RGBL_MAX_LEVELS + level];
+    *n_out = n;
+    if (n > cap) { c->err = "capacity too small"; return RGBL_E_CAPACITY; }
+    for (int k = 0; k < n; ++k) {
+        const uint32_t p = c->h_dense[off + k];
+        xys[3 * k] = (int)(p & 0xfff); xys[3 * k + 1] = (int)((p >> 12) & 0xfff); xys[3 * k + 2] = (int)(p >> 24);
+    }
+    return RGBL_OK;
+}
+
+int rgbl_depth_from_pcd(rgbl_ctx* ctx, const float* pts4xn, int n_pts, const float P[12], int width, int height,
+                        const rgbl_depth_params* prm, const rgbl_keypoint* kps, const rgbl_keypoint* kps_un, int n_kp,
+                        float* depth, float* uright, float* raw_map, float* processed_map) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!pts4xn || !P || !prm || n_pts < 0 || n_kp < 0 || (n_kp > 0 && (!kps || !kps_un || !depth || !uright))) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (width != c->cfg.width || height != c->cfg.height) { c->err = "image size does not match the context"; return RGBL_E_INVALID; }
+    if (n_pts > c->cfg.max_points) { c->err = "n_pts exceeds max_points"; return RGBL_E_CAPACITY; }
+    if (n_kp > c->cap_kp) { c->err = "n_kp exceeds keypoint capacity"; return RGBL_E_CAPACITY; }
+    CU(cudaSetDevice(c->cfg.device));
+    DepthDev dd;
+    int rc = setup_depth(c, P, prm, dd); if (rc) return rc;
+    const size_t WH = (size_t)width * height;
+    c->h_n_pts[0] = n_pts;
+    int* h_nkp = c->h_overflow;          // 1-int pinned scratch (overflow flag is re-read on every extract)
+    *h_nkp = n_kp;
+    if (n_pts) CU(cudaMemcpyAsync(c->d_pts, pts4xn, (size_t)4 * n_pts * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(c->d_n_pts, c->h_n_pts, sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(c->d_n_kp_in, h_nkp, sizeof(int), cudaMemcpyHostToDevice, c->st));
+    if (n_kp) {
+        CU(cudaMemcpyAsync(c->d_kps_in, kps, (size_t)n_kp * sizeof(rgbl_keypoint), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(c->d_kps_un, kps_un, (size_t)n_kp * sizeof(rgbl_keypoint), cudaMemcpyHostToDevice, c->st));
+    }
+    launch_depth_project(c->st, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, n_pts, dd, width, height, c->d_idx_map, c->stamp, 1);
+    launch_depth_resolve_dilate(c->st, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, dd, width, height, c->d_idx_map, c->stamp,
+                                c->d_raw, c->d_processed, 1);
+    launch_depth_gather(c->st, c->d_processed, width, height, c->d_kps_in, c->d_kps_un, c->d_n_kp_in, c->cap_kp, n_kp, dd.bf,
+                        c->d_depth, c->d_uright, 1);
+    CU(cudaGetLastError());
+    if (n_kp) {
+        CU(cudaMemcpyAsync(depth, c->d_depth, (size_t)n_kp * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(uright, c->d_uright, (size_t)n_kp * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    }
+    if (raw_map) CU(cudaMemcpyAsync(raw_map, c->d_raw, WH * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    if (processed_map) CU(cudaMemcpyAsync(processed_map, c->d_processed, WH * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return RGBL_OK;
+}
+
+int rgbl_frame_rgbl_batch(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
+                          const float* const* pts4xn, const int* n_pts, const float P[12], const rgbl_depth_params* prm,
+                          rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!gray || !pts4xn || !n_pts || !P || !prm || !kps || !desc || !depth || !uright || !n_out || n_frames < 1) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (width <= 0 || height <= 0) { c->err = "empty image"; return RGBL_E_EMPTY; }
+    if (width != c->cfg.width || height != c->cfg.height || stride < width) { c->err = "image size does not match the context"; return RGBL_E_INVALID; }
+    if (n_frames > c->cfg.max_batch) { c->err = "n_frames exceeds max_batch"; return RGBL_E_CAPACITY; }
+    int max_pts = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        if (!gray[f]) { c->err = "empty image"; return RGBL_E_EMPTY; }
+        if (n_pts[f] < 0 || n_pts[f] > c->cfg.max_points || (n_pts[f] && !pts4xn[f])) { c->err = "bad point cloud"; return RGBL_E_CAPACITY; }
+        max_pts = std::max(max_pts, n_pts[f]);
+    }
+    CU(cudaSetDevice(c->cfg.device));
+    DepthDev dd;
+    int rc = setup_depth(c, P, prm, dd); if (rc) return rc;
+    // depth projection/upsampling does not depend on the keypoints: issue it on the aux stream first
+    for (int f = 0; f < n_frames; ++f) {
+        c->h_n_pts[f] = n_pts[f];
+        if (n_pts[f]) CU(cudaMemcpyAsync(c->d_pts + (size_t)f * 4 * c->cfg.max_points, pts4xn[f], (size_t)4 * n_pts[f] * sizeof(float), cudaMemcpyHostToDevice, c->st_aux));
+    }
+    CU(cudaMemcpyAsync(c->d_n_pts, c->h_n_pts, (size_t)n_frames * sizeof(int), cudaMemcpyHostToDevice, c->st_aux));
+    launch_depth_project(c->st_aux, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, max_pts, dd, width, height, c->d_idx_map, c->stamp, n_frames);
+    launch_depth_resolve_dilate(c->st_aux, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, dd, width, height, c->d_idx_map, c->stamp,
+                                nullptr, c->d_processed, n_frames);
+    int max_n = run_extract(c, n_frames, gray, stride);     // waits on ev_blur (recorded after the depth work on st_aux)
+    if (max_n < 0) return max_n;
+    launch_depth_gather(c->st, c->d_processed, width, height, c->d_kps, c->d_kps, c->d_n_sel, c->cap_kp, max_n, dd.bf,
+                        c->d_depth, c->d_uright, n_frames);
+    CU(cudaGetLastError());
+    for (int f = 0; f < n_frames; ++f) {
+        const int n = c->h_n_sel[f];
+        n_out[f] = n;
+        if (n > cap) { c->err = "output capacity too small"; return RGBL_E_CAPACITY; }
+        if (!n) continue;
+        CU(cudaMemcpyAsync(kps + (size_t)f * cap, c->d_kps + (size_t)f * c->cap_kp, (size_t)n * sizeof(rgbl_keypoint), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(desc + (size_t)f * cap * 32, c->d_desc + (size_t)f * c->cap_kp * 32, (size_t)n * 32, cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(depth + (size_t)f * cap, c->d_depth + (size_t)f * c->cap_kp, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(uright + (size_t)f * cap, c->d_uright + (size_t)f * c->cap_kp, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    }
+    CU(cudaStreamSynchronize(c->st));
+    return RGBL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// DepthModule kernels for sm_100a (reference: src/DepthModule.cc:50-139,230-274).
+//
+//   project  : one LiDAR point per thread; Q = P*X with each dot product accumulated in double and
+//              rounded once (what cv::gemm does for CV_32F), u = Qx*(1/Qz), v = Qy*(1/Qz) with the
+//              reciprocal rounded separately (Mat::mul(1/row)), strict bounds, C truncation.
+//              The reference scatters sequentially, so the LAST point in file order owns a pixel:
+//              atomicMax on (stamp << 22 | point_index+1).  The per-call stamp makes stale entries of
+//              earlier frames lose automatically, so the index map is never cleared on the hot path.
+//   resolve+dilate : per tile, recompute the winning point's depth (same arithmetic), build the
+//              inverted map t = M - d (zeroed above M-1), take the max over the structuring element,
+//              invert back: the exact float pipeline of Upsample_InverseDilation.
+//   gather   : GetFeatureDepthFromDepthMap (:82-104).
+#include <cfloat>
+
+#include "rgbl_device.cuh"
+#include "rgbl_kernels.h"
+
+namespace rgbl {
+
+constexpr int kStampShift = 22;
+constexpr uint32_t kIdxMask = (1u << kStampShift) - 1u;
+
+__device__ __forceinline__ float project_row(const float* P, float x, float y, float z, float o) {
+    double acc = __dmul_rn((double)P[0], (double)x);
+    acc = __dadd_rn(acc, __dmul_rn((double)P[1], (double)y));
+    acc = __dadd_rn(acc, __dmul_rn((double)P[2], (double)z));
+    acc = __dadd_rn(acc, __dmul_rn((double)P[3], (double)o));
+    return (float)acc;
+}
+
+__global__ void __launch_bounds__(256) depth_project_kernel(const float* __restrict__ pts, int pts_stride,
+                                                            const int* __restrict__ n_pts, DepthDev prm, int W, int H,
+                                                            uint32_t* __restrict__ idx_map, uint32_t stamp) {
+    const int frame = blockIdx.y;
+    const int n = n_pts[frame];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float* X = pts + (size_t)frame * pts_stride;
+    const float x = __ldg(X + i), y = __ldg(X + n + i), z = __ldg(X + 2 * (size_t)n + i), o = __ldg(X + 3 * (size_t)n + i);
+    const float q0 = project_row(prm.P, x, y, z, o);
+    const float q1 = project_row(prm.P + 4, x, y, z, o);
+    const float d = project_row(prm.P + 8, x, y, z, o);
+    const float inv = __fdiv_rn(1.0f, d);
+    const float u = __fmul_rn(q0, inv), v = __fmul_rn(q1, inv);
+    if (u > 0.f && v > 0.f && u < (float)W && v < (float)H && d > prm.min_dist && d < prm.max_dist) {
+        uint32_t* m = idx_map + (size_t)frame * W * H + (size_t)(int)v * W + (int)u;
+        atomicMax(m, (stamp << kStampShift) | (uint32_t)(i + 1));
+    }
+}
+
+__global__ void __launch_bounds__(256) depth_resolve_dilate_kernel(const float* __restrict__ pts, int pts_stride,
+                                                                   const int* __restrict__ n_pts, DepthDev prm, int W,
+                                                                   int H, const uint32_t* __restrict__ idx_map,
+                                                                   uint32_t stamp, float* __restrict__ raw,
+                                                                   float* __restrict__ processed) {
+    constexpr int TW = 32, TH = 8, HALO = 4;
+    __shared__ float t[TH + 2 * HALO][TW + 2 * HALO + 1];
+    __shared__ uint8_t mask[81];
+    const int frame = blockIdx.z, tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int ax = prm.ku / 2, ay = prm.kv / 2;
+    const int n = n_pts[frame];
+    const float* X = pts + (size_t)frame * pts_stride;
+    const uint32_t* im = idx_map + (size_t)frame * W * H;
+    const float M = prm.inv_scale_m, thr = __fsub_rn(M, 1.0f);
+    if (tid < 81) mask[tid] = prm.mask[tid];
+
+    for (int i = tid; i < (TH + 2 * HALO) * (TW + 2 * HALO); i += 256) {
+        const int r = i / (TW + 2 * HALO), c = i - r * (TW + 2 * HALO);
+        const int gy = y0 + r - HALO, gx = x0 + c - HALO;
+        float tv = -FLT_MAX;                      // out-of-image taps are ignored by cv::dilate
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+            const uint32_t e = __ldg(im + (size_t)gy * W + gx);
+            float d = 0.f;
+            if ((e >> kStampShift) == stamp) {
+                const int p = (int)(e & kIdxMask) - 1;
+                d = project_row(prm.P + 8, __ldg(X + p), __ldg(X + n + p), __ldg(X + 2 * (size_t)n + p),
+                                __ldg(X + 3 * (size_t)n + p));
+            }
+            const bool interior = (r >= HALO && r < HALO + TH && c >= HALO && c < HALO + TW);
+            if (interior && raw) raw[(size_t)frame * W * H + (size_t)gy * W + gx] = d;
+            const float inv = __fsub_rn(M, d);
+            tv = (inv > thr) ? 0.f : inv;         // THRESH_TOZERO_INV at M-1
+        }
+        t[r][c] = tv;
+    }
+    __syncthreads();
+    const int lx = tid & 31, ly = tid >> 5;
+    const int gx = x0 + lx, gy = y0 + ly;
+    if (gx < W && gy < H) {
+        float best = -FLT_MAX;
+        for (int j = 0; j < prm.kv; ++j)
+            for (int i = 0; i < prm.ku; ++i)
+                if (mask[j * prm.ku + i]) best = fmaxf(best, t[ly + HALO + j - ay][lx + HALO + i - ax]);
+        const float o = __fsub_rn(M, best);
+        processed[(size_t)frame * W * H + (size_t)gy * W + gx] = (o > thr) ? 0.f : o;
+    }
+}
+
+__global__ void __launch_bounds__(256) depth_gather_kernel(const float* __restrict__ processed, int W, int H,
+                                                           const rgbl_keypoint* __restrict__ kps,
+                                                           const rgbl_keypoint* __restrict__ kps_un,
+                                                           const int* __restrict__ n_kp, int cap, float bf,
+                                                           float* __restrict__ depth, float* __restrict__ uright) {
+    const int frame = blockIdx.y;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= n_kp[frame]) return;
+    const size_t o = (size_t)frame * cap + k;
+    const float u = kps[o].x, v = kps[o].y;
+    const float d = __ldg(processed + (size_t)frame * W * H + (size_t)(int)v * W + (int)u);
+    float dd = -1.f, ur = -1.f;
+    if (d > 0.f) {
+        dd = d;
+        ur = __fsub_rn(kps_un[o].x, __fdiv_rn(bf, d));
+    }
+    depth[o] = dd;
+    uright[o] = ur;
+}
+
+void launch_depth_project(cudaStream_t st, const float* pts, int pts_stride, const int* n_pts, int max_n_pts,
+                          const DepthDev& prm, int W, int H, uint32_t* idx_map, uint32_t stamp, int n_frames) {
+    if (max_n_pts <= 0) return;
+    depth_project_kernel<<<dim3((max_n_pts + 255) / 256, n_frames), 256, 0, st>>>(pts, pts_stride, n_pts, prm, W, H,
+                                                                                 idx_map, stamp);
+}
+
+void launch_depth_resolve_dilate(cudaStream_t st, const float* pts, int pts_stride, const int* n_pts,
+                                 const DepthDev& prm, int W, int H, const uint32_t* idx_map, uint32_t stamp,
+                                 float* raw, float* processed, int n_frames) {
+    depth_resolve_dilate_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, st>>>(
+        pts, pts_stride, n_pts, prm, W, H, idx_map, stamp, raw, processed);
+}
+
+void launch_depth_gather(cudaStream_t st, const float* processed, int W, int H, const rgbl_keypoint* kps,
+                         const rgbl_keypoint* kps_un, const int* n_kp, int cap, int max_n, float bf, float* depth,
+                         float* uright, int n_frames) {
+    if (max_n <= 0) return;
+    depth_gather_kernel<<<dim3((max_n + 255) / 256, n_frames), 256, 0, st>>>(processed, W, H, kps, kps_un, n_kp, cap, bf,
+                                                                            depth, uright);
+}
+
+}  // namespace rgbl

@@ -1,0 +1,408 @@
+// ORB extractor kernels for sm_100a: pyramid, per-cell FAST-9/16 + cell-local NMS, candidate
+// compaction, 7x7 Gaussian pre-filter, and the fused orientation + rBRIEF describe kernel.
+// Reference semantics: src/ORBextractor.cc (cited per kernel) with the OpenCV primitives restated
+// in integer/fixed-point form.  Every frame of a batch is processed by the
+// same launch (blockIdx.z / blockIdx.y = frame slot).
+#include "rgbl_device.cuh"
+#include "rgbl_kernels.h"
+
+namespace rgbl {
+
+// ------------------------------------------------------------------------------------------------
+// Pyramid: level l = cv::resize(level l-1, INTER_LINEAR)  (src/ORBextractor.cc:1183).
+// One thread produces 4 horizontally adjacent output bytes (one 32-bit store).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_level_kernel(uint8_t* __restrict__ pyr, size_t frame_stride,
+                                                           LevelGeom src, LevelGeom dst,
+                                                           const LinCoef* __restrict__ tabx,
+                                                           const LinCoef* __restrict__ taby) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x4 >= dst.w || y >= dst.h) return;
+    const uint8_t* s = pyr + (size_t)blockIdx.z * frame_stride + src.off;
+    uint8_t* d = pyr + (size_t)blockIdx.z * frame_stride + dst.off;
+    const LinCoef cy = taby[y];
+    const uint8_t* r0 = s + (size_t)cy.s * src.pitch;
+    const uint8_t* r1 = s + (size_t)min(cy.s + 1, src.h - 1) * src.pitch;
+    const int b0 = cy.c0, b1 = cy.c1;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = x4 + i;
+        if (x < dst.w) {
+            const LinCoef cx = tabx[x];
+            const int s0 = cx.s, s1 = min(s0 + 1, src.w - 1);
+            const int h0 = (int)__ldg(r0 + s0) * cx.c0 + (int)__ldg(r0 + s1) * cx.c1;
+            const int h1 = (int)__ldg(r1 + s0) * cx.c0 + (int)__ldg(r1 + s1) * cx.c1;
+            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            out |= (uint32_t)(v & 0xff) << (8 * i);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(d + (size_t)y * dst.pitch + x4) = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FAST: one CTA per (cell, frame).  Equivalent of the per-cell cv::FAST(th=iniTh, nms) with the
+// cv::FAST(th=minTh, nms) fallback when the first call returns nothing (src/ORBextractor.cc:805-868).
+//   score(p) = K-1 with K the arc strength (corner at threshold t  <=>  K > t  <=>  score >= t);
+//   NMS survivors at minTh = {s >= minTh, s > all 8 neighbours (non-corners / outside the window = 0)};
+//   survivors at iniTh = survivors at minTh with s >= iniTh (a weaker neighbour never suppresses).
+// Survivors are written in row-major order (the order cv::FAST returns) into the cell's slot array.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fast_score_at(const uint8_t* p, int th) {
+    constexpr int P = kFastTilePitch;
+    const int v = p[0];
+    int r[16];
+    r[0] = p[3 * P]; r[4] = p[3]; r[8] = p[-3 * P]; r[12] = p[-3];
+    const int hi_t = v + th, lo_t = v - th;
+    const int ndark = (r[0] < lo_t) + (r[4] < lo_t) + (r[8] < lo_t) + (r[12] < lo_t);
+    const int nbright = (r[0] > hi_t) + (r[4] > hi_t) + (r[8] > hi_t) + (r[12] > hi_t);
+    if (ndark < 2 && nbright < 2) return 0;      // a 9-arc always covers >= 2 of the 4 compass points
+    r[1] = p[3 * P + 1];  r[2] = p[2 * P + 2];   r[3] = p[P + 3];
+    r[5] = p[-P + 3];     r[6] = p[-2 * P + 2];  r[7] = p[-3 * P + 1];
+    r[9] = p[-3 * P - 1]; r[10] = p[-2 * P - 2]; r[11] = p[-P - 3];
+    r[13] = p[P - 3];     r[14] = p[2 * P - 2];  r[15] = p[3 * P - 1];
+    const int K = fast_arc_strength16(v, r);
+    return (K > th) ? (K - 1) : 0;
+}
+
+__global__ void __launch_bounds__(256) fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
+                                                         const LevelGeom* __restrict__ levels,
+                                                         const CellInfo* __restrict__ cells, int n_cells,
+                                                         int ini_th, int min_th,
+                                                         uint32_t* __restrict__ slots, int* __restrict__ counts,
+                                                         int* __restrict__ overflow) {
+    constexpr int P = kFastTilePitch;
+    __shared__ __align__(16) uint8_t tile[P * P];
+    __shared__ __align__(16) uint8_t sc[P * P];
+    __shared__ int warp_sums[8];
+
+    const int cell = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
+    const CellInfo ci = cells[cell];
+    const LevelGeom lg = levels[ci.level];
+    const int cw = ci.cw, ch = ci.ch;
+    const uint8_t* src = pyr + (size_t)frame * frame_stride + lg.off + (size_t)ci.y0 * lg.pitch + ci.x0;
+
+    for (int i = tid; i < cw * ch; i += 256) {
+        const int y = i / cw, x = i - y * cw;
+        tile[y * P + x] = __ldg(src + (size_t)y * lg.pitch + x);
+        sc[y * P + x] = 0;
+    }
+    __syncthreads();
+
+    const int tw = cw - 6, th = ch - 6;          // tested region [3, cw-3) x [3, ch-3)
+    const int n_t = (tw > 0 && th > 0) ? tw * th : 0;
+    for (int i = tid; i < n_t; i += 256) {
+        const int y = i / tw + 3, x = i - (y - 3) * tw + 3;
+        const int s = fast_score_at(&tile[y * P + x], min_th);
+        sc[y * P + x] = (uint8_t)s;
+    }
+    __syncthreads();
+
+    // contiguous row-major chunk per thread -> ordered emission
+    const int per = (n_t + 255) / 256;           // <= 21 for windows < 78 px
+    const int beg = min(tid * per, n_t), end = min(beg + per, n_t);
+    uint32_t m_min = 0, m_ini = 0;
+    for (int i = beg; i < end; ++i) {
+        const int y = i / tw + 3, x = i - (y - 3) * tw + 3;
+        const uint8_t* c = &sc[y * P + x];
+        const int s = c[0];
+        if (s == 0) continue;
+        const bool keep = s > c[-1] && s > c[1] && s > c[-P - 1] && s > c[-P] && s > c[-P + 1] &&
+                          s > c[P - 1] && s > c[P] && s > c[P + 1];
+        if (keep) {
+            m_min |= 1u << (i - beg);
+            if (s >= ini_th) m_ini |= 1u << (i - beg);
+        }
+    }
+    const int any_ini = __syncthreads_or(m_ini != 0);
+    const uint32_t m = any_ini ? m_ini : m_min;
+    const int cnt = __popc(m);
+
+    // block-wide exclusive scan of cnt
+    const int lane = tid & 31, warp = tid >> 5;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int ws = warp_sums[w];
+        if (w < warp) base += ws;
+        total += ws;
+    }
+    int pos = base + incl - cnt;
+    uint32_t* out = slots + ((size_t)frame * n_cells + cell) * kCellCap;
+    uint32_t mm = m;
+    while (mm) {
+        const int b = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const int i = beg + b;
+        const int y = i / tw + 3, x = i - (y - 3) * tw + 3;
+        if (pos < kCellCap) out[pos] = pack_cand_dev(x + ci.off_x, y + ci.off_y, sc[y * P + x]);
+        ++pos;
+    }
+    if (tid == 0) {
+        counts[(size_t)frame * n_cells + cell] = min(total, kCellCap);
+        if (total > kCellCap) atomicExch(overflow, 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Candidate compaction.  Pass A (one CTA per frame): exclusive scan of the cell counts in reference
+// cell order -> per-cell offsets, per-level counts/offsets, frame total.  Pass B (grid of CTAs):
+// every CTA recomputes the tiny prefix over frame totals and copies its cells' slot arrays into one
+// dense buffer, so the host fetches exactly sum(total) candidates with a single copy.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cand_scan_kernel(const int* __restrict__ counts, int n_cells,
+                                                        const LevelGeom* __restrict__ levels, int n_levels,
+                                                        int* __restrict__ cell_off, int* __restrict__ level_cnt,
+                                                        int* __restrict__ frame_total) {
+    __shared__ int warp_sums[8];
+    __shared__ int carry;
+    const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* c = counts + (size_t)frame * n_cells;
+    int* o = cell_off + (size_t)frame * n_cells;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int b = 0; b < n_cells; b += 256) {
+        const int i = b + tid;
+        const int v = (i < n_cells) ? c[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, k);
+            if (lane >= k) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        int base = carry;
+        for (int w = 0; w < warp; ++w) base += warp_sums[w];
+        if (i < n_cells) o[i] = base + incl - v;
+        __syncthreads();
+        if (tid == 255) carry = base + incl;
+        __syncthreads();
+    }
+    if (tid < n_levels) {
+        const LevelGeom lg = levels[tid];
+        int s = 0;
+        for (int k = 0; k < lg.n_cells; ++k) s += c[lg.cell_base + k];
+        level_cnt[frame * RGBL_MAX_LEVELS + tid] = s;
+    }
+    if (tid == 0) frame_total[frame] = carry;
+}
+
+__global__ void __launch_bounds__(256) cand_gather_kernel(const uint32_t* __restrict__ slots,
+                                                          const int* __restrict__ counts,
+                                                          const int* __restrict__ cell_off,
+                                                          const int* __restrict__ frame_total, int n_cells,
+                                                          uint32_t* __restrict__ dense, int dense_cap,
+                                                          int* __restrict__ overflow) {
+    const int frame = blockIdx.y;
+    int fbase = 0;
+    for (int f = 0; f < frame; ++f) fbase += frame_total[f];
+    const int warp_global = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int n_warps = gridDim.x * 8;
+    for (int cell = warp_global; cell < n_cells; cell += n_warps) {
+        const int n = counts[(size_t)frame * n_cells + cell];
+        const int off = fbase + cell_off[(size_t)frame * n_cells + cell];
+        const uint32_t* s = slots + ((size_t)frame * n_cells + cell) * kCellCap;
+        for (int k = lane; k < n; k += 32) {
+            if (off + k < dense_cap) dense[off + k] = s[k];
+            else atomicExch(overflow, 2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) on each un-padded level (src/ORBextractor.cc:
+// 1132-1133): 8.8 fixed-point kernel {18,34,48,56,48,34,18}, exact separable sums, one
+// final rounding.  CTA tile: 64 x 32 outputs; each thread writes 4 adjacent bytes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int n) {
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * (n - 1) - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(256) blur_level_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
+                                                         size_t frame_stride, LevelGeom lg) {
+    constexpr int TW = 64, TH = 32, IW = TW + 6, IH = TH + 6;
+    __shared__ uint8_t in[IH][IW + 2];
+    __shared__ uint16_t hb[IH][TW];
+    const uint8_t* s = pyr + (size_t)blockIdx.z * frame_stride + lg.off;
+    uint8_t* d = blur + (size_t)blockIdx.z * frame_stride + lg.off;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, tid = threadIdx.x;
+    for (int i = tid; i < IW * IH; i += 256) {
+        const int r = i / IW, c = i - r * IW;
+        const int gy = reflect101(y0 + r - 3, lg.h), gx = reflect101(x0 + c - 3, lg.w);
+        in[r][c] = __ldg(s + (size_t)gy * lg.pitch + gx);
+    }
+    __syncthreads();
+    for (int i = tid; i < TW * IH; i += 256) {
+        const int r = i / TW, c = i - r * TW;
+        const uint8_t* p = &in[r][c];
+        const int acc = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
+        hb[r][c] = (uint16_t)acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < (TW / 4) * TH; i += 256) {
+        const int r = i / (TW / 4), c4 = (i - r * (TW / 4)) * 4;
+        const int gy = y0 + r, gx = x0 + c4;
+        if (gy >= lg.h || gx >= lg.w) continue;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c4 + k;
+            const uint32_t acc = 18u * (hb[r][c] + hb[r + 6][c]) + 34u * (hb[r + 1][c] + hb[r + 5][c]) +
+                                 48u * (hb[r + 2][c] + hb[r + 4][c]) + 56u * hb[r + 3][c];
+            out |= ((acc + 32768u) >> 16) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(d + (size_t)gy * lg.pitch + gx) = out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Describe: one warp per selected keypoint.  IC_Angle (src/ORBextractor.cc:76-103) on the un-blurred
+// level, then computeOrbDescriptor (:107-146) on the blurred level, then the cv::KeyPoint record with
+// the level->image coordinate scaling of operator() (:1143-1151).
+// ------------------------------------------------------------------------------------------------
+__device__ const int8_t g_pattern[1024] = {
+#include "orb_pattern_31.inc"
+};
+
+struct UmaxTable { int v[16]; };
+
+__global__ void __launch_bounds__(256) describe_kernel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
+                                                       size_t frame_stride, const LevelGeom* __restrict__ levels,
+                                                       const SelKp* __restrict__ sel, const int* __restrict__ n_sel,
+                                                       int cap, UmaxTable umax, rgbl_keypoint* __restrict__ kps,
+                                                       uint8_t* __restrict__ desc) {
+    const int frame = blockIdx.y;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= n_sel[frame]) return;
+    const SelKp kp = sel[(size_t)frame * cap + k];
+    const LevelGeom lg = levels[kp.level];
+    const uint8_t* img = pyr + (size_t)frame * frame_stride + lg.off;
+    const uint8_t* c = img + (size_t)kp.y * lg.pitch + kp.x;
+
+    // intensity centroid: lane <-> row v = lane-15 of the radius-15 disc (lane 31 idle)
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int v = lane - kHalfPatch;
+        const int dmax = umax.v[v < 0 ? -v : v];
+        const uint8_t* row = c + v * lg.pitch;
+        int rs = 0;
+        for (int u = -dmax; u <= dmax; ++u) {
+            const int val = __ldg(row + u);
+            m10 += u * val;
+            rs += val;
+        }
+        m01 = v * rs;
+    }
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // steered BRIEF: lane i computes descriptor byte i (8 comparisons, 16 samples)
+    const float factor_pi = (float)(3.14159265358979323846 / 180.0);
+    float a, b;
+    glibc_sincosf(__fmul_rn(angle, factor_pi), &b, &a);       // a = cos, b = sin
+    const uint8_t* bc = blur + (size_t)frame * frame_stride + lg.off + (size_t)kp.y * lg.pitch + kp.x;
+    const int8_t* pat = g_pattern + lane * 32;
+    int val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int t[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float px = (float)pat[4 * j + 2 * e], py = (float)pat[4 * j + 2 * e + 1];
+            const int rr = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            const int cc = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            t[e] = __ldg(bc + rr * lg.pitch + cc);
+        }
+        val |= (t[0] < t[1]) << j;
+    }
+    desc[((size_t)frame * cap + k) * 32 + lane] = (uint8_t)val;
+
+    if (lane == 0) {
+        rgbl_keypoint o;
+        const float fx = (float)kp.x, fy = (float)kp.y;
+        o.x = (kp.level != 0) ? __fmul_rn(fx, lg.scale) : fx;
+        o.y = (kp.level != 0) ? __fmul_rn(fy, lg.scale) : fy;
+        o.size = (float)lg.scaled_patch;
+        o.angle = angle;
+        o.response = (float)kp.score;
+        o.octave = kp.level;
+        o.class_id = -1;
+        kps[(size_t)frame * cap + k] = o;
+    }
+}
+
+// mvImagePyramid[level] with its 19 px BORDER_REFLECT_101 frame (src/ORBextractor.cc:1185-1191),
+// synthesised on demand: the hot path itself never reads the border.
+__global__ void padded_level_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride, int frame, LevelGeom lg,
+                                    uint8_t* __restrict__ dst, int dst_pitch) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int W = lg.w + 2 * kEdgeThreshold, H = lg.h + 2 * kEdgeThreshold;
+    if (x >= W || y >= H) return;
+    const uint8_t* s = pyr + (size_t)frame * frame_stride + lg.off;
+    dst[(size_t)y * dst_pitch + x] = s[(size_t)reflect101(y - kEdgeThreshold, lg.h) * lg.pitch + reflect101(x - kEdgeThreshold, lg.w)];
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+void launch_pyramid(cudaStream_t st, uint8_t* pyr, size_t frame_stride, const LevelGeom* h_levels, int n_levels,
+                    const LinCoef* d_coefs, int n_frames) {
+    for (int l = 1; l < n_levels; ++l) {
+        const LevelGeom& src = h_levels[l - 1];
+        const LevelGeom& dst = h_levels[l];
+        dim3 blk(32, 8), grd(((dst.w + 3) / 4 + 31) / 32, (dst.h + 7) / 8, n_frames);
+        resize_level_kernel<<<grd, blk, 0, st>>>(pyr, frame_stride, src, dst, d_coefs + dst.tabx_off, d_coefs + dst.taby_off);
+    }
+}
+
+void launch_fast(cudaStream_t st, const uint8_t* pyr, size_t frame_stride, const LevelGeom* d_levels, int n_levels,
+                 const CellInfo* d_cells, int n_cells, int ini_th, int min_th, uint32_t* slots, int* counts,
+                 int* cell_off, int* level_cnt, int* frame_total, uint32_t* dense, int dense_cap, int* overflow,
+                 int n_frames) {
+    fast_cells_kernel<<<dim3(n_cells, n_frames), 256, 0, st>>>(pyr, frame_stride, d_levels, d_cells, n_cells, ini_th,
+                                                             min_th, slots, counts, overflow);
+    cand_scan_kernel<<<n_frames, 256, 0, st>>>(counts, n_cells, d_levels, n_levels, cell_off, level_cnt, frame_total);
+    const int gx = (n_cells + 63) / 64;
+    cand_gather_kernel<<<dim3(gx, n_frames), 256, 0, st>>>(slots, counts, cell_off, frame_total, n_cells, dense,
+                                                         dense_cap, overflow);
+}
+
+void launch_blur(cudaStream_t st, const uint8_t* pyr, uint8_t* blur, size_t frame_stride, const LevelGeom* h_levels,
+                 int n_levels, int n_frames) {
+    for (int l = 0; l < n_levels; ++l) {
+        const LevelGeom& lg = h_levels[l];
+        dim3 grd((lg.w + 63) / 64, (lg.h + 31) / 32, n_frames);
+        blur_level_kernel<<<grd, 256, 0, st>>>(pyr, blur, frame_stride, lg);
+    }
+}
+
+void launch_describe(cudaStream_t st, const uint8_t* pyr, const uint8_t* blur, size_t frame_stride,
+                     const LevelGeom* d_levels, const SelKp* sel, const int* n_sel, int cap, int max_n,
+                     const int umax[16], rgbl_keypoint* kps, uint8_t* desc, int n_frames) {
+    if (max_n <= 0) return;
+    UmaxTable t;
+    for (int i = 0; i < 16; ++i) t.v[i] = umax[i];
+    describe_kernel<<<dim3((max_n + 7) / 8, n_frames), 256, 0, st>>>(pyr, blur, frame_stride, d_levels, sel, n_sel, cap,
+                                                                   t, kps, desc);
+}
+
+void launch_padded_level(cudaStream_t st, const uint8_t* pyr, size_t frame_stride, int frame, const LevelGeom& lg,
+                         uint8_t* dst, int dst_pitch) {
+    const int W = lg.w + 2 * kEdgeThreshold, H = lg.h + 2 * kEdgeThreshold;
+    padded_level_kernel<<<dim3((W + 31) / 32, (H + 7) / 8), dim3(32, 8), 0, st>>>(pyr, frame_stride, frame, lg, dst, dst_pitch);
+}
+
+}  // namespace rgbl

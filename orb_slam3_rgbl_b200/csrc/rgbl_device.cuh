@@ -1,0 +1,141 @@
+// Device-side arithmetic shared by the kernels.  Every float/double operation that must reproduce
+// the reference's CPU result bit for bit uses explicit round-to-nearest intrinsics so that nvcc can
+// never contract it into an FMA (the library is additionally built with -fmad=false).
+#ifndef RGBL_DEVICE_CUH
+#define RGBL_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rgbl_internal.h"
+
+namespace rgbl {
+
+#if defined(__CUDACC__)
+#define RGBL_HD __host__ __device__ __forceinline__
+#else
+#define RGBL_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define RGBL_FMUL(a, b) __fmul_rn((a), (b))
+#define RGBL_FADD(a, b) __fadd_rn((a), (b))
+#define RGBL_FSUB(a, b) __fsub_rn((a), (b))
+#define RGBL_FDIV(a, b) __fdiv_rn((a), (b))
+#define RGBL_DMUL(a, b) __dmul_rn((a), (b))
+#define RGBL_DADD(a, b) __dadd_rn((a), (b))
+#define RGBL_DSUB(a, b) __dsub_rn((a), (b))
+#else   // host build of the same header (tests/host_math_harness.cpp); compiled with -ffp-contract=off
+#define RGBL_FMUL(a, b) ((float)(a) * (float)(b))
+#define RGBL_FADD(a, b) ((float)(a) + (float)(b))
+#define RGBL_FSUB(a, b) ((float)(a) - (float)(b))
+#define RGBL_FDIV(a, b) ((float)(a) / (float)(b))
+#define RGBL_DMUL(a, b) ((double)(a) * (double)(b))
+#define RGBL_DADD(a, b) ((double)(a) + (double)(b))
+#define RGBL_DSUB(a, b) ((double)(a) - (double)(b))
+#endif
+
+// cv::fastAtan2 scalar path, degrees in [0, 360).
+RGBL_HD float fast_atan2_deg(float y, float x) {
+    const float k = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = RGBL_FMUL(0.9997878412794807f, k), p3 = RGBL_FMUL(-0.3258083974640975f, k),
+                p5 = RGBL_FMUL(0.1555786518463281f, k), p7 = RGBL_FMUL(-0.04432655554792128f, k);
+    const float eps = 2.2204460492503131e-16f;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = RGBL_FDIV(ay, RGBL_FADD(ax, eps));
+        c2 = RGBL_FMUL(c, c);
+        a = RGBL_FMUL(RGBL_FADD(RGBL_FMUL(RGBL_FADD(RGBL_FMUL(RGBL_FADD(RGBL_FMUL(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = RGBL_FDIV(ax, RGBL_FADD(ay, eps));
+        c2 = RGBL_FMUL(c, c);
+        a = RGBL_FSUB(90.f, RGBL_FMUL(RGBL_FADD(RGBL_FMUL(RGBL_FADD(RGBL_FMUL(RGBL_FADD(RGBL_FMUL(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = RGBL_FSUB(180.f, a);
+    if (y < 0) a = RGBL_FSUB(360.f, a);
+    return a;
+}
+
+// glibc >= 2.28 sinf/cosf (the "sincosf" double-precision polynomial algorithm), restated so that the
+// device reproduces the libm results the reference's computeOrbDescriptor sees (src/ORBextractor.cc:112).
+// Verified bit-identical to glibc 2.39 on every float in [0, 6.4] (tests/test_host_math.py samples it).
+// Valid for |y| < 120; descriptor angles are in [0, 2*pi].
+RGBL_HD uint32_t f32_top12(float x) {
+#if defined(__CUDA_ARCH__)
+    return (__float_as_uint(x) >> 20) & 0x7ffu;
+#else
+    union { float f; uint32_t u; } c; c.f = x; return (c.u >> 20) & 0x7ffu;
+#endif
+}
+
+RGBL_HD float sincosf_poly(double x, double x2, bool neg_cos, int n) {
+    // neg_cos selects the second coefficient table (cosine coefficients negated).
+    if ((n & 1) == 0) {
+        const double s1c = -0x1.555545995a603p-3, s2c = 0x1.1107605230bc4p-7, s3c = -0x1.994eb3774cf24p-13;
+        const double x3 = RGBL_DMUL(x, x2);
+        const double s1 = RGBL_DADD(s2c, RGBL_DMUL(x2, s3c));
+        const double x7 = RGBL_DMUL(x3, x2);
+        const double s = RGBL_DADD(x, RGBL_DMUL(x3, s1c));
+        return (float)RGBL_DADD(s, RGBL_DMUL(x7, s1));
+    } else {
+        const double sg = neg_cos ? -1.0 : 1.0;
+        const double c0 = sg * 0x1p0, c1c = sg * -0x1.ffffffd0c621cp-2, c2c = sg * 0x1.55553e1068f19p-5,
+                     c3c = sg * -0x1.6c087e89a359dp-10, c4c = sg * 0x1.99343027bf8c3p-16;
+        const double x4 = RGBL_DMUL(x2, x2);
+        const double c2 = RGBL_DADD(c3c, RGBL_DMUL(x2, c4c));
+        const double c1 = RGBL_DADD(c0, RGBL_DMUL(x2, c1c));
+        const double x6 = RGBL_DMUL(x4, x2);
+        const double c = RGBL_DADD(c1, RGBL_DMUL(x4, c2c));
+        return (float)RGBL_DADD(c, RGBL_DMUL(x6, c2));
+    }
+}
+
+RGBL_HD void glibc_sincosf(float y, float* sin_out, float* cos_out) {
+    double x = (double)y;
+    if (f32_top12(y) < f32_top12(0x1.921FB6p-1f)) {
+        const double s = RGBL_DMUL(x, x);
+        if (f32_top12(y) < f32_top12(0x1p-12f)) { *sin_out = y; *cos_out = 1.0f; return; }
+        *sin_out = sincosf_poly(x, s, false, 0);
+        *cos_out = sincosf_poly(x, s, false, 1);
+        return;
+    }
+    const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
+    const double r = RGBL_DMUL(x, hpi_inv);
+    const int n = ((int32_t)r + 0x800000) >> 24;
+    x = RGBL_DSUB(x, RGBL_DMUL((double)n, hpi));
+    const int q = n & 3;
+    const double sgn = (q == 1 || q == 2) ? -1.0 : 1.0;     // sign[] = {1,-1,-1,1}
+    const bool second = (n & 2) != 0;
+    const double xs = RGBL_DMUL(x, sgn), x2 = RGBL_DMUL(x, x);
+    *sin_out = sincosf_poly(xs, x2, second, n);
+    *cos_out = sincosf_poly(xs, x2, second, n ^ 1);
+}
+
+// FAST-9/16 arc strength K: the largest t such that the pixel is a corner for every threshold < t,
+// i.e. max over the 16 contiguous 9-arcs of min(v - r) (bright) and of min(r - v) (dark); cv score = K-1.
+// r[k] = ring intensities in OpenCV's ring order, v = centre.
+// Formulated on the raw intensities (K = max(v - min_arc max r, max_arc min r - v)) so that no negated
+// value ever feeds a 3-input min/max: ptxas 12.9 for sm_100a was observed to drop the negation when it
+// fuses max(max(a, -b), c) into VIMNMX3 (first GPU run of this kernel returned K = max(d)).
+RGBL_HD int fast_arc_strength16(int v, const int r[16]) {
+    int m2[16], M2[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) { m2[s] = min(r[s], r[(s + 1) & 15]); M2[s] = max(r[s], r[(s + 1) & 15]); }
+    int m4[16], M4[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) { m4[s] = min(m2[s], m2[(s + 2) & 15]); M4[s] = max(M2[s], M2[(s + 2) & 15]); }
+    int lo = 255, hi = 0;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int m8 = min(m4[s], m4[(s + 4) & 15]), M8 = max(M4[s], M4[(s + 4) & 15]);
+        const int m9 = min(m8, r[(s + 8) & 15]), M9 = max(M8, r[(s + 8) & 15]);
+        lo = min(lo, M9);      // darkest "all-below" bound: arc whose maximum is smallest
+        hi = max(hi, m9);      // brightest "all-above" bound: arc whose minimum is largest
+    }
+    const int kb = v - lo, kd = hi - v;
+    return kb > kd ? kb : kd;
+}
+
+}  // namespace rgbl
+#endif

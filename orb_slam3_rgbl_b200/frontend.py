@@ -1,0 +1,187 @@
+"""Host-side mirror of the reference's hot-path classes on top of the C ABI.
+
+Names and argument meaning follow the reference so the parity tests read like reference usage:
+  ORBextractor  <- include/ORBextractor.h:45-108  (operator() -> __call__)
+  DepthModule   <- include/DepthModule.h:30-164   (CalculateDepthFromPcd, mvDepth, mvuRight, ...)
+All compute happens in librgbl_b200.so on the GPU; this file only marshals numpy buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import KP_DTYPE, DepthParams, OrbParams, check, lib, ptr
+
+
+class Context:
+    """One rgbl_ctx: fixed image size, batch capacity and ORB parameters, bound to one CUDA device."""
+
+    def __init__(self, width: int, height: int, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=12, min_th=7,
+                 max_batch=1, max_points=0, max_candidates=0, device=0):
+        self.orb = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        self.cfg = L.Config(device, width, height, max_batch, max_points, max_candidates, self.orb)
+        self.handle = C.c_void_p()
+        rc = lib().rgbl_create(C.byref(self.cfg), C.byref(self.handle))
+        if rc != 0:
+            msg = lib().rgbl_last_error(None)
+            raise L.RgblError(rc, msg.decode() if msg else "rgbl_create failed")
+        self.width, self.height, self.nlevels, self.nfeatures = width, height, nlevels, nfeatures
+        self.max_batch = max_batch
+        self.cap = nfeatures + 3 * nlevels
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().rgbl_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def orb_tables(nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=12, min_th=7):
+    p = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th)
+    sc, inv, s2, is2 = (np.empty(nlevels, np.float32) for _ in range(4))
+    q = np.empty(nlevels, np.int32); um = np.empty(16, np.int32)
+    check(lib().rgbl_orb_tables(C.byref(p), ptr(sc), ptr(inv), ptr(s2), ptr(is2), ptr(q), ptr(um)))
+    return dict(scale=sc, inv_scale=inv, sigma2=s2, inv_sigma2=is2, features_per_level=q, umax=um)
+
+
+class ORBextractor:
+    """ORB_SLAM3::ORBextractor drop-in (src/ORBextractor.cc)."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, width, height, max_batch=1, device=0,
+                 ctx: Context | None = None):
+        self.ctx = ctx or Context(width, height, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_batch, 0, 0, device)
+        t = orb_tables(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+        self.mvScaleFactor, self.mvInvScaleFactor = t["scale"], t["inv_scale"]
+        self.mvLevelSigma2, self.mvInvLevelSigma2 = t["sigma2"], t["inv_sigma2"]
+        self.mnFeaturesPerLevel, self.umax = t["features_per_level"], t["umax"]
+        self.nlevels, self.nfeatures, self.scaleFactor = nlevels, nfeatures, scaleFactor
+
+    # getters of include/ORBextractor.h:61-81
+    def GetLevels(self): return self.nlevels
+    def GetScaleFactor(self): return self.scaleFactor
+    def GetScaleFactors(self): return self.mvScaleFactor
+    def GetInverseScaleFactors(self): return self.mvInvScaleFactor
+    def GetScaleSigmaSquares(self): return self.mvLevelSigma2
+    def GetInverseScaleSigmaSquares(self): return self.mvInvLevelSigma2
+
+    def __call__(self, image: np.ndarray, mask=None, vLappingArea=(0, 0)):
+        """-> (monoIndex, keypoints[KP_DTYPE], descriptors[N,32]); monoIndex == -1 for an empty image."""
+        if image is None or image.size == 0:
+            return -1, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 expected (src/ORBextractor.cc:1094)"
+        img = image if image.strides[1] == 1 else np.ascontiguousarray(image)
+        cap = self.ctx.cap
+        kps = np.empty(cap, KP_DTYPE); desc = np.empty((cap, 32), np.uint8)
+        n = C.c_int(0); mono = C.c_int(0)
+        check(lib().rgbl_orb_extract(self.ctx.handle, ptr(img), img.shape[1], img.shape[0], img.strides[0],
+                                     int(vLappingArea[0]), int(vLappingArea[1]), ptr(kps), ptr(desc), cap,
+                                     C.byref(n), C.byref(mono)), self.ctx.handle)
+        return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images):
+        """Batched operator(): list of equally sized CV_8UC1 images -> list of (kps, desc)."""
+        imgs = [np.ascontiguousarray(i, np.uint8) for i in images]
+        nF = len(imgs); cap = self.ctx.cap
+        arr = (C.c_void_p * nF)(*[i.ctypes.data for i in imgs])
+        kps = np.empty((nF, cap), KP_DTYPE); desc = np.empty((nF, cap, 32), np.uint8)
+        n = np.zeros(nF, np.int32); mono = np.zeros(nF, np.int32)
+        check(lib().rgbl_orb_extract_batch(self.ctx.handle, nF, arr, imgs[0].shape[1], imgs[0].shape[0], imgs[0].strides[0],
+                                           0, 0, ptr(kps), ptr(desc), cap, ptr(n), ptr(mono)), self.ctx.handle)
+        return [(kps[f, :n[f]].copy(), desc[f, :n[f]].copy()) for f in range(nF)]
+
+    # mvImagePyramid[level] (include/ORBextractor.h:83): padded plane and its ROI
+    def image_pyramid_padded(self, level: int, frame: int = 0) -> np.ndarray:
+        w, h = C.c_int(), C.c_int()
+        buf = np.empty((self.ctx.height + 38, self.ctx.width + 38), np.uint8)
+        check(lib().rgbl_orb_get_pyramid(self.ctx.handle, frame, level, ptr(buf), buf.strides[0], C.byref(w), C.byref(h)), self.ctx.handle)
+        return buf[:h.value + 38, :w.value + 38].copy()
+
+    def level_image(self, level: int, frame: int = 0) -> np.ndarray:
+        w, h = C.c_int(), C.c_int()
+        buf = np.empty((self.ctx.height, self.ctx.width), np.uint8)
+        check(lib().rgbl_orb_get_level(self.ctx.handle, frame, level, ptr(buf), buf.strides[0], C.byref(w), C.byref(h)), self.ctx.handle)
+        return buf[:h.value, :w.value].copy()
+
+    def blurred_level(self, level: int, frame: int = 0) -> np.ndarray:
+        ref = self.level_image(level, frame)
+        buf = np.empty_like(ref)
+        check(lib().rgbl_orb_get_blurred_level(self.ctx.handle, frame, level, ptr(buf), buf.strides[0]), self.ctx.handle)
+        return buf
+
+    def level_candidates(self, level: int, frame: int = 0) -> np.ndarray:
+        cap = 1 << 18
+        out = np.empty((cap, 3), np.int32); n = C.c_int(0)
+        check(lib().rgbl_orb_get_candidates(self.ctx.handle, frame, level, ptr(out), cap, C.byref(n)), self.ctx.handle)
+        return out[:n.value].copy()
+
+
+def structuring_element(kind: str, ku: int, kv: int | None = None) -> np.ndarray:
+    kv = ku if kv is None else kv
+    m = np.zeros((kv, ku), np.uint8)
+    check(lib().rgbl_depth_structuring_element(kind.encode(), ku, kv, ptr(m)))
+    return m
+
+
+def make_depth_params(method=L.DEPTH_INVERSE_DILATION, min_dist=5.0, max_dist=200.0, bf=100.0, kernel_type="Diamond",
+                      ku=5, kv=5, scale=1.0, avg_kernel=5, nn_radius=7.0) -> DepthParams:
+    p = DepthParams()
+    p.method, p.min_dist, p.max_dist, p.bf, p.inv_dilation_scale = method, min_dist, max_dist, bf, scale
+    p.ku, p.kv = ku, kv
+    m = structuring_element(kernel_type, ku, kv)
+    flat = np.zeros(81, np.uint8); flat[:ku * kv] = m.reshape(-1)
+    C.memmove(p.mask, flat.ctypes.data, 81)
+    p.avg_kernel, p.nn_search_radius = avg_kernel, nn_radius
+    return p
+
+
+class DepthModule:
+    """ORB_SLAM3::DepthModule drop-in for the RGB-L hot path (src/DepthModule.cc:50-274).
+
+    The YAML parsing of the reference constructor (src/DepthModule.cc:281-601) stays with the caller;
+    the parsed values are passed here (LidarProjectionMatrix, LiDAR.Method, min/max dist, kernel).
+    """
+
+    def __init__(self, ctx: Context, LidarProjectionMatrix: np.ndarray, bf: float, method="InverseDilation",
+                 min_dist=5.0, max_dist=200.0, kernel_type="Diamond", kernel_size_u=5, kernel_size_v=5):
+        methods = {"None": L.DEPTH_NONE, "NearestNeighborPixel": L.DEPTH_NEAREST_NEIGHBOR_PIXEL,
+                   "AverageFiltering": L.DEPTH_AVERAGE_FILTERING, "InverseDilation": L.DEPTH_INVERSE_DILATION}
+        self.ctx = ctx
+        self.LidarProjectionMatrix = np.ascontiguousarray(LidarProjectionMatrix, np.float32).reshape(3, 4)
+        self.params = make_depth_params(methods[method], min_dist, max_dist, bf, kernel_type, kernel_size_u, kernel_size_v)
+        self.mvDepth = np.empty(0, np.float32); self.mvuRight = np.empty(0, np.float32)
+        self.RawDepthMap = None; self.ProcessedDepthMap = None
+
+    def CalculateDepthFromPcd(self, mvKeys, mvKeysUn, PointCloud, imwidth, imheight, want_maps=True):
+        pts = np.ascontiguousarray(PointCloud, np.float32)
+        assert pts.ndim == 2 and pts.shape[0] == 4, "4 x N CV_32F point cloud expected"
+        k = np.ascontiguousarray(mvKeys, KP_DTYPE); ku = np.ascontiguousarray(mvKeysUn, KP_DTYPE)
+        n = len(k)
+        d = np.empty(n, np.float32); u = np.empty(n, np.float32)
+        raw = np.empty((imheight, imwidth), np.float32) if want_maps else None
+        proc = np.empty((imheight, imwidth), np.float32) if want_maps else None
+        check(lib().rgbl_depth_from_pcd(self.ctx.handle, ptr(pts), pts.shape[1], ptr(self.LidarProjectionMatrix), imwidth, imheight,
+                                        C.byref(self.params), ptr(k), ptr(ku), n, ptr(d), ptr(u),
+                                        ptr(raw) if want_maps else None, ptr(proc) if want_maps else None), self.ctx.handle)
+        self.mvDepth, self.mvuRight, self.RawDepthMap, self.ProcessedDepthMap = d, u, raw, proc
+
+
+def frame_rgbl_batch(ctx: Context, images, clouds, P, depth_params: DepthParams):
+    """Fused Frame construction for n RGB-L frames (src/Frame.cc:289-377): ExtractORB + CalculateDepthFromPcd."""
+    nF = len(images); cap = ctx.cap
+    imgs = [np.ascontiguousarray(i, np.uint8) for i in images]
+    pcs = [np.ascontiguousarray(p, np.float32) for p in clouds]
+    ia = (C.c_void_p * nF)(*[i.ctypes.data for i in imgs]); pa = (C.c_void_p * nF)(*[p.ctypes.data for p in pcs])
+    npts = np.array([p.shape[1] for p in pcs], np.int32)
+    P = np.ascontiguousarray(P, np.float32).reshape(12)
+    kps = np.empty((nF, cap), KP_DTYPE); desc = np.empty((nF, cap, 32), np.uint8)
+    depth = np.empty((nF, cap), np.float32); ur = np.empty((nF, cap), np.float32); n = np.zeros(nF, np.int32)
+    check(lib().rgbl_frame_rgbl_batch(ctx.handle, nF, ia, imgs[0].shape[1], imgs[0].shape[0], imgs[0].strides[0], pa, ptr(npts),
+                                      ptr(P), C.byref(depth_params), ptr(kps), ptr(desc), ptr(depth), ptr(ur), cap, ptr(n)), ctx.handle)
+    return [(kps[f, :n[f]].copy(), desc[f, :n[f]].copy(), depth[f, :n[f]].copy(), ur[f, :n[f]].copy()) for f in range(nF)]

@@ -1,0 +1,109 @@
+"""GPU parity: CUDA ORB extractor (through the C ABI) vs the CPU oracle, stage by stage and end to end.
+Bar: bit-exact (integer/byte/index work; angles are float32 results of identical operation sequences)."""
+import numpy as np
+import pytest
+
+import oracle
+from orb_slam3_rgbl_b200 import frontend as F
+from orb_slam3_rgbl_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp_kps(a, b):
+    assert len(a) == len(b), f"keypoint count {len(a)} vs oracle {len(b)}"
+    bad = {f: int((a[f] != b[f]).sum()) for f in a.dtype.names}
+    assert not any(bad.values()), f"keypoint field mismatches: {bad}"
+
+
+@pytest.fixture(scope="module")
+def kitti_ctx():
+    ex = F.ORBextractor(2000, 1.2, 8, 12, 7, S.KITTI_W, S.KITTI_H, max_batch=4)
+    yield ex
+    ex.ctx.close()
+
+
+@pytest.mark.parametrize("seed", [0, 11])
+def test_stages_and_keypoints_kitti(kitti_ctx, seed, report_dir):
+    img = S.make_image(seed)
+    ref = oracle.Extractor(2000)
+    rk, rd, rmono = ref(img)
+    mono, k, d = kitti_ctx(img)
+    lines = []
+    for l in range(8):
+        a, b = kitti_ctx.level_image(l), ref.level_image(l)
+        assert a.shape == b.shape
+        lines.append(f"level {l}: pyramid mismatches {(a != b).sum()}")
+        assert (a == b).all(), lines[-1]
+        ab, bb = kitti_ctx.blurred_level(l), oracle.gaussian_blur7(b)
+        lines.append(f"level {l}: blur mismatches {(ab != bb).sum()}")
+        assert (ab == bb).all(), lines[-1]
+        ca, cb = kitti_ctx.level_candidates(l), ref.level_candidates(l)
+        lines.append(f"level {l}: candidates {len(ca)} vs {len(cb)}")
+        assert ca.shape == cb.shape and (ca == cb).all(), lines[-1]
+    (report_dir / f"extractor_stage_report_{seed}.txt").write_text("\n".join(lines))
+    _cmp_kps(k, rk)
+    assert (d == rd).all(), f"descriptor rows differing: {(d != rd).any(axis=1).sum()}"
+    assert mono == rmono
+
+
+def test_batch_equals_single(kitti_ctx):
+    imgs = [S.make_image(s) for s in (21, 22, 23)]
+    outs = kitti_ctx.extract_batch(imgs)
+    ref = oracle.Extractor(2000)
+    for img, (k, d) in zip(imgs, outs):
+        rk, rd, _ = ref(img)
+        _cmp_kps(k, rk)
+        assert (d == rd).all()
+
+
+def test_padded_pyramid_matches_reflect101(kitti_ctx):
+    img = S.make_image(3)
+    kitti_ctx(img)
+    ref = oracle.Extractor(2000); ref(img)
+    for l in (0, 3, 7):
+        p = kitti_ctx.image_pyramid_padded(l)
+        r = np.pad(ref.level_image(l), 19, mode="reflect")       # numpy 'reflect' == BORDER_REFLECT_101
+        assert p.shape == r.shape and (p == r).all()
+
+
+@pytest.mark.parametrize("w,h,nf", [(640, 480, 1000), (752, 480, 1200), (1920, 1080, 4000)])
+def test_other_sizes(w, h, nf):
+    img = S.make_image(7, w, h)
+    ex = F.ORBextractor(nf, 1.2, 8, 12, 7, w, h)
+    try:
+        mono, k, d = ex(img)
+    finally:
+        ex.ctx.close()
+    rk, rd, _ = oracle.Extractor(nf)(img)
+    _cmp_kps(k, rk)
+    assert (d == rd).all()
+
+
+def test_flat_image_gives_no_keypoints():
+    img = np.full((S.KITTI_H, S.KITTI_W), 100, np.uint8)
+    ex = F.ORBextractor(1000, 1.2, 8, 12, 7, S.KITTI_W, S.KITTI_H)
+    try:
+        mono, k, d = ex(img)
+    finally:
+        ex.ctx.close()
+    assert mono == 0 and len(k) == 0 and d.shape == (0, 32)
+
+
+def test_empty_image_returns_minus_one(kitti_ctx):
+    mono, k, d = kitti_ctx(np.empty((0, 0), np.uint8))
+    assert mono == -1
+
+
+def test_low_texture_uses_min_threshold():
+    # faint texture: most cells fall back to minThFAST=7 (src/ORBextractor.cc:843-846)
+    rng = np.random.default_rng(5)
+    img = (100 + 6 * rng.standard_normal((S.KITTI_H, S.KITTI_W))).clip(0, 255).astype(np.uint8)
+    ex = F.ORBextractor(1000, 1.2, 8, 12, 7, S.KITTI_W, S.KITTI_H)
+    try:
+        mono, k, d = ex(img)
+    finally:
+        ex.ctx.close()
+    rk, rd, _ = oracle.Extractor(1000)(img)
+    _cmp_kps(k, rk)
+    assert (d == rd).all()

@@ -85,6 +85,8 @@ int rgbl_create(const rgbl_config* cfg, rgbl_ctx** out);
 void rgbl_destroy(rgbl_ctx* ctx);
 const char* rgbl_last_error(const rgbl_ctx* ctx);     /* ctx may be NULL: error of the last failed rgbl_create */
 int rgbl_abi_version(void);
+/* Upper bound of keypoints one frame can yield (sum over levels of max(quota+3, 4*nIni)); size kps/desc with it. */
+int rgbl_keypoint_capacity(const rgbl_ctx* ctx);
 
 /* Tables computed by ORBextractor::ORBextractor (src/ORBextractor.cc:409-469) and exposed through
  * GetScaleFactors()/GetInverseScaleFactors()/... (include/ORBextractor.h:61-81).  Host-only. */
@@ -92,8 +94,8 @@ int rgbl_orb_tables(const rgbl_orb_params* p, float* scale, float* inv_scale, fl
                     int32_t* features_per_level, int32_t* umax16);
 
 /* ---- ORBextractor::operator() (include/ORBextractor.h:57-59, src/ORBextractor.cc:1086-1168) ---- *
- * gray: CV_8UC1 host image.  kps/desc: capacity `cap` entries (cap >= nfeatures + 2*nlevels is
- * always sufficient).  lap0/lap1 = vLappingArea.  *mono_index = the return value of
+ * gray: CV_8UC1 host image.  kps/desc: capacity `cap` entries (cap >= rgbl_keypoint_capacity(ctx)
+ * is always sufficient).  lap0/lap1 = vLappingArea.  *mono_index = the return value of
  * the reference operator().  Returns RGBL_E_EMPTY for an empty image.                               */
 int rgbl_orb_extract(rgbl_ctx* ctx, const uint8_t* gray, int width, int height, int stride, int lap0, int lap1,
                      rgbl_keypoint* kps, uint8_t* desc, int cap, int* n_out, int* mono_index);
@@ -131,6 +133,28 @@ int rgbl_depth_structuring_element(const char* kind, int ku, int kv, uint8_t* ma
 int rgbl_frame_rgbl_batch(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
                           const float* const* pts4xn, const int* n_pts, const float P[12], const rgbl_depth_params* prm,
                           rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out);
+
+/* Resident form of the same work (device-throughput measurement, pipelined callers): inputs are
+ * copied to HBM once, rgbl_resident_process can then be repeated with no host->device input traffic
+ * and leaves its results in HBM until rgbl_resident_download.                                     */
+int rgbl_resident_upload(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
+                         const float* const* pts4xn, const int* n_pts);
+int rgbl_resident_process(rgbl_ctx* ctx, const float P[12], const rgbl_depth_params* prm, int* n_out /* nullable */);
+int rgbl_resident_download(rgbl_ctx* ctx, rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out);
+
+/* CUDA-event stopwatch on the context's main stream: mark(0) ... work ... mark(1); elapsed = device time
+ * between the two marks (includes host gaps of the pipeline, excludes nothing).                      */
+int rgbl_timer_mark(rgbl_ctx* ctx, int which);
+int rgbl_timer_elapsed_ms(rgbl_ctx* ctx, double* ms);
+
+/* ---- profiling: CUDA-event time per stage on the launching streams, kernel launch counts.  The
+ * reference's counterpart is REGISTER_TIMES (include/Settings.h:24, src/Frame.cc:311-319).          */
+int rgbl_profile_enable(rgbl_ctx* ctx, int on);
+int rgbl_profile_reset(rgbl_ctx* ctx);
+int rgbl_profile_num_stages(void);
+const char* rgbl_profile_stage_name(int stage);
+int rgbl_profile_read(const rgbl_ctx* ctx, int stage, double* total_ms, int64_t* kernel_launches, int64_t* calls);
+int rgbl_profile_totals(const rgbl_ctx* ctx, int64_t* kernel_launches, double* host_quadtree_ms);
 
 /* ---- ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2058-2074).  Host-only helper. ---- */
 int rgbl_descriptor_distance(const uint8_t a[32], const uint8_t b[32]);

@@ -146,7 +146,14 @@ void fast_window(const uint8_t* win, int w, int h, int stride, int th, std::vect
     std::vector<int> sc((size_t)w * h, 0);
     for (int y = 3; y < h - 3; ++y)
         for (int x = 3; x < w - 3; ++x) {
-            int K = fast_arc_strength(win + (size_t)y * stride + x, stride);
+            const uint8_t* p = win + (size_t)y * stride + x;
+            // cheap necessary condition (OpenCV's own high-speed test has the same role): any 9-arc covers
+            // at least two of the four compass ring pixels, so a corner at th has >= 2 of them beyond +-th
+            const int v = p[0], c0 = p[3 * stride], c4 = p[3], c8 = p[-3 * stride], c12 = p[-3];
+            const int nb = (v - c0 > th) + (v - c4 > th) + (v - c8 > th) + (v - c12 > th);
+            const int nd = (c0 - v > th) + (c4 - v > th) + (c8 - v > th) + (c12 - v > th);
+            if (nb < 2 && nd < 2) continue;
+            int K = fast_arc_strength(p, stride);
             if (K > th) sc[(size_t)y * w + x] = K - 1;
         }
     for (int y = 3; y < h - 3; ++y)

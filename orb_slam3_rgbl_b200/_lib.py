@@ -57,6 +57,7 @@ SYMBOLS = {
     "rgbl_destroy": (None, [_vp]),
     "rgbl_last_error": (C.c_char_p, [_vp]),
     "rgbl_abi_version": (_i, []),
+    "rgbl_keypoint_capacity": (_i, [_vp]),
     "rgbl_orb_tables": (_i, [C.POINTER(OrbParams), _vp, _vp, _vp, _vp, _vp, _vp]),
     "rgbl_orb_extract": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _ip, _ip]),
     "rgbl_orb_extract_batch": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
@@ -67,6 +68,17 @@ SYMBOLS = {
     "rgbl_depth_from_pcd": (_i, [_vp, _vp, _i, _vp, _i, _i, C.POINTER(DepthParams), _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "rgbl_depth_structuring_element": (_i, [C.c_char_p, _i, _i, _vp]),
     "rgbl_frame_rgbl_batch": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(DepthParams), _vp, _vp, _vp, _vp, _i, _vp]),
+    "rgbl_resident_upload": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "rgbl_resident_process": (_i, [_vp, _vp, C.POINTER(DepthParams), _vp]),
+    "rgbl_resident_download": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "rgbl_timer_mark": (_i, [_vp, _i]),
+    "rgbl_timer_elapsed_ms": (_i, [_vp, C.POINTER(C.c_double)]),
+    "rgbl_profile_enable": (_i, [_vp, _i]),
+    "rgbl_profile_reset": (_i, [_vp]),
+    "rgbl_profile_num_stages": (_i, []),
+    "rgbl_profile_stage_name": (C.c_char_p, [_i]),
+    "rgbl_profile_read": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "rgbl_profile_totals": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "rgbl_descriptor_distance": (_i, [_vp, _vp]),
     "rgbl_quadtree_select": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i]),
 }

@@ -2,8 +2,11 @@
 // There is no CPU fallback anywhere in this file: every compute entry point needs the CUDA device
 // the context was created on and reports RGBL_E_CUDA otherwise.
 #include <atomic>
+#include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -13,6 +16,11 @@
 namespace rgbl {
 
 static thread_local std::string g_create_error;
+
+enum Stage { ST_PYRAMID = 0, ST_FAST, ST_COMPACT, ST_BLUR, ST_DESCRIBE, ST_DEPTH_PROJECT, ST_DEPTH_DILATE, ST_DEPTH_GATHER,
+             ST_MATCH, ST_POSE, kNumStages };
+static const char* kStageNames[kNumStages] = {"pyramid", "fast", "compact", "blur", "describe", "depth_project",
+                                              "depth_resolve_dilate", "depth_gather", "match", "pose"};
 
 struct Ctx {
     rgbl_config cfg{};
@@ -27,7 +35,7 @@ struct Ctx {
     std::string err;
 
     cudaStream_t st = nullptr, st_aux = nullptr;
-    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
+    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
 
     // device
     LevelGeom* d_levels = nullptr;
@@ -55,7 +63,19 @@ struct Ctx {
     uint32_t* h_dense = nullptr;
     SelKp* h_sel = nullptr;
 
+    // profiling (rgbl_profile_*): CUDA events on the launching stream around every stage
+    bool prof_on = false;
+    cudaEvent_t ev_b[kNumStages] = {}, ev_e[kNumStages] = {};
+    bool st_used[kNumStages] = {};
+    int st_pending_launches[kNumStages] = {};
+    double st_ms[kNumStages] = {};
+    long st_launches[kNumStages] = {};
+    long st_calls[kNumStages] = {};
+    double host_quadtree_ms = 0.0;
+    long total_launches = 0;
+
     int last_frames = 0;         // frames valid in the device buffers
+    int resident_frames = 0, resident_max_pts = 0;
     bool blur_valid = false;
 };
 
@@ -83,6 +103,9 @@ static void release(Ctx* c) {
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = {c->h_level_cnt, c->h_frame_total, c->h_overflow, c->h_n_sel, c->h_n_pts, c->h_dense, c->h_sel};
     for (void* p : host) if (p) cudaFreeHost(p);
+    for (int i = 0; i < kNumStages; ++i) { if (c->ev_b[i]) cudaEventDestroy(c->ev_b[i]); if (c->ev_e[i]) cudaEventDestroy(c->ev_e[i]); }
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
     if (c->ev_blur) cudaEventDestroy(c->ev_blur);
     if (c->st) cudaStreamDestroy(c->st);
@@ -101,7 +124,13 @@ static int create(const rgbl_config* cfg, Ctx** out) {
     rc = build_geometry(cfg->width, cfg->height, c->tab, c->levels, c->cells, c->coefs, c->frame_bytes, c->err);
     if (rc) return fail(rc);
     c->n_cells = (int)c->cells.size();
-    c->cap_kp = cfg->orb.nfeatures + 3 * cfg->orb.nlevels;
+    // DistributeOctTree returns at most max(quota + 2, 4 * nIni) keypoints per level (the very
+    // first subdivision pass is unguarded, later ones stop within +3 of the budget).
+    c->cap_kp = 0;
+    for (const LevelGeom& g : c->levels) {
+        const int n_ini = (int)std::round(static_cast<float>(g.max_bx - g.min_bx) / (g.max_by - g.min_by));
+        c->cap_kp += std::max(g.quota + 3, 4 * n_ini);
+    }
     const int B = cfg->max_batch;
     const int per_frame_cand = cfg->max_candidates > 0 ? cfg->max_candidates : std::max(32768, cfg->width * cfg->height / 8);
     c->dense_cap = per_frame_cand * B;
@@ -113,8 +142,11 @@ static int create(const rgbl_config* cfg, Ctx** out) {
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { c->err = std::string(#call) + ": " + cudaGetErrorString(e_); return fail(RGBL_E_CUDA); } } while (0)
     CUF(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CUF(cudaStreamCreateWithFlags(&c->st_aux, cudaStreamNonBlocking));
+    CUF(cudaEventCreate(&c->ev_t0));
+    CUF(cudaEventCreate(&c->ev_t1));
     CUF(cudaEventCreateWithFlags(&c->ev_pyr, cudaEventDisableTiming));
     CUF(cudaEventCreateWithFlags(&c->ev_blur, cudaEventDisableTiming));
+    for (int i = 0; i < kNumStages; ++i) { CUF(cudaEventCreate(&c->ev_b[i])); CUF(cudaEventCreate(&c->ev_e[i])); }
     CUF(dmalloc(&c->d_levels, nl));
     CUF(dmalloc(&c->d_cells, c->cells.size()));
     CUF(dmalloc(&c->d_coefs, std::max<size_t>(c->coefs.size(), 1)));
@@ -164,24 +196,62 @@ static int create(const rgbl_config* cfg, Ctx** out) {
     return RGBL_OK;
 }
 
+// ---- profiling helpers -----------------------------------------------------------------------------
+static inline void stage_begin(Ctx* c, int stage, cudaStream_t st) {
+    if (c->prof_on) { cudaEventRecord(c->ev_b[stage], st); c->st_used[stage] = true; }
+}
+static inline void stage_end(Ctx* c, int stage, cudaStream_t st, int launches) {
+    c->total_launches += launches;
+    c->st_pending_launches[stage] += launches;
+    if (c->prof_on) cudaEventRecord(c->ev_e[stage], st);
+}
+// call after both streams are idle
+static void prof_collect(Ctx* c) {
+    for (int i = 0; i < kNumStages; ++i) {
+        if (c->prof_on && c->st_used[i]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c->ev_b[i], c->ev_e[i]) == cudaSuccess) { c->st_ms[i] += ms; c->st_calls[i] += 1; c->st_launches[i] += c->st_pending_launches[i]; }
+        }
+        c->st_used[i] = false;
+        c->st_pending_launches[i] = 0;
+    }
+}
+
 // ---- extraction pipeline -----------------------------------------------------------------------
-// Stage 1 (device): upload, pyramid, FAST + compaction; blur on the aux stream.
+// Stage 0 (copy):   images -> level 0 of each frame slot (upload_images).
+// Stage 1 (device): pyramid, FAST + compaction on the main stream; blur on the aux stream.
 // Stage 2 (host):   quad-tree per (frame, level) on worker threads -> SelKp lists.
-// Stage 3 (device): describe.  Results stay in d_kps / d_desc (and are copied out by the callers).
-static int run_extract(Ctx* c, int n_frames, const uint8_t* const* gray, int stride) {
-    const int W = c->cfg.width, H = c->cfg.height, nl = c->tab.nlevels;
+// Stage 3 (device): describe.  Results stay in d_kps / d_desc (copied out by the callers).
+static int upload_images(Ctx* c, int n_frames, const uint8_t* const* gray, int stride, cudaStream_t st) {
     const LevelGeom& l0 = c->levels[0];
     for (int f = 0; f < n_frames; ++f)
-        CU(cudaMemcpy2DAsync(c->d_pyr + (size_t)f * c->frame_bytes + l0.off, l0.pitch, gray[f], stride, W, H,
-                             cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpy2DAsync(c->d_pyr + (size_t)f * c->frame_bytes + l0.off, l0.pitch, gray[f], stride, c->cfg.width,
+                             c->cfg.height, cudaMemcpyHostToDevice, st));
+    return RGBL_OK;
+}
+
+static int run_extract(Ctx* c, int n_frames, const std::function<void()>& aux_work = nullptr) {
+    const int nl = c->tab.nlevels;
+    stage_begin(c, ST_PYRAMID, c->st);
     launch_pyramid(c->st, c->d_pyr, c->frame_bytes, c->levels.data(), nl, c->d_coefs, n_frames);
+    stage_end(c, ST_PYRAMID, c->st, nl - 1);
+    stage_begin(c, ST_FAST, c->st);
+    launch_fast(c->st, c->d_pyr, c->frame_bytes, c->d_levels, c->d_cells, c->n_cells, c->cfg.orb.ini_th_fast,
+                c->cfg.orb.min_th_fast, c->d_slots, c->d_counts, c->d_overflow, n_frames);
+    stage_end(c, ST_FAST, c->st, 1);
+    stage_begin(c, ST_COMPACT, c->st);
+    launch_compact(c->st, c->d_levels, nl, c->n_cells, c->d_slots, c->d_counts, c->d_cell_off, c->d_level_cnt,
+                   c->d_frame_total, c->d_dense, c->dense_cap, c->d_overflow, n_frames);
+    stage_end(c, ST_COMPACT, c->st, 2);
+    // The aux stream starts once FAST + compaction are done, i.e. it runs the blur (and, for RGB-L frames, the
+    // depth maps queued by the caller via `aux_work`) while the host is busy with the quad-tree.
     CU(cudaEventRecord(c->ev_pyr, c->st));
     CU(cudaStreamWaitEvent(c->st_aux, c->ev_pyr, 0));
+    stage_begin(c, ST_BLUR, c->st_aux);
     launch_blur(c->st_aux, c->d_pyr, c->d_blur, c->frame_bytes, c->levels.data(), nl, n_frames);
+    stage_end(c, ST_BLUR, c->st_aux, nl);
+    if (aux_work) aux_work();
     CU(cudaEventRecord(c->ev_blur, c->st_aux));
-    launch_fast(c->st, c->d_pyr, c->frame_bytes, c->d_levels, nl, c->d_cells, c->n_cells, c->cfg.orb.ini_th_fast,
-                c->cfg.orb.min_th_fast, c->d_slots, c->d_counts, c->d_cell_off, c->d_level_cnt, c->d_frame_total,
-                c->d_dense, c->dense_cap, c->d_overflow, n_frames);
     CU(cudaMemcpyAsync(c->h_level_cnt, c->d_level_cnt, (size_t)n_frames * RGBL_MAX_LEVELS * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(c->h_frame_total, c->d_frame_total, (size_t)n_frames * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->st));
@@ -199,7 +269,7 @@ static int run_extract(Ctx* c, int n_frames, const uint8_t* const* gray, int str
     CU(cudaStreamSynchronize(c->st));
 
     // host quad-tree: tasks = (frame, level)
-    std::vector<int> sel_count((size_t)n_frames * nl, 0);
+    const auto t0 = std::chrono::steady_clock::now();
     std::vector<std::vector<SelKp>> sel_lists((size_t)n_frames * nl);
     std::atomic<int> next{0};
     std::atomic<int> status{0};
@@ -219,7 +289,7 @@ static int run_extract(Ctx* c, int n_frames, const uint8_t* const* gray, int str
                 const uint32_t p = c->h_dense[off + k];
                 xys[3 * k] = (int)(p & 0xfff); xys[3 * k + 1] = (int)((p >> 12) & 0xfff); xys[3 * k + 2] = (int)(p >> 24);
             }
-            idx.resize((size_t)lg.quota + 8);
+            idx.resize((size_t)c->cap_kp);
             int m = quadtree_select(xys.data(), n, lg.min_bx, lg.max_bx, lg.min_by, lg.max_by, lg.quota, idx.data(), (int)idx.size());
             if (m < 0) { status.store(m); continue; }
             std::vector<SelKp>& out = sel_lists[t];
@@ -245,23 +315,37 @@ static int run_extract(Ctx* c, int n_frames, const uint8_t* const* gray, int str
     for (int f = 0; f < n_frames; ++f) {
         int n = 0;
         for (int l = 0; l < nl; ++l) {
-            const std::vector<SelKp>& s = sel_lists[(size_t)f * nl + l];
-            if (n + (int)s.size() > c->cap_kp) { c->err = "keypoint capacity exceeded"; return RGBL_E_CAPACITY; }
-            if (!s.empty()) std::memcpy(c->h_sel + (size_t)f * c->cap_kp + n, s.data(), s.size() * sizeof(SelKp));
-            n += (int)s.size();
+            const std::vector<SelKp>& sl = sel_lists[(size_t)f * nl + l];
+            if (n + (int)sl.size() > c->cap_kp) { c->err = "keypoint capacity exceeded"; return RGBL_E_CAPACITY; }
+            if (!sl.empty()) std::memcpy(c->h_sel + (size_t)f * c->cap_kp + n, sl.data(), sl.size() * sizeof(SelKp));
+            n += (int)sl.size();
         }
         c->h_n_sel[f] = n;
         max_n = std::max(max_n, n);
     }
+    c->host_quadtree_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     CU(cudaMemcpyAsync(c->d_sel, c->h_sel, (size_t)n_frames * c->cap_kp * sizeof(SelKp), cudaMemcpyHostToDevice, c->st));
     CU(cudaMemcpyAsync(c->d_n_sel, c->h_n_sel, (size_t)n_frames * sizeof(int), cudaMemcpyHostToDevice, c->st));
     CU(cudaStreamWaitEvent(c->st, c->ev_blur, 0));
+    stage_begin(c, ST_DESCRIBE, c->st);
     launch_describe(c->st, c->d_pyr, c->d_blur, c->frame_bytes, c->d_levels, c->d_sel, c->d_n_sel, c->cap_kp, max_n,
                     c->tab.umax, c->d_kps, c->d_desc, n_frames);
+    stage_end(c, ST_DESCRIBE, c->st, max_n > 0 ? 1 : 0);
     CU(cudaGetLastError());
     c->last_frames = n_frames;
     c->blur_valid = true;
     return max_n;
+}
+
+// Depth maps for n_frames resident point clouds (d_pts / d_n_pts) on stream st.
+static void run_depth_maps(Ctx* c, const DepthDev& dd, int n_frames, int max_pts, float* raw, cudaStream_t st) {
+    const int W = c->cfg.width, H = c->cfg.height;
+    stage_begin(c, ST_DEPTH_PROJECT, st);
+    launch_depth_project(st, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, max_pts, dd, W, H, c->d_idx_map, c->stamp, n_frames);
+    stage_end(c, ST_DEPTH_PROJECT, st, max_pts > 0 ? 1 : 0);
+    stage_begin(c, ST_DEPTH_DILATE, st);
+    launch_depth_resolve_dilate(st, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, dd, W, H, c->d_idx_map, c->stamp, raw, c->d_processed, n_frames);
+    stage_end(c, ST_DEPTH_DILATE, st, 1);
 }
 
 static int setup_depth(Ctx* c, const float P[12], const rgbl_depth_params* prm, DepthDev& dd) {
@@ -301,6 +385,8 @@ int rgbl_create(const rgbl_config* cfg, rgbl_ctx** out) {
 
 void rgbl_destroy(rgbl_ctx* ctx) { release(reinterpret_cast<Ctx*>(ctx)); }
 
+int rgbl_keypoint_capacity(const rgbl_ctx* ctx) { return ctx ? reinterpret_cast<const Ctx*>(ctx)->cap_kp : RGBL_E_INVALID; }
+
 const char* rgbl_last_error(const rgbl_ctx* ctx) {
     if (!ctx) return g_create_error.c_str();
     return reinterpret_cast<const Ctx*>(ctx)->err.c_str();
@@ -316,7 +402,9 @@ int rgbl_orb_extract_batch(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gr
     if (width != c->cfg.width || height != c->cfg.height || stride < width) { c->err = "image size does not match the context"; return RGBL_E_INVALID; }
     if (n_frames > c->cfg.max_batch) { c->err = "n_frames exceeds max_batch"; return RGBL_E_CAPACITY; }
     CU(cudaSetDevice(c->cfg.device));
-    int rc = run_extract(c, n_frames, gray, stride);
+    int rc = upload_images(c, n_frames, gray, stride, c->st);
+    if (rc) return rc;
+    rc = run_extract(c, n_frames);
     if (rc < 0) return rc;
     for (int f = 0; f < n_frames; ++f) {
         const int n = c->h_n_sel[f];
@@ -328,6 +416,8 @@ int rgbl_orb_extract_batch(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gr
         }
     }
     CU(cudaStreamSynchronize(c->st));
+    CU(cudaStreamSynchronize(c->st_aux));
+    prof_collect(c);
     // vLappingArea placement (src/ORBextractor.cc:1153-1162): lapping keypoints fill the back.
     for (int f = 0; f < n_frames; ++f) {
         const int n = n_out[f];
@@ -447,11 +537,11 @@ int rgbl_depth_from_pcd(rgbl_ctx* ctx, const float* pts4xn, int n_pts, const flo
         CU(cudaMemcpyAsync(c->d_kps_in, kps, (size_t)n_kp * sizeof(rgbl_keypoint), cudaMemcpyHostToDevice, c->st));
         CU(cudaMemcpyAsync(c->d_kps_un, kps_un, (size_t)n_kp * sizeof(rgbl_keypoint), cudaMemcpyHostToDevice, c->st));
     }
-    launch_depth_project(c->st, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, n_pts, dd, width, height, c->d_idx_map, c->stamp, 1);
-    launch_depth_resolve_dilate(c->st, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, dd, width, height, c->d_idx_map, c->stamp,
-                                c->d_raw, c->d_processed, 1);
+    run_depth_maps(c, dd, 1, n_pts, c->d_raw, c->st);
+    stage_begin(c, ST_DEPTH_GATHER, c->st);
     launch_depth_gather(c->st, c->d_processed, width, height, c->d_kps_in, c->d_kps_un, c->d_n_kp_in, c->cap_kp, n_kp, dd.bf,
                         c->d_depth, c->d_uright, 1);
+    stage_end(c, ST_DEPTH_GATHER, c->st, n_kp > 0 ? 1 : 0);
     CU(cudaGetLastError());
     if (n_kp) {
         CU(cudaMemcpyAsync(depth, c->d_depth, (size_t)n_kp * sizeof(float), cudaMemcpyDeviceToHost, c->st));
@@ -460,41 +550,56 @@ int rgbl_depth_from_pcd(rgbl_ctx* ctx, const float* pts4xn, int n_pts, const flo
     if (raw_map) CU(cudaMemcpyAsync(raw_map, c->d_raw, WH * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     if (processed_map) CU(cudaMemcpyAsync(processed_map, c->d_processed, WH * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     CU(cudaStreamSynchronize(c->st));
+    prof_collect(c);
     return RGBL_OK;
 }
 
-int rgbl_frame_rgbl_batch(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
-                          const float* const* pts4xn, const int* n_pts, const float P[12], const rgbl_depth_params* prm,
-                          rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out) {
-    Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    if (!c) return RGBL_E_INVALID;
-    if (!gray || !pts4xn || !n_pts || !P || !prm || !kps || !desc || !depth || !uright || !n_out || n_frames < 1) { c->err = "null argument"; return RGBL_E_INVALID; }
+static int check_batch_args(Ctx* c, int n_frames, int width, int height, int stride) {
     if (width <= 0 || height <= 0) { c->err = "empty image"; return RGBL_E_EMPTY; }
     if (width != c->cfg.width || height != c->cfg.height || stride < width) { c->err = "image size does not match the context"; return RGBL_E_INVALID; }
+    if (n_frames < 1) { c->err = "n_frames < 1"; return RGBL_E_INVALID; }
     if (n_frames > c->cfg.max_batch) { c->err = "n_frames exceeds max_batch"; return RGBL_E_CAPACITY; }
+    return RGBL_OK;
+}
+
+// H2D of one batch of RGB-L inputs into the context's frame slots (images on the main stream, clouds on aux).
+static int upload_rgbl(Ctx* c, int n_frames, const uint8_t* const* gray, int stride, const float* const* pts4xn, const int* n_pts, int* max_pts_out) {
+    if (!c->d_pts) { c->err = "context was created with max_points == 0"; return RGBL_E_INVALID; }
     int max_pts = 0;
     for (int f = 0; f < n_frames; ++f) {
         if (!gray[f]) { c->err = "empty image"; return RGBL_E_EMPTY; }
         if (n_pts[f] < 0 || n_pts[f] > c->cfg.max_points || (n_pts[f] && !pts4xn[f])) { c->err = "bad point cloud"; return RGBL_E_CAPACITY; }
         max_pts = std::max(max_pts, n_pts[f]);
     }
-    CU(cudaSetDevice(c->cfg.device));
-    DepthDev dd;
-    int rc = setup_depth(c, P, prm, dd); if (rc) return rc;
-    // depth projection/upsampling does not depend on the keypoints: issue it on the aux stream first
     for (int f = 0; f < n_frames; ++f) {
         c->h_n_pts[f] = n_pts[f];
         if (n_pts[f]) CU(cudaMemcpyAsync(c->d_pts + (size_t)f * 4 * c->cfg.max_points, pts4xn[f], (size_t)4 * n_pts[f] * sizeof(float), cudaMemcpyHostToDevice, c->st_aux));
     }
     CU(cudaMemcpyAsync(c->d_n_pts, c->h_n_pts, (size_t)n_frames * sizeof(int), cudaMemcpyHostToDevice, c->st_aux));
-    launch_depth_project(c->st_aux, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, max_pts, dd, width, height, c->d_idx_map, c->stamp, n_frames);
-    launch_depth_resolve_dilate(c->st_aux, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, dd, width, height, c->d_idx_map, c->stamp,
-                                nullptr, c->d_processed, n_frames);
-    int max_n = run_extract(c, n_frames, gray, stride);     // waits on ev_blur (recorded after the depth work on st_aux)
+    int rc = upload_images(c, n_frames, gray, stride, c->st);
+    if (rc) return rc;
+    c->resident_frames = n_frames;
+    c->resident_max_pts = max_pts;
+    *max_pts_out = max_pts;
+    return RGBL_OK;
+}
+
+// Everything of Frame::Frame (RGB-L) after the inputs are in HBM: depth maps (aux stream) || extraction, then gather.
+static int process_rgbl(Ctx* c, int n_frames, int max_pts, const float P[12], const rgbl_depth_params* prm) {
+    DepthDev dd;
+    int rc = setup_depth(c, P, prm, dd); if (rc) return rc;
+    // depth maps run on the aux stream behind the blur, overlapping the host quad-tree; describe waits for both
+    int max_n = run_extract(c, n_frames, [&]() { run_depth_maps(c, dd, n_frames, max_pts, nullptr, c->st_aux); });
     if (max_n < 0) return max_n;
-    launch_depth_gather(c->st, c->d_processed, width, height, c->d_kps, c->d_kps, c->d_n_sel, c->cap_kp, max_n, dd.bf,
+    stage_begin(c, ST_DEPTH_GATHER, c->st);
+    launch_depth_gather(c->st, c->d_processed, c->cfg.width, c->cfg.height, c->d_kps, c->d_kps, c->d_n_sel, c->cap_kp, max_n, dd.bf,
                         c->d_depth, c->d_uright, n_frames);
+    stage_end(c, ST_DEPTH_GATHER, c->st, max_n > 0 ? 1 : 0);
     CU(cudaGetLastError());
+    return max_n;
+}
+
+static int download_rgbl(Ctx* c, int n_frames, rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out) {
     for (int f = 0; f < n_frames; ++f) {
         const int n = c->h_n_sel[f];
         n_out[f] = n;
@@ -506,6 +611,112 @@ int rgbl_frame_rgbl_batch(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gra
         CU(cudaMemcpyAsync(uright + (size_t)f * cap, c->d_uright + (size_t)f * c->cap_kp, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
     }
     CU(cudaStreamSynchronize(c->st));
+    CU(cudaStreamSynchronize(c->st_aux));
+    prof_collect(c);
+    return RGBL_OK;
+}
+
+int rgbl_frame_rgbl_batch(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
+                          const float* const* pts4xn, const int* n_pts, const float P[12], const rgbl_depth_params* prm,
+                          rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!gray || !pts4xn || !n_pts || !P || !prm || !kps || !desc || !depth || !uright || !n_out) { c->err = "null argument"; return RGBL_E_INVALID; }
+    int rc = check_batch_args(c, n_frames, width, height, stride); if (rc) return rc;
+    CU(cudaSetDevice(c->cfg.device));
+    int max_pts = 0;
+    rc = upload_rgbl(c, n_frames, gray, stride, pts4xn, n_pts, &max_pts); if (rc) return rc;
+    rc = process_rgbl(c, n_frames, max_pts, P, prm); if (rc < 0) return rc;
+    return download_rgbl(c, n_frames, kps, desc, depth, uright, cap, n_out);
+}
+
+/* Resident form used to measure device throughput: inputs are uploaded once, processing can then be
+ * repeated without any host->device input traffic; results stay in HBM until rgbl_resident_download. */
+int rgbl_resident_upload(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
+                         const float* const* pts4xn, const int* n_pts) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!gray || !pts4xn || !n_pts) { c->err = "null argument"; return RGBL_E_INVALID; }
+    int rc = check_batch_args(c, n_frames, width, height, stride); if (rc) return rc;
+    CU(cudaSetDevice(c->cfg.device));
+    int max_pts = 0;
+    rc = upload_rgbl(c, n_frames, gray, stride, pts4xn, n_pts, &max_pts); if (rc) return rc;
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaStreamSynchronize(c->st_aux));
+    return RGBL_OK;
+}
+
+int rgbl_resident_process(rgbl_ctx* ctx, const float P[12], const rgbl_depth_params* prm, int* n_out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!P || !prm) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (c->resident_frames < 1) { c->err = "nothing uploaded"; return RGBL_E_INVALID; }
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = process_rgbl(c, c->resident_frames, c->resident_max_pts, P, prm); if (rc < 0) return rc;
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaStreamSynchronize(c->st_aux));
+    prof_collect(c);
+    if (n_out) for (int f = 0; f < c->resident_frames; ++f) n_out[f] = c->h_n_sel[f];
+    return RGBL_OK;
+}
+
+int rgbl_resident_download(rgbl_ctx* ctx, rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!kps || !desc || !depth || !uright || !n_out) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (c->last_frames < 1) { c->err = "nothing processed"; return RGBL_E_INVALID; }
+    CU(cudaSetDevice(c->cfg.device));
+    return download_rgbl(c, c->last_frames, kps, desc, depth, uright, cap, n_out);
+}
+
+/* ---- device-side stopwatch on the context's main stream ---- */
+int rgbl_timer_mark(rgbl_ctx* ctx, int which) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || (which != 0 && which != 1)) return RGBL_E_INVALID;
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaEventRecord(which == 0 ? c->ev_t0 : c->ev_t1, c->st));
+    return RGBL_OK;
+}
+int rgbl_timer_elapsed_ms(rgbl_ctx* ctx, double* ms) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !ms) return RGBL_E_INVALID;
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaEventSynchronize(c->ev_t1));
+    float f = 0.f;
+    CU(cudaEventElapsedTime(&f, c->ev_t0, c->ev_t1));
+    *ms = f;
+    return RGBL_OK;
+}
+
+/* ---- profiling ---- */
+int rgbl_profile_enable(rgbl_ctx* ctx, int on) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    c->prof_on = on != 0;
+    return RGBL_OK;
+}
+int rgbl_profile_reset(rgbl_ctx* ctx) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    for (int i = 0; i < kNumStages; ++i) { c->st_ms[i] = 0; c->st_launches[i] = 0; c->st_calls[i] = 0; }
+    c->host_quadtree_ms = 0; c->total_launches = 0;
+    return RGBL_OK;
+}
+int rgbl_profile_num_stages(void) { return kNumStages; }
+const char* rgbl_profile_stage_name(int stage) { return (stage >= 0 && stage < kNumStages) ? kStageNames[stage] : ""; }
+int rgbl_profile_read(const rgbl_ctx* ctx, int stage, double* total_ms, int64_t* kernel_launches, int64_t* calls) {
+    const Ctx* c = reinterpret_cast<const Ctx*>(ctx);
+    if (!c || stage < 0 || stage >= kNumStages) return RGBL_E_INVALID;
+    if (total_ms) *total_ms = c->st_ms[stage];
+    if (kernel_launches) *kernel_launches = c->st_launches[stage];
+    if (calls) *calls = c->st_calls[stage];
+    return RGBL_OK;
+}
+int rgbl_profile_totals(const rgbl_ctx* ctx, int64_t* kernel_launches, double* host_quadtree_ms) {
+    const Ctx* c = reinterpret_cast<const Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (kernel_launches) *kernel_launches = c->total_launches;
+    if (host_quadtree_ms) *host_quadtree_ms = c->host_quadtree_ms;
     return RGBL_OK;
 }
 

@@ -368,12 +368,16 @@ void launch_pyramid(cudaStream_t st, uint8_t* pyr, size_t frame_stride, const Le
     }
 }
 
-void launch_fast(cudaStream_t st, const uint8_t* pyr, size_t frame_stride, const LevelGeom* d_levels, int n_levels,
+void launch_fast(cudaStream_t st, const uint8_t* pyr, size_t frame_stride, const LevelGeom* d_levels,
                  const CellInfo* d_cells, int n_cells, int ini_th, int min_th, uint32_t* slots, int* counts,
-                 int* cell_off, int* level_cnt, int* frame_total, uint32_t* dense, int dense_cap, int* overflow,
-                 int n_frames) {
+                 int* overflow, int n_frames) {
     fast_cells_kernel<<<dim3(n_cells, n_frames), 256, 0, st>>>(pyr, frame_stride, d_levels, d_cells, n_cells, ini_th,
                                                              min_th, slots, counts, overflow);
+}
+
+void launch_compact(cudaStream_t st, const LevelGeom* d_levels, int n_levels, int n_cells, const uint32_t* slots,
+                    const int* counts, int* cell_off, int* level_cnt, int* frame_total, uint32_t* dense, int dense_cap,
+                    int* overflow, int n_frames) {
     cand_scan_kernel<<<n_frames, 256, 0, st>>>(counts, n_cells, d_levels, n_levels, cell_off, level_cnt, frame_total);
     const int gx = (n_cells + 63) / 64;
     cand_gather_kernel<<<dim3(gx, n_frames), 256, 0, st>>>(slots, counts, cell_off, frame_total, n_cells, dense,

@@ -24,10 +24,12 @@ __device__ __forceinline__ uint32_t pack_cand_dev(int x, int y, int s) {
 // orb_kernels.cu
 void launch_pyramid(cudaStream_t st, uint8_t* pyr, size_t frame_stride, const LevelGeom* h_levels, int n_levels,
                     const LinCoef* d_coefs, int n_frames);
-void launch_fast(cudaStream_t st, const uint8_t* pyr, size_t frame_stride, const LevelGeom* d_levels, int n_levels,
+void launch_fast(cudaStream_t st, const uint8_t* pyr, size_t frame_stride, const LevelGeom* d_levels,
                  const CellInfo* d_cells, int n_cells, int ini_th, int min_th, uint32_t* slots, int* counts,
-                 int* cell_off, int* level_cnt, int* frame_total, uint32_t* dense, int dense_cap, int* overflow,
-                 int n_frames);
+                 int* overflow, int n_frames);
+void launch_compact(cudaStream_t st, const LevelGeom* d_levels, int n_levels, int n_cells, const uint32_t* slots,
+                    const int* counts, int* cell_off, int* level_cnt, int* frame_total, uint32_t* dense, int dense_cap,
+                    int* overflow, int n_frames);
 void launch_blur(cudaStream_t st, const uint8_t* pyr, uint8_t* blur, size_t frame_stride, const LevelGeom* h_levels,
                  int n_levels, int n_frames);
 void launch_describe(cudaStream_t st, const uint8_t* pyr, const uint8_t* blur, size_t frame_stride,

@@ -29,7 +29,34 @@ class Context:
             raise L.RgblError(rc, msg.decode() if msg else "rgbl_create failed")
         self.width, self.height, self.nlevels, self.nfeatures = width, height, nlevels, nfeatures
         self.max_batch = max_batch
-        self.cap = nfeatures + 3 * nlevels
+        self.cap = lib().rgbl_keypoint_capacity(self.handle)
+
+    # ---- profiling / timing (rgbl_profile_*, rgbl_timer_*) ----
+    def profile_enable(self, on=True):
+        check(lib().rgbl_profile_enable(self.handle, int(on)), self.handle)
+
+    def profile_reset(self):
+        check(lib().rgbl_profile_reset(self.handle), self.handle)
+
+    def profile_read(self) -> dict:
+        out = {}
+        for s in range(lib().rgbl_profile_num_stages()):
+            ms, nl, nc = C.c_double(), C.c_int64(), C.c_int64()
+            check(lib().rgbl_profile_read(self.handle, s, C.byref(ms), C.byref(nl), C.byref(nc)), self.handle)
+            out[lib().rgbl_profile_stage_name(s).decode()] = dict(ms=ms.value, launches=nl.value, calls=nc.value)
+        nl, hq = C.c_int64(), C.c_double()
+        check(lib().rgbl_profile_totals(self.handle, C.byref(nl), C.byref(hq)), self.handle)
+        out["_total_launches"] = nl.value
+        out["_host_quadtree_ms"] = hq.value
+        return out
+
+    def timer_mark(self, which: int):
+        check(lib().rgbl_timer_mark(self.handle, which), self.handle)
+
+    def timer_elapsed_ms(self) -> float:
+        ms = C.c_double()
+        check(lib().rgbl_timer_elapsed_ms(self.handle, C.byref(ms)), self.handle)
+        return ms.value
 
     def close(self):
         if getattr(self, "handle", None):
@@ -185,3 +212,67 @@ def frame_rgbl_batch(ctx: Context, images, clouds, P, depth_params: DepthParams)
     check(lib().rgbl_frame_rgbl_batch(ctx.handle, nF, ia, imgs[0].shape[1], imgs[0].shape[0], imgs[0].strides[0], pa, ptr(npts),
                                       ptr(P), C.byref(depth_params), ptr(kps), ptr(desc), ptr(depth), ptr(ur), cap, ptr(n)), ctx.handle)
     return [(kps[f, :n[f]].copy(), desc[f, :n[f]].copy(), depth[f, :n[f]].copy(), ur[f, :n[f]].copy()) for f in range(nF)]
+
+
+class RgblBatch:
+    """Reusable (pinned if torch+CUDA are available) host buffers for rgbl_frame_rgbl_batch / the resident API."""
+
+    def __init__(self, ctx: Context, images, clouds, P, depth_params: DepthParams, pinned=True):
+        self.ctx = ctx
+        nF = len(images); cap = ctx.cap
+        self.nF, self.cap = nF, cap
+        alloc = _pinned_alloc if pinned else (lambda shape, dt: np.empty(shape, dt))
+        H, W = images[0].shape
+        self.img = alloc((nF, H, W), np.uint8)
+        maxn = max(p.shape[1] for p in clouds)
+        self.pts = alloc((nF, 4 * maxn), np.float32)
+        self.npts = np.array([p.shape[1] for p in clouds], np.int32)
+        for f in range(nF):
+            self.img[f] = images[f]
+            self.pts[f, :4 * clouds[f].shape[1]] = np.ascontiguousarray(clouds[f], np.float32).reshape(-1)
+        self.ia = (C.c_void_p * nF)(*[self.img[f].ctypes.data for f in range(nF)])
+        self.pa = (C.c_void_p * nF)(*[self.pts[f].ctypes.data for f in range(nF)])
+        self.P = np.ascontiguousarray(P, np.float32).reshape(12)
+        self.prm = depth_params
+        self.kps = alloc((nF, cap), KP_DTYPE); self.desc = alloc((nF, cap, 32), np.uint8)
+        self.depth = alloc((nF, cap), np.float32); self.uright = alloc((nF, cap), np.float32)
+        self.n = np.zeros(nF, np.int32)
+        self.W, self.H = W, H
+        self.h2d_bytes = int(nF * W * H + 4 * 4 * int(self.npts.sum()))
+
+    def run_e2e(self):
+        """One end-to-end call with host buffers: H2D inputs + all kernels + D2H results."""
+        c = self.ctx
+        check(lib().rgbl_frame_rgbl_batch(c.handle, self.nF, self.ia, self.W, self.H, self.W, self.pa, ptr(self.npts), ptr(self.P),
+                                          C.byref(self.prm), ptr(self.kps), ptr(self.desc), ptr(self.depth), ptr(self.uright),
+                                          self.cap, ptr(self.n)), c.handle)
+        return self.n
+
+    def d2h_bytes(self) -> int:
+        return int(self.n.sum()) * (28 + 32 + 4 + 4)
+
+    def upload(self):
+        c = self.ctx
+        check(lib().rgbl_resident_upload(c.handle, self.nF, self.ia, self.W, self.H, self.W, self.pa, ptr(self.npts)), c.handle)
+
+    def process_resident(self):
+        c = self.ctx
+        check(lib().rgbl_resident_process(c.handle, ptr(self.P), C.byref(self.prm), ptr(self.n)), c.handle)
+        return self.n
+
+    def download(self):
+        c = self.ctx
+        check(lib().rgbl_resident_download(c.handle, ptr(self.kps), ptr(self.desc), ptr(self.depth), ptr(self.uright), self.cap, ptr(self.n)), c.handle)
+        return [(self.kps[f, :self.n[f]], self.desc[f, :self.n[f]], self.depth[f, :self.n[f]], self.uright[f, :self.n[f]]) for f in range(self.nF)]
+
+
+_pinned_keep = []
+
+
+def _pinned_alloc(shape, dtype):
+    """numpy view of page-locked memory (torch is only the allocator here)."""
+    import torch
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    _pinned_keep.append(t)
+    return t.numpy()[:nbytes].view(dtype).reshape(shape)

@@ -1,0 +1,125 @@
+"""CPU-side checks of the product library: it loads, exports every symbol include/rgbl_b200.h declares,
+fails loudly without a GPU, and its host-side pieces (tables, geometry, quad-tree, masks) match the oracle."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from orb_slam3_rgbl_b200 import _lib as L
+from orb_slam3_rgbl_b200 import frontend as F
+from orb_slam3_rgbl_b200 import synthetic as S
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = (ROOT / "include" / "rgbl_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rgbl_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    lib = C.CDLL(str(L.LIB_PATH))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"librgbl_b200.so does not export {name}"
+    assert declared == set(L.SYMBOLS), f"python binding out of sync: {declared ^ set(L.SYMBOLS)}"
+    assert L.lib().rgbl_abi_version() >= 1
+
+
+def test_no_cpu_fallback(have_gpu):
+    if have_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(L.RgblError) as e:
+        F.Context(S.KITTI_W, S.KITTI_H)
+    assert e.value.code == L.RGBL_E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    for p in (ROOT / "orb_slam3_rgbl_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cpp", ".h", ".cuh") and p.is_file():
+            txt = p.read_text(errors="ignore")
+            assert "import oracle" not in txt and "liborb_oracle" not in txt and "oracle/" not in txt, p
+
+
+@pytest.mark.parametrize("nf,sf,nl", [(2000, 1.2, 8), (1000, 1.2, 8), (4000, 1.2, 8), (1200, 1.5, 5), (500, 1.1, 12)])
+def test_orb_tables_match_oracle(nf, sf, nl):
+    t = F.orb_tables(nf, sf, nl)
+    ex = oracle.Extractor(nf, sf, nl)
+    assert (t["scale"] == ex.scale_factors).all() and (t["inv_scale"] == ex.inv_scale_factors).all()
+    assert (t["features_per_level"] == ex.features_per_level).all() and (t["umax"] == ex.umax).all()
+    assert list(t["umax"]) == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+
+
+def test_structuring_elements_match_reference_tables():
+    for kind in ("Rectangle", "Cross", "Ellipse"):
+        for ku, kv in ((3, 3), (5, 3), (7, 5), (9, 9), (1, 1), (4, 6)):
+            assert (F.structuring_element(kind, ku, kv) == S.structuring_element(kind, ku, kv)).all()
+    d5 = F.structuring_element("Diamond", 5)
+    assert d5.tolist() == [[0, 0, 1, 0, 0], [0, 1, 1, 1, 0], [1, 1, 1, 1, 1], [0, 1, 1, 1, 0], [0, 0, 1, 0, 0]]   # DepthModule.h:141-145
+    with pytest.raises(L.RgblError):
+        F.structuring_element("Diamond", 4)
+    with pytest.raises(L.RgblError):
+        F.structuring_element("Hexagon", 5)
+
+
+def test_descriptor_distance_is_popcount():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        a = rng.integers(0, 256, 32, dtype=np.uint8); b = rng.integers(0, 256, 32, dtype=np.uint8)
+        assert L.lib().rgbl_descriptor_distance(L.ptr(a), L.ptr(b)) == int(np.unpackbits(a ^ b).sum())
+    z = np.zeros(32, np.uint8); o = np.full(32, 255, np.uint8)
+    assert L.lib().rgbl_descriptor_distance(L.ptr(z), L.ptr(o)) == 256
+
+
+def _quadtree(cand, w, h, n):
+    out = np.empty(max(n + 3, 4 * max(1, round((w - 32) / (h - 32)))), np.int32)
+    m = L.lib().rgbl_quadtree_select(L.ptr(np.ascontiguousarray(cand, np.int32)), len(cand), 16, w - 16, 16, h - 16, n, L.ptr(out), len(out))
+    assert m >= 0
+    return out[:m]
+
+
+def _oracle_quadtree(cand, w, h, n):
+    k = np.zeros(len(cand), oracle.KP_DTYPE)
+    k["x"], k["y"], k["response"] = cand[:, 0], cand[:, 1], cand[:, 2]
+    return oracle.distribute_quadtree(k, 16, w - 16, 16, h - 16, n)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_quadtree_matches_oracle_on_real_candidates(seed):
+    img = S.make_image(100 + seed, 900, 300)
+    ex = oracle.Extractor(1500); ex(img)
+    for l in range(8):
+        cand = ex.level_candidates(l)
+        h, w = ex.level_image(l).shape
+        sel = cand[_quadtree(cand, w, h, int(ex.features_per_level[l]))]
+        ref = ex.level_keypoints(l)
+        assert len(sel) == len(ref)
+        assert (sel[:, 0] + 16 == ref["x"]).all() and (sel[:, 1] + 16 == ref["y"]).all() and (sel[:, 2] == ref["response"]).all()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_quadtree_matches_oracle_random(seed):
+    """Random candidate clouds incl. heavy score ties and tiny/huge budgets: the tie-sensitive paths
+    (std::sort order, first-max) must agree with the oracle's std::list restatement."""
+    rng = np.random.default_rng(seed)
+    w, h = int(rng.integers(120, 1300)), int(rng.integers(100, 420))
+    n = int(rng.integers(1, 6000))
+    xy = np.unique(np.stack([rng.integers(0, w - 32, n) // 2 * 2, rng.integers(0, h - 32, n) // 2 * 2], 1), axis=0)
+    order = np.lexsort((xy[:, 0], xy[:, 1]))             # row-major like cv::FAST
+    xy = xy[order]
+    sc = rng.integers(7, 12 if seed % 2 else 200, len(xy))
+    cand = np.concatenate([xy, sc[:, None]], 1).astype(np.int32)
+    for budget in (1, 5, 60, 434, 5000):
+        if round((w - 32) / (h - 32)) < 1:
+            continue
+        sel = cand[_quadtree(cand, w, h, budget)]
+        ref = _oracle_quadtree(cand, w, h, budget)
+        assert len(sel) == len(ref)
+        assert (sel[:, 0] == ref["x"]).all() and (sel[:, 1] == ref["y"]).all() and (sel[:, 2] == ref["response"]).all()
+
+
+def test_quadtree_empty_and_single():
+    assert len(_quadtree(np.zeros((0, 3), np.int32), 400, 200, 50)) == 0
+    one = np.array([[10, 10, 30]], np.int32)
+    assert _quadtree(one, 400, 200, 50).tolist() == [0]

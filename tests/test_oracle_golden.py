@@ -1,0 +1,124 @@
+"""Pin the C++ oracle against the committed cv2-generated fixtures (tests/golden/make_golden.py) and,
+when python-cv2 is importable, against cv2 live.  CPU only."""
+import hashlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from orb_slam3_rgbl_b200 import synthetic as S
+
+G = Path(__file__).resolve().parent / "golden"
+
+
+def sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", ["extract_kitti_seed2", "extract_small_seed9"])
+def test_extractor_against_cv2_fixture(name):
+    g = np.load(G / f"{name}.npz")
+    img = S.make_image(int(g["seed"]), int(g["W"]), int(g["H"]))
+    assert sha(img) == str(g["image_sha"]), "synthetic generator drifted: regenerate the fixtures"
+    ex = oracle.Extractor(int(g["nfeatures"]))
+    k, d, mono = ex(img)
+    for l in range(8):
+        lv = ex.level_image(l)
+        assert sha(lv) == str(g[f"level_sha{l}"]), f"pyramid level {l}"
+        assert sha(oracle.gaussian_blur7(lv)) == str(g[f"blur_sha{l}"]), f"blur level {l}"
+        assert (ex.level_candidates(l) == g[f"cand{l}"].astype(np.int32)).all(), f"FAST candidates level {l}"
+    gk = g["kps"]
+    assert len(k) == len(gk) == mono
+    for f in k.dtype.names:
+        assert (k[f] == gk[f]).all(), f
+    assert (d == g["desc"]).all()
+
+
+def test_depth_against_cv2_fixture():
+    g = np.load(G / "depth_kitti_seed2.npz")
+    W, H = int(g["W"]), int(g["H"])
+    pts = S.make_pointcloud(int(g["seed"]), 64, int(g["n_az"]))
+    assert sha(pts) == str(g["pts_sha"])
+    raw = oracle.depth_project(pts, g["P"], W, H)
+    assert sha(raw) == str(g["raw_sha"])
+    nz = g["raw_nonzero"].astype(int)
+    assert (raw[nz[:, 0], nz[:, 1]] == g["raw_vals"]).all()
+    for key in g.files:
+        if key.startswith("mask_"):
+            kind = key[len("mask_"):]
+            proc = oracle.depth_inverse_dilation(raw, g[key])
+            assert sha(proc) == str(g[f"proc_sha_{kind}"]), kind
+    proc = oracle.depth_inverse_dilation(raw, S.structuring_element("diamond", 5))
+    yx = g["probe_yx"].astype(int)
+    assert (proc[yx[:, 0], yx[:, 1]] == g["probe_vals"]).all()
+
+
+def test_fast_atan2_fixture():
+    g = np.load(G / "primitives.npz")
+    got = np.array([oracle.fast_atan2(y, x) for y, x in zip(g["atan_y"], g["atan_x"])], np.float32)
+    assert (got == g["atan_deg"]).all()
+
+
+# ---- live cv2 (same library family the reference links); skipped where cv2 is absent ----
+cv2 = pytest.importorskip("cv2", reason="python-cv2 not installed") if False else None
+try:
+    import cv2 as _cv2
+    import cv2_reference as R
+    HAVE = True
+except Exception:  # pragma: no cover
+    HAVE = False
+needs_cv2 = pytest.mark.skipif(not HAVE, reason="python-cv2 not installed")
+
+
+@needs_cv2
+@pytest.mark.parametrize("shape", [(1241, 376, 1034, 313), (346, 105, 288, 88), (640, 480, 533, 400), (67, 70, 56, 58)])
+def test_resize_live(shape):
+    sw, sh, dw, dh = shape
+    img = S.make_image(4, max(sw, 80), max(sh, 80))[:sh, :sw]
+    assert (oracle.resize_linear(img, dw, dh) == _cv2.resize(np.ascontiguousarray(img), (dw, dh), interpolation=_cv2.INTER_LINEAR)).all()
+
+
+@needs_cv2
+def test_blur_and_fast_live():
+    img = S.make_image(6, 500, 200)
+    assert (oracle.gaussian_blur7(img) == _cv2.GaussianBlur(img, (7, 7), 2, 2, borderType=_cv2.BORDER_REFLECT_101)).all()
+    rng = np.random.default_rng(0)
+    for th in (7, 12, 20):
+        det = _cv2.FastFeatureDetector_create(th, True, _cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+        for _ in range(40):
+            x, y = int(rng.integers(0, 440)), int(rng.integers(0, 150)); w, h = int(rng.integers(7, 50)), int(rng.integers(7, 50))
+            win = img[y:y + h, x:x + w]
+            ref = np.array([[int(p.pt[0]), int(p.pt[1]), int(p.response)] for p in det.detect(win)], np.int32).reshape(-1, 3)
+            got = oracle.fast_window(win, th)
+            assert got.shape == ref.shape and (got == ref).all()
+
+
+@needs_cv2
+def test_full_extractor_live():
+    img = S.make_image(13, 800, 300)
+    ex = oracle.Extractor(1200)
+    k, d, _ = ex(img)
+    k2, d2, per, rois = R.extract_cv2(img, oracle.distribute_quadtree, nfeatures=1200, quota=ex.features_per_level)
+    assert len(k) == len(k2) and all((k[f] == k2[f]).all() for f in k.dtype.names) and (d == d2).all()
+
+
+@needs_cv2
+def test_depth_live():
+    pts = S.make_pointcloud(5); P = S.lidar_projection_matrix()
+    raw = oracle.depth_project(pts, P, S.KITTI_W, S.KITTI_H)
+    assert (raw == R.project_cv2(pts, P, S.KITTI_W, S.KITTI_H)).all()
+    m = S.structuring_element("diamond", 7)
+    assert (oracle.depth_inverse_dilation(raw, m) == R.inverse_dilation_cv2(raw, m)).all()
+
+
+def test_glibc_sincos_is_what_the_descriptor_sees():
+    """The oracle's descriptor uses libm cosf/sinf (canonical semantics, SURVEY hard part 4)."""
+    img = S.make_image(1, 200, 200)
+    blur = oracle.gaussian_blur7(img)
+    kp = np.zeros(1, oracle.KP_DTYPE); kp["x"], kp["y"], kp["angle"] = 100, 100, 37.25
+    d0 = oracle.descriptor(kp[0], blur)
+    if HAVE:
+        d1 = R.descriptor_np(blur, 100, 100, 37.25, R.load_pattern())
+        assert (d0 == d1).all()
+    assert d0.shape == (32,)

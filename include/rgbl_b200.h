@@ -134,6 +134,58 @@ int rgbl_frame_rgbl_batch(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gra
                           const float* const* pts4xn, const int* n_pts, const float P[12], const rgbl_depth_params* prm,
                           rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out);
 
+/* ---- tracking-thread stages ------------------------------------------------------------------------ *
+ * The members of ORB_SLAM3::Frame the matchers read, for frames with Nleft == -1 (mono / stereo-rectified /
+ * RGB-D / RGB-L): mvKeysUn, mvuRight, mDescriptors, image bounds (src/Frame.cc:871-899), mvScaleFactors,
+ * calibration, mfLogScaleFactor.  The 64x48 grid (AssignFeaturesToGrid, src/Frame.cc:475-506) is rebuilt on
+ * the device from these.                                                                                  */
+typedef struct {
+    int32_t n;
+    const rgbl_keypoint* keys_un;
+    const float* uright;
+    const uint8_t* desc;
+    float min_x, max_x, min_y, max_y;
+    int32_t n_levels;
+    const float* scale_factors;
+    float fx, fy, cx, cy, bf;
+    float log_scale_factor;
+} rgbl_frame_view;
+
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, float th, bool bMono)
+ * (include/ORBmatcher.h:53, src/ORBmatcher.cc:1676-1887).  Poses are Sophus::SE3f as (qx,qy,qz,qw,tx,ty,tz).
+ * Last-frame map points i = 0..n_last-1 in LastFrame order: valid[i] = mvpMapPoints[i] != NULL &&
+ * !mvbOutlier[i]; xw = GetWorldPos(); mp_desc = GetDescriptor(); last_octave/last_angle = the last frame's
+ * keypoint; obs_pos[i] = Observations() > 0.  cur_state[i2] (nullable = all free): 0 free, 1 holds a point
+ * with Observations() > 0, 2 holds a point without observations.  match[i2]: >= 0 index i now assigned,
+ * -1 untouched, -2 cleared by the rotation-consistency check.  *n_matches = the reference's return value. */
+int rgbl_search_by_projection_last(rgbl_ctx* ctx, const rgbl_frame_view* cur, const float cur_pose[7], const float last_pose[7],
+                                   int n_last, const uint8_t* valid, const float* xw, const uint8_t* mp_desc,
+                                   const int32_t* last_octave, const float* last_angle, const uint8_t* obs_pos, float th, int mono,
+                                   int check_orientation, const uint8_t* cur_state, int32_t* match, int* n_matches);
+
+/* Frame::isInFrustum(MapPoint*, viewingCosLimit) for n map points (src/Frame.cc:602-664, Tracking.cc:3411).
+ * Rcw row-major, tcw, Ow = Frame::mRcw/mtcw/mOw; normal = GetNormal(); mf_min/max_dist = mfMinDistance /
+ * mfMaxDistance.  Outputs = mbTrackInView, mTrackProjX/Y/XR, mTrackDepth, mnTrackScaleLevel, mTrackViewCos. */
+int rgbl_is_in_frustum(rgbl_ctx* ctx, const rgbl_frame_view* cur, const float Rcw[9], const float tcw[3], const float Ow[3], int n,
+                       const float* xw, const float* normal, const float* mf_min_dist, const float* mf_max_dist, float cos_limit,
+                       uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, float* track_depth, int32_t* level, float* view_cos);
+
+/* ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, float th, bool bFarPoints, float thFarPoints)
+ * (include/ORBmatcher.h:49, src/ORBmatcher.cc:43-213).  in_view[i] = mbTrackInView && !isBad(); the mTrack*
+ * fields as filled by isInFrustum; nn_ratio = mfNNratio.  match/cur_state as above.                         */
+int rgbl_search_by_projection_local(rgbl_ctx* ctx, const rgbl_frame_view* cur, int n, const uint8_t* in_view, const float* proj_x,
+                                    const float* proj_y, const float* proj_xr, const float* track_depth, const int32_t* level,
+                                    const float* view_cos, const uint8_t* mp_desc, const uint8_t* obs_pos, float th, float nn_ratio,
+                                    int far_points, float th_far, const uint8_t* cur_state, int32_t* match, int* n_matches);
+
+/* Optimizer::PoseOptimization(Frame*) (include/Optimizer.h, src/Optimizer.cc:814-1114) for Nleft == -1 frames.
+ * One edge per keypoint that has a map point, in keypoint order: xw = GetWorldPos(), obs = (kpUn.x, kpUn.y,
+ * mvuRight[i]), inv_sigma2 = mvInvLevelSigma2[octave], stereo[i] = mvuRight[i] >= 0.  pose = Frame::GetPose().
+ * outlier[i] = mvbOutlier; *n_inliers = the return value (0 and pose unchanged if n < 3).                   */
+int rgbl_pose_optimize(rgbl_ctx* ctx, const float pose_in[7], int n, const float* xw, const float* obs, const float* inv_sigma2,
+                       const uint8_t* stereo, float fx, float fy, float cx, float cy, float bf, float pose_out[7], uint8_t* outlier,
+                       int* n_inliers);
+
 /* Resident form of the same work (device-throughput measurement, pipelined callers): inputs are
  * copied to HBM once, rgbl_resident_process can then be repeated with no host->device input traffic
  * and leaves its results in HBM until rgbl_resident_download.                                     */

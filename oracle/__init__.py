@@ -242,3 +242,118 @@ def depth_from_pcd(pts4xn, P, W, H, mask, bf, kps, kps_un, min_d=5.0, max_d=200.
     lib().orc_depth_from_pcd(_p(pts), pts.shape[1], _p(P), W, H, min_d, max_d, _p(mask), mask.shape[1], mask.shape[0],
                              bf, _p(kps), _p(kps_un), n, _p(d), _p(u), _p(raw), _p(proc))
     return d, u, raw, proc
+
+
+# ------------------------------------------------------------------------------------------------
+# ORBmatcher / Frame grid / Optimizer::PoseOptimization
+# ------------------------------------------------------------------------------------------------
+
+class FrameViewC(C.Structure):
+    _fields_ = [("n", C.c_int), ("keys_un", C.c_void_p), ("uright", C.c_void_p), ("desc", C.c_void_p),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("n_levels", C.c_int), ("scale_factors", C.c_void_p),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("log_scale_factor", C.c_float)]
+
+
+class FrameView:
+    """The members of ORB_SLAM3::Frame the tracking matchers read (Nleft == -1)."""
+
+    def __init__(self, keys_un, uright, desc, width, height, scale_factors, fx, fy, cx, cy, bf):
+        self.keys_un = np.ascontiguousarray(keys_un, KP_DTYPE)
+        self.uright = np.ascontiguousarray(uright, np.float32)
+        self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.scale_factors = np.ascontiguousarray(scale_factors, np.float32)
+        self.width, self.height = width, height
+        self.fx, self.fy, self.cx, self.cy, self.bf = fx, fy, cx, cy, bf
+        self.log_scale_factor = float(np.float32(np.log(np.float32(self.scale_factors[1]))))   # mfLogScaleFactor = log(mfScaleFactor)
+        self.c = FrameViewC(len(self.keys_un), _p(self.keys_un), _p(self.uright), _p(self.desc), 0.0, float(width), 0.0, float(height),
+                            len(self.scale_factors), _p(self.scale_factors), fx, fy, cx, cy, bf, self.log_scale_factor)
+
+
+_LATE_DECL_DONE = False
+
+
+def _late(L):
+    global _LATE_DECL_DONE
+    if _LATE_DECL_DONE:
+        return
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    fv = C.POINTER(FrameViewC)
+    L.orc_descriptor_distance.argtypes = [vp, vp]; L.orc_descriptor_distance.restype = i
+    L.orc_features_in_area.argtypes = [fv, f, f, f, i, i, vp, i]; L.orc_features_in_area.restype = i
+    L.orc_search_by_projection_last.argtypes = [fv, vp, vp, i, vp, vp, vp, vp, vp, vp, f, i, i, vp, vp]
+    L.orc_search_by_projection_last.restype = i
+    L.orc_is_in_frustum.argtypes = [fv, vp, vp, vp, i, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, vp, vp]
+    L.orc_search_by_projection_local.argtypes = [fv, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, f, f, i, f, vp, vp]
+    L.orc_search_by_projection_local.restype = i
+    L.orc_pose_optimize.argtypes = [vp, i, vp, vp, vp, vp, f, f, f, f, f, vp, vp]
+    L.orc_pose_optimize.restype = i
+    _LATE_DECL_DONE = True
+
+
+def descriptor_distance(a, b) -> int:
+    _late(lib())
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_descriptor_distance(_p(a), _p(b))
+
+
+def features_in_area(fv: FrameView, x, y, r, min_level=-1, max_level=-1) -> np.ndarray:
+    _late(lib())
+    out = np.empty(fv.c.n + 1, np.int32)
+    n = lib().orc_features_in_area(C.byref(fv.c), x, y, r, min_level, max_level, _p(out), len(out))
+    return out[:n].copy()
+
+
+def search_by_projection_last(cur: FrameView, cur_pose, last_pose, valid, xw, mp_desc, last_octave, last_angle, obs_pos,
+                              th, mono=False, check_orientation=True, cur_state=None):
+    _late(lib())
+    n_last = len(valid)
+    cur_pose = np.ascontiguousarray(cur_pose, np.float32); last_pose = np.ascontiguousarray(last_pose, np.float32)
+    valid = np.ascontiguousarray(valid, np.uint8); xw = np.ascontiguousarray(xw, np.float32).reshape(-1, 3)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8); last_octave = np.ascontiguousarray(last_octave, np.int32)
+    last_angle = np.ascontiguousarray(last_angle, np.float32); obs_pos = np.ascontiguousarray(obs_pos, np.uint8)
+    cs = np.zeros(cur.c.n, np.uint8) if cur_state is None else np.ascontiguousarray(cur_state, np.uint8)
+    match = np.empty(cur.c.n, np.int32)
+    nm = lib().orc_search_by_projection_last(C.byref(cur.c), _p(cur_pose), _p(last_pose), n_last, _p(valid), _p(xw), _p(mp_desc),
+                                             _p(last_octave), _p(last_angle), _p(obs_pos), th, int(mono), int(check_orientation),
+                                             _p(cs), _p(match))
+    return nm, match
+
+
+def is_in_frustum(fv: FrameView, Rcw, tcw, Ow, xw, normal, mf_min_dist, mf_max_dist, cos_limit=0.5):
+    _late(lib())
+    n = len(xw)
+    Rcw = np.ascontiguousarray(Rcw, np.float32); tcw = np.ascontiguousarray(tcw, np.float32); Ow = np.ascontiguousarray(Ow, np.float32)
+    xw = np.ascontiguousarray(xw, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+    mn = np.ascontiguousarray(mf_min_dist, np.float32); mx = np.ascontiguousarray(mf_max_dist, np.float32)
+    out = dict(in_view=np.empty(n, np.uint8), proj_x=np.empty(n, np.float32), proj_y=np.empty(n, np.float32),
+               proj_xr=np.empty(n, np.float32), depth=np.empty(n, np.float32), level=np.empty(n, np.int32), view_cos=np.empty(n, np.float32))
+    lib().orc_is_in_frustum(C.byref(fv.c), _p(Rcw), _p(tcw), _p(Ow), n, _p(xw), _p(normal), _p(mn), _p(mx), cos_limit,
+                            _p(out["in_view"]), _p(out["proj_x"]), _p(out["proj_y"]), _p(out["proj_xr"]), _p(out["depth"]),
+                            _p(out["level"]), _p(out["view_cos"]))
+    return out
+
+
+def search_by_projection_local(fv: FrameView, tr: dict, mp_desc, obs_pos, th, nn_ratio=0.8, far_points=False, th_far=0.0, cur_state=None):
+    _late(lib())
+    n = len(tr["in_view"])
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8); obs_pos = np.ascontiguousarray(obs_pos, np.uint8)
+    cs = np.zeros(fv.c.n, np.uint8) if cur_state is None else np.ascontiguousarray(cur_state, np.uint8)
+    match = np.empty(fv.c.n, np.int32)
+    nm = lib().orc_search_by_projection_local(C.byref(fv.c), n, _p(tr["in_view"]), _p(tr["proj_x"]), _p(tr["proj_y"]), _p(tr["proj_xr"]),
+                                              _p(tr["depth"]), _p(tr["level"]), _p(tr["view_cos"]), _p(mp_desc), _p(obs_pos), th, nn_ratio,
+                                              int(far_points), th_far, _p(cs), _p(match))
+    return nm, match
+
+
+def pose_optimize(pose, xw, obs, inv_sigma2, stereo, fx, fy, cx, cy, bf):
+    """-> (n_inliers, pose_out[7], outlier[n])"""
+    _late(lib())
+    pose = np.ascontiguousarray(pose, np.float32); xw = np.ascontiguousarray(xw, np.float32).reshape(-1, 3)
+    obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 3); inv_sigma2 = np.ascontiguousarray(inv_sigma2, np.float32)
+    stereo = np.ascontiguousarray(stereo, np.uint8)
+    n = len(xw)
+    out = np.empty(7, np.float32); outlier = np.zeros(n, np.uint8)
+    r = lib().orc_pose_optimize(_p(pose), n, _p(xw), _p(obs), _p(inv_sigma2), _p(stereo), fx, fy, cx, cy, bf, _p(out), _p(outlier))
+    return r, out, outlier

@@ -33,6 +33,14 @@ class DepthParams(C.Structure):
                 ("mask", C.c_uint8 * 81), ("avg_kernel", C.c_int32), ("nn_search_radius", C.c_float)]
 
 
+class FrameViewC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys_un", C.c_void_p), ("uright", C.c_void_p), ("desc", C.c_void_p),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("n_levels", C.c_int32), ("scale_factors", C.c_void_p),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("log_scale_factor", C.c_float)]
+
+
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("max_batch", C.c_int32),
                 ("max_points", C.c_int32), ("max_candidates", C.c_int32), ("orb", OrbParams)]
@@ -68,6 +76,10 @@ SYMBOLS = {
     "rgbl_depth_from_pcd": (_i, [_vp, _vp, _i, _vp, _i, _i, C.POINTER(DepthParams), _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "rgbl_depth_structuring_element": (_i, [C.c_char_p, _i, _i, _vp]),
     "rgbl_frame_rgbl_batch": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(DepthParams), _vp, _vp, _vp, _vp, _i, _vp]),
+    "rgbl_search_by_projection_last": (_i, [_vp, C.POINTER(FrameViewC), _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _ip]),
+    "rgbl_is_in_frustum": (_i, [_vp, C.POINTER(FrameViewC), _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rgbl_search_by_projection_local": (_i, [_vp, C.POINTER(FrameViewC), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, _vp, _vp, _ip]),
+    "rgbl_pose_optimize": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _vp, _vp, _ip]),
     "rgbl_resident_upload": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "rgbl_resident_process": (_i, [_vp, _vp, C.POINTER(DepthParams), _vp]),
     "rgbl_resident_download": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),

@@ -11,82 +11,11 @@
 #include <thread>
 #include <vector>
 
-#include "rgbl_kernels.h"
+#include "rgbl_ctx.h"
 
 namespace rgbl {
 
 static thread_local std::string g_create_error;
-
-enum Stage { ST_PYRAMID = 0, ST_FAST, ST_COMPACT, ST_BLUR, ST_DESCRIBE, ST_DEPTH_PROJECT, ST_DEPTH_DILATE, ST_DEPTH_GATHER,
-             ST_MATCH, ST_POSE, kNumStages };
-static const char* kStageNames[kNumStages] = {"pyramid", "fast", "compact", "blur", "describe", "depth_project",
-                                              "depth_resolve_dilate", "depth_gather", "match", "pose"};
-
-struct Ctx {
-    rgbl_config cfg{};
-    OrbTables tab{};
-    std::vector<LevelGeom> levels;
-    std::vector<CellInfo> cells;
-    std::vector<LinCoef> coefs;
-    size_t frame_bytes = 0;
-    int n_cells = 0;
-    int cap_kp = 0;              // keypoints per frame capacity (nfeatures + 3 per level)
-    int dense_cap = 0;           // candidates per batch capacity
-    std::string err;
-
-    cudaStream_t st = nullptr, st_aux = nullptr;
-    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
-
-    // device
-    LevelGeom* d_levels = nullptr;
-    CellInfo* d_cells = nullptr;
-    LinCoef* d_coefs = nullptr;
-    uint8_t *d_pyr = nullptr, *d_blur = nullptr;
-    uint32_t* d_slots = nullptr;
-    int *d_counts = nullptr, *d_cell_off = nullptr, *d_level_cnt = nullptr, *d_frame_total = nullptr, *d_overflow = nullptr;
-    uint32_t* d_dense = nullptr;
-    SelKp* d_sel = nullptr;
-    int* d_n_sel = nullptr;
-    rgbl_keypoint *d_kps = nullptr, *d_kps_un = nullptr, *d_kps_in = nullptr;
-    int* d_n_kp_in = nullptr;
-    uint8_t* d_desc = nullptr;
-    float* d_pts = nullptr;
-    int* d_n_pts = nullptr;
-    uint32_t* d_idx_map = nullptr;
-    float *d_raw = nullptr, *d_processed = nullptr, *d_depth = nullptr, *d_uright = nullptr;
-    uint8_t* d_scratch = nullptr;   // padded-level export
-    size_t scratch_bytes = 0;
-    uint32_t stamp = 0;
-
-    // pinned host
-    int *h_level_cnt = nullptr, *h_frame_total = nullptr, *h_overflow = nullptr, *h_n_sel = nullptr, *h_n_pts = nullptr;
-    uint32_t* h_dense = nullptr;
-    SelKp* h_sel = nullptr;
-
-    // profiling (rgbl_profile_*): CUDA events on the launching stream around every stage
-    bool prof_on = false;
-    cudaEvent_t ev_b[kNumStages] = {}, ev_e[kNumStages] = {};
-    bool st_used[kNumStages] = {};
-    int st_pending_launches[kNumStages] = {};
-    double st_ms[kNumStages] = {};
-    long st_launches[kNumStages] = {};
-    long st_calls[kNumStages] = {};
-    double host_quadtree_ms = 0.0;
-    long total_launches = 0;
-
-    int last_frames = 0;         // frames valid in the device buffers
-    int resident_frames = 0, resident_max_pts = 0;
-    bool blur_valid = false;
-};
-
-#define CU(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) {                                                                   \
-            c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
-            return RGBL_E_CUDA;                                                                    \
-        }                                                                                          \
-    } while (0)
 
 template <class T>
 static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
@@ -101,7 +30,8 @@ static void release(Ctx* c) {
                    c->d_kps_un, c->d_desc, c->d_pts, c->d_n_pts, c->d_idx_map, c->d_raw, c->d_processed, c->d_depth,
                    c->d_uright, c->d_scratch, c->d_kps_in, c->d_n_kp_in};
     for (void* p : dev) if (p) cudaFree(p);
-    void* host[] = {c->h_level_cnt, c->h_frame_total, c->h_overflow, c->h_n_sel, c->h_n_pts, c->h_dense, c->h_sel};
+    c->trk.release();
+    void* host[] = {c->h_scalars, c->h_level_cnt, c->h_frame_total, c->h_overflow, c->h_n_sel, c->h_n_pts, c->h_dense, c->h_sel};
     for (void* p : host) if (p) cudaFreeHost(p);
     for (int i = 0; i < kNumStages; ++i) { if (c->ev_b[i]) cudaEventDestroy(c->ev_b[i]); if (c->ev_e[i]) cudaEventDestroy(c->ev_e[i]); }
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -185,6 +115,7 @@ static int create(const rgbl_config* cfg, Ctx** out) {
     }
     c->scratch_bytes = (size_t)(cfg->width + 2 * kEdgeThreshold + 64) * (cfg->height + 2 * kEdgeThreshold);
     CUF(dmalloc(&c->d_scratch, c->scratch_bytes));
+    CUF(hmalloc(&c->h_scalars, 16));
     CUF(hmalloc(&c->h_level_cnt, (size_t)B * RGBL_MAX_LEVELS));
     CUF(hmalloc(&c->h_frame_total, (size_t)B));
     CUF(hmalloc(&c->h_overflow, 1));
@@ -197,16 +128,16 @@ static int create(const rgbl_config* cfg, Ctx** out) {
 }
 
 // ---- profiling helpers -----------------------------------------------------------------------------
-static inline void stage_begin(Ctx* c, int stage, cudaStream_t st) {
+void stage_begin(Ctx* c, int stage, cudaStream_t st) {
     if (c->prof_on) { cudaEventRecord(c->ev_b[stage], st); c->st_used[stage] = true; }
 }
-static inline void stage_end(Ctx* c, int stage, cudaStream_t st, int launches) {
+void stage_end(Ctx* c, int stage, cudaStream_t st, int launches) {
     c->total_launches += launches;
     c->st_pending_launches[stage] += launches;
     if (c->prof_on) cudaEventRecord(c->ev_e[stage], st);
 }
 // call after both streams are idle
-static void prof_collect(Ctx* c) {
+void prof_collect(Ctx* c) {
     for (int i = 0; i < kNumStages; ++i) {
         if (c->prof_on && c->st_used[i]) {
             float ms = 0.f;

@@ -1,0 +1,269 @@
+// C ABI entry points of the tracking-thread stages: ORBmatcher::SearchByProjection (x2), Frame::isInFrustum and
+// Optimizer::PoseOptimization.  MapPoint* / Frame objects of the reference are flat arrays here (the C++ shim
+// gathers them); all compute runs on the context's CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "rgbl_ctx.h"
+
+namespace rgbl {
+
+template <class T>
+static bool grow(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return true;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    const size_t n = need + need / 4 + 64;
+    if (cudaMalloc((void**)p, n * sizeof(T)) != cudaSuccess) { *cap = 0; return false; }
+    *cap = n;
+    return true;
+}
+
+#define GROW(ptr, capvar, need) do { if (!grow(&(ptr), &(capvar), (size_t)(need))) { c->err = "cudaMalloc failed (tracking scratch)"; return RGBL_E_CUDA; } } while (0)
+
+static int ensure_frame(Ctx* c, int n_frame) {
+    TrackBufs& t = c->trk;
+    GROW(t.keys, t.cap_keys, n_frame); GROW(t.uright, t.cap_uright, n_frame); GROW(t.desc, t.cap_desc, (size_t)n_frame * 32);
+    GROW(t.csr_idx, t.cap_csr, n_frame); GROW(t.kp_cell, t.cap_kpcell, n_frame); GROW(t.state, t.cap_state, n_frame);
+    GROW(t.match, t.cap_match, n_frame); GROW(t.minq, t.cap_minq, n_frame);
+    GROW(t.cell_start, t.cap_cellstart, kGridCols * kGridRows + 1);
+    GROW(t.scalars, t.cap_scalars, 16);
+    return RGBL_OK;
+}
+
+static int ensure_queries(Ctx* c, int n_q) {
+    TrackBufs& t = c->trk;
+    GROW(t.lists, t.cap_lists, (size_t)n_q * kMatchListCap); GROW(t.list_n, t.cap_listn, n_q);
+    GROW(t.choice, t.cap_choice, n_q); GROW(t.resolved, t.cap_resolved, n_q);
+    GROW(t.q_u8a, t.cap_q_u8a, n_q); GROW(t.q_u8b, t.cap_q_u8b, n_q); GROW(t.q_desc, t.cap_q_desc, (size_t)n_q * 32);
+    GROW(t.q_f3a, t.cap_q_f3a, (size_t)n_q * 3); GROW(t.q_f3b, t.cap_q_f3b, (size_t)n_q * 3);
+    for (int k = 0; k < 7; ++k) GROW(t.q_f[k], t.cap_q_f[k], n_q);
+    GROW(t.q_i, t.cap_q_i, n_q);
+    return RGBL_OK;
+}
+
+// uploads the frame view and builds its 64x48 grid; fills FrameDev
+static int upload_frame(Ctx* c, const rgbl_frame_view* v, FrameDev& f) {
+    if (!v || v->n < 0 || (v->n > 0 && (!v->keys_un || !v->uright || !v->desc)) || !v->scale_factors || v->n_levels < 1 || v->n_levels > RGBL_MAX_LEVELS) {
+        c->err = "bad frame view"; return RGBL_E_INVALID;
+    }
+    int rc = ensure_frame(c, std::max(v->n, 1)); if (rc) return rc;
+    TrackBufs& t = c->trk;
+    if (v->n) {
+        CU(cudaMemcpyAsync(t.keys, v->keys_un, (size_t)v->n * sizeof(rgbl_keypoint), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.uright, v->uright, (size_t)v->n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.desc, v->desc, (size_t)v->n * 32, cudaMemcpyHostToDevice, c->st));
+    }
+    c->h_scalars[0] = v->n;
+    CU(cudaMemcpyAsync(t.scalars, c->h_scalars, sizeof(int), cudaMemcpyHostToDevice, c->st));
+    f.n = t.scalars; f.keys = t.keys; f.uright = t.uright; f.desc = t.desc;
+    f.min_x = v->min_x; f.max_x = v->max_x; f.min_y = v->min_y; f.max_y = v->max_y;
+    f.inv_w = static_cast<float>(kGridCols) / static_cast<float>(v->max_x - v->min_x);      // src/Frame.cc:351-352
+    f.inv_h = static_cast<float>(kGridRows) / static_cast<float>(v->max_y - v->min_y);
+    f.n_levels = v->n_levels;
+    for (int l = 0; l < v->n_levels; ++l) f.scale[l] = v->scale_factors[l];
+    f.fx = v->fx; f.fy = v->fy; f.cx = v->cx; f.cy = v->cy; f.bf = v->bf;
+    f.mb = v->bf / v->fx;                                                                     // src/Frame.cc:360
+    f.log_scale_factor = v->log_scale_factor;
+    stage_begin(c, ST_MATCH, c->st);
+    launch_grid_build(c->st, f, t.cell_start, t.csr_idx, t.kp_cell);
+    return RGBL_OK;
+}
+
+static MatchScratch scratch(Ctx* c) {
+    TrackBufs& t = c->trk;
+    MatchScratch s;
+    s.lists = t.lists; s.list_cap = kMatchListCap; s.list_n = t.list_n; s.minq = t.minq; s.choice = t.choice; s.resolved = t.resolved;
+    s.overflow = c->d_overflow; s.rounds = t.scalars + 2;
+    return s;
+}
+
+// Sophus::SE3f helpers on the host (float32, compiled with -ffp-contract=off): so3.hpp:358-366, se3.hpp inverse()
+static void h_rotate(const float* T, const float p[3], float out[3]) {
+    const float qx = T[0], qy = T[1], qz = T[2], qw = T[3];
+    float uv[3] = {qy * p[2] - qz * p[1], qz * p[0] - qx * p[2], qx * p[1] - qy * p[0]};
+    uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+    const float cr[3] = {qy * uv[2] - qz * uv[1], qz * uv[0] - qx * uv[2], qx * uv[1] - qy * uv[0]};
+    for (int i = 0; i < 3; ++i) out[i] = (p[i] + qw * uv[i]) + cr[i];
+}
+
+static int finish_search(Ctx* c, int n_frame, int32_t* match, int* n_matches) {
+    TrackBufs& t = c->trk;
+    stage_end(c, ST_MATCH, c->st, 3);
+    CU(cudaGetLastError());
+    if (n_frame) CU(cudaMemcpyAsync(match, t.match, (size_t)n_frame * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(c->h_scalars + 4, t.scalars + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    prof_collect(c);
+    if (*c->h_overflow) {
+        cudaMemsetAsync(c->d_overflow, 0, sizeof(int), c->st);
+        c->err = "matcher candidate list overflow (> 512 admissible candidates for one map point)";
+        return RGBL_E_CAPACITY;
+    }
+    if (n_matches) *n_matches = c->h_scalars[4];
+    c->last_match_rounds = c->h_scalars[5];
+    return RGBL_OK;
+}
+
+}  // namespace rgbl
+
+using namespace rgbl;
+
+extern "C" {
+
+int rgbl_search_by_projection_last(rgbl_ctx* ctx, const rgbl_frame_view* cur, const float cur_pose[7], const float last_pose[7],
+                                   int n_last, const uint8_t* valid, const float* xw, const uint8_t* mp_desc,
+                                   const int32_t* last_octave, const float* last_angle, const uint8_t* obs_pos, float th, int mono,
+                                   int check_orientation, const uint8_t* cur_state, int32_t* match, int* n_matches) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!cur || !cur_pose || !last_pose || n_last < 0 || !match || (n_last > 0 && (!valid || !xw || !mp_desc || !last_octave || !last_angle || !obs_pos))) { c->err = "null argument"; return RGBL_E_INVALID; }
+    CU(cudaSetDevice(c->cfg.device));
+    FrameDev f;
+    int rc = upload_frame(c, cur, f); if (rc) return rc;
+    rc = ensure_queries(c, std::max(n_last, 1)); if (rc) return rc;
+    TrackBufs& t = c->trk;
+    if (n_last) {
+        CU(cudaMemcpyAsync(t.q_u8a, valid, n_last, cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_f3a, xw, (size_t)n_last * 3 * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_desc, mp_desc, (size_t)n_last * 32, cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_i, last_octave, (size_t)n_last * sizeof(int), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_f[0], last_angle, (size_t)n_last * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_u8b, obs_pos, n_last, cudaMemcpyHostToDevice, c->st));
+    }
+    if (cur->n) {
+        if (cur_state) CU(cudaMemcpyAsync(t.state, cur_state, cur->n, cudaMemcpyHostToDevice, c->st));
+        else CU(cudaMemsetAsync(t.state, 0, cur->n, c->st));
+    }
+    SearchLastParams prm;
+    std::memcpy(prm.cur_pose, cur_pose, 7 * sizeof(float));
+    prm.th = th; prm.check_orientation = check_orientation;
+    {   // bForward / bBackward, src/ORBmatcher.cc:1686-1693
+        float inv[7] = {-cur_pose[0], -cur_pose[1], -cur_pose[2], cur_pose[3], 0, 0, 0};
+        const float nt[3] = {cur_pose[4] * -1.f, cur_pose[5] * -1.f, cur_pose[6] * -1.f};
+        float twc[3], r[3];
+        h_rotate(inv, nt, twc);
+        h_rotate(last_pose, twc, r);
+        const float tlc_z = r[2] + last_pose[6];
+        prm.forward = (tlc_z > f.mb && !mono) ? 1 : 0;
+        prm.backward = (-tlc_z > f.mb && !mono) ? 1 : 0;
+    }
+    LastFrameDev lf{n_last, t.q_u8a, t.q_f3a, t.q_desc, t.q_i, t.q_f[0], t.q_u8b};
+    if (n_last == 0) { CU(cudaMemsetAsync(t.match, 0xff, (size_t)std::max(cur->n, 1) * sizeof(int), c->st)); CU(cudaMemsetAsync(t.scalars + 1, 0, 2 * sizeof(int), c->st)); }
+    launch_search_last(c->st, f, t.cell_start, t.csr_idx, lf, prm, scratch(c), t.state, t.match, t.scalars + 1);
+    return finish_search(c, cur->n, match, n_matches);
+}
+
+int rgbl_is_in_frustum(rgbl_ctx* ctx, const rgbl_frame_view* cur, const float Rcw[9], const float tcw[3], const float Ow[3], int n,
+                       const float* xw, const float* normal, const float* mf_min_dist, const float* mf_max_dist, float cos_limit,
+                       uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, float* track_depth, int32_t* level, float* view_cos) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!cur || !Rcw || !tcw || !Ow || n < 0 || (n > 0 && (!xw || !normal || !mf_min_dist || !mf_max_dist || !in_view || !proj_x || !proj_y || !proj_xr || !track_depth || !level || !view_cos))) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (n == 0) return RGBL_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = ensure_queries(c, n); if (rc) return rc;
+    TrackBufs& t = c->trk;
+    FrameDev f{};
+    f.min_x = cur->min_x; f.max_x = cur->max_x; f.min_y = cur->min_y; f.max_y = cur->max_y;
+    f.n_levels = cur->n_levels; f.fx = cur->fx; f.fy = cur->fy; f.cx = cur->cx; f.cy = cur->cy; f.bf = cur->bf;
+    f.log_scale_factor = cur->log_scale_factor;
+    FrustumParams prm;
+    std::memcpy(prm.Rcw, Rcw, 9 * sizeof(float)); std::memcpy(prm.tcw, tcw, 3 * sizeof(float)); std::memcpy(prm.Ow, Ow, 3 * sizeof(float));
+    prm.cos_limit = cos_limit;
+    CU(cudaMemcpyAsync(t.q_f3a, xw, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.q_f3b, normal, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.q_f[4], mf_min_dist, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.q_f[5], mf_max_dist, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    stage_begin(c, ST_MATCH, c->st);
+    launch_frustum(c->st, f, prm, n, t.q_f3a, t.q_f3b, t.q_f[4], t.q_f[5], t.q_u8a, t.q_f[0], t.q_f[1], t.q_f[2], t.q_f[3], t.q_i, t.q_f[6]);
+    stage_end(c, ST_MATCH, c->st, 1);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(in_view, t.q_u8a, n, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(proj_x, t.q_f[0], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(proj_y, t.q_f[1], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(proj_xr, t.q_f[2], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(track_depth, t.q_f[3], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(level, t.q_i, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(view_cos, t.q_f[6], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    prof_collect(c);
+    return RGBL_OK;
+}
+
+int rgbl_search_by_projection_local(rgbl_ctx* ctx, const rgbl_frame_view* cur, int n, const uint8_t* in_view, const float* proj_x,
+                                    const float* proj_y, const float* proj_xr, const float* track_depth, const int32_t* level,
+                                    const float* view_cos, const uint8_t* mp_desc, const uint8_t* obs_pos, float th, float nn_ratio,
+                                    int far_points, float th_far, const uint8_t* cur_state, int32_t* match, int* n_matches) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!cur || n < 0 || !match || (n > 0 && (!in_view || !proj_x || !proj_y || !proj_xr || !track_depth || !level || !view_cos || !mp_desc || !obs_pos))) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (!(nn_ratio > 0.f)) { c->err = "nn_ratio must be > 0"; return RGBL_E_INVALID; }
+    CU(cudaSetDevice(c->cfg.device));
+    FrameDev f;
+    int rc = upload_frame(c, cur, f); if (rc) return rc;
+    rc = ensure_queries(c, std::max(n, 1)); if (rc) return rc;
+    TrackBufs& t = c->trk;
+    if (n) {
+        CU(cudaMemcpyAsync(t.q_u8a, in_view, n, cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_f[0], proj_x, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_f[1], proj_y, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_f[2], proj_xr, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_f[3], track_depth, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_i, level, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_f[4], view_cos, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_desc, mp_desc, (size_t)n * 32, cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_u8b, obs_pos, n, cudaMemcpyHostToDevice, c->st));
+    }
+    if (cur->n) {
+        if (cur_state) CU(cudaMemcpyAsync(t.state, cur_state, cur->n, cudaMemcpyHostToDevice, c->st));
+        else CU(cudaMemsetAsync(t.state, 0, cur->n, c->st));
+    }
+    SearchLocalParams prm;
+    prm.th = th; prm.nn_ratio = nn_ratio; prm.th_far = th_far; prm.far_points = far_points;
+    prm.use_factor = (th != 1.0) ? 1 : 0;                                         // bFactor, src/ORBmatcher.cc:47
+    // a second-best beyond TH_HIGH / nnratio can never reject: best <= TH_HIGH < nnratio * second
+    prm.keep_max = std::min(256, (int)std::floor((float)100 / nn_ratio) + 1);
+    LocalPointsDev lp{n, t.q_u8a, t.q_f[0], t.q_f[1], t.q_f[2], t.q_f[3], t.q_i, t.q_f[4], t.q_desc, t.q_u8b};
+    if (n == 0) { CU(cudaMemsetAsync(t.match, 0xff, (size_t)std::max(cur->n, 1) * sizeof(int), c->st)); CU(cudaMemsetAsync(t.scalars + 1, 0, 2 * sizeof(int), c->st)); }
+    launch_search_local(c->st, f, t.cell_start, t.csr_idx, lp, prm, scratch(c), t.state, t.match, t.scalars + 1);
+    return finish_search(c, cur->n, match, n_matches);
+}
+
+int rgbl_pose_optimize(rgbl_ctx* ctx, const float pose_in[7], int n, const float* xw, const float* obs, const float* inv_sigma2,
+                       const uint8_t* stereo, float fx, float fy, float cx, float cy, float bf, float pose_out[7], uint8_t* outlier,
+                       int* n_inliers) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!pose_in || !pose_out || n < 0 || !n_inliers || (n > 0 && (!xw || !obs || !inv_sigma2 || !stereo || !outlier))) { c->err = "null argument"; return RGBL_E_INVALID; }
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = ensure_queries(c, std::max(n, 1)); if (rc) return rc;
+    rc = ensure_frame(c, 1); if (rc) return rc;
+    TrackBufs& t = c->trk;
+    GROW(t.pose_work, t.cap_pose_work, (size_t)std::max(n, 1) * 3);
+    if (n) {
+        CU(cudaMemcpyAsync(t.q_f3a, xw, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_f3b, obs, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_f[0], inv_sigma2, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_u8a, stereo, n, cudaMemcpyHostToDevice, c->st));
+    }
+    PoseProblemDev p;
+    p.n = n; p.xw = t.q_f3a; p.obs = t.q_f3b; p.inv_sigma2 = t.q_f[0]; p.stereo = t.q_u8a;
+    p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf;
+    std::memcpy(p.pose_in, pose_in, 7 * sizeof(float));
+    stage_begin(c, ST_POSE, c->st);
+    launch_pose_optimize(c->st, p, t.pose_work, t.q_u8b, t.resolved, t.q_f[1], reinterpret_cast<int*>(t.scalars + 8));
+    stage_end(c, ST_POSE, c->st, 1);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pose_out, t.q_f[1], 7 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    if (n >= 3) CU(cudaMemcpyAsync(outlier, t.resolved, n, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(c->h_scalars + 8, t.scalars + 8, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    prof_collect(c);
+    *n_inliers = c->h_scalars[8];
+    return RGBL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,438 @@
+// Tracking-thread matcher kernels for sm_100a.
+//   grid build          Frame::AssignFeaturesToGrid / PosInGrid          src/Frame.cc:475-506, 815-825
+//   candidate search    Frame::GetFeaturesInArea + DescriptorDistance    src/Frame.cc:747-813, src/ORBmatcher.cc:2058-2074
+//   SearchByProjection(CurrentFrame, LastFrame, th, bMono)               src/ORBmatcher.cc:1676-1887
+//   SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints)      src/ORBmatcher.cc:43-213
+//   Frame::isInFrustum + MapPoint::PredictScale                          src/Frame.cc:602-664, src/MapPoint.cc:531-545
+//
+// The reference loops are sequential and greedy: a feature claimed by an earlier map point (with
+// Observations() > 0) is skipped by later ones, so results depend on iteration order.  Here the
+// distance work is data-parallel (one warp per query, __popc Hamming over the 64x48 grid's CSR
+// ranges) and the greedy order is reproduced afterwards by an exact "serial dictatorship" resolution:
+// in rounds, every unresolved query proposes its best still-available candidate and becomes final
+// as soon as no lower-indexed unresolved query can still take (any of) the candidates its decision
+// depends on.  The lowest unresolved query is always final, so the loop terminates; on real data a
+// handful of rounds suffice.  Candidate order (which decides ties) is the reference's: grid column,
+// then row, then keypoint index = ascending position in the column-major CSR.
+#include <cfloat>
+
+#include "rgbl_device.cuh"
+#include "rgbl_kernels.h"
+
+namespace rgbl {
+
+constexpr int kGridCells = kGridCols * kGridRows;
+constexpr int kThHigh = 100;          // ORBmatcher::TH_HIGH
+constexpr int kHistoLength = 30;      // ORBmatcher::HISTO_LENGTH
+constexpr uint32_t kPosMask = (1u << 20) - 1u;
+
+// ---- grid --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int* __restrict__ cell_start /*kGridCells+1*/,
+                                                          int* __restrict__ csr_idx, int* __restrict__ kp_cell) {
+    __shared__ int cnt[kGridCells];
+    __shared__ int off[kGridCells + 1];
+    const int tid = threadIdx.x;
+    const int n = *f.n;
+    for (int c = tid; c < kGridCells; c += 1024) cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const rgbl_keypoint kp = f.keys[i];
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(kp.x, f.min_x), f.inv_w));
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(kp.y, f.min_y), f.inv_h));
+        int c = -1;
+        if (px >= 0 && px < kGridCols && py >= 0 && py < kGridRows) { c = px * kGridRows + py; atomicAdd(&cnt[c], 1); }
+        kp_cell[i] = c;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int s = 0;
+        for (int c = 0; c < kGridCells; ++c) { off[c] = s; s += cnt[c]; }
+        off[kGridCells] = s;
+    }
+    __syncthreads();
+    for (int c = tid; c <= kGridCells; c += 1024) cell_start[c] = off[c];
+    for (int c = tid; c < kGridCells; c += 1024) cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const int c = kp_cell[i];
+        if (c >= 0) csr_idx[off[c] + atomicAdd(&cnt[c], 1)] = i;
+    }
+    __syncthreads();
+    // insertion order inside a cell is ascending keypoint index: sort each (tiny) cell list
+    for (int c = tid; c < kGridCells; c += 1024) {
+        const int b = off[c], e = off[c + 1];
+        for (int a = b + 1; a < e; ++a) {
+            const int v = csr_idx[a];
+            int k = a - 1;
+            while (k >= b && csr_idx[k] > v) { csr_idx[k + 1] = csr_idx[k]; --k; }
+            csr_idx[k + 1] = v;
+        }
+    }
+}
+
+// ---- shared helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint8_t* __restrict__ b) {
+    const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(b)), b1 = __ldg(reinterpret_cast<const uint4*>(b) + 1);
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+struct CellRange { int min_cx, max_cx, min_cy, max_cy; bool ok; };
+
+__device__ __forceinline__ CellRange cell_range(const FrameDev& f, float x, float y, float r) {
+    CellRange c; c.ok = false;
+    c.min_cx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, f.min_x), r), f.inv_w)));
+    if (c.min_cx >= kGridCols) return c;
+    c.max_cx = min(kGridCols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, f.min_x), r), f.inv_w)));
+    if (c.max_cx < 0) return c;
+    c.min_cy = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, f.min_y), r), f.inv_h)));
+    if (c.min_cy >= kGridRows) return c;
+    c.max_cy = min(kGridRows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, f.min_y), r), f.inv_h)));
+    if (c.max_cy < 0) return c;
+    c.ok = true;
+    return c;
+}
+
+// Sophus::SE3f point action (so3.hpp:358-366, se3.hpp:321-324), float32, no FMA.
+__device__ __forceinline__ void se3f_rotate(const float* T, const float p[3], float out[3]) {
+    const float qx = T[0], qy = T[1], qz = T[2], qw = T[3];
+    float uv[3] = {__fsub_rn(__fmul_rn(qy, p[2]), __fmul_rn(qz, p[1])), __fsub_rn(__fmul_rn(qz, p[0]), __fmul_rn(qx, p[2])),
+                   __fsub_rn(__fmul_rn(qx, p[1]), __fmul_rn(qy, p[0]))};
+    uv[0] = __fadd_rn(uv[0], uv[0]); uv[1] = __fadd_rn(uv[1], uv[1]); uv[2] = __fadd_rn(uv[2], uv[2]);
+    const float c[3] = {__fsub_rn(__fmul_rn(qy, uv[2]), __fmul_rn(qz, uv[1])), __fsub_rn(__fmul_rn(qz, uv[0]), __fmul_rn(qx, uv[2])),
+                        __fsub_rn(__fmul_rn(qx, uv[1]), __fmul_rn(qy, uv[0]))};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[i] = __fadd_rn(__fadd_rn(p[i], __fmul_rn(qw, uv[i])), c[i]);
+}
+
+// One warp scans the candidate cells of a query and appends every admissible candidate as
+// key = dist << 20 | csr_pos to the query's list (warp-aggregated append into a global pool).
+// `keep_max` = largest distance that can still influence the decision.
+template <class Filter>
+__device__ __forceinline__ int warp_collect(const FrameDev& f, const int* __restrict__ cell_start,
+                                            const int* __restrict__ csr_idx, const CellRange cr, float x, float y,
+                                            float r, int min_level, int max_level, const uint4 d0, const uint4 d1,
+                                            int keep_max, uint32_t* __restrict__ list, int list_cap, Filter admit) {
+    const int lane = threadIdx.x & 31;
+    const bool check_levels = (min_level > 0) || (max_level >= 0);
+    int count = 0;
+    for (int ix = cr.min_cx; ix <= cr.max_cx; ++ix) {
+        const int b = cell_start[ix * kGridRows + cr.min_cy], e = cell_start[ix * kGridRows + cr.max_cy + 1];
+        for (int p0 = b; p0 < e; p0 += 32) {
+            const int p = p0 + lane;
+            bool keep = false;
+            uint32_t key = 0;
+            if (p < e) {
+                const int idx = csr_idx[p];
+                const rgbl_keypoint kp = f.keys[idx];
+                bool ok = true;
+                if (check_levels) {
+                    if (kp.octave < min_level) ok = false;
+                    if (max_level >= 0 && kp.octave > max_level) ok = false;
+                }
+                if (ok) {
+                    const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
+                    ok = fabsf(dx) < r && fabsf(dy) < r;
+                }
+                if (ok) ok = admit(idx);
+                if (ok) {
+                    const int d = hamming256(d0, d1, f.desc + (size_t)idx * 32);
+                    if (d <= keep_max) { keep = true; key = ((uint32_t)d << 20) | (uint32_t)p; }
+                }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int o = count + __popc(m & ((1u << lane) - 1u));
+                if (o < list_cap) list[o] = key;
+            }
+            count += __popc(m);
+        }
+    }
+    return count;
+}
+
+// ---- SearchByProjection(CurrentFrame, LastFrame): candidate phase --------------------------------
+__global__ void __launch_bounds__(256) search_last_collect_kernel(FrameDev f, const int* __restrict__ cell_start,
+                                                                  const int* __restrict__ csr_idx, LastFrameDev lf,
+                                                                  SearchLastParams prm, uint32_t* __restrict__ lists,
+                                                                  int list_cap, int* __restrict__ list_n,
+                                                                  int* __restrict__ overflow) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= lf.n) return;
+    int count = 0;
+    if (lf.valid[q]) {
+        const float p[3] = {lf.xw[3 * q], lf.xw[3 * q + 1], lf.xw[3 * q + 2]};
+        float xc[3];
+        se3f_rotate(prm.cur_pose, p, xc);
+        xc[0] = __fadd_rn(xc[0], prm.cur_pose[4]); xc[1] = __fadd_rn(xc[1], prm.cur_pose[5]); xc[2] = __fadd_rn(xc[2], prm.cur_pose[6]);
+        const float invzc = (float)__ddiv_rn(1.0, (double)xc[2]);
+        bool ok = !(invzc < 0);
+        const float u = __fadd_rn(__fdiv_rn(__fmul_rn(f.fx, xc[0]), xc[2]), f.cx);
+        const float v = __fadd_rn(__fdiv_rn(__fmul_rn(f.fy, xc[1]), xc[2]), f.cy);
+        if (ok && (u < f.min_x || u > f.max_x)) ok = false;
+        if (ok && (v < f.min_y || v > f.max_y)) ok = false;
+        if (ok) {
+            const int oct = lf.octave[q];
+            const float radius = __fmul_rn(prm.th, f.scale[oct]);
+            int lo, hi;
+            if (prm.forward) { lo = oct; hi = -1; }
+            else if (prm.backward) { lo = 0; hi = oct; }
+            else { lo = oct - 1; hi = oct + 1; }
+            const CellRange cr = cell_range(f, u, v, radius);
+            if (cr.ok) {
+                const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(lf.desc + (size_t)q * 32));
+                const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(lf.desc + (size_t)q * 32) + 1);
+                const float ur = __fsub_rn(u, __fmul_rn(f.bf, invzc));
+                const float* uright = f.uright;
+                count = warp_collect(f, cell_start, csr_idx, cr, u, v, radius, lo, hi, d0, d1, kThHigh,
+                                     lists + (size_t)q * list_cap, list_cap, [&](int idx) {
+                                         const float urt = uright[idx];
+                                         if (urt > 0.f) { if (fabsf(__fsub_rn(ur, urt)) > radius) return false; }
+                                         return true;
+                                     });
+            }
+        }
+    }
+    if (lane == 0) {
+        list_n[q] = min(count, list_cap);
+        if (count > list_cap) atomicExch(overflow, 3);
+    }
+}
+
+// ---- SearchByProjection(F, vpMapPoints): candidate phase ---------------------------------------------
+__global__ void __launch_bounds__(256) search_local_collect_kernel(FrameDev f, const int* __restrict__ cell_start,
+                                                                   const int* __restrict__ csr_idx, LocalPointsDev lp,
+                                                                   SearchLocalParams prm, uint32_t* __restrict__ lists,
+                                                                   int list_cap, int* __restrict__ list_n,
+                                                                   int* __restrict__ overflow) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= lp.n) return;
+    int count = 0;
+    bool active = lp.in_view[q] != 0;
+    if (active && prm.far_points && lp.depth[q] > prm.th_far) active = false;
+    if (active) {
+        const int pl = lp.level[q];
+        float r = ((double)lp.view_cos[q] > 0.998) ? 2.5f : 4.0f;
+        if (prm.use_factor) r = __fmul_rn(r, prm.th);
+        const float rad = __fmul_rn(r, f.scale[pl]);
+        const float x = lp.proj_x[q], y = lp.proj_y[q];
+        const CellRange cr = cell_range(f, x, y, rad);
+        if (cr.ok) {
+            const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(lp.desc + (size_t)q * 32));
+            const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(lp.desc + (size_t)q * 32) + 1);
+            const float xr = lp.proj_xr[q];
+            const float* uright = f.uright;
+            count = warp_collect(f, cell_start, csr_idx, cr, x, y, rad, pl - 1, pl, d0, d1, prm.keep_max,
+                                 lists + (size_t)q * list_cap, list_cap, [&](int idx) {
+                                     const float urt = uright[idx];
+                                     if (urt > 0.f) { if (fabsf(__fsub_rn(xr, urt)) > rad) return false; }
+                                     return true;
+                                 });
+        }
+    }
+    if (lane == 0) {
+        list_n[q] = min(count, list_cap);
+        if (count > list_cap) atomicExch(overflow, 3);
+    }
+}
+
+// ---- greedy resolution (single CTA) -------------------------------------------------------------------
+// mode 0: last-frame search (best <= TH_HIGH wins, rotation histogram);  mode 1: local-map search
+// (best / second best with levels, ratio test).  state[f]: 0 free, 1 blocked (holds a point with
+// observations), 2 holds a 0-observation point (may be re-claimed).  match[f]: -1 untouched,
+// >= 0 query index, -2 cleared by the rotation check.
+__global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const int* __restrict__ n_q_dev, FrameDev f,
+                                                       const int* __restrict__ csr_idx,
+                                                       const uint32_t* __restrict__ lists, int list_cap,
+                                                       const int* __restrict__ list_n,
+                                                       const uint8_t* __restrict__ obs_pos,
+                                                       const float* __restrict__ q_angle, float nn_ratio,
+                                                       int check_orientation, uint8_t* __restrict__ state,
+                                                       int* __restrict__ minq, int* __restrict__ choice,
+                                                       uint8_t* __restrict__ resolved, int* __restrict__ match,
+                                                       int* __restrict__ n_matches, int* __restrict__ rounds_out) {
+    __shared__ int s_unresolved;
+    __shared__ int hist[kHistoLength];
+    __shared__ int keep_bin[3];
+    __shared__ int s_nm;
+    const int tid = threadIdx.x;
+    if (n_q_dev) n_q = *n_q_dev;
+    const int n_f = *f.n;
+    for (int i = tid; i < n_f; i += 1024) match[i] = -1;
+    for (int q = tid; q < n_q; q += 1024) { choice[q] = -1; resolved[q] = (list_n[q] == 0); }
+    if (tid == 0) s_nm = 0;
+    __syncthreads();
+    int rounds = 0;
+    for (;;) {
+        if (tid == 0) s_unresolved = 0;
+        for (int i = tid; i < n_f; i += 1024) minq[i] = 0x7fffffff;
+        __syncthreads();
+        for (int q = tid; q < n_q; q += 1024) {
+            if (resolved[q]) continue;
+            const uint32_t* l = lists + (size_t)q * list_cap;
+            const int n = list_n[q];
+            for (int k = 0; k < n; ++k) {
+                const int ft = csr_idx[l[k] & kPosMask];
+                if (state[ft] != 1) atomicMin(&minq[ft], q);
+            }
+        }
+        __syncthreads();
+        for (int q = tid; q < n_q; q += 1024) {
+            if (resolved[q]) continue;
+            const uint32_t* l = lists + (size_t)q * list_cap;
+            const int n = list_n[q];
+            uint32_t best = 0xffffffffu, best2 = 0xffffffffu;     // smallest / second smallest (dist, order) keys
+            int lvl = -1, lvl2 = -1;
+            bool depends_ok = true;
+            for (int k = 0; k < n; ++k) {
+                const uint32_t key = l[k];
+                const int ft = csr_idx[key & kPosMask];
+                if (state[ft] == 1) continue;
+                if (mode == 1 && minq[ft] != q) depends_ok = false;
+                const int d = (int)(key >> 20);
+                if (mode == 0) {
+                    if (key < best) best = key;
+                } else {
+                    // reference scan order = ascending csr position; emulate "dist < bestDist" / "else if dist < bestDist2"
+                    // order-independently: best = min by (dist, pos); second = min dist among the rest (level of the
+                    // FIRST candidate in scan order reaching that distance)
+                    if (key < best) { best2 = best; lvl2 = lvl; best = key; lvl = f.keys[ft].octave; }
+                    else if (key < best2) { best2 = key; lvl2 = f.keys[ft].octave; }
+                    (void)d;
+                }
+            }
+            if (best == 0xffffffffu) { resolved[q] = 1; continue; }
+            const int fb = csr_idx[best & kPosMask];
+            const bool final_ok = (mode == 0) ? (minq[fb] == q) : depends_ok;
+            if (!final_ok) { atomicAdd(&s_unresolved, 1); continue; }
+            resolved[q] = 1;
+            const int bd = (int)(best >> 20);
+            bool accept = bd <= kThHigh;
+            if (mode == 1 && accept) {
+                const int bd2 = (best2 == 0xffffffffu) ? 256 : (int)(best2 >> 20);
+                if (lvl == lvl2 && (float)bd > __fmul_rn(nn_ratio, (float)bd2)) accept = false;
+            }
+            if (accept) {
+                choice[q] = fb;
+                if (obs_pos[q]) state[fb] = 1; else if (state[fb] == 0) state[fb] = 2;
+                atomicAdd(&s_nm, 1);
+            }
+        }
+        __syncthreads();
+        ++rounds;
+        if (s_unresolved == 0) break;
+        __syncthreads();
+    }
+    // owner of a feature = the last (highest-index) query that chose it
+    for (int q = tid; q < n_q; q += 1024) if (choice[q] >= 0) atomicMax(&match[choice[q]], q);
+    if (mode == 0 && check_orientation) {
+        for (int b = tid; b < kHistoLength; b += 1024) hist[b] = 0;
+        __syncthreads();
+        const float factor = 1.0f / kHistoLength;
+        for (int q = tid; q < n_q; q += 1024) {
+            if (choice[q] < 0) continue;
+            float rot = __fsub_rn(q_angle[q], f.keys[choice[q]].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, factor));
+            if (bin == kHistoLength) bin = 0;
+            atomicAdd(&hist[bin], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {       // ORBmatcher::ComputeThreeMaxima, src/ORBmatcher.cc:2012-2053
+            int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+            for (int i = 0; i < kHistoLength; ++i) {
+                const int s = hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+                else if (s > max3) { max3 = s; i3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) i3 = -1;
+            keep_bin[0] = i1; keep_bin[1] = i2; keep_bin[2] = i3;
+        }
+        __syncthreads();
+        for (int q = tid; q < n_q; q += 1024) {
+            if (choice[q] < 0) continue;
+            float rot = __fsub_rn(q_angle[q], f.keys[choice[q]].angle);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, factor));
+            if (bin == kHistoLength) bin = 0;
+            if (bin != keep_bin[0] && bin != keep_bin[1] && bin != keep_bin[2]) { match[choice[q]] = -2; atomicSub(&s_nm, 1); }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { *n_matches = s_nm; if (rounds_out) *rounds_out = rounds; }
+}
+
+// ---- Frame::isInFrustum for a list of local map points ----------------------------------------------
+__global__ void __launch_bounds__(256) frustum_kernel(FrameDev f, FrustumParams prm, int n, const float* __restrict__ xw,
+                                                      const float* __restrict__ normal, const float* __restrict__ mf_min,
+                                                      const float* __restrict__ mf_max, uint8_t* __restrict__ in_view,
+                                                      float* __restrict__ px, float* __restrict__ py,
+                                                      float* __restrict__ pxr, float* __restrict__ depth,
+                                                      int* __restrict__ level, float* __restrict__ view_cos) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    uint8_t iv = 0; float ox = -1.f, oy = -1.f, oxr = 0.f, od = 0.f, ovc = 0.f; int ol = 0;
+    const float P[3] = {xw[3 * i], xw[3 * i + 1], xw[3 * i + 2]};
+    float Pc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        Pc[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(prm.Rcw[3 * r], P[0]), __fmul_rn(prm.Rcw[3 * r + 1], P[1])),
+                                    __fmul_rn(prm.Rcw[3 * r + 2], P[2])), prm.tcw[r]);
+    const float pc_dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(Pc[0], Pc[0]), __fmul_rn(Pc[1], Pc[1])), __fmul_rn(Pc[2], Pc[2])));
+    const float z = Pc[2];
+    const float invz = __fdiv_rn(1.0f, z);
+    bool ok = !(z < 0.0f);
+    const float u = __fadd_rn(__fdiv_rn(__fmul_rn(f.fx, Pc[0]), Pc[2]), f.cx);
+    const float v = __fadd_rn(__fdiv_rn(__fmul_rn(f.fy, Pc[1]), Pc[2]), f.cy);
+    if (ok && (u < f.min_x || u > f.max_x)) ok = false;
+    if (ok && (v < f.min_y || v > f.max_y)) ok = false;
+    if (ok) {
+        ox = u; oy = v;
+        const float PO[3] = {__fsub_rn(P[0], prm.Ow[0]), __fsub_rn(P[1], prm.Ow[1]), __fsub_rn(P[2], prm.Ow[2])};
+        const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(PO[0], PO[0]), __fmul_rn(PO[1], PO[1])), __fmul_rn(PO[2], PO[2])));
+        if (!(dist < __fmul_rn(0.8f, mf_min[i]) || dist > __fmul_rn(1.2f, mf_max[i]))) {
+            const float* Pn = normal + 3 * i;
+            const float vc = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(PO[0], Pn[0]), __fmul_rn(PO[1], Pn[1])), __fmul_rn(PO[2], Pn[2])), dist);
+            if (!(vc < prm.cos_limit)) {
+                const float ratio = __fdiv_rn(mf_max[i], dist);
+                const float lg = (float)log((double)ratio);          // correctly-rounded stand-in for glibc logf
+                int ns = (int)ceilf(__fdiv_rn(lg, f.log_scale_factor));
+                if (ns < 0) ns = 0; else if (ns >= f.n_levels) ns = f.n_levels - 1;
+                iv = 1; oxr = __fsub_rn(u, __fmul_rn(f.bf, invz)); od = pc_dist; ol = ns; ovc = vc;
+            }
+        }
+    }
+    in_view[i] = iv; px[i] = ox; py[i] = oy; pxr[i] = oxr; depth[i] = od; level[i] = ol; view_cos[i] = ovc;
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------
+void launch_grid_build(cudaStream_t st, const FrameDev& f, int* cell_start, int* csr_idx, int* kp_cell) {
+    grid_build_kernel<<<1, 1024, 0, st>>>(f, cell_start, csr_idx, kp_cell);
+}
+
+void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LastFrameDev& lf,
+                        const SearchLastParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches) {
+    if (lf.n <= 0) return;
+    search_last_collect_kernel<<<(lf.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lf, prm, s.lists, s.list_cap, s.list_n, s.overflow);
+    resolve_kernel<<<1, 1024, 0, st>>>(0, lf.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lf.obs_pos, lf.angle, 0.f,
+                                       prm.check_orientation, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds);
+}
+
+void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LocalPointsDev& lp,
+                         const SearchLocalParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches) {
+    if (lp.n <= 0) return;
+    search_local_collect_kernel<<<(lp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
+    resolve_kernel<<<1, 1024, 0, st>>>(1, lp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lp.obs_pos, nullptr, prm.nn_ratio,
+                                       0, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds);
+}
+
+void launch_frustum(cudaStream_t st, const FrameDev& f, const FrustumParams& prm, int n, const float* xw, const float* normal,
+                    const float* mf_min, const float* mf_max, uint8_t* in_view, float* px, float* py, float* pxr, float* depth,
+                    int* level, float* view_cos) {
+    if (n <= 0) return;
+    frustum_kernel<<<(n + 255) / 256, 256, 0, st>>>(f, prm, n, xw, normal, mf_min, mf_max, in_view, px, py, pxr, depth, level, view_cos);
+}
+
+}  // namespace rgbl

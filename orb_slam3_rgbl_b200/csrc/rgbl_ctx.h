@@ -1,0 +1,124 @@
+// Context of librgbl_b200.so: memory plan, streams, profiling state (shared by api.cu and api_track.cu).
+#ifndef RGBL_CTX_H
+#define RGBL_CTX_H
+
+#include <string>
+#include <vector>
+
+#include "rgbl_kernels.h"
+
+namespace rgbl {
+
+enum Stage { ST_PYRAMID = 0, ST_FAST, ST_COMPACT, ST_BLUR, ST_DESCRIBE, ST_DEPTH_PROJECT, ST_DEPTH_DILATE, ST_DEPTH_GATHER,
+             ST_MATCH, ST_POSE, kNumStages };
+static const char* const kStageNames[kNumStages] = {"pyramid", "fast", "compact", "blur", "describe", "depth_project",
+                                              "depth_resolve_dilate", "depth_gather", "match", "pose"};
+
+constexpr int kMatchListCap = 512;    // admissible candidates kept per map point (overflow is reported)
+
+// Lazily grown device scratch of the tracking entry points (api_track.cu).
+struct TrackBufs {
+    rgbl_keypoint* keys = nullptr; size_t cap_keys = 0;
+    float* uright = nullptr; size_t cap_uright = 0;
+    uint8_t* desc = nullptr; size_t cap_desc = 0;
+    int* csr_idx = nullptr; size_t cap_csr = 0;
+    int* kp_cell = nullptr; size_t cap_kpcell = 0;
+    int* cell_start = nullptr; size_t cap_cellstart = 0;
+    uint8_t* state = nullptr; size_t cap_state = 0;
+    int* match = nullptr; size_t cap_match = 0;
+    int* minq = nullptr; size_t cap_minq = 0;
+    int* scalars = nullptr; size_t cap_scalars = 0;
+    uint32_t* lists = nullptr; size_t cap_lists = 0;
+    int* list_n = nullptr; size_t cap_listn = 0;
+    int* choice = nullptr; size_t cap_choice = 0;
+    uint8_t* resolved = nullptr; size_t cap_resolved = 0;
+    uint8_t *q_u8a = nullptr, *q_u8b = nullptr, *q_desc = nullptr; size_t cap_q_u8a = 0, cap_q_u8b = 0, cap_q_desc = 0;
+    float *q_f3a = nullptr, *q_f3b = nullptr; size_t cap_q_f3a = 0, cap_q_f3b = 0;
+    float* q_f[7] = {}; size_t cap_q_f[7] = {};
+    int* q_i = nullptr; size_t cap_q_i = 0;
+    double* pose_work = nullptr; size_t cap_pose_work = 0;
+    void release() {
+        void* all[] = {keys, uright, desc, csr_idx, kp_cell, cell_start, state, match, minq, scalars, lists, list_n, choice, resolved,
+                       q_u8a, q_u8b, q_desc, q_f3a, q_f3b, q_f[0], q_f[1], q_f[2], q_f[3], q_f[4], q_f[5], q_f[6], q_i, pose_work};
+        for (void* p : all) if (p) cudaFree(p);
+    }
+};
+
+struct Ctx {
+    rgbl_config cfg{};
+    OrbTables tab{};
+    std::vector<LevelGeom> levels;
+    std::vector<CellInfo> cells;
+    std::vector<LinCoef> coefs;
+    size_t frame_bytes = 0;
+    int n_cells = 0;
+    int cap_kp = 0;              // keypoints per frame capacity (nfeatures + 3 per level)
+    int dense_cap = 0;           // candidates per batch capacity
+    std::string err;
+
+    cudaStream_t st = nullptr, st_aux = nullptr;
+    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+
+    // device
+    LevelGeom* d_levels = nullptr;
+    CellInfo* d_cells = nullptr;
+    LinCoef* d_coefs = nullptr;
+    uint8_t *d_pyr = nullptr, *d_blur = nullptr;
+    uint32_t* d_slots = nullptr;
+    int *d_counts = nullptr, *d_cell_off = nullptr, *d_level_cnt = nullptr, *d_frame_total = nullptr, *d_overflow = nullptr;
+    uint32_t* d_dense = nullptr;
+    SelKp* d_sel = nullptr;
+    int* d_n_sel = nullptr;
+    rgbl_keypoint *d_kps = nullptr, *d_kps_un = nullptr, *d_kps_in = nullptr;
+    int* d_n_kp_in = nullptr;
+    uint8_t* d_desc = nullptr;
+    float* d_pts = nullptr;
+    int* d_n_pts = nullptr;
+    uint32_t* d_idx_map = nullptr;
+    float *d_raw = nullptr, *d_processed = nullptr, *d_depth = nullptr, *d_uright = nullptr;
+    uint8_t* d_scratch = nullptr;   // padded-level export
+    size_t scratch_bytes = 0;
+    uint32_t stamp = 0;
+
+    // pinned host
+    int *h_level_cnt = nullptr, *h_frame_total = nullptr, *h_overflow = nullptr, *h_n_sel = nullptr, *h_n_pts = nullptr;
+    uint32_t* h_dense = nullptr;
+    SelKp* h_sel = nullptr;
+
+    // profiling (rgbl_profile_*): CUDA events on the launching stream around every stage
+    bool prof_on = false;
+    cudaEvent_t ev_b[kNumStages] = {}, ev_e[kNumStages] = {};
+    bool st_used[kNumStages] = {};
+    int st_pending_launches[kNumStages] = {};
+    double st_ms[kNumStages] = {};
+    long st_launches[kNumStages] = {};
+    long st_calls[kNumStages] = {};
+    double host_quadtree_ms = 0.0;
+    long total_launches = 0;
+
+    TrackBufs trk;
+    int* h_scalars = nullptr;    // pinned, 16 ints
+    int last_match_rounds = 0;
+
+    int last_frames = 0;         // frames valid in the device buffers
+    int resident_frames = 0, resident_max_pts = 0;
+    bool blur_valid = false;
+};
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return RGBL_E_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+
+// profiling helpers (api.cu)
+void stage_begin(Ctx* c, int stage, cudaStream_t st);
+void stage_end(Ctx* c, int stage, cudaStream_t st, int launches);
+void prof_collect(Ctx* c);
+
+}  // namespace rgbl
+#endif

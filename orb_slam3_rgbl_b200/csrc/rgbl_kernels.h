@@ -54,5 +54,51 @@ void launch_depth_gather(cudaStream_t st, const float* processed, int W, int H, 
                          const rgbl_keypoint* kps_un, const int* n_kp, int cap, int max_n, float bf, float* depth,
                          float* uright, int n_frames);
 
+
+// match_kernels.cu ---------------------------------------------------------------------------------
+// Device view of the Frame members the matchers read (Nleft == -1 frames).
+struct FrameDev {
+    const int* n;                    // device int: number of keypoints
+    const rgbl_keypoint* keys;       // mvKeysUn
+    const float* uright;             // mvuRight
+    const uint8_t* desc;             // mDescriptors
+    float min_x, max_x, min_y, max_y, inv_w, inv_h;
+    int n_levels;
+    float scale[RGBL_MAX_LEVELS];
+    float fx, fy, cx, cy, bf, mb, log_scale_factor;
+};
+struct LastFrameDev {                // LastFrame.mvpMapPoints as flat arrays (device pointers)
+    int n;
+    const uint8_t* valid; const float* xw; const uint8_t* desc; const int* octave; const float* angle; const uint8_t* obs_pos;
+};
+struct LocalPointsDev {              // vpMapPoints with the mTrack* fields isInFrustum fills
+    int n;
+    const uint8_t* in_view; const float *proj_x, *proj_y, *proj_xr, *depth; const int* level; const float* view_cos;
+    const uint8_t* desc; const uint8_t* obs_pos;
+};
+struct SearchLastParams { float cur_pose[7]; float th; int forward, backward, check_orientation; };
+struct SearchLocalParams { float th, nn_ratio, th_far; int use_factor, far_points, keep_max; };
+struct FrustumParams { float Rcw[9], tcw[3], Ow[3], cos_limit; };
+struct MatchScratch { uint32_t* lists; int list_cap; int* list_n; int* minq; int* choice; uint8_t* resolved; int* overflow; int* rounds; };
+
+void launch_grid_build(cudaStream_t st, const FrameDev& f, int* cell_start, int* csr_idx, int* kp_cell);
+void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LastFrameDev& lf,
+                        const SearchLastParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches);
+void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LocalPointsDev& lp,
+                         const SearchLocalParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches);
+void launch_frustum(cudaStream_t st, const FrameDev& f, const FrustumParams& prm, int n, const float* xw, const float* normal,
+                    const float* mf_min, const float* mf_max, uint8_t* in_view, float* px, float* py, float* pxr, float* depth,
+                    int* level, float* view_cos);
+
+// pose_kernels.cu ----------------------------------------------------------------------------------
+struct PoseProblemDev {
+    int n;                           // edges (keypoint order)
+    const float* xw; const float* obs; const float* inv_sigma2; const uint8_t* stereo;
+    float fx, fy, cx, cy, bf;
+    float pose_in[7];
+};
+void launch_pose_optimize(cudaStream_t st, const PoseProblemDev& p, double* work /* n*4 doubles */, uint8_t* level, uint8_t* outlier,
+                          float* pose_out /*7*/, int* n_inliers);
+
 }  // namespace rgbl
 #endif

@@ -214,6 +214,92 @@ def frame_rgbl_batch(ctx: Context, images, clouds, P, depth_params: DepthParams)
     return [(kps[f, :n[f]].copy(), desc[f, :n[f]].copy(), depth[f, :n[f]].copy(), ur[f, :n[f]].copy()) for f in range(nF)]
 
 
+class FrameView:
+    """The members of ORB_SLAM3::Frame the tracking matchers read (Nleft == -1 frames), see rgbl_frame_view."""
+
+    def __init__(self, keys_un, uright, desc, width, height, scale_factors, fx, fy, cx, cy, bf):
+        self.keys_un = np.ascontiguousarray(keys_un, KP_DTYPE)
+        self.uright = np.ascontiguousarray(uright, np.float32)
+        self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.scale_factors = np.ascontiguousarray(scale_factors, np.float32)
+        self.n = len(self.keys_un)
+        log_sf = float(np.float32(np.log(np.float32(self.scale_factors[1])))) if len(self.scale_factors) > 1 else 1.0
+        self.c = L.FrameViewC(self.n, self.keys_un.ctypes.data, self.uright.ctypes.data, self.desc.ctypes.data,
+                              0.0, float(width), 0.0, float(height), len(self.scale_factors), self.scale_factors.ctypes.data,
+                              fx, fy, cx, cy, bf, log_sf)
+
+
+class ORBmatcher:
+    """ORB_SLAM3::ORBmatcher, the tracking-thread entry points (include/ORBmatcher.h:40-69)."""
+
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
+
+    def __init__(self, ctx: Context, nnratio=0.6, checkOri=True):
+        self.ctx, self.mfNNratio, self.mbCheckOrientation = ctx, nnratio, checkOri
+
+    @staticmethod
+    def DescriptorDistance(a, b) -> int:
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        return lib().rgbl_descriptor_distance(ptr(a), ptr(b))
+
+    def SearchByProjectionLastFrame(self, cur: FrameView, cur_pose, last_pose, valid, xw, mp_desc, last_octave, last_angle,
+                                    obs_pos, th, bMono=False, cur_state=None):
+        """SearchByProjection(CurrentFrame, LastFrame, th, bMono) -> (nmatches, match[cur.n])"""
+        cur_pose = np.ascontiguousarray(cur_pose, np.float32); last_pose = np.ascontiguousarray(last_pose, np.float32)
+        valid = np.ascontiguousarray(valid, np.uint8); xw = np.ascontiguousarray(xw, np.float32)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8); last_octave = np.ascontiguousarray(last_octave, np.int32)
+        last_angle = np.ascontiguousarray(last_angle, np.float32); obs_pos = np.ascontiguousarray(obs_pos, np.uint8)
+        cs = None if cur_state is None else np.ascontiguousarray(cur_state, np.uint8)
+        match = np.empty(cur.n, np.int32); nm = C.c_int(0)
+        check(lib().rgbl_search_by_projection_last(self.ctx.handle, C.byref(cur.c), ptr(cur_pose), ptr(last_pose), len(valid), ptr(valid),
+                                                   ptr(xw), ptr(mp_desc), ptr(last_octave), ptr(last_angle), ptr(obs_pos), th, int(bMono),
+                                                   int(self.mbCheckOrientation), None if cs is None else ptr(cs), ptr(match), C.byref(nm)),
+              self.ctx.handle)
+        return nm.value, match
+
+    def SearchByProjectionLocal(self, cur: FrameView, tr: dict, mp_desc, obs_pos, th, bFarPoints=False, thFarPoints=50.0, cur_state=None):
+        """SearchByProjection(F, vpMapPoints, th, bFarPoints, thFarPoints) -> (nmatches, match[cur.n]); tr = is_in_frustum output"""
+        n = len(tr["in_view"])
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8); obs_pos = np.ascontiguousarray(obs_pos, np.uint8)
+        cs = None if cur_state is None else np.ascontiguousarray(cur_state, np.uint8)
+        match = np.empty(cur.n, np.int32); nm = C.c_int(0)
+        check(lib().rgbl_search_by_projection_local(self.ctx.handle, C.byref(cur.c), n, ptr(tr["in_view"]), ptr(tr["proj_x"]), ptr(tr["proj_y"]),
+                                                    ptr(tr["proj_xr"]), ptr(tr["depth"]), ptr(tr["level"]), ptr(tr["view_cos"]), ptr(mp_desc),
+                                                    ptr(obs_pos), th, self.mfNNratio, int(bFarPoints), thFarPoints,
+                                                    None if cs is None else ptr(cs), ptr(match), C.byref(nm)), self.ctx.handle)
+        return nm.value, match
+
+
+def is_in_frustum(ctx: Context, cur: FrameView, Rcw, tcw, Ow, xw, normal, mf_min_dist, mf_max_dist, cos_limit=0.5) -> dict:
+    """Frame::isInFrustum over a list of map points -> dict of the mTrack* fields."""
+    n = len(xw)
+    Rcw = np.ascontiguousarray(Rcw, np.float32).reshape(9); tcw = np.ascontiguousarray(tcw, np.float32); Ow = np.ascontiguousarray(Ow, np.float32)
+    xw = np.ascontiguousarray(xw, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+    mn = np.ascontiguousarray(mf_min_dist, np.float32); mx = np.ascontiguousarray(mf_max_dist, np.float32)
+    out = dict(in_view=np.empty(n, np.uint8), proj_x=np.empty(n, np.float32), proj_y=np.empty(n, np.float32), proj_xr=np.empty(n, np.float32),
+               depth=np.empty(n, np.float32), level=np.empty(n, np.int32), view_cos=np.empty(n, np.float32))
+    check(lib().rgbl_is_in_frustum(ctx.handle, C.byref(cur.c), ptr(Rcw), ptr(tcw), ptr(Ow), n, ptr(xw), ptr(normal), ptr(mn), ptr(mx), cos_limit,
+                                   ptr(out["in_view"]), ptr(out["proj_x"]), ptr(out["proj_y"]), ptr(out["proj_xr"]), ptr(out["depth"]),
+                                   ptr(out["level"]), ptr(out["view_cos"])), ctx.handle)
+    return out
+
+
+class Optimizer:
+    """ORB_SLAM3::Optimizer::PoseOptimization (src/Optimizer.cc:814-1114)."""
+
+    @staticmethod
+    def PoseOptimization(ctx: Context, pose, xw, obs, inv_sigma2, stereo, fx, fy, cx, cy, bf):
+        """-> (nInliers, pose_out[7], mvbOutlier[n])"""
+        pose = np.ascontiguousarray(pose, np.float32); xw = np.ascontiguousarray(xw, np.float32).reshape(-1, 3)
+        obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 3); inv_sigma2 = np.ascontiguousarray(inv_sigma2, np.float32)
+        stereo = np.ascontiguousarray(stereo, np.uint8)
+        n = len(xw)
+        out = np.empty(7, np.float32); outlier = np.zeros(max(n, 1), np.uint8); ni = C.c_int(0)
+        check(lib().rgbl_pose_optimize(ctx.handle, ptr(pose), n, ptr(xw), ptr(obs), ptr(inv_sigma2), ptr(stereo), fx, fy, cx, cy, bf,
+                                       ptr(out), ptr(outlier), C.byref(ni)), ctx.handle)
+        return ni.value, out, outlier[:n]
+
+
 class RgblBatch:
     """Reusable (pinned if torch+CUDA are available) host buffers for rgbl_frame_rgbl_batch / the resident API."""
 

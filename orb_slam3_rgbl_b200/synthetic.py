@@ -132,3 +132,42 @@ def structuring_element(kind: str, ku: int, kv: int | None = None) -> np.ndarray
     else:
         raise ValueError(f"invalid kernel type: {kind}")
     return m
+
+
+# ------------------------------------------------------------------------------------------------
+# A geometrically consistent synthetic sequence (SURVEY.md 8(d) "Sequence"): a textured fronto-parallel
+# plane at depth Z seen by a camera translating along +x.  Frame t is an integer-pixel crop of one big
+# texture, so consecutive frames show the same corners shifted by `shift_px`; the LiDAR points are the
+# ring/azimuth rays intersected with the same plane, expressed in the Velodyne frame of each pose.
+# ------------------------------------------------------------------------------------------------
+
+class PlaneSequence:
+    def __init__(self, seed: int, n_frames: int, shift_px: int = 7, Z: float = 20.0, W: int = KITTI_W, H: int = KITTI_H,
+                 n_rings: int = 64, n_azimuth: int = 1875):
+        self.seed, self.n_frames, self.shift, self.Z, self.W, self.H = seed, n_frames, shift_px, Z, W, H
+        self.texture = make_image(seed, W + shift_px * n_frames + 8, H)
+        self.dX = shift_px * Z / KITTI_FX            # camera translation per frame (metres along +x)
+        self.n_rings, self.n_az = n_rings, n_azimuth
+        Tr4 = np.eye(4); Tr4[:3] = KITTI_TR
+        self.Tr_inv = np.linalg.inv(Tr4)
+        self.P = lidar_projection_matrix()
+
+    def image(self, t: int) -> np.ndarray:
+        return np.ascontiguousarray(self.texture[:, t * self.shift: t * self.shift + self.W])
+
+    def pose(self, t: int) -> np.ndarray:
+        """Tcw as (qx, qy, qz, qw, tx, ty, tz): identity rotation, camera centre at x = t*dX."""
+        return np.array([0, 0, 0, 1, -t * self.dX, 0, 0], np.float32)
+
+    def cloud(self, t: int) -> np.ndarray:
+        """float32 4 x N planar: a Velodyne-like fan of rays hitting the plane z = Z (camera frame)."""
+        rng = np.random.default_rng(self.seed * 7919 + t)
+        # sample directions over the camera's field of view (plus margin), ring-major
+        v = np.linspace(-0.30, 0.28, self.n_rings)[:, None]          # tan(elevation) in camera y
+        u = np.linspace(-1.1, 1.1, self.n_az)[None, :]               # tan(azimuth) in camera x
+        X = (u * self.Z) * np.ones_like(v); Y = (v * self.Z) * np.ones_like(u); Zc = np.full_like(X, self.Z)
+        Zc = Zc + rng.normal(0.0, 0.01, Zc.shape)
+        cam = np.stack([X.ravel(), Y.ravel(), Zc.ravel(), np.ones(X.size)])
+        velo = self.Tr_inv @ cam
+        pts = np.stack([velo[0], velo[1], velo[2], np.ones(X.size)]).astype(np.float32)
+        return np.ascontiguousarray(pts)

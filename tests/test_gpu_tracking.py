@@ -1,0 +1,132 @@
+"""GPU parity of the tracking-thread stages (matchers, isInFrustum, pose optimisation) vs the CPU oracle.
+Bar: matches / flags / integer fields bit-exact; isInFrustum floats bit-exact; pose within 1e-5 abs (1e-4 rel is
+the north-star tolerance) with identical outlier flags."""
+import numpy as np
+import pytest
+
+import oracle
+import tracking_data as TD
+from orb_slam3_rgbl_b200 import frontend as F
+from orb_slam3_rgbl_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = F.Context(S.KITTI_W, S.KITTI_H, 2000)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def seq_frames():
+    seq = S.PlaneSequence(5, 4)
+    frames, sf = TD.extract_frames(seq, [0, 1, 2])
+    return seq, frames, sf
+
+
+@pytest.mark.parametrize("th,mono,mix_obs,preoccupy", [(15.0, False, False, False), (7.0, False, False, True), (15.0, True, True, False), (30.0, False, True, True)])
+def test_search_by_projection_last(ctx, seq_frames, th, mono, mix_obs, preoccupy):
+    seq, frames, sf = seq_frames
+    last, cur = frames[0], frames[1]
+    xw, ok = TD.unproject(last, seq.pose(0))
+    rng = np.random.default_rng(3)
+    valid = ok.astype(np.uint8)
+    obs_pos = np.ones(len(valid), np.uint8)
+    if mix_obs:
+        obs_pos[rng.random(len(valid)) < 0.4] = 0
+    state = None
+    if preoccupy:
+        state = rng.choice([0, 0, 0, 1, 2], len(cur["k"])).astype(np.uint8)
+    args = (seq.pose(1), seq.pose(0), valid, xw, last["d"], last["k"]["octave"], last["k"]["angle"], obs_pos, th)
+    rn, rmatch = oracle.search_by_projection_last(oracle.FrameView(*TD.frame_view_args(cur, sf)), *args, mono=mono, cur_state=state)
+    m = F.ORBmatcher(ctx, 0.9, True)
+    n, match = m.SearchByProjectionLastFrame(F.FrameView(*TD.frame_view_args(cur, sf)), *args, bMono=mono, cur_state=state)
+    assert rn > 300
+    assert (match == rmatch).all(), f"{(match != rmatch).sum()} of {len(match)} assignments differ"
+    assert n == rn
+
+
+def test_search_last_backward_and_static(ctx, seq_frames):
+    seq, frames, sf = seq_frames
+    last, cur = frames[1], frames[0]
+    xw, ok = TD.unproject(last, seq.pose(1))
+    ones = np.ones(len(ok), np.uint8)
+    for cp, lp in ((seq.pose(0), seq.pose(1)), (np.array([0, 0, 0, 1, 0, 0, -1.0], np.float32), np.array([0, 0, 0, 1, 0, 0, 0], np.float32)),
+                   (np.array([0, 0, 0, 1, 0, 0, 1.0], np.float32), np.array([0, 0, 0, 1, 0, 0, 0], np.float32))):
+        args = (cp, lp, ok.astype(np.uint8), xw, last["d"], last["k"]["octave"], last["k"]["angle"], ones, 15.0)
+        rn, rmatch = oracle.search_by_projection_last(oracle.FrameView(*TD.frame_view_args(cur, sf)), *args)
+        n, match = F.ORBmatcher(ctx, 0.9, True).SearchByProjectionLastFrame(F.FrameView(*TD.frame_view_args(cur, sf)), *args)
+        assert (match == rmatch).all() and n == rn
+
+
+def test_is_in_frustum_and_local_search(ctx, seq_frames):
+    seq, frames, sf = seq_frames
+    rng = np.random.default_rng(9)
+    xw, desc, normal, mn, mx = TD.local_map([frames[0], frames[2]], [seq.pose(0), seq.pose(2)], sf, rng)
+    cur = frames[1]
+    pose = seq.pose(1)
+    Rcw = np.eye(3, dtype=np.float32); tcw = pose[4:7].copy(); Ow = -tcw
+    ofv = oracle.FrameView(*TD.frame_view_args(cur, sf)); gfv = F.FrameView(*TD.frame_view_args(cur, sf))
+    rt = oracle.is_in_frustum(ofv, Rcw, tcw, Ow, xw, normal, mn, mx, 0.5)
+    gt = F.is_in_frustum(ctx, gfv, Rcw, tcw, Ow, xw, normal, mn, mx, 0.5)
+    assert rt["in_view"].sum() > 1000
+    for k in rt:
+        assert (rt[k] == gt[k]).all(), f"isInFrustum field {k}: {(rt[k] != gt[k]).sum()} differ"
+    obs_pos = np.ones(len(xw), np.uint8)
+    for th, nn, state_mode in ((3.0, 0.8, 0), (1.0, 0.8, 1), (5.0, 0.6, 2), (15.0, 0.9, 1)):
+        state = None
+        if state_mode == 1:
+            state = rng.choice([0, 0, 1], len(cur["k"])).astype(np.uint8)
+        op = obs_pos.copy()
+        if state_mode == 2:
+            op[rng.random(len(op)) < 0.3] = 0
+        rn, rmatch = oracle.search_by_projection_local(ofv, rt, desc, op, th, nn, False, 0.0, state)
+        n, match = F.ORBmatcher(ctx, nn, True).SearchByProjectionLocal(gfv, gt, desc, op, th, cur_state=state)
+        assert rn > 100
+        assert (match == rmatch).all(), f"th={th}: {(match != rmatch).sum()} assignments differ"
+        assert n == rn
+    # far-point gate
+    rn, rmatch = oracle.search_by_projection_local(ofv, rt, desc, obs_pos, 3.0, 0.8, True, 20.05, None)
+    n, match = F.ORBmatcher(ctx, 0.8, True).SearchByProjectionLocal(gfv, gt, desc, obs_pos, 3.0, bFarPoints=True, thFarPoints=20.05)
+    assert (match == rmatch).all() and n == rn
+
+
+def test_empty_inputs(ctx, seq_frames):
+    seq, frames, sf = seq_frames
+    cur = frames[1]
+    gfv = F.FrameView(*TD.frame_view_args(cur, sf))
+    z = np.zeros(0)
+    n, match = F.ORBmatcher(ctx, 0.9, True).SearchByProjectionLastFrame(gfv, seq.pose(1), seq.pose(0), z, np.zeros((0, 3)), np.zeros((0, 32)), z, z, z, 15.0)
+    assert n == 0 and (match == -1).all()
+
+
+@pytest.mark.parametrize("seed,n,of,sf_", [(0, 900, 0.3, 0.7), (1, 2000, 0.1, 1.0), (2, 300, 0.5, 0.0), (3, 40, 0.2, 0.5), (4, 9, 0.0, 1.0), (5, 2, 0.0, 1.0)])
+def test_pose_optimization(ctx, seed, n, of, sf_):
+    p = TD.pose_problem(seed, n, of, sf_)
+    rn, rpose, rout = oracle.pose_optimize(p["pose0"], p["xw"], p["obs"], p["inv_s2"], p["stereo"], *TD.CAM)
+    gn, gpose, gout = F.Optimizer.PoseOptimization(ctx, p["pose0"], p["xw"], p["obs"], p["inv_s2"], p["stereo"], *TD.CAM)
+    assert np.abs(gpose - rpose).max() < 1e-5, (gpose, rpose)     # north star: pose within 1e-4 rel
+    assert (gout == rout).all() and gn == rn
+    if n >= 300:
+        assert np.abs(gpose[4:] - p["truth"][4:]).max() < 0.05 and np.abs(gpose[:4] - p["truth"][:4]).max() < 2e-3
+
+
+def test_track_with_motion_model_chain(ctx, seq_frames):
+    """SearchByProjection(last) -> PoseOptimization on device reproduces the oracle's chain and recovers the true motion."""
+    seq, frames, sf = seq_frames
+    last, cur = frames[0], frames[1]
+    xw, ok = TD.unproject(last, seq.pose(0))
+    ones = np.ones(len(ok), np.uint8)
+    gfv = F.FrameView(*TD.frame_view_args(cur, sf))
+    n, match = F.ORBmatcher(ctx, 0.9, True).SearchByProjectionLastFrame(gfv, seq.pose(0), seq.pose(0), ok.astype(np.uint8), xw, last["d"],
+                                                                          last["k"]["octave"], last["k"]["angle"], ones, 15.0)
+    m = np.nonzero(match >= 0)[0]
+    obs = np.stack([cur["k"]["x"][m], cur["k"]["y"][m], cur["ur"][m]], 1)
+    inv_s2 = (1.0 / sf[cur["k"]["octave"][m]] ** 2).astype(np.float32)
+    st = (cur["ur"][m] >= 0).astype(np.uint8)
+    gn, gpose, gout = F.Optimizer.PoseOptimization(ctx, seq.pose(0), xw[match[m]], obs, inv_s2, st, *TD.CAM)
+    rn, rpose, rout = oracle.pose_optimize(seq.pose(0), xw[match[m]], obs, inv_s2, st, *TD.CAM)
+    assert np.abs(gpose - rpose).max() < 1e-5 and (gout == rout).all()
+    assert abs(gpose[4] - seq.pose(1)[4]) < 0.01 and gn > 300

@@ -194,6 +194,10 @@ int rgbl_resident_upload(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray
 int rgbl_resident_process(rgbl_ctx* ctx, const float P[12], const rgbl_depth_params* prm, int* n_out /* nullable */);
 int rgbl_resident_download(rgbl_ctx* ctx, rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out);
 
+/* Keypoint distribution (DistributeOctTree) runs on the device by default (one CTA per (frame, level)); on != 0
+ * selects the host implementation instead (also: environment RGBL_HOST_QUADTREE=1).  Both are exact.           */
+int rgbl_set_host_quadtree(rgbl_ctx* ctx, int on);
+
 /* CUDA-event stopwatch on the context's main stream: mark(0) ... work ... mark(1); elapsed = device time
  * between the two marks (includes host gaps of the pipeline, excludes nothing).                      */
 int rgbl_timer_mark(rgbl_ctx* ctx, int which);
@@ -217,6 +221,12 @@ int rgbl_descriptor_distance(const uint8_t a[32], const uint8_t b[32]);
  * reference's output order.  Returns the number selected (<= N + 3).                             */
 int rgbl_quadtree_select(const int32_t* xys, int n, int min_x, int max_x, int min_y, int max_y, int n_desired,
                          int32_t* out_idx, int cap);
+
+/* Test hooks (host-only): the device quad-tree's block algorithm executed phase-sequentially on the host, and the
+ * restated libstdc++ std::sort it uses.  out_xys: n x 3 survivors in the reference's output order.              */
+int rgbl_quadtree_select_block_emulation(const int32_t* xys, int n, int min_x, int max_x, int min_y, int max_y, int n_desired,
+                                         int32_t* out_xys, int cap);
+int rgbl_std_sort_emulation(const int32_t* size_ulx, int n, int32_t* perm_out);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -28,7 +29,8 @@ static void release(Ctx* c) {
     void* dev[] = {c->d_levels, c->d_cells, c->d_coefs, c->d_pyr, c->d_blur, c->d_slots, c->d_counts, c->d_cell_off,
                    c->d_level_cnt, c->d_frame_total, c->d_overflow, c->d_dense, c->d_sel, c->d_n_sel, c->d_kps,
                    c->d_kps_un, c->d_desc, c->d_pts, c->d_n_pts, c->d_idx_map, c->d_raw, c->d_processed, c->d_depth,
-                   c->d_uright, c->d_scratch, c->d_kps_in, c->d_n_kp_in};
+                   c->d_uright, c->d_scratch, c->d_kps_in, c->d_n_kp_in, c->qt_scr.perm_a, c->qt_scr.perm_b, c->qt_scr.node_a,
+                   c->qt_scr.node_b, c->qt_scr.scan, c->qt_scr.quad, c->d_sel_lvl, c->d_n_sel_lvl, c->d_lvl_region};
     for (void* p : dev) if (p) cudaFree(p);
     c->trk.release();
     void* host[] = {c->h_scalars, c->h_level_cnt, c->h_frame_total, c->h_overflow, c->h_n_sel, c->h_n_pts, c->h_dense, c->h_sel};
@@ -92,9 +94,31 @@ static int create(const rgbl_config* cfg, Ctx** out) {
     CUF(dmalloc(&c->d_cell_off, (size_t)B * c->n_cells));
     CUF(dmalloc(&c->d_level_cnt, (size_t)B * RGBL_MAX_LEVELS));
     CUF(dmalloc(&c->d_frame_total, (size_t)B));
-    CUF(dmalloc(&c->d_overflow, 1));
-    CUF(cudaMemset(c->d_overflow, 0, sizeof(int)));
+    CUF(dmalloc(&c->d_overflow, 4));
+    CUF(cudaMemset(c->d_overflow, 0, 4 * sizeof(int)));
     CUF(dmalloc(&c->d_dense, (size_t)c->dense_cap));
+    {   // device quad-tree: per-level survivor regions + scratch mirroring the dense candidate buffer
+        std::vector<int> region(nl + 1, 0);
+        bool fits = true;
+        for (int l = 0; l < nl; ++l) {
+            const LevelGeom& g = c->levels[l];
+            const int n_ini = (int)std::round(static_cast<float>(g.max_bx - g.min_bx) / (g.max_by - g.min_by));
+            region[l + 1] = region[l] + std::max(g.quota + 3, 4 * n_ini);
+            if (g.quota + 3 > 1024 || 4 * n_ini > 1024 || n_ini < 1 || n_ini > 64) fits = false;
+        }
+        int dev_smem = 0;
+        cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+        const char* env = getenv("RGBL_HOST_QUADTREE");
+        c->device_quadtree = fits && dev_smem >= quadtree_smem_bytes() && !(env && env[0] == '1');
+        CUF(dmalloc(&c->d_lvl_region, nl + 1));
+        CUF(cudaMemcpy(c->d_lvl_region, region.data(), (nl + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        CUF(dmalloc(&c->d_sel_lvl, (size_t)B * c->cap_kp));
+        CUF(dmalloc(&c->d_n_sel_lvl, (size_t)B * RGBL_MAX_LEVELS));
+        CUF(dmalloc(&c->qt_scr.perm_a, (size_t)c->dense_cap)); CUF(dmalloc(&c->qt_scr.perm_b, (size_t)c->dense_cap));
+        CUF(dmalloc(&c->qt_scr.node_a, (size_t)c->dense_cap)); CUF(dmalloc(&c->qt_scr.node_b, (size_t)c->dense_cap));
+        CUF(dmalloc(&c->qt_scr.scan, (size_t)c->dense_cap + (size_t)B * nl + 8));
+        CUF(dmalloc(&c->qt_scr.quad, (size_t)c->dense_cap));
+    }
     CUF(dmalloc(&c->d_sel, (size_t)B * c->cap_kp));
     CUF(dmalloc(&c->d_n_sel, (size_t)B));
     CUF(dmalloc(&c->d_kps, (size_t)B * c->cap_kp));
@@ -118,7 +142,7 @@ static int create(const rgbl_config* cfg, Ctx** out) {
     CUF(hmalloc(&c->h_scalars, 16));
     CUF(hmalloc(&c->h_level_cnt, (size_t)B * RGBL_MAX_LEVELS));
     CUF(hmalloc(&c->h_frame_total, (size_t)B));
-    CUF(hmalloc(&c->h_overflow, 1));
+    CUF(hmalloc(&c->h_overflow, 4));
     CUF(hmalloc(&c->h_n_sel, (size_t)B));
     CUF(hmalloc(&c->h_dense, (size_t)c->dense_cap));
     CUF(hmalloc(&c->h_sel, (size_t)B * c->cap_kp));
@@ -183,6 +207,25 @@ static int run_extract(Ctx* c, int n_frames, const std::function<void()>& aux_wo
     stage_end(c, ST_BLUR, c->st_aux, nl);
     if (aux_work) aux_work();
     CU(cudaEventRecord(c->ev_blur, c->st_aux));
+    if (c->device_quadtree) {
+        // Fully on-device keypoint distribution: no host round trip between FAST and describe.
+        stage_begin(c, ST_QUADTREE, c->st);
+        if (launch_quadtree(c->st, c->d_dense, c->d_level_cnt, c->d_frame_total, c->d_levels, nl, c->qt_scr, c->d_sel_lvl, c->d_n_sel_lvl,
+                            c->d_lvl_region, c->cap_kp, c->d_overflow + 1, c->d_sel, c->d_n_sel, n_frames) != 0) {
+            c->err = "quad-tree kernel needs more shared memory than this device allows"; return RGBL_E_CUDA;
+        }
+        stage_end(c, ST_QUADTREE, c->st, 2);
+        CU(cudaStreamWaitEvent(c->st, c->ev_blur, 0));
+        stage_begin(c, ST_DESCRIBE, c->st);
+        launch_describe(c->st, c->d_pyr, c->d_blur, c->frame_bytes, c->d_levels, c->d_sel, c->d_n_sel, c->cap_kp, c->cap_kp,
+                        c->tab.umax, c->d_kps, c->d_desc, n_frames);
+        stage_end(c, ST_DESCRIBE, c->st, 1);
+        CU(cudaGetLastError());
+        c->last_frames = n_frames;
+        c->blur_valid = true;
+        c->host_counts_valid = false;
+        return c->cap_kp;        // upper bound of keypoints per frame (exact counts are in d_n_sel)
+    }
     CU(cudaMemcpyAsync(c->h_level_cnt, c->d_level_cnt, (size_t)n_frames * RGBL_MAX_LEVELS * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(c->h_frame_total, c->d_frame_total, (size_t)n_frames * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CU(cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->st));
@@ -265,7 +308,23 @@ static int run_extract(Ctx* c, int n_frames, const std::function<void()>& aux_wo
     CU(cudaGetLastError());
     c->last_frames = n_frames;
     c->blur_valid = true;
+    c->host_counts_valid = true;
     return max_n;
+}
+
+// Device-quad-tree mode: bring the per-frame keypoint counts and the status flags to the host (one small sync).
+static int fetch_counts(Ctx* c, int n_frames) {
+    if (c->host_counts_valid) return RGBL_OK;
+    CU(cudaMemcpyAsync(c->h_n_sel, c->d_n_sel, (size_t)n_frames * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(c->h_overflow, c->d_overflow, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (c->h_overflow[0] || c->h_overflow[1]) {
+        const int a = c->h_overflow[0], b = c->h_overflow[1];
+        cudaMemsetAsync(c->d_overflow, 0, 2 * sizeof(int), c->st);
+        c->err = b ? "device quad-tree capacity exceeded (set RGBL_HOST_QUADTREE=1)" : (a == 1 ? "FAST cell slot overflow (>256 survivors in one cell)" : "candidate buffer overflow: raise max_candidates");
+        return RGBL_E_CAPACITY;
+    }
+    return RGBL_OK;
 }
 
 // Depth maps for n_frames resident point clouds (d_pts / d_n_pts) on stream st.
@@ -337,6 +396,7 @@ int rgbl_orb_extract_batch(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gr
     if (rc) return rc;
     rc = run_extract(c, n_frames);
     if (rc < 0) return rc;
+    rc = fetch_counts(c, n_frames); if (rc) return rc;
     for (int f = 0; f < n_frames; ++f) {
         const int n = c->h_n_sel[f];
         n_out[f] = n;
@@ -432,6 +492,17 @@ int rgbl_orb_get_candidates(rgbl_ctx* ctx, int frame, int level, int32_t* xys, i
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c || !xys || !n_out) return RGBL_E_INVALID;
     int rc = check_frame_level(c, frame, level); if (rc) return rc;
+    if (!c->host_counts_valid) {
+        CU(cudaSetDevice(c->cfg.device));
+        CU(cudaMemcpyAsync(c->h_level_cnt, c->d_level_cnt, (size_t)c->last_frames * RGBL_MAX_LEVELS * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(c->h_frame_total, c->d_frame_total, (size_t)c->last_frames * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        size_t tot = 0;
+        for (int f = 0; f < c->last_frames; ++f) tot += c->h_frame_total[f];
+        if (tot > (size_t)c->dense_cap) { c->err = "candidate buffer overflow"; return RGBL_E_CAPACITY; }
+        if (tot) CU(cudaMemcpyAsync(c->h_dense, c->d_dense, tot * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaStreamSynchronize(c->st));
+    }
     size_t off = 0;
     for (int f = 0; f < frame; ++f) off += c->h_frame_total[f];
     for (int l = 0; l < level; ++l) off += c->h_level_cnt[frame * RGBL_MAX_LEVELS + l];
@@ -531,6 +602,7 @@ static int process_rgbl(Ctx* c, int n_frames, int max_pts, const float P[12], co
 }
 
 static int download_rgbl(Ctx* c, int n_frames, rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out) {
+    { int rc = fetch_counts(c, n_frames); if (rc) return rc; }
     for (int f = 0; f < n_frames; ++f) {
         const int n = c->h_n_sel[f];
         n_out[f] = n;
@@ -584,6 +656,7 @@ int rgbl_resident_process(rgbl_ctx* ctx, const float P[12], const rgbl_depth_par
     if (c->resident_frames < 1) { c->err = "nothing uploaded"; return RGBL_E_INVALID; }
     CU(cudaSetDevice(c->cfg.device));
     int rc = process_rgbl(c, c->resident_frames, c->resident_max_pts, P, prm); if (rc < 0) return rc;
+    if (n_out) { rc = fetch_counts(c, c->resident_frames); if (rc) return rc; }
     CU(cudaStreamSynchronize(c->st));
     CU(cudaStreamSynchronize(c->st_aux));
     prof_collect(c);
@@ -598,6 +671,16 @@ int rgbl_resident_download(rgbl_ctx* ctx, rgbl_keypoint* kps, uint8_t* desc, flo
     if (c->last_frames < 1) { c->err = "nothing processed"; return RGBL_E_INVALID; }
     CU(cudaSetDevice(c->cfg.device));
     return download_rgbl(c, c->last_frames, kps, desc, depth, uright, cap, n_out);
+}
+
+int rgbl_set_host_quadtree(rgbl_ctx* ctx, int on) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!on) {
+        for (const LevelGeom& g : c->levels) if (g.quota + 3 > 1024) { c->err = "quota too large for the device quad-tree"; return RGBL_E_UNSUPPORTED; }
+    }
+    c->device_quadtree = !on;
+    return RGBL_OK;
 }
 
 /* ---- device-side stopwatch on the context's main stream ---- */

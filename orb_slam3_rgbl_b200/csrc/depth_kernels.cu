@@ -48,50 +48,58 @@ __global__ void __launch_bounds__(256) depth_project_kernel(const float* __restr
     }
 }
 
+struct DilateTaps { int n; int8_t dx[81], dy[81]; };
+
 __global__ void __launch_bounds__(256) depth_resolve_dilate_kernel(const float* __restrict__ pts, int pts_stride,
-                                                                   const int* __restrict__ n_pts, DepthDev prm, int W,
-                                                                   int H, const uint32_t* __restrict__ idx_map,
+                                                                   const int* __restrict__ n_pts, DepthDev prm,
+                                                                   DilateTaps taps, int W, int H,
+                                                                   const uint32_t* __restrict__ idx_map,
                                                                    uint32_t stamp, float* __restrict__ raw,
                                                                    float* __restrict__ processed) {
-    constexpr int TW = 32, TH = 8, HALO = 4;
-    __shared__ float t[TH + 2 * HALO][TW + 2 * HALO + 1];
-    __shared__ uint8_t mask[81];
+    constexpr int TW = 32, TH = 32, HALO = 4, SW = TW + 2 * HALO, SH = TH + 2 * HALO;
+    __shared__ float t[SH][SW + 1];
     const int frame = blockIdx.z, tid = threadIdx.x;
+    const int lx = tid & 31, ly = tid >> 5;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    const int ax = prm.ku / 2, ay = prm.kv / 2;
     const int n = n_pts[frame];
     const float* X = pts + (size_t)frame * pts_stride;
     const uint32_t* im = idx_map + (size_t)frame * W * H;
     const float M = prm.inv_scale_m, thr = __fsub_rn(M, 1.0f);
-    if (tid < 81) mask[tid] = prm.mask[tid];
 
-    for (int i = tid; i < (TH + 2 * HALO) * (TW + 2 * HALO); i += 256) {
-        const int r = i / (TW + 2 * HALO), c = i - r * (TW + 2 * HALO);
-        const int gy = y0 + r - HALO, gx = x0 + c - HALO;
-        float tv = -FLT_MAX;                      // out-of-image taps are ignored by cv::dilate
-        if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
-            const uint32_t e = __ldg(im + (size_t)gy * W + gx);
-            float d = 0.f;
-            if ((e >> kStampShift) == stamp) {
-                const int p = (int)(e & kIdxMask) - 1;
-                d = project_row(prm.P + 8, __ldg(X + p), __ldg(X + n + p), __ldg(X + 2 * (size_t)n + p),
-                                __ldg(X + 3 * (size_t)n + p));
+    // rows: warp `ly` handles rows ly, ly+8, ...; lanes cover the 40 columns in two passes
+    for (int r = ly; r < SH; r += 8) {
+        const int gy = y0 + r - HALO;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = lx + 32 * cc;
+            if (c >= SW) break;
+            const int gx = x0 + c - HALO;
+            float tv = -FLT_MAX;                      // out-of-image taps are ignored by cv::dilate
+            if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+                const uint32_t e = __ldg(im + (size_t)gy * W + gx);
+                float d = 0.f;
+                if ((e >> kStampShift) == stamp) {
+                    const int p = (int)(e & kIdxMask) - 1;
+                    d = project_row(prm.P + 8, __ldg(X + p), __ldg(X + n + p), __ldg(X + 2 * (size_t)n + p),
+                                    __ldg(X + 3 * (size_t)n + p));
+                }
+                const bool interior = (r >= HALO && r < HALO + TH && c >= HALO && c < HALO + TW);
+                if (interior && raw) raw[(size_t)frame * W * H + (size_t)gy * W + gx] = d;
+                const float inv = __fsub_rn(M, d);
+                tv = (inv > thr) ? 0.f : inv;         // THRESH_TOZERO_INV at M-1
             }
-            const bool interior = (r >= HALO && r < HALO + TH && c >= HALO && c < HALO + TW);
-            if (interior && raw) raw[(size_t)frame * W * H + (size_t)gy * W + gx] = d;
-            const float inv = __fsub_rn(M, d);
-            tv = (inv > thr) ? 0.f : inv;         // THRESH_TOZERO_INV at M-1
+            t[r][c] = tv;
         }
-        t[r][c] = tv;
     }
     __syncthreads();
-    const int lx = tid & 31, ly = tid >> 5;
-    const int gx = x0 + lx, gy = y0 + ly;
-    if (gx < W && gy < H) {
+    const int gx = x0 + lx;
+    if (gx >= W) return;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = ly + 8 * k, gy = y0 + r;
+        if (gy >= H) break;
         float best = -FLT_MAX;
-        for (int j = 0; j < prm.kv; ++j)
-            for (int i = 0; i < prm.ku; ++i)
-                if (mask[j * prm.ku + i]) best = fmaxf(best, t[ly + HALO + j - ay][lx + HALO + i - ax]);
+        for (int q = 0; q < taps.n; ++q) best = fmaxf(best, t[r + HALO + taps.dy[q]][lx + HALO + taps.dx[q]]);
         const float o = __fsub_rn(M, best);
         processed[(size_t)frame * W * H + (size_t)gy * W + gx] = (o > thr) ? 0.f : o;
     }
@@ -127,8 +135,14 @@ void launch_depth_project(cudaStream_t st, const float* pts, int pts_stride, con
 void launch_depth_resolve_dilate(cudaStream_t st, const float* pts, int pts_stride, const int* n_pts,
                                  const DepthDev& prm, int W, int H, const uint32_t* idx_map, uint32_t stamp,
                                  float* raw, float* processed, int n_frames) {
-    depth_resolve_dilate_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, n_frames), 256, 0, st>>>(
-        pts, pts_stride, n_pts, prm, W, H, idx_map, stamp, raw, processed);
+    DilateTaps taps;
+    taps.n = 0;
+    const int ax = prm.ku / 2, ay = prm.kv / 2;
+    for (int j = 0; j < prm.kv; ++j)
+        for (int i = 0; i < prm.ku; ++i)
+            if (prm.mask[j * prm.ku + i]) { taps.dx[taps.n] = (int8_t)(i - ax); taps.dy[taps.n] = (int8_t)(j - ay); ++taps.n; }
+    depth_resolve_dilate_kernel<<<dim3((W + 31) / 32, (H + 31) / 32, n_frames), 256, 0, st>>>(
+        pts, pts_stride, n_pts, prm, taps, W, H, idx_map, stamp, raw, processed);
 }
 
 void launch_depth_gather(cudaStream_t st, const float* processed, int W, int H, const rgbl_keypoint* kps,

@@ -104,7 +104,7 @@ int build_geometry(int width, int height, const OrbTables& t, std::vector<LevelG
                 c.x0 = (int16_t)iniX; c.y0 = (int16_t)iniY;
                 c.cw = (int16_t)((int)maxX - (int)iniX); c.ch = (int16_t)((int)maxY - (int)iniY);
                 c.off_x = (int16_t)(j * g.w_cell); c.off_y = (int16_t)(i * g.h_cell);
-                if (c.cw > kFastTilePitch - 2 || c.ch > kFastTilePitch - 2) { err = "FAST cell window exceeds the shared-memory tile"; return RGBL_E_UNSUPPORTED; }
+                if (c.cw > 78 || c.ch > 78) { err = "FAST cell window exceeds the shared-memory tile"; return RGBL_E_UNSUPPORTED; }
                 cells.push_back(c);
             }
         }

@@ -49,15 +49,21 @@ __global__ void __launch_bounds__(256) resize_level_kernel(uint8_t* __restrict__
 //   survivors at iniTh = survivors at minTh with s >= iniTh (a weaker neighbour never suppresses).
 // Survivors are written in row-major order (the order cv::FAST returns) into the cell's slot array.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool fast_quick_test(const uint8_t* p, int th) {
+    constexpr int P = kFastTilePitch;
+    const int v = p[0];
+    const int r0 = p[3 * P], r4 = p[3], r8 = p[-3 * P], r12 = p[-3];
+    const int hi_t = v + th, lo_t = v - th;
+    const int ndark = (r0 < lo_t) + (r4 < lo_t) + (r8 < lo_t) + (r12 < lo_t);
+    const int nbright = (r0 > hi_t) + (r4 > hi_t) + (r8 > hi_t) + (r12 > hi_t);
+    return ndark >= 2 || nbright >= 2;           // a 9-arc always covers >= 2 of the 4 compass points
+}
+
 __device__ __forceinline__ int fast_score_at(const uint8_t* p, int th) {
     constexpr int P = kFastTilePitch;
     const int v = p[0];
     int r[16];
     r[0] = p[3 * P]; r[4] = p[3]; r[8] = p[-3 * P]; r[12] = p[-3];
-    const int hi_t = v + th, lo_t = v - th;
-    const int ndark = (r[0] < lo_t) + (r[4] < lo_t) + (r[8] < lo_t) + (r[12] < lo_t);
-    const int nbright = (r[0] > hi_t) + (r[4] > hi_t) + (r[8] > hi_t) + (r[12] > hi_t);
-    if (ndark < 2 && nbright < 2) return 0;      // a 9-arc always covers >= 2 of the 4 compass points
     r[1] = p[3 * P + 1];  r[2] = p[2 * P + 2];   r[3] = p[P + 3];
     r[5] = p[-P + 3];     r[6] = p[-2 * P + 2];  r[7] = p[-3 * P + 1];
     r[9] = p[-3 * P - 1]; r[10] = p[-2 * P - 2]; r[11] = p[-P - 3];
@@ -66,53 +72,92 @@ __device__ __forceinline__ int fast_score_at(const uint8_t* p, int th) {
     return (K > th) ? (K - 1) : 0;
 }
 
+// Phases: (1) window -> shared memory with aligned 32-bit loads; (2) high-speed test on every tested pixel,
+// survivors appended (warp ballot) to a shared list; (3) full arc score only for the listed pixels, densely
+// packed across the CTA (the heavy path no longer runs divergently on whole warps); (4) cell-local NMS +
+// threshold fallback + ordered emission.
 __global__ void __launch_bounds__(256) fast_cells_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
                                                          const LevelGeom* __restrict__ levels,
                                                          const CellInfo* __restrict__ cells, int n_cells,
                                                          int ini_th, int min_th,
                                                          uint32_t* __restrict__ slots, int* __restrict__ counts,
                                                          int* __restrict__ overflow) {
-    constexpr int P = kFastTilePitch;
-    __shared__ __align__(16) uint8_t tile[P * P];
-    __shared__ __align__(16) uint8_t sc[P * P];
+    constexpr int P = kFastTilePitch;            // 88: 3 alignment bytes + 78-byte window, multiple of 4
+    constexpr int ROWS = kFastTilePitch - 8;     // 80 >= max window height 78
+    __shared__ __align__(16) uint8_t tile[P * ROWS];
+    __shared__ __align__(16) uint8_t sc[P * ROWS];
+    __shared__ uint16_t list[72 * 72 + 32];
     __shared__ int warp_sums[8];
+    __shared__ int n_list;
 
     const int cell = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const CellInfo ci = cells[cell];
     const LevelGeom lg = levels[ci.level];
     const int cw = ci.cw, ch = ci.ch;
-    const uint8_t* src = pyr + (size_t)frame * frame_stride + lg.off + (size_t)ci.y0 * lg.pitch + ci.x0;
+    const int a = ci.x0 & 3;                      // byte offset of the window inside its first aligned word
+    const uint8_t* src = pyr + (size_t)frame * frame_stride + lg.off + (size_t)ci.y0 * lg.pitch + (ci.x0 - a);
+    const int nw = (cw + a + 3) >> 2;             // words per row (<= 21)
 
-    for (int i = tid; i < cw * ch; i += 256) {
-        const int y = i / cw, x = i - y * cw;
-        tile[y * P + x] = __ldg(src + (size_t)y * lg.pitch + x);
-        sc[y * P + x] = 0;
+    if (tid == 0) n_list = 0;
+    for (int y = warp; y < ch; y += 8) {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(src + (size_t)y * lg.pitch);
+        uint32_t* t = reinterpret_cast<uint32_t*>(tile + y * P);
+        uint32_t* z = reinterpret_cast<uint32_t*>(sc + y * P);
+        if (lane < nw) { t[lane] = __ldg(g + lane); z[lane] = 0; }
     }
     __syncthreads();
 
     const int tw = cw - 6, th = ch - 6;          // tested region [3, cw-3) x [3, ch-3)
     const int n_t = (tw > 0 && th > 0) ? tw * th : 0;
-    for (int i = tid; i < n_t; i += 256) {
-        const int y = i / tw + 3, x = i - (y - 3) * tw + 3;
-        const int s = fast_score_at(&tile[y * P + x], min_th);
-        sc[y * P + x] = (uint8_t)s;
+    {
+        // incremental (x, y) of flattened index i = tid + 256*k without per-iteration divisions
+        const int q = (tw > 0) ? 256 / tw : 0, r = (tw > 0) ? 256 - q * tw : 0;
+        int y = (tw > 0) ? tid / tw : 0, x = tid - y * tw;
+        for (int i0 = 0; i0 < n_t; i0 += 256) {
+            const bool valid = (i0 + tid) < n_t;
+            bool pass = false;
+            int pos = 0;
+            if (valid) {
+                pos = (y + 3) * P + x + 3 + a;
+                pass = fast_quick_test(&tile[pos], min_th);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&n_list, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)pos;
+            x += r; y += q;
+            if (x >= tw) { x -= tw; ++y; }
+        }
+    }
+    __syncthreads();
+    const int nl = n_list;
+    for (int j = tid; j < nl; j += 256) {
+        const int pos = list[j];
+        sc[pos] = (uint8_t)fast_score_at(&tile[pos], min_th);
     }
     __syncthreads();
 
     // contiguous row-major chunk per thread -> ordered emission
-    const int per = (n_t + 255) / 256;           // <= 21 for windows < 78 px
+    const int per = (n_t + 255) / 256;           // <= 21 for windows <= 78 px
     const int beg = min(tid * per, n_t), end = min(beg + per, n_t);
     uint32_t m_min = 0, m_ini = 0;
-    for (int i = beg; i < end; ++i) {
-        const int y = i / tw + 3, x = i - (y - 3) * tw + 3;
-        const uint8_t* c = &sc[y * P + x];
-        const int s = c[0];
-        if (s == 0) continue;
-        const bool keep = s > c[-1] && s > c[1] && s > c[-P - 1] && s > c[-P] && s > c[-P + 1] &&
-                          s > c[P - 1] && s > c[P] && s > c[P + 1];
-        if (keep) {
-            m_min |= 1u << (i - beg);
-            if (s >= ini_th) m_ini |= 1u << (i - beg);
+    int y0c = (tw > 0) ? beg / tw : 0, x0c = beg - y0c * tw;
+    {
+        int y = y0c, x = x0c;
+        for (int i = beg; i < end; ++i) {
+            const uint8_t* c = &sc[(y + 3) * P + x + 3 + a];
+            const int s = c[0];
+            if (s != 0) {
+                const bool keep = s > c[-1] && s > c[1] && s > c[-P - 1] && s > c[-P] && s > c[-P + 1] &&
+                                  s > c[P - 1] && s > c[P] && s > c[P + 1];
+                if (keep) {
+                    m_min |= 1u << (i - beg);
+                    if (s >= ini_th) m_ini |= 1u << (i - beg);
+                }
+            }
+            if (++x == tw) { x = 0; ++y; }
         }
     }
     const int any_ini = __syncthreads_or(m_ini != 0);
@@ -120,7 +165,6 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const uint8_t* __restri
     const int cnt = __popc(m);
 
     // block-wide exclusive scan of cnt
-    const int lane = tid & 31, warp = tid >> 5;
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -142,9 +186,9 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const uint8_t* __restri
     while (mm) {
         const int b = __ffs(mm) - 1;
         mm &= mm - 1;
-        const int i = beg + b;
-        const int y = i / tw + 3, x = i - (y - 3) * tw + 3;
-        if (pos < kCellCap) out[pos] = pack_cand_dev(x + ci.off_x, y + ci.off_y, sc[y * P + x]);
+        int x = x0c + b, y = y0c;
+        while (x >= tw) { x -= tw; ++y; }
+        if (pos < kCellCap) out[pos] = pack_cand_dev(x + 3 + ci.off_x, y + 3 + ci.off_y, sc[(y + 3) * P + x + 3 + a]);
         ++pos;
     }
     if (tid == 0) {
@@ -232,38 +276,77 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 
 __global__ void __launch_bounds__(256) blur_level_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
                                                          size_t frame_stride, LevelGeom lg) {
-    constexpr int TW = 64, TH = 32, IW = TW + 6, IH = TH + 6;
-    __shared__ uint8_t in[IH][IW + 2];
-    __shared__ uint16_t hb[IH][TW];
+    // CTA tile: 128 x 32 outputs.  Input rows are staged as 32-bit words (aligned loads in the interior, per-byte
+    // REFLECT_101 assembly on the level's edges); the horizontal pass keeps 8.8 sums packed as u16x2; the vertical
+    // pass gives every thread a 4 x 4 output block (one 32-bit store per row).
+    constexpr int TW = 128, TH = 32, IH = TH + 6, IWW = (TW + 8) / 4;     // 34 input words per row: x0-4 .. x0+131
+    __shared__ uint32_t in[IH][IWW + 1];
+    __shared__ uint32_t hb[IH][TW / 2 + 1];
     const uint8_t* s = pyr + (size_t)blockIdx.z * frame_stride + lg.off;
     uint8_t* d = blur + (size_t)blockIdx.z * frame_stride + lg.off;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, tid = threadIdx.x;
-    for (int i = tid; i < IW * IH; i += 256) {
-        const int r = i / IW, c = i - r * IW;
-        const int gy = reflect101(y0 + r - 3, lg.h), gx = reflect101(x0 + c - 3, lg.w);
-        in[r][c] = __ldg(s + (size_t)gy * lg.pitch + gx);
-    }
-    __syncthreads();
-    for (int i = tid; i < TW * IH; i += 256) {
-        const int r = i / TW, c = i - r * TW;
-        const uint8_t* p = &in[r][c];
-        const int acc = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
-        hb[r][c] = (uint16_t)acc;
-    }
-    __syncthreads();
-    for (int i = tid; i < (TW / 4) * TH; i += 256) {
-        const int r = i / (TW / 4), c4 = (i - r * (TW / 4)) * 4;
-        const int gy = y0 + r, gx = x0 + c4;
-        if (gy >= lg.h || gx >= lg.w) continue;
-        uint32_t out = 0;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int r = warp; r < IH; r += 8) {
+        const int gy = reflect101(y0 + r - 3, lg.h);
+        const uint8_t* row = s + (size_t)gy * lg.pitch;
+        for (int w = lane; w < IWW; w += 32) {
+            const int gx = x0 - 4 + 4 * w;
+            uint32_t v;
+            if (gx >= 0 && gx + 3 < lg.w) {
+                v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+            } else {
+                v = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = c4 + k;
-            const uint32_t acc = 18u * (hb[r][c] + hb[r + 6][c]) + 34u * (hb[r + 1][c] + hb[r + 5][c]) +
-                                 48u * (hb[r + 2][c] + hb[r + 4][c]) + 56u * hb[r + 3][c];
-            out |= ((acc + 32768u) >> 16) << (8 * k);
+                for (int k = 0; k < 4; ++k) {
+                    int px = gx + k;
+                    px = reflect101(px, lg.w);
+                    px = min(max(px, 0), lg.w - 1);             // tiles hanging far over the right edge: value unused
+                    v |= (uint32_t)__ldg(row + px) << (8 * k);
+                }
+            }
+            in[r][w] = v;
         }
-        *reinterpret_cast<uint32_t*>(d + (size_t)gy * lg.pitch + gx) = out;
+    }
+    __syncthreads();
+    for (int item = tid; item < IH * 32; item += 256) {
+        const int r = item >> 5, g = item & 31;                 // g: group of 4 output columns
+        const uint32_t w0 = in[r][g], w1 = in[r][g + 1], w2 = in[r][g + 2];
+        int b[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { b[k] = (w0 >> (8 * k)) & 0xff; b[4 + k] = (w1 >> (8 * k)) & 0xff; b[8 + k] = (w2 >> (8 * k)) & 0xff; }
+        uint32_t acc[4];
+#pragma unroll
+        for (int jx = 0; jx < 4; ++jx)
+            acc[jx] = 18 * (b[1 + jx] + b[7 + jx]) + 34 * (b[2 + jx] + b[6 + jx]) + 48 * (b[3 + jx] + b[5 + jx]) + 56 * b[4 + jx];
+        hb[r][2 * g] = acc[0] | (acc[1] << 16);
+        hb[r][2 * g + 1] = acc[2] | (acc[3] << 16);
+    }
+    __syncthreads();
+    {
+        const int g = lane, rg = warp;                          // 32 column groups x 8 row groups of 4 rows
+        const int gx = x0 + 4 * g;
+        if (gx >= lg.w) return;
+        uint32_t c0[10], c1[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { c0[k] = hb[4 * rg + k][2 * g]; c1[k] = hb[4 * rg + k][2 * g + 1]; }
+#pragma unroll
+        for (int ry = 0; ry < 4; ++ry) {
+            const int gy = y0 + 4 * rg + ry;
+            if (gy >= lg.h) break;
+            uint32_t out = 0;
+#pragma unroll
+            for (int jx = 0; jx < 4; ++jx) {
+                uint32_t h[7];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    const uint32_t w = (jx < 2) ? c0[ry + k] : c1[ry + k];
+                    h[k] = (jx & 1) ? (w >> 16) : (w & 0xffffu);
+                }
+                const uint32_t acc = 18u * (h[0] + h[6]) + 34u * (h[1] + h[5]) + 48u * (h[2] + h[4]) + 56u * h[3];
+                out |= ((acc + 32768u) >> 16) << (8 * jx);
+            }
+            *reinterpret_cast<uint32_t*>(d + (size_t)gy * lg.pitch + gx) = out;
+        }
     }
 }
 
@@ -388,7 +471,7 @@ void launch_blur(cudaStream_t st, const uint8_t* pyr, uint8_t* blur, size_t fram
                  int n_levels, int n_frames) {
     for (int l = 0; l < n_levels; ++l) {
         const LevelGeom& lg = h_levels[l];
-        dim3 grd((lg.w + 63) / 64, (lg.h + 31) / 32, n_frames);
+        dim3 grd((lg.w + 127) / 128, (lg.h + 31) / 32, n_frames);
         blur_level_kernel<<<grd, 256, 0, st>>>(pyr, blur, frame_stride, lg);
     }
 }

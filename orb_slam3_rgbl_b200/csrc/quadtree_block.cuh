@@ -1,0 +1,493 @@
+// Block-parallel quad-tree keypoint distribution: the semantics of ORBextractor::DistributeOctTree
+// (src/ORBextractor.cc:555-779) for ONE (frame, level), executed by one CTA.  The sequential reference
+// (std::list + std::vector per node + std::sort) is re-expressed as bulk-synchronous passes:
+//
+//   * the node "list" is an array kept in list order and rebuilt every pass:
+//        new list = reverse(children pushed this pass, in push order)  ++  surviving old nodes in old order
+//   * every node owns a contiguous segment of one key permutation; dividing a set D of nodes is a segmented,
+//     stable 4-way partition computed with one block-wide scan of packed quadrant counters
+//   * the budgeted expansion (":689-754") sorts (size, UL.x) with an exact re-implementation of libstdc++'s
+//     std::sort (introsort: median-of-3 to first, unguarded partition, heapsort fallback, final insertion
+//     sort with threshold 16) so that ties land exactly where the reference's sort puts them, then finds how
+//     many nodes the sequential loop would divide before the list reaches N with a prefix sum
+//   * survivors = first key with the maximal response per node, emitted in list order.
+//
+// The same source compiles for the host (QT_HOST: every phase runs its "threads" sequentially) so the logic is
+// validated on the CPU against the oracle's std::list restatement (tests/test_host_abi.py).
+#ifndef RGBL_QUADTREE_BLOCK_CUH
+#define RGBL_QUADTREE_BLOCK_CUH
+
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__)
+#define QT_DEVICE 1
+#define QT_FN __device__
+#define QT_NT ((int)blockDim.x)
+#define QT_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
+#define QT_SYNC() __syncthreads()
+#define QT_SINGLE if (threadIdx.x == 0)
+#else
+#define QT_DEVICE 0
+#define QT_FN inline
+#define QT_NT 1
+#define QT_FOR(i, n) for (int i = 0; i < (n); ++i)
+#define QT_SYNC()
+#define QT_SINGLE
+#include <cmath>
+#endif
+
+namespace rgbl {
+namespace qt {
+
+constexpr int kMaxNodes = 1024;       // list capacity (needs quota + 3 <= kMaxNodes and 4 * nIni <= kMaxNodes)
+constexpr int kMaxRoots = 64;
+
+struct SortItem { int size; int ulx; int node; };
+
+QT_FN bool item_less(const SortItem& a, const SortItem& b) {       // compareNodes, src/ORBextractor.cc:538-553
+    if (a.size < b.size) return true;
+    if (a.size > b.size) return false;
+    return a.ulx < b.ulx;
+}
+
+// ---- libstdc++ std::sort, restated (bits/stl_algo.h: __introsort_loop, __final_insertion_sort; bits/stl_heap.h) ----
+QT_FN void qs_swap(SortItem* v, int a, int b) { const SortItem t = v[a]; v[a] = v[b]; v[b] = t; }
+
+QT_FN void qs_adjust_heap(SortItem* first, int hole, int len, SortItem value) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (item_less(first[child], first[child - 1])) --child;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;                       // __push_heap
+    while (hole > top && item_less(first[parent], value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+
+QT_FN void qs_heapsort(SortItem* first, int len) {     // __partial_sort(first, last, last): make_heap + sort_heap
+    if (len < 2) return;
+    for (int parent = (len - 2) / 2;; --parent) {
+        const SortItem v = first[parent];
+        qs_adjust_heap(first, parent, len, v);
+        if (parent == 0) break;
+    }
+    for (int last = len; last > 1;) {
+        --last;
+        const SortItem v = first[last];
+        first[last] = first[0];
+        qs_adjust_heap(first, 0, last, v);
+    }
+}
+
+QT_FN void qs_unguarded_linear_insert(SortItem* v, int last) {
+    const SortItem val = v[last];
+    int next = last - 1;
+    while (item_less(val, v[next])) { v[last] = v[next]; last = next; --next; }
+    v[last] = val;
+}
+
+QT_FN void qs_insertion_sort(SortItem* v, int first, int last) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (item_less(v[i], v[first])) {
+            const SortItem val = v[i];
+            for (int k = i; k > first; --k) v[k] = v[k - 1];
+            v[first] = val;
+        } else {
+            qs_unguarded_linear_insert(v, i);
+        }
+    }
+}
+
+QT_FN void std_sort(SortItem* v, int n) {
+    if (n <= 1) return;
+    // iterative form of __introsort_loop: an explicit stack of (first, last, depth) for the right-hand recursions
+    int stk_first[64], stk_last[64], stk_depth[64], sp = 0;
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) ++lg;
+    stk_first[0] = 0; stk_last[0] = n; stk_depth[0] = 2 * lg; sp = 1;
+    while (sp > 0) {
+        --sp;
+        int first = stk_first[sp], last = stk_last[sp], depth = stk_depth[sp];
+        while (last - first > 16) {
+            if (depth == 0) { qs_heapsort(v + first, last - first); break; }
+            --depth;
+            // __unguarded_partition_pivot
+            const int mid = first + (last - first) / 2;
+            {   // __move_median_to_first(first, first+1, mid, last-1)
+                const int a = first + 1, b = mid, c = last - 1;
+                if (item_less(v[a], v[b])) {
+                    if (item_less(v[b], v[c])) qs_swap(v, first, b);
+                    else if (item_less(v[a], v[c])) qs_swap(v, first, c);
+                    else qs_swap(v, first, a);
+                } else if (item_less(v[a], v[c])) qs_swap(v, first, a);
+                else if (item_less(v[b], v[c])) qs_swap(v, first, c);
+                else qs_swap(v, first, b);
+            }
+            int lo = first + 1, hi = last;
+            for (;;) {   // __unguarded_partition(first+1, last, pivot=first)
+                while (item_less(v[lo], v[first])) ++lo;
+                --hi;
+                while (item_less(v[first], v[hi])) --hi;
+                if (!(lo < hi)) break;
+                qs_swap(v, lo, hi);
+                ++lo;
+            }
+            const int cut = lo;
+            // recurse on [cut, last) (the reference recurses first, then loops on [first, cut)): the two ranges
+            // are disjoint, so the processing order does not change the result
+            stk_first[sp] = cut; stk_last[sp] = last; stk_depth[sp] = depth; ++sp;
+            last = cut;
+        }
+    }
+    // __final_insertion_sort
+    if (n > 16) {
+        qs_insertion_sort(v, 0, 16);
+        for (int i = 16; i < n; ++i) qs_unguarded_linear_insert(v, i);
+    } else {
+        qs_insertion_sort(v, 0, n);
+    }
+}
+
+// ---- shared-memory state of one tree ------------------------------------------------------------------
+struct NodeTable {
+    short ulx[kMaxNodes], uly[kMaxNodes], brx[kMaxNodes], bry[kMaxNodes];
+    int beg[kMaxNodes], end[kMaxNodes];
+};
+
+struct Shared {
+    NodeTable tab[2];
+    // per node of the current table
+    int cc[kMaxNodes][4];          // child key counts of a node that is being divided
+    short pushes[kMaxNodes];       // non-empty children (0 if the node is not divided this pass)
+    short proc[kMaxNodes];         // processing rank inside D (-1 = not divided)
+    int pushbase[kMaxNodes];       // exclusive prefix of pushes in processing order (indexed by processing rank)
+    int keepbase[kMaxNodes];       // exclusive prefix of "survives" flags in list order
+    short by_rank[kMaxNodes];      // node index by processing rank
+    SortItem open[2][kMaxNodes];   // expandable children: [cur] produced by the last pass, [1-cur] being built
+    int open_slot[kMaxNodes * 4];  // per push index: position in the next open list, or -1
+    int n_nodes, n_open, cur_tab, cur_open, n_div, total_push, n_keep, n_expand, scan_total, flag;
+    int root_cnt[kMaxRoots + 1];
+    unsigned long long scan_carry[1024 + 32];
+};
+
+// global scratch of one tree (segments of the per-batch arrays)
+struct Scratch {
+    int* perm_a; int* perm_b;                // key permutation (ping-pong)
+    int* node_a; int* node_b;                // node index of the key at each position (ping-pong)
+    unsigned long long* scan;                // n + 1 packed quadrant counters
+    unsigned char* quad;                     // quadrant of the key at each position (4 = not moving)
+};
+
+// Exclusive scan of packed counters a[0..n) -> a (exclusive), a[n] = total.  Block-parallel on the device.
+QT_FN void scan_u64(unsigned long long* a, int n, Shared& s) {
+#if QT_DEVICE
+    const int nt = blockDim.x, tid = threadIdx.x;
+    const int per = (n + nt - 1) / nt;
+    const int b = min(tid * per, n), e = min(b + per, n);
+    unsigned long long sum = 0;
+    for (int i = b; i < e; ++i) sum += a[i];
+    s.scan_carry[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long run = 0;
+        for (int t = 0; t < nt; ++t) { const unsigned long long v = s.scan_carry[t]; s.scan_carry[t] = run; run += v; }
+        a[n] = run;
+    }
+    __syncthreads();
+    unsigned long long run = s.scan_carry[tid];
+    for (int i = b; i < e; ++i) { const unsigned long long v = a[i]; a[i] = run; run += v; }
+    __syncthreads();
+#else
+    unsigned long long run = 0;
+    for (int i = 0; i < n; ++i) { const unsigned long long v = a[i]; a[i] = run; run += v; }
+    a[n] = run;
+    (void)s;
+#endif
+}
+
+QT_FN int cand_x(unsigned int c) { return (int)(c & 0xfffu); }
+QT_FN int cand_y(unsigned int c) { return (int)((c >> 12) & 0xfffu); }
+QT_FN int cand_s(unsigned int c) { return (int)(c >> 24); }
+
+// Divide the nodes marked in s.proc (processing rank >= 0, s.n_div of them, s.by_rank filled) and rebuild the list.
+// On exit: s.cur_tab flipped, s.n_nodes updated, s.open[1-cur_open] holds the new expandable children in push
+// order and s.cur_open is flipped; perm/node arrays flipped by the caller-visible flag `pp` (returns new value).
+QT_FN int divide_pass(Shared& s, const unsigned int* cand, int n, Scratch g, int pp) {
+    NodeTable& T = s.tab[s.cur_tab];
+    NodeTable& U = s.tab[1 - s.cur_tab];
+    int* perm = pp ? g.perm_b : g.perm_a;
+    int* perm2 = pp ? g.perm_a : g.perm_b;
+    int* nod = pp ? g.node_b : g.node_a;
+    int* nod2 = pp ? g.node_a : g.node_b;
+    const int nn = s.n_nodes;
+
+    // quadrant of every key that belongs to a divided node
+    QT_FOR(p, n) {
+        const int nd = nod[p];
+        unsigned long long v = 0;
+        unsigned char q = 4;
+        if (s.proc[nd] >= 0) {
+            const int hx = (T.brx[nd] - T.ulx[nd] + 1) >> 1;           // ceil(float(w)/2) for w >= 0
+            const int hy = (T.bry[nd] - T.uly[nd] + 1) >> 1;
+            const int mx = T.ulx[nd] + hx, my = T.uly[nd] + hy;
+            const unsigned int c = cand[perm[p]];
+            q = (unsigned char)((cand_x(c) < mx) ? ((cand_y(c) < my) ? 0 : 2) : ((cand_y(c) < my) ? 1 : 3));
+            v = 1ull << (16 * q);
+        }
+        g.quad[p] = q;
+        g.scan[p] = v;
+    }
+    QT_SYNC();
+    scan_u64(g.scan, n, s);
+    QT_SYNC();
+    // child counts and number of pushes per divided node
+    QT_FOR(i, nn) {
+        int k = 0;
+        if (s.proc[i] >= 0) {
+            const unsigned long long d = g.scan[T.end[i]] - g.scan[T.beg[i]];
+            for (int q = 0; q < 4; ++q) { const int c = (int)((d >> (16 * q)) & 0xffffu); s.cc[i][q] = c; k += (c > 0); }
+        }
+        s.pushes[i] = (short)k;
+    }
+    QT_SYNC();
+    // prefix of pushes in processing order, prefix of survivors in list order (serial: <= 1024 nodes)
+    QT_SINGLE {
+        int run = 0;
+        for (int r = 0; r < s.n_div; ++r) { s.pushbase[r] = run; run += s.pushes[s.by_rank[r]]; }
+        s.total_push = run;
+        int keep = 0;
+        for (int i = 0; i < nn; ++i) { s.keepbase[i] = keep; keep += (s.proc[i] < 0); }
+        s.n_keep = keep;
+    }
+    QT_SYNC();
+    const int total_push = s.total_push;
+    // new node table: children (reverse push order) then survivors
+    QT_FOR(i, nn) {
+        if (s.proc[i] < 0) {
+            const int j = total_push + s.keepbase[i];
+            U.ulx[j] = T.ulx[i]; U.uly[j] = T.uly[i]; U.brx[j] = T.brx[i]; U.bry[j] = T.bry[i];
+            U.beg[j] = T.beg[i]; U.end[j] = T.end[i];
+        } else {
+            const int hx = (T.brx[i] - T.ulx[i] + 1) >> 1, hy = (T.bry[i] - T.uly[i] + 1) >> 1;
+            const int mx = T.ulx[i] + hx, my = T.uly[i] + hy;
+            const int x0[4] = {T.ulx[i], mx, T.ulx[i], mx}, y0[4] = {T.uly[i], T.uly[i], my, my};
+            const int x1[4] = {mx, T.brx[i], mx, T.brx[i]}, y1[4] = {my, my, T.bry[i], T.bry[i]};
+            int push = s.pushbase[s.proc[i]], start = T.beg[i];
+            for (int q = 0; q < 4; ++q) {
+                const int c = s.cc[i][q];
+                if (c == 0) continue;
+                const int j = total_push - 1 - push;
+                U.ulx[j] = (short)x0[q]; U.uly[j] = (short)y0[q]; U.brx[j] = (short)x1[q]; U.bry[j] = (short)y1[q];
+                U.beg[j] = start; U.end[j] = start + c;
+                s.open_slot[push] = (c > 1) ? 1 : 0;
+                start += c;
+                ++push;
+            }
+        }
+    }
+    QT_SYNC();
+    // expandable children in push order -> next open list
+    QT_SINGLE {
+        int m = 0;
+        SortItem* o = s.open[1 - s.cur_open];
+        for (int push = 0; push < total_push; ++push) {
+            if (!s.open_slot[push]) continue;
+            const int j = total_push - 1 - push;
+            o[m].size = U.end[j] - U.beg[j]; o[m].ulx = U.ulx[j]; o[m].node = j; ++m;
+        }
+        s.n_expand = m;
+    }
+    // move the keys: stable 4-way partition inside every divided segment; everything else keeps its place
+    QT_FOR(p, n) {
+        const int nd = nod[p];
+        int np = p, nj;
+        if (s.proc[nd] < 0) {
+            nj = total_push + s.keepbase[nd];
+        } else {
+            const int q = g.quad[p], b = T.beg[nd];
+            int before = 0, rankq = 0;
+            for (int qq = 0; qq < q; ++qq) before += s.cc[nd][qq];
+            int nonempty_before = 0;
+            for (int qq = 0; qq < q; ++qq) nonempty_before += (s.cc[nd][qq] > 0);
+            rankq = (int)(((g.scan[p] - g.scan[b]) >> (16 * q)) & 0xffffu);
+            np = b + before + rankq;
+            nj = total_push - 1 - (s.pushbase[s.proc[nd]] + nonempty_before);
+        }
+        perm2[np] = perm[p];
+        nod2[np] = nj;
+    }
+    QT_SYNC();
+    QT_SINGLE {
+        s.n_nodes = total_push + s.n_keep;
+        s.cur_tab = 1 - s.cur_tab;
+        s.cur_open = 1 - s.cur_open;
+        s.n_open = s.n_expand;
+    }
+    QT_SYNC();
+    return 1 - pp;
+}
+
+// Whole DistributeOctTree.  cand: n packed candidates (x, y relative to (minX, minY), reference order).
+// out: packed candidates of the survivors in the reference's output order.  Returns the count (or -1 if the
+// configuration exceeds the on-chip capacities; the caller then uses the host implementation).
+QT_FN int distribute(Shared& s, const unsigned int* cand, int n, int width, int height, int N, Scratch g,
+                     unsigned int* out, int out_cap) {
+    if (n <= 0) return 0;
+#if QT_DEVICE
+    const int n_ini = (int)roundf(static_cast<float>(width) / height);
+#else
+    const int n_ini = (int)std::round(static_cast<float>(width) / height);
+#endif
+    if (n_ini < 1 || n_ini > kMaxRoots || 4 * n_ini > kMaxNodes || N + 3 > kMaxNodes || n >= 65535) return -1;
+    const float hX = static_cast<float>(width) / n_ini;
+
+    // ---- roots: stable bucket of the candidates by root index ----
+    QT_FOR(r, n_ini + 1) s.root_cnt[r] = 0;
+    QT_SYNC();
+    int pp = 0;
+    // one stable pass per root (n_ini is tiny): positions from a scan of the membership flags
+    QT_SINGLE { s.flag = 0; }
+    QT_SYNC();
+    for (int r = 0; r < n_ini; ++r) {
+        QT_FOR(p, n) {
+            int rr = (int)(static_cast<float>(cand_x(cand[p])) / hX);
+            if (rr >= n_ini) rr = n_ini - 1;
+            g.scan[p] = (rr == r) ? 1ull : 0ull;
+        }
+        QT_SYNC();
+        scan_u64(g.scan, n, s);
+        QT_SYNC();
+        const int base = s.flag;
+        QT_FOR(p, n) {
+            int rr = (int)(static_cast<float>(cand_x(cand[p])) / hX);
+            if (rr >= n_ini) rr = n_ini - 1;
+            if (rr == r) g.perm_a[base + (int)g.scan[p]] = p;
+        }
+        QT_SYNC();
+        QT_SINGLE { s.root_cnt[r] = (int)g.scan[n]; s.flag = base + (int)g.scan[n]; }
+        QT_SYNC();
+    }
+    QT_SINGLE {
+        NodeTable& T = s.tab[0];
+        int m = 0, start = 0;
+        for (int r = 0; r < n_ini; ++r) {
+            const int c = s.root_cnt[r];
+            if (c > 0) {
+                T.ulx[m] = (short)(int)(hX * static_cast<float>(r)); T.uly[m] = 0;
+                T.brx[m] = (short)(int)(hX * static_cast<float>(r + 1)); T.bry[m] = (short)height;
+                T.beg[m] = start; T.end[m] = start + c;
+                ++m;
+            }
+            start += c;
+        }
+        s.n_nodes = m; s.cur_tab = 0; s.cur_open = 0; s.n_open = 0;
+    }
+    QT_SYNC();
+    {
+        const NodeTable& T = s.tab[0];
+        const int m = s.n_nodes;
+        QT_FOR(i, m) { for (int p = T.beg[i]; p < T.end[i]; ++p) g.node_a[p] = i; }
+    }
+    QT_SYNC();
+
+    // ---- subdivision loop (src/ORBextractor.cc:609-755) ----
+    for (;;) {
+        const int prev = s.n_nodes;
+        {   // full pass: D = every node with more than one key, processed in list order
+            const NodeTable& T = s.tab[s.cur_tab];
+            QT_SINGLE {
+                int r = 0;
+                for (int i = 0; i < prev; ++i) {
+                    if (T.end[i] - T.beg[i] > 1) { s.proc[i] = (short)r; s.by_rank[r] = (short)i; ++r; }
+                    else s.proc[i] = -1;
+                }
+                s.n_div = r;
+            }
+            QT_SYNC();
+        }
+        pp = divide_pass(s, cand, n, g, pp);
+        const int size = s.n_nodes, n_expand = s.n_open;
+        if (size >= N || size == prev) break;
+        if (size + n_expand * 3 > N) {
+            // budgeted expansion: biggest nodes first, stop as soon as the list holds N nodes
+            bool done = false;
+            while (!done) {
+                const int prev2 = s.n_nodes;
+                const int n_open = s.n_open;
+                QT_SINGLE { std_sort(s.open[s.cur_open], n_open); }
+                QT_SYNC();
+                // child counts of every open node (they are all candidates for division)
+                {
+                    const NodeTable& T = s.tab[s.cur_tab];
+                    QT_FOR(i, prev2) s.proc[i] = -1;
+                    QT_SYNC();
+                    QT_FOR(k, n_open) { const int r = n_open - 1 - k; s.proc[s.open[s.cur_open][k].node] = (short)r; s.by_rank[r] = (short)s.open[s.cur_open][k].node; }
+                    QT_SYNC();
+                    // count non-empty children per open node with a direct scan of its (small) key segment
+                    int* perm = pp ? g.perm_b : g.perm_a;
+                    QT_FOR(r, n_open) {
+                        const int nd = s.by_rank[r];
+                        const int hx = (T.brx[nd] - T.ulx[nd] + 1) >> 1, hy = (T.bry[nd] - T.uly[nd] + 1) >> 1;
+                        const int mx = T.ulx[nd] + hx, my = T.uly[nd] + hy;
+                        int mask = 0;
+                        for (int p = T.beg[nd]; p < T.end[nd]; ++p) {
+                            const unsigned int c = cand[perm[p]];
+                            mask |= 1 << ((cand_x(c) < mx) ? ((cand_y(c) < my) ? 0 : 2) : ((cand_y(c) < my) ? 1 : 3));
+                        }
+                        s.pushes[nd] = (short)(((mask >> 0) & 1) + ((mask >> 1) & 1) + ((mask >> 2) & 1) + ((mask >> 3) & 1));
+                    }
+                    QT_SYNC();
+                    QT_SINGLE {
+                        int size2 = prev2, m = 0;
+                        for (int r = 0; r < n_open; ++r) {
+                            size2 += s.pushes[s.by_rank[r]] - 1;
+                            ++m;
+                            if (size2 >= N) break;
+                        }
+                        // nodes beyond the break are not divided in this iteration
+                        for (int r = m; r < n_open; ++r) s.proc[s.by_rank[r]] = -1;
+                        s.n_div = m;
+                    }
+                    QT_SYNC();
+                }
+                pp = divide_pass(s, cand, n, g, pp);
+                if (s.n_nodes >= N || s.n_nodes == prev2) done = true;
+            }
+            break;
+        }
+    }
+
+    // ---- best key per node, in list order (src/ORBextractor.cc:757-776) ----
+    {
+        const NodeTable& T = s.tab[s.cur_tab];
+        const int* perm = pp ? g.perm_b : g.perm_a;
+        const int m = s.n_nodes;
+        QT_FOR(i, m) {
+            unsigned int best = cand[perm[T.beg[i]]];
+            for (int p = T.beg[i] + 1; p < T.end[i]; ++p) {
+                const unsigned int c = cand[perm[p]];
+                if (cand_s(c) > cand_s(best)) best = c;
+            }
+            if (i < out_cap) out[i] = best;
+        }
+        QT_SYNC();
+        return m;
+    }
+}
+
+}  // namespace qt
+}  // namespace rgbl
+#endif

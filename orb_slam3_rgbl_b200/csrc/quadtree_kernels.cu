@@ -1,0 +1,113 @@
+// Device quad-tree distribution (one CTA per (frame, level)) + packing of the per-level survivor lists into the
+// per-frame SelKp list the describe kernel consumes.  Algorithm: quadtree_block.cuh.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "quadtree_block.cuh"
+#include "rgbl_kernels.h"
+
+namespace rgbl {
+
+__global__ void __launch_bounds__(512) quadtree_kernel(const uint32_t* __restrict__ dense, const int* __restrict__ level_cnt,
+                                                       const int* __restrict__ frame_total, const LevelGeom* __restrict__ levels,
+                                                       int n_levels, QtScratchDev scr, uint32_t* __restrict__ sel_lvl,
+                                                       int* __restrict__ n_sel_lvl, const int* __restrict__ lvl_region,
+                                                       int cap_kp, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    qt::Shared& s = *reinterpret_cast<qt::Shared*>(smem_raw);
+    const int l = blockIdx.x, f = blockIdx.y;
+    int off = 0;
+    for (int k = 0; k < f; ++k) off += frame_total[k];
+    for (int k = 0; k < l; ++k) off += level_cnt[f * RGBL_MAX_LEVELS + k];
+    const int n = level_cnt[f * RGBL_MAX_LEVELS + l];
+    const LevelGeom lg = levels[l];
+    qt::Scratch g;
+    const int so = off + (f * n_levels + l);          // one extra scan slot per preceding tree
+    g.perm_a = scr.perm_a + off; g.perm_b = scr.perm_b + off; g.node_a = scr.node_a + off; g.node_b = scr.node_b + off;
+    g.scan = scr.scan + so; g.quad = scr.quad + off;
+    uint32_t* out = sel_lvl + (size_t)f * cap_kp + lvl_region[l];
+    const int region_cap = lvl_region[l + 1] - lvl_region[l];
+    const int m = qt::distribute(s, dense + off, n, lg.max_bx - lg.min_bx, lg.max_by - lg.min_by, lg.quota, g, out, region_cap);
+    if (threadIdx.x == 0) {
+        if (m < 0 || m > region_cap) { atomicExch(status, 1); n_sel_lvl[f * RGBL_MAX_LEVELS + l] = 0; }
+        else n_sel_lvl[f * RGBL_MAX_LEVELS + l] = m;
+    }
+}
+
+// per frame: concatenate the level regions -> SelKp list (+16 offset applied) and n_sel
+__global__ void __launch_bounds__(256) sel_pack_kernel(const uint32_t* __restrict__ sel_lvl, const int* __restrict__ n_sel_lvl,
+                                                       const int* __restrict__ lvl_region, int n_levels, int cap_kp,
+                                                       SelKp* __restrict__ sel, int* __restrict__ n_sel) {
+    const int f = blockIdx.x;
+    int base = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        const int m = n_sel_lvl[f * RGBL_MAX_LEVELS + l];
+        const uint32_t* src = sel_lvl + (size_t)f * cap_kp + lvl_region[l];
+        for (int i = threadIdx.x; i < m; i += 256) {
+            const uint32_t c = src[i];
+            SelKp k;
+            k.x = (uint16_t)((c & 0xfffu) + kFastBorder); k.y = (uint16_t)(((c >> 12) & 0xfffu) + kFastBorder);
+            k.level = (uint8_t)l; k.score = (uint8_t)(c >> 24); k.pad = 0;
+            sel[(size_t)f * cap_kp + base + i] = k;
+        }
+        base += m;
+    }
+    if (threadIdx.x == 0) n_sel[f] = base;
+}
+
+int quadtree_smem_bytes() { return (int)sizeof(qt::Shared); }
+
+int launch_quadtree(cudaStream_t st, const uint32_t* dense, const int* level_cnt, const int* frame_total, const LevelGeom* d_levels,
+                    int n_levels, const QtScratchDev& scr, uint32_t* sel_lvl, int* n_sel_lvl, const int* lvl_region, int cap_kp,
+                    int* status, SelKp* sel, int* n_sel, int n_frames) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(qt::Shared)) != cudaSuccess) return -1;
+        attr_set = true;
+    }
+    quadtree_kernel<<<dim3(n_levels, n_frames), 512, sizeof(qt::Shared), st>>>(dense, level_cnt, frame_total, d_levels, n_levels, scr,
+                                                                            sel_lvl, n_sel_lvl, lvl_region, cap_kp, status);
+    sel_pack_kernel<<<n_frames, 256, 0, st>>>(sel_lvl, n_sel_lvl, lvl_region, n_levels, cap_kp, sel, n_sel);
+    return 0;
+}
+
+// Host execution of the SAME block algorithm (phase-sequential): CPU validation of the device logic.
+int quadtree_block_host(const uint32_t* cand, int n, int width, int height, int N, uint32_t* out, int out_cap) {
+    std::vector<int> pa(n + 1), pb(n + 1), na(n + 1), nb(n + 1);
+    std::vector<unsigned long long> scan(n + 2);
+    std::vector<unsigned char> quad(n + 1);
+    qt::Scratch g{pa.data(), pb.data(), na.data(), nb.data(), scan.data(), quad.data()};
+    qt::Shared* s = new qt::Shared();
+    const int m = qt::distribute(*s, cand, n, width, height, N, g, out, out_cap);
+    delete s;
+    return m;
+}
+
+}  // namespace rgbl
+
+extern "C" {
+
+// test hook: the block algorithm run on the host; xys n x 3 (x, y, score) like rgbl_quadtree_select
+int rgbl_quadtree_select_block_emulation(const int32_t* xys, int n, int min_x, int max_x, int min_y, int max_y, int n_desired,
+                                         int32_t* out_xys, int cap) {
+    if (n < 0 || (n > 0 && !xys) || !out_xys) return RGBL_E_INVALID;
+    std::vector<uint32_t> c(n), o(cap);
+    for (int i = 0; i < n; ++i) c[i] = rgbl::pack_cand(xys[3 * i], xys[3 * i + 1], xys[3 * i + 2]);
+    const int m = rgbl::quadtree_block_host(c.data(), n, max_x - min_x, max_y - min_y, n_desired, o.data(), cap);
+    if (m < 0) return RGBL_E_UNSUPPORTED;
+    if (m > cap) return RGBL_E_CAPACITY;
+    for (int i = 0; i < m; ++i) { out_xys[3 * i] = (int)(o[i] & 0xfff); out_xys[3 * i + 1] = (int)((o[i] >> 12) & 0xfff); out_xys[3 * i + 2] = (int)(o[i] >> 24); }
+    return m;
+}
+
+// test hook: the restated libstdc++ introsort on (size, ulx) pairs; returns the permutation
+int rgbl_std_sort_emulation(const int32_t* size_ulx, int n, int32_t* perm_out) {
+    std::vector<rgbl::qt::SortItem> v(n);
+    for (int i = 0; i < n; ++i) { v[i].size = size_ulx[2 * i]; v[i].ulx = size_ulx[2 * i + 1]; v[i].node = i; }
+    rgbl::qt::std_sort(v.data(), n);
+    for (int i = 0; i < n; ++i) perm_out[i] = v[i].node;
+    return 0;
+}
+
+}  // extern "C"

@@ -10,9 +10,9 @@
 namespace rgbl {
 
 enum Stage { ST_PYRAMID = 0, ST_FAST, ST_COMPACT, ST_BLUR, ST_DESCRIBE, ST_DEPTH_PROJECT, ST_DEPTH_DILATE, ST_DEPTH_GATHER,
-             ST_MATCH, ST_POSE, kNumStages };
+             ST_MATCH, ST_POSE, ST_QUADTREE, kNumStages };
 static const char* const kStageNames[kNumStages] = {"pyramid", "fast", "compact", "blur", "describe", "depth_project",
-                                              "depth_resolve_dilate", "depth_gather", "match", "pose"};
+                                              "depth_resolve_dilate", "depth_gather", "match", "pose", "quadtree"};
 
 constexpr int kMatchListCap = 512;    // admissible candidates kept per map point (overflow is reported)
 
@@ -95,6 +95,12 @@ struct Ctx {
     long st_calls[kNumStages] = {};
     double host_quadtree_ms = 0.0;
     long total_launches = 0;
+
+    // device quad-tree (quadtree_kernels.cu)
+    bool device_quadtree = false, host_counts_valid = false;
+    QtScratchDev qt_scr{};
+    uint32_t* d_sel_lvl = nullptr;
+    int *d_n_sel_lvl = nullptr, *d_lvl_region = nullptr;
 
     TrackBufs trk;
     int* h_scalars = nullptr;    // pinned, 16 ints

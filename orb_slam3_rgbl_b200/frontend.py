@@ -50,6 +50,9 @@ class Context:
         out["_host_quadtree_ms"] = hq.value
         return out
 
+    def set_host_quadtree(self, on: bool):
+        check(lib().rgbl_set_host_quadtree(self.handle, int(on)), self.handle)
+
     def timer_mark(self, which: int):
         check(lib().rgbl_timer_mark(self.handle, which), self.handle)
 

@@ -47,6 +47,19 @@ def test_stages_and_keypoints_kitti(kitti_ctx, seed, report_dir):
     assert mono == rmono
 
 
+def test_host_and_device_quadtree_agree(kitti_ctx):
+    img = S.make_image(41)
+    rk, rd, _ = oracle.Extractor(2000)(img)
+    try:
+        for host in (True, False):
+            kitti_ctx.ctx.set_host_quadtree(host)
+            mono, k, d = kitti_ctx(img)
+            _cmp_kps(k, rk)
+            assert (d == rd).all()
+    finally:
+        kitti_ctx.ctx.set_host_quadtree(False)
+
+
 def test_batch_equals_single(kitti_ctx):
     imgs = [S.make_image(s) for s in (21, 22, 23)]
     outs = kitti_ctx.extract_batch(imgs)

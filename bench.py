@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
 """bench.py — RGB-L front-end frames/s on KITTI-sized synthetic frames (BASELINE.json metric).
 
-A "step" = one batch of T synthetic RGB-L frames (1241x376 image + ~120k Velodyne points each,
-nFeatures=2000, 8 levels: BASELINE.json configs[1]) through the hot path: pyramid -> FAST -> quad-tree ->
-orientation + rBRIEF -> LiDAR projection -> inverse dilation -> per-keypoint depth.
+A "step" = one batch of T consecutive frames of a synthetic RGB-L sequence (1241x376 image + 120k Velodyne
+points each, nFeatures=2000, 8 levels: BASELINE.json configs[1]) through the whole hot path: pyramid -> FAST ->
+quad-tree -> orientation + rBRIEF -> LiDAR projection -> inverse dilation -> per-keypoint depth (batched), then per
+frame SearchByProjection(last frame) -> PoseOptimization (serial in time, on the device).
 
   value : frames/s with the batch already resident in HBM (rgbl_resident_process), CUDA-event timed
   e2e   : frames/s through the public C ABI with pinned HOST buffers (rgbl_frame_rgbl_batch):
@@ -33,6 +34,7 @@ from orb_slam3_rgbl_b200 import synthetic as S  # noqa: E402
 
 METRIC = "rgbl_frontend_frames_per_sec_kitti_1241x376"
 UNIT = "frames/s"
+WORKLOAD = "KITTI-00-like synthetic RGB-L sequence: 1241x376 + 120k Velodyne pts/frame, nFeatures=2000, 8 levels (configs[1]); frame construction + SearchByProjection(last) + PoseOptimization"
 
 
 def algorithmic_bytes(levels_wh, n_cand, n_kp, n_pts, W, H, n_in):
@@ -98,30 +100,59 @@ class ClockSampler:
 
 
 def make_batch_inputs(rank: int, T: int):
-    imgs, pcs = [], []
-    for f in range(T):
-        seed = 1000 * rank + f
-        imgs.append(S.make_image(seed))
-        pcs.append(S.make_pointcloud(seed))
-    return imgs, pcs
+    """T consecutive frames of the synthetic sequence `rank` (plane world): images, clouds, P, pose0."""
+    seq = S.PlaneSequence(1000 + rank, T + 1)
+    return [seq.image(t) for t in range(T)], [seq.cloud(t) for t in range(T)], seq
+
+
+CAM = (S.KITTI_FX, S.KITTI_FY, S.KITTI_CX, S.KITTI_CY, S.KITTI_BF)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/), else None
+TRAFFIC = {}
+
+
+def cpu_track_step(fv_args_cur, last, pose, sf):
+    """oracle SearchByProjection(last frame) + PoseOptimization for one frame (same glue as rgbl_resident_track)."""
+    import oracle
+    import tracking_data as TD
+    xw, ok = TD.chain_unproject(last, pose)
+    fv = oracle.FrameView(*fv_args_cur)
+    cur_k, cur_ur = fv_args_cur[0], fv_args_cur[1]
+    nm, match = oracle.search_by_projection_last(fv, pose, pose, ok.astype(np.uint8), xw, last["d"], last["k"]["octave"], last["k"]["angle"],
+                                                 np.ones(len(ok), np.uint8), 15.0)
+    m = np.nonzero(match >= 0)[0]
+    obs = np.stack([cur_k["x"][m], cur_k["y"][m], cur_ur[m]], 1).astype(np.float32)
+    sc = sf[cur_k["octave"][m]]
+    inv_s2 = (np.float32(1.0) / (sc * sc).astype(np.float32)).astype(np.float32)
+    st = (cur_ur[m] >= 0).astype(np.uint8)
+    ni, pose2, _ = oracle.pose_optimize(pose, xw[match[m]], obs, inv_s2, st, *CAM)
+    return pose2
 
 
 def cpu_frame(ex, img, pts, P, mask):
+    """Frame construction on the CPU: ORBextractor::operator() + DepthModule::CalculateDepthFromPcd (oracle)."""
     import oracle
     k, d, _ = ex(img)
-    oracle.depth_from_pcd(pts, P, S.KITTI_W, S.KITTI_H, mask, S.KITTI_BF, k, k)
-    return len(k)
+    dep, ur, _, _ = oracle.depth_from_pcd(pts, P, S.KITTI_W, S.KITTI_H, mask, S.KITTI_BF, k, k)
+    return dict(k=k, d=d, depth=dep, ur=ur)
 
 
-def cpu_baseline_single(imgs, pcs, P, budget_s=12.0):
-    """Oracle (port) on ONE host core over a bounded sample of the same workload."""
+def cpu_baseline_single(imgs, pcs, seq, budget_s=12.0):
+    """Oracle (port) on ONE host core over a bounded sample of the same workload (frame construction + tracking)."""
     import oracle
+    sys.path.insert(0, str(ROOT / "tests"))
     ex = oracle.Extractor(2000)
+    sf = ex.scale_factors.copy()
     mask = S.structuring_element("diamond", 5)
-    cpu_frame(ex, imgs[0], pcs[0], P, mask)            # warm-up
+    last = cpu_frame(ex, imgs[0], pcs[0], seq.P, mask)            # warm-up / frame 0
+    pose = seq.pose(0)
     n, t0 = 0, time.perf_counter()
     while True:
-        cpu_frame(ex, imgs[n % len(imgs)], pcs[n % len(pcs)], P, mask)
+        t = 1 + n % (len(imgs) - 1)
+        if t == 1:
+            last = cpu_frame(ex, imgs[0], pcs[0], seq.P, mask); pose = seq.pose(0); n += 1
+        cur = cpu_frame(ex, imgs[t], pcs[t], seq.P, mask)
+        pose = cpu_track_step((cur["k"], cur["ur"], cur["d"], S.KITTI_W, S.KITTI_H, sf) + CAM, last, pose, sf)
+        last = cur
         n += 1
         el = time.perf_counter() - t0
         if el > budget_s or n >= 400:
@@ -135,32 +166,38 @@ def run_reference(args, rank, world):
         return
     import oracle
     from concurrent.futures import ThreadPoolExecutor
+    sys.path.insert(0, str(ROOT / "tests"))
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    T = max(cores, 8)
-    imgs, pcs = make_batch_inputs(0, min(T, 16))
-    P = S.lidar_projection_matrix()
+    frames_per_step = max(8, min(2 * cores, 32))
+    imgs, pcs, seq = make_batch_inputs(0, frames_per_step)
     mask = S.structuring_element("diamond", 5)
     exs = [oracle.Extractor(2000) for _ in range(cores)]
+    sf = exs[0].scale_factors.copy()
 
     def work(i):
-        return cpu_frame(exs[i % cores], imgs[i % len(imgs)], pcs[i % len(pcs)], P, mask)
+        return cpu_frame(exs[i % cores], imgs[i % len(imgs)], pcs[i % len(pcs)], seq.P, mask)
 
-    frames_per_step = 2 * cores
+    def step(pool):
+        # frame construction is independent per frame (all threads); the tracking chain is serial in time
+        frs = list(pool.map(work, range(frames_per_step)))
+        pose = seq.pose(0)
+        for t in range(1, len(frs)):
+            pose = cpu_track_step((frs[t]["k"], frs[t]["ur"], frs[t]["d"], S.KITTI_W, S.KITTI_H, sf) + CAM, frs[t - 1], pose, sf)
+
     with ThreadPoolExecutor(cores) as pool:
         for _ in range(args.warmup):
-            list(pool.map(work, range(cores)))
+            step(pool)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            list(pool.map(work, range(frames_per_step)))
+            step(pool)
         el = time.perf_counter() - t0
     fps = frames_per_step * args.steps / el
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "KITTI-00-like RGB-L 1241x376 + ~120k pts, nFeatures=2000, 8 levels (configs[1])",
-                       "frames_per_step": frames_per_step},
+            "config": {"workload": WORKLOAD, "frames_per_step": frames_per_step},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{frames_per_step} frames/step x {args.steps} steps, oracle (C++ restatement, scalar) on {cores} threads"},
+                             "sample": f"{frames_per_step} frames/step x {args.steps} steps, oracle (C++ restatement, scalar): frame construction on {cores} threads, tracking chain serial"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -184,47 +221,47 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
     from orb_slam3_rgbl_b200 import frontend as F
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from orb_slam3_rgbl_b200.dist import Reporter
+    rep = Reporter("nccl", torch.device("cuda", local_rank))      # sequences shard over ranks; NCCL only for the report
 
     T = args.batch
-    imgs, pcs = make_batch_inputs(rank, T)
-    P = S.lidar_projection_matrix()
+    imgs, pcs, seq = make_batch_inputs(rank, T)
+    P = seq.P
     max_pts = max(p.shape[1] for p in pcs)
     ctx = F.Context(S.KITTI_W, S.KITTI_H, 2000, max_batch=T, max_points=max_pts, device=local_rank)
     prm = F.make_depth_params(bf=S.KITTI_BF)
     batch = F.RgblBatch(ctx, imgs, pcs, P, prm, pinned=True)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        rep.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = rep.max_over_ranks
 
     # ---- device-resident throughput ("value") ----
     batch.upload()
+    pose0 = seq.pose(0)
+
+    def device_step():
+        n = batch.process_resident()
+        poses, nm, ni = batch.track(pose0, *CAM, th=15.0)
+        return n, poses, nm, ni
+
     for _ in range(args.warmup):
-        batch.process_resident()
+        device_step()
     ctx.profile_enable(True); ctx.profile_reset()
     sampler = ClockSampler(local_rank); sampler.start()
     barrier()
     ctx.timer_mark(0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        n_kp = batch.process_resident().copy()
+        n_kp, poses, nm, ni = device_step()
+        n_kp = n_kp.copy()
     ctx.timer_mark(1)
     dev_ms = ctx.timer_elapsed_ms()
     barrier()
@@ -236,12 +273,16 @@ def main():
     fps = world * T * args.steps / (dev_ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ("e2e") ----
+    def e2e_step():
+        batch.run_e2e()                                  # H2D inputs, kernels, D2H keypoints/descriptors/depths
+        return batch.track(pose0, *CAM, th=15.0)         # D2H poses + counts
+
     for _ in range(2):
-        batch.run_e2e()
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        batch.run_e2e()
+        e2e_step()
     barrier()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
     e2e_fps = world * T * args.steps / (e2e_ms * 1e-3)
@@ -269,43 +310,66 @@ def main():
         else:
             peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
         kernels = {}
+        other = {}
         for name, st in prof.items():
-            if name.startswith("_") or st["calls"] == 0 or name not in per_frame:
+            if name.startswith("_") or st["calls"] == 0:
+                continue
+            if name not in per_frame:
+                other[name] = {"ms_per_step": st["ms"] / args.steps, "launches_per_step": st["launches"] / args.steps}
                 continue
             ms_per_call = st["ms"] / st["calls"]
             gbs = per_frame[name] * T / (ms_per_call * 1e-3) / 1e9
             kernels[name] = {"ms_per_step": ms_per_call, "launches_per_step": st["launches"] / st["calls"],
                              "algorithmic_MB_per_step": per_frame[name] * T / 1e6, "achieved_GBs": gbs, "frac": gbs / peak}
+        def roof(name, kd, note=None):
+            r = {"bound": "hbm", "kernel": name, "achieved": kd["achieved_GBs"], "peak": peak, "unit": "GB/s",
+                 "frac": kd["frac"], "traffic": TRAFFIC.get(name), "peak_source": peak_src,
+                 "avg_launch_ms": kd["ms_per_step"] / max(kd["launches_per_step"], 1),
+                 "algorithmic_bytes_per_launch": kd["algorithmic_MB_per_step"] * 1e6 / max(kd["launches_per_step"], 1)}
+            if note:
+                r["note"] = note
+            return r
+
+        # tracking chain (grid + collect + resolve + edges + PoseOptimization per frame): 64 B per evaluated descriptor pair
+        # and 64 B per edge per LM evaluation; latency-bound by construction (serial in time, one CTA)
+        if "match" in other:
+            pairs = 30000.0; evals = 60.0
+            bytes_step = (T - 1) * (64.0 * pairs + 64.0 * float(np.mean(nm[1:])) * evals)
+            ms = other["match"]["ms_per_step"]
+            kernels["tracking_chain"] = {"ms_per_step": ms, "launches_per_step": other["match"]["launches_per_step"],
+                                         "algorithmic_MB_per_step": bytes_step / 1e6, "achieved_GBs": bytes_step / (ms * 1e-3) / 1e9,
+                                         "frac": bytes_step / (ms * 1e-3) / 1e9 / peak}
         dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
         roofline = None
         if dom:
-            kd = kernels[dom]
-            roofline = {"bound": "hbm", "kernel": dom, "achieved": kd["achieved_GBs"], "peak": peak, "unit": "GB/s",
-                        "frac": kd["frac"], "traffic": None, "peak_source": peak_src,
-                        "avg_launch_ms": kd["ms_per_step"] / max(kd["launches_per_step"], 1),
-                        "algorithmic_bytes_per_launch": per_frame[dom] * T / max(kd["launches_per_step"], 1)}
+            roofline = roof(dom, kernels[dom], "latency-bound serial chain (pose_optimize_kernel ~80 % of it): one persistent CTA per frame, FP64 LM"
+                            if dom == "tracking_chain" else None)
+        stream = {k: v for k, v in kernels.items() if k != "tracking_chain"}
+        dom_s = max(stream, key=lambda k: stream[k]["ms_per_step"]) if stream else None
+        roofline_streaming = roof(dom_s, stream[dom_s], "dominant frame-construction kernel; FAST is ALU/issue-bound (see DESIGN.md 4)") if dom_s else None
         working_set_mb = (2 * 1.74 + 4 * 4 * max_pts / 1e6 + 2 * 4 * S.KITTI_W * S.KITTI_H / 1e6) * T
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "KITTI-00-like RGB-L 1241x376 + ~120k pts, nFeatures=2000, 8 levels (configs[1])",
+                "config": {"workload": WORKLOAD,
                            "frames_per_step_per_gpu": T, "parallelism": f"sequences sharded x{world}",
                            "l2": f"inputs larger than L2: ~{working_set_mb:.0f} MB touched per step vs 126 MB L2",
                            "timing": "CUDA events on the library stream around K steps (host quad-tree gaps included), max over ranks"},
                 "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": batch.h2d_bytes, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(prof["_total_launches"]),
-                "clocks": clocks, "roofline": roofline, "kernels": kernels,
+                "clocks": clocks, "roofline": roofline, "roofline_frame_construction": roofline_streaming, "kernels": kernels, "latency_bound_stages": other,
+                "tracking": {"matches_per_frame": float(np.mean(nm[1:])), "inliers_per_frame": float(np.mean(ni[1:])),
+                             "pose_x_error_m_last_frame": float(abs(poses[-1, 4] - seq.pose(T - 1)[4]))},
                 "host_quadtree_ms_per_step": prof["_host_quadtree_ms"] / args.steps,
                 "wall_ms_per_step": wall_ms / args.steps}
         if world == 1 and not args.no_cpu_baseline:
-            v, n = cpu_baseline_single(imgs, pcs, P)
+            v, n = cpu_baseline_single(imgs, pcs, seq)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"{n} frames of the same workload, oracle (C++ restatement of ORBextractor+DepthModule, scalar, -O3) on one core"}
+                                    "sample": f"{n} frames of the same workload, oracle (C++ restatement of ORBextractor + DepthModule + SearchByProjection + PoseOptimization, scalar, -O3) on one core"}
         print(json.dumps(line))
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    rep.close()
 
 
 if __name__ == "__main__":

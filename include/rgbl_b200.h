@@ -194,6 +194,14 @@ int rgbl_resident_upload(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray
 int rgbl_resident_process(rgbl_ctx* ctx, const float P[12], const rgbl_depth_params* prm, int* n_out /* nullable */);
 int rgbl_resident_download(rgbl_ctx* ctx, rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out);
 
+/* Resident tracking chain over the frames of the last batched call, entirely on the device: for t = 1..n-1
+ * SearchByProjection(frame t, frame t-1, th) -> PoseOptimization, every LiDAR-depth keypoint of frame t-1 acting as a map
+ * point (Frame::UnprojectStereo, src/Frame.cc:1097-1112, with the estimated pose of t-1; constant-pose motion model).
+ * This is harness glue around the two reference functions (Tracking::TrackWithMotionModel, src/Tracking.cc:2888-2981,
+ * stays on the host in the drop-in).  poses_out[n][7], n_matches[n], n_inliers[n]; entry 0 = (pose0, 0, 0).           */
+int rgbl_resident_track(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono,
+                        float* poses_out, int* n_matches, int* n_inliers);
+
 /* Keypoint distribution (DistributeOctTree) runs on the device by default (one CTA per (frame, level)); on != 0
  * selects the host implementation instead (also: environment RGBL_HOST_QUADTREE=1).  Both are exact.           */
 int rgbl_set_host_quadtree(rgbl_ctx* ctx, int on);

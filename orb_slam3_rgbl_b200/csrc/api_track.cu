@@ -139,7 +139,7 @@ int rgbl_search_by_projection_last(rgbl_ctx* ctx, const rgbl_frame_view* cur, co
     }
     SearchLastParams prm;
     std::memcpy(prm.cur_pose, cur_pose, 7 * sizeof(float));
-    prm.th = th; prm.check_orientation = check_orientation;
+    prm.th = th; prm.check_orientation = check_orientation; prm.cur_pose_dev = nullptr; prm.flags_dev = nullptr;
     {   // bForward / bBackward, src/ORBmatcher.cc:1686-1693
         float inv[7] = {-cur_pose[0], -cur_pose[1], -cur_pose[2], cur_pose[3], 0, 0, 0};
         const float nt[3] = {cur_pose[4] * -1.f, cur_pose[5] * -1.f, cur_pose[6] * -1.f};
@@ -251,7 +251,7 @@ int rgbl_pose_optimize(rgbl_ctx* ctx, const float pose_in[7], int n, const float
     }
     PoseProblemDev p;
     p.n = n; p.xw = t.q_f3a; p.obs = t.q_f3b; p.inv_sigma2 = t.q_f[0]; p.stereo = t.q_u8a;
-    p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf;
+    p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf; p.n_dev = nullptr; p.pose_in_dev = nullptr;
     std::memcpy(p.pose_in, pose_in, 7 * sizeof(float));
     stage_begin(c, ST_POSE, c->st);
     launch_pose_optimize(c->st, p, t.pose_work, t.q_u8b, t.resolved, t.q_f[1], reinterpret_cast<int*>(t.scalars + 8));
@@ -263,6 +263,70 @@ int rgbl_pose_optimize(rgbl_ctx* ctx, const float pose_in[7], int n, const float
     CU(cudaStreamSynchronize(c->st));
     prof_collect(c);
     *n_inliers = c->h_scalars[8];
+    return RGBL_OK;
+}
+
+
+/* Resident tracking chain over the frames of the last rgbl_resident_process / rgbl_frame_rgbl_batch call, entirely on the
+ * device (no host round trip per frame): for t = 1..n-1  SearchByProjection(frame t, frame t-1) -> PoseOptimization, with
+ * every LiDAR-depth keypoint of frame t-1 acting as a map point (Frame::UnprojectStereo with the estimated pose of t-1)
+ * and the constant-pose motion model.  poses_out[n][7], n_matches[n], n_inliers[n] (entry 0 = pose0, 0, 0).           */
+int rgbl_resident_track(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono,
+                        float* poses_out, int* n_matches, int* n_inliers) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!pose0 || !poses_out || !n_matches || !n_inliers) { c->err = "null argument"; return RGBL_E_INVALID; }
+    const int nF = c->last_frames, cap = c->cap_kp;
+    if (nF < 1) { c->err = "nothing processed"; return RGBL_E_INVALID; }
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = ensure_frame(c, cap); if (rc) return rc;
+    rc = ensure_queries(c, cap); if (rc) return rc;
+    TrackBufs& t = c->trk;
+    GROW(t.pose_work, t.cap_pose_work, (size_t)cap * 3);
+    GROW(t.ch_poses, t.cap_ch_poses, (size_t)nF * 7); GROW(t.ch_counts, t.cap_ch_counts, (size_t)nF * 2 + 4);
+    GROW(t.e_xw, t.cap_e_xw, (size_t)cap * 3); GROW(t.e_obs, t.cap_e_obs, (size_t)cap * 3); GROW(t.e_info, t.cap_e_info, cap);
+    GROW(t.e_st, t.cap_e_st, cap); GROW(t.e_lvl, t.cap_e_lvl, cap); GROW(t.e_out, t.cap_e_out, cap); GROW(t.e_idx, t.cap_e_idx, cap);
+    CU(cudaMemcpyAsync(t.ch_poses, pose0, 7 * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemsetAsync(t.ch_counts, 0, ((size_t)nF * 2 + 4) * sizeof(int), c->st));
+    int* d_nm = t.ch_counts; int* d_ni = t.ch_counts + nF; int* d_ne = t.ch_counts + 2 * nF; int* d_flags = t.ch_counts + 2 * nF + 1;
+    FrameDev f{};
+    f.min_x = 0.f; f.max_x = (float)c->cfg.width; f.min_y = 0.f; f.max_y = (float)c->cfg.height;      // k1 == 0: image bounds
+    f.inv_w = static_cast<float>(kGridCols) / static_cast<float>(f.max_x - f.min_x);
+    f.inv_h = static_cast<float>(kGridRows) / static_cast<float>(f.max_y - f.min_y);
+    f.n_levels = c->tab.nlevels;
+    for (int l = 0; l < f.n_levels; ++l) f.scale[l] = c->tab.scale[l];
+    f.fx = fx; f.fy = fy; f.cx = cx; f.cy = cy; f.bf = bf; f.mb = bf / fx;
+    f.log_scale_factor = std::log(c->cfg.orb.scale_factor);
+    MatchScratch ms = scratch(c);
+    stage_begin(c, ST_MATCH, c->st);
+    for (int k = 1; k < nF; ++k) {
+        const size_t lo = (size_t)(k - 1) * cap, cu = (size_t)k * cap;
+        const float* last_pose = t.ch_poses + 7 * (k - 1);
+        launch_chain_prep(c->st, c->d_kps + lo, c->d_depth + lo, c->d_n_sel + (k - 1), last_pose, last_pose, f, mono, cap,
+                          t.q_u8a, t.q_f3a, t.q_i, t.q_f[0], t.q_u8b, d_flags);
+        f.n = c->d_n_sel + k; f.keys = c->d_kps + cu; f.uright = c->d_uright + cu; f.desc = c->d_desc + cu * 32;
+        launch_grid_build(c->st, f, t.cell_start, t.csr_idx, t.kp_cell);
+        CU(cudaMemsetAsync(t.state, 0, cap, c->st));
+        SearchLastParams prm{};
+        prm.th = th; prm.check_orientation = 1; prm.cur_pose_dev = last_pose; prm.flags_dev = d_flags;
+        LastFrameDev lf{cap, t.q_u8a, t.q_f3a, c->d_desc + lo * 32, t.q_i, t.q_f[0], t.q_u8b};
+        launch_search_last(c->st, f, t.cell_start, t.csr_idx, lf, prm, ms, t.state, t.match, d_nm + k);
+        launch_chain_edges(c->st, f.keys, f.uright, f.n, t.match, t.q_f3a, f, t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne);
+        PoseProblemDev p{};
+        p.n = 0; p.n_dev = d_ne; p.pose_in_dev = last_pose;
+        p.xw = t.e_xw; p.obs = t.e_obs; p.inv_sigma2 = t.e_info; p.stereo = t.e_st;
+        p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf;
+        launch_pose_optimize(c->st, p, t.pose_work, t.e_lvl, t.e_out, t.ch_poses + 7 * k, d_ni + k);
+    }
+    stage_end(c, ST_MATCH, c->st, 6 * (nF - 1));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(poses_out, t.ch_poses, (size_t)nF * 7 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(n_matches, d_nm, (size_t)nF * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(n_inliers, d_ni, (size_t)nF * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    prof_collect(c);
+    if (*c->h_overflow) { cudaMemsetAsync(c->d_overflow, 0, sizeof(int), c->st); c->err = "matcher candidate list overflow"; return RGBL_E_CAPACITY; }
     return RGBL_OK;
 }
 

@@ -44,10 +44,27 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int* __res
         kp_cell[i] = c;
     }
     __syncthreads();
-    if (tid == 0) {
-        int s = 0;
-        for (int c = 0; c < kGridCells; ++c) { off[c] = s; s += cnt[c]; }
-        off[kGridCells] = s;
+    {   // block-wide exclusive scan of the 3072 cell counts: 3 consecutive cells per thread + warp/block scan
+        __shared__ int wsum[32];
+        const int c0 = tid * 3;
+        const int a0 = cnt[c0], a1 = cnt[c0 + 1], a2 = cnt[c0 + 2];
+        const int mine = a0 + a1 + a2;
+        int incl = mine;
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int v = wsum[lane], w = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            wsum[lane] = w - v;                      // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int base = wsum[warp] + incl - mine;
+        off[c0] = base; off[c0 + 1] = base + a0; off[c0 + 2] = base + a0 + a1;
+        if (tid == 1023) off[kGridCells] = base + mine;
     }
     __syncthreads();
     for (int c = tid; c <= kGridCells; c += 1024) cell_start[c] = off[c];
@@ -163,8 +180,9 @@ __global__ void __launch_bounds__(256) search_last_collect_kernel(FrameDev f, co
     if (lf.valid[q]) {
         const float p[3] = {lf.xw[3 * q], lf.xw[3 * q + 1], lf.xw[3 * q + 2]};
         float xc[3];
-        se3f_rotate(prm.cur_pose, p, xc);
-        xc[0] = __fadd_rn(xc[0], prm.cur_pose[4]); xc[1] = __fadd_rn(xc[1], prm.cur_pose[5]); xc[2] = __fadd_rn(xc[2], prm.cur_pose[6]);
+        const float* T = prm.cur_pose_dev ? prm.cur_pose_dev : prm.cur_pose;
+        se3f_rotate(T, p, xc);
+        xc[0] = __fadd_rn(xc[0], T[4]); xc[1] = __fadd_rn(xc[1], T[5]); xc[2] = __fadd_rn(xc[2], T[6]);
         const float invzc = (float)__ddiv_rn(1.0, (double)xc[2]);
         bool ok = !(invzc < 0);
         const float u = __fadd_rn(__fdiv_rn(__fmul_rn(f.fx, xc[0]), xc[2]), f.cx);
@@ -175,8 +193,9 @@ __global__ void __launch_bounds__(256) search_last_collect_kernel(FrameDev f, co
             const int oct = lf.octave[q];
             const float radius = __fmul_rn(prm.th, f.scale[oct]);
             int lo, hi;
-            if (prm.forward) { lo = oct; hi = -1; }
-            else if (prm.backward) { lo = 0; hi = oct; }
+            const int fwd = prm.flags_dev ? prm.flags_dev[0] : prm.forward, bwd = prm.flags_dev ? prm.flags_dev[1] : prm.backward;
+            if (fwd) { lo = oct; hi = -1; }
+            else if (bwd) { lo = 0; hi = oct; }
             else { lo = oct - 1; hi = oct + 1; }
             const CellRange cr = cell_range(f, u, v, radius);
             if (cr.ok) {
@@ -407,6 +426,89 @@ __global__ void __launch_bounds__(256) frustum_kernel(FrameDev f, FrustumParams 
     in_view[i] = iv; px[i] = ox; py[i] = oy; pxr[i] = oxr; depth[i] = od; level[i] = ol; view_cos[i] = ovc;
 }
 
+// ---- resident tracking chain (TrackWithMotionModel-style glue between the reference functions) ----------------
+// Every keypoint of the last frame that has a LiDAR depth acts as a map point: Frame::UnprojectStereo
+// (src/Frame.cc:1097-1112) with the last pose, descriptor = the keypoint's own descriptor.
+__global__ void __launch_bounds__(256) chain_prep_kernel(const rgbl_keypoint* __restrict__ kps, const float* __restrict__ depth,
+                                                         const int* __restrict__ n_ptr, const float* __restrict__ last_pose,
+                                                         const float* __restrict__ cur_pose, float fx, float fy, float cx, float cy,
+                                                         float mb, int mono, int cap, uint8_t* __restrict__ valid,
+                                                         float* __restrict__ xw, int* __restrict__ octave, float* __restrict__ angle,
+                                                         uint8_t* __restrict__ obs_pos, int* __restrict__ flags) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const float inv[4] = {-last_pose[0], -last_pose[1], -last_pose[2], last_pose[3]};
+    if (i == 0) {
+        // bForward / bBackward (src/ORBmatcher.cc:1686-1693): tlc = Tlw * (Tcw^-1).translation()
+        const float cinv[4] = {-cur_pose[0], -cur_pose[1], -cur_pose[2], cur_pose[3]};
+        const float nt[3] = {__fmul_rn(cur_pose[4], -1.f), __fmul_rn(cur_pose[5], -1.f), __fmul_rn(cur_pose[6], -1.f)};
+        float twc[3], r[3];
+        se3f_rotate(cinv, nt, twc);
+        se3f_rotate(last_pose, twc, r);
+        const float tlc_z = __fadd_rn(r[2], last_pose[6]);
+        flags[0] = (tlc_z > mb && !mono) ? 1 : 0;
+        flags[1] = (-tlc_z > mb && !mono) ? 1 : 0;
+    }
+    if (i >= cap) return;
+    uint8_t v = 0;
+    if (i < *n_ptr) {
+        const float z = depth[i];
+        const rgbl_keypoint kp = kps[i];
+        octave[i] = kp.octave; angle[i] = kp.angle; obs_pos[i] = 1;
+        if (z > 0.f) {
+            const float invfx = __fdiv_rn(1.0f, fx), invfy = __fdiv_rn(1.0f, fy);
+            const float pc[3] = {__fmul_rn(__fmul_rn(__fsub_rn(kp.x, cx), z), invfx), __fmul_rn(__fmul_rn(__fsub_rn(kp.y, cy), z), invfy), z};
+            // Twc * x3Dc with Twc = Tcw^-1 = (q*, q* (x) (-t))
+            const float nt[3] = {__fmul_rn(last_pose[4], -1.f), __fmul_rn(last_pose[5], -1.f), __fmul_rn(last_pose[6], -1.f)};
+            float ow[3], pr[3];
+            se3f_rotate(inv, nt, ow);
+            se3f_rotate(inv, pc, pr);
+            xw[3 * i] = __fadd_rn(pr[0], ow[0]); xw[3 * i + 1] = __fadd_rn(pr[1], ow[1]); xw[3 * i + 2] = __fadd_rn(pr[2], ow[2]);
+            v = 1;
+        }
+    }
+    valid[i] = v;
+}
+
+// ordered compaction of the matched features into PoseOptimization edges (keypoint order)
+__global__ void __launch_bounds__(1024) chain_edges_kernel(const rgbl_keypoint* __restrict__ kps, const float* __restrict__ uright,
+                                                           const int* __restrict__ n_ptr, const int* __restrict__ match,
+                                                           const float* __restrict__ last_xw, FrameDev f, float* __restrict__ exw,
+                                                           float* __restrict__ eobs, float* __restrict__ einfo, uint8_t* __restrict__ est,
+                                                           int* __restrict__ eidx, int* __restrict__ n_edges) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = *n_ptr;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int b = 0; b < n; b += 1024) {
+        const int i = b + tid;
+        const int m = (i < n) ? match[i] : -1;
+        const int flag = m >= 0;
+        int incl = flag;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int base = carry;
+        for (int w = 0; w < warp; ++w) base += wsum[w];
+        if (flag) {
+            const int e = base + incl - 1;
+            const rgbl_keypoint kp = kps[i];
+            exw[3 * e] = last_xw[3 * m]; exw[3 * e + 1] = last_xw[3 * m + 1]; exw[3 * e + 2] = last_xw[3 * m + 2];
+            const float ur = uright[i];
+            eobs[3 * e] = kp.x; eobs[3 * e + 1] = kp.y; eobs[3 * e + 2] = ur;
+            const float sc = f.scale[kp.octave];
+            einfo[e] = __fdiv_rn(1.0f, __fmul_rn(sc, sc));            // mvInvLevelSigma2 (src/ORBextractor.cc:421-429)
+            est[e] = ur >= 0.f;
+            eidx[e] = i;
+        }
+        __syncthreads();
+        if (tid == 1023) carry = base + incl;
+        __syncthreads();
+    }
+    if (tid == 0) *n_edges = carry;
+}
+
 // ---- launchers ---------------------------------------------------------------------------------------
 void launch_grid_build(cudaStream_t st, const FrameDev& f, int* cell_start, int* csr_idx, int* kp_cell) {
     grid_build_kernel<<<1, 1024, 0, st>>>(f, cell_start, csr_idx, kp_cell);
@@ -426,6 +528,18 @@ void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_sta
     search_local_collect_kernel<<<(lp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
     resolve_kernel<<<1, 1024, 0, st>>>(1, lp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lp.obs_pos, nullptr, prm.nn_ratio,
                                        0, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds);
+}
+
+void launch_chain_prep(cudaStream_t st, const rgbl_keypoint* kps, const float* depth, const int* n_ptr, const float* last_pose,
+                       const float* cur_pose, const FrameDev& f, int mono, int cap, uint8_t* valid, float* xw, int* octave, float* angle,
+                       uint8_t* obs_pos, int* flags) {
+    chain_prep_kernel<<<(cap + 255) / 256, 256, 0, st>>>(kps, depth, n_ptr, last_pose, cur_pose, f.fx, f.fy, f.cx, f.cy, f.mb, mono, cap,
+                                                       valid, xw, octave, angle, obs_pos, flags);
+}
+
+void launch_chain_edges(cudaStream_t st, const rgbl_keypoint* kps, const float* uright, const int* n_ptr, const int* match,
+                        const float* last_xw, const FrameDev& f, float* exw, float* eobs, float* einfo, uint8_t* est, int* eidx, int* n_edges) {
+    chain_edges_kernel<<<1, 1024, 0, st>>>(kps, uright, n_ptr, match, last_xw, f, exw, eobs, einfo, est, eidx, n_edges);
 }
 
 void launch_frustum(cudaStream_t st, const FrameDev& f, const FrustumParams& prm, int n, const float* xw, const float* normal,

@@ -42,7 +42,21 @@ __device__ __forceinline__ void se3_map(const Se3d& T, const double p[3], double
     out[0] += T.tx; out[1] += T.ty; out[2] += T.tz;
 }
 
-__device__ void quat_from_matrix(const double R[3][3], Se3d& q) {
+template <int I>
+__device__ __forceinline__ void quat_from_matrix_case(const double R[3][3], Se3d& q) {
+    constexpr int J = (I + 1) % 3, K = (J + 1) % 3;
+    double t = sqrt(R[I][I] - R[J][J] - R[K][K] + 1.0);
+    double v[3];
+    v[I] = 0.5 * t;
+    t = 0.5 / t;
+    q.qw = (R[K][J] - R[J][K]) * t;
+    v[J] = (R[J][I] + R[I][J]) * t;
+    v[K] = (R[K][I] + R[I][K]) * t;
+    q.qx = v[0]; q.qy = v[1]; q.qz = v[2];
+}
+
+// Eigen quaternion-from-rotation-matrix; every array index is a compile-time constant (registers, no local memory)
+__device__ __forceinline__ void quat_from_matrix(const double R[3][3], Se3d& q) {
     double t = R[0][0] + R[1][1] + R[2][2];
     if (t > 0) {
         t = sqrt(t + 1.0);
@@ -52,32 +66,32 @@ __device__ void quat_from_matrix(const double R[3][3], Se3d& q) {
     } else {
         int i = 0;
         if (R[1][1] > R[0][0]) i = 1;
-        if (R[2][2] > R[i][i]) i = 2;
-        const int j = (i + 1) % 3, k = (j + 1) % 3;
-        t = sqrt(R[i][i] - R[j][j] - R[k][k] + 1.0);
-        double v[3];
-        v[i] = 0.5 * t;
-        t = 0.5 / t;
-        q.qw = (R[k][j] - R[j][k]) * t;
-        v[j] = (R[j][i] + R[i][j]) * t;
-        v[k] = (R[k][i] + R[i][k]) * t;
-        q.qx = v[0]; q.qy = v[1]; q.qz = v[2];
+        if (i == 0) { if (R[2][2] > R[0][0]) i = 2; } else { if (R[2][2] > R[1][1]) i = 2; }
+        if (i == 0) quat_from_matrix_case<0>(R, q);
+        else if (i == 1) quat_from_matrix_case<1>(R, q);
+        else quat_from_matrix_case<2>(R, q);
     }
 }
 
-__device__ void se3_exp(const double u[6], Se3d& T) {
+__device__ __noinline__ void se3_exp(const double* u, Se3d& T) {
     const double om[3] = {u[0], u[1], u[2]}, up[3] = {u[3], u[4], u[5]};
     const double theta = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
     const double O[3][3] = {{0, -om[2], om[1]}, {om[2], 0, -om[0]}, {-om[1], om[0], 0}};
     double O2[3][3], R[3][3], V[3][3];
+#pragma unroll
     for (int i = 0; i < 3; ++i)
+#pragma unroll
         for (int j = 0; j < 3; ++j) O2[i][j] = O[i][0] * O[0][j] + O[i][1] * O[1][j] + O[i][2] * O[2][j];
     if (theta < 0.00001) {
+#pragma unroll
         for (int i = 0; i < 3; ++i)
+#pragma unroll
             for (int j = 0; j < 3; ++j) { R[i][j] = (i == j ? 1.0 : 0.0) + O[i][j] + O2[i][j]; V[i][j] = R[i][j]; }
     } else {
-        const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / pow(theta, 3.0);
+        const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / (theta * theta * theta);
+#pragma unroll
         for (int i = 0; i < 3; ++i)
+#pragma unroll
             for (int j = 0; j < 3; ++j) {
                 R[i][j] = (i == j ? 1.0 : 0.0) + a * O[i][j] + b * O2[i][j];
                 V[i][j] = (i == j ? 1.0 : 0.0) + b * O[i][j] + c * O2[i][j];
@@ -90,7 +104,7 @@ __device__ void se3_exp(const double u[6], Se3d& T) {
     normalize_rotation(T);
 }
 
-__device__ void se3_mul(const Se3d& a, const Se3d& b, Se3d& r) {
+__device__ __noinline__ void se3_mul(const Se3d& a, const Se3d& b, Se3d& r) {
     const double bt[3] = {b.tx, b.ty, b.tz};
     double rt[3];
     quat_rotate(a, bt, rt);
@@ -102,35 +116,78 @@ __device__ void se3_mul(const Se3d& a, const Se3d& b, Se3d& r) {
     normalize_rotation(r);
 }
 
-// 6x6 LDL^T with diagonal pivoting (what Eigen::LDLT does), positive-semidefinite check.
-__device__ bool solve6(const double* Hsym /*21 upper*/, double lambda, const double b[6], double x[6]) {
-    double A[6][6]; int perm[6];
-    int t = 0;
-    for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { A[i][j] = Hsym[t]; A[j][i] = Hsym[t]; ++t; }
-    for (int i = 0; i < 6; ++i) { A[i][i] += lambda; perm[i] = i; }
-    bool positive = true;
+// 6x6 LDL^T with diagonal pivoting (what Eigen::LDLT does), positive-semidefinite check.  Unrolled with branch-free
+// (select-based) row/column swaps so that every array index is a compile-time constant and the matrix lives in
+// registers; __noinline__ keeps one copy of it in the kernel (an earlier inlined, branchy version made ptxas emit
+// 180k instructions and the single-CTA kernel became instruction-fetch bound).
+__device__ __noinline__ bool solve6(const double* Hsym /*21 upper*/, double lambda, const double* b, double* x) {
+    double A[6][6], y[6];
+    int pivs[6];
+    {
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j) { A[i][j] = Hsym[t]; A[j][i] = Hsym[t]; ++t; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { A[i][i] += lambda; y[i] = b[i]; }
+    }
+    bool positive = true, stop = false;
+#pragma unroll
     for (int k = 0; k < 6; ++k) {
-        int piv = k; double best = fabs(A[k][k]);
-        for (int i = k + 1; i < 6; ++i) if (fabs(A[i][i]) > best) { best = fabs(A[i][i]); piv = i; }
-        if (piv != k) {
-            for (int j = 0; j < 6; ++j) { const double s = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = s; }
-            for (int i = 0; i < 6; ++i) { const double s = A[i][k]; A[i][k] = A[i][piv]; A[i][piv] = s; }
-            const int s = perm[k]; perm[k] = perm[piv]; perm[piv] = s;
+        int piv = k;
+        double best = fabs(A[k][k]);
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) { const bool g = fabs(A[i][i]) > best; best = g ? fabs(A[i][i]) : best; piv = g ? i : piv; }
+        piv = stop ? k : piv;
+        pivs[k] = piv;
+#pragma unroll
+        for (int p = k + 1; p < 6; ++p) {
+            const bool sw = (piv == p);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) { const double a = A[k][j], c = A[p][j]; A[k][j] = sw ? c : a; A[p][j] = sw ? a : c; }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { const double a = A[i][k], c = A[i][p]; A[i][k] = sw ? c : a; A[i][p] = sw ? a : c; }
+            { const double a = y[k], c = y[p]; y[k] = sw ? c : a; y[p] = sw ? a : c; }
         }
         const double d = A[k][k];
-        if (d < 0) positive = false;
-        if (d == 0) break;
-        for (int i = k + 1; i < 6; ++i) A[i][k] /= d;
+        positive = positive && (stop || !(d < 0));
+        stop = stop || (d == 0);
+        const double dd = stop ? 1.0 : d;            // after an exact zero pivot Eigen leaves the trailing block untouched
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) A[i][k] = stop ? A[i][k] : A[i][k] / dd;
+#pragma unroll
         for (int i = k + 1; i < 6; ++i)
-            for (int j = k + 1; j <= i; ++j) { A[i][j] -= A[i][k] * d * A[j][k]; A[j][i] = A[i][j]; }
+#pragma unroll
+            for (int j = k + 1; j <= i; ++j) {
+                const double nv = A[i][j] - A[i][k] * dd * A[j][k];
+                A[i][j] = stop ? A[i][j] : nv;
+                A[j][i] = A[i][j];
+            }
     }
     if (!positive) return false;
-    double y[6];
-    for (int i = 0; i < 6; ++i) y[i] = b[perm[i]];
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
+#pragma unroll
     for (int i = 0; i < 6; ++i) y[i] = (A[i][i] != 0) ? y[i] / A[i][i] : 0.0;
-    for (int i = 5; i >= 0; --i) for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
-    for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
+#pragma unroll
+    for (int i = 5; i >= 0; --i)
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
+    // x = P^T y: undo the swaps in reverse order
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {
+#pragma unroll
+        for (int p = k + 1; p < 6; ++p) {
+            const bool sw = (pivs[k] == p);
+            const double a = y[k], c = y[p];
+            y[k] = sw ? c : a; y[p] = sw ? a : c;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = y[i];
     return true;
 }
 
@@ -140,9 +197,10 @@ __device__ __forceinline__ void huber(double e2, double delta, float dsqr, doubl
 }
 
 constexpr int kAcc = 28;      // 21 H + 6 b + 1 chi
+constexpr int kPoseThreads = 512, kPoseWarps = kPoseThreads / 32;
 
 // block-wide sum of kAcc doubles (fixed tree: lane shuffles, then warps 0..7 in order); result broadcast in `out`
-__device__ void block_reduce(double* v, double* smem /* 8*kAcc */, double* out /* kAcc, shared */) {
+__device__ __forceinline__ void block_reduce(double* v, double* smem /* 8*kAcc */, double* out /* kAcc, shared */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < kAcc; ++k) {
@@ -154,7 +212,7 @@ __device__ void block_reduce(double* v, double* smem /* 8*kAcc */, double* out /
     __syncthreads();
     if (threadIdx.x < kAcc) {
         double s = 0;
-        for (int w = 0; w < 8; ++w) s += smem[w * kAcc + threadIdx.x];
+        for (int w = 0; w < kPoseWarps; ++w) s += smem[w * kAcc + threadIdx.x];
         out[threadIdx.x] = s;
     }
     __syncthreads();
@@ -162,18 +220,19 @@ __device__ void block_reduce(double* v, double* smem /* 8*kAcc */, double* out /
 
 }  // namespace
 
-__global__ void __launch_bounds__(256) pose_optimize_kernel(PoseProblemDev p, double* __restrict__ work, uint8_t* __restrict__ level,
+__global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblemDev p, double* __restrict__ work, uint8_t* __restrict__ level,
                                                             uint8_t* __restrict__ outlier, float* __restrict__ pose_out,
                                                             int* __restrict__ n_inliers) {
-    __shared__ double red[8 * kAcc];
+    __shared__ double red[kPoseWarps * kAcc];
     __shared__ double acc[kAcc];
     __shared__ Se3d s_est, s_init, s_backup;
     __shared__ double s_x[6], s_lambda, s_ni, s_rho, s_current, s_ini, s_temp;
     __shared__ int s_nbad_lm, s_qmax, s_ok, s_ok2, s_continue;
-    const int tid = threadIdx.x, n = p.n;
+    const int tid = threadIdx.x, n = p.n_dev ? *p.n_dev : p.n;
+    const float* pose_in = p.pose_in_dev ? p.pose_in_dev : p.pose_in;
 
     if (n < 3) {                      // src/Optimizer.cc:996
-        if (tid < 7) pose_out[tid] = p.pose_in[tid];
+        if (tid < 7) pose_out[tid] = pose_in[tid];
         if (tid == 0) *n_inliers = 0;
         return;
     }
@@ -184,11 +243,11 @@ __global__ void __launch_bounds__(256) pose_optimize_kernel(PoseProblemDev p, do
     const double fx = p.fx, fy = p.fy, cx = p.cx, cy = p.cy, bf = p.bf;
 
     if (tid == 0) {
-        Se3d T = {p.pose_in[0], p.pose_in[1], p.pose_in[2], p.pose_in[3], p.pose_in[4], p.pose_in[5], p.pose_in[6]};
+        Se3d T = {pose_in[0], pose_in[1], pose_in[2], pose_in[3], pose_in[4], pose_in[5], pose_in[6]};
         normalize_rotation(T);
         s_init = T;
     }
-    for (int k = tid; k < n; k += 256) { level[k] = 0; outlier[k] = 0; }
+    for (int k = tid; k < n; k += kPoseThreads) { level[k] = 0; outlier[k] = 0; }
     __syncthreads();
     bool robust = true;
     int n_bad = 0;
@@ -197,7 +256,7 @@ __global__ void __launch_bounds__(256) pose_optimize_kernel(PoseProblemDev p, do
     auto eval_errors = [&](double& chi_part) {
         const Se3d T = s_est;
         chi_part = 0;
-        for (int k = tid; k < n; k += 256) {
+        for (int k = tid; k < n; k += kPoseThreads) {
             if (level[k] != 0) continue;
             const double xw[3] = {p.xw[3 * k], p.xw[3 * k + 1], p.xw[3 * k + 2]};
             double pc[3];
@@ -232,7 +291,7 @@ __global__ void __launch_bounds__(256) pose_optimize_kernel(PoseProblemDev p, do
             for (int k = 0; k < kAcc; ++k) v[k] = 0;
             {
                 const Se3d T = s_est;
-                for (int k = tid; k < n; k += 256) {
+                for (int k = tid; k < n; k += kPoseThreads) {
                     if (level[k] != 0) continue;
                     const double xw[3] = {p.xw[3 * k], p.xw[3 * k + 1], p.xw[3 * k + 2]};
                     double pc[3];
@@ -258,26 +317,33 @@ __global__ void __launch_bounds__(256) pose_optimize_kernel(PoseProblemDev p, do
                         e[1] = (double)p.obs[3 * k + 1] - ((double)p.fy * pc[1] / pc[2] + (double)p.cy);
                         const double pj[2][3] = {{(double)p.fx / z, 0.0, -(double)p.fx * x / (z * z)}, {0.0, (double)p.fy / z, -(double)p.fy * y / (z * z)}};
                         const double D[3][6] = {{0, z, -y, 1, 0, 0}, {-z, 0, x, 0, 1, 0}, {y, -x, 0, 0, 0, 1}};
+#pragma unroll
                         for (int r = 0; r < 2; ++r)
+#pragma unroll
                             for (int c = 0; c < 6; ++c) J[r][c] = (-pj[r][0]) * D[0][c] + (-pj[r][1]) * D[1][c] + (-pj[r][2]) * D[2][c];
+#pragma unroll
                         for (int c = 0; c < 6; ++c) J[2][c] = 0;
                     }
                     work[3 * (size_t)k] = e[0]; work[3 * (size_t)k + 1] = e[1]; work[3 * (size_t)k + 2] = e[2];
-                    const int dim = st ? 3 : 2;
+                    // mono edges carry a zero third row (J[2][*] = 0, e[2] = 0): identical sums, static indices -> registers
                     double chi = 0;
-                    for (int r = 0; r < dim; ++r) chi += e[r] * (info * e[r]);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) chi += e[r] * (info * e[r]);
                     double w = 1.0, r0 = chi;
                     if (robust) huber(chi, st ? ds : dm, st ? dsqr_s : dsqr_m, r0, w);
                     v[27] += r0;
-                    int t = 0;
+#pragma unroll
                     for (int i = 0; i < 6; ++i) {
                         double sb = 0;
-                        for (int r = 0; r < dim; ++r) sb += J[r][i] * (info * e[r]);
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) sb += J[r][i] * (info * e[r]);
                         v[21 + i] -= w * sb;
+#pragma unroll
                         for (int j = i; j < 6; ++j) {
                             double h = 0;
-                            for (int r = 0; r < dim; ++r) h += J[r][i] * (w * info) * J[r][j];
-                            v[t++] += h;
+#pragma unroll
+                            for (int r = 0; r < 3; ++r) h += J[r][i] * (w * info) * J[r][j];
+                            v[i * 6 - (i * (i - 1)) / 2 + (j - i)] += h;
                         }
                     }
                 }
@@ -308,22 +374,18 @@ __global__ void __launch_bounds__(256) pose_optimize_kernel(PoseProblemDev p, do
                 __syncthreads();
                 double part;
                 eval_errors(part);
-                double vv[kAcc];
-#pragma unroll
-                for (int k = 0; k < kAcc; ++k) vv[k] = 0;
-                vv[27] = part;
                 __syncthreads();
                 {
                     // reduce only the chi2 slot (slot 27) but reuse the fixed tree
                     const int lane = tid & 31, warp = tid >> 5;
-                    double x = vv[27];
+                    double x = part;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
                     if (lane == 0) red[warp] = x;
                     __syncthreads();
                     if (tid == 0) {
                         double s = 0;
-                        for (int w = 0; w < 8; ++w) s += red[w];
+                        for (int w = 0; w < kPoseWarps; ++w) s += red[w];
                         double temp = s;
                         if (!s_ok2) temp = DBL_MAX;
                         double rho = s_current - temp;
@@ -332,7 +394,8 @@ __global__ void __launch_bounds__(256) pose_optimize_kernel(PoseProblemDev p, do
                         scale += 1e-3;
                         rho /= scale;
                         if (rho > 0 && isfinite(temp)) {
-                            double alpha = 1. - pow((2 * rho - 1), 3.0);
+                            const double r21 = 2 * rho - 1;
+                            double alpha = 1. - r21 * r21 * r21;
                             alpha = fmin(alpha, 2. / 3.);
                             const double sf = fmax(1. / 3., alpha);
                             s_lambda *= sf; s_ni = 2; s_current = temp;
@@ -362,7 +425,7 @@ __global__ void __launch_bounds__(256) pose_optimize_kernel(PoseProblemDev p, do
         {
             const Se3d T = s_est;
             int bad = 0;
-            for (int k = tid; k < n; k += 256) {
+            for (int k = tid; k < n; k += kPoseThreads) {
                 const bool st = p.stereo[k] != 0;
                 const double info = (double)p.inv_sigma2[k];
                 double e0, e1, e2 = 0;
@@ -411,7 +474,7 @@ __global__ void __launch_bounds__(256) pose_optimize_kernel(PoseProblemDev p, do
 
 void launch_pose_optimize(cudaStream_t st, const PoseProblemDev& p, double* work, uint8_t* level, uint8_t* outlier,
                           float* pose_out, int* n_inliers) {
-    pose_optimize_kernel<<<1, 256, 0, st>>>(p, work, level, outlier, pose_out, n_inliers);
+    pose_optimize_kernel<<<1, kPoseThreads, 0, st>>>(p, work, level, outlier, pose_out, n_inliers);
 }
 
 }  // namespace rgbl

@@ -22,6 +22,7 @@
 #if defined(__CUDA_ARCH__)
 #define QT_DEVICE 1
 #define QT_FN __device__
+#define QT_BIG __device__ __noinline__
 #define QT_NT ((int)blockDim.x)
 #define QT_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
 #define QT_SYNC() __syncthreads()
@@ -29,6 +30,7 @@
 #else
 #define QT_DEVICE 0
 #define QT_FN inline
+#define QT_BIG inline
 #define QT_NT 1
 #define QT_FOR(i, n) for (int i = 0; i < (n); ++i)
 #define QT_SYNC()
@@ -111,7 +113,7 @@ QT_FN void qs_insertion_sort(SortItem* v, int first, int last) {
     }
 }
 
-QT_FN void std_sort(SortItem* v, int n) {
+QT_BIG void std_sort(SortItem* v, int n) {
     if (n <= 1) return;
     // iterative form of __introsort_loop: an explicit stack of (first, last, depth) for the right-hand recursions
     int stk_first[64], stk_last[64], stk_depth[64], sp = 0;
@@ -191,29 +193,68 @@ struct Scratch {
     unsigned char* quad;                     // quadrant of the key at each position (4 = not moving)
 };
 
-// Exclusive scan of packed counters a[0..n) -> a (exclusive), a[n] = total.  Block-parallel on the device.
-QT_FN void scan_u64(unsigned long long* a, int n, Shared& s) {
+// Exclusive scan of packed counters a[0..n) -> a (exclusive), a[n] = total.  Block-parallel on the device:
+// per-thread chunks, warp shuffle scan of the chunk sums, then a scan of the <= 32 warp totals by warp 0.
+QT_BIG void scan_u64(unsigned long long* a, int n, Shared& s) {
 #if QT_DEVICE
-    const int nt = blockDim.x, tid = threadIdx.x;
+    const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     const int per = (n + nt - 1) / nt;
     const int b = min(tid * per, n), e = min(b + per, n);
     unsigned long long sum = 0;
     for (int i = b; i < e; ++i) sum += a[i];
-    s.scan_carry[tid] = sum;
+    unsigned long long incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s.scan_carry[warp] = incl;
     __syncthreads();
-    if (tid == 0) {
-        unsigned long long run = 0;
-        for (int t = 0; t < nt; ++t) { const unsigned long long v = s.scan_carry[t]; s.scan_carry[t] = run; run += v; }
-        a[n] = run;
+    if (warp == 0) {
+        unsigned long long v = (lane < nw) ? s.scan_carry[lane] : 0ull, w = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        if (lane < nw) s.scan_carry[lane] = w - v;
+        if (lane == nw - 1) a[n] = w;
     }
     __syncthreads();
-    unsigned long long run = s.scan_carry[tid];
+    unsigned long long run = s.scan_carry[warp] + incl - sum;
     for (int i = b; i < e; ++i) { const unsigned long long v = a[i]; a[i] = run; run += v; }
     __syncthreads();
 #else
     unsigned long long run = 0;
     for (int i = 0; i < n; ++i) { const unsigned long long v = a[i]; a[i] = run; run += v; }
     a[n] = run;
+    (void)s;
+#endif
+}
+
+// Exclusive scan of ints in shared memory (n <= 2 * blockDim), total returned through *total (shared).
+QT_BIG void scan_int(int* a, int n, int* total, Shared& s) {
+#if QT_DEVICE
+    const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int per = (n + nt - 1) / nt;
+    const int b = min(tid * per, n), e = min(b + per, n);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += a[i];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    int* carry = reinterpret_cast<int*>(s.scan_carry);
+    if (lane == 31) carry[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = (lane < nw) ? carry[lane] : 0, w = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        if (lane < nw) carry[lane] = w - v;
+        if (lane == nw - 1) *total = w;
+    }
+    __syncthreads();
+    int run = carry[warp] + incl - sum;
+    for (int i = b; i < e; ++i) { const int v = a[i]; a[i] = run; run += v; }
+    __syncthreads();
+#else
+    int run = 0;
+    for (int i = 0; i < n; ++i) { const int v = a[i]; a[i] = run; run += v; }
+    *total = run;
     (void)s;
 #endif
 }
@@ -225,7 +266,7 @@ QT_FN int cand_s(unsigned int c) { return (int)(c >> 24); }
 // Divide the nodes marked in s.proc (processing rank >= 0, s.n_div of them, s.by_rank filled) and rebuild the list.
 // On exit: s.cur_tab flipped, s.n_nodes updated, s.open[1-cur_open] holds the new expandable children in push
 // order and s.cur_open is flipped; perm/node arrays flipped by the caller-visible flag `pp` (returns new value).
-QT_FN int divide_pass(Shared& s, const unsigned int* cand, int n, Scratch g, int pp) {
+QT_BIG int divide_pass(Shared& s, const unsigned int* cand, int n, Scratch g, int pp) {
     NodeTable& T = s.tab[s.cur_tab];
     NodeTable& U = s.tab[1 - s.cur_tab];
     int* perm = pp ? g.perm_b : g.perm_a;
@@ -263,15 +304,13 @@ QT_FN int divide_pass(Shared& s, const unsigned int* cand, int n, Scratch g, int
         s.pushes[i] = (short)k;
     }
     QT_SYNC();
-    // prefix of pushes in processing order, prefix of survivors in list order (serial: <= 1024 nodes)
-    QT_SINGLE {
-        int run = 0;
-        for (int r = 0; r < s.n_div; ++r) { s.pushbase[r] = run; run += s.pushes[s.by_rank[r]]; }
-        s.total_push = run;
-        int keep = 0;
-        for (int i = 0; i < nn; ++i) { s.keepbase[i] = keep; keep += (s.proc[i] < 0); }
-        s.n_keep = keep;
-    }
+    // prefix of pushes in processing order, prefix of survivors in list order (block scans)
+    QT_FOR(r, s.n_div) s.pushbase[r] = s.pushes[s.by_rank[r]];
+    QT_FOR(i, nn) s.keepbase[i] = (s.proc[i] < 0) ? 1 : 0;
+    QT_SYNC();
+    scan_int(s.pushbase, s.n_div, &s.total_push, s);
+    QT_SYNC();
+    scan_int(s.keepbase, nn, &s.n_keep, s);
     QT_SYNC();
     const int total_push = s.total_push;
     // new node table: children (reverse push order) then survivors
@@ -299,16 +338,18 @@ QT_FN int divide_pass(Shared& s, const unsigned int* cand, int n, Scratch g, int
         }
     }
     QT_SYNC();
-    // expandable children in push order -> next open list
-    QT_SINGLE {
-        int m = 0;
+    // expandable children in push order -> next open list (compaction through a scan of the flags)
+    scan_int(s.open_slot, total_push, &s.n_expand, s);
+    QT_SYNC();
+    {
         SortItem* o = s.open[1 - s.cur_open];
-        for (int push = 0; push < total_push; ++push) {
-            if (!s.open_slot[push]) continue;
-            const int j = total_push - 1 - push;
-            o[m].size = U.end[j] - U.beg[j]; o[m].ulx = U.ulx[j]; o[m].node = j; ++m;
+        QT_FOR(push, total_push) {
+            const int nxt = (push + 1 < total_push) ? s.open_slot[push + 1] : s.n_expand;
+            if (nxt != s.open_slot[push]) {
+                const int j = total_push - 1 - push, m = s.open_slot[push];
+                o[m].size = U.end[j] - U.beg[j]; o[m].ulx = U.ulx[j]; o[m].node = j;
+            }
         }
-        s.n_expand = m;
     }
     // move the keys: stable 4-way partition inside every divided segment; everything else keeps its place
     QT_FOR(p, n) {

@@ -37,9 +37,15 @@ struct TrackBufs {
     float* q_f[7] = {}; size_t cap_q_f[7] = {};
     int* q_i = nullptr; size_t cap_q_i = 0;
     double* pose_work = nullptr; size_t cap_pose_work = 0;
+    // resident tracking chain
+    float* ch_poses = nullptr; size_t cap_ch_poses = 0;
+    int* ch_counts = nullptr; size_t cap_ch_counts = 0;
+    float *e_xw = nullptr, *e_obs = nullptr, *e_info = nullptr; size_t cap_e_xw = 0, cap_e_obs = 0, cap_e_info = 0;
+    uint8_t *e_st = nullptr, *e_lvl = nullptr, *e_out = nullptr; size_t cap_e_st = 0, cap_e_lvl = 0, cap_e_out = 0;
+    int* e_idx = nullptr; size_t cap_e_idx = 0;
     void release() {
         void* all[] = {keys, uright, desc, csr_idx, kp_cell, cell_start, state, match, minq, scalars, lists, list_n, choice, resolved,
-                       q_u8a, q_u8b, q_desc, q_f3a, q_f3b, q_f[0], q_f[1], q_f[2], q_f[3], q_f[4], q_f[5], q_f[6], q_i, pose_work};
+                       q_u8a, q_u8b, q_desc, q_f3a, q_f3b, q_f[0], q_f[1], q_f[2], q_f[3], q_f[4], q_f[5], q_f[6], q_i, pose_work, ch_poses, ch_counts, e_xw, e_obs, e_info, e_st, e_lvl, e_out, e_idx};
         for (void* p : all) if (p) cudaFree(p);
     }
 };

@@ -84,7 +84,7 @@ struct LocalPointsDev {              // vpMapPoints with the mTrack* fields isIn
     const uint8_t* in_view; const float *proj_x, *proj_y, *proj_xr, *depth; const int* level; const float* view_cos;
     const uint8_t* desc; const uint8_t* obs_pos;
 };
-struct SearchLastParams { float cur_pose[7]; float th; int forward, backward, check_orientation; };
+struct SearchLastParams { float cur_pose[7]; float th; int forward, backward, check_orientation; const float* cur_pose_dev; const int* flags_dev; };
 struct SearchLocalParams { float th, nn_ratio, th_far; int use_factor, far_points, keep_max; };
 struct FrustumParams { float Rcw[9], tcw[3], Ow[3], cos_limit; };
 struct MatchScratch { uint32_t* lists; int list_cap; int* list_n; int* minq; int* choice; uint8_t* resolved; int* overflow; int* rounds; };
@@ -94,6 +94,11 @@ void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_star
                         const SearchLastParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches);
 void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LocalPointsDev& lp,
                          const SearchLocalParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches);
+void launch_chain_prep(cudaStream_t st, const rgbl_keypoint* kps, const float* depth, const int* n_ptr, const float* last_pose,
+                       const float* cur_pose, const FrameDev& f, int mono, int cap, uint8_t* valid, float* xw, int* octave, float* angle,
+                       uint8_t* obs_pos, int* flags);
+void launch_chain_edges(cudaStream_t st, const rgbl_keypoint* kps, const float* uright, const int* n_ptr, const int* match,
+                        const float* last_xw, const FrameDev& f, float* exw, float* eobs, float* einfo, uint8_t* est, int* eidx, int* n_edges);
 void launch_frustum(cudaStream_t st, const FrameDev& f, const FrustumParams& prm, int n, const float* xw, const float* normal,
                     const float* mf_min, const float* mf_max, uint8_t* in_view, float* px, float* py, float* pxr, float* depth,
                     int* level, float* view_cos);
@@ -101,6 +106,8 @@ void launch_frustum(cudaStream_t st, const FrameDev& f, const FrustumParams& prm
 // pose_kernels.cu ----------------------------------------------------------------------------------
 struct PoseProblemDev {
     int n;                           // edges (keypoint order)
+    const int* n_dev;                // if non-null: edge count read on the device
+    const float* pose_in_dev;        // if non-null: initial pose read on the device
     const float* xw; const float* obs; const float* inv_sigma2; const uint8_t* stereo;
     float fx, fy, cx, cy, bf;
     float pose_in[7];

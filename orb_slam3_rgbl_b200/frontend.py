@@ -349,6 +349,14 @@ class RgblBatch:
         check(lib().rgbl_resident_process(c.handle, ptr(self.P), C.byref(self.prm), ptr(self.n)), c.handle)
         return self.n
 
+    def track(self, pose0, fx, fy, cx, cy, bf, th=15.0, mono=False):
+        """Resident tracking chain (rgbl_resident_track) -> (poses[nF,7], n_matches[nF], n_inliers[nF])"""
+        c = self.ctx
+        pose0 = np.ascontiguousarray(pose0, np.float32)
+        poses = np.empty((self.nF, 7), np.float32); nm = np.zeros(self.nF, np.int32); ni = np.zeros(self.nF, np.int32)
+        check(lib().rgbl_resident_track(c.handle, ptr(pose0), fx, fy, cx, cy, bf, th, int(mono), ptr(poses), ptr(nm), ptr(ni)), c.handle)
+        return poses, nm, ni
+
     def download(self):
         c = self.ctx
         check(lib().rgbl_resident_download(c.handle, ptr(self.kps), ptr(self.desc), ptr(self.depth), ptr(self.uright), self.cap, ptr(self.n)), c.handle)

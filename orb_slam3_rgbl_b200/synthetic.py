@@ -163,8 +163,8 @@ class PlaneSequence:
         """float32 4 x N planar: a Velodyne-like fan of rays hitting the plane z = Z (camera frame)."""
         rng = np.random.default_rng(self.seed * 7919 + t)
         # sample directions over the camera's field of view (plus margin), ring-major
-        v = np.linspace(-0.30, 0.28, self.n_rings)[:, None]          # tan(elevation) in camera y
-        u = np.linspace(-1.1, 1.1, self.n_az)[None, :]               # tan(azimuth) in camera x
+        v = np.linspace(-0.50, 0.40, self.n_rings)[:, None]          # tan(elevation) in camera y (image covers +-0.26)
+        u = np.linspace(-3.0, 3.0, self.n_az)[None, :]               # tan(azimuth) in camera x (image covers +-0.85): ~16 % land inside
         X = (u * self.Z) * np.ones_like(v); Y = (v * self.Z) * np.ones_like(u); Zc = np.full_like(X, self.Z)
         Zc = Zc + rng.normal(0.0, 0.01, Zc.shape)
         cam = np.stack([X.ravel(), Y.ravel(), Zc.ravel(), np.ones(X.size)])

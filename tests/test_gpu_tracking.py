@@ -43,7 +43,7 @@ def test_search_by_projection_last(ctx, seq_frames, th, mono, mix_obs, preoccupy
     rn, rmatch = oracle.search_by_projection_last(oracle.FrameView(*TD.frame_view_args(cur, sf)), *args, mono=mono, cur_state=state)
     m = F.ORBmatcher(ctx, 0.9, True)
     n, match = m.SearchByProjectionLastFrame(F.FrameView(*TD.frame_view_args(cur, sf)), *args, bMono=mono, cur_state=state)
-    assert rn > 300
+    assert rn > 150
     assert (match == rmatch).all(), f"{(match != rmatch).sum()} of {len(match)} assignments differ"
     assert n == rn
 
@@ -71,7 +71,7 @@ def test_is_in_frustum_and_local_search(ctx, seq_frames):
     ofv = oracle.FrameView(*TD.frame_view_args(cur, sf)); gfv = F.FrameView(*TD.frame_view_args(cur, sf))
     rt = oracle.is_in_frustum(ofv, Rcw, tcw, Ow, xw, normal, mn, mx, 0.5)
     gt = F.is_in_frustum(ctx, gfv, Rcw, tcw, Ow, xw, normal, mn, mx, 0.5)
-    assert rt["in_view"].sum() > 1000
+    assert rt["in_view"].sum() > 400
     for k in rt:
         assert (rt[k] == gt[k]).all(), f"isInFrustum field {k}: {(rt[k] != gt[k]).sum()} differ"
     obs_pos = np.ones(len(xw), np.uint8)
@@ -129,4 +129,26 @@ def test_track_with_motion_model_chain(ctx, seq_frames):
     gn, gpose, gout = F.Optimizer.PoseOptimization(ctx, seq.pose(0), xw[match[m]], obs, inv_s2, st, *TD.CAM)
     rn, rpose, rout = oracle.pose_optimize(seq.pose(0), xw[match[m]], obs, inv_s2, st, *TD.CAM)
     assert np.abs(gpose - rpose).max() < 1e-5 and (gout == rout).all()
-    assert abs(gpose[4] - seq.pose(1)[4]) < 0.01 and gn > 300
+    assert abs(gpose[4] - seq.pose(1)[4]) < 0.01 and gn > 150
+
+
+def test_resident_tracking_chain_matches_oracle_chain():
+    """extract + depth + (SearchByProjection -> PoseOptimization) x (n-1), all on the device, vs the same chain driven through
+    the oracle; and it follows the true camera motion of the synthetic sequence."""
+    T = 6
+    seq = S.PlaneSequence(8, T + 1)
+    imgs = [seq.image(t) for t in range(T)]; pcs = [seq.cloud(t) for t in range(T)]
+    c = F.Context(S.KITTI_W, S.KITTI_H, 2000, max_batch=T, max_points=pcs[0].shape[1])
+    try:
+        b = F.RgblBatch(c, imgs, pcs, seq.P, F.make_depth_params(bf=S.KITTI_BF), pinned=False)
+        b.upload(); b.process_resident()
+        poses, nm, ni = b.track(seq.pose(0), *TD.CAM, th=15.0)
+    finally:
+        c.close()
+    frames, sf = TD.extract_frames(seq, list(range(T)))
+    rposes, rnm, rni = TD.oracle_chain(frames, sf, seq.pose(0))
+    assert (nm == rnm).all() and (ni == rni).all(), (nm, rnm, ni, rni)
+    assert np.abs(poses - rposes).max() < 2e-5
+    for t in range(T):
+        assert abs(poses[t, 4] - seq.pose(t)[4]) < 0.02 and np.abs(poses[t, :3]).max() < 2e-3
+    assert (nm[1:] > 200).all() and (ni[1:] > 150).all()

@@ -77,3 +77,50 @@ def pose_problem(seed, n=900, outlier_frac=0.3, stereo_frac=0.7):
     pose0 = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
     return dict(pose0=pose0, xw=Xw.astype(np.float32), obs=obs.astype(np.float32), inv_s2=inv_s2, stereo=stereo,
                 truth=np.r_[q_true, t_true])
+
+
+# ---- float32 mirror of the resident chain's glue (Frame::UnprojectStereo with a Sophus SE3f pose) ----
+f32 = np.float32
+
+
+def se3f_rotate(q, p):
+    """Sophus SO3f * point (so3.hpp:358-366), float32, same operation order as the kernels."""
+    qx, qy, qz, qw = (f32(v) for v in q[:4])
+    px, py, pz = p[:, 0], p[:, 1], p[:, 2]
+    uv = np.stack([qy * pz - qz * py, qz * px - qx * pz, qx * py - qy * px], 1).astype(f32)
+    uv = (uv + uv).astype(f32)
+    c = np.stack([qy * uv[:, 2] - qz * uv[:, 1], qz * uv[:, 0] - qx * uv[:, 2], qx * uv[:, 1] - qy * uv[:, 0]], 1).astype(f32)
+    return ((p + qw * uv).astype(f32) + c).astype(f32)
+
+
+def chain_unproject(fr, pose):
+    k, z = fr["k"], fr["depth"]
+    ok = z > 0
+    zz = np.where(ok, z, f32(1)).astype(f32)
+    invfx, invfy = f32(1.0) / f32(S.KITTI_FX), f32(1.0) / f32(S.KITTI_FY)
+    pc = np.stack([((k["x"] - f32(S.KITTI_CX)) * zz).astype(f32) * invfx, ((k["y"] - f32(S.KITTI_CY)) * zz).astype(f32) * invfy, zz], 1).astype(f32)
+    inv = np.array([-pose[0], -pose[1], -pose[2], pose[3]], f32)
+    nt = (np.asarray(pose[4:7], f32) * f32(-1.0)).astype(f32)[None, :]
+    ow = se3f_rotate(inv, nt)
+    xw = (se3f_rotate(inv, pc) + ow).astype(f32)
+    return xw, ok
+
+
+def oracle_chain(frames, sf, pose0, th=15.0):
+    poses = [np.asarray(pose0, f32)]
+    nms, nis = [0], [0]
+    for t in range(1, len(frames)):
+        last, cur = frames[t - 1], frames[t]
+        lp = poses[-1]
+        xw, ok = chain_unproject(last, lp)
+        fv = oracle.FrameView(*frame_view_args(cur, sf))
+        nm, match = oracle.search_by_projection_last(fv, lp, lp, ok.astype(np.uint8), xw, last["d"], last["k"]["octave"], last["k"]["angle"],
+                                                     np.ones(len(ok), np.uint8), th)
+        m = np.nonzero(match >= 0)[0]
+        obs = np.stack([cur["k"]["x"][m], cur["k"]["y"][m], cur["ur"][m]], 1).astype(f32)
+        s = sf[cur["k"]["octave"][m]]
+        inv_s2 = (f32(1.0) / (s * s).astype(f32)).astype(f32)
+        st = (cur["ur"][m] >= 0).astype(np.uint8)
+        ni, pose, _ = oracle.pose_optimize(lp, xw[match[m]], obs, inv_s2, st, *CAM)
+        poses.append(pose); nms.append(nm); nis.append(ni)
+    return np.stack(poses), np.array(nms), np.array(nis)

@@ -107,7 +107,7 @@ def make_batch_inputs(rank: int, T: int):
 
 CAM = (S.KITTI_FX, S.KITTI_FY, S.KITTI_CX, S.KITTI_CY, S.KITTI_BF)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/), else None
-TRAFFIC = {}
+TRAFFIC = {"fast": 42294016 + 183552}   # profiles/r01_ncu_full_fast_cells_kernel.txt (32-frame launch)
 
 
 def cpu_track_step(fv_args_cur, last, pose, sf):

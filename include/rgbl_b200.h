@@ -178,6 +178,26 @@ int rgbl_search_by_projection_local(rgbl_ctx* ctx, const rgbl_frame_view* cur, i
                                     const float* view_cos, const uint8_t* mp_desc, const uint8_t* obs_pos, float th, float nn_ratio,
                                     int far_points, float th_far, const uint8_t* cur_state, int32_t* match, int* n_matches);
 
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (include/ORBmatcher.h:65,
+ * src/ORBmatcher.cc:223-425), Nleft == -1.  pKF->mFeatVec and F.mFeatVec (DBoW2::FeatureVector = std::map<NodeId,
+ * vector<unsigned>>) are passed as CSR: ascending node ids, node_start[n_nodes+1], feature indices in vector order.
+ * kf_valid[i] = vpMapPointsKF[i] != NULL && !isBad().  match[idxF] = key-frame feature index whose map point is assigned
+ * to F's feature idxF, or -1 (= NULL).  *n_matches = the reference's return value.                                    */
+int rgbl_search_by_bow(rgbl_ctx* ctx, int n_kf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid,
+                       int n_nodes_kf, const uint32_t* kf_node_ids, const int32_t* kf_node_start, const int32_t* kf_node_feat,
+                       int n_f, const uint8_t* f_desc, const float* f_angle,
+                       int n_nodes_f, const uint32_t* f_node_ids, const int32_t* f_node_start, const int32_t* f_node_feat,
+                       float nn_ratio, int check_orientation, int32_t* match, int* n_matches);
+
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, float th,
+ * int ORBdist) (include/ORBmatcher.h:57, src/ORBmatcher.cc:1889-2010): relocalisation refinement.  Key-frame map points
+ * i: valid[i] = pMP && !isBad() && !sAlreadyFound.count(pMP); kf_angle = pKF->mvKeysUn[i].angle; mf_min/max_dist =
+ * mfMinDistance / mfMaxDistance.  cur_occupied[i2] != 0 <=> CurrentFrame.mvpMapPoints[i2] != NULL.  match as above.   */
+int rgbl_search_by_projection_reloc(rgbl_ctx* ctx, const rgbl_frame_view* cur, const float cur_pose[7], int n, const uint8_t* valid,
+                                    const float* xw, const uint8_t* mp_desc, const float* kf_angle, const float* mf_min_dist,
+                                    const float* mf_max_dist, float th, int orb_dist, int check_orientation, const uint8_t* cur_occupied,
+                                    int32_t* match, int* n_matches);
+
 /* Optimizer::PoseOptimization(Frame*) (include/Optimizer.h, src/Optimizer.cc:814-1114) for Nleft == -1 frames.
  * One edge per keypoint that has a map point, in keypoint order: xw = GetWorldPos(), obs = (kpUn.x, kpUn.y,
  * mvuRight[i]), inv_sigma2 = mvInvLevelSigma2[octave], stereo[i] = mvuRight[i] >= 0.  pose = Frame::GetPose().

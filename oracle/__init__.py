@@ -287,6 +287,10 @@ def _late(L):
     L.orc_is_in_frustum.argtypes = [fv, vp, vp, vp, i, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, vp, vp]
     L.orc_search_by_projection_local.argtypes = [fv, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, f, f, i, f, vp, vp]
     L.orc_search_by_projection_local.restype = i
+    L.orc_search_by_bow.argtypes = [i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, f, i, vp]
+    L.orc_search_by_bow.restype = i
+    L.orc_search_by_projection_reloc.argtypes = [fv, vp, i, vp, vp, vp, vp, vp, vp, f, i, i, vp, vp]
+    L.orc_search_by_projection_reloc.restype = i
     L.orc_pose_optimize.argtypes = [vp, i, vp, vp, vp, vp, f, f, f, f, f, vp, vp]
     L.orc_pose_optimize.restype = i
     _LATE_DECL_DONE = True
@@ -357,3 +361,32 @@ def pose_optimize(pose, xw, obs, inv_sigma2, stereo, fx, fy, cx, cy, bf):
     out = np.empty(7, np.float32); outlier = np.zeros(n, np.uint8)
     r = lib().orc_pose_optimize(_p(pose), n, _p(xw), _p(obs), _p(inv_sigma2), _p(stereo), fx, fy, cx, cy, bf, _p(out), _p(outlier))
     return r, out, outlier
+
+
+def _csr(node_ids, node_start, node_feat):
+    return (np.ascontiguousarray(node_ids, np.uint32), np.ascontiguousarray(node_start, np.int32), np.ascontiguousarray(node_feat, np.int32))
+
+
+def search_by_bow(kf_desc, kf_angle, kf_valid, kf_csr, f_desc, f_angle, f_csr, nn_ratio=0.7, check_orientation=True):
+    """SearchByBoW(KF, F): csr = (node_ids ascending, node_start[n+1], node_feat). -> (nmatches, match[n_f] = KF index or -1)"""
+    _late(lib())
+    kf_desc = np.ascontiguousarray(kf_desc, np.uint8); f_desc = np.ascontiguousarray(f_desc, np.uint8)
+    kf_angle = np.ascontiguousarray(kf_angle, np.float32); f_angle = np.ascontiguousarray(f_angle, np.float32)
+    kf_valid = np.ascontiguousarray(kf_valid, np.uint8)
+    ki, ks, kfeat = _csr(*kf_csr); fi, fs, ffeat = _csr(*f_csr)
+    match = np.empty(len(f_desc), np.int32)
+    nm = lib().orc_search_by_bow(len(kf_desc), _p(kf_desc), _p(kf_angle), _p(kf_valid), len(ki), _p(ki), _p(ks), _p(kfeat),
+                                 len(f_desc), _p(f_desc), _p(f_angle), len(fi), _p(fi), _p(fs), _p(ffeat), nn_ratio, int(check_orientation), _p(match))
+    return nm, match
+
+
+def search_by_projection_reloc(cur: FrameView, cur_pose, valid, xw, mp_desc, kf_angle, mf_min, mf_max, th, orb_dist, check_orientation=True, cur_occupied=None):
+    _late(lib())
+    cur_pose = np.ascontiguousarray(cur_pose, np.float32); valid = np.ascontiguousarray(valid, np.uint8)
+    xw = np.ascontiguousarray(xw, np.float32); mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    kf_angle = np.ascontiguousarray(kf_angle, np.float32); mn = np.ascontiguousarray(mf_min, np.float32); mx = np.ascontiguousarray(mf_max, np.float32)
+    occ = np.zeros(cur.c.n, np.uint8) if cur_occupied is None else np.ascontiguousarray(cur_occupied, np.uint8)
+    match = np.empty(cur.c.n, np.int32)
+    nm = lib().orc_search_by_projection_reloc(C.byref(cur.c), _p(cur_pose), len(valid), _p(valid), _p(xw), _p(mp_desc), _p(kf_angle), _p(mn), _p(mx),
+                                              th, int(orb_dist), int(check_orientation), _p(occ), _p(match))
+    return nm, match

@@ -306,4 +306,128 @@ int orc_search_by_projection_local(const orc_frame_view* fv, int n, const uint8_
     return nmatches;
 }
 
+
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), Nleft == -1 path (src/ORBmatcher.cc:223-425).
+// The two DBoW2::FeatureVector maps are given as CSR: ascending node ids, per node the feature indices in vector order.
+// kf_valid[i] = (vpMapPointsKF[i] != NULL && !isBad()).  match[idxF] = KF feature index (the caller maps it to the
+// MapPoint*) or -1.  Returns nmatches.
+int orc_search_by_bow(int n_kf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid,
+                      int n_nodes_kf, const uint32_t* kf_node_ids, const int* kf_node_start, const int* kf_node_feat,
+                      int n_f, const uint8_t* f_desc, const float* f_angle,
+                      int n_nodes_f, const uint32_t* f_node_ids, const int* f_node_start, const int* f_node_feat,
+                      float nn_ratio, int check_orientation, int* match) {
+    constexpr int TH_LOW = 50;
+    (void)n_kf;
+    for (int i = 0; i < n_f; ++i) match[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rot_hist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int a = 0, b = 0;
+    while (a < n_nodes_kf && b < n_nodes_f) {
+        if (kf_node_ids[a] == f_node_ids[b]) {
+            for (int ik = kf_node_start[a]; ik < kf_node_start[a + 1]; ++ik) {
+                const int ikf = kf_node_feat[ik];
+                if (!kf_valid[ikf]) continue;
+                int best1 = 256, best_idx = -1, best2 = 256;
+                for (int jf = f_node_start[b]; jf < f_node_start[b + 1]; ++jf) {
+                    const int idf = f_node_feat[jf];
+                    if (match[idf] >= 0) continue;
+                    const int d = descriptor_distance(kf_desc + 32 * ikf, f_desc + 32 * idf);
+                    if (d < best1) { best2 = best1; best1 = d; best_idx = idf; }
+                    else if (d < best2) best2 = d;
+                }
+                if (best1 <= TH_LOW) {
+                    if (static_cast<float>(best1) < nn_ratio * static_cast<float>(best2)) {
+                        match[best_idx] = ikf;
+                        if (check_orientation) {
+                            float rot = kf_angle[ikf] - f_angle[best_idx];
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = (int)std::round(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            rot_hist[bin].push_back(best_idx);
+                        }
+                        ++nmatches;
+                    }
+                }
+            }
+            ++a; ++b;
+        } else if (kf_node_ids[a] < f_node_ids[b]) {
+            while (a < n_nodes_kf && kf_node_ids[a] < f_node_ids[b]) ++a;      // lower_bound
+        } else {
+            while (b < n_nodes_f && f_node_ids[b] < kf_node_ids[a]) ++b;
+        }
+    }
+    if (check_orientation) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rot_hist, HISTO_LENGTH, i1, i2, i3);
+        for (int k = 0; k < HISTO_LENGTH; ++k) {
+            if (k == i1 || k == i2 || k == i3) continue;
+            for (int idx : rot_hist[k]) { match[idx] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame*, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
+// (src/ORBmatcher.cc:1889-2010), the relocalisation refinement.  Per key-frame map point i: valid[i] = (pMP && !isBad() &&
+// !sAlreadyFound.count(pMP)), xw, descriptor, the key frame's keypoint angle, mfMinDistance / mfMaxDistance.
+// cur_occupied[i2] != 0 <=> CurrentFrame.mvpMapPoints[i2] != NULL.  match[i2]: >= 0 index i, -1 untouched, -2 cleared.
+int orc_search_by_projection_reloc(const orc_frame_view* cur, const float cur_pose[7], int n, const uint8_t* valid,
+                                   const float* xw, const uint8_t* mp_desc, const float* kf_angle, const float* mf_min_dist,
+                                   const float* mf_max_dist, float th, int orb_dist, int check_orientation,
+                                   const uint8_t* cur_occupied, int* match) {
+    FrameView F = to_view(cur);
+    Grid g; g.build(F);
+    Pose Tcw = {cur_pose[0], cur_pose[1], cur_pose[2], cur_pose[3], cur_pose[4], cur_pose[5], cur_pose[6]};
+    float Ow[3];
+    inverse_translation(Tcw, Ow);
+    int nmatches = 0;
+    std::vector<int> rot_hist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<uint8_t> occ(cur_occupied, cur_occupied + F.n);
+    for (int i = 0; i < F.n; ++i) match[i] = -1;
+    std::vector<int> cand;
+    for (int i = 0; i < n; ++i) {
+        if (!valid[i]) continue;
+        float xc[3];
+        transform(Tcw, xw + 3 * i, xc);
+        const float u = F.fx * xc[0] / xc[2] + F.cx, v = F.fy * xc[1] / xc[2] + F.cy;
+        if (u < F.min_x || u > F.max_x) continue;
+        if (v < F.min_y || v > F.max_y) continue;
+        const float PO[3] = {xw[3 * i] - Ow[0], xw[3 * i + 1] - Ow[1], xw[3 * i + 2] - Ow[2]};
+        const float dist3D = std::sqrt((PO[0] * PO[0] + PO[1] * PO[1]) + PO[2] * PO[2]);
+        if (dist3D < 0.8f * mf_min_dist[i] || dist3D > 1.2f * mf_max_dist[i]) continue;
+        const float ratio = mf_max_dist[i] / dist3D;
+        int pl = (int)std::ceil(std::log(ratio) / F.log_scale_factor);
+        if (pl < 0) pl = 0; else if (pl >= F.n_levels) pl = F.n_levels - 1;
+        const float radius = th * F.scale_factors[pl];
+        features_in_area(F, g, u, v, radius, pl - 1, pl + 1, cand);
+        if (cand.empty()) continue;
+        int best = 256, best_idx = -1;
+        for (int i2 : cand) {
+            if (occ[i2]) continue;
+            const int d = descriptor_distance(mp_desc + 32 * i, F.desc + 32 * i2);
+            if (d < best) { best = d; best_idx = i2; }
+        }
+        if (best <= orb_dist) {
+            match[best_idx] = i; occ[best_idx] = 1; ++nmatches;
+            if (check_orientation) {
+                float rot = kf_angle[i] - F.keys_un[best_idx].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rot_hist[bin].push_back(best_idx);
+            }
+        }
+    }
+    if (check_orientation) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        three_maxima(rot_hist, HISTO_LENGTH, i1, i2, i3);
+        for (int b = 0; b < HISTO_LENGTH; ++b)
+            if (b != i1 && b != i2 && b != i3)
+                for (int idx : rot_hist[b]) { match[idx] = -2; --nmatches; }
+    }
+    return nmatches;
+}
+
 }  // extern "C"

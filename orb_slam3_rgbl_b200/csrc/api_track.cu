@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "rgbl_ctx.h"
 
@@ -266,6 +267,108 @@ int rgbl_pose_optimize(rgbl_ctx* ctx, const float pose_in[7], int n, const float
     return RGBL_OK;
 }
 
+
+int rgbl_search_by_bow(rgbl_ctx* ctx, int n_kf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid,
+                       int n_nodes_kf, const uint32_t* kf_node_ids, const int32_t* kf_node_start, const int32_t* kf_node_feat,
+                       int n_f, const uint8_t* f_desc, const float* f_angle,
+                       int n_nodes_f, const uint32_t* f_node_ids, const int32_t* f_node_start, const int32_t* f_node_feat,
+                       float nn_ratio, int check_orientation, int32_t* match, int* n_matches) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (n_kf < 0 || n_f < 0 || n_nodes_kf < 0 || n_nodes_f < 0 || !match || !(nn_ratio > 0.f) ||
+        (n_kf > 0 && (!kf_desc || !kf_angle || !kf_valid)) || (n_f > 0 && (!f_desc || !f_angle)) ||
+        (n_nodes_kf > 0 && (!kf_node_ids || !kf_node_start || !kf_node_feat)) || (n_nodes_f > 0 && (!f_node_ids || !f_node_start || !f_node_feat))) {
+        c->err = "bad argument"; return RGBL_E_INVALID;
+    }
+    CU(cudaSetDevice(c->cfg.device));
+    // merge-join of the two feature vectors (src/ORBmatcher.cc:239-393): queries in the reference's processing order
+    std::vector<int> q_feat, q_cbeg, q_cend;
+    std::vector<float> q_ang;
+    int a = 0, b = 0;
+    while (a < n_nodes_kf && b < n_nodes_f) {
+        if (kf_node_ids[a] == f_node_ids[b]) {
+            for (int ik = kf_node_start[a]; ik < kf_node_start[a + 1]; ++ik) {
+                const int ikf = kf_node_feat[ik];
+                if (ikf < 0 || ikf >= n_kf) { c->err = "KF feature index out of range"; return RGBL_E_INVALID; }
+                if (!kf_valid[ikf]) continue;
+                q_feat.push_back(ikf); q_cbeg.push_back(f_node_start[b]); q_cend.push_back(f_node_start[b + 1]); q_ang.push_back(kf_angle[ikf]);
+            }
+            ++a; ++b;
+        } else if (kf_node_ids[a] < f_node_ids[b]) ++a;
+        else ++b;
+    }
+    const int n_q = (int)q_feat.size();
+    const int n_fcsr = n_nodes_f > 0 ? f_node_start[n_nodes_f] : 0;
+    for (int i = 0; i < n_f; ++i) match[i] = -1;
+    if (n_matches) *n_matches = 0;
+    if (n_q == 0 || n_f == 0) return RGBL_OK;
+    int rc = ensure_frame(c, std::max(n_f, n_fcsr)); if (rc) return rc;
+    rc = ensure_queries(c, std::max(n_q, n_kf)); if (rc) return rc;
+    TrackBufs& t = c->trk;
+    GROW(t.e_idx, t.cap_e_idx, (size_t)3 * n_q);
+    CU(cudaMemcpyAsync(t.q_desc, kf_desc, (size_t)n_kf * 32, cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.desc, f_desc, (size_t)n_f * 32, cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.uright, f_angle, (size_t)n_f * sizeof(float), cudaMemcpyHostToDevice, c->st));       // reused as F angles
+    CU(cudaMemcpyAsync(t.csr_idx, f_node_feat, (size_t)n_fcsr * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.e_idx, q_feat.data(), (size_t)n_q * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.e_idx + n_q, q_cbeg.data(), (size_t)n_q * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.e_idx + 2 * n_q, q_cend.data(), (size_t)n_q * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.q_f[0], q_ang.data(), (size_t)n_q * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemsetAsync(t.q_u8b, 1, n_q, c->st));                                                              // every assignment blocks
+    CU(cudaMemsetAsync(t.state, 0, n_f, c->st));
+    c->h_scalars[0] = n_f;
+    CU(cudaMemcpyAsync(t.scalars, c->h_scalars, sizeof(int), cudaMemcpyHostToDevice, c->st));
+    FrameDev f{};
+    f.n = t.scalars;
+    // a second-best beyond TH_LOW / nnratio can never reject: best <= TH_LOW < nnratio * second
+    const int keep_max = std::min(256, (int)std::floor(50.0f / nn_ratio) + 1);
+    stage_begin(c, ST_MATCH, c->st);
+    launch_search_bow(c->st, f, n_q, t.e_idx, t.e_idx + n_q, t.e_idx + 2 * n_q, t.q_desc, t.desc, t.q_f[0], t.uright, t.csr_idx, nn_ratio, keep_max,
+                      check_orientation, t.q_u8b, scratch(c), t.state, t.match, t.scalars + 1);
+    std::vector<int32_t> mq(n_f);
+    rc = finish_search(c, n_f, mq.data(), n_matches); if (rc) return rc;
+    for (int i = 0; i < n_f; ++i) match[i] = (mq[i] >= 0) ? q_feat[mq[i]] : -1;       // cleared (-2) -> NULL like the reference
+    return RGBL_OK;
+}
+
+int rgbl_search_by_projection_reloc(rgbl_ctx* ctx, const rgbl_frame_view* cur, const float cur_pose[7], int n, const uint8_t* valid,
+                                    const float* xw, const uint8_t* mp_desc, const float* kf_angle, const float* mf_min_dist,
+                                    const float* mf_max_dist, float th, int orb_dist, int check_orientation, const uint8_t* cur_occupied,
+                                    int32_t* match, int* n_matches) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!cur || !cur_pose || n < 0 || !match || (n > 0 && (!valid || !xw || !mp_desc || !kf_angle || !mf_min_dist || !mf_max_dist))) { c->err = "null argument"; return RGBL_E_INVALID; }
+    CU(cudaSetDevice(c->cfg.device));
+    FrameDev f;
+    int rc = upload_frame(c, cur, f); if (rc) return rc;
+    rc = ensure_queries(c, std::max(n, 1)); if (rc) return rc;
+    TrackBufs& t = c->trk;
+    if (n) {
+        CU(cudaMemcpyAsync(t.q_u8a, valid, n, cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_f3a, xw, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_desc, mp_desc, (size_t)n * 32, cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_f[0], kf_angle, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_f[4], mf_min_dist, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(t.q_f[5], mf_max_dist, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemsetAsync(t.q_u8b, 1, n, c->st));
+    }
+    std::vector<uint8_t> st(std::max(cur->n, 1), 0);
+    if (cur_occupied) for (int i = 0; i < cur->n; ++i) st[i] = cur_occupied[i] ? 1 : 0;        // any map point blocks (:1950-1951)
+    if (cur->n) CU(cudaMemcpyAsync(t.state, st.data(), cur->n, cudaMemcpyHostToDevice, c->st));
+    SearchRelocParams prm;
+    std::memcpy(prm.cur_pose, cur_pose, 7 * sizeof(float));
+    {   // Ow = Tcw.inverse().translation()
+        float inv[7] = {-cur_pose[0], -cur_pose[1], -cur_pose[2], cur_pose[3], 0, 0, 0};
+        const float nt[3] = {cur_pose[4] * -1.f, cur_pose[5] * -1.f, cur_pose[6] * -1.f};
+        h_rotate(inv, nt, prm.Ow);
+    }
+    prm.th = th; prm.orb_dist = orb_dist; prm.check_orientation = check_orientation;
+    RelocPointsDev rp{n, t.q_u8a, t.q_f3a, t.q_desc, t.q_f[0], t.q_f[4], t.q_f[5]};
+    if (n == 0) { CU(cudaMemsetAsync(t.match, 0xff, (size_t)std::max(cur->n, 1) * sizeof(int), c->st)); CU(cudaMemsetAsync(t.scalars + 1, 0, 2 * sizeof(int), c->st)); }
+    launch_search_reloc(c->st, f, t.cell_start, t.csr_idx, rp, prm, t.q_u8b, scratch(c), t.state, t.match, t.scalars + 1);
+    CU(cudaStreamSynchronize(c->st));      // `st` (host vector) must outlive the async copy
+    return finish_search(c, cur->n, match, n_matches);
+}
 
 /* Resident tracking chain over the frames of the last rgbl_resident_process / rgbl_frame_rgbl_batch call, entirely on the
  * device (no host round trip per frame): for t = 1..n-1  SearchByProjection(frame t, frame t-1) -> PoseOptimization, with

@@ -266,7 +266,8 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
                                                        const int* __restrict__ list_n,
                                                        const uint8_t* __restrict__ obs_pos,
                                                        const float* __restrict__ q_angle, float nn_ratio,
-                                                       int check_orientation, uint8_t* __restrict__ state,
+                                                       int check_orientation, int th_accept,
+                                                       const float* __restrict__ f_angle, uint8_t* __restrict__ state,
                                                        int* __restrict__ minq, int* __restrict__ choice,
                                                        uint8_t* __restrict__ resolved, int* __restrict__ match,
                                                        int* __restrict__ n_matches, int* __restrict__ rounds_out) {
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
                 const uint32_t key = l[k];
                 const int ft = csr_idx[key & kPosMask];
                 if (state[ft] == 1) continue;
-                if (mode == 1 && minq[ft] != q) depends_ok = false;
+                if (mode >= 1 && minq[ft] != q) depends_ok = false;
                 const int d = (int)(key >> 20);
                 if (mode == 0) {
                     if (key < best) best = key;
@@ -315,8 +316,9 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
                     // reference scan order = ascending csr position; emulate "dist < bestDist" / "else if dist < bestDist2"
                     // order-independently: best = min by (dist, pos); second = min dist among the rest (level of the
                     // FIRST candidate in scan order reaching that distance)
-                    if (key < best) { best2 = best; lvl2 = lvl; best = key; lvl = f.keys[ft].octave; }
-                    else if (key < best2) { best2 = key; lvl2 = f.keys[ft].octave; }
+                    const int oc = (mode == 1) ? f.keys[ft].octave : 0;
+                    if (key < best) { best2 = best; lvl2 = lvl; best = key; lvl = oc; }
+                    else if (key < best2) { best2 = key; lvl2 = oc; }
                     (void)d;
                 }
             }
@@ -326,10 +328,14 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             if (!final_ok) { atomicAdd(&s_unresolved, 1); continue; }
             resolved[q] = 1;
             const int bd = (int)(best >> 20);
-            bool accept = bd <= kThHigh;
+            bool accept = bd <= th_accept;
             if (mode == 1 && accept) {
                 const int bd2 = (best2 == 0xffffffffu) ? 256 : (int)(best2 >> 20);
                 if (lvl == lvl2 && (float)bd > __fmul_rn(nn_ratio, (float)bd2)) accept = false;
+            }
+            if (mode == 2 && accept) {            // SearchByBoW: bestDist1 < mfNNratio * bestDist2 (src/ORBmatcher.cc:324)
+                const int bd2 = (best2 == 0xffffffffu) ? 256 : (int)(best2 >> 20);
+                accept = (float)bd < __fmul_rn(nn_ratio, (float)bd2);
             }
             if (accept) {
                 choice[q] = fb;
@@ -344,13 +350,13 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
     }
     // owner of a feature = the last (highest-index) query that chose it
     for (int q = tid; q < n_q; q += 1024) if (choice[q] >= 0) atomicMax(&match[choice[q]], q);
-    if (mode == 0 && check_orientation) {
+    if (mode != 1 && check_orientation) {
         for (int b = tid; b < kHistoLength; b += 1024) hist[b] = 0;
         __syncthreads();
         const float factor = 1.0f / kHistoLength;
         for (int q = tid; q < n_q; q += 1024) {
             if (choice[q] < 0) continue;
-            float rot = __fsub_rn(q_angle[q], f.keys[choice[q]].angle);
+            float rot = __fsub_rn(q_angle[q], f_angle ? f_angle[choice[q]] : f.keys[choice[q]].angle);
             if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
             int bin = (int)roundf(__fmul_rn(rot, factor));
             if (bin == kHistoLength) bin = 0;
@@ -372,7 +378,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         __syncthreads();
         for (int q = tid; q < n_q; q += 1024) {
             if (choice[q] < 0) continue;
-            float rot = __fsub_rn(q_angle[q], f.keys[choice[q]].angle);
+            float rot = __fsub_rn(q_angle[q], f_angle ? f_angle[choice[q]] : f.keys[choice[q]].angle);
             if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
             int bin = (int)roundf(__fmul_rn(rot, factor));
             if (bin == kHistoLength) bin = 0;
@@ -424,6 +430,73 @@ __global__ void __launch_bounds__(256) frustum_kernel(FrameDev f, FrustumParams 
         }
     }
     in_view[i] = iv; px[i] = ox; py[i] = oy; pxr[i] = oxr; depth[i] = od; level[i] = ol; view_cos[i] = ovc;
+}
+
+// ---- SearchByBoW(KF, F): candidates = the F features of the same vocabulary node -----------------------------------
+__global__ void __launch_bounds__(256) bow_collect_kernel(int n_q, const int* __restrict__ q_feat, const int* __restrict__ q_cbeg,
+                                                          const int* __restrict__ q_cend, const uint8_t* __restrict__ kf_desc,
+                                                          const uint8_t* __restrict__ f_desc, const int* __restrict__ f_node_feat,
+                                                          int keep_max, uint32_t* __restrict__ lists, int list_cap,
+                                                          int* __restrict__ list_n, int* __restrict__ overflow) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= n_q) return;
+    const uint8_t* dq = kf_desc + (size_t)q_feat[q] * 32;
+    const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(dq)), d1 = __ldg(reinterpret_cast<const uint4*>(dq) + 1);
+    const int b = q_cbeg[q], e = q_cend[q];
+    uint32_t* list = lists + (size_t)q * list_cap;
+    int count = 0;
+    for (int p0 = b; p0 < e; p0 += 32) {
+        const int p = p0 + lane;
+        bool keep = false;
+        uint32_t key = 0;
+        if (p < e) {
+            const int d = hamming256(d0, d1, f_desc + (size_t)f_node_feat[p] * 32);
+            if (d <= keep_max) { keep = true; key = ((uint32_t)d << 20) | (uint32_t)p; }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) { const int o = count + __popc(m & ((1u << lane) - 1u)); if (o < list_cap) list[o] = key; }
+        count += __popc(m);
+    }
+    if (lane == 0) { list_n[q] = min(count, list_cap); if (count > list_cap) atomicExch(overflow, 3); }
+}
+
+// ---- SearchByProjection(CurrentFrame, KeyFrame, sAlreadyFound, th, ORBdist): candidate phase -------------------------
+__global__ void __launch_bounds__(256) search_reloc_collect_kernel(FrameDev f, const int* __restrict__ cell_start,
+                                                                   const int* __restrict__ csr_idx, RelocPointsDev rp,
+                                                                   SearchRelocParams prm, uint32_t* __restrict__ lists,
+                                                                   int list_cap, int* __restrict__ list_n,
+                                                                   int* __restrict__ overflow) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= rp.n) return;
+    int count = 0;
+    if (rp.valid[q]) {
+        const float p[3] = {rp.xw[3 * q], rp.xw[3 * q + 1], rp.xw[3 * q + 2]};
+        float xc[3];
+        se3f_rotate(prm.cur_pose, p, xc);
+        xc[0] = __fadd_rn(xc[0], prm.cur_pose[4]); xc[1] = __fadd_rn(xc[1], prm.cur_pose[5]); xc[2] = __fadd_rn(xc[2], prm.cur_pose[6]);
+        const float u = __fadd_rn(__fdiv_rn(__fmul_rn(f.fx, xc[0]), xc[2]), f.cx);
+        const float v = __fadd_rn(__fdiv_rn(__fmul_rn(f.fy, xc[1]), xc[2]), f.cy);
+        bool ok = !(u < f.min_x || u > f.max_x) && !(v < f.min_y || v > f.max_y);     // note: no positive-depth test in the reference
+        if (ok) {
+            const float PO[3] = {__fsub_rn(p[0], prm.Ow[0]), __fsub_rn(p[1], prm.Ow[1]), __fsub_rn(p[2], prm.Ow[2])};
+            const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(PO[0], PO[0]), __fmul_rn(PO[1], PO[1])), __fmul_rn(PO[2], PO[2])));
+            if (!(dist < __fmul_rn(0.8f, rp.mf_min[q]) || dist > __fmul_rn(1.2f, rp.mf_max[q]))) {
+                const float ratio = __fdiv_rn(rp.mf_max[q], dist);
+                const float lg = (float)log((double)ratio);
+                int pl = (int)ceilf(__fdiv_rn(lg, f.log_scale_factor));
+                if (pl < 0) pl = 0; else if (pl >= f.n_levels) pl = f.n_levels - 1;
+                const float radius = __fmul_rn(prm.th, f.scale[pl]);
+                const CellRange cr = cell_range(f, u, v, radius);
+                if (cr.ok) {
+                    const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(rp.desc + (size_t)q * 32));
+                    const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(rp.desc + (size_t)q * 32) + 1);
+                    count = warp_collect(f, cell_start, csr_idx, cr, u, v, radius, pl - 1, pl + 1, d0, d1, prm.orb_dist,
+                                         lists + (size_t)q * list_cap, list_cap, [](int) { return true; });
+                }
+            }
+        }
+    }
+    if (lane == 0) { list_n[q] = min(count, list_cap); if (count > list_cap) atomicExch(overflow, 3); }
 }
 
 // ---- resident tracking chain (TrackWithMotionModel-style glue between the reference functions) ----------------
@@ -519,7 +592,7 @@ void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_star
     if (lf.n <= 0) return;
     search_last_collect_kernel<<<(lf.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lf, prm, s.lists, s.list_cap, s.list_n, s.overflow);
     resolve_kernel<<<1, 1024, 0, st>>>(0, lf.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lf.obs_pos, lf.angle, 0.f,
-                                       prm.check_orientation, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds);
+                                       prm.check_orientation, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds);
 }
 
 void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LocalPointsDev& lp,
@@ -527,7 +600,26 @@ void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_sta
     if (lp.n <= 0) return;
     search_local_collect_kernel<<<(lp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
     resolve_kernel<<<1, 1024, 0, st>>>(1, lp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lp.obs_pos, nullptr, prm.nn_ratio,
-                                       0, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds);
+                                       0, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds);
+}
+
+void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q_feat, const int* q_cbeg, const int* q_cend,
+                       const uint8_t* kf_desc, const uint8_t* f_desc, const float* q_angle, const float* f_angle, const int* f_node_feat,
+                       float nn_ratio, int keep_max, int check_orientation, const uint8_t* obs_pos, MatchScratch s, uint8_t* state, int* match,
+                       int* n_matches) {
+    if (n_q <= 0) return;
+    bow_collect_kernel<<<(n_q + 7) / 8, 256, 0, st>>>(n_q, q_feat, q_cbeg, q_cend, kf_desc, f_desc, f_node_feat, keep_max, s.lists, s.list_cap,
+                                                    s.list_n, s.overflow);
+    resolve_kernel<<<1, 1024, 0, st>>>(2, n_q, nullptr, f, f_node_feat, s.lists, s.list_cap, s.list_n, obs_pos, q_angle, nn_ratio,
+                                       check_orientation, 50 /* TH_LOW */, f_angle, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds);
+}
+
+void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const RelocPointsDev& rp,
+                         const SearchRelocParams& prm, const uint8_t* obs_pos, MatchScratch s, uint8_t* state, int* match, int* n_matches) {
+    if (rp.n <= 0) return;
+    search_reloc_collect_kernel<<<(rp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, rp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
+    resolve_kernel<<<1, 1024, 0, st>>>(0, rp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, obs_pos, rp.angle, 0.f,
+                                       prm.check_orientation, prm.orb_dist, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds);
 }
 
 void launch_chain_prep(cudaStream_t st, const rgbl_keypoint* kps, const float* depth, const int* n_ptr, const float* last_pose,

@@ -86,6 +86,8 @@ struct LocalPointsDev {              // vpMapPoints with the mTrack* fields isIn
 };
 struct SearchLastParams { float cur_pose[7]; float th; int forward, backward, check_orientation; const float* cur_pose_dev; const int* flags_dev; };
 struct SearchLocalParams { float th, nn_ratio, th_far; int use_factor, far_points, keep_max; };
+struct RelocPointsDev { int n; const uint8_t* valid; const float* xw; const uint8_t* desc; const float* angle; const float *mf_min, *mf_max; };
+struct SearchRelocParams { float cur_pose[7]; float Ow[3]; float th; int orb_dist, check_orientation; };
 struct FrustumParams { float Rcw[9], tcw[3], Ow[3], cos_limit; };
 struct MatchScratch { uint32_t* lists; int list_cap; int* list_n; int* minq; int* choice; uint8_t* resolved; int* overflow; int* rounds; };
 
@@ -94,6 +96,12 @@ void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_star
                         const SearchLastParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches);
 void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LocalPointsDev& lp,
                          const SearchLocalParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches);
+void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q_feat, const int* q_cbeg, const int* q_cend,
+                       const uint8_t* kf_desc, const uint8_t* f_desc, const float* q_angle, const float* f_angle, const int* f_node_feat,
+                       float nn_ratio, int keep_max, int check_orientation, const uint8_t* obs_pos, MatchScratch s, uint8_t* state, int* match,
+                       int* n_matches);
+void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const RelocPointsDev& rp,
+                         const SearchRelocParams& prm, const uint8_t* obs_pos, MatchScratch s, uint8_t* state, int* match, int* n_matches);
 void launch_chain_prep(cudaStream_t st, const rgbl_keypoint* kps, const float* depth, const int* n_ptr, const float* last_pose,
                        const float* cur_pose, const FrameDev& f, int mono, int cap, uint8_t* valid, float* xw, int* octave, float* angle,
                        uint8_t* obs_pos, int* flags);

@@ -273,6 +273,32 @@ class ORBmatcher:
         return nm.value, match
 
 
+    def SearchByBoW(self, kf_desc, kf_angle, kf_valid, kf_csr, f_desc, f_angle, f_csr):
+        """SearchByBoW(pKF, F, vpMapPointMatches); csr = (node_ids ascending, node_start[n+1], node_feat) -> (nmatches, match[n_f])"""
+        kf_desc = np.ascontiguousarray(kf_desc, np.uint8); f_desc = np.ascontiguousarray(f_desc, np.uint8)
+        kf_angle = np.ascontiguousarray(kf_angle, np.float32); f_angle = np.ascontiguousarray(f_angle, np.float32)
+        kf_valid = np.ascontiguousarray(kf_valid, np.uint8)
+        ki, ks, kfe = (np.ascontiguousarray(kf_csr[0], np.uint32), np.ascontiguousarray(kf_csr[1], np.int32), np.ascontiguousarray(kf_csr[2], np.int32))
+        fi, fs, ffe = (np.ascontiguousarray(f_csr[0], np.uint32), np.ascontiguousarray(f_csr[1], np.int32), np.ascontiguousarray(f_csr[2], np.int32))
+        match = np.empty(len(f_desc), np.int32); nm = C.c_int(0)
+        check(lib().rgbl_search_by_bow(self.ctx.handle, len(kf_desc), ptr(kf_desc), ptr(kf_angle), ptr(kf_valid), len(ki), ptr(ki), ptr(ks), ptr(kfe),
+                                       len(f_desc), ptr(f_desc), ptr(f_angle), len(fi), ptr(fi), ptr(fs), ptr(ffe), self.mfNNratio,
+                                       int(self.mbCheckOrientation), ptr(match), C.byref(nm)), self.ctx.handle)
+        return nm.value, match
+
+    def SearchByProjectionReloc(self, cur: FrameView, cur_pose, valid, xw, mp_desc, kf_angle, mf_min, mf_max, th, ORBdist, cur_occupied=None):
+        """SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) -> (nmatches, match[cur.n])"""
+        cur_pose = np.ascontiguousarray(cur_pose, np.float32); valid = np.ascontiguousarray(valid, np.uint8)
+        xw = np.ascontiguousarray(xw, np.float32); mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        kf_angle = np.ascontiguousarray(kf_angle, np.float32); mn = np.ascontiguousarray(mf_min, np.float32); mx = np.ascontiguousarray(mf_max, np.float32)
+        occ = None if cur_occupied is None else np.ascontiguousarray(cur_occupied, np.uint8)
+        match = np.empty(cur.n, np.int32); nm = C.c_int(0)
+        check(lib().rgbl_search_by_projection_reloc(self.ctx.handle, C.byref(cur.c), ptr(cur_pose), len(valid), ptr(valid), ptr(xw), ptr(mp_desc),
+                                                    ptr(kf_angle), ptr(mn), ptr(mx), th, int(ORBdist), int(self.mbCheckOrientation),
+                                                    None if occ is None else ptr(occ), ptr(match), C.byref(nm)), self.ctx.handle)
+        return nm.value, match
+
+
 def is_in_frustum(ctx: Context, cur: FrameView, Rcw, tcw, Ow, xw, normal, mf_min_dist, mf_max_dist, cos_limit=0.5) -> dict:
     """Frame::isInFrustum over a list of map points -> dict of the mTrack* fields."""
     n = len(xw)

@@ -152,3 +152,33 @@ def test_resident_tracking_chain_matches_oracle_chain():
     for t in range(T):
         assert abs(poses[t, 4] - seq.pose(t)[4]) < 0.02 and np.abs(poses[t, :3]).max() < 2e-3
     assert (nm[1:] > 200).all() and (ni[1:] > 150).all()
+
+
+@pytest.mark.parametrize("ratio,bits,check", [(0.7, 6, True), (0.9, 4, True), (0.6, 7, False)])
+def test_search_by_bow(ctx, seq_frames, ratio, bits, check):
+    seq, frames, sf = seq_frames
+    kf, cur = frames[0], frames[1]
+    rng = np.random.default_rng(4)
+    kf_valid = (rng.random(len(kf["k"])) < 0.8).astype(np.uint8)
+    kcsr = TD.pseudo_feature_vector(kf["d"], bits); fcsr = TD.pseudo_feature_vector(cur["d"], bits)
+    rn, rmatch = oracle.search_by_bow(kf["d"], kf["k"]["angle"], kf_valid, kcsr, cur["d"], cur["k"]["angle"], fcsr, ratio, check)
+    n, match = F.ORBmatcher(ctx, ratio, check).SearchByBoW(kf["d"], kf["k"]["angle"], kf_valid, kcsr, cur["d"], cur["k"]["angle"], fcsr)
+    assert rn > 100
+    assert (match == rmatch).all(), f"{(match != rmatch).sum()} assignments differ"
+    assert n == rn
+
+
+def test_search_by_projection_reloc(ctx, seq_frames):
+    seq, frames, sf = seq_frames
+    rng = np.random.default_rng(12)
+    xw, desc, normal, mn, mx = TD.local_map([frames[0]], [seq.pose(0)], sf, rng)
+    ang = rng.uniform(0, 360, len(xw)).astype(np.float32)
+    cur = frames[1]
+    ofv = oracle.FrameView(*TD.frame_view_args(cur, sf)); gfv = F.FrameView(*TD.frame_view_args(cur, sf))
+    valid = (rng.random(len(xw)) < 0.9).astype(np.uint8)
+    for th, orb, occ_mode in ((10.0, 100, 0), (3.0, 64, 1)):
+        occ = None if occ_mode == 0 else (rng.random(len(cur["k"])) < 0.3).astype(np.uint8)
+        rn, rmatch = oracle.search_by_projection_reloc(ofv, seq.pose(1), valid, xw, desc, ang, mn, mx, th, orb, True, occ)
+        n, match = F.ORBmatcher(ctx, 0.9, True).SearchByProjectionReloc(gfv, seq.pose(1), valid, xw, desc, ang, mn, mx, th, orb, occ)
+        assert rn > 50
+        assert (match == rmatch).all() and n == rn

@@ -124,3 +124,15 @@ def oracle_chain(frames, sf, pose0, th=15.0):
         ni, pose, _ = oracle.pose_optimize(lp, xw[match[m]], obs, inv_s2, st, *CAM)
         poses.append(pose); nms.append(nm); nis.append(ni)
     return np.stack(poses), np.array(nms), np.array(nis)
+
+
+def pseudo_feature_vector(desc, n_bits=6):
+    """Stand-in for DBoW2's FeatureVector (node -> feature indices): node id = a few stable descriptor bits.  Returns the
+    CSR triple (ascending node ids, node_start, feature indices in ascending feature order, like Frame::ComputeBoW)."""
+    node = (desc[:, 0].astype(np.uint32) >> (8 - n_bits)) * 7 + 3           # arbitrary non-contiguous ids
+    ids = np.unique(node)
+    start = [0]; feat = []
+    for n in ids:
+        idx = np.nonzero(node == n)[0]
+        feat.extend(idx.tolist()); start.append(len(feat))
+    return ids.astype(np.uint32), np.array(start, np.int32), np.array(feat, np.int32)

@@ -87,6 +87,7 @@ def _declare(L):
     L.orc_depth_inverse_dilation.argtypes = [vp, i, i, f, f, vp, i, i, vp]
     L.orc_depth_average_filter.argtypes = [vp, i, i, i, vp]
     L.orc_depth_gather.argtypes = [vp, i, vp, vp, i, f, vp, vp]
+    L.orc_depth_nearest_neighbor_pixel.argtypes = [vp, i, i, vp, vp, i, f, f, vp, vp]
     L.orc_depth_from_pcd.argtypes = [vp, i, vp, i, i, f, f, vp, i, i, f, vp, vp, i, vp, vp, vp, vp]
     for name, (args, res) in _LATE.items():
         if hasattr(L, name):
@@ -221,6 +222,14 @@ def depth_average_filter(raw: np.ndarray, k: int) -> np.ndarray:
     out = np.empty_like(raw)
     lib().orc_depth_average_filter(_p(raw), raw.shape[1], raw.shape[0], k, _p(out))
     return out
+
+
+def depth_nearest_neighbor_pixel(raw: np.ndarray, kps, kps_un, bf: float, R: float = 7.0):
+    raw = np.ascontiguousarray(raw, np.float32)
+    kps = np.ascontiguousarray(kps, KP_DTYPE); kps_un = np.ascontiguousarray(kps_un, KP_DTYPE)
+    d = np.empty(len(kps), np.float32); u = np.empty(len(kps), np.float32)
+    lib().orc_depth_nearest_neighbor_pixel(_p(raw), raw.shape[1], raw.shape[0], _p(kps), _p(kps_un), len(kps), bf, R, _p(d), _p(u))
+    return d, u
 
 
 def depth_gather(dmap: np.ndarray, kps: np.ndarray, kps_un: np.ndarray, bf: float):

@@ -334,23 +334,59 @@ static void run_depth_maps(Ctx* c, const DepthDev& dd, int n_frames, int max_pts
     launch_depth_project(st, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, max_pts, dd, W, H, c->d_idx_map, c->stamp, n_frames);
     stage_end(c, ST_DEPTH_PROJECT, st, max_pts > 0 ? 1 : 0);
     stage_begin(c, ST_DEPTH_DILATE, st);
-    launch_depth_resolve_dilate(st, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, dd, W, H, c->d_idx_map, c->stamp, raw, c->d_processed, n_frames);
-    stage_end(c, ST_DEPTH_DILATE, st, 1);
+    const bool need_raw = dd.method == RGBL_DEPTH_AVERAGE_FILTERING || dd.method == RGBL_DEPTH_NEAREST_NEIGHBOR_PIXEL;
+    float* raw_out = need_raw ? c->d_raw : raw;
+    launch_depth_resolve_dilate(st, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, dd, W, H, c->d_idx_map, c->stamp, raw_out, c->d_processed, n_frames);
+    int launches = 1;
+    if (dd.method == RGBL_DEPTH_AVERAGE_FILTERING) { launch_depth_average_filter(st, c->d_raw, W, H, dd.avg_kernel, c->d_processed, n_frames); ++launches; }
+    stage_end(c, ST_DEPTH_DILATE, st, launches);
+}
+
+// GetFeatureDepthFromDepthMap / the per-keypoint part of Upsample_NearestNeighbor_Pixel
+static void run_depth_keypoints(Ctx* c, const DepthDev& dd, const rgbl_keypoint* kps, const rgbl_keypoint* kps_un, const int* n_kp, int max_n,
+                                int n_frames, cudaStream_t st) {
+    const int W = c->cfg.width, H = c->cfg.height;
+    stage_begin(c, ST_DEPTH_GATHER, st);
+    if (dd.method == RGBL_DEPTH_NEAREST_NEIGHBOR_PIXEL)
+        launch_depth_nn_pixel(st, c->d_raw, W, H, kps, kps_un, n_kp, c->cap_kp, max_n, dd.bf, dd.nn_radius, c->d_depth, c->d_uright, n_frames);
+    else
+        launch_depth_gather(st, c->d_processed, W, H, kps, kps_un, n_kp, c->cap_kp, max_n, dd.method == RGBL_DEPTH_NONE ? -1.f : dd.bf,
+                            c->d_depth, c->d_uright, n_frames);
+    stage_end(c, ST_DEPTH_GATHER, st, max_n > 0 ? 1 : 0);
 }
 
 static int setup_depth(Ctx* c, const float P[12], const rgbl_depth_params* prm, DepthDev& dd) {
     if (!c->d_pts) { c->err = "context was created with max_points == 0"; return RGBL_E_INVALID; }
-    if (prm->method != RGBL_DEPTH_INVERSE_DILATION) { c->err = "only LiDAR.Method InverseDilation is implemented on the device"; return RGBL_E_UNSUPPORTED; }
-    if (prm->ku < 1 || prm->kv < 1 || prm->ku > 9 || prm->kv > 9) { c->err = "structuring element must be 1..9"; return RGBL_E_INVALID; }
     std::memcpy(dd.P, P, sizeof(float) * 12);
     dd.min_dist = prm->min_dist; dd.max_dist = prm->max_dist; dd.bf = prm->bf;
     dd.inv_scale_m = prm->max_dist * prm->inv_dilation_scale;
-    dd.ku = prm->ku; dd.kv = prm->kv;
-    std::memcpy(dd.mask, prm->mask, 81);
+    dd.method = prm->method; dd.avg_kernel = prm->avg_kernel; dd.nn_radius = prm->nn_search_radius;
+    switch (prm->method) {
+        case RGBL_DEPTH_INVERSE_DILATION:
+            if (prm->ku < 1 || prm->kv < 1 || prm->ku > 9 || prm->kv > 9) { c->err = "structuring element must be 1..9"; return RGBL_E_INVALID; }
+            dd.ku = prm->ku; dd.kv = prm->kv;
+            std::memcpy(dd.mask, prm->mask, 81);
+            break;
+        case RGBL_DEPTH_AVERAGE_FILTERING:
+            if (prm->avg_kernel < 1 || prm->avg_kernel > 9) { c->err = "AverageFiltering kernel size must be 1..9"; return RGBL_E_INVALID; }
+            dd.ku = dd.kv = 1; std::memset(dd.mask, 0, 81); dd.mask[0] = 1;          // resolve only: Raw is the filter input
+            break;
+        case RGBL_DEPTH_NEAREST_NEIGHBOR_PIXEL:
+            if (!(prm->nn_search_radius >= 1.f) || prm->nn_search_radius > 30.f) { c->err = "NearestNeighborPixel search distance must be 1..30"; return RGBL_E_INVALID; }
+            dd.ku = dd.kv = 1; std::memset(dd.mask, 0, 81); dd.mask[0] = 1;
+            break;
+        case RGBL_DEPTH_NONE:
+            dd.ku = dd.kv = 1; std::memset(dd.mask, 0, 81); dd.mask[0] = 1;
+            break;
+        default:
+            c->err = "LiDAR.Method not implemented (IPBasic has no definition in the reference either, src/DepthModule.cc:62-77)";
+            return RGBL_E_UNSUPPORTED;
+    }
     if (++c->stamp >= 1023u) {
-        // stamp wrap: clear the index map once every 1022 calls
-        if (cudaMemsetAsync(c->d_idx_map, 0, (size_t)c->cfg.max_batch * c->cfg.width * c->cfg.height * sizeof(uint32_t), c->st) != cudaSuccess) {
-            c->err = "cudaMemsetAsync(idx_map) failed"; return RGBL_E_CUDA;
+        // stamp wrap: clear the index map once every 1022 calls (both streams idle first)
+        cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st_aux);
+        if (cudaMemset(c->d_idx_map, 0, (size_t)c->cfg.max_batch * c->cfg.width * c->cfg.height * sizeof(uint32_t)) != cudaSuccess) {
+            c->err = "cudaMemset(idx_map) failed"; return RGBL_E_CUDA;
         }
         c->stamp = 1;
     }
@@ -540,10 +576,7 @@ int rgbl_depth_from_pcd(rgbl_ctx* ctx, const float* pts4xn, int n_pts, const flo
         CU(cudaMemcpyAsync(c->d_kps_un, kps_un, (size_t)n_kp * sizeof(rgbl_keypoint), cudaMemcpyHostToDevice, c->st));
     }
     run_depth_maps(c, dd, 1, n_pts, c->d_raw, c->st);
-    stage_begin(c, ST_DEPTH_GATHER, c->st);
-    launch_depth_gather(c->st, c->d_processed, width, height, c->d_kps_in, c->d_kps_un, c->d_n_kp_in, c->cap_kp, n_kp, dd.bf,
-                        c->d_depth, c->d_uright, 1);
-    stage_end(c, ST_DEPTH_GATHER, c->st, n_kp > 0 ? 1 : 0);
+    run_depth_keypoints(c, dd, c->d_kps_in, c->d_kps_un, c->d_n_kp_in, n_kp, 1, c->st);
     CU(cudaGetLastError());
     if (n_kp) {
         CU(cudaMemcpyAsync(depth, c->d_depth, (size_t)n_kp * sizeof(float), cudaMemcpyDeviceToHost, c->st));
@@ -593,10 +626,7 @@ static int process_rgbl(Ctx* c, int n_frames, int max_pts, const float P[12], co
     // depth maps run on the aux stream behind the blur, overlapping the host quad-tree; describe waits for both
     int max_n = run_extract(c, n_frames, [&]() { run_depth_maps(c, dd, n_frames, max_pts, nullptr, c->st_aux); });
     if (max_n < 0) return max_n;
-    stage_begin(c, ST_DEPTH_GATHER, c->st);
-    launch_depth_gather(c->st, c->d_processed, c->cfg.width, c->cfg.height, c->d_kps, c->d_kps, c->d_n_sel, c->cap_kp, max_n, dd.bf,
-                        c->d_depth, c->d_uright, n_frames);
-    stage_end(c, ST_DEPTH_GATHER, c->st, max_n > 0 ? 1 : 0);
+    run_depth_keypoints(c, dd, c->d_kps, c->d_kps, c->d_n_sel, max_n, n_frames, c->st);
     CU(cudaGetLastError());
     return max_n;
 }

@@ -52,12 +52,17 @@ struct DepthDev {
     float min_dist, max_dist, bf, inv_scale_m;   // inv_scale_m = max_dist * ScaleFactor (the inversion constant M)
     int ku, kv;
     uint8_t mask[81];
+    int method, avg_kernel;          // rgbl_depth_method, AverageFiltering kernel size
+    float nn_radius;                 // NearestNeighborPixel SearchDistance
 };
 void launch_depth_project(cudaStream_t st, const float* pts, int pts_stride, const int* n_pts, int max_n_pts,
                           const DepthDev& prm, int W, int H, uint32_t* idx_map, uint32_t stamp, int n_frames);
 void launch_depth_resolve_dilate(cudaStream_t st, const float* pts, int pts_stride, const int* n_pts,
                                  const DepthDev& prm, int W, int H, const uint32_t* idx_map, uint32_t stamp,
                                  float* raw, float* processed, int n_frames);
+void launch_depth_average_filter(cudaStream_t st, const float* raw, int W, int H, int k, float* processed, int n_frames);
+void launch_depth_nn_pixel(cudaStream_t st, const float* raw, int W, int H, const rgbl_keypoint* kps, const rgbl_keypoint* kps_un,
+                           const int* n_kp, int cap, int max_n, float bf, float R, float* depth, float* uright, int n_frames);
 void launch_depth_gather(cudaStream_t st, const float* processed, int W, int H, const rgbl_keypoint* kps,
                          const rgbl_keypoint* kps_un, const int* n_kp, int cap, int max_n, float bf, float* depth,
                          float* uright, int n_frames);

@@ -71,3 +71,40 @@ def test_frame_rgbl_batch(ctx):
         assert len(k) == len(rk) and all((k[f] == rk[f]).all() for f in k.dtype.names) and (d == rd).all()
         rdep, rur, _, _ = oracle.depth_from_pcd(pc, P, S.KITTI_W, S.KITTI_H, mask, S.KITTI_BF, rk, rk)
         assert (dep == rdep).all() and (ur == rur).all()
+
+
+@pytest.mark.parametrize("k", [5, 3, 7])
+def test_average_filtering(ctx, k):
+    """LiDAR.Method AverageFiltering (src/DepthModule.cc:200-228): bit-exact incl. the NaN pattern of empty windows."""
+    pts = S.make_pointcloud(6); P = S.lidar_projection_matrix(); kp = _kps(7)
+    dm = F.DepthModule(ctx, P, S.KITTI_BF, "AverageFiltering", avg_kernel=k)
+    dm.CalculateDepthFromPcd(kp, kp, pts, S.KITTI_W, S.KITTI_H)
+    raw = oracle.depth_project(pts, P, S.KITTI_W, S.KITTI_H)
+    with np.errstate(all="ignore"):
+        proc = oracle.depth_average_filter(raw, k)
+    d, u = oracle.depth_gather(proc, kp, kp, S.KITTI_BF)
+    assert (dm.RawDepthMap == raw).all()
+    assert (np.isnan(dm.ProcessedDepthMap) == np.isnan(proc)).all()
+    m = ~np.isnan(proc)
+    assert (dm.ProcessedDepthMap[m] == proc[m]).all()
+    assert (dm.mvDepth == d).all() and (dm.mvuRight == u).all() and (d > 0).sum() > 100
+
+
+@pytest.mark.parametrize("R", [7.0, 3.0, 12.0])
+def test_nearest_neighbor_pixel(ctx, R):
+    """LiDAR.Method NearestNeighborPixel (src/DepthModule.cc:145-198), incl. the fixed-point chamfer distance transform."""
+    pts = S.make_pointcloud(8); P = S.lidar_projection_matrix(); kp = _kps(9, 1800)
+    dm = F.DepthModule(ctx, P, S.KITTI_BF, "NearestNeighborPixel", nn_radius=R)
+    dm.CalculateDepthFromPcd(kp, kp, pts, S.KITTI_W, S.KITTI_H)
+    raw = oracle.depth_project(pts, P, S.KITTI_W, S.KITTI_H)
+    d, u = oracle.depth_nearest_neighbor_pixel(raw, kp, kp, S.KITTI_BF, R)
+    assert (dm.mvDepth == d).all() and (dm.mvuRight == u).all()
+    assert (d > 0).sum() > 200
+
+
+def test_method_none_projects_only(ctx):
+    pts = S.make_pointcloud(8); P = S.lidar_projection_matrix(); kp = _kps(9, 100)
+    dm = F.DepthModule(ctx, P, S.KITTI_BF, "None")
+    dm.CalculateDepthFromPcd(kp, kp, pts, S.KITTI_W, S.KITTI_H)
+    assert (dm.RawDepthMap == oracle.depth_project(pts, P, S.KITTI_W, S.KITTI_H)).all()
+    assert (dm.mvDepth == -1).all()

@@ -122,3 +122,38 @@ def test_glibc_sincos_is_what_the_descriptor_sees():
         d1 = R.descriptor_np(blur, 100, 100, 37.25, R.load_pattern())
         assert (d0 == d1).all()
     assert d0.shape == (32,)
+
+
+@needs_cv2
+def test_other_upsamplers_live():
+    """AverageFiltering (filter2D with FMA accumulation) and NearestNeighborPixel (fixed-point chamfer distanceTransform)."""
+    pts = S.make_pointcloud(3); P = S.lidar_projection_matrix()
+    raw = oracle.depth_project(pts, P, S.KITTI_W, S.KITTI_H)
+    for k in (3, 5):
+        a = oracle.depth_average_filter(raw, k)
+        F = _cv2.filter2D(raw, -1, np.ones((k, k), np.float32) / (k * k), anchor=(-1, -1), delta=0, borderType=_cv2.BORDER_DEFAULT)
+        _, B = _cv2.threshold(raw, 0, 1, 0)
+        Cn = _cv2.filter2D(B, -1, np.ones((k, k), np.uint16), anchor=(-1, -1), delta=0, borderType=_cv2.BORDER_DEFAULT)
+        with np.errstate(all="ignore"):
+            ref = _cv2.multiply(F, _cv2.divide(float(k * k), Cn))
+        m = ~(np.isnan(a) & np.isnan(ref))
+        assert (np.isnan(a) == np.isnan(ref)).all() and (a[m] == ref[m]).all()
+    R = 7
+    rng = np.random.default_rng(0); n = 800
+    k = np.zeros(n, oracle.KP_DTYPE); k["x"] = rng.uniform(19, S.KITTI_W - 19, n).astype(np.float32); k["y"] = rng.uniform(19, S.KITTI_H - 19, n).astype(np.float32)
+    pad = _cv2.copyMakeBorder(raw, R, R, R, R, _cv2.BORDER_CONSTANT, value=0)
+    D8 = np.clip(np.rint(raw), 0, 255).astype(np.uint8)
+    _, DM = _cv2.threshold(D8, 0, 1, _cv2.THRESH_BINARY_INV)
+    dist, _ = _cv2.distanceTransformWithLabels(DM, _cv2.DIST_L2, 5)
+    dref = np.full(n, -1, np.float32)
+    for i in range(n):
+        u, v = k["x"][i], k["y"][i]
+        sr = int(dist[int(v), int(u)]); d = 0.0
+        if 0 <= sr < R:
+            sr += 1
+            x0 = int(np.float32(u) + np.float32(R) - np.float32(sr)); y0 = int(np.float32(v) + np.float32(R) - np.float32(sr))
+            d = float(pad[y0:y0 + 2 * sr, x0:x0 + 2 * sr].max())
+        if d > 0:
+            dref[i] = d
+    d, _u = oracle.depth_nearest_neighbor_pixel(raw, k, k, 100.0, float(R))
+    assert (d == dref).all()

@@ -178,6 +178,11 @@ int rgbl_search_by_projection_local(rgbl_ctx* ctx, const rgbl_frame_view* cur, i
                                     const float* view_cos, const uint8_t* mp_desc, const uint8_t* obs_pos, float th, float nn_ratio,
                                     int far_points, float th_far, const uint8_t* cur_state, int32_t* match, int* n_matches);
 
+/* Frame::ComputeStereoMatches (src/Frame.cc:901-1071) between two frame slots of the last batched extraction (the left and
+ * right image of a rectified stereo pair extracted as one batch: the reference runs its two ORBextractors on two threads,
+ * src/Frame.cc:122-125).  mb = mbf / fx, mbf = Camera.bf.  depth / uright [n_left] = mvDepth / mvuRight of the left frame. */
+int rgbl_stereo_matches(rgbl_ctx* ctx, int slot_left, int slot_right, float mb, float mbf, float* depth, float* uright, int cap);
+
 /* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (include/ORBmatcher.h:65,
  * src/ORBmatcher.cc:223-425), Nleft == -1.  pKF->mFeatVec and F.mFeatVec (DBoW2::FeatureVector = std::map<NodeId,
  * vector<unsigned>>) are passed as CSR: ascending node ids, node_start[n_nodes+1], feature indices in vector order.

@@ -300,6 +300,7 @@ def _late(L):
     L.orc_search_by_bow.restype = i
     L.orc_search_by_projection_reloc.argtypes = [fv, vp, i, vp, vp, vp, vp, vp, vp, f, i, i, vp, vp]
     L.orc_search_by_projection_reloc.restype = i
+    L.orc_stereo_matches.argtypes = [i, vp, vp, i, vp, vp, i, vp, vp, vp, vp, vp, vp, f, f, vp, vp]
     L.orc_pose_optimize.argtypes = [vp, i, vp, vp, vp, vp, f, f, f, f, f, vp, vp]
     L.orc_pose_optimize.restype = i
     _LATE_DECL_DONE = True
@@ -399,3 +400,18 @@ def search_by_projection_reloc(cur: FrameView, cur_pose, valid, xw, mp_desc, kf_
     nm = lib().orc_search_by_projection_reloc(C.byref(cur.c), _p(cur_pose), len(valid), _p(valid), _p(xw), _p(mp_desc), _p(kf_angle), _p(mn), _p(mx),
                                               th, int(orb_dist), int(check_orientation), _p(occ), _p(match))
     return nm, match
+
+
+def stereo_matches(kps_l, desc_l, kps_r, desc_r, ex_l: "Extractor", ex_r: "Extractor", mb: float, mbf: float):
+    """Frame::ComputeStereoMatches on the pyramids held by two oracle extractors (after they extracted left / right)."""
+    _late(lib())
+    kps_l = np.ascontiguousarray(kps_l, KP_DTYPE); kps_r = np.ascontiguousarray(kps_r, KP_DTYPE)
+    desc_l = np.ascontiguousarray(desc_l, np.uint8); desc_r = np.ascontiguousarray(desc_r, np.uint8)
+    nl = ex_l.nlevels
+    ll = [ex_l.level_image(l) for l in range(nl)]; lr = [ex_r.level_image(l) for l in range(nl)]
+    pl = (C.c_void_p * nl)(*[a.ctypes.data for a in ll]); pr = (C.c_void_p * nl)(*[a.ctypes.data for a in lr])
+    lw = np.array([a.shape[1] for a in ll], np.int32); lh = np.array([a.shape[0] for a in ll], np.int32)
+    d = np.empty(len(kps_l), np.float32); u = np.empty(len(kps_l), np.float32)
+    lib().orc_stereo_matches(len(kps_l), _p(kps_l), _p(desc_l), len(kps_r), _p(kps_r), _p(desc_r), nl, _p(ex_l.scale_factors),
+                             _p(ex_l.inv_scale_factors), pl, pr, _p(lw), _p(lh), mb, mbf, _p(d), _p(u))
+    return d, u

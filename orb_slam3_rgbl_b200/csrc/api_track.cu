@@ -268,6 +268,38 @@ int rgbl_pose_optimize(rgbl_ctx* ctx, const float pose_in[7], int n, const float
 }
 
 
+int rgbl_stereo_matches(rgbl_ctx* ctx, int slot_left, int slot_right, float mb, float mbf, float* depth, float* uright, int cap) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!depth || !uright) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (slot_left < 0 || slot_right < 0 || slot_left >= c->last_frames || slot_right >= c->last_frames) { c->err = "frame slot out of range (extract the stereo pair as one batch first)"; return RGBL_E_INVALID; }
+    if (c->cap_kp > 65535) { c->err = "more than 65535 keypoints per frame"; return RGBL_E_UNSUPPORTED; }
+    CU(cudaSetDevice(c->cfg.device));
+    TrackBufs& t = c->trk;
+    GROW(t.e_idx, t.cap_e_idx, c->cap_kp);
+    StereoFrameDev L{}, R{};
+    L.n = c->d_n_sel + slot_left; L.keys = c->d_kps + (size_t)slot_left * c->cap_kp; L.desc = c->d_desc + (size_t)slot_left * c->cap_kp * 32;
+    R.n = c->d_n_sel + slot_right; R.keys = c->d_kps + (size_t)slot_right * c->cap_kp; R.desc = c->d_desc + (size_t)slot_right * c->cap_kp * 32;
+    for (int l = 0; l < c->tab.nlevels; ++l) { L.scale[l] = R.scale[l] = c->tab.scale[l]; L.inv_scale[l] = R.inv_scale[l] = c->tab.inv_scale[l]; }
+    float* d_depth = c->d_depth + (size_t)slot_left * c->cap_kp;
+    float* d_ur = c->d_uright + (size_t)slot_left * c->cap_kp;
+    stage_begin(c, ST_MATCH, c->st);
+    launch_stereo_matches(c->st, c->d_pyr, c->frame_bytes, slot_left, slot_right, c->d_levels, L, R, mb, mbf, c->cfg.height, c->cap_kp, d_depth, d_ur, t.e_idx);
+    stage_end(c, ST_MATCH, c->st, 2);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_scalars, L.n, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    const int n = c->h_scalars[0];
+    if (n > cap) { c->err = "output capacity too small"; return RGBL_E_CAPACITY; }
+    if (n) {
+        CU(cudaMemcpyAsync(depth, d_depth, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(uright, d_ur, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    }
+    CU(cudaStreamSynchronize(c->st));
+    prof_collect(c);
+    return RGBL_OK;
+}
+
 int rgbl_search_by_bow(rgbl_ctx* ctx, int n_kf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid,
                        int n_nodes_kf, const uint32_t* kf_node_ids, const int32_t* kf_node_start, const int32_t* kf_node_feat,
                        int n_f, const uint8_t* f_desc, const float* f_angle,

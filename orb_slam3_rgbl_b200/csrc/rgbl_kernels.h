@@ -116,6 +116,12 @@ void launch_frustum(cudaStream_t st, const FrameDev& f, const FrustumParams& prm
                     const float* mf_min, const float* mf_max, uint8_t* in_view, float* px, float* py, float* pxr, float* depth,
                     int* level, float* view_cos);
 
+// stereo_kernels.cu --------------------------------------------------------------------------------
+struct StereoFrameDev { const int* n; const rgbl_keypoint* keys; const uint8_t* desc; float scale[RGBL_MAX_LEVELS], inv_scale[RGBL_MAX_LEVELS]; };
+void launch_stereo_matches(cudaStream_t st, const uint8_t* pyr, size_t frame_stride, int slot_l, int slot_r, const LevelGeom* d_levels,
+                           const StereoFrameDev& L, const StereoFrameDev& R, float mb, float mbf, int n_rows, int cap, float* depth,
+                           float* uright, int* sad);
+
 // pose_kernels.cu ----------------------------------------------------------------------------------
 struct PoseProblemDev {
     int n;                           // edges (keypoint order)

@@ -152,6 +152,16 @@ class ORBextractor:
         return out[:n.value].copy()
 
 
+def compute_stereo_matches(extractor: "ORBextractor", images_lr, mb: float, mbf: float):
+    """Stereo Frame construction (src/Frame.cc:101-197): both images extracted as one batch, then Frame::ComputeStereoMatches.
+    -> ((kps_l, desc_l), (kps_r, desc_r), mvDepth, mvuRight)"""
+    (kl, dl), (kr, dr) = extractor.extract_batch(list(images_lr))
+    cap = extractor.ctx.cap
+    depth = np.empty(cap, np.float32); ur = np.empty(cap, np.float32)
+    check(lib().rgbl_stereo_matches(extractor.ctx.handle, 0, 1, mb, mbf, ptr(depth), ptr(ur), cap), extractor.ctx.handle)
+    return (kl, dl), (kr, dr), depth[:len(kl)].copy(), ur[:len(kl)].copy()
+
+
 def structuring_element(kind: str, ku: int, kv: int | None = None) -> np.ndarray:
     kv = ku if kv is None else kv
     m = np.zeros((kv, ku), np.uint8)

@@ -120,3 +120,22 @@ def test_low_texture_uses_min_threshold():
     rk, rd, _ = oracle.Extractor(1000)(img)
     _cmp_kps(k, rk)
     assert (d == rd).all()
+
+
+def test_compute_stereo_matches():
+    """Frame::ComputeStereoMatches on a synthetic rectified pair (uniform 5 px disparity): bit-exact mvDepth / mvuRight."""
+    tex = S.make_image(77, S.KITTI_W + 40, S.KITTI_H)
+    left = np.ascontiguousarray(tex[:, 10:10 + S.KITTI_W]); right = np.ascontiguousarray(tex[:, 15:15 + S.KITTI_W])
+    el, er = oracle.Extractor(2000), oracle.Extractor(2000)
+    kl, dl, _ = el(left); kr, dr, _ = er(right)
+    mb = np.float32(S.KITTI_BF) / np.float32(S.KITTI_FX); mbf = np.float32(S.KITTI_BF)
+    rd, ru = oracle.stereo_matches(kl, dl, kr, dr, el, er, mb, mbf)
+    ex = F.ORBextractor(2000, 1.2, 8, 12, 7, S.KITTI_W, S.KITTI_H, max_batch=2)
+    try:
+        (gkl, gdl), (gkr, gdr), gd, gu = F.compute_stereo_matches(ex, (left, right), float(mb), float(mbf))
+    finally:
+        ex.ctx.close()
+    _cmp_kps(gkl, kl); _cmp_kps(gkr, kr)
+    assert (gd == rd).all() and (gu == ru).all(), f"{(gd != rd).sum()} depths differ"
+    ok = rd > 0
+    assert ok.sum() > 800 and abs(np.median(kl["x"][ok] - ru[ok]) - 5.0) < 0.05

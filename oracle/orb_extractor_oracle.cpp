@@ -93,21 +93,27 @@ const int kGauss7[7] = {18, 34, 48, 56, 48, 34, 18};
 
 void gaussian_blur7_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride) {
     std::vector<uint16_t> hbuf((size_t)w * h);
+    std::vector<uint8_t> prow(w + 6);
     for (int y = 0; y < h; ++y) {
         const uint8_t* r = src + (size_t)y * sstride;
+        for (int k = 0; k < 3; ++k) { prow[k] = r[reflect101(k - 3, w)]; prow[w + 3 + k] = r[reflect101(w + k, w)]; }
+        memcpy(&prow[3], r, w);
+        uint16_t* ho = &hbuf[(size_t)y * w];
         for (int x = 0; x < w; ++x) {
-            unsigned acc = 0;
-            for (int k = 0; k < 7; ++k) acc += kGauss7[k] * r[reflect101(x + k - 3, w)];
-            hbuf[(size_t)y * w + x] = (uint16_t)acc;
+            const uint8_t* p = &prow[x];
+            ho[x] = (uint16_t)(kGauss7[0] * (p[0] + p[6]) + kGauss7[1] * (p[1] + p[5]) + kGauss7[2] * (p[2] + p[4]) + kGauss7[3] * p[3]);
         }
     }
-    for (int y = 0; y < h; ++y)
+    for (int y = 0; y < h; ++y) {
+        const uint16_t* rr[7];
+        for (int k = 0; k < 7; ++k) rr[k] = &hbuf[(size_t)reflect101(y + k - 3, h) * w];
+        uint8_t* o = dst + (size_t)y * dstride;
         for (int x = 0; x < w; ++x) {
-            uint32_t acc = 0;
-            for (int k = 0; k < 7; ++k)
-                acc += (uint32_t)kGauss7[k] * hbuf[(size_t)reflect101(y + k - 3, h) * w + x];
-            dst[(size_t)y * dstride + x] = (uint8_t)((acc + 32768u) >> 16);
+            const uint32_t acc = (uint32_t)kGauss7[0] * (rr[0][x] + rr[6][x]) + (uint32_t)kGauss7[1] * (rr[1][x] + rr[5][x]) +
+                                 (uint32_t)kGauss7[2] * (rr[2][x] + rr[4][x]) + (uint32_t)kGauss7[3] * rr[3][x];
+            o[x] = (uint8_t)((acc + 32768u) >> 16);
         }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

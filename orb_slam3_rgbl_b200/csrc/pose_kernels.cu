@@ -24,10 +24,14 @@ namespace {
 
 struct Se3d { double qx, qy, qz, qw, tx, ty, tz; };
 
+// SE3Quat::normalizeRotation (se3quat.h:280-285).  A product of unit quaternions has |q|^2 = 1 + d with |d| ~ 1e-16, where
+// 1/sqrt(1 + d) = 1 - d/2 to far below one ulp: one FMA instead of an rsqrt on the serial FP64 chain; anything farther
+// from unit norm (the caller's initial pose) takes the general path.
 __device__ __forceinline__ void normalize_rotation(Se3d& T) {
     if (T.qw < 0) { T.qx *= -1; T.qy *= -1; T.qz *= -1; T.qw *= -1; }
-    const double n = sqrt(T.qx * T.qx + T.qy * T.qy + T.qz * T.qz + T.qw * T.qw);
-    T.qx /= n; T.qy /= n; T.qz /= n; T.qw /= n;
+    const double n2 = T.qx * T.qx + T.qy * T.qy + T.qz * T.qz + T.qw * T.qw;
+    const double inv = (fabs(n2 - 1.0) < 1e-7) ? 1.5 - 0.5 * n2 : rsqrt(n2);
+    T.qx *= inv; T.qy *= inv; T.qz *= inv; T.qw *= inv;
 }
 
 __device__ __forceinline__ void quat_rotate(const Se3d& q, const double v[3], double out[3]) {
@@ -73,38 +77,53 @@ __device__ __forceinline__ void quat_from_matrix(const double R[3][3], Se3d& q) 
     }
 }
 
-__device__ __noinline__ void se3_exp(const double* u, Se3d& T) {
+// Taylor coefficients in th^2 (k = 0..8), generated from exact rationals: sin(th/2)/th, cos(th/2), (1-cos th)/th^2, (th-sin th)/th^3
+__device__ constexpr double kQs[9] = {0.5, -0.020833333333333332, 0.00026041666666666666, -1.5500992063492063e-06, 5.382288910934745e-09, -1.2232474797578965e-11, 1.9603324996120133e-14, -2.333729166204778e-17, 2.1449716601146855e-20};   // (-1)^k / (2 4^k (2k+1)!)
+__device__ constexpr double kQc[9] = {1.0, -0.125, 0.0026041666666666665, -2.170138888888889e-05, 9.68812003968254e-08, -2.691144455467372e-10, 5.096864498991235e-13, -7.001187498614334e-16, 7.292903644389931e-19};   // (-1)^k / (4^k (2k)!)
+__device__ constexpr double kB[9] = {0.5, -0.041666666666666664, 0.001388888888888889, -2.48015873015873e-05, 2.755731922398589e-07, -2.08767569878681e-09, 1.1470745597729725e-11, -4.779477332387385e-14, 1.5619206968586225e-16};   // (-1)^k / (2k+2)!
+__device__ constexpr double kC[9] = {0.16666666666666666, -0.008333333333333333, 0.0001984126984126984, -2.7557319223985893e-06, 2.505210838544172e-08, -1.6059043836821613e-10, 7.647163731819816e-13, -2.8114572543455206e-15, 8.22063524662433e-18};   // (-1)^k / (2k+3)!
+
+// SE3Quat::exp (Thirdparty/g2o/g2o/types/se3quat.h:214-254).  g2o builds R = I + a*Omega + b*Omega^2 with
+// a = sin(th)/th, b = (1-cos th)/th^2, c = (th - sin th)/th^3, V = I + b*Omega + c*Omega^2, converts R to a quaternion and
+// normalises.  The same rotation in closed form is q = (omega * sin(th/2)/th, cos(th/2)).  All four scalar functions are even
+// in th, i.e. power series in th^2: for th^2 < 0.25 (every LM step of a tracking problem) they are evaluated as degree-8
+// Horner polynomials in th^2 (truncation < 1e-20, and no th - sin th cancellation), which takes sqrt, sincos and three
+// divisions off the serial FP64 dependency chain; larger steps use sincos.  Equal to g2o's value up to rounding.
+__device__ __forceinline__ void se3_exp(const double* u, Se3d& T) {
     const double om[3] = {u[0], u[1], u[2]}, up[3] = {u[3], u[4], u[5]};
-    const double theta = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+    const double t = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
     const double O[3][3] = {{0, -om[2], om[1]}, {om[2], 0, -om[0]}, {-om[1], om[0], 0}};
-    double O2[3][3], R[3][3], V[3][3];
+    double O2[3][3], V[3][3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) O2[i][j] = O[i][0] * O[0][j] + O[i][1] * O[1][j] + O[i][2] * O[2][j];
-    if (theta < 0.00001) {
+    double qs, qc, b, c;
+    if (t < 0.25) {
+        qs = 0; qc = 0; b = 0; c = 0;
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) { R[i][j] = (i == j ? 1.0 : 0.0) + O[i][j] + O2[i][j]; V[i][j] = R[i][j]; }
+        for (int k = 8; k >= 0; --k) {
+            qs = qs * t + kQs[k]; qc = qc * t + kQc[k]; b = b * t + kB[k]; c = c * t + kC[k];
+        }
     } else {
-        const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / (theta * theta * theta);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                R[i][j] = (i == j ? 1.0 : 0.0) + a * O[i][j] + b * O2[i][j];
-                V[i][j] = (i == j ? 1.0 : 0.0) + b * O[i][j] + c * O2[i][j];
-            }
+        const double it = rsqrt(t), theta = t * it, it2 = it * it;
+        double sh, ch;
+        sincos(0.5 * theta, &sh, &ch);
+        qs = sh * it; qc = ch;
+        b = 2 * sh * sh * it2; c = (theta - 2 * sh * ch) * (it2 * it);
     }
-    quat_from_matrix(R, T);
+    T.qx = om[0] * qs; T.qy = om[1] * qs; T.qz = om[2] * qs; T.qw = qc;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) V[i][j] = (i == j ? 1.0 : 0.0) + b * O[i][j] + c * O2[i][j];
     T.tx = V[0][0] * up[0] + V[0][1] * up[1] + V[0][2] * up[2];
     T.ty = V[1][0] * up[0] + V[1][1] * up[1] + V[1][2] * up[2];
     T.tz = V[2][0] * up[0] + V[2][1] * up[1] + V[2][2] * up[2];
     normalize_rotation(T);
 }
 
-__device__ __noinline__ void se3_mul(const Se3d& a, const Se3d& b, Se3d& r) {
+__device__ __forceinline__ void se3_mul(const Se3d& a, const Se3d& b, Se3d& r) {
     const double bt[3] = {b.tx, b.ty, b.tz};
     double rt[3];
     quat_rotate(a, bt, rt);
@@ -116,107 +135,131 @@ __device__ __noinline__ void se3_mul(const Se3d& a, const Se3d& b, Se3d& r) {
     normalize_rotation(r);
 }
 
-// 6x6 LDL^T with diagonal pivoting (what Eigen::LDLT does), positive-semidefinite check.  Unrolled with branch-free
-// (select-based) row/column swaps so that every array index is a compile-time constant and the matrix lives in
-// registers; __noinline__ keeps one copy of it in the kernel (an earlier inlined, branchy version made ptxas emit
-// 180k instructions and the single-CTA kernel became instruction-fetch bound).
-__device__ __noinline__ bool solve6(const double* Hsym /*21 upper*/, double lambda, const double* b, double* x) {
-    double A[6][6], y[6];
-    int pivs[6];
-    {
-        int t = 0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int j = i; j < 6; ++j) { A[i][j] = Hsym[t]; A[j][i] = Hsym[t]; ++t; }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { A[i][i] += lambda; y[i] = b[i]; }
-    }
-    bool positive = true, stop = false;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        int piv = k;
-        double best = fabs(A[k][k]);
-#pragma unroll
-        for (int i = k + 1; i < 6; ++i) { const bool g = fabs(A[i][i]) > best; best = g ? fabs(A[i][i]) : best; piv = g ? i : piv; }
-        piv = stop ? k : piv;
-        pivs[k] = piv;
-#pragma unroll
-        for (int p = k + 1; p < 6; ++p) {
-            const bool sw = (piv == p);
-#pragma unroll
-            for (int j = 0; j < 6; ++j) { const double a = A[k][j], c = A[p][j]; A[k][j] = sw ? c : a; A[p][j] = sw ? a : c; }
-#pragma unroll
-            for (int i = 0; i < 6; ++i) { const double a = A[i][k], c = A[i][p]; A[i][k] = sw ? c : a; A[i][p] = sw ? a : c; }
-            { const double a = y[k], c = y[p]; y[k] = sw ? c : a; y[p] = sw ? a : c; }
-        }
-        const double d = A[k][k];
-        positive = positive && (stop || !(d < 0));
-        stop = stop || (d == 0);
-        const double dd = stop ? 1.0 : d;            // after an exact zero pivot Eigen leaves the trailing block untouched
-#pragma unroll
-        for (int i = k + 1; i < 6; ++i) A[i][k] = stop ? A[i][k] : A[i][k] / dd;
-#pragma unroll
-        for (int i = k + 1; i < 6; ++i)
-#pragma unroll
-            for (int j = k + 1; j <= i; ++j) {
-                const double nv = A[i][j] - A[i][k] * dd * A[j][k];
-                A[i][j] = stop ? A[i][j] : nv;
-                A[j][i] = A[i][j];
-            }
-    }
-    if (!positive) return false;
+// 1/d for a positive normal double: MUFU.RCP64H seed (~20 bits) + two Newton steps (error ~ 1 ulp), 5 dependent operations
+// instead of the ~20 of the IEEE division sequence.
+__device__ __forceinline__ double rcp_newton(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0); r = fma(r, e, r);
+    e = fma(-d, r, 1.0);        r = fma(r, e, r);
+    return r;
+}
+
+// Solves (H + lambda I) x = b for the 6x6 damped normal equations.  H = sum rho' J^T Omega J is positive semi-definite and
+// lambda > 0, so the system is SPD and an unpivoted LDL^T (the "small on-device Cholesky") is backward stable; g2o's dense
+// solver uses Eigen's diagonally pivoted LDLT (Thirdparty/g2o/g2o/solvers/linear_solver_dense.h), which differs from this by
+// rounding only (covered by the 1e-5 pose tolerance of the parity tests; the oracle keeps the pivoted form).  This runs on
+// ONE thread and is bound by the latency of dependent FP64 operations (~36 cycles each, measured), so it is written for a
+// short dependency chain: compile-time indices (registers), b eliminated alongside the columns, one Newton reciprocal per
+// pivot, column-oriented back substitution.  Returns false when a pivot is negative or not finite (Eigen's isPositive() ==
+// false -> g2o treats the trial as failed); an exactly zero pivot (no active edge and lambda == 0) leaves that unknown at 0
+// like Eigen's solve does.
+__device__ __forceinline__ bool solve6(const double* Hsym /*21 upper*/, double lambda, const double* b, double* x) {
+    double L[6][6], dinv[6], y[6];
+    // every loop has the constant trip count 6 with compile-time guards: triangular bounds defeat the unroller, and one
+    // surviving loop would turn the register arrays into local memory
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
+        for (int j = 0; j < 6; ++j)
+            if (j >= i) L[j][i] = Hsym[i * 6 - (i * (i - 1)) / 2 + (j - i)];       // lower triangle, column i
 #pragma unroll
-    for (int i = 0; i < 6; ++i) y[i] = (A[i][i] != 0) ? y[i] / A[i][i] : 0.0;
+    for (int i = 0; i < 6; ++i) { L[i][i] += lambda; y[i] = b[i]; }
+    bool positive = true;
 #pragma unroll
-    for (int i = 5; i >= 0; --i)
+    for (int k = 0; k < 6; ++k) {
+        const double d = L[k][k];
+        positive = positive && (d >= 0) && (d <= DBL_MAX);
+        dinv[k] = (d >= DBL_MIN && d <= DBL_MAX) ? rcp_newton(d) : 0.0;
 #pragma unroll
-        for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
-    // x = P^T y: undo the swaps in reverse order
+        for (int i = 0; i < 6; ++i) {
+            if (i > k) {
+                const double aik = L[i][k], lik = aik * dinv[k];
 #pragma unroll
-    for (int k = 5; k >= 0; --k) {
-#pragma unroll
-        for (int p = k + 1; p < 6; ++p) {
-            const bool sw = (pivs[k] == p);
-            const double a = y[k], c = y[p];
-            y[k] = sw ? c : a; y[p] = sw ? a : c;
+                for (int j = 0; j < 6; ++j)
+                    if (j > k && j < i) L[i][j] -= aik * L[j][k];          // rows j < i already hold the scaled l_jk
+                L[i][i] -= aik * lik;
+                L[i][k] = lik;
+                y[i] -= lik * y[k];                                        // forward substitution rides along
+            }
         }
+    }
+    if (!positive) return false;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] *= dinv[i];
+#pragma unroll
+    for (int jj = 0; jj < 5; ++jj) {
+        const int j = 5 - jj;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            if (i < j) y[i] -= L[j][i] * y[j];
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = y[i];
     return true;
 }
 
+// 1/sqrt(x) for a positive normal double: MUFU.RSQ64H seed + two Newton steps (7 dependent operations)
+__device__ __forceinline__ double rsqrt_newton(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double t = x * y, h = 0.5 * y;
+        const double e = fma(-t, h, 0.5);       // (1 - x y^2) / 2
+        y = fma(y, e, y);
+    }
+    return y;
+}
+
+// reciprocal of the camera-frame depth; the Newton form for every normal value, IEEE division (inf / NaN propagation) otherwise
+__device__ __forceinline__ double rcp_depth(double z) {
+    const double az = fabs(z);
+    return (az >= DBL_MIN && az <= DBL_MAX) ? rcp_newton(z) : 1.0 / z;
+}
+
+// RobustKernelHuber::robustify (Thirdparty/g2o/g2o/core/robust_kernel_impl.cpp:65-91), branch-free: rho0 = robust cost,
+// rho1 = weight.  sqrt(e2) and delta / sqrt(e2) both come from one Newton rsqrt (the IEEE sqrt followed by an IEEE division is
+// ~40 dependent FP64 operations on the per-edge critical path).
 __device__ __forceinline__ void huber(double e2, double delta, float dsqr, double& rho0, double& rho1) {
-    if (e2 <= (double)dsqr) { rho0 = e2; rho1 = 1.0; }
-    else { const double sq = sqrt(e2); rho0 = 2 * sq * delta - (double)dsqr; rho1 = delta / sq; }
+    const double rs = rsqrt_newton(fmax(e2, 1e-300)), sq = e2 * rs;
+    const bool in = e2 <= (double)dsqr;
+    rho0 = in ? e2 : 2 * sq * delta - (double)dsqr;
+    rho1 = in ? 1.0 : delta * rs;
 }
 
 constexpr int kAcc = 28;      // 21 H + 6 b + 1 chi
 constexpr int kPoseThreads = 512, kPoseWarps = kPoseThreads / 32;
+constexpr int kMaxTrials = 10;    // g2o _maxTrialsAfterFailure
 
-// block-wide sum of kAcc doubles (fixed tree: lane shuffles, then warps 0..7 in order); result broadcast in `out`
-__device__ __forceinline__ void block_reduce(double* v, double* smem /* 8*kAcc */, double* out /* kAcc, shared */) {
+// block-wide sum of kAcc doubles.  Inside a warp the 28 sums are folded with a halving butterfly: at distance h every lane
+// keeps one half of its slots and ships the other half to its partner, so 16+8+4+2+1 = 31 exchanges replace 28 x 5 and
+// lane L ends up with the warp total of slot L.  The warp totals are then added in warp order (fixed tree: deterministic).
+__device__ __forceinline__ void block_reduce(double* v /* 32 slots, 28..31 zero */, double* smem /* warps*kAcc */, double* out /* kAcc, shared */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < kAcc; ++k) {
-        double x = v[k];
+    for (int h = 16; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if (lane == 0) smem[warp * kAcc + k] = x;
+        for (int k = 0; k < h; ++k) {
+            const double send = up ? v[k] : v[k + h];
+            const double keep = up ? v[k + h] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
     }
+    if (lane < kAcc) smem[warp * kAcc + lane] = v[0];
     __syncthreads();
     if (threadIdx.x < kAcc) {
         double s = 0;
+#pragma unroll
         for (int w = 0; w < kPoseWarps; ++w) s += smem[w * kAcc + threadIdx.x];
         out[threadIdx.x] = s;
     }
     __syncthreads();
 }
+
+// structural zeros shared by the mono and the stereo Jacobian (d(u)/d(ty) = d(v)/d(tx) = d(ur)/d(ty) = 0)
+__device__ constexpr bool kJnz[3][6] = {{true, true, true, true, false, true}, {true, true, true, false, true, true}, {true, true, true, true, false, true}};
 
 }  // namespace
 
@@ -225,10 +268,18 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
                                                             int* __restrict__ n_inliers) {
     __shared__ double red[kPoseWarps * kAcc];
     __shared__ double acc[kAcc];
-    __shared__ Se3d s_est, s_init, s_backup;
-    __shared__ double s_x[6], s_lambda, s_ni, s_rho, s_current, s_ini, s_temp;
-    __shared__ int s_nbad_lm, s_qmax, s_ok, s_ok2, s_continue;
+    __shared__ Se3d s_est, s_init, s_cand[kMaxTrials];
+    __shared__ double s_cx[kMaxTrials][6], s_lambda, s_ni, s_rho, s_current, s_ini, s_temp;
+    __shared__ int s_nbad_lm, s_qmax, s_ok, s_cok[kMaxTrials], s_continue;
     const int tid = threadIdx.x, n = p.n_dev ? *p.n_dev : p.n;
+#ifdef POSE_TIMING
+    long long tm[6] = {0, 0, 0, 0, 0, 0}; int tc[3] = {0, 0, 0}; long long t0_ = clock64(), tA_;
+#define TM_START() tA_ = clock64()
+#define TM_ADD(i) do { long long tB_ = clock64(); tm[i] += tB_ - tA_; tA_ = tB_; } while (0)
+#else
+#define TM_START()
+#define TM_ADD(i)
+#endif
     const float* pose_in = p.pose_in_dev ? p.pose_in_dev : p.pose_in;
 
     if (n < 3) {                      // src/Optimizer.cc:996
@@ -252,30 +303,37 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
     bool robust = true;
     int n_bad = 0;
 
-    // evaluates errors of the active edges at s_est, stores them, returns this thread's partial robust chi2
-    auto eval_errors = [&](double& chi_part) {
-        const Se3d T = s_est;
+    // One edge at pose T: camera-frame point, 1/z and the reprojection error, one code path for both edge types (no warp
+    // divergence between mono and stereo keypoints).  Reference: EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose
+    // ::computeError (src/OptimizableTypes.h, Thirdparty/g2o/g2o/types/types_six_dof_expmap.cpp:339-404): the stereo
+    // projection uses a FLOAT 1/z (cam_project), the mono one fx*x/z in double; 1/z is a Newton reciprocal (<= 1 ulp).
+    // All loads are issued up front (none depends on the level test).
+    struct Edge { double pc[3], invz, e[3], info; bool st, active; };
+    auto load_edge = [&](const Se3d& T, int k, Edge& E) {
+        const float xwf[3] = {p.xw[3 * k], p.xw[3 * k + 1], p.xw[3 * k + 2]};
+        const float ob[3] = {p.obs[3 * k], p.obs[3 * k + 1], p.obs[3 * k + 2]};
+        E.st = p.stereo[k] != 0;
+        E.info = (double)p.inv_sigma2[k];
+        E.active = level[k] == 0;
+        const double xw[3] = {xwf[0], xwf[1], xwf[2]};
+        se3_map(T, xw, E.pc);
+        E.invz = rcp_depth(E.pc[2]);
+        const double iz = E.st ? (double)(float)E.invz : E.invz;
+        const double u = E.pc[0] * iz * fx + cx, v = E.pc[1] * iz * fy + cy;
+        E.e[0] = (double)ob[0] - u; E.e[1] = (double)ob[1] - v;
+        E.e[2] = E.st ? (double)ob[2] - (u - bf * iz) : 0.0;
+    };
+
+    // evaluates errors of the active edges at pose T, stores them, returns this thread's partial robust chi2
+    auto eval_errors = [&](const Se3d& T, double& chi_part) {
         chi_part = 0;
         for (int k = tid; k < n; k += kPoseThreads) {
-            if (level[k] != 0) continue;
-            const double xw[3] = {p.xw[3 * k], p.xw[3 * k + 1], p.xw[3 * k + 2]};
-            double pc[3];
-            se3_map(T, xw, pc);
-            const bool st = p.stereo[k] != 0;
-            const double info = (double)p.inv_sigma2[k];
-            double e0, e1, e2 = 0;
-            if (st) {
-                const float invz = (float)(1.0 / pc[2]);
-                const double u = pc[0] * invz * fx + cx, v = pc[1] * invz * fy + cy;
-                e0 = (double)p.obs[3 * k] - u; e1 = (double)p.obs[3 * k + 1] - v; e2 = (double)p.obs[3 * k + 2] - (u - bf * invz);
-            } else {
-                e0 = (double)p.obs[3 * k] - ((double)p.fx * pc[0] / pc[2] + (double)p.cx);
-                e1 = (double)p.obs[3 * k + 1] - ((double)p.fy * pc[1] / pc[2] + (double)p.cy);
-            }
-            work[3 * (size_t)k] = e0; work[3 * (size_t)k + 1] = e1; work[3 * (size_t)k + 2] = e2;
-            double chi = e0 * (info * e0) + e1 * (info * e1);
-            if (st) chi += e2 * (info * e2);
-            if (robust) { double r0, r1; huber(chi, st ? ds : dm, st ? dsqr_s : dsqr_m, r0, r1); chi = r0; }
+            Edge E;
+            load_edge(T, k, E);
+            if (!E.active) continue;
+            work[3 * (size_t)k] = E.e[0]; work[3 * (size_t)k + 1] = E.e[1]; work[3 * (size_t)k + 2] = E.e[2];
+            double chi = E.e[0] * (E.info * E.e[0]) + E.e[1] * (E.info * E.e[1]) + E.e[2] * (E.info * E.e[2]);
+            if (robust) { double r0, r1; huber(chi, E.st ? ds : dm, E.st ? dsqr_s : dsqr_m, r0, r1); chi = r0; }
             chi_part += chi;
         }
     };
@@ -286,69 +344,67 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
         for (int iter = 0; iter < 10; ++iter) {
             if (!s_ok) break;
             // ---- computeActiveErrors + activeRobustChi2 + buildSystem at the current estimate ----
-            double v[kAcc];
+            double v[32];
 #pragma unroll
-            for (int k = 0; k < kAcc; ++k) v[k] = 0;
+            for (int k = 0; k < 32; ++k) v[k] = 0;
+            TM_START();
             {
                 const Se3d T = s_est;
                 for (int k = tid; k < n; k += kPoseThreads) {
-                    if (level[k] != 0) continue;
-                    const double xw[3] = {p.xw[3 * k], p.xw[3 * k + 1], p.xw[3 * k + 2]};
-                    double pc[3];
-                    se3_map(T, xw, pc);
-                    const bool st = p.stereo[k] != 0;
-                    const double info = (double)p.inv_sigma2[k];
-                    const double x = pc[0], y = pc[1];
-                    double e[3] = {0, 0, 0}, J[3][6];
-                    if (st) {
-                        const float invzf = (float)(1.0 / pc[2]);
-                        const double u = pc[0] * invzf * fx + cx, vv = pc[1] * invzf * fy + cy;
-                        e[0] = (double)p.obs[3 * k] - u; e[1] = (double)p.obs[3 * k + 1] - vv; e[2] = (double)p.obs[3 * k + 2] - (u - bf * invzf);
-                        const double invz = 1.0 / pc[2], invz_2 = invz * invz;
-                        J[0][0] = x * y * invz_2 * fx;  J[0][1] = -(1 + (x * x * invz_2)) * fx; J[0][2] = y * invz * fx;
-                        J[0][3] = -invz * fx;           J[0][4] = 0;                           J[0][5] = x * invz_2 * fx;
-                        J[1][0] = (1 + y * y * invz_2) * fy; J[1][1] = -x * y * invz_2 * fy;   J[1][2] = -x * invz * fy;
-                        J[1][3] = 0;                    J[1][4] = -invz * fy;                  J[1][5] = y * invz_2 * fy;
-                        J[2][0] = J[0][0] - bf * y * invz_2; J[2][1] = J[0][1] + bf * x * invz_2; J[2][2] = J[0][2];
-                        J[2][3] = J[0][3];              J[2][4] = 0;                           J[2][5] = J[0][5] - bf * invz_2;
-                    } else {
-                        const double z = pc[2];
-                        e[0] = (double)p.obs[3 * k] - ((double)p.fx * pc[0] / pc[2] + (double)p.cx);
-                        e[1] = (double)p.obs[3 * k + 1] - ((double)p.fy * pc[1] / pc[2] + (double)p.cy);
-                        const double pj[2][3] = {{(double)p.fx / z, 0.0, -(double)p.fx * x / (z * z)}, {0.0, (double)p.fy / z, -(double)p.fy * y / (z * z)}};
-                        const double D[3][6] = {{0, z, -y, 1, 0, 0}, {-z, 0, x, 0, 1, 0}, {y, -x, 0, 0, 0, 1}};
-#pragma unroll
-                        for (int r = 0; r < 2; ++r)
-#pragma unroll
-                            for (int c = 0; c < 6; ++c) J[r][c] = (-pj[r][0]) * D[0][c] + (-pj[r][1]) * D[1][c] + (-pj[r][2]) * D[2][c];
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) J[2][c] = 0;
-                    }
+                    Edge E;
+                    load_edge(T, k, E);
+                    if (!E.active) continue;
+                    const bool st = E.st;
+                    const double info = E.info, x = E.pc[0], y = E.pc[1], invz = E.invz, invz_2 = invz * invz;
+                    const double e[3] = {E.e[0], E.e[1], E.e[2]};
+                    double J[3][6];
+                    // rows 0/1 are the same expressions for both edge types (mono: -projectJac * [-(p)x | I], expanded);
+                    // the third row of a mono edge is zero, so its terms add exact zeros to the sums
+                    J[0][0] = x * y * invz_2 * fx;       J[0][1] = -(1 + (x * x * invz_2)) * fx; J[0][2] = y * invz * fx;
+                    J[0][3] = -invz * fx;                J[0][4] = 0;                           J[0][5] = x * invz_2 * fx;
+                    J[1][0] = (1 + y * y * invz_2) * fy; J[1][1] = -x * y * invz_2 * fy;        J[1][2] = -x * invz * fy;
+                    J[1][3] = 0;                         J[1][4] = -invz * fy;                  J[1][5] = y * invz_2 * fy;
+                    const double sbf = st ? bf : 0.0;
+                    J[2][0] = st ? J[0][0] - sbf * y * invz_2 : 0.0; J[2][1] = st ? J[0][1] + sbf * x * invz_2 : 0.0;
+                    J[2][2] = st ? J[0][2] : 0.0;                    J[2][3] = st ? J[0][3] : 0.0;
+                    J[2][4] = 0;                                     J[2][5] = st ? J[0][5] - sbf * invz_2 : 0.0;
                     work[3 * (size_t)k] = e[0]; work[3 * (size_t)k + 1] = e[1]; work[3 * (size_t)k + 2] = e[2];
-                    // mono edges carry a zero third row (J[2][*] = 0, e[2] = 0): identical sums, static indices -> registers
                     double chi = 0;
 #pragma unroll
                     for (int r = 0; r < 3; ++r) chi += e[r] * (info * e[r]);
                     double w = 1.0, r0 = chi;
                     if (robust) huber(chi, st ? ds : dm, st ? dsqr_s : dsqr_m, r0, w);
                     v[27] += r0;
+                    const double wi = w * info;
+                    double WJ[3][6], we[3];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        we[r] = wi * e[r];
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) WJ[r][c] = kJnz[r][c] ? wi * J[r][c] : 0.0;
+                    }
 #pragma unroll
                     for (int i = 0; i < 6; ++i) {
                         double sb = 0;
 #pragma unroll
-                        for (int r = 0; r < 3; ++r) sb += J[r][i] * (info * e[r]);
-                        v[21 + i] -= w * sb;
+                        for (int r = 0; r < 3; ++r) if (kJnz[r][i]) sb += J[r][i] * we[r];
+                        v[21 + i] -= sb;
 #pragma unroll
                         for (int j = i; j < 6; ++j) {
                             double h = 0;
 #pragma unroll
-                            for (int r = 0; r < 3; ++r) h += J[r][i] * (w * info) * J[r][j];
+                            for (int r = 0; r < 3; ++r) if (kJnz[r][i] && kJnz[r][j]) h += J[r][i] * WJ[r][j];
                             v[i * 6 - (i * (i - 1)) / 2 + (j - i)] += h;
                         }
                     }
                 }
             }
+            TM_ADD(0);
             block_reduce(v, red, acc);
+            TM_ADD(1);
+#ifdef POSE_TIMING
+            tc[0]++;
+#endif
             if (tid == 0) {
                 s_current = acc[27]; s_ini = acc[27]; s_temp = acc[27];
                 if (iter == 0) {
@@ -359,24 +415,37 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
                 s_rho = 0; s_qmax = 0;
             }
             __syncthreads();
-            // ---- LM trials ----
-            for (;;) {
-                if (tid == 0) {
-                    s_backup = s_est;
-                    double x[6] = {0, 0, 0, 0, 0, 0};
-                    s_ok2 = solve6(acc, s_lambda, acc + 21, x) ? 1 : 0;
-                    for (int i = 0; i < 6; ++i) s_x[i] = x[i];
-                    Se3d E, Tn;
-                    se3_exp(x, E);
-                    se3_mul(E, s_est, Tn);
-                    s_est = Tn;
-                }
-                __syncthreads();
+            // ---- LM trials.  A rejected trial only changes lambda (x nu, nu doubling), never H, b or the estimate, so the damped solves of all (<= 10) possible trials of this iteration
+            // are independent: lane 0 of warp w solves trial w while the other warps would idle anyway, and a retry then
+            // costs one error evaluation instead of a serial solve + exp. ----
+            TM_START();
+            if ((tid & 31) == 0 && (tid >> 5) < kMaxTrials) {
+                const int w = tid >> 5;
+                double lam = s_lambda, ni = s_ni;
+                for (int m = 0; m < w; ++m) { lam *= ni; ni *= 2; }
+                double x[6] = {0, 0, 0, 0, 0, 0};
+#ifdef POSE_TIMING
+                const long long ts_ = clock64();
+#endif
+                s_cok[w] = solve6(acc, lam, acc + 21, x) ? 1 : 0;
+#ifdef POSE_TIMING
+                tm[5] += clock64() - ts_;
+#endif
+#pragma unroll
+                for (int i = 0; i < 6; ++i) s_cx[w][i] = x[i];
+                Se3d E, Tn;
+                se3_exp(x, E);
+                se3_mul(E, s_est, Tn);
+                s_cand[w] = Tn;
+            }
+            __syncthreads();
+            TM_ADD(2);
+            for (int trial = 0;; ++trial) {
+                TM_START();
                 double part;
-                eval_errors(part);
-                __syncthreads();
+                eval_errors(s_cand[trial], part);
+                TM_ADD(3);
                 {
-                    // reduce only the chi2 slot (slot 27) but reuse the fixed tree
                     const int lane = tid & 31, warp = tid >> 5;
                     double x = part;
 #pragma unroll
@@ -387,10 +456,10 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
                         double s = 0;
                         for (int w = 0; w < kPoseWarps; ++w) s += red[w];
                         double temp = s;
-                        if (!s_ok2) temp = DBL_MAX;
+                        if (!s_cok[trial]) temp = DBL_MAX;
                         double rho = s_current - temp;
                         double scale = 0;
-                        for (int j = 0; j < 6; ++j) scale += s_x[j] * (s_lambda * s_x[j] + acc[21 + j]);
+                        for (int j = 0; j < 6; ++j) scale += s_cx[trial][j] * (s_lambda * s_cx[trial][j] + acc[21 + j]);
                         scale += 1e-3;
                         rho /= scale;
                         if (rho > 0 && isfinite(temp)) {
@@ -398,21 +467,25 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
                             double alpha = 1. - r21 * r21 * r21;
                             alpha = fmin(alpha, 2. / 3.);
                             const double sf = fmax(1. / 3., alpha);
-                            s_lambda *= sf; s_ni = 2; s_current = temp;
+                            s_lambda *= sf; s_ni = 2; s_current = temp; s_est = s_cand[trial];
                         } else {
-                            s_lambda *= s_ni; s_ni *= 2; s_est = s_backup;
+                            s_lambda *= s_ni; s_ni *= 2;          // the estimate is restored = left untouched
                         }
                         s_rho = rho;
                         s_qmax += 1;
-                        s_continue = (rho < 0 && s_qmax < 10) ? 1 : 0;
+                        s_continue = (rho < 0 && s_qmax < kMaxTrials) ? 1 : 0;
                     }
                     __syncthreads();
                 }
+                TM_ADD(4);
+#ifdef POSE_TIMING
+                tc[1]++;
+#endif
                 if (!s_continue) break;
             }
             if (tid == 0) {
                 int ok = 1;
-                if (s_qmax == 10 || s_rho == 0) ok = 0;
+                if (s_qmax == kMaxTrials || s_rho == 0) ok = 0;
                 else {
                     if ((s_ini - s_current) * 1e3 < s_ini) s_nbad_lm += 1; else s_nbad_lm = 0;
                     if (s_nbad_lm >= 3) ok = 0;
@@ -430,17 +503,9 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
                 const double info = (double)p.inv_sigma2[k];
                 double e0, e1, e2 = 0;
                 if (outlier[k]) {
-                    const double xw[3] = {p.xw[3 * k], p.xw[3 * k + 1], p.xw[3 * k + 2]};
-                    double pc[3];
-                    se3_map(T, xw, pc);
-                    if (st) {
-                        const float invz = (float)(1.0 / pc[2]);
-                        const double u = pc[0] * invz * fx + cx, v = pc[1] * invz * fy + cy;
-                        e0 = (double)p.obs[3 * k] - u; e1 = (double)p.obs[3 * k + 1] - v; e2 = (double)p.obs[3 * k + 2] - (u - bf * invz);
-                    } else {
-                        e0 = (double)p.obs[3 * k] - ((double)p.fx * pc[0] / pc[2] + (double)p.cx);
-                        e1 = (double)p.obs[3 * k + 1] - ((double)p.fy * pc[1] / pc[2] + (double)p.cy);
-                    }
+                    Edge E;
+                    load_edge(T, k, E);
+                    e0 = E.e[0]; e1 = E.e[1]; e2 = E.e[2];
                     work[3 * (size_t)k] = e0; work[3 * (size_t)k + 1] = e1; work[3 * (size_t)k + 2] = e2;
                 } else {
                     e0 = work[3 * (size_t)k]; e1 = work[3 * (size_t)k + 1]; e2 = work[3 * (size_t)k + 2];
@@ -469,6 +534,9 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
         pose_out[0] = (float)T.qx; pose_out[1] = (float)T.qy; pose_out[2] = (float)T.qz; pose_out[3] = (float)T.qw;
         pose_out[4] = (float)T.tx; pose_out[5] = (float)T.ty; pose_out[6] = (float)T.tz;
         *n_inliers = n - n_bad;
+#ifdef POSE_TIMING
+        printf("pose n=%d total=%lld build=%lld(%d) breduce=%lld solve=%lld eval=%lld(%d) evalred=%lld solve6=%lld\n", n, clock64() - t0_, tm[0], tc[0], tm[1], tm[2], tm[3], tc[1], tm[4], tm[5]);
+#endif
     }
 }
 

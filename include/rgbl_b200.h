@@ -227,6 +227,14 @@ int rgbl_resident_download(rgbl_ctx* ctx, rgbl_keypoint* kps, uint8_t* desc, flo
 int rgbl_resident_track(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono,
                         float* poses_out, int* n_matches, int* n_inliers);
 
+/* Asynchronous form of the same chain.  _begin copies the batch's frame outputs into chain-owned buffers, enqueues the chain
+ * on the context's tracking stream and returns at once; _end blocks until it has finished and writes the results.  Between
+ * the two calls rgbl_resident_process / rgbl_resident_upload may be called for the NEXT batch (frame construction of batch
+ * i+1 then overlaps the tracking of batch i, as the tracking thread's pipeline does in the reference); every other
+ * tracking entry point returns RGBL_E_INVALID until _end has been called.                                              */
+int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono);
+int rgbl_resident_track_end(rgbl_ctx* ctx, float* poses_out, int* n_matches, int* n_inliers);
+
 /* Keypoint distribution (DistributeOctTree) runs on the device by default (one CTA per (frame, level)); on != 0
  * selects the host implementation instead (also: environment RGBL_HOST_QUADTREE=1).  Both are exact.           */
 int rgbl_set_host_quadtree(rgbl_ctx* ctx, int on);

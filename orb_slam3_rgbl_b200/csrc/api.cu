@@ -40,6 +40,12 @@ static void release(Ctx* c) {
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
     if (c->ev_blur) cudaEventDestroy(c->ev_blur);
+    if (c->st_trk) { cudaStreamSynchronize(c->st_trk); cudaStreamDestroy(c->st_trk); }
+    if (c->ev_snap) cudaEventDestroy(c->ev_snap);
+    if (c->ev_chain_b) cudaEventDestroy(c->ev_chain_b);
+    if (c->ev_chain_e) cudaEventDestroy(c->ev_chain_e);
+    if (c->h_chain_f) cudaFreeHost(c->h_chain_f);
+    if (c->h_chain_i) cudaFreeHost(c->h_chain_i);
     if (c->st) cudaStreamDestroy(c->st);
     if (c->st_aux) cudaStreamDestroy(c->st_aux);
     delete c;

@@ -120,6 +120,7 @@ int rgbl_search_by_projection_last(rgbl_ctx* ctx, const rgbl_frame_view* cur, co
                                    int check_orientation, const uint8_t* cur_state, int32_t* match, int* n_matches) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
+    if (c->chain_pending) { c->err = "a tracking chain is in flight (rgbl_resident_track_end not called)"; return RGBL_E_INVALID; }
     if (!cur || !cur_pose || !last_pose || n_last < 0 || !match || (n_last > 0 && (!valid || !xw || !mp_desc || !last_octave || !last_angle || !obs_pos))) { c->err = "null argument"; return RGBL_E_INVALID; }
     CU(cudaSetDevice(c->cfg.device));
     FrameDev f;
@@ -162,6 +163,7 @@ int rgbl_is_in_frustum(rgbl_ctx* ctx, const rgbl_frame_view* cur, const float Rc
                        uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, float* track_depth, int32_t* level, float* view_cos) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
+    if (c->chain_pending) { c->err = "a tracking chain is in flight (rgbl_resident_track_end not called)"; return RGBL_E_INVALID; }
     if (!cur || !Rcw || !tcw || !Ow || n < 0 || (n > 0 && (!xw || !normal || !mf_min_dist || !mf_max_dist || !in_view || !proj_x || !proj_y || !proj_xr || !track_depth || !level || !view_cos))) { c->err = "null argument"; return RGBL_E_INVALID; }
     if (n == 0) return RGBL_OK;
     CU(cudaSetDevice(c->cfg.device));
@@ -200,6 +202,7 @@ int rgbl_search_by_projection_local(rgbl_ctx* ctx, const rgbl_frame_view* cur, i
                                     int far_points, float th_far, const uint8_t* cur_state, int32_t* match, int* n_matches) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
+    if (c->chain_pending) { c->err = "a tracking chain is in flight (rgbl_resident_track_end not called)"; return RGBL_E_INVALID; }
     if (!cur || n < 0 || !match || (n > 0 && (!in_view || !proj_x || !proj_y || !proj_xr || !track_depth || !level || !view_cos || !mp_desc || !obs_pos))) { c->err = "null argument"; return RGBL_E_INVALID; }
     if (!(nn_ratio > 0.f)) { c->err = "nn_ratio must be > 0"; return RGBL_E_INVALID; }
     CU(cudaSetDevice(c->cfg.device));
@@ -238,6 +241,7 @@ int rgbl_pose_optimize(rgbl_ctx* ctx, const float pose_in[7], int n, const float
                        int* n_inliers) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
+    if (c->chain_pending) { c->err = "a tracking chain is in flight (rgbl_resident_track_end not called)"; return RGBL_E_INVALID; }
     if (!pose_in || !pose_out || n < 0 || !n_inliers || (n > 0 && (!xw || !obs || !inv_sigma2 || !stereo || !outlier))) { c->err = "null argument"; return RGBL_E_INVALID; }
     CU(cudaSetDevice(c->cfg.device));
     int rc = ensure_queries(c, std::max(n, 1)); if (rc) return rc;
@@ -271,6 +275,7 @@ int rgbl_pose_optimize(rgbl_ctx* ctx, const float pose_in[7], int n, const float
 int rgbl_stereo_matches(rgbl_ctx* ctx, int slot_left, int slot_right, float mb, float mbf, float* depth, float* uright, int cap) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
+    if (c->chain_pending) { c->err = "a tracking chain is in flight (rgbl_resident_track_end not called)"; return RGBL_E_INVALID; }
     if (!depth || !uright) { c->err = "null argument"; return RGBL_E_INVALID; }
     if (slot_left < 0 || slot_right < 0 || slot_left >= c->last_frames || slot_right >= c->last_frames) { c->err = "frame slot out of range (extract the stereo pair as one batch first)"; return RGBL_E_INVALID; }
     if (c->cap_kp > 65535) { c->err = "more than 65535 keypoints per frame"; return RGBL_E_UNSUPPORTED; }
@@ -307,6 +312,7 @@ int rgbl_search_by_bow(rgbl_ctx* ctx, int n_kf, const uint8_t* kf_desc, const fl
                        float nn_ratio, int check_orientation, int32_t* match, int* n_matches) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
+    if (c->chain_pending) { c->err = "a tracking chain is in flight (rgbl_resident_track_end not called)"; return RGBL_E_INVALID; }
     if (n_kf < 0 || n_f < 0 || n_nodes_kf < 0 || n_nodes_f < 0 || !match || !(nn_ratio > 0.f) ||
         (n_kf > 0 && (!kf_desc || !kf_angle || !kf_valid)) || (n_f > 0 && (!f_desc || !f_angle)) ||
         (n_nodes_kf > 0 && (!kf_node_ids || !kf_node_start || !kf_node_feat)) || (n_nodes_f > 0 && (!f_node_ids || !f_node_start || !f_node_feat))) {
@@ -369,6 +375,7 @@ int rgbl_search_by_projection_reloc(rgbl_ctx* ctx, const rgbl_frame_view* cur, c
                                     int32_t* match, int* n_matches) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
+    if (c->chain_pending) { c->err = "a tracking chain is in flight (rgbl_resident_track_end not called)"; return RGBL_E_INVALID; }
     if (!cur || !cur_pose || n < 0 || !match || (n > 0 && (!valid || !xw || !mp_desc || !kf_angle || !mf_min_dist || !mf_max_dist))) { c->err = "null argument"; return RGBL_E_INVALID; }
     CU(cudaSetDevice(c->cfg.device));
     FrameDev f;
@@ -406,24 +413,65 @@ int rgbl_search_by_projection_reloc(rgbl_ctx* ctx, const rgbl_frame_view* cur, c
  * device (no host round trip per frame): for t = 1..n-1  SearchByProjection(frame t, frame t-1) -> PoseOptimization, with
  * every LiDAR-depth keypoint of frame t-1 acting as a map point (Frame::UnprojectStereo with the estimated pose of t-1)
  * and the constant-pose motion model.  poses_out[n][7], n_matches[n], n_inliers[n] (entry 0 = pose0, 0, 0).           */
-int rgbl_resident_track(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono,
-                        float* poses_out, int* n_matches, int* n_inliers) {
+// The chain is asynchronous: _begin snapshots the batch's frame outputs into chain-owned buffers (a ~5 MB device copy),
+// enqueues the whole per-frame chain on the context's high-priority tracking stream and returns; _end waits for it and
+// hands the poses out.  Between the two calls the caller may run rgbl_resident_process on the NEXT batch: its kernels
+// fill the SMs the single-CTA chain kernels leave idle (the chain is a latency-bound sequence of small launches).
+int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
-    if (!pose0 || !poses_out || !n_matches || !n_inliers) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (!pose0) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (c->chain_pending) { c->err = "a tracking chain is already in flight: call rgbl_resident_track_end first"; return RGBL_E_INVALID; }
     const int nF = c->last_frames, cap = c->cap_kp;
     if (nF < 1) { c->err = "nothing processed"; return RGBL_E_INVALID; }
     CU(cudaSetDevice(c->cfg.device));
+    if (!c->st_trk) {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->st_trk, cudaStreamNonBlocking, hi));
+        CU(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+        CU(cudaEventCreate(&c->ev_chain_b));
+        CU(cudaEventCreate(&c->ev_chain_e));
+    }
+    if (c->h_chain_cap < (size_t)nF) {
+        if (c->h_chain_f) cudaFreeHost(c->h_chain_f);
+        if (c->h_chain_i) cudaFreeHost(c->h_chain_i);
+        c->h_chain_f = nullptr; c->h_chain_i = nullptr; c->h_chain_cap = 0;
+        const size_t capF = (size_t)std::max(nF, c->cfg.max_batch);
+        CU(cudaMallocHost(&c->h_chain_f, (7 + capF * 7) * sizeof(float)));
+        CU(cudaMallocHost(&c->h_chain_i, (2 * capF + 4) * sizeof(int)));
+        c->h_chain_cap = capF;
+    }
     int rc = ensure_frame(c, cap); if (rc) return rc;
     rc = ensure_queries(c, cap); if (rc) return rc;
     TrackBufs& t = c->trk;
+    const size_t tot = (size_t)nF * cap;
     GROW(t.pose_work, t.cap_pose_work, (size_t)cap * 3);
     GROW(t.ch_poses, t.cap_ch_poses, (size_t)nF * 7); GROW(t.ch_counts, t.cap_ch_counts, (size_t)nF * 2 + 4);
     GROW(t.e_xw, t.cap_e_xw, (size_t)cap * 3); GROW(t.e_obs, t.cap_e_obs, (size_t)cap * 3); GROW(t.e_info, t.cap_e_info, cap);
     GROW(t.e_st, t.cap_e_st, cap); GROW(t.e_lvl, t.cap_e_lvl, cap); GROW(t.e_out, t.cap_e_out, cap); GROW(t.e_idx, t.cap_e_idx, cap);
-    CU(cudaMemcpyAsync(t.ch_poses, pose0, 7 * sizeof(float), cudaMemcpyHostToDevice, c->st));
-    CU(cudaMemsetAsync(t.ch_counts, 0, ((size_t)nF * 2 + 4) * sizeof(int), c->st));
+    GROW(t.s_kps, t.cap_s_kps, tot); GROW(t.s_desc, t.cap_s_desc, tot * 32); GROW(t.s_depth, t.cap_s_depth, tot);
+    GROW(t.s_uright, t.cap_s_uright, tot); GROW(t.s_nsel, t.cap_s_nsel, nF);
+    GROW(t.b_cell_start, t.cap_b_cell_start, (size_t)nF * (kGridCols * kGridRows + 1));
+    GROW(t.b_csr_idx, t.cap_b_csr_idx, tot); GROW(t.b_kp_cell, t.cap_b_kp_cell, tot);
+
+    // snapshot on the frame-construction stream (ordered after the batch's kernels, before the next batch's)
+    CU(cudaMemcpyAsync(t.s_kps, c->d_kps, tot * sizeof(rgbl_keypoint), cudaMemcpyDeviceToDevice, c->st));
+    CU(cudaMemcpyAsync(t.s_desc, c->d_desc, tot * 32, cudaMemcpyDeviceToDevice, c->st));
+    CU(cudaMemcpyAsync(t.s_depth, c->d_depth, tot * sizeof(float), cudaMemcpyDeviceToDevice, c->st));
+    CU(cudaMemcpyAsync(t.s_uright, c->d_uright, tot * sizeof(float), cudaMemcpyDeviceToDevice, c->st));
+    CU(cudaMemcpyAsync(t.s_nsel, c->d_n_sel, (size_t)nF * sizeof(int), cudaMemcpyDeviceToDevice, c->st));
+    CU(cudaEventRecord(c->ev_snap, c->st));
+    CU(cudaStreamWaitEvent(c->st_aux, c->ev_snap, 0));      // the aux stream writes depth / uright of the next batch
+    cudaStream_t cs = c->st_trk;
+    CU(cudaStreamWaitEvent(cs, c->ev_snap, 0));
+
+    for (int i = 0; i < 7; ++i) c->h_chain_f[i] = pose0[i];
+    if (c->prof_on) CU(cudaEventRecord(c->ev_chain_b, cs));
+    CU(cudaMemcpyAsync(t.ch_poses, c->h_chain_f, 7 * sizeof(float), cudaMemcpyHostToDevice, cs));
+    CU(cudaMemsetAsync(t.ch_counts, 0, ((size_t)nF * 2 + 4) * sizeof(int), cs));
     int* d_nm = t.ch_counts; int* d_ni = t.ch_counts + nF; int* d_ne = t.ch_counts + 2 * nF; int* d_flags = t.ch_counts + 2 * nF + 1;
+    int* d_ovf = t.ch_counts + 2 * nF + 2;
     FrameDev f{};
     f.min_x = 0.f; f.max_x = (float)c->cfg.width; f.min_y = 0.f; f.max_y = (float)c->cfg.height;      // k1 == 0: image bounds
     f.inv_w = static_cast<float>(kGridCols) / static_cast<float>(f.max_x - f.min_x);
@@ -433,36 +481,73 @@ int rgbl_resident_track(rgbl_ctx* ctx, const float pose0[7], float fx, float fy,
     f.fx = fx; f.fy = fy; f.cx = cx; f.cy = cy; f.bf = bf; f.mb = bf / fx;
     f.log_scale_factor = std::log(c->cfg.orb.scale_factor);
     MatchScratch ms = scratch(c);
-    stage_begin(c, ST_MATCH, c->st);
+    ms.overflow = d_ovf;
+    // the 64x48 grids do not depend on the poses: all frames in one launch (one CTA per frame)
+    f.n = t.s_nsel; f.keys = t.s_kps;
+    launch_grid_build_batch(cs, f, nF, cap, t.b_cell_start, t.b_csr_idx, t.b_kp_cell);
     for (int k = 1; k < nF; ++k) {
         const size_t lo = (size_t)(k - 1) * cap, cu = (size_t)k * cap;
         const float* last_pose = t.ch_poses + 7 * (k - 1);
-        launch_chain_prep(c->st, c->d_kps + lo, c->d_depth + lo, c->d_n_sel + (k - 1), last_pose, last_pose, f, mono, cap,
+        launch_chain_prep(cs, t.s_kps + lo, t.s_depth + lo, t.s_nsel + (k - 1), last_pose, last_pose, f, mono, cap,
                           t.q_u8a, t.q_f3a, t.q_i, t.q_f[0], t.q_u8b, d_flags);
-        f.n = c->d_n_sel + k; f.keys = c->d_kps + cu; f.uright = c->d_uright + cu; f.desc = c->d_desc + cu * 32;
-        launch_grid_build(c->st, f, t.cell_start, t.csr_idx, t.kp_cell);
-        CU(cudaMemsetAsync(t.state, 0, cap, c->st));
+        f.n = t.s_nsel + k; f.keys = t.s_kps + cu; f.uright = t.s_uright + cu; f.desc = t.s_desc + cu * 32;
+        const int* cell_start = t.b_cell_start + (size_t)k * (kGridCols * kGridRows + 1);
+        const int* csr_idx = t.b_csr_idx + cu;
+        CU(cudaMemsetAsync(t.state, 0, cap, cs));
         SearchLastParams prm{};
         prm.th = th; prm.check_orientation = 1; prm.cur_pose_dev = last_pose; prm.flags_dev = d_flags;
-        LastFrameDev lf{cap, t.q_u8a, t.q_f3a, c->d_desc + lo * 32, t.q_i, t.q_f[0], t.q_u8b};
-        launch_search_last(c->st, f, t.cell_start, t.csr_idx, lf, prm, ms, t.state, t.match, d_nm + k);
-        launch_chain_edges(c->st, f.keys, f.uright, f.n, t.match, t.q_f3a, f, t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne);
+        LastFrameDev lf{cap, t.q_u8a, t.q_f3a, t.s_desc + lo * 32, t.q_i, t.q_f[0], t.q_u8b};
+        launch_search_last(cs, f, cell_start, csr_idx, lf, prm, ms, t.state, t.match, d_nm + k);
+        launch_chain_edges(cs, f.keys, f.uright, f.n, t.match, t.q_f3a, f, t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne);
         PoseProblemDev p{};
         p.n = 0; p.n_dev = d_ne; p.pose_in_dev = last_pose;
         p.xw = t.e_xw; p.obs = t.e_obs; p.inv_sigma2 = t.e_info; p.stereo = t.e_st;
         p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf;
-        launch_pose_optimize(c->st, p, t.pose_work, t.e_lvl, t.e_out, t.ch_poses + 7 * k, d_ni + k);
+        launch_pose_optimize(cs, p, t.pose_work, t.e_lvl, t.e_out, t.ch_poses + 7 * k, d_ni + k);
     }
-    stage_end(c, ST_MATCH, c->st, 6 * (nF - 1));
+    if (c->prof_on) CU(cudaEventRecord(c->ev_chain_e, cs));
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(poses_out, t.ch_poses, (size_t)nF * 7 * sizeof(float), cudaMemcpyDeviceToHost, c->st));
-    CU(cudaMemcpyAsync(n_matches, d_nm, (size_t)nF * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    CU(cudaMemcpyAsync(n_inliers, d_ni, (size_t)nF * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    CU(cudaMemcpyAsync(c->h_overflow, c->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    CU(cudaStreamSynchronize(c->st));
-    prof_collect(c);
-    if (*c->h_overflow) { cudaMemsetAsync(c->d_overflow, 0, sizeof(int), c->st); c->err = "matcher candidate list overflow"; return RGBL_E_CAPACITY; }
+    CU(cudaMemcpyAsync(c->h_chain_f + 7, t.ch_poses, (size_t)nF * 7 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    CU(cudaMemcpyAsync(c->h_chain_i, t.ch_counts, ((size_t)nF * 2 + 4) * sizeof(int), cudaMemcpyDeviceToHost, cs));
+    c->chain_pending = true;
+    c->chain_frames = nF;
+    c->chain_launches = 1 + 5 * (nF - 1);
     return RGBL_OK;
+}
+
+int rgbl_resident_track_end(rgbl_ctx* ctx, float* poses_out, int* n_matches, int* n_inliers) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!poses_out || !n_matches || !n_inliers) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (!c->chain_pending) { c->err = "no tracking chain in flight"; return RGBL_E_INVALID; }
+    CU(cudaSetDevice(c->cfg.device));
+    c->chain_pending = false;
+    CU(cudaStreamSynchronize(c->st_trk));
+    const int nF = c->chain_frames;
+    std::memcpy(poses_out, c->h_chain_f + 7, (size_t)nF * 7 * sizeof(float));
+    std::memcpy(n_matches, c->h_chain_i, (size_t)nF * sizeof(int));
+    std::memcpy(n_inliers, c->h_chain_i + nF, (size_t)nF * sizeof(int));
+    c->total_launches += c->chain_launches;
+    if (c->prof_on) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev_chain_b, c->ev_chain_e) == cudaSuccess) {
+            c->st_ms[ST_MATCH] += ms; c->st_calls[ST_MATCH] += 1; c->st_launches[ST_MATCH] += c->chain_launches;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (c->h_chain_i[2 * nF + 2]) { c->err = "matcher candidate list overflow"; return RGBL_E_CAPACITY; }
+    return RGBL_OK;
+}
+
+int rgbl_resident_track(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono,
+                        float* poses_out, int* n_matches, int* n_inliers) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!pose0 || !poses_out || !n_matches || !n_inliers) { c->err = "null argument"; return RGBL_E_INVALID; }
+    const int rc = rgbl_resident_track_begin(ctx, pose0, fx, fy, cx, cy, bf, th, mono);
+    if (rc) return rc;
+    return rgbl_resident_track_end(ctx, poses_out, n_matches, n_inliers);
 }
 
 }  // extern "C"

@@ -27,11 +27,16 @@ constexpr int kHistoLength = 30;      // ORBmatcher::HISTO_LENGTH
 constexpr uint32_t kPosMask = (1u << 20) - 1u;
 
 // ---- grid --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int* __restrict__ cell_start /*kGridCells+1*/,
+__global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int kp_stride, int* __restrict__ cell_start /*kGridCells+1*/,
                                                           int* __restrict__ csr_idx, int* __restrict__ kp_cell) {
     __shared__ int cnt[kGridCells];
     __shared__ int off[kGridCells + 1];
     const int tid = threadIdx.x;
+    {   // batched launch: one CTA per frame
+        const size_t b = blockIdx.x;
+        f.n += b; f.keys += b * kp_stride;
+        cell_start += b * (kGridCells + 1); csr_idx += b * kp_stride; kp_cell += b * kp_stride;
+    }
     const int n = *f.n;
     for (int c = tid; c < kGridCells; c += 1024) cnt[c] = 0;
     __syncthreads();
@@ -584,7 +589,12 @@ __global__ void __launch_bounds__(1024) chain_edges_kernel(const rgbl_keypoint* 
 
 // ---- launchers ---------------------------------------------------------------------------------------
 void launch_grid_build(cudaStream_t st, const FrameDev& f, int* cell_start, int* csr_idx, int* kp_cell) {
-    grid_build_kernel<<<1, 1024, 0, st>>>(f, cell_start, csr_idx, kp_cell);
+    grid_build_kernel<<<1, 1024, 0, st>>>(f, 0, cell_start, csr_idx, kp_cell);
+}
+
+void launch_grid_build_batch(cudaStream_t st, const FrameDev& f, int n_frames, int kp_stride, int* cell_start, int* csr_idx, int* kp_cell) {
+    if (n_frames <= 0) return;
+    grid_build_kernel<<<n_frames, 1024, 0, st>>>(f, kp_stride, cell_start, csr_idx, kp_cell);
 }
 
 void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LastFrameDev& lf,

@@ -43,9 +43,17 @@ struct TrackBufs {
     float *e_xw = nullptr, *e_obs = nullptr, *e_info = nullptr; size_t cap_e_xw = 0, cap_e_obs = 0, cap_e_info = 0;
     uint8_t *e_st = nullptr, *e_lvl = nullptr, *e_out = nullptr; size_t cap_e_st = 0, cap_e_lvl = 0, cap_e_out = 0;
     int* e_idx = nullptr; size_t cap_e_idx = 0;
+    // chain-owned snapshot of the batch's frame outputs (so that the next batch's frame construction may overwrite the
+    // context's buffers while the chain of this batch is still running) + per-frame grids built in one launch
+    rgbl_keypoint* s_kps = nullptr; size_t cap_s_kps = 0;
+    uint8_t* s_desc = nullptr; size_t cap_s_desc = 0;
+    float *s_depth = nullptr, *s_uright = nullptr; size_t cap_s_depth = 0, cap_s_uright = 0;
+    int* s_nsel = nullptr; size_t cap_s_nsel = 0;
+    int *b_cell_start = nullptr, *b_csr_idx = nullptr, *b_kp_cell = nullptr; size_t cap_b_cell_start = 0, cap_b_csr_idx = 0, cap_b_kp_cell = 0;
     void release() {
         void* all[] = {keys, uright, desc, csr_idx, kp_cell, cell_start, state, match, minq, scalars, lists, list_n, choice, resolved,
-                       q_u8a, q_u8b, q_desc, q_f3a, q_f3b, q_f[0], q_f[1], q_f[2], q_f[3], q_f[4], q_f[5], q_f[6], q_i, pose_work, ch_poses, ch_counts, e_xw, e_obs, e_info, e_st, e_lvl, e_out, e_idx};
+                       q_u8a, q_u8b, q_desc, q_f3a, q_f3b, q_f[0], q_f[1], q_f[2], q_f[3], q_f[4], q_f[5], q_f[6], q_i, pose_work, ch_poses, ch_counts, e_xw, e_obs, e_info, e_st, e_lvl, e_out, e_idx,
+                       s_kps, s_desc, s_depth, s_uright, s_nsel, b_cell_start, b_csr_idx, b_kp_cell};
         for (void* p : all) if (p) cudaFree(p);
     }
 };
@@ -111,6 +119,15 @@ struct Ctx {
     TrackBufs trk;
     int* h_scalars = nullptr;    // pinned, 16 ints
     int last_match_rounds = 0;
+
+    // asynchronous tracking chain (rgbl_resident_track_begin / _end): own high-priority stream, pinned result staging
+    cudaStream_t st_trk = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_chain_b = nullptr, ev_chain_e = nullptr;
+    bool chain_pending = false;
+    int chain_frames = 0, chain_launches = 0;
+    float* h_chain_f = nullptr;  // pinned: pose0 (7) | poses (max_batch * 7)
+    int* h_chain_i = nullptr;    // pinned: n_matches | n_inliers | overflow
+    size_t h_chain_cap = 0;
 
     int last_frames = 0;         // frames valid in the device buffers
     int resident_frames = 0, resident_max_pts = 0;

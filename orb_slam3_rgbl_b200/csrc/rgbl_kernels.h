@@ -97,6 +97,8 @@ struct FrustumParams { float Rcw[9], tcw[3], Ow[3], cos_limit; };
 struct MatchScratch { uint32_t* lists; int list_cap; int* list_n; int* minq; int* choice; uint8_t* resolved; int* overflow; int* rounds; };
 
 void launch_grid_build(cudaStream_t st, const FrameDev& f, int* cell_start, int* csr_idx, int* kp_cell);
+// one CTA per frame: frame b reads f.n[b], f.keys + b * kp_stride and writes cell_start + b * (cells + 1), csr_idx / kp_cell + b * kp_stride
+void launch_grid_build_batch(cudaStream_t st, const FrameDev& f, int n_frames, int kp_stride, int* cell_start, int* csr_idx, int* kp_cell);
 void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LastFrameDev& lf,
                         const SearchLastParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches);
 void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LocalPointsDev& lp,

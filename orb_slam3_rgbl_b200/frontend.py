@@ -393,6 +393,20 @@ class RgblBatch:
         check(lib().rgbl_resident_track(c.handle, ptr(pose0), fx, fy, cx, cy, bf, th, int(mono), ptr(poses), ptr(nm), ptr(ni)), c.handle)
         return poses, nm, ni
 
+    def track_begin(self, pose0, fx, fy, cx, cy, bf, th=15.0, mono=False):
+        """Enqueue the tracking chain of the batch just processed (rgbl_resident_track_begin) and return at once; the next
+        batch's process_resident / run_e2e may be issued before track_end and overlaps the chain on the device."""
+        c = self.ctx
+        pose0 = np.ascontiguousarray(pose0, np.float32)
+        check(lib().rgbl_resident_track_begin(c.handle, ptr(pose0), fx, fy, cx, cy, bf, th, int(mono)), c.handle)
+
+    def track_end(self):
+        """Wait for the chain started by track_begin -> (poses[nF,7], n_matches[nF], n_inliers[nF])"""
+        c = self.ctx
+        poses = np.empty((self.nF, 7), np.float32); nm = np.zeros(self.nF, np.int32); ni = np.zeros(self.nF, np.int32)
+        check(lib().rgbl_resident_track_end(c.handle, ptr(poses), ptr(nm), ptr(ni)), c.handle)
+        return poses, nm, ni
+
     def download(self):
         c = self.ctx
         check(lib().rgbl_resident_download(c.handle, ptr(self.kps), ptr(self.desc), ptr(self.depth), ptr(self.uright), self.cap, ptr(self.n)), c.handle)

@@ -154,6 +154,40 @@ def test_resident_tracking_chain_matches_oracle_chain():
     assert (nm[1:] > 200).all() and (ni[1:] > 150).all()
 
 
+def test_async_chain_overlapping_next_batch_is_identical():
+    """rgbl_resident_track_begin/_end: the chain of batch A keeps running on its own stream (on its snapshot of A's frame
+    outputs) while batch B is uploaded and processed in the same context; both chains must equal the synchronous results,
+    and the entry points that share the chain's scratch are refused while it is in flight."""
+    T = 5
+    seqA, seqB = S.PlaneSequence(21, T + 1), S.PlaneSequence(22, T + 1)
+    mk = lambda seq: ([seq.image(t) for t in range(T)], [seq.cloud(t) for t in range(T)])
+    (ia, pa), (ib, pb) = mk(seqA), mk(seqB)
+    maxp = max(p.shape[1] for p in pa + pb)
+    c = F.Context(S.KITTI_W, S.KITTI_H, 2000, max_batch=T, max_points=maxp)
+    try:
+        prm = F.make_depth_params(bf=S.KITTI_BF)
+        A = F.RgblBatch(c, ia, pa, seqA.P, prm, pinned=False); B = F.RgblBatch(c, ib, pb, seqB.P, prm, pinned=False)
+        A.upload(); A.process_resident(); refA = A.track(seqA.pose(0), *TD.CAM, th=15.0)
+        B.upload(); B.process_resident(); refB = B.track(seqB.pose(0), *TD.CAM, th=15.0)
+        for _ in range(3):
+            A.upload(); A.process_resident()
+            A.track_begin(seqA.pose(0), *TD.CAM, th=15.0)
+            with pytest.raises(Exception):
+                A.track_begin(seqA.pose(0), *TD.CAM, th=15.0)       # one chain at a time
+            B.upload(); nB = B.process_resident().copy()            # overwrites every frame buffer of the context
+            gotA = A.track_end()
+            B.track_begin(seqB.pose(0), *TD.CAM, th=15.0)
+            outB = B.download()                                     # D2H of B's frame outputs while B's chain runs
+            gotB = B.track_end()
+            for got, ref in ((gotA, refA), (gotB, refB)):
+                assert np.array_equal(got[0], ref[0]) and (got[1] == ref[1]).all() and (got[2] == ref[2]).all()
+            assert [len(o[0]) for o in outB] == list(nB)
+        with pytest.raises(Exception):
+            A.track_end()                                           # nothing in flight
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("ratio,bits,check", [(0.7, 6, True), (0.9, 4, True), (0.6, 7, False)])
 def test_search_by_bow(ctx, seq_frames, ratio, bits, check):
     seq, frames, sf = seq_frames

@@ -3,6 +3,8 @@
 // gathers them); all compute runs on the context's CUDA device.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -485,26 +487,38 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
     // the 64x48 grids do not depend on the poses: all frames in one launch (one CTA per frame)
     f.n = t.s_nsel; f.keys = t.s_kps;
     launch_grid_build_batch(cs, f, nF, cap, t.b_cell_start, t.b_csr_idx, t.b_kp_cell);
+    // RGBL_CHAIN_TIMING=1: CUDA events between the launches of the middle frame (warm, in-stream kernel times; stderr at _end)
+    static const bool chain_timing = std::getenv("RGBL_CHAIN_TIMING") != nullptr;
+    static cudaEvent_t tev[8] = {};
+    if (chain_timing && !tev[0]) for (auto& e : tev) cudaEventCreate(&e);
     for (int k = 1; k < nF; ++k) {
+        const bool tm = chain_timing && k == std::max(1, nF / 2);
         const size_t lo = (size_t)(k - 1) * cap, cu = (size_t)k * cap;
         const float* last_pose = t.ch_poses + 7 * (k - 1);
+        if (tm) cudaEventRecord(tev[0], cs);
         launch_chain_prep(cs, t.s_kps + lo, t.s_depth + lo, t.s_nsel + (k - 1), last_pose, last_pose, f, mono, cap,
                           t.q_u8a, t.q_f3a, t.q_i, t.q_f[0], t.q_u8b, d_flags);
         f.n = t.s_nsel + k; f.keys = t.s_kps + cu; f.uright = t.s_uright + cu; f.desc = t.s_desc + cu * 32;
         const int* cell_start = t.b_cell_start + (size_t)k * (kGridCols * kGridRows + 1);
         const int* csr_idx = t.b_csr_idx + cu;
+        if (tm) cudaEventRecord(tev[1], cs);
         CU(cudaMemsetAsync(t.state, 0, cap, cs));
+        if (tm) cudaEventRecord(tev[2], cs);
         SearchLastParams prm{};
         prm.th = th; prm.check_orientation = 1; prm.cur_pose_dev = last_pose; prm.flags_dev = d_flags;
         LastFrameDev lf{cap, t.q_u8a, t.q_f3a, t.s_desc + lo * 32, t.q_i, t.q_f[0], t.q_u8b};
         launch_search_last(cs, f, cell_start, csr_idx, lf, prm, ms, t.state, t.match, d_nm + k);
+        if (tm) cudaEventRecord(tev[3], cs);
         launch_chain_edges(cs, f.keys, f.uright, f.n, t.match, t.q_f3a, f, t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne);
+        if (tm) cudaEventRecord(tev[4], cs);
         PoseProblemDev p{};
         p.n = 0; p.n_dev = d_ne; p.pose_in_dev = last_pose;
         p.xw = t.e_xw; p.obs = t.e_obs; p.inv_sigma2 = t.e_info; p.stereo = t.e_st;
         p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf;
         launch_pose_optimize(cs, p, t.pose_work, t.e_lvl, t.e_out, t.ch_poses + 7 * k, d_ni + k);
+        if (tm) cudaEventRecord(tev[5], cs);
     }
+    if (chain_timing) c->chain_timing_ev = tev;
     if (c->prof_on) CU(cudaEventRecord(c->ev_chain_e, cs));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_chain_f + 7, t.ch_poses, (size_t)nF * 7 * sizeof(float), cudaMemcpyDeviceToHost, cs));
@@ -524,6 +538,12 @@ int rgbl_resident_track_end(rgbl_ctx* ctx, float* poses_out, int* n_matches, int
     c->chain_pending = false;
     CU(cudaStreamSynchronize(c->st_trk));
     const int nF = c->chain_frames;
+    if (c->chain_timing_ev) {
+        const cudaEvent_t* e = static_cast<const cudaEvent_t*>(c->chain_timing_ev);
+        const char* names[5] = {"chain_prep", "memset_state", "search_last(collect+resolve)", "chain_edges", "pose_optimize"};
+        for (int i = 0; i < 5; ++i) { float ms = 0; if (cudaEventElapsedTime(&ms, e[i], e[i + 1]) == cudaSuccess) std::fprintf(stderr, "[chain timing] %-30s %8.2f us\n", names[i], ms * 1e3f); }
+        cudaGetLastError();
+    }
     std::memcpy(poses_out, c->h_chain_f + 7, (size_t)nF * 7 * sizeof(float));
     std::memcpy(n_matches, c->h_chain_i, (size_t)nF * sizeof(int));
     std::memcpy(n_inliers, c->h_chain_i + nF, (size_t)nF * sizeof(int));

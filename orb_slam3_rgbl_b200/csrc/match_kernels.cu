@@ -275,21 +275,180 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
                                                        const float* __restrict__ f_angle, uint8_t* __restrict__ state,
                                                        int* __restrict__ minq, int* __restrict__ choice,
                                                        uint8_t* __restrict__ resolved, int* __restrict__ match,
-                                                       int* __restrict__ n_matches, int* __restrict__ rounds_out) {
-    __shared__ int s_unresolved;
+                                                       int* __restrict__ n_matches, int* __restrict__ rounds_out, int dyn_bytes) {
+    extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int hist[kHistoLength];
     __shared__ int keep_bin[3];
     __shared__ int s_nm;
+    __shared__ int s_wsum[32];
+    __shared__ int s_total;
+#ifdef RESOLVE_DEBUG
+    __shared__ long long s_rt[12];
+#endif
     const int tid = threadIdx.x;
+#ifdef RESOLVE_DEBUG
+    long long tq[6]; tq[0] = clock64();
+#define RQ(i) tq[i] = clock64()
+#else
+#define RQ(i)
+#endif
     if (n_q_dev) n_q = *n_q_dev;
     const int n_f = *f.n;
     for (int i = tid; i < n_f; i += 1024) match[i] = -1;
-    for (int q = tid; q < n_q; q += 1024) { choice[q] = -1; resolved[q] = (list_n[q] == 0); }
+    for (int q = tid; q < n_q; q += 1024) choice[q] = -1;
     if (tid == 0) s_nm = 0;
+
+    // ---- working set into shared memory: the rounds below are a chain of barriers around short dependent loads, so their
+    // cost is the latency of those loads; with the candidate entries (key, feature, octave), the feature states and the
+    // proposal table on chip a round costs a few hundred cycles instead of several L2 round trips.  Exclusive scan of the
+    // list lengths -> entry offsets; falls back to the global-memory rounds when the problem does not fit.
+    const int per = (n_q + 1023) >> 10;
+    const int qb = min(n_q, tid * per), qe = min(n_q, qb + per);
+    int mine = 0;
+    for (int q = qb; q < qe; ++q) mine += list_n[q];
+    int incl = mine;
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int v = s_wsum[lane], w = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            s_wsum[lane] = w - v;
+            if (lane == 31) s_total = w;
+        }
+        __syncthreads();
+        incl += s_wsum[warp];
+    }
+    RQ(1);
+    const int E = s_total;
+    const size_t need = (size_t)4 * n_f + (size_t)4 * (n_q + 1) + (size_t)8 * (E + 4) + (size_t)4 * n_q + (size_t)n_f + (size_t)2 * n_q + 64;
+    const bool on_chip = n_f <= 65535 && need <= (size_t)dyn_bytes;
+    int rounds = 0, nm_local = 0;          // nm_local: accepted minus rotation-rejected matches of this thread
+    int* ch = choice;                      // chosen feature per query (shared memory on the on-chip path)
+    uint8_t* bins = resolved;              // rotation bin per query (the global flags array is free after the rounds)
+    if (on_chip) {
+        // entry = key << 32 | octave << 16 | feature: one 64-bit load per candidate
+        unsigned long long* s_ent = reinterpret_cast<unsigned long long*>(dyn);
+        int* s_minq = reinterpret_cast<int*>(s_ent + E + 4);
+        int* s_off = s_minq + n_f;
+        int* s_choice = s_off + n_q + 1;
+        uint8_t* s_state = reinterpret_cast<uint8_t*>(s_choice + n_q);
+        uint8_t* s_res = s_state + n_f;    // bit 0: resolved, bit 1: the query's point has observations
+        uint8_t* s_bin = s_res + n_q;
+        ch = s_choice; bins = s_bin;
+        {
+            int o = incl - mine;
+            for (int q = qb; q < qe; ++q) { s_off[q] = o; o += list_n[q]; }
+            if (tid == 1023) s_off[n_q] = E;
+        }
+        for (int i = tid; i < n_f; i += 1024) s_state[i] = state[i];
+        if (tid < 4) s_ent[E + tid] = 0xffffffff00000000ull;     // sentinels: worst key, feature 0
+        __syncthreads();
+        for (int q = tid; q < n_q; q += 1024) {
+            const int o = s_off[q], n = s_off[q + 1] - o;
+            s_res[q] = (uint8_t)((n == 0 ? 1 : 0) | (obs_pos[q] ? 2 : 0));
+            s_choice[q] = -1;
+            const uint32_t* l = lists + (size_t)q * list_cap;
+            for (int k = 0; k < n; ++k) {
+                const uint32_t key = l[k];
+                const int ft = csr_idx[key & kPosMask];
+                const unsigned oc = (mode == 1) ? (unsigned)f.keys[ft].octave & 0xffu : 0u;
+                s_ent[o + k] = ((unsigned long long)key << 32) | (oc << 16) | (unsigned)ft;
+            }
+        }
+        __syncthreads();
+        RQ(2);
+        // The slowest thread of a round is the one with the longest list and every entry costs a chain of dependent
+        // shared-memory loads (entry -> state -> proposal): four entries are in flight at a time.
+        for (;;) {
+            bool any_unresolved = false;
+            for (int i = tid; i < n_f; i += 1024) s_minq[i] = 0x7fffffff;
+            __syncthreads();
+            for (int q = tid; q < n_q; q += 1024) {
+                if (s_res[q] & 1) continue;
+                const int e = s_off[q + 1];
+                for (int k = s_off[q]; k < e; k += 4) {
+                    unsigned long long en[4]; uint8_t st[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) en[u] = s_ent[k + u];                 // 4 sentinel slots follow the last entry
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) st[u] = s_state[(unsigned)en[u] & 0xffffu];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (k + u < e && st[u] != 1) atomicMin(&s_minq[(unsigned)en[u] & 0xffffu], q);
+                }
+            }
+            __syncthreads();
+            for (int q = tid; q < n_q; q += 1024) {
+                const uint8_t flags = s_res[q];
+                if (flags & 1) continue;
+                uint32_t best = 0xffffffffu, best2 = 0xffffffffu;
+                int lvl = -1, lvl2 = -1, fb = -1;
+                bool depends_ok = true;
+                const int e = s_off[q + 1];
+                for (int k = s_off[q]; k < e; k += 4) {
+                    unsigned long long en[4]; uint8_t st[4]; int mq[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) en[u] = s_ent[k + u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) st[u] = s_state[(unsigned)en[u] & 0xffffu];
+                    if (mode >= 1) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) mq[u] = s_minq[(unsigned)en[u] & 0xffffu];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (k + u >= e || st[u] == 1) continue;
+                        const uint32_t key = (uint32_t)(en[u] >> 32);
+                        const int ft = (int)((unsigned)en[u] & 0xffffu);
+                        if (mode >= 1 && mq[u] != q) depends_ok = false;
+                        if (mode == 0) {
+                            if (key < best) { best = key; fb = ft; }
+                        } else {
+                            const int oc = (int)(((unsigned)en[u] >> 16) & 0xffu);
+                            if (key < best) { best2 = best; lvl2 = lvl; best = key; lvl = oc; fb = ft; }
+                            else if (key < best2) { best2 = key; lvl2 = oc; }
+                        }
+                    }
+                }
+                if (best == 0xffffffffu) { s_res[q] = flags | 1; continue; }
+                const bool final_ok = (mode == 0) ? (s_minq[fb] == q) : depends_ok;
+                if (!final_ok) { any_unresolved = true; continue; }
+                s_res[q] = flags | 1;
+                const int bd = (int)(best >> 20);
+                bool accept = bd <= th_accept;
+                if (mode == 1 && accept) {
+                    const int bd2 = (best2 == 0xffffffffu) ? 256 : (int)(best2 >> 20);
+                    if (lvl == lvl2 && (float)bd > __fmul_rn(nn_ratio, (float)bd2)) accept = false;
+                }
+                if (mode == 2 && accept) {            // SearchByBoW: bestDist1 < mfNNratio * bestDist2 (src/ORBmatcher.cc:324)
+                    const int bd2 = (best2 == 0xffffffffu) ? 256 : (int)(best2 >> 20);
+                    accept = (float)bd < __fmul_rn(nn_ratio, (float)bd2);
+                }
+                if (accept) {
+                    s_choice[q] = fb;
+                    if (flags & 2) s_state[fb] = 1; else if (s_state[fb] == 0) s_state[fb] = 2;
+                    ++nm_local;
+                }
+            }
+            ++rounds;
+#ifdef RESOLVE_DEBUG
+            if (tid == 0 && rounds <= 12) s_rt[rounds - 1] = clock64() - tq[2];
+#endif
+            if (!__syncthreads_or(any_unresolved)) break;      // barrier + block-wide "someone is still waiting"
+        }
+        RQ(3);
+        for (int i = tid; i < n_f; i += 1024) state[i] = s_state[i];
+        __syncthreads();
+    } else {
+    for (int q = tid; q < n_q; q += 1024) resolved[q] = (list_n[q] == 0);
     __syncthreads();
-    int rounds = 0;
     for (;;) {
-        if (tid == 0) s_unresolved = 0;
+        bool any_unresolved = false;
         for (int i = tid; i < n_f; i += 1024) minq[i] = 0x7fffffff;
         __syncthreads();
         for (int q = tid; q < n_q; q += 1024) {
@@ -330,7 +489,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             if (best == 0xffffffffu) { resolved[q] = 1; continue; }
             const int fb = csr_idx[best & kPosMask];
             const bool final_ok = (mode == 0) ? (minq[fb] == q) : depends_ok;
-            if (!final_ok) { atomicAdd(&s_unresolved, 1); continue; }
+            if (!final_ok) { any_unresolved = true; continue; }
             resolved[q] = 1;
             const int bd = (int)(best >> 20);
             bool accept = bd <= th_accept;
@@ -345,53 +504,70 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             if (accept) {
                 choice[q] = fb;
                 if (obs_pos[q]) state[fb] = 1; else if (state[fb] == 0) state[fb] = 2;
-                atomicAdd(&s_nm, 1);
+                ++nm_local;
             }
         }
-        __syncthreads();
         ++rounds;
-        if (s_unresolved == 0) break;
-        __syncthreads();
+        if (!__syncthreads_or(any_unresolved)) break;
+    }
     }
     // owner of a feature = the last (highest-index) query that chose it
-    for (int q = tid; q < n_q; q += 1024) if (choice[q] >= 0) atomicMax(&match[choice[q]], q);
+    for (int q = tid; q < n_q; q += 1024) if (ch[q] >= 0) atomicMax(&match[ch[q]], q);
     if (mode != 1 && check_orientation) {
         for (int b = tid; b < kHistoLength; b += 1024) hist[b] = 0;
         __syncthreads();
         const float factor = 1.0f / kHistoLength;
-        for (int q = tid; q < n_q; q += 1024) {
-            if (choice[q] < 0) continue;
-            float rot = __fsub_rn(q_angle[q], f_angle ? f_angle[choice[q]] : f.keys[choice[q]].angle);
-            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-            int bin = (int)roundf(__fmul_rn(rot, factor));
-            if (bin == kHistoLength) bin = 0;
-            atomicAdd(&hist[bin], 1);
+        for (int q0 = 0; q0 < n_q; q0 += 1024) {          // uniform trip count: the warp-level vote below needs all lanes
+            const int q = q0 + tid;
+            const int c = q < n_q ? ch[q] : -1;
+            const bool valid = c >= 0;
+            int bin = 64 + (tid & 31);                      // unique key for lanes without a match
+            if (valid) {
+                float rot = __fsub_rn(q_angle[q], f_angle ? f_angle[c] : f.keys[c].angle);
+                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                bin = (int)roundf(__fmul_rn(rot, factor));
+                if (bin == kHistoLength) bin = 0;
+                bins[q] = (uint8_t)bin;
+            }
+            // nearly every match falls into one or two bins: aggregate equal bins inside the warp, one atomic per group
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (valid && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
         }
         __syncthreads();
-        if (tid == 0) {       // ORBmatcher::ComputeThreeMaxima, src/ORBmatcher.cc:2012-2053
+        if (tid < 32) {       // ORBmatcher::ComputeThreeMaxima, src/ORBmatcher.cc:2012-2053 (lane 0; the bins are preloaded by the warp)
+            const int mine_h = tid < kHistoLength ? hist[tid] : 0;
             int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+#pragma unroll
             for (int i = 0; i < kHistoLength; ++i) {
-                const int s = hist[i];
-                if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
-                else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
-                else if (s > max3) { max3 = s; i3 = i; }
+                const int sv = __shfl_sync(0xffffffffu, mine_h, i);
+                if (sv > max1) { max3 = max2; max2 = max1; max1 = sv; i3 = i2; i2 = i1; i1 = i; }
+                else if (sv > max2) { max3 = max2; max2 = sv; i3 = i2; i2 = i; }
+                else if (sv > max3) { max3 = sv; i3 = i; }
             }
             if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
             else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) i3 = -1;
-            keep_bin[0] = i1; keep_bin[1] = i2; keep_bin[2] = i3;
+            if (tid == 0) { keep_bin[0] = i1; keep_bin[1] = i2; keep_bin[2] = i3; }
         }
         __syncthreads();
         for (int q = tid; q < n_q; q += 1024) {
-            if (choice[q] < 0) continue;
-            float rot = __fsub_rn(q_angle[q], f_angle ? f_angle[choice[q]] : f.keys[choice[q]].angle);
-            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-            int bin = (int)roundf(__fmul_rn(rot, factor));
-            if (bin == kHistoLength) bin = 0;
-            if (bin != keep_bin[0] && bin != keep_bin[1] && bin != keep_bin[2]) { match[choice[q]] = -2; atomicSub(&s_nm, 1); }
+            const int c = ch[q];
+            if (c < 0) continue;
+            const int bin = bins[q];
+            if (bin != keep_bin[0] && bin != keep_bin[1] && bin != keep_bin[2]) { match[c] = -2; --nm_local; }
         }
+    }
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nm_local += __shfl_down_sync(0xffffffffu, nm_local, o);
+        if ((tid & 31) == 0 && nm_local != 0) atomicAdd(&s_nm, nm_local);
     }
     __syncthreads();
     if (tid == 0) { *n_matches = s_nm; if (rounds_out) *rounds_out = rounds; }
+#ifdef RESOLVE_DEBUG
+    if (tid == 0) printf("resolve mode=%d n_q=%d n_f=%d E=%d on_chip=%d rounds=%d nm=%d | scan=%lld fill=%lld rounds=%lld epilogue=%lld\n", mode, n_q, n_f, E, (int)on_chip, rounds, s_nm,
+                         tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], clock64() - tq[3]);
+    if (tid == 0 && on_chip) { for (int i = 0; i < min(rounds, 12); ++i) printf(" r%d=%lld", i + 1, s_rt[i]); printf("\n"); }
+#endif
 }
 
 // ---- Frame::isInFrustum for a list of local map points ----------------------------------------------
@@ -588,6 +764,19 @@ __global__ void __launch_bounds__(1024) chain_edges_kernel(const rgbl_keypoint* 
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------
+// dynamic shared memory of resolve_kernel (opt-in above 48 KB, set once per device)
+static int resolve_dyn_bytes() {
+    constexpr int kBytes = 160 * 1024;
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !done[dev]) {
+        cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
+        done[dev] = true;
+    }
+    return kBytes;
+}
+
 void launch_grid_build(cudaStream_t st, const FrameDev& f, int* cell_start, int* csr_idx, int* kp_cell) {
     grid_build_kernel<<<1, 1024, 0, st>>>(f, 0, cell_start, csr_idx, kp_cell);
 }
@@ -601,16 +790,16 @@ void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_star
                         const SearchLastParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches) {
     if (lf.n <= 0) return;
     search_last_collect_kernel<<<(lf.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lf, prm, s.lists, s.list_cap, s.list_n, s.overflow);
-    resolve_kernel<<<1, 1024, 0, st>>>(0, lf.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lf.obs_pos, lf.angle, 0.f,
-                                       prm.check_orientation, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds);
+    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, lf.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lf.obs_pos, lf.angle, 0.f,
+                                       prm.check_orientation, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes());
 }
 
 void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LocalPointsDev& lp,
                          const SearchLocalParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches) {
     if (lp.n <= 0) return;
     search_local_collect_kernel<<<(lp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
-    resolve_kernel<<<1, 1024, 0, st>>>(1, lp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lp.obs_pos, nullptr, prm.nn_ratio,
-                                       0, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds);
+    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(1, lp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lp.obs_pos, nullptr, prm.nn_ratio,
+                                       0, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes());
 }
 
 void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q_feat, const int* q_cbeg, const int* q_cend,
@@ -620,16 +809,16 @@ void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q
     if (n_q <= 0) return;
     bow_collect_kernel<<<(n_q + 7) / 8, 256, 0, st>>>(n_q, q_feat, q_cbeg, q_cend, kf_desc, f_desc, f_node_feat, keep_max, s.lists, s.list_cap,
                                                     s.list_n, s.overflow);
-    resolve_kernel<<<1, 1024, 0, st>>>(2, n_q, nullptr, f, f_node_feat, s.lists, s.list_cap, s.list_n, obs_pos, q_angle, nn_ratio,
-                                       check_orientation, 50 /* TH_LOW */, f_angle, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds);
+    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(2, n_q, nullptr, f, f_node_feat, s.lists, s.list_cap, s.list_n, obs_pos, q_angle, nn_ratio,
+                                       check_orientation, 50 /* TH_LOW */, f_angle, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes());
 }
 
 void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const RelocPointsDev& rp,
                          const SearchRelocParams& prm, const uint8_t* obs_pos, MatchScratch s, uint8_t* state, int* match, int* n_matches) {
     if (rp.n <= 0) return;
     search_reloc_collect_kernel<<<(rp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, rp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
-    resolve_kernel<<<1, 1024, 0, st>>>(0, rp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, obs_pos, rp.angle, 0.f,
-                                       prm.check_orientation, prm.orb_dist, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds);
+    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, rp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, obs_pos, rp.angle, 0.f,
+                                       prm.check_orientation, prm.orb_dist, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes());
 }
 
 void launch_chain_prep(cudaStream_t st, const rgbl_keypoint* kps, const float* depth, const int* n_ptr, const float* last_pose,

@@ -46,37 +46,6 @@ __device__ __forceinline__ void se3_map(const Se3d& T, const double p[3], double
     out[0] += T.tx; out[1] += T.ty; out[2] += T.tz;
 }
 
-template <int I>
-__device__ __forceinline__ void quat_from_matrix_case(const double R[3][3], Se3d& q) {
-    constexpr int J = (I + 1) % 3, K = (J + 1) % 3;
-    double t = sqrt(R[I][I] - R[J][J] - R[K][K] + 1.0);
-    double v[3];
-    v[I] = 0.5 * t;
-    t = 0.5 / t;
-    q.qw = (R[K][J] - R[J][K]) * t;
-    v[J] = (R[J][I] + R[I][J]) * t;
-    v[K] = (R[K][I] + R[I][K]) * t;
-    q.qx = v[0]; q.qy = v[1]; q.qz = v[2];
-}
-
-// Eigen quaternion-from-rotation-matrix; every array index is a compile-time constant (registers, no local memory)
-__device__ __forceinline__ void quat_from_matrix(const double R[3][3], Se3d& q) {
-    double t = R[0][0] + R[1][1] + R[2][2];
-    if (t > 0) {
-        t = sqrt(t + 1.0);
-        q.qw = 0.5 * t;
-        t = 0.5 / t;
-        q.qx = (R[2][1] - R[1][2]) * t; q.qy = (R[0][2] - R[2][0]) * t; q.qz = (R[1][0] - R[0][1]) * t;
-    } else {
-        int i = 0;
-        if (R[1][1] > R[0][0]) i = 1;
-        if (i == 0) { if (R[2][2] > R[0][0]) i = 2; } else { if (R[2][2] > R[1][1]) i = 2; }
-        if (i == 0) quat_from_matrix_case<0>(R, q);
-        else if (i == 1) quat_from_matrix_case<1>(R, q);
-        else quat_from_matrix_case<2>(R, q);
-    }
-}
-
 // Taylor coefficients in th^2 (k = 0..8), generated from exact rationals: sin(th/2)/th, cos(th/2), (1-cos th)/th^2, (th-sin th)/th^3
 __device__ constexpr double kQs[9] = {0.5, -0.020833333333333332, 0.00026041666666666666, -1.5500992063492063e-06, 5.382288910934745e-09, -1.2232474797578965e-11, 1.9603324996120133e-14, -2.333729166204778e-17, 2.1449716601146855e-20};   // (-1)^k / (2 4^k (2k+1)!)
 __device__ constexpr double kQc[9] = {1.0, -0.125, 0.0026041666666666665, -2.170138888888889e-05, 9.68812003968254e-08, -2.691144455467372e-10, 5.096864498991235e-13, -7.001187498614334e-16, 7.292903644389931e-19};   // (-1)^k / (4^k (2k)!)
@@ -88,7 +57,9 @@ __device__ constexpr double kC[9] = {0.16666666666666666, -0.008333333333333333,
 // normalises.  The same rotation in closed form is q = (omega * sin(th/2)/th, cos(th/2)).  All four scalar functions are even
 // in th, i.e. power series in th^2: for th^2 < 0.25 (every LM step of a tracking problem) they are evaluated as degree-8
 // Horner polynomials in th^2 (truncation < 1e-20, and no th - sin th cancellation), which takes sqrt, sincos and three
-// divisions off the serial FP64 dependency chain; larger steps use sincos.  Equal to g2o's value up to rounding.
+// divisions off the serial FP64 dependency chain; larger steps use sincos.  Equal to g2o's value up to rounding (for
+// th < 1e-5 g2o switches to R = V = I + Omega + Omega^2, a first-order form that differs from the exact series used here by
+// < 1e-10, far inside the parity tolerance).
 __device__ __forceinline__ void se3_exp(const double* u, Se3d& T) {
     const double om[3] = {u[0], u[1], u[2]}, up[3] = {u[3], u[4], u[5]};
     const double t = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
@@ -269,8 +240,8 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
     __shared__ double red[kPoseWarps * kAcc];
     __shared__ double acc[kAcc];
     __shared__ Se3d s_est, s_init, s_cand[kMaxTrials];
-    __shared__ double s_cx[kMaxTrials][6], s_lambda, s_ni, s_rho, s_current, s_ini, s_temp;
-    __shared__ int s_nbad_lm, s_qmax, s_ok, s_cok[kMaxTrials], s_continue;
+    __shared__ double s_cinv[kMaxTrials], s_lambda, s_ni, s_current, s_ini;
+    __shared__ int s_nbad_lm, s_ok, s_cok[kMaxTrials], s_continue;
     const int tid = threadIdx.x, n = p.n_dev ? *p.n_dev : p.n;
 #ifdef POSE_TIMING
     long long tm[6] = {0, 0, 0, 0, 0, 0}; int tc[3] = {0, 0, 0}; long long t0_ = clock64(), tA_;
@@ -405,24 +376,29 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
 #ifdef POSE_TIMING
             tc[0]++;
 #endif
-            if (tid == 0) {
-                s_current = acc[27]; s_ini = acc[27]; s_temp = acc[27];
-                if (iter == 0) {
-                    double mx = 0; int t = 0;
-                    for (int i = 0; i < 6; ++i) { mx = fmax(fabs(acc[t]), mx); t += 6 - i; }
-                    s_lambda = 1e-5 * mx; s_ni = 2; s_nbad_lm = 0;
-                }
-                s_rho = 0; s_qmax = 0;
-            }
-            __syncthreads();
             // ---- LM trials.  A rejected trial only changes lambda (x nu, nu doubling), never H, b or the estimate, so the damped solves of all (<= 10) possible trials of this iteration
             // are independent: lane 0 of warp w solves trial w while the other warps would idle anyway, and a retry then
             // costs one error evaluation instead of a serial solve + exp. ----
             TM_START();
             if ((tid & 31) == 0 && (tid >> 5) < kMaxTrials) {
                 const int w = tid >> 5;
-                double lam = s_lambda, ni = s_ni;
-                for (int m = 0; m < w; ++m) { lam *= ni; ni *= 2; }
+                // lambda of trial w = lambda * nu * 2nu * ... (w factors); nu is a power of two, so this is one exponent shift
+                // (lambda0 = 1e-5 * max diag(H) and nu = 2 at iteration 0 of a round: every solver lane derives them itself
+                // from the reduced system, thread 0 also publishes them, so no barrier is needed before this stage)
+                double lam_base, ni_base;
+                if (iter == 0) {
+                    double mx = 0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) mx = fmax(fabs(acc[i * 6 - (i * (i - 1)) / 2]), mx);
+                    lam_base = 1e-5 * mx; ni_base = 2;
+                } else {
+                    lam_base = s_lambda; ni_base = s_ni;
+                }
+                if (w == 0) {
+                    s_current = acc[27]; s_ini = acc[27];
+                    if (iter == 0) { s_lambda = lam_base; s_ni = 2; s_nbad_lm = 0; }
+                }
+                const double lam = scalbn(lam_base, w * ilogb(ni_base) + (w * (w - 1)) / 2);
                 double x[6] = {0, 0, 0, 0, 0, 0};
 #ifdef POSE_TIMING
                 const long long ts_ = clock64();
@@ -431,8 +407,12 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
 #ifdef POSE_TIMING
                 tm[5] += clock64() - ts_;
 #endif
+                // denominator of the gain ratio, x^T (lambda x + b) + 1e-3 (optimization_algorithm_levenberg.cpp:129-135):
+                // known here, so its reciprocal is off the serial accept/reject path
+                double scale = 0;
 #pragma unroll
-                for (int i = 0; i < 6; ++i) s_cx[w][i] = x[i];
+                for (int i = 0; i < 6; ++i) scale += x[i] * (lam * x[i] + acc[21 + i]);
+                s_cinv[w] = 1.0 / (scale + 1e-3);
                 Se3d E, Tn;
                 se3_exp(x, E);
                 se3_mul(E, s_est, Tn);
@@ -452,28 +432,36 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
                     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
                     if (lane == 0) red[warp] = x;
                     __syncthreads();
-                    if (tid == 0) {
-                        double s = 0;
-                        for (int w = 0; w < kPoseWarps; ++w) s += red[w];
-                        double temp = s;
-                        if (!s_cok[trial]) temp = DBL_MAX;
-                        double rho = s_current - temp;
-                        double scale = 0;
-                        for (int j = 0; j < 6; ++j) scale += s_cx[trial][j] * (s_lambda * s_cx[trial][j] + acc[21 + j]);
-                        scale += 1e-3;
-                        rho /= scale;
-                        if (rho > 0 && isfinite(temp)) {
-                            const double r21 = 2 * rho - 1;
-                            double alpha = 1. - r21 * r21 * r21;
-                            alpha = fmin(alpha, 2. / 3.);
-                            const double sf = fmax(1. / 3., alpha);
-                            s_lambda *= sf; s_ni = 2; s_current = temp; s_est = s_cand[trial];
-                        } else {
-                            s_lambda *= s_ni; s_ni *= 2;          // the estimate is restored = left untouched
+                    if (warp == 0) {
+                        double s = lane < kPoseWarps ? red[lane] : 0.0;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+                        if (lane == 0) {
+                            double temp = s;
+                            if (!s_cok[trial]) temp = DBL_MAX;
+                            const double rho = (s_current - temp) * s_cinv[trial];
+                            if (rho > 0 && isfinite(temp)) {
+                                const double r21 = 2 * rho - 1;
+                                double alpha = 1. - r21 * r21 * r21;
+                                alpha = fmin(alpha, 2. / 3.);
+                                const double sf = fmax(1. / 3., alpha);
+                                s_lambda *= sf; s_ni = 2; s_current = temp; s_est = s_cand[trial];
+                            } else {
+                                s_lambda *= s_ni; s_ni *= 2;          // the estimate is restored = left untouched
+                            }
+                            const int qmax = trial + 1;
+                            const int cont = (rho < 0 && qmax < kMaxTrials) ? 1 : 0;
+                            s_continue = cont;
+                            if (!cont) {                              // end of this LM iteration: g2o's stop tests
+                                int ok = 1;
+                                if (qmax == kMaxTrials || rho == 0) ok = 0;
+                                else {
+                                    if ((s_ini - s_current) * 1e3 < s_ini) s_nbad_lm += 1; else s_nbad_lm = 0;
+                                    if (s_nbad_lm >= 3) ok = 0;
+                                }
+                                s_ok = ok;
+                            }
                         }
-                        s_rho = rho;
-                        s_qmax += 1;
-                        s_continue = (rho < 0 && s_qmax < kMaxTrials) ? 1 : 0;
                     }
                     __syncthreads();
                 }
@@ -483,16 +471,6 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
 #endif
                 if (!s_continue) break;
             }
-            if (tid == 0) {
-                int ok = 1;
-                if (s_qmax == kMaxTrials || s_rho == 0) ok = 0;
-                else {
-                    if ((s_ini - s_current) * 1e3 < s_ini) s_nbad_lm += 1; else s_nbad_lm = 0;
-                    if (s_nbad_lm >= 3) ok = 0;
-                }
-                s_ok = ok;
-            }
-            __syncthreads();
         }
         // ---- classification (src/Optimizer.cc:1014-1100) ----
         {

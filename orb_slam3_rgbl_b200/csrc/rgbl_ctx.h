@@ -128,6 +128,7 @@ struct Ctx {
     float* h_chain_f = nullptr;  // pinned: pose0 (7) | poses (max_batch * 7)
     int* h_chain_i = nullptr;    // pinned: n_matches | n_inliers | overflow
     size_t h_chain_cap = 0;
+    const void* chain_timing_ev = nullptr;   // RGBL_CHAIN_TIMING development aid
 
     int last_frames = 0;         // frames valid in the device buffers
     int resident_frames = 0, resident_max_pts = 0;

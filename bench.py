@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="frames per step (per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi-sequences", type=int, default=4, help="extra capacity figure: independent sequences tracked concurrently on one GPU (N=1 only; 0/1 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -297,6 +298,45 @@ def main():
     e2e_fps = world * T * args.steps / (e2e_ms * 1e-3)
     d2h = batch.d2h_bytes()
 
+    # ---- capacity: several independent sequences on ONE GPU (extra information, not the headline: configs[1] is one
+    # sequence per GPU).  A single sequence is bound by the latency of its serial tracking chain (one SM busy); chains of
+    # different sequences run side by side on their own streams until the frame construction saturates the device.
+    multi = None
+    if world == 1 and args.multi_sequences > 1:
+        nS = args.multi_sequences
+        ctxs, batches, pose0s = [ctx], [batch], [pose0]
+        for sidx in range(1, nS):
+            im2, pc2, seq2 = make_batch_inputs(100 + sidx, T)
+            c2 = F.Context(S.KITTI_W, S.KITTI_H, 2000, max_batch=T, max_points=max(p.shape[1] for p in pc2), device=local_rank)
+            b2 = F.RgblBatch(c2, im2, pc2, seq2.P, prm, pinned=False)
+            b2.upload()
+            ctxs.append(c2); batches.append(b2); pose0s.append(seq2.pose(0))
+        batch.upload()
+
+        def multi_rounds(k):
+            pend = [False] * nS
+            for _ in range(k):
+                for i in range(nS):
+                    batches[i].process_resident()
+                    if pend[i]:
+                        batches[i].track_end()
+                    batches[i].track_begin(pose0s[i], *CAM, th=15.0); pend[i] = True
+            return [batches[i].track_end() for i in range(nS)]
+
+        multi_rounds(2)
+        torch.cuda.synchronize()
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        t0 = time.perf_counter()
+        res = multi_rounds(args.steps)
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0)
+        multi = {"sequences_per_gpu": nS, "value": nS * T * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_round": ms / args.steps,
+                 "timing": "host wall clock around K rounds with device synchronisation on both sides (several library streams)",
+                 "inliers_per_frame": [float(np.mean(r[2][1:])) for r in res]}
+        for c2 in ctxs[1:]:
+            c2.close()
+
     if rank == 0:
         # roofline of the dominant kernel (per-stage CUDA-event time / launches, measured above)
         levels = []
@@ -371,6 +411,7 @@ def main():
                 "clocks": clocks, "roofline": roofline, "roofline_frame_construction": roofline_streaming, "kernels": kernels, "latency_bound_stages": other,
                 "tracking": {"matches_per_frame": float(np.mean(nm[1:])), "inliers_per_frame": float(np.mean(ni[1:])),
                              "pose_x_error_m_last_frame": float(abs(poses[-1, 4] - seq.pose(T - 1)[4]))},
+                "multi_sequence_capacity": multi,
                 "host_quadtree_ms_per_step": prof["_host_quadtree_ms"] / args.steps,
                 "wall_ms_per_step": wall_ms / args.steps}
         if world == 1 and not args.no_cpu_baseline:

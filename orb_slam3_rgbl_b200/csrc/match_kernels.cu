@@ -282,8 +282,8 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
     __shared__ int s_nm;
     __shared__ int s_wsum[32];
     __shared__ int s_total;
+    __shared__ int s_cnt[2];
 #ifdef RESOLVE_DEBUG
-    __shared__ long long s_rt[12];
 #endif
     const int tid = threadIdx.x;
 #ifdef RESOLVE_DEBUG
@@ -294,8 +294,6 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
 #endif
     if (n_q_dev) n_q = *n_q_dev;
     const int n_f = *f.n;
-    for (int i = tid; i < n_f; i += 1024) match[i] = -1;
-    for (int q = tid; q < n_q; q += 1024) choice[q] = -1;
     if (tid == 0) s_nm = 0;
 
     // ---- working set into shared memory: the rounds below are a chain of barriers around short dependent loads, so their
@@ -325,127 +323,204 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
     }
     RQ(1);
     const int E = s_total;
-    const size_t need = (size_t)4 * n_f + (size_t)4 * (n_q + 1) + (size_t)8 * (E + 4) + (size_t)4 * n_q + (size_t)n_f + (size_t)2 * n_q + 64;
+    const size_t need = (size_t)12 * n_f + (size_t)4 * (n_q + 1) + (size_t)8 * (E + 4) + (size_t)12 * n_q + (size_t)n_f + (size_t)2 * n_q + 64;
     const bool on_chip = n_f <= 65535 && need <= (size_t)dyn_bytes;
+    const bool orient = mode != 1 && check_orientation;
     int rounds = 0, nm_local = 0;          // nm_local: accepted minus rotation-rejected matches of this thread
     int* ch = choice;                      // chosen feature per query (shared memory on the on-chip path)
     uint8_t* bins = resolved;              // rotation bin per query (the global flags array is free after the rounds)
+    int* mt = match;                       // match table (shared memory on the on-chip path, written out at the end)
     if (on_chip) {
-        // entry = key << 32 | octave << 16 | feature: one 64-bit load per candidate
+        // entry = key << 32 | rotation bin << 24 | octave << 16 | feature: one 64-bit load per candidate
         unsigned long long* s_ent = reinterpret_cast<unsigned long long*>(dyn);
         int* s_minq = reinterpret_cast<int*>(s_ent + E + 4);
-        int* s_off = s_minq + n_f;
+        int* s_match = s_minq + 2 * (size_t)n_f;        // after the two proposal tables
+        int* s_off = s_match + n_f;
         int* s_choice = s_off + n_q + 1;
-        uint8_t* s_state = reinterpret_cast<uint8_t*>(s_choice + n_q);
+        int* s_list = s_choice + n_q;                    // two compact lists of waiting queries
+        uint8_t* s_state = reinterpret_cast<uint8_t*>(s_list + 2 * (size_t)n_q);
         uint8_t* s_res = s_state + n_f;    // bit 0: resolved, bit 1: the query's point has observations
         uint8_t* s_bin = s_res + n_q;
-        ch = s_choice; bins = s_bin;
+        ch = s_choice; bins = s_bin; mt = s_match;
         {
             int o = incl - mine;
             for (int q = qb; q < qe; ++q) { s_off[q] = o; o += list_n[q]; }
             if (tid == 1023) s_off[n_q] = E;
         }
-        for (int i = tid; i < n_f; i += 1024) s_state[i] = state[i];
-        if (tid < 4) s_ent[E + tid] = 0xffffffff00000000ull;     // sentinels: worst key, feature 0
+        for (int i = tid; i < n_f; i += 1024) { s_state[i] = state[i]; s_match[i] = -1; }
+        if (tid < 4) s_ent[E + tid] = 0xffffffff00000000ull;     // padding: worst key, feature 0
         __syncthreads();
         for (int q = tid; q < n_q; q += 1024) {
-            const int o = s_off[q], n = s_off[q + 1] - o;
-            s_res[q] = (uint8_t)((n == 0 ? 1 : 0) | (obs_pos[q] ? 2 : 0));
+            s_res[q] = (uint8_t)((s_off[q + 1] == s_off[q] ? 1 : 0) | (obs_pos[q] ? 2 : 0));
             s_choice[q] = -1;
-            const uint32_t* l = lists + (size_t)q * list_cap;
-            for (int k = 0; k < n; ++k) {
-                const uint32_t key = l[k];
-                const int ft = csr_idx[key & kPosMask];
-                const unsigned oc = (mode == 1) ? (unsigned)f.keys[ft].octave & 0xffu : 0u;
-                s_ent[o + k] = ((unsigned long long)key << 32) | (oc << 16) | (unsigned)ft;
+        }
+        // one thread per ENTRY (a query's list may hold dozens of candidates: a per-query loop would serialise its chains of
+        // dependent global loads list -> csr -> keypoint); the owning query is found by bisection of the offsets
+        const float factor = 1.0f / kHistoLength;
+        for (int en = tid; en < E; en += 1024) {
+            int lo = 0, hi = n_q;                          // largest q with s_off[q] <= en
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= en) lo = mid; else hi = mid; }
+            const int q = lo;
+            const uint32_t key = lists[(size_t)q * list_cap + (en - s_off[q])];
+            const int ft = csr_idx[key & kPosMask];
+            unsigned oc = 0, bin = 0;
+            if (mode == 1) oc = (unsigned)f.keys[ft].octave & 0xffu;
+            if (orient) {
+                float rot = __fsub_rn(q_angle[q], f_angle ? f_angle[ft] : f.keys[ft].angle);
+                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                int b = (int)roundf(__fmul_rn(rot, factor));
+                if (b == kHistoLength) b = 0;
+                bin = (unsigned)b & 0xffu;
             }
+            s_ent[en] = ((unsigned long long)key << 32) | (bin << 24) | (oc << 16) | (unsigned)ft;
         }
         __syncthreads();
         RQ(2);
-        // The slowest thread of a round is the one with the longest list and every entry costs a chain of dependent
-        // shared-memory loads (entry -> state -> proposal): four entries are in flight at a time.
-        for (;;) {
-            bool any_unresolved = false;
+        // phase 1 of a round: every waiting query proposes itself (min index wins) at each still-available candidate feature
+        constexpr int kChunk = 4;
+        auto propose = [&](int q, int* mq) {
+            const int e = s_off[q + 1];
+            for (int k = s_off[q]; k < e; k += kChunk) {          // kChunk entries in flight: the chain entry -> state -> atomic is all latency
+                unsigned long long en[kChunk]; uint8_t st[kChunk];
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u) en[u] = (k + u < e) ? s_ent[k + u] : 0xffffffff00000000ull;
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u) st[u] = (k + u < e) ? s_state[(unsigned)en[u] & 0xffffu] : (uint8_t)1;
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u)
+                    if (st[u] != 1) atomicMin(&mq[(unsigned)en[u] & 0xffffu], q);
+            }
+        };
+        // phase 2: best (and second best) available candidate; final when no lower-index waiting query can still interfere.
+        // Returns true while the query has to wait for another round.
+        auto decide = [&](int q, const int* mq) -> bool {
+            const uint8_t flags = s_res[q];
+            uint32_t best = 0xffffffffu, best2 = 0xffffffffu;
+            int lvl = -1, lvl2 = -1, fb = -1, bb = 0;
+            bool depends_ok = true;
+            const int e = s_off[q + 1];
+            for (int k = s_off[q]; k < e; k += kChunk) {
+                unsigned long long en[kChunk]; uint8_t st[kChunk]; int mv[kChunk];
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u) en[u] = (k + u < e) ? s_ent[k + u] : 0xffffffff00000000ull;
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u) st[u] = (k + u < e) ? s_state[(unsigned)en[u] & 0xffffu] : (uint8_t)1;
+                if (mode >= 1) {
+#pragma unroll
+                    for (int u = 0; u < kChunk; ++u) mv[u] = (st[u] != 1) ? mq[(unsigned)en[u] & 0xffffu] : q;
+                }
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u) {
+                    if (st[u] == 1) continue;
+                    const uint32_t key = (uint32_t)(en[u] >> 32);
+                    const int ft = (int)((unsigned)en[u] & 0xffffu);
+                    if (mode >= 1 && mv[u] != q) depends_ok = false;
+                    const int eb = (int)(((unsigned)en[u] >> 24) & 0xffu);
+                    if (mode == 0) {
+                        if (key < best) { best = key; fb = ft; bb = eb; }
+                    } else {
+                        const int oc = (int)(((unsigned)en[u] >> 16) & 0xffu);
+                        if (key < best) { best2 = best; lvl2 = lvl; best = key; lvl = oc; fb = ft; bb = eb; }
+                        else if (key < best2) { best2 = key; lvl2 = oc; }
+                    }
+                }
+            }
+            if (best == 0xffffffffu) { s_res[q] = flags | 1; return false; }
+            const bool final_ok = (mode == 0) ? (mq[fb] == q) : depends_ok;
+            if (!final_ok) return true;
+            s_res[q] = flags | 1;
+            const int bd = (int)(best >> 20);
+            bool accept = bd <= th_accept;
+            if (mode == 1 && accept) {
+                const int bd2 = (best2 == 0xffffffffu) ? 256 : (int)(best2 >> 20);
+                if (lvl == lvl2 && (float)bd > __fmul_rn(nn_ratio, (float)bd2)) accept = false;
+            }
+            if (mode == 2 && accept) {            // SearchByBoW: bestDist1 < mfNNratio * bestDist2 (src/ORBmatcher.cc:324)
+                const int bd2 = (best2 == 0xffffffffu) ? 256 : (int)(best2 >> 20);
+                accept = (float)bd < __fmul_rn(nn_ratio, (float)bd2);
+            }
+            if (accept) {
+                s_choice[q] = fb; s_bin[q] = (uint8_t)bb;
+                if (flags & 2) s_state[fb] = 1; else if (s_state[fb] == 0) s_state[fb] = 2;
+                ++nm_local;
+            }
+            return false;
+        };
+
+        // Block rounds over a COMPACT list of the waiting queries (two barriers per round; the proposal table is double
+        // buffered: the idle copy is cleared while the live one is read).  Why the list: a warp pays for the longest candidate
+        // list among its lanes, so with the waiting queries scattered over all 32 warps every warp ran the full loop in every
+        // round (measured: the rounds were issue-bound, not latency-bound); packed, round r touches ceil(waiting / 32) warps.
+        // A 1024-thread barrier costs ~500 cycles, so once <= 32 queries wait warp 0 finishes alone with warp-level syncs.
+        int cur = 0, n_act;
+        {
+            if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
             for (int i = tid; i < n_f; i += 1024) s_minq[i] = 0x7fffffff;
             __syncthreads();
-            for (int q = tid; q < n_q; q += 1024) {
-                if (s_res[q] & 1) continue;
-                const int e = s_off[q + 1];
-                for (int k = s_off[q]; k < e; k += 4) {
-                    unsigned long long en[4]; uint8_t st[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) en[u] = s_ent[k + u];                 // 4 sentinel slots follow the last entry
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) st[u] = s_state[(unsigned)en[u] & 0xffffu];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (k + u < e && st[u] != 1) atomicMin(&s_minq[(unsigned)en[u] & 0xffffu], q);
-                }
+            for (int q0 = 0; q0 < n_q; q0 += 1024) {
+                const int q = q0 + tid;
+                const bool w = q < n_q && !(s_res[q] & 1);
+                const unsigned m = __ballot_sync(0xffffffffu, w);
+                int base = 0;
+                if ((tid & 31) == 0 && m) base = atomicAdd(&s_cnt[0], __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (w) s_list[base + __popc(m & ((1u << (tid & 31)) - 1u))] = q;
             }
             __syncthreads();
-            for (int q = tid; q < n_q; q += 1024) {
-                const uint8_t flags = s_res[q];
-                if (flags & 1) continue;
-                uint32_t best = 0xffffffffu, best2 = 0xffffffffu;
-                int lvl = -1, lvl2 = -1, fb = -1;
-                bool depends_ok = true;
-                const int e = s_off[q + 1];
-                for (int k = s_off[q]; k < e; k += 4) {
-                    unsigned long long en[4]; uint8_t st[4]; int mq[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) en[u] = s_ent[k + u];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) st[u] = s_state[(unsigned)en[u] & 0xffffu];
-                    if (mode >= 1) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) mq[u] = s_minq[(unsigned)en[u] & 0xffffu];
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (k + u >= e || st[u] == 1) continue;
-                        const uint32_t key = (uint32_t)(en[u] >> 32);
-                        const int ft = (int)((unsigned)en[u] & 0xffffu);
-                        if (mode >= 1 && mq[u] != q) depends_ok = false;
-                        if (mode == 0) {
-                            if (key < best) { best = key; fb = ft; }
-                        } else {
-                            const int oc = (int)(((unsigned)en[u] >> 16) & 0xffu);
-                            if (key < best) { best2 = best; lvl2 = lvl; best = key; lvl = oc; fb = ft; }
-                            else if (key < best2) { best2 = key; lvl2 = oc; }
-                        }
-                    }
-                }
-                if (best == 0xffffffffu) { s_res[q] = flags | 1; continue; }
-                const bool final_ok = (mode == 0) ? (s_minq[fb] == q) : depends_ok;
-                if (!final_ok) { any_unresolved = true; continue; }
-                s_res[q] = flags | 1;
-                const int bd = (int)(best >> 20);
-                bool accept = bd <= th_accept;
-                if (mode == 1 && accept) {
-                    const int bd2 = (best2 == 0xffffffffu) ? 256 : (int)(best2 >> 20);
-                    if (lvl == lvl2 && (float)bd > __fmul_rn(nn_ratio, (float)bd2)) accept = false;
-                }
-                if (mode == 2 && accept) {            // SearchByBoW: bestDist1 < mfNNratio * bestDist2 (src/ORBmatcher.cc:324)
-                    const int bd2 = (best2 == 0xffffffffu) ? 256 : (int)(best2 >> 20);
-                    accept = (float)bd < __fmul_rn(nn_ratio, (float)bd2);
-                }
-                if (accept) {
-                    s_choice[q] = fb;
-                    if (flags & 2) s_state[fb] = 1; else if (s_state[fb] == 0) s_state[fb] = 2;
-                    ++nm_local;
-                }
+            n_act = s_cnt[0];
+        }
+        while (n_act > 32) {
+            int* mq = s_minq + (size_t)cur * n_f;
+            int* mq_next = s_minq + (size_t)(cur ^ 1) * n_f;
+            const int* lst = s_list + (size_t)cur * n_q;
+            int* lst_next = s_list + (size_t)(cur ^ 1) * n_q;
+            if (tid == 0) s_cnt[cur ^ 1] = 0;
+            for (int i = tid; i < n_f; i += 1024) mq_next[i] = 0x7fffffff;
+            for (int i = tid; i < n_act; i += 1024) propose(lst[i], mq);
+            __syncthreads();
+            for (int i0 = 0; i0 < n_act; i0 += 1024) {
+                const int i = i0 + tid;
+                const int q = i < n_act ? lst[i] : -1;
+                const bool w = q >= 0 && decide(q, mq);
+                const unsigned m = __ballot_sync(0xffffffffu, w);
+                int base = 0;
+                if ((tid & 31) == 0 && m) base = atomicAdd(&s_cnt[cur ^ 1], __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (w) lst_next[base + __popc(m & ((1u << (tid & 31)) - 1u))] = q;
             }
             ++rounds;
-#ifdef RESOLVE_DEBUG
-            if (tid == 0 && rounds <= 12) s_rt[rounds - 1] = clock64() - tq[2];
-#endif
-            if (!__syncthreads_or(any_unresolved)) break;      // barrier + block-wide "someone is still waiting"
+            cur ^= 1;
+            __syncthreads();
+            n_act = s_cnt[cur];
         }
+        if (n_act > 0 && tid < 32) {
+            int* mq = s_minq + (size_t)cur * n_f;     // a fully cleared table; the tail clears only what it touches
+            const int q0 = tid < n_act ? s_list[(size_t)cur * n_q + tid] : -1;
+            int q = q0;
+            for (;;) {
+                if (q >= 0) propose(q, mq);
+                __syncwarp();
+                bool waiting = false;
+                if (q >= 0) waiting = decide(q, mq);
+                ++rounds;
+                if (!__any_sync(0xffffffffu, waiting)) break;
+                if (!waiting) q = -1;
+                // clear every proposal of this round, also those of the queries that just finished: a stale index of a
+                // resolved query would keep its features "claimed" forever
+                if (q0 >= 0) {
+                    const int e = s_off[q0 + 1];
+                    for (int k = s_off[q0]; k < e; ++k) mq[(unsigned)s_ent[k] & 0xffffu] = 0x7fffffff;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
         RQ(3);
         for (int i = tid; i < n_f; i += 1024) state[i] = s_state[i];
         __syncthreads();
     } else {
-    for (int q = tid; q < n_q; q += 1024) resolved[q] = (list_n[q] == 0);
+    for (int i = tid; i < n_f; i += 1024) match[i] = -1;
+    for (int q = tid; q < n_q; q += 1024) { choice[q] = -1; resolved[q] = (list_n[q] == 0); }
     __syncthreads();
     for (;;) {
         bool any_unresolved = false;
@@ -512,8 +587,8 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
     }
     }
     // owner of a feature = the last (highest-index) query that chose it
-    for (int q = tid; q < n_q; q += 1024) if (ch[q] >= 0) atomicMax(&match[ch[q]], q);
-    if (mode != 1 && check_orientation) {
+    for (int q = tid; q < n_q; q += 1024) if (ch[q] >= 0) atomicMax(&mt[ch[q]], q);
+    if (orient) {
         for (int b = tid; b < kHistoLength; b += 1024) hist[b] = 0;
         __syncthreads();
         const float factor = 1.0f / kHistoLength;
@@ -523,29 +598,40 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             const bool valid = c >= 0;
             int bin = 64 + (tid & 31);                      // unique key for lanes without a match
             if (valid) {
-                float rot = __fsub_rn(q_angle[q], f_angle ? f_angle[c] : f.keys[c].angle);
-                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                bin = (int)roundf(__fmul_rn(rot, factor));
-                if (bin == kHistoLength) bin = 0;
-                bins[q] = (uint8_t)bin;
+                if (on_chip) {
+                    bin = bins[q];                          // computed with the candidate entry
+                } else {
+                    float rot = __fsub_rn(q_angle[q], f_angle ? f_angle[c] : f.keys[c].angle);
+                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                    bin = (int)roundf(__fmul_rn(rot, factor));
+                    if (bin == kHistoLength) bin = 0;
+                    bins[q] = (uint8_t)bin;
+                }
             }
             // nearly every match falls into one or two bins: aggregate equal bins inside the warp, one atomic per group
             const unsigned peers = __match_any_sync(0xffffffffu, bin);
             if (valid && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
         }
         __syncthreads();
-        if (tid < 32) {       // ORBmatcher::ComputeThreeMaxima, src/ORBmatcher.cc:2012-2053 (lane 0; the bins are preloaded by the warp)
-            const int mine_h = tid < kHistoLength ? hist[tid] : 0;
-            int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+        if (tid < 32) {
+            // ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:2012-2053).  The reference scans the bins in index order with
+            // strict '>' updates of (max1, max2, max3): the result is the three largest NON-EMPTY bins ordered by (count
+            // descending, index ascending).  Done here as three warp arg-max reductions over count << 8 | (255 - index)
+            // instead of a 30-step serial scan (the scan alone was ~4k cycles of one thread).
+            const int cnt = tid < kHistoLength ? hist[tid] : 0;
+            int key = cnt > 0 ? ((cnt << 8) | (255 - tid)) : 0;
+            int top_i[3], top_c[3];
 #pragma unroll
-            for (int i = 0; i < kHistoLength; ++i) {
-                const int sv = __shfl_sync(0xffffffffu, mine_h, i);
-                if (sv > max1) { max3 = max2; max2 = max1; max1 = sv; i3 = i2; i2 = i1; i1 = i; }
-                else if (sv > max2) { max3 = max2; max2 = sv; i3 = i2; i2 = i; }
-                else if (sv > max3) { max3 = sv; i3 = i; }
+            for (int r = 0; r < 3; ++r) {
+                int m = key;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+                top_c[r] = m >> 8; top_i[r] = m > 0 ? 255 - (m & 0xff) : -1;
+                if (key == m) key = 0;                      // keys are unique (index in the low byte) unless 0
             }
-            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
-            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) i3 = -1;
+            int i1 = top_i[0], i2 = top_i[1], i3 = top_i[2];
+            if ((float)top_c[1] < __fmul_rn(0.1f, (float)top_c[0])) { i2 = -1; i3 = -1; }
+            else if ((float)top_c[2] < __fmul_rn(0.1f, (float)top_c[0])) i3 = -1;
             if (tid == 0) { keep_bin[0] = i1; keep_bin[1] = i2; keep_bin[2] = i3; }
         }
         __syncthreads();
@@ -553,8 +639,12 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             const int c = ch[q];
             if (c < 0) continue;
             const int bin = bins[q];
-            if (bin != keep_bin[0] && bin != keep_bin[1] && bin != keep_bin[2]) { match[c] = -2; --nm_local; }
+            if (bin != keep_bin[0] && bin != keep_bin[1] && bin != keep_bin[2]) { mt[c] = -2; --nm_local; }
         }
+    }
+    if (on_chip) {
+        __syncthreads();
+        for (int i = tid; i < n_f; i += 1024) match[i] = mt[i];
     }
     {
 #pragma unroll
@@ -566,7 +656,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
 #ifdef RESOLVE_DEBUG
     if (tid == 0) printf("resolve mode=%d n_q=%d n_f=%d E=%d on_chip=%d rounds=%d nm=%d | scan=%lld fill=%lld rounds=%lld epilogue=%lld\n", mode, n_q, n_f, E, (int)on_chip, rounds, s_nm,
                          tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], clock64() - tq[3]);
-    if (tid == 0 && on_chip) { for (int i = 0; i < min(rounds, 12); ++i) printf(" r%d=%lld", i + 1, s_rt[i]); printf("\n"); }
+
 #endif
 }
 

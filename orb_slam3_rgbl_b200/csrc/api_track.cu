@@ -497,13 +497,11 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
         const float* last_pose = t.ch_poses + 7 * (k - 1);
         if (tm) cudaEventRecord(tev[0], cs);
         launch_chain_prep(cs, t.s_kps + lo, t.s_depth + lo, t.s_nsel + (k - 1), last_pose, last_pose, f, mono, cap,
-                          t.q_u8a, t.q_f3a, t.q_i, t.q_f[0], t.q_u8b, d_flags);
+                          t.q_u8a, t.q_f3a, t.q_i, t.q_f[0], t.q_u8b, d_flags, t.state);
         f.n = t.s_nsel + k; f.keys = t.s_kps + cu; f.uright = t.s_uright + cu; f.desc = t.s_desc + cu * 32;
         const int* cell_start = t.b_cell_start + (size_t)k * (kGridCols * kGridRows + 1);
         const int* csr_idx = t.b_csr_idx + cu;
-        if (tm) cudaEventRecord(tev[1], cs);
-        CU(cudaMemsetAsync(t.state, 0, cap, cs));
-        if (tm) cudaEventRecord(tev[2], cs);
+        if (tm) { cudaEventRecord(tev[1], cs); cudaEventRecord(tev[2], cs); }
         SearchLastParams prm{};
         prm.th = th; prm.check_orientation = 1; prm.cur_pose_dev = last_pose; prm.flags_dev = d_flags;
         LastFrameDev lf{cap, t.q_u8a, t.q_f3a, t.s_desc + lo * 32, t.q_i, t.q_f[0], t.q_u8b};
@@ -540,7 +538,7 @@ int rgbl_resident_track_end(rgbl_ctx* ctx, float* poses_out, int* n_matches, int
     const int nF = c->chain_frames;
     if (c->chain_timing_ev) {
         const cudaEvent_t* e = static_cast<const cudaEvent_t*>(c->chain_timing_ev);
-        const char* names[5] = {"chain_prep", "memset_state", "search_last(collect+resolve)", "chain_edges", "pose_optimize"};
+        const char* names[5] = {"chain_prep (+state clear)", "-", "search_last(collect+resolve)", "chain_edges", "pose_optimize"};
         for (int i = 0; i < 5; ++i) { float ms = 0; if (cudaEventElapsedTime(&ms, e[i], e[i + 1]) == cudaSuccess) std::fprintf(stderr, "[chain timing] %-30s %8.2f us\n", names[i], ms * 1e3f); }
         cudaGetLastError();
     }

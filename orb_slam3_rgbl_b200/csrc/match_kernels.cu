@@ -778,8 +778,10 @@ __global__ void __launch_bounds__(256) chain_prep_kernel(const rgbl_keypoint* __
                                                          const float* __restrict__ cur_pose, float fx, float fy, float cx, float cy,
                                                          float mb, int mono, int cap, uint8_t* __restrict__ valid,
                                                          float* __restrict__ xw, int* __restrict__ octave, float* __restrict__ angle,
-                                                         uint8_t* __restrict__ obs_pos, int* __restrict__ flags) {
+                                                         uint8_t* __restrict__ obs_pos, int* __restrict__ flags,
+                                                         uint8_t* __restrict__ state_clear) {
     const int i = blockIdx.x * 256 + threadIdx.x;
+    if (state_clear && i < cap) state_clear[i] = 0;      // feature states of the search that follows (saves a memset node)
     const float inv[4] = {-last_pose[0], -last_pose[1], -last_pose[2], last_pose[3]};
     if (i == 0) {
         // bForward / bBackward (src/ORBmatcher.cc:1686-1693): tlc = Tlw * (Tcw^-1).translation()
@@ -913,9 +915,9 @@ void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_sta
 
 void launch_chain_prep(cudaStream_t st, const rgbl_keypoint* kps, const float* depth, const int* n_ptr, const float* last_pose,
                        const float* cur_pose, const FrameDev& f, int mono, int cap, uint8_t* valid, float* xw, int* octave, float* angle,
-                       uint8_t* obs_pos, int* flags) {
+                       uint8_t* obs_pos, int* flags, uint8_t* state_clear) {
     chain_prep_kernel<<<(cap + 255) / 256, 256, 0, st>>>(kps, depth, n_ptr, last_pose, cur_pose, f.fx, f.fy, f.cx, f.cy, f.mb, mono, cap,
-                                                       valid, xw, octave, angle, obs_pos, flags);
+                                                       valid, xw, octave, angle, obs_pos, flags, state_clear);
 }
 
 void launch_chain_edges(cudaStream_t st, const rgbl_keypoint* kps, const float* uright, const int* n_ptr, const int* match,

@@ -111,7 +111,7 @@ void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_sta
                          const SearchRelocParams& prm, const uint8_t* obs_pos, MatchScratch s, uint8_t* state, int* match, int* n_matches);
 void launch_chain_prep(cudaStream_t st, const rgbl_keypoint* kps, const float* depth, const int* n_ptr, const float* last_pose,
                        const float* cur_pose, const FrameDev& f, int mono, int cap, uint8_t* valid, float* xw, int* octave, float* angle,
-                       uint8_t* obs_pos, int* flags);
+                       uint8_t* obs_pos, int* flags, uint8_t* state_clear /* nullable: cap bytes zeroed */);
 void launch_chain_edges(cudaStream_t st, const rgbl_keypoint* kps, const float* uright, const int* n_ptr, const int* match,
                         const float* last_xw, const FrameDev& f, float* exw, float* eobs, float* einfo, uint8_t* est, int* eidx, int* n_edges);
 void launch_frustum(cudaStream_t st, const FrameDev& f, const FrustumParams& prm, int n, const float* xw, const float* normal,

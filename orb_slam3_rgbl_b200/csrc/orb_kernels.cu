@@ -12,10 +12,69 @@ namespace rgbl {
 // Pyramid: level l = cv::resize(level l-1, INTER_LINEAR)  (src/ORBextractor.cc:1183).
 // One thread produces 4 horizontally adjacent output bytes (one 32-bit store).
 // ------------------------------------------------------------------------------------------------
+// CTA tile: 128 x 16 outputs.  The source rectangle of the tile (<= 22 rows x 176 bytes at scale 1.2) is staged in shared
+// memory with 16-byte loads (rows are 64-byte aligned); every thread then produces 4 adjacent outputs in two rows from
+// shared-memory bytes.  (The first version gathered 16 single bytes per thread straight from global memory and was bound by
+// the number of load instructions, not by HBM.)
+constexpr int kRzTW = 128, kRzTH = 16, kRzSrcRows = 24, kRzSrcVec = 12;     // staged source: 24 rows x 192 bytes max
 __global__ void __launch_bounds__(256) resize_level_kernel(uint8_t* __restrict__ pyr, size_t frame_stride,
                                                            LevelGeom src, LevelGeom dst,
                                                            const LinCoef* __restrict__ tabx,
                                                            const LinCoef* __restrict__ taby) {
+    __shared__ uint4 tile[kRzSrcRows][kRzSrcVec];
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int x0 = blockIdx.x * kRzTW, y0 = blockIdx.y * kRzTH;
+    const uint8_t* s = pyr + (size_t)blockIdx.z * frame_stride + src.off;
+    uint8_t* d = pyr + (size_t)blockIdx.z * frame_stride + dst.off;
+    // source rectangle of this tile (tables are monotone)
+    const int xl = min(x0 + kRzTW - 1, dst.w - 1), yl = min(y0 + kRzTH - 1, dst.h - 1);
+    const int sx_lo = tabx[x0].s & ~15, sx_hi = min(tabx[xl].s + 1, src.w - 1);
+    const int sy_lo = taby[y0].s, sy_hi = min(taby[yl].s + 1, src.h - 1);
+    const int n_vec = min(min((sx_hi - sx_lo) / 16 + 1, kRzSrcVec), (src.pitch - sx_lo) / 16);
+    const int n_rows = min(sy_hi - sy_lo + 1, kRzSrcRows);
+    for (int i = tid; i < n_rows * n_vec; i += 256) {
+        const int r = i / n_vec, v = i - r * n_vec;
+        tile[r][v] = __ldg(reinterpret_cast<const uint4*>(s + (size_t)(sy_lo + r) * src.pitch + sx_lo) + v);
+    }
+    __syncthreads();
+    const int x4 = x0 + 4 * tx;
+    if (x4 >= dst.w) return;
+    const uint8_t* tb = reinterpret_cast<const uint8_t*>(&tile[0][0]);
+    constexpr int kTP = kRzSrcVec * 16;
+    int s0[4], s1[4], c0[4], c1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const LinCoef cx = tabx[min(x4 + i, dst.w - 1)];
+        s0[i] = cx.s - sx_lo; s1[i] = min(cx.s + 1, src.w - 1) - sx_lo; c0[i] = cx.c0; c1[i] = cx.c1;
+    }
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry) {
+        const int y = y0 + ty + 8 * ry;
+        if (y >= dst.h) break;
+        const LinCoef cy = taby[y];
+        const uint8_t* r0 = tb + (cy.s - sy_lo) * kTP;
+        const uint8_t* r1 = tb + (min(cy.s + 1, src.h - 1) - sy_lo) * kTP;
+        const int b0 = cy.c0, b1 = cy.c1;
+        uint32_t out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (x4 + i < dst.w) {
+                const int h0 = (int)r0[s0[i]] * c0[i] + (int)r0[s1[i]] * c1[i];
+                const int h1 = (int)r1[s0[i]] * c0[i] + (int)r1[s1[i]] * c1[i];
+                const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                out |= (uint32_t)(v & 0xff) << (8 * i);
+            }
+        }
+        *reinterpret_cast<uint32_t*>(d + (size_t)y * dst.pitch + x4) = out;
+    }
+}
+
+// Fallback for level ratios whose source rectangle does not fit the staged tile (scale factors above ~1.35): one thread
+// gathers the 16 source bytes of 4 adjacent outputs directly from global memory.
+__global__ void __launch_bounds__(256) resize_level_gather_kernel(uint8_t* __restrict__ pyr, size_t frame_stride,
+                                                                  LevelGeom src, LevelGeom dst,
+                                                                  const LinCoef* __restrict__ tabx,
+                                                                  const LinCoef* __restrict__ taby) {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x4 >= dst.w || y >= dst.h) return;
@@ -446,8 +505,14 @@ void launch_pyramid(cudaStream_t st, uint8_t* pyr, size_t frame_stride, const Le
     for (int l = 1; l < n_levels; ++l) {
         const LevelGeom& src = h_levels[l - 1];
         const LevelGeom& dst = h_levels[l];
-        dim3 blk(32, 8), grd(((dst.w + 3) / 4 + 31) / 32, (dst.h + 7) / 8, n_frames);
-        resize_level_kernel<<<grd, blk, 0, st>>>(pyr, frame_stride, src, dst, d_coefs + dst.tabx_off, d_coefs + dst.taby_off);
+        const double rx = (double)src.w / dst.w, ry = (double)src.h / dst.h;
+        if (rx * (kRzTW - 1) + 18.0 <= kRzSrcVec * 16 - 1 && ry * (kRzTH - 1) + 3.0 <= kRzSrcRows) {
+            dim3 grd((dst.w + kRzTW - 1) / kRzTW, (dst.h + kRzTH - 1) / kRzTH, n_frames);
+            resize_level_kernel<<<grd, 256, 0, st>>>(pyr, frame_stride, src, dst, d_coefs + dst.tabx_off, d_coefs + dst.taby_off);
+        } else {
+            dim3 blk(32, 8), grd(((dst.w + 3) / 4 + 31) / 32, (dst.h + 7) / 8, n_frames);
+            resize_level_gather_kernel<<<grd, blk, 0, st>>>(pyr, frame_stride, src, dst, d_coefs + dst.tabx_off, d_coefs + dst.taby_off);
+        }
     }
 }
 

@@ -93,6 +93,25 @@ def test_other_sizes(w, h, nf):
     assert (d == rd).all()
 
 
+@pytest.mark.parametrize("scale,levels,nf", [(1.5, 5, 1500), (1.1, 8, 2000), (1.35, 6, 1000), (1.6, 4, 800)])
+def test_other_scale_factors(scale, levels, nf):
+    """Settings other than the KITTI yaml: the staged-tile resize kernel serves level ratios up to ~1.35, larger ones take the
+    gather kernel; both must stay bit-exact with the oracle (pyramid, keypoints, descriptors)."""
+    img = S.make_image(5, S.KITTI_W, S.KITTI_H)
+    ex = F.ORBextractor(nf, scale, levels, 12, 7, S.KITTI_W, S.KITTI_H)
+    try:
+        mono, k, d = ex(img)
+        pyr = [ex.level_image(l) for l in range(levels)]
+    finally:
+        ex.ctx.close()
+    ref = oracle.Extractor(nf, scale, levels)
+    rk, rd, _ = ref(img)
+    for l in range(levels):
+        assert np.array_equal(pyr[l], ref.level_image(l)), f"level {l} differs"
+    _cmp_kps(k, rk)
+    assert (d == rd).all()
+
+
 def test_flat_image_gives_no_keypoints():
     img = np.full((S.KITTI_H, S.KITTI_W), 100, np.uint8)
     ex = F.ORBextractor(1000, 1.2, 8, 12, 7, S.KITTI_W, S.KITTI_H)

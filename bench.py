@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="frames per step (per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bow", action="store_true", help="skip the ComputeBoW side measurement")
     ap.add_argument("--multi-sequences", type=int, default=4, help="extra capacity figure: independent sequences tracked concurrently on one GPU (N=1 only; 0/1 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -337,6 +338,39 @@ def main():
         for c2 in ctxs[1:]:
             c2.close()
 
+    # ---- Frame::ComputeBoW (keyframes only in the reference, reported on its own, not part of `value`) ----
+    bow = None
+    if world == 1 and not args.no_bow:
+        k_, L_ = 10, 6                                     # the shape of ORBvoc.txt (k = 10, L = 6: 1 111 111 nodes)
+        nn = (k_ ** (L_ + 1) - 1) // (k_ - 1)
+        rng = np.random.default_rng(7)
+        inner = (k_ ** L_ - 1) // (k_ - 1)
+        cb = np.minimum(np.arange(nn + 1, dtype=np.int64) * k_, inner * k_).astype(np.int32)
+        ci = np.arange(1, nn, dtype=np.int32)              # BFS numbering: children of i are k i + 1 .. k i + k
+        nd = rng.integers(0, 256, (nn, 32), dtype=np.uint8)
+        wid = np.full(nn, -1, np.int32); wid[inner:] = np.arange(nn - inner, dtype=np.int32)
+        nw = np.zeros(nn, np.float64); nw[inner:] = rng.uniform(0.5, 12.0, nn - inner)
+        voc = F.ORBVocabulary(ctx, cb, ci, nd, nw, wid, L_)
+        batch.upload(); batch.process_resident()
+        for f in range(3):
+            voc.transform_resident(f)
+        t0 = time.perf_counter()
+        res = [voc.transform_resident(f) for f in range(T)]
+        gpu_ms = 1e3 * (time.perf_counter() - t0) / T
+        voc.close()
+        bow = {"gpu_ms_per_frame": gpu_ms, "words_per_frame": float(np.mean([len(r[0][0]) for r in res])),
+               "vocabulary": f"synthetic k={k_} L={L_} ({nn} nodes, {nn * 32 / 1e6:.0f} MB of node descriptors), TF-IDF / L1, levelsup 4",
+               "timing": "host wall clock per rgbl_resident_compute_bow call (descriptors already in HBM; includes the D2H of both maps)"}
+        if not args.no_cpu_baseline:
+            from oracle import compute_bow as cpu_bow
+            vd = dict(child_begin=cb, child_index=ci, node_desc=nd, node_weight=nw, word_id=wid, levels=L_)
+            descs = [o[1] for o in batch.download()[:4]]
+            t0 = time.perf_counter()
+            for dsc in descs:
+                cpu_bow(vd, dsc)
+            bow["cpu_ms_per_frame"] = 1e3 * (time.perf_counter() - t0) / len(descs)
+            bow["cpu"] = "oracle (std::map restatement of DBoW2 transform), one core"
+
     if rank == 0:
         # roofline of the dominant kernel (per-stage CUDA-event time / launches, measured above)
         levels = []
@@ -411,7 +445,7 @@ def main():
                 "clocks": clocks, "roofline": roofline, "roofline_frame_construction": roofline_streaming, "kernels": kernels, "latency_bound_stages": other,
                 "tracking": {"matches_per_frame": float(np.mean(nm[1:])), "inliers_per_frame": float(np.mean(ni[1:])),
                              "pose_x_error_m_last_frame": float(abs(poses[-1, 4] - seq.pose(T - 1)[4]))},
-                "multi_sequence_capacity": multi,
+                "multi_sequence_capacity": multi, "compute_bow": bow,
                 "host_quadtree_ms_per_step": prof["_host_quadtree_ms"] / args.steps,
                 "wall_ms_per_step": wall_ms / args.steps}
         if world == 1 and not args.no_cpu_baseline:

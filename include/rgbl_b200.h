@@ -219,6 +219,29 @@ int rgbl_resident_upload(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray
 int rgbl_resident_process(rgbl_ctx* ctx, const float P[12], const rgbl_depth_params* prm, int* n_out /* nullable */);
 int rgbl_resident_download(rgbl_ctx* ctx, rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out);
 
+/* ---- Frame::ComputeBoW (src/Frame.cc:828-835) -------------------------------------------------------------------------
+ * = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, BowVector&, FeatureVector&, levelsup)
+ * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1206, per-feature descent :1218-1259, FORB::distance FORB.cpp:81-101).
+ * The vocabulary is uploaded once, flattened by the shim from m_nodes: node i (0 = root) has the children
+ * child_index[child_begin[i] .. child_begin[i+1]) in m_nodes[i].children order, a 32-byte descriptor, its WordValue weight and
+ * word_id (>= 0 for leaves).  levels = m_L; weighting / scoring = the DBoW2 enum values of the vocabulary file header
+ * (TF_IDF = 0 or TF = 1; any scoring that normalises with L1: L1_NORM = 0, CHI_SQUARE = 2, KL = 3, BHATTACHARYYA = 4; others
+ * return RGBL_E_UNSUPPORTED).                                                                                            */
+typedef struct rgbl_vocabulary rgbl_vocabulary;
+int rgbl_vocabulary_create(rgbl_ctx* ctx, int n_nodes, const int32_t* child_begin /* n_nodes + 1 */, const int32_t* child_index,
+                           const uint8_t* node_desc /* n_nodes x 32 */, const double* node_weight, const int32_t* word_id, int levels,
+                           int weighting, int scoring, rgbl_vocabulary** out);
+void rgbl_vocabulary_destroy(rgbl_vocabulary* voc);
+/* BowVector (std::map<WordId, WordValue>) as ascending bow_word[] / bow_value[] (doubles, bit-identical to the map built by
+ * addWeight + normalize(L1)); FeatureVector (std::map<NodeId, vector<unsigned>>) as CSR: ascending fv_node[], fv_start[n_fv_nodes + 1],
+ * fv_feature[] in insertion order - the layout rgbl_search_by_bow takes.  All output arrays need room for n entries (fv_start: n + 1).
+ * A leaf above level (levels - levelsup) leaves the reference's node id uninitialised; it is 0 (the root) here.               */
+int rgbl_compute_bow(rgbl_ctx* ctx, const rgbl_vocabulary* voc, int n, const uint8_t* desc /* n x 32 */, int levelsup, int32_t* bow_word,
+                     double* bow_value, int* n_words, int32_t* fv_node, int32_t* fv_start, int32_t* fv_feature, int* n_fv_nodes);
+/* same on the descriptors of frame `frame` of the last batched call, which are already in HBM */
+int rgbl_resident_compute_bow(rgbl_ctx* ctx, const rgbl_vocabulary* voc, int frame, int levelsup, int32_t* bow_word, double* bow_value,
+                              int* n_words, int32_t* fv_node, int32_t* fv_start, int32_t* fv_feature, int* n_fv_nodes);
+
 /* Resident tracking chain over the frames of the last batched call, entirely on the device: for t = 1..n-1
  * SearchByProjection(frame t, frame t-1, th) -> PoseOptimization, every LiDAR-depth keypoint of frame t-1 acting as a map
  * point (Frame::UnprojectStereo, src/Frame.cc:1097-1112, with the estimated pose of t-1; constant-pose motion model).

@@ -303,6 +303,8 @@ def _late(L):
     L.orc_stereo_matches.argtypes = [i, vp, vp, i, vp, vp, i, vp, vp, vp, vp, vp, vp, f, f, vp, vp]
     L.orc_pose_optimize.argtypes = [vp, i, vp, vp, vp, vp, f, f, f, f, f, vp, vp]
     L.orc_pose_optimize.restype = i
+    L.orc_compute_bow.argtypes = [i, vp, vp, vp, vp, vp, i, i, vp, i, vp, vp, C.POINTER(i), vp, vp, vp, C.POINTER(i)]
+    L.orc_compute_bow.restype = i
     _LATE_DECL_DONE = True
 
 
@@ -415,3 +417,19 @@ def stereo_matches(kps_l, desc_l, kps_r, desc_r, ex_l: "Extractor", ex_r: "Extra
     lib().orc_stereo_matches(len(kps_l), _p(kps_l), _p(desc_l), len(kps_r), _p(kps_r), _p(desc_r), nl, _p(ex_l.scale_factors),
                              _p(ex_l.inv_scale_factors), pl, pr, _p(lw), _p(lh), mb, mbf, _p(d), _p(u))
     return d, u
+
+
+def compute_bow(vocab: dict, desc, levelsup: int = 4):
+    """Frame::ComputeBoW on a flattened vocabulary dict(child_begin, child_index, node_desc, node_weight, word_id, levels)
+    -> ((word ids, values), (node ids, node_start, features)) exactly as std::map iteration yields them."""
+    _late(lib())
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); n = len(desc)
+    cb = np.ascontiguousarray(vocab["child_begin"], np.int32); ci = np.ascontiguousarray(vocab["child_index"], np.int32)
+    nd = np.ascontiguousarray(vocab["node_desc"], np.uint8); nw = np.ascontiguousarray(vocab["node_weight"], np.float64)
+    wi = np.ascontiguousarray(vocab["word_id"], np.int32)
+    bw = np.empty(max(n, 1), np.int32); bv = np.empty(max(n, 1), np.float64)
+    fn = np.empty(max(n, 1), np.int32); fs = np.empty(n + 1, np.int32); ff = np.empty(max(n, 1), np.int32)
+    k, m = C.c_int(0), C.c_int(0)
+    lib().orc_compute_bow(len(wi), _p(cb), _p(ci), _p(nd), _p(nw), _p(wi), int(vocab["levels"]), n, _p(desc), levelsup,
+                          _p(bw), _p(bv), C.byref(k), _p(fn), _p(fs), _p(ff), C.byref(m))
+    return (bw[:k.value].copy(), bv[:k.value].copy()), (fn[:m.value].copy(), fs[:m.value + 1].copy(), ff[:fs[m.value]].copy())

@@ -136,5 +136,19 @@ struct PoseProblemDev {
 void launch_pose_optimize(cudaStream_t st, const PoseProblemDev& p, double* work /* n*4 doubles */, uint8_t* level, uint8_t* outlier,
                           float* pose_out /*7*/, int* n_inliers);
 
+// bow_kernels.cu ------------------------------------------------------------------------------------
+struct VocabDev {                    // DBoW2 vocabulary, flattened (node 0 = root)
+    const int* child_begin;          // n_nodes + 1
+    const int* child_index;          // children in m_nodes[i].children order
+    const uint8_t* node_desc;        // n_nodes x 32
+    const double* node_weight;       // WordValue
+    const int* word_id;              // >= 0 for leaves
+};
+void launch_bow_descend(cudaStream_t st, const VocabDev& voc, int n, const uint8_t* desc, int nid_level, int* f_word, double* f_weight,
+                        int* f_node);
+// returns the padded key count (power of two) or -1 when n exceeds the shared-memory sort capacity
+int launch_bow_assemble(cudaStream_t st, int n, const int* f_word, const double* f_weight, const int* f_node, int* bow_word,
+                        double* bow_value, int* fv_node, int* fv_start, int* fv_feature, int* counts /*3*/, int* scratch);
+
 }  // namespace rgbl
 #endif

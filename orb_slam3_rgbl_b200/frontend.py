@@ -162,6 +162,53 @@ def compute_stereo_matches(extractor: "ORBextractor", images_lr, mb: float, mbf:
     return (kl, dl), (kr, dr), depth[:len(kl)].copy(), ur[:len(kl)].copy()
 
 
+class ORBVocabulary:
+    """DBoW2 vocabulary (ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB>, include/ORBVocabulary.h) uploaded once as a
+    flat tree; `transform` = Frame::ComputeBoW's mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4)."""
+
+    TF_IDF, TF = 0, 1
+    L1_NORM = 0
+
+    def __init__(self, ctx: Context, child_begin, child_index, node_desc, node_weight, word_id, levels: int, weighting=0, scoring=0):
+        self.ctx = ctx
+        cb = np.ascontiguousarray(child_begin, np.int32); ci = np.ascontiguousarray(child_index, np.int32)
+        nd = np.ascontiguousarray(node_desc, np.uint8); nw = np.ascontiguousarray(node_weight, np.float64)
+        wi = np.ascontiguousarray(word_id, np.int32)
+        h = C.c_void_p()
+        check(lib().rgbl_vocabulary_create(ctx.handle, len(wi), ptr(cb), ptr(ci) if len(ci) else None, ptr(nd), ptr(nw), ptr(wi), int(levels),
+                                           int(weighting), int(scoring), C.byref(h)), ctx.handle)
+        self.handle = h
+
+    def close(self):
+        if self.handle:
+            lib().rgbl_vocabulary_destroy(self.handle)
+            self.handle = None
+
+    def _out(self, n):
+        return (np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.float64), np.empty(max(n, 1), np.int32), np.empty(n + 1, np.int32),
+                np.empty(max(n, 1), np.int32))
+
+    @staticmethod
+    def _pack(bw, bv, nw, fn, fs, ff, nn):
+        nw, nn = nw.value, nn.value
+        return (bw[:nw].copy(), bv[:nw].copy()), (fn[:nn].copy(), fs[:nn + 1].copy(), ff[:fs[nn]].copy())
+
+    def transform(self, desc, levelsup: int = 4):
+        """-> (BowVector as (word ids ascending, values), FeatureVector as CSR (node ids ascending, node_start, features))"""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        bw, bv, fn, fs, ff = self._out(len(desc)); nw, nn = C.c_int(0), C.c_int(0)
+        check(lib().rgbl_compute_bow(self.ctx.handle, self.handle, len(desc), ptr(desc) if len(desc) else None, levelsup, ptr(bw), ptr(bv),
+                                     C.byref(nw), ptr(fn), ptr(fs), ptr(ff), C.byref(nn)), self.ctx.handle)
+        return self._pack(bw, bv, nw, fn, fs, ff, nn)
+
+    def transform_resident(self, frame: int, levelsup: int = 4):
+        """Same on the descriptors of frame `frame` of the context's last batched call (no upload)."""
+        bw, bv, fn, fs, ff = self._out(self.ctx.cap); nw, nn = C.c_int(0), C.c_int(0)
+        check(lib().rgbl_resident_compute_bow(self.ctx.handle, self.handle, frame, levelsup, ptr(bw), ptr(bv), C.byref(nw), ptr(fn), ptr(fs),
+                                              ptr(ff), C.byref(nn)), self.ctx.handle)
+        return self._pack(bw, bv, nw, fn, fs, ff, nn)
+
+
 def structuring_element(kind: str, ku: int, kv: int | None = None) -> np.ndarray:
     kv = ku if kv is None else kv
     m = np.zeros((kv, ku), np.uint8)

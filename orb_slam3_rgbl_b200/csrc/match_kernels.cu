@@ -441,6 +441,11 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             }
             if (accept) {
                 s_choice[q] = fb; s_bin[q] = (uint8_t)bb;
+                // This write races with the state reads of other queries deciding in the same phase (compute-sanitizer
+                // racecheck reports it); it is benign: only 0/2 -> 1 matters to a reader, and a query q' that reads state[fb]
+                // has fb in its list, so it proposed there too and the winner q satisfies q < q'.  If q' sees the old value
+                // it waits one more round (minq[fb] = q != q') and then sees 1; if it sees the new value it skips fb now,
+                // exactly what the sequential scan does after q took fb.  Either way q' ends with the same feature.
                 if (flags & 2) s_state[fb] = 1; else if (s_state[fb] == 0) s_state[fb] = 2;
                 ++nm_local;
             }

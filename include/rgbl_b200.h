@@ -219,6 +219,20 @@ int rgbl_resident_upload(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray
 int rgbl_resident_process(rgbl_ctx* ctx, const float P[12], const rgbl_depth_params* prm, int* n_out /* nullable */);
 int rgbl_resident_download(rgbl_ctx* ctx, rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out);
 
+/* ---- Optimizer::LocalBundleAdjustment (src/Optimizer.cc:1116-1499), numerical core ------------------------------------
+ * The shim gathers the local graph exactly as the reference builds it (:1210-1404): key-frame poses Tcw (local ones, the
+ * fixed ones and pose_fixed = 1 for those and for the map's initial key frame), local map points, one edge per observation
+ * (stereo = mvuRight >= 0, obs = (kpUn.x, kpUn.y, mvuRight), inv_sigma2 = mvInvLevelSigma2[octave]).  Runs g2o's
+ * Levenberg-Marquardt with the Schur-complement solver for `iterations` (10 in the reference) and returns the optimised
+ * poses / points (fixed poses unchanged) plus, per edge, the reference's erase test (:1416-1461: chi2 of the last
+ * evaluated errors > 5.991 / 7.815, or non-positive depth).  Map bookkeeping (EraseMapPointMatch, SetPose, ...) stays in
+ * the shim.  One Pinhole camera for all key frames (RGB-L / RGB-D / stereo rigs of the reference).                     */
+int rgbl_local_bundle_adjustment(rgbl_ctx* ctx, int n_poses, const float* poses /* n_poses x 7: qx qy qz qw tx ty tz */, const uint8_t* pose_fixed,
+                                 int n_points, const float* points /* n_points x 3 */, int n_edges, const int32_t* e_point, const int32_t* e_pose,
+                                 const float* obs /* n_edges x 3 */, const uint8_t* stereo, const float* inv_sigma2, float fx, float fy, float cx,
+                                 float cy, float bf, int iterations, float* poses_out, float* points_out, uint8_t* edge_erase,
+                                 int* iterations_run /* nullable */);
+
 /* ---- Frame::ComputeBoW (src/Frame.cc:828-835) -------------------------------------------------------------------------
  * = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, BowVector&, FeatureVector&, levelsup)
  * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1206, per-feature descent :1218-1259, FORB::distance FORB.cpp:81-101).

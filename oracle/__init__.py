@@ -305,6 +305,8 @@ def _late(L):
     L.orc_pose_optimize.restype = i
     L.orc_compute_bow.argtypes = [i, vp, vp, vp, vp, vp, i, i, vp, i, vp, vp, C.POINTER(i), vp, vp, vp, C.POINTER(i)]
     L.orc_compute_bow.restype = i
+    L.orc_local_bundle_adjustment.argtypes = [i, vp, vp, i, vp, i, vp, vp, vp, vp, vp, f, f, f, f, f, i, vp, vp, vp, vp]
+    L.orc_local_bundle_adjustment.restype = i
     _LATE_DECL_DONE = True
 
 
@@ -433,3 +435,17 @@ def compute_bow(vocab: dict, desc, levelsup: int = 4):
     lib().orc_compute_bow(len(wi), _p(cb), _p(ci), _p(nd), _p(nw), _p(wi), int(vocab["levels"]), n, _p(desc), levelsup,
                           _p(bw), _p(bv), C.byref(k), _p(fn), _p(fs), _p(ff), C.byref(m))
     return (bw[:k.value].copy(), bv[:k.value].copy()), (fn[:m.value].copy(), fs[:m.value + 1].copy(), ff[:fs[m.value]].copy())
+
+
+def local_bundle_adjustment(poses, pose_fixed, points, e_point, e_pose, obs, stereo, inv_sigma2, fx, fy, cx, cy, bf, iterations=10):
+    """Numerical core of Optimizer::LocalBundleAdjustment on a flat graph -> (poses[n,7], points[m,3], erase[n_edges], iterations, chi2)"""
+    _late(lib())
+    poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 7); pose_fixed = np.ascontiguousarray(pose_fixed, np.uint8)
+    points = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    e_point = np.ascontiguousarray(e_point, np.int32); e_pose = np.ascontiguousarray(e_pose, np.int32)
+    obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 3); stereo = np.ascontiguousarray(stereo, np.uint8)
+    inv_sigma2 = np.ascontiguousarray(inv_sigma2, np.float32)
+    po = np.empty_like(poses); pt = np.empty_like(points); er = np.zeros(len(e_point), np.uint8); chi = C.c_double(0)
+    it = lib().orc_local_bundle_adjustment(len(poses), _p(poses), _p(pose_fixed), len(points), _p(points), len(e_point), _p(e_point), _p(e_pose),
+                                           _p(obs), _p(stereo), _p(inv_sigma2), fx, fy, cx, cy, bf, iterations, _p(po), _p(pt), _p(er), C.byref(chi))
+    return po, pt, er, it, chi.value

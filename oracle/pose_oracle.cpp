@@ -18,99 +18,7 @@
 
 namespace {
 
-struct Quat { double x, y, z, w; };
-struct SE3 { Quat r; double t[3]; };
-
-inline void normalize_rotation(SE3& T) {                       // se3quat.h:280-285
-    if (T.r.w < 0) { T.r.x *= -1; T.r.y *= -1; T.r.z *= -1; T.r.w *= -1; }
-    const double n = std::sqrt(T.r.x * T.r.x + T.r.y * T.r.y + T.r.z * T.r.z + T.r.w * T.r.w);
-    T.r.x /= n; T.r.y /= n; T.r.z /= n; T.r.w /= n;
-}
-
-inline void quat_rotate(const Quat& q, const double v[3], double out[3]) {     // Eigen QuaternionBase::_transformVector
-    double uv[3] = {q.y * v[2] - q.z * v[1], q.z * v[0] - q.x * v[2], q.x * v[1] - q.y * v[0]};
-    uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
-    const double c[3] = {q.y * uv[2] - q.z * uv[1], q.z * uv[0] - q.x * uv[2], q.x * uv[1] - q.y * uv[0]};
-    for (int i = 0; i < 3; ++i) out[i] = v[i] + q.w * uv[i] + c[i];
-}
-
-inline void se3_map(const SE3& T, const double p[3], double out[3]) {          // se3quat.h:214-217
-    quat_rotate(T.r, p, out);
-    out[0] += T.t[0]; out[1] += T.t[1]; out[2] += T.t[2];
-}
-
-inline Quat quat_mul(const Quat& a, const Quat& b) {                           // Eigen quaternion product
-    Quat r;
-    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
-    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
-    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
-    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
-    return r;
-}
-
-inline Quat quat_from_matrix(const double R[3][3]) {           // Eigen quaternionbase_assign_impl<Mat,3,3>
-    Quat q;
-    double t = R[0][0] + R[1][1] + R[2][2];
-    if (t > 0) {
-        t = std::sqrt(t + 1.0);
-        q.w = 0.5 * t;
-        t = 0.5 / t;
-        q.x = (R[2][1] - R[1][2]) * t;
-        q.y = (R[0][2] - R[2][0]) * t;
-        q.z = (R[1][0] - R[0][1]) * t;
-    } else {
-        int i = 0;
-        if (R[1][1] > R[0][0]) i = 1;
-        if (R[2][2] > R[i][i]) i = 2;
-        const int j = (i + 1) % 3, k = (j + 1) % 3;
-        t = std::sqrt(R[i][i] - R[j][j] - R[k][k] + 1.0);
-        double v[3];
-        v[i] = 0.5 * t;
-        t = 0.5 / t;
-        q.w = (R[k][j] - R[j][k]) * t;
-        v[j] = (R[j][i] + R[i][j]) * t;
-        v[k] = (R[k][i] + R[i][k]) * t;
-        q.x = v[0]; q.y = v[1]; q.z = v[2];
-    }
-    return q;
-}
-
-SE3 se3_exp(const double u[6]) {                               // se3quat.h:220-254
-    const double om[3] = {u[0], u[1], u[2]}, up[3] = {u[3], u[4], u[5]};
-    const double theta = std::sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
-    const double O[3][3] = {{0, -om[2], om[1]}, {om[2], 0, -om[0]}, {-om[1], om[0], 0}};
-    double O2[3][3];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) O2[i][j] = O[i][0] * O[0][j] + O[i][1] * O[1][j] + O[i][2] * O[2][j];
-    double R[3][3], V[3][3];
-    if (theta < 0.00001) {
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) { R[i][j] = (i == j ? 1.0 : 0.0) + O[i][j] + O2[i][j]; V[i][j] = R[i][j]; }
-    } else {
-        const double a = std::sin(theta) / theta, b = (1 - std::cos(theta)) / (theta * theta),
-                     c = (theta - std::sin(theta)) / std::pow(theta, 3);
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) {
-                R[i][j] = (i == j ? 1.0 : 0.0) + a * O[i][j] + b * O2[i][j];
-                V[i][j] = (i == j ? 1.0 : 0.0) + b * O[i][j] + c * O2[i][j];
-            }
-    }
-    SE3 T;
-    T.r = quat_from_matrix(R);
-    for (int i = 0; i < 3; ++i) T.t[i] = V[i][0] * up[0] + V[i][1] * up[1] + V[i][2] * up[2];
-    normalize_rotation(T);
-    return T;
-}
-
-SE3 se3_mul(const SE3& a, const SE3& b) {                      // se3quat.h:104-110
-    SE3 r = a;
-    double rt[3];
-    quat_rotate(a.r, b.t, rt);
-    r.t[0] += rt[0]; r.t[1] += rt[1]; r.t[2] += rt[2];
-    r.r = quat_mul(a.r, b.r);
-    normalize_rotation(r);
-    return r;
-}
+#include "g2o_se3.inc"
 
 struct Edge {
     double xw[3], obs[3];

@@ -162,6 +162,21 @@ def compute_stereo_matches(extractor: "ORBextractor", images_lr, mb: float, mbf:
     return (kl, dl), (kr, dr), depth[:len(kl)].copy(), ur[:len(kl)].copy()
 
 
+def local_bundle_adjustment(ctx: Context, poses, pose_fixed, points, e_point, e_pose, obs, stereo, inv_sigma2, fx, fy, cx, cy, bf, iterations=10):
+    """Optimizer::LocalBundleAdjustment's numerical core on a flat graph (rgbl_local_bundle_adjustment)
+    -> (poses[n,7], points[m,3], erase[n_edges], iterations_run)"""
+    poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 7); pose_fixed = np.ascontiguousarray(pose_fixed, np.uint8)
+    points = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    e_point = np.ascontiguousarray(e_point, np.int32); e_pose = np.ascontiguousarray(e_pose, np.int32)
+    obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 3); stereo = np.ascontiguousarray(stereo, np.uint8)
+    inv_sigma2 = np.ascontiguousarray(inv_sigma2, np.float32)
+    po = np.empty_like(poses); pt = np.empty_like(points); er = np.zeros(max(len(e_point), 1), np.uint8); it = C.c_int(0)
+    nz = lambda a: ptr(a) if a.size else None
+    check(lib().rgbl_local_bundle_adjustment(ctx.handle, len(poses), nz(poses), nz(pose_fixed), len(points), nz(points), len(e_point), nz(e_point), nz(e_pose),
+                                             nz(obs), nz(stereo), nz(inv_sigma2), fx, fy, cx, cy, bf, iterations, nz(po), nz(pt), ptr(er), C.byref(it)), ctx.handle)
+    return po, pt, er[:len(e_point)], it.value
+
+
 class ORBVocabulary:
     """DBoW2 vocabulary (ORBVocabulary = TemplatedVocabulary<FORB::TDescriptor, FORB>, include/ORBVocabulary.h) uploaded once as a
     flat tree; `transform` = Frame::ComputeBoW's mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4)."""

@@ -371,6 +371,27 @@ def main():
             bow["cpu_ms_per_frame"] = 1e3 * (time.perf_counter() - t0) / len(descs)
             bow["cpu"] = "oracle (std::map restatement of DBoW2 transform), one core"
 
+    # ---- Optimizer::LocalBundleAdjustment (mapping thread, reported on its own) ----
+    lba = None
+    if world == 1 and not args.no_bow:
+        sys.path.insert(0, str(ROOT / "tests"))
+        import ba_data
+        prob = ba_data.make_problem(42, n_kf=20, n_fixed=4, n_points=2500, outlier_frac=0.02)
+        F.local_bundle_adjustment(ctx, *ba_data.args(prob))
+        t0 = time.perf_counter()
+        for _ in range(3):
+            gpo, gpt, ger, git = F.local_bundle_adjustment(ctx, *ba_data.args(prob))
+        gpu_ms = 1e3 * (time.perf_counter() - t0) / 3
+        lba = {"gpu_ms": gpu_ms, "key_frames": 20, "fixed": 4, "points": 2500, "edges": int(len(prob["e_point"])), "lm_iterations": int(git),
+               "timing": "host wall clock per rgbl_local_bundle_adjustment call with host arrays (uploads, ~12 launches + one scalar read-back per LM trial, downloads)"}
+        if not args.no_cpu_baseline:
+            from oracle import local_bundle_adjustment as cpu_lba
+            t0 = time.perf_counter()
+            rpo = cpu_lba(*ba_data.args(prob))[0]
+            lba["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+            lba["cpu"] = "oracle (dense Schur restatement of the g2o problem), one core"
+            lba["max_pose_diff_vs_cpu"] = float(np.abs(gpo - rpo).max())
+
     if rank == 0:
         # roofline of the dominant kernel (per-stage CUDA-event time / launches, measured above)
         levels = []
@@ -445,7 +466,7 @@ def main():
                 "clocks": clocks, "roofline": roofline, "roofline_frame_construction": roofline_streaming, "kernels": kernels, "latency_bound_stages": other,
                 "tracking": {"matches_per_frame": float(np.mean(nm[1:])), "inliers_per_frame": float(np.mean(ni[1:])),
                              "pose_x_error_m_last_frame": float(abs(poses[-1, 4] - seq.pose(T - 1)[4]))},
-                "multi_sequence_capacity": multi, "compute_bow": bow,
+                "multi_sequence_capacity": multi, "compute_bow": bow, "local_bundle_adjustment": lba,
                 "host_quadtree_ms_per_step": prof["_host_quadtree_ms"] / args.steps,
                 "wall_ms_per_step": wall_ms / args.steps}
         if world == 1 and not args.no_cpu_baseline:

@@ -221,14 +221,15 @@ __global__ void __launch_bounds__(128) ba_point_sum_kernel(BaDev g, const double
     for (int t = 0; t < 3; ++t) bl[3 * (size_t)l + t] = a[6 + t];
 }
 
-// H_pp (21 unique) and b_p (6) per non-fixed pose: one warp per pose, lanes stride the pose's edges, fixed shuffle tree
-__global__ void __launch_bounds__(128) ba_pose_sum_kernel(BaDev g, const double* __restrict__ blk, double* __restrict__ Hpp, double* __restrict__ bp) {
-    const int s = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (s >= g.n_opt) return;
+// H_pp (21 unique) and b_p (6) per non-fixed pose: one CTA per pose, threads stride the pose's edges (a key frame sees
+// thousands of points), fixed reduction tree (shuffles inside a warp, then the 8 warp sums in order): deterministic
+__global__ void __launch_bounds__(256) ba_pose_sum_kernel(BaDev g, const double* __restrict__ blk, double* __restrict__ Hpp, double* __restrict__ bp) {
+    __shared__ double sm[8][27];
+    const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double a[27];
 #pragma unroll
     for (int t = 0; t < 27; ++t) a[t] = 0;
-    for (int i = g.ps_start[s] + lane; i < g.ps_start[s + 1]; i += 32) {
+    for (int i = g.ps_start[s] + threadIdx.x; i < g.ps_start[s + 1]; i += 256) {
         const double* o = blk + (size_t)g.ps_edges[i] * kEdgeBlk + 9;
 #pragma unroll
         for (int t = 0; t < 27; ++t) a[t] += o[t];
@@ -238,7 +239,14 @@ __global__ void __launch_bounds__(128) ba_pose_sum_kernel(BaDev g, const double*
         double v = a[t];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) { if (t < 21) Hpp[21 * (size_t)s + t] = v; else bp[6 * (size_t)s + (t - 21)] = v; }
+        if (lane == 0) sm[warp][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 27) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += sm[w][threadIdx.x];
+        if (threadIdx.x < 21) Hpp[21 * (size_t)s + threadIdx.x] = v; else bp[6 * (size_t)s + (threadIdx.x - 21)] = v;
     }
 }
 
@@ -281,81 +289,91 @@ __global__ void __launch_bounds__(256) ba_schur_init_kernel(BaDev g, const doubl
     }
 }
 
+// one warp per point: the lanes share the m^2 pose pairs of the point (m observations)
 __global__ void __launch_bounds__(128) ba_schur_kernel(BaDev g, const double* __restrict__ blk, const double* __restrict__ Hll, const double* __restrict__ bl,
                                                        double lam, double* __restrict__ S, double* __restrict__ coef) {
-    const int l = blockIdx.x * 128 + threadIdx.x;
+    const int l = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (l >= g.n_points) return;
     double D[9];
     dinv3(Hll + 6 * (size_t)l, lam, D);
     const double b0 = bl[3 * (size_t)l], b1 = bl[3 * (size_t)l + 1], b2 = bl[3 * (size_t)l + 2];
     const double db[3] = {D[0] * b0 + D[1] * b1 + D[2] * b2, D[3] * b0 + D[4] * b1 + D[5] * b2, D[6] * b0 + D[7] * b1 + D[8] * b2};
-    const int n = 6 * g.n_opt, eb = g.pt_start[l], ee = g.pt_start[l + 1];
-    for (int i1 = eb; i1 < ee; ++i1) {
-        const int k1 = g.pt_edges[i1], s1 = g.pose_slot[g.e_pose[k1]];
+    const int n = 6 * g.n_opt, eb = g.pt_start[l], m = g.pt_start[l + 1] - eb;
+    for (int i1 = lane; i1 < m; i1 += 32) {
+        const int k1 = g.pt_edges[eb + i1], s1 = g.pose_slot[g.e_pose[k1]];
         if (s1 < 0) continue;
         const double* B1 = blk + (size_t)k1 * kEdgeBlk + 36;
-        double BD[18];
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) BD[3 * i + j] = B1[3 * i] * D[j] + B1[3 * i + 1] * D[3 + j] + B1[3 * i + 2] * D[6 + j];
 #pragma unroll
         for (int i = 0; i < 6; ++i) atomicAdd(&coef[6 * s1 + i], B1[3 * i] * db[0] + B1[3 * i + 1] * db[1] + B1[3 * i + 2] * db[2]);
-        for (int i2 = eb; i2 < ee; ++i2) {
-            const int k2 = g.pt_edges[i2], s2 = g.pose_slot[g.e_pose[k2]];
-            if (s2 < 0 || s2 > s1) continue;                      // lower triangle only (the Cholesky reads it)
-            const double* B2 = blk + (size_t)k2 * kEdgeBlk + 36;
+    }
+    for (int t = lane; t < m * m; t += 32) {
+        const int i1 = t / m, i2 = t - i1 * m;
+        const int k1 = g.pt_edges[eb + i1], k2 = g.pt_edges[eb + i2];
+        const int s1 = g.pose_slot[g.e_pose[k1]], s2 = g.pose_slot[g.e_pose[k2]];
+        if (s1 < 0 || s2 < 0 || s2 > s1) continue;                 // lower triangle only (the Cholesky reads it)
+        const double* B1 = blk + (size_t)k1 * kEdgeBlk + 36;
+        const double* B2 = blk + (size_t)k2 * kEdgeBlk + 36;
+        double b2v[18];
 #pragma unroll
-            for (int i = 0; i < 6; ++i)
+        for (int i = 0; i < 18; ++i) b2v[i] = B2[i];
 #pragma unroll
-                for (int j = 0; j < 6; ++j)
-                    atomicAdd(&S[(size_t)(6 * s1 + i) * n + 6 * s2 + j], -(BD[3 * i] * B2[3 * j] + BD[3 * i + 1] * B2[3 * j + 1] + BD[3 * i + 2] * B2[3 * j + 2]));
+        for (int i = 0; i < 6; ++i) {
+            const double a0 = B1[3 * i], a1 = B1[3 * i + 1], a2 = B1[3 * i + 2];
+            const double bd0 = a0 * D[0] + a1 * D[3] + a2 * D[6], bd1 = a0 * D[1] + a1 * D[4] + a2 * D[7], bd2 = a0 * D[2] + a1 * D[5] + a2 * D[8];
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                atomicAdd(&S[(size_t)(6 * s1 + i) * n + 6 * s2 + j], -(bd0 * b2v[3 * j] + bd1 * b2v[3 * j + 1] + bd2 * b2v[3 * j + 2]));
         }
     }
 }
 
-// dense Cholesky S = L L^T on the lower triangle (in place), then L L^T x = b_p - coef.  status[0] = 1 on a non-positive pivot.
-__global__ void __launch_bounds__(1024) ba_cholesky_kernel(int n, double* __restrict__ S, const double* __restrict__ bp, const double* __restrict__ coef,
+// dense Cholesky S = L L^T on the lower triangle, then L L^T x = b_p - coef, by one CTA.  The matrix is staged in shared
+// memory when it fits (n <= 160: 6 n_opt squared doubles), else it is factored in place in global memory.  status[0] = 1 on a
+// non-positive pivot (g2o: the linear solver fails -> the LM trial is rejected).
+__global__ void __launch_bounds__(1024) ba_cholesky_kernel(int n, int use_smem, double* __restrict__ Sg, const double* __restrict__ bp, const double* __restrict__ coef,
                                                            double* __restrict__ x, int* __restrict__ status) {
-    __shared__ double s_d;
-    __shared__ int s_fail;
-    const int tid = threadIdx.x;
-    if (tid == 0) s_fail = 0;
+    extern __shared__ double s_mat[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* S = use_smem ? s_mat : Sg;
+    double* y = use_smem ? s_mat + (size_t)n * n : x;
+    if (use_smem) for (int i = tid; i < n * n; i += nt) S[i] = Sg[i];
+    for (int i = tid; i < n; i += nt) y[i] = bp[i] - coef[i];
     __syncthreads();
+    // two barriers per column: every thread reads the pivot itself (uniform failure test, no broadcast step)
+    bool fail = false;
     for (int k = 0; k < n; ++k) {
-        if (tid == 0) {
-            const double d = S[(size_t)k * n + k];
-            if (!(d > 0) || !(d <= DBL_MAX)) s_fail = 1;
-            s_d = sqrt(d);
-        }
+        const double d = S[(size_t)k * n + k];
+        if (!(d > 0) || !(d <= DBL_MAX)) { fail = true; break; }
+        const double sd = sqrt(d), inv = 1.0 / sd;
+        __syncthreads();                                          // everyone has read the pivot before it is overwritten
+        for (int i = k + tid; i < n; i += nt) S[(size_t)i * n + k] = (i == k) ? sd : S[(size_t)i * n + k] * inv;
         __syncthreads();
-        if (s_fail) break;
-        const double inv = 1.0 / s_d;
-        for (int i = k + tid; i < n; i += 1024) S[(size_t)i * n + k] = (i == k) ? s_d : S[(size_t)i * n + k] * inv;
-        __syncthreads();
-        // trailing update of the lower triangle: rows i > k, columns k < j <= i
-        const int m = n - k - 1;
-        for (long long t = tid; t < (long long)m * m; t += 1024) {
-            const int i = k + 1 + (int)(t / m), j = k + 1 + (int)(t % m);
-            if (j <= i) S[(size_t)i * n + j] -= S[(size_t)i * n + k] * S[(size_t)j * n + k];
+        // trailing update of the lower triangle (rows i > k, columns k < j <= i) on a 16-wide thread grid: no index divisions
+        const int tx = tid & 15, ty = tid >> 4, ny = nt >> 4;
+        for (int i = k + 1 + ty; i < n; i += ny) {
+            const double lik = S[(size_t)i * n + k];
+            for (int j = k + 1 + tx; j <= i; j += 16) S[(size_t)i * n + j] -= lik * S[(size_t)j * n + k];
         }
         __syncthreads();
     }
-    if (s_fail) { if (tid == 0) status[0] = 1; for (int i = tid; i < n; i += 1024) x[i] = 0; return; }
+    if (fail) { if (tid == 0) status[0] = 1; for (int i = tid; i < n; i += nt) x[i] = 0; return; }
     if (tid == 0) status[0] = 0;
-    // forward / backward substitution by one warp-free thread: n <= a few hundred
-    if (tid == 0) {
-        for (int i = 0; i < n; ++i) {
-            double v = bp[i] - coef[i];
-            for (int m = 0; m < i; ++m) v -= S[(size_t)i * n + m] * x[m];
-            x[i] = v / S[(size_t)i * n + i];
-        }
-        for (int i = n - 1; i >= 0; --i) {
-            double v = x[i];
-            for (int m = i + 1; m < n; ++m) v -= S[(size_t)m * n + i] * x[m];
-            x[i] = v / S[(size_t)i * n + i];
-        }
+    // column-oriented substitutions, one barrier per column: every thread forms y[k] / L[k][k] itself
+    for (int k = 0; k < n; ++k) {
+        const double yk = y[k] / S[(size_t)k * n + k];
+        __syncthreads();
+        if (tid == 0) y[k] = yk;
+        for (int i = k + 1 + tid; i < n; i += nt) y[i] -= S[(size_t)i * n + k] * yk;
+        __syncthreads();
     }
+    for (int k = n - 1; k >= 0; --k) {
+        const double yk = y[k] / S[(size_t)k * n + k];
+        __syncthreads();
+        if (tid == 0) y[k] = yk;
+        for (int i = tid; i < k; i += nt) y[i] -= S[(size_t)k * n + i] * yk;
+        __syncthreads();
+    }
+    if (use_smem) for (int i = tid; i < n; i += nt) x[i] = y[i];
 }
 
 // landmark increments, trial points, gain denominator terms of the landmarks
@@ -537,6 +555,15 @@ extern "C" int rgbl_local_bundle_adjustment(rgbl_ctx* ctx, int n_poses, const fl
     const int init_n = std::max(n_poses, 3 * n_points);
     ba_init_state_kernel<<<(init_n + 255) / 256, 256, 0, st>>>(n_poses, d_poses_f, d_pose[0], 3 * n_points, d_pts_f, d_pts[0]);
 
+    const size_t chol_need = ((size_t)n * n + n) * sizeof(double);
+    const int chol_in_smem = chol_need <= 200 * 1024 ? 1 : 0;
+    const size_t chol_smem = chol_in_smem ? chol_need : 0;
+    const int chol_threads = n <= 192 ? 256 : 1024;          // small systems: cheaper barriers matter more than lanes
+    {
+        static bool done[64] = {};
+        const int dev = c->cfg.device;
+        if (dev >= 0 && dev < 64 && !done[dev]) { cudaFuncSetAttribute(ba_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done[dev] = true; }
+    }
     double* h = reinterpret_cast<double*>(c->h_scalars);      // 16 pinned ints = 8 doubles
     int cur = 0, it_run = 0;
     double lambda = 0, ni = 2;
@@ -548,7 +575,7 @@ extern "C" int rgbl_local_bundle_adjustment(rgbl_ctx* ctx, int n_poses, const fl
         ba_linearize_kernel<<<eb, 128, 0, st>>>(g, d_pose[cur], d_pts[cur], d_err, d_blk, d_part);
         ba_final_sum_kernel<<<1, 256, 0, st>>>(d_part, eb, d_scal + 0);
         ba_point_sum_kernel<<<pb, 128, 0, st>>>(g, d_blk, d_Hll, d_bl);
-        if (n_opt) ba_pose_sum_kernel<<<(n_opt + 3) / 4, 128, 0, st>>>(g, d_blk, d_Hpp, d_bp);
+        if (n_opt) ba_pose_sum_kernel<<<n_opt, 256, 0, st>>>(g, d_blk, d_Hpp, d_bp);
         launches += 4;
         if (it == 0) { ba_maxdiag_kernel<<<1, 256, 0, st>>>(g, d_Hpp, d_Hll, d_scal + 1); ++launches; }
         CU(cudaMemcpyAsync(h, d_scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -561,8 +588,8 @@ extern "C" int rgbl_local_bundle_adjustment(rgbl_ctx* ctx, int n_poses, const fl
             const int nxt = cur ^ 1;
             if (n_opt) {
                 ba_schur_init_kernel<<<std::min((n * n + 255) / 256, 1024), 256, 0, st>>>(g, d_Hpp, lambda, d_S, d_coef);
-                ba_schur_kernel<<<pb, 128, 0, st>>>(g, d_blk, d_Hll, d_bl, lambda, d_S, d_coef);
-                ba_cholesky_kernel<<<1, 1024, 0, st>>>(n, d_S, d_bp, d_coef, d_xp, d_status);
+                ba_schur_kernel<<<(n_points + 3) / 4, 128, 0, st>>>(g, d_blk, d_Hll, d_bl, lambda, d_S, d_coef);
+                ba_cholesky_kernel<<<1, chol_threads, chol_smem, st>>>(n, chol_in_smem, d_S, d_bp, d_coef, d_xp, d_status);
                 launches += 3;
             }
             ba_point_update_kernel<<<pb, 128, 0, st>>>(g, d_blk, d_Hll, d_bl, lambda, d_xp, d_pts[cur], d_pts[nxt], d_part);

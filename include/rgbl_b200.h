@@ -216,6 +216,11 @@ int rgbl_pose_optimize(rgbl_ctx* ctx, const float pose_in[7], int n, const float
  * and leaves its results in HBM until rgbl_resident_download.                                     */
 int rgbl_resident_upload(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
                          const float* const* pts4xn, const int* n_pts);
+/* Same with the point clouds as raw KITTI .bin records, xyzr[f] = n_pts[f] x (x, y, z, reflectance) floats exactly as read from
+ * the file: the element-wise re-layout of LoadPointcloudBinaryMat (Examples/RGB-L/rgbl_kitti.cc:151-185: rows x, y, z and a
+ * row of ones) happens on the device.  The reference reads at most 1 000 000 floats (250 000 points) per file.             */
+int rgbl_resident_upload_kitti(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
+                               const float* const* xyzr, const int* n_pts);
 int rgbl_resident_process(rgbl_ctx* ctx, const float P[12], const rgbl_depth_params* prm, int* n_out /* nullable */);
 int rgbl_resident_download(rgbl_ctx* ctx, rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out);
 

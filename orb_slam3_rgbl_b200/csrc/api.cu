@@ -40,6 +40,7 @@ static void release(Ctx* c) {
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
     if (c->ev_blur) cudaEventDestroy(c->ev_blur);
+    if (c->d_pts_raw) cudaFree(c->d_pts_raw);
     if (c->st_trk) { cudaStreamSynchronize(c->st_trk); cudaStreamDestroy(c->st_trk); }
     if (c->ev_snap) cudaEventDestroy(c->ev_snap);
     if (c->ev_chain_b) cudaEventDestroy(c->ev_chain_b);
@@ -604,8 +605,16 @@ static int check_batch_args(Ctx* c, int n_frames, int width, int height, int str
 }
 
 // H2D of one batch of RGB-L inputs into the context's frame slots (images on the main stream, clouds on aux).
-static int upload_rgbl(Ctx* c, int n_frames, const uint8_t* const* gray, int stride, const float* const* pts4xn, const int* n_pts, int* max_pts_out) {
+// layout 0: planar 4 x N rows (x, y, z, 1) as LoadPointcloudBinaryMat builds them; layout 1: the raw KITTI .bin records
+// (x, y, z, reflectance) x N, de-interleaved on the device (the 4th row becomes 1, Examples/RGB-L/rgbl_kitti.cc:168-177)
+static int upload_rgbl(Ctx* c, int n_frames, const uint8_t* const* gray, int stride, const float* const* pts4xn, const int* n_pts, int* max_pts_out,
+                       int layout = 0) {
     if (!c->d_pts) { c->err = "context was created with max_points == 0"; return RGBL_E_INVALID; }
+    if (layout == 1 && !c->d_pts_raw) {
+        if (cudaMalloc((void**)&c->d_pts_raw, (size_t)c->cfg.max_batch * 4 * c->cfg.max_points * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError(); c->err = "cudaMalloc failed (raw point records)"; return RGBL_E_CUDA;
+        }
+    }
     int max_pts = 0;
     for (int f = 0; f < n_frames; ++f) {
         if (!gray[f]) { c->err = "empty image"; return RGBL_E_EMPTY; }
@@ -614,9 +623,11 @@ static int upload_rgbl(Ctx* c, int n_frames, const uint8_t* const* gray, int str
     }
     for (int f = 0; f < n_frames; ++f) {
         c->h_n_pts[f] = n_pts[f];
-        if (n_pts[f]) CU(cudaMemcpyAsync(c->d_pts + (size_t)f * 4 * c->cfg.max_points, pts4xn[f], (size_t)4 * n_pts[f] * sizeof(float), cudaMemcpyHostToDevice, c->st_aux));
+        float* dst = (layout == 1 ? c->d_pts_raw : c->d_pts) + (size_t)f * 4 * c->cfg.max_points;
+        if (n_pts[f]) CU(cudaMemcpyAsync(dst, pts4xn[f], (size_t)4 * n_pts[f] * sizeof(float), cudaMemcpyHostToDevice, c->st_aux));
     }
     CU(cudaMemcpyAsync(c->d_n_pts, c->h_n_pts, (size_t)n_frames * sizeof(int), cudaMemcpyHostToDevice, c->st_aux));
+    if (layout == 1 && max_pts > 0) launch_deinterleave_xyzr(c->st_aux, c->d_pts_raw, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, max_pts, n_frames);
     int rc = upload_images(c, n_frames, gray, stride, c->st);
     if (rc) return rc;
     c->resident_frames = n_frames;
@@ -680,6 +691,20 @@ int rgbl_resident_upload(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray
     CU(cudaSetDevice(c->cfg.device));
     int max_pts = 0;
     rc = upload_rgbl(c, n_frames, gray, stride, pts4xn, n_pts, &max_pts); if (rc) return rc;
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaStreamSynchronize(c->st_aux));
+    return RGBL_OK;
+}
+
+int rgbl_resident_upload_kitti(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
+                               const float* const* xyzr, const int* n_pts) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!gray || !xyzr || !n_pts) { c->err = "null argument"; return RGBL_E_INVALID; }
+    int rc = check_batch_args(c, n_frames, width, height, stride); if (rc) return rc;
+    CU(cudaSetDevice(c->cfg.device));
+    int max_pts = 0;
+    rc = upload_rgbl(c, n_frames, gray, stride, xyzr, n_pts, &max_pts, 1); if (rc) return rc;
     CU(cudaStreamSynchronize(c->st));
     CU(cudaStreamSynchronize(c->st_aux));
     return RGBL_OK;

@@ -48,6 +48,17 @@ __global__ void __launch_bounds__(256) depth_project_kernel(const float* __restr
     }
 }
 
+// The reference's loader (Examples/RGB-L/rgbl_kitti.cc:151-185) re-lays the .bin records out element by element on the host
+// (x, y, z rows and a row of ones); here the records are uploaded as they are and transposed on the device.
+__global__ void __launch_bounds__(256) deinterleave_xyzr_kernel(const float* __restrict__ raw, float* __restrict__ pts, int pts_stride,
+                                                                const int* __restrict__ n_pts) {
+    const int frame = blockIdx.y, n = n_pts[frame], i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float4 r = __ldg(reinterpret_cast<const float4*>(raw + (size_t)frame * pts_stride) + i);
+    float* X = pts + (size_t)frame * pts_stride;
+    X[i] = r.x; X[n + i] = r.y; X[2 * (size_t)n + i] = r.z; X[3 * (size_t)n + i] = 1.0f;
+}
+
 struct DilateTaps { int n; int8_t dx[81], dy[81]; };
 
 __global__ void __launch_bounds__(256) depth_resolve_dilate_kernel(const float* __restrict__ pts, int pts_stride,
@@ -237,6 +248,11 @@ void launch_depth_project(cudaStream_t st, const float* pts, int pts_stride, con
     if (max_n_pts <= 0) return;
     depth_project_kernel<<<dim3((max_n_pts + 255) / 256, n_frames), 256, 0, st>>>(pts, pts_stride, n_pts, prm, W, H,
                                                                                  idx_map, stamp);
+}
+
+void launch_deinterleave_xyzr(cudaStream_t st, const float* raw, float* pts, int pts_stride, const int* n_pts, int max_n_pts, int n_frames) {
+    if (max_n_pts <= 0) return;
+    deinterleave_xyzr_kernel<<<dim3((max_n_pts + 255) / 256, n_frames), 256, 0, st>>>(raw, pts, pts_stride, n_pts);
 }
 
 void launch_depth_resolve_dilate(cudaStream_t st, const float* pts, int pts_stride, const int* n_pts,

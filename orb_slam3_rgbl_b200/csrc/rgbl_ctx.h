@@ -90,6 +90,7 @@ struct Ctx {
     int* d_n_kp_in = nullptr;
     uint8_t* d_desc = nullptr;
     float* d_pts = nullptr;
+    float* d_pts_raw = nullptr;   // lazily allocated: raw (x, y, z, r) records awaiting de-interleave
     int* d_n_pts = nullptr;
     uint32_t* d_idx_map = nullptr;
     float *d_raw = nullptr, *d_processed = nullptr, *d_depth = nullptr, *d_uright = nullptr;

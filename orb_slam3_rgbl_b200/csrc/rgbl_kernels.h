@@ -55,6 +55,8 @@ struct DepthDev {
     int method, avg_kernel;          // rgbl_depth_method, AverageFiltering kernel size
     float nn_radius;                 // NearestNeighborPixel SearchDistance
 };
+// raw KITTI records (x, y, z, reflectance) x n -> planar rows x | y | z | 1 (frame stride pts_stride floats in both buffers)
+void launch_deinterleave_xyzr(cudaStream_t st, const float* raw, float* pts, int pts_stride, const int* n_pts, int max_n_pts, int n_frames);
 void launch_depth_project(cudaStream_t st, const float* pts, int pts_stride, const int* n_pts, int max_n_pts,
                           const DepthDev& prm, int W, int H, uint32_t* idx_map, uint32_t stamp, int n_frames);
 void launch_depth_resolve_dilate(cudaStream_t st, const float* pts, int pts_stride, const int* n_pts,

@@ -442,6 +442,14 @@ class RgblBatch:
         c = self.ctx
         check(lib().rgbl_resident_upload(c.handle, self.nF, self.ia, self.W, self.H, self.W, self.pa, ptr(self.npts)), c.handle)
 
+    def upload_kitti(self, xyzr_list):
+        """Resident upload with raw KITTI .bin records (n x 4: x, y, z, reflectance) instead of the planar 4 x n clouds."""
+        c = self.ctx
+        raw = [np.ascontiguousarray(r, np.float32).reshape(-1, 4) for r in xyzr_list]
+        npts = np.array([len(r) for r in raw], np.int32)
+        arr = (C.c_void_p * self.nF)(*[r.ctypes.data for r in raw])
+        check(lib().rgbl_resident_upload_kitti(c.handle, self.nF, self.ia, self.W, self.H, self.W, arr, ptr(npts)), c.handle)
+
     def process_resident(self):
         c = self.ctx
         check(lib().rgbl_resident_process(c.handle, ptr(self.P), C.byref(self.prm), ptr(self.n)), c.handle)

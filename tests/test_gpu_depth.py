@@ -73,6 +73,25 @@ def test_frame_rgbl_batch(ctx):
         assert (dep == rdep).all() and (ur == rur).all()
 
 
+def test_raw_kitti_records_equal_host_relayout(ctx):
+    """rgbl_resident_upload_kitti: the .bin records (x, y, z, reflectance) de-interleaved on the device must give exactly what the
+    reference's host loop (LoadPointcloudBinaryMat: rows x, y, z, 1) gives; ragged and empty clouds included."""
+    seeds = (41, 42, 43)
+    imgs = [S.make_image(s) for s in seeds]; pcs = [S.make_pointcloud(s) for s in seeds]
+    pcs[1] = np.ascontiguousarray(pcs[1][:, :77777]); pcs[2] = np.ascontiguousarray(pcs[2][:, :0])
+    rng = np.random.default_rng(0)
+    raw = [np.ascontiguousarray(np.column_stack([pc[0], pc[1], pc[2], rng.random(pc.shape[1], dtype=np.float32)])) for pc in pcs]
+    prm = F.make_depth_params(bf=S.KITTI_BF)
+    b = F.RgblBatch(ctx, imgs, [pc if pc.shape[1] else np.zeros((4, 1), np.float32) for pc in pcs], S.lidar_projection_matrix(), prm, pinned=False)
+    b.npts[:] = [pc.shape[1] for pc in pcs]
+    b.upload(); b.process_resident(); ref = b.download()
+    ref = [tuple(a.copy() for a in fr) for fr in ref]
+    b.upload_kitti(raw); b.process_resident(); got = b.download()
+    for (rk, rd, rdep, rur), (k, d, dep, ur) in zip(ref, got):
+        assert np.array_equal(k, rk) and np.array_equal(d, rd) and np.array_equal(dep, rdep) and np.array_equal(ur, rur)
+    assert (got[0][2] > 0).sum() > 100 and (got[2][2] > 0).sum() == 0        # the empty cloud gives no depth
+
+
 @pytest.mark.parametrize("k", [5, 3, 7])
 def test_average_filtering(ctx, k):
     """LiDAR.Method AverageFiltering (src/DepthModule.cc:200-228): bit-exact incl. the NaN pattern of empty windows."""

@@ -238,6 +238,25 @@ int rgbl_local_bundle_adjustment(rgbl_ctx* ctx, int n_poses, const float* poses 
                                  float cy, float bf, int iterations, float* poses_out, float* points_out, uint8_t* edge_erase,
                                  int* iterations_run /* nullable */);
 
+/* ---- LocalMapping-thread kernels -----------------------------------------------------------------
+ * MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:329-403) for a batch of map points: the descriptors observed for
+ * point p are desc[obs_start[p] .. obs_start[p+1]) (vDescriptors in the reference's order); best[p] = index within that list of
+ * the descriptor with the least median Hamming distance to the others (first minimum), -1 for a point without observations.  */
+int rgbl_distinctive_descriptors(rgbl_ctx* ctx, int n_points, const int32_t* obs_start /* n_points + 1 */, const uint8_t* desc, int32_t* best);
+
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (include/ORBmatcher.h, src/ORBmatcher.cc:907-1146),
+ * Nleft == -1 and one camera.  has_mp*[i] = GetMapPoint(i) != NULL; uright* = mvuRight; feature vectors as CSR like
+ * rgbl_search_by_bow.  The per-pair constants are computed by the shim with the reference's own code: F12 = K1^-T [t12]x R12 K2^-1
+ * (row-major, Pinhole::epipolarConstrain, src/CameraModels/Pinhole.cpp:109-112) and ep = pKF2->mpCamera->project(T2w * Cw);
+ * scale_factors2 / level_sigma2_2 = pKF2->mvScaleFactors / mvLevelSigma2.  match12[idx1] = idx2 or -1 (vMatchedPairs = the
+ * pairs in ascending idx1); *n_matches = the return value.                                                                 */
+int rgbl_search_for_triangulation(rgbl_ctx* ctx, int n1, const uint8_t* desc1, const rgbl_keypoint* keys1, const uint8_t* has_mp1, const float* uright1,
+                                  int n_nodes1, const uint32_t* node_ids1, const int32_t* node_start1, const int32_t* node_feat1,
+                                  int n2, const uint8_t* desc2, const rgbl_keypoint* keys2, const uint8_t* has_mp2, const float* uright2,
+                                  int n_nodes2, const uint32_t* node_ids2, const int32_t* node_start2, const int32_t* node_feat2,
+                                  const float F12[9], const float ep[2], int n_levels, const float* scale_factors2, const float* level_sigma2_2,
+                                  int only_stereo, int coarse, int check_orientation, int32_t* match12, int* n_matches);
+
 /* ---- Frame::ComputeBoW (src/Frame.cc:828-835) -------------------------------------------------------------------------
  * = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, BowVector&, FeatureVector&, levelsup)
  * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1206, per-feature descent :1218-1259, FORB::distance FORB.cpp:81-101).

@@ -307,6 +307,9 @@ def _late(L):
     L.orc_compute_bow.restype = i
     L.orc_local_bundle_adjustment.argtypes = [i, vp, vp, i, vp, i, vp, vp, vp, vp, vp, f, f, f, f, f, i, vp, vp, vp, vp]
     L.orc_local_bundle_adjustment.restype = i
+    L.orc_distinctive_descriptors.argtypes = [i, vp, vp, vp]
+    L.orc_search_for_triangulation.argtypes = [i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, i, i, i, vp]
+    L.orc_search_for_triangulation.restype = i
     _LATE_DECL_DONE = True
 
 
@@ -449,3 +452,27 @@ def local_bundle_adjustment(poses, pose_fixed, points, e_point, e_pose, obs, ste
     it = lib().orc_local_bundle_adjustment(len(poses), _p(poses), _p(pose_fixed), len(points), _p(points), len(e_point), _p(e_point), _p(e_pose),
                                            _p(obs), _p(stereo), _p(inv_sigma2), fx, fy, cx, cy, bf, iterations, _p(po), _p(pt), _p(er), C.byref(chi))
     return po, pt, er, it, chi.value
+
+
+def distinctive_descriptors(obs_start, desc):
+    _late(lib())
+    obs_start = np.ascontiguousarray(obs_start, np.int32); desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    best = np.empty(max(len(obs_start) - 1, 1), np.int32)
+    lib().orc_distinctive_descriptors(len(obs_start) - 1, _p(obs_start), _p(desc), _p(best))
+    return best[:len(obs_start) - 1]
+
+
+def search_for_triangulation(kf1: dict, kf2: dict, F12, ep, scale_factors2, level_sigma2_2, only_stereo=False, coarse=False, check_orientation=True):
+    _late(lib())
+    def unpack(k):
+        return (np.ascontiguousarray(k["desc"], np.uint8), np.ascontiguousarray(k["keys"]), np.ascontiguousarray(k["has_mp"], np.uint8),
+                np.ascontiguousarray(k["uright"], np.float32), np.ascontiguousarray(k["fv"][0], np.uint32), np.ascontiguousarray(k["fv"][1], np.int32),
+                np.ascontiguousarray(k["fv"][2], np.int32))
+    d1, k1, m1, u1, i1, s1, f1 = unpack(kf1); d2, k2, m2, u2, i2, s2, f2 = unpack(kf2)
+    F12 = np.ascontiguousarray(F12, np.float32).reshape(9); ep = np.ascontiguousarray(ep, np.float32)
+    sf = np.ascontiguousarray(scale_factors2, np.float32); sg = np.ascontiguousarray(level_sigma2_2, np.float32)
+    match = np.empty(max(len(d1), 1), np.int32)
+    nm = lib().orc_search_for_triangulation(len(d1), _p(d1), _p(k1), _p(m1), _p(u1), len(i1), _p(i1), _p(s1), _p(f1), len(d2), _p(d2), _p(k2), _p(m2), _p(u2),
+                                            len(i2), _p(i2), _p(s2), _p(f2), _p(F12), _p(ep), _p(sf), _p(sg), int(only_stereo), int(coarse),
+                                            int(check_orientation), _p(match))
+    return nm, match[:len(d1)]

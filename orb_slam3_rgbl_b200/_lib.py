@@ -87,6 +87,9 @@ SYMBOLS = {
     "rgbl_resident_upload_kitti": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "rgbl_resident_process": (_i, [_vp, _vp, C.POINTER(DepthParams), _vp]),
     "rgbl_resident_download": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "rgbl_distinctive_descriptors": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "rgbl_search_for_triangulation": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp,
+                                           _i, _i, _i, _vp, _ip]),
     "rgbl_local_bundle_adjustment": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp, _ip]),
     "rgbl_vocabulary_create": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(C.c_void_p)]),
     "rgbl_vocabulary_destroy": (None, [_vp]),

@@ -162,6 +162,32 @@ def compute_stereo_matches(extractor: "ORBextractor", images_lr, mb: float, mbf:
     return (kl, dl), (kr, dr), depth[:len(kl)].copy(), ur[:len(kl)].copy()
 
 
+def distinctive_descriptors(ctx: Context, obs_start, desc):
+    """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (CSR of observed descriptors) -> best index per point"""
+    obs_start = np.ascontiguousarray(obs_start, np.int32); desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    best = np.empty(max(len(obs_start) - 1, 1), np.int32)
+    check(lib().rgbl_distinctive_descriptors(ctx.handle, len(obs_start) - 1, ptr(obs_start), ptr(desc) if len(desc) else None, ptr(best)), ctx.handle)
+    return best[:len(obs_start) - 1]
+
+
+def search_for_triangulation(ctx: Context, kf1: dict, kf2: dict, F12, ep, scale_factors2, level_sigma2_2, only_stereo=False, coarse=False,
+                             check_orientation=True):
+    """ORBmatcher::SearchForTriangulation; kf = dict(desc, keys, has_mp, uright, fv=(node_ids, node_start, node_feat)) -> (nmatches, match12)"""
+    def unpack(k):
+        return (np.ascontiguousarray(k["desc"], np.uint8), np.ascontiguousarray(k["keys"]), np.ascontiguousarray(k["has_mp"], np.uint8),
+                np.ascontiguousarray(k["uright"], np.float32), np.ascontiguousarray(k["fv"][0], np.uint32), np.ascontiguousarray(k["fv"][1], np.int32),
+                np.ascontiguousarray(k["fv"][2], np.int32))
+    d1, k1, m1, u1, i1, s1, f1 = unpack(kf1); d2, k2, m2, u2, i2, s2, f2 = unpack(kf2)
+    F12 = np.ascontiguousarray(F12, np.float32).reshape(9); ep = np.ascontiguousarray(ep, np.float32)
+    sf = np.ascontiguousarray(scale_factors2, np.float32); sg = np.ascontiguousarray(level_sigma2_2, np.float32)
+    match = np.empty(max(len(d1), 1), np.int32); nm = C.c_int(0)
+    nz = lambda a: ptr(a) if a.size else None
+    check(lib().rgbl_search_for_triangulation(ctx.handle, len(d1), nz(d1), nz(k1), nz(m1), nz(u1), len(i1), nz(i1), nz(s1), nz(f1),
+                                              len(d2), nz(d2), nz(k2), nz(m2), nz(u2), len(i2), nz(i2), nz(s2), nz(f2), ptr(F12), ptr(ep), len(sf), ptr(sf),
+                                              ptr(sg), int(only_stereo), int(coarse), int(check_orientation), ptr(match), C.byref(nm)), ctx.handle)
+    return nm.value, match[:len(d1)]
+
+
 def local_bundle_adjustment(ctx: Context, poses, pose_fixed, points, e_point, e_pose, obs, stereo, inv_sigma2, fx, fy, cx, cy, bf, iterations=10):
     """Optimizer::LocalBundleAdjustment's numerical core on a flat graph (rgbl_local_bundle_adjustment)
     -> (poses[n,7], points[m,3], erase[n_edges], iterations_run)"""

@@ -257,6 +257,15 @@ int rgbl_search_for_triangulation(rgbl_ctx* ctx, int n1, const uint8_t* desc1, c
                                   const float F12[9], const float ep[2], int n_levels, const float* scale_factors2, const float* level_sigma2_2,
                                   int only_stereo, int coarse, int check_orientation, int32_t* match12, int* n_matches);
 
+/* ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, float th, bool bRight = false) (src/ORBmatcher.cc:1148-1330),
+ * the search part (:1176-1303).  kf = the key frame's members (a KeyFrame has the same grid / keypoint members as a Frame);
+ * Tcw = pKF->GetPose(), Ow = pKF->GetCameraCenter(); valid[i] = pMP && !isBad() && !IsInKeyFrame(pKF); mf_min / mf_max =
+ * mfMinDistance / mfMaxDistance.  best_idx[i] / best_dist[i] = bestIdx / bestDist of the reference's loop (-1 / 256 when the
+ * point is rejected or has no candidate); the shim applies `bestDist <= TH_LOW` and the Replace / AddObservation bookkeeping.   */
+int rgbl_fuse_search(rgbl_ctx* ctx, const rgbl_frame_view* kf, const float Tcw[7], const float Ow[3], int n, const uint8_t* valid, const float* xw,
+                     const float* normal, const float* mf_min_dist, const float* mf_max_dist, const uint8_t* mp_desc, float th, int32_t* best_idx,
+                     int32_t* best_dist);
+
 /* ---- Frame::ComputeBoW (src/Frame.cc:828-835) -------------------------------------------------------------------------
  * = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, BowVector&, FeatureVector&, levelsup)
  * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1206, per-feature descent :1218-1259, FORB::distance FORB.cpp:81-101).

@@ -307,6 +307,7 @@ def _late(L):
     L.orc_compute_bow.restype = i
     L.orc_local_bundle_adjustment.argtypes = [i, vp, vp, i, vp, i, vp, vp, vp, vp, vp, f, f, f, f, f, i, vp, vp, vp, vp]
     L.orc_local_bundle_adjustment.restype = i
+    L.orc_fuse_search.argtypes = [fv, vp, vp, i, vp, vp, vp, vp, vp, vp, f, vp, vp]
     L.orc_distinctive_descriptors.argtypes = [i, vp, vp, vp]
     L.orc_search_for_triangulation.argtypes = [i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, i, i, i, vp]
     L.orc_search_for_triangulation.restype = i
@@ -476,3 +477,14 @@ def search_for_triangulation(kf1: dict, kf2: dict, F12, ep, scale_factors2, leve
                                             len(i2), _p(i2), _p(s2), _p(f2), _p(F12), _p(ep), _p(sf), _p(sg), int(only_stereo), int(coarse),
                                             int(check_orientation), _p(match))
     return nm, match[:len(d1)]
+
+
+def fuse_search(kf: FrameView, Tcw, Ow, valid, xw, normal, mf_min_dist, mf_max_dist, mp_desc, th=3.0):
+    _late(lib())
+    Tcw = np.ascontiguousarray(Tcw, np.float32); Ow = np.ascontiguousarray(Ow, np.float32); valid = np.ascontiguousarray(valid, np.uint8)
+    xw = np.ascontiguousarray(xw, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+    mn = np.ascontiguousarray(mf_min_dist, np.float32); mx = np.ascontiguousarray(mf_max_dist, np.float32); d = np.ascontiguousarray(mp_desc, np.uint8)
+    n = len(valid)
+    bi = np.empty(max(n, 1), np.int32); bd = np.empty(max(n, 1), np.int32)
+    lib().orc_fuse_search(C.byref(kf.c), _p(Tcw), _p(Ow), n, _p(valid), _p(xw), _p(normal), _p(mn), _p(mx), _p(d), th, _p(bi), _p(bd))
+    return bi[:n], bd[:n]

@@ -368,6 +368,62 @@ int orc_search_by_bow(int n_kf, const uint8_t* kf_desc, const float* kf_angle, c
     return nmatches;
 }
 
+// ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>&, th, bRight = false) (src/ORBmatcher.cc:1148-1330), the search part:
+// per map point (valid[i] = pMP && !isBad() && !IsInKeyFrame(pKF)) the best key-frame feature in the radius (index, Hamming
+// distance) or (-1, 256); the Replace / AddObservation bookkeeping that follows (:1306-1325) consumes best_dist <= TH_LOW on the
+// host.  The key frame's members the search reads are those of the frame view (KeyFrame::GetFeaturesInArea = Frame's,
+// src/KeyFrame.cc:704-748; IsInImage :750-753; mvInvLevelSigma2 = 1 / scale^2).
+void orc_fuse_search(const orc_frame_view* kf, const float Tcw_[7], const float Ow[3], int n, const uint8_t* valid, const float* xw,
+                     const float* normal, const float* mf_min_dist, const float* mf_max_dist, const uint8_t* mp_desc, float th,
+                     int* best_idx, int* best_dist) {
+    FrameView F = to_view(kf);
+    Grid g; g.build(F);
+    const Pose Tcw = {Tcw_[0], Tcw_[1], Tcw_[2], Tcw_[3], Tcw_[4], Tcw_[5], Tcw_[6]};
+    std::vector<int> cand;
+    for (int i = 0; i < n; ++i) {
+        best_idx[i] = -1; best_dist[i] = 256;
+        if (!valid[i]) continue;
+        const float* P = xw + 3 * i;
+        float Pc[3];
+        transform(Tcw, P, Pc);
+        if (Pc[2] < 0.0f) continue;
+        const float invz = 1 / Pc[2];
+        const float u = F.fx * Pc[0] / Pc[2] + F.cx, v = F.fy * Pc[1] / Pc[2] + F.cy;      // Pinhole::project(Vector3f)
+        if (!(u >= F.min_x && u < F.max_x && v >= F.min_y && v < F.max_y)) continue;        // KeyFrame::IsInImage
+        const float ur = u - F.bf * invz;
+        const float max_d = 1.2f * mf_max_dist[i], min_d = 0.8f * mf_min_dist[i];           // Get{Max,Min}DistanceInvariance
+        const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+        const float dist3D = std::sqrt((PO[0] * PO[0] + PO[1] * PO[1]) + PO[2] * PO[2]);
+        if (dist3D < min_d || dist3D > max_d) continue;
+        const float* Pn = normal + 3 * i;
+        if (((PO[0] * Pn[0] + PO[1] * Pn[1]) + PO[2] * Pn[2]) < 0.5 * dist3D) continue;
+        const float ratio = mf_max_dist[i] / dist3D;                                        // MapPoint::PredictScale(dist, KeyFrame*)
+        int level = (int)std::ceil(std::log(ratio) / F.log_scale_factor);
+        if (level < 0) level = 0; else if (level >= F.n_levels) level = F.n_levels - 1;
+        const float radius = th * F.scale_factors[level];
+        features_in_area(F, g, u, v, radius, -1, -1, cand);
+        int bd = 256, bi = -1;
+        for (int idx : cand) {
+            const KeyPoint& kp = F.keys_un[idx];
+            const int kl = kp.octave;
+            if (kl < level - 1 || kl > level) continue;
+            const float inv_sigma2 = 1.0f / (F.scale_factors[kl] * F.scale_factors[kl]);
+            if (F.uright[idx] >= 0) {
+                const float ex = u - kp.x, ey = v - kp.y, er = ur - F.uright[idx];
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * inv_sigma2 > 7.8) continue;
+            } else {
+                const float ex = u - kp.x, ey = v - kp.y;
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * inv_sigma2 > 5.99) continue;
+            }
+            const int d = descriptor_distance(mp_desc + 32 * (size_t)i, F.desc + 32 * (size_t)idx);
+            if (d < bd) { bd = d; bi = idx; }
+        }
+        best_idx[i] = bi; best_dist[i] = bd;
+    }
+}
+
 // ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame*, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
 // (src/ORBmatcher.cc:1889-2010), the relocalisation refinement.  Per key-frame map point i: valid[i] = (pMP && !isBad() &&
 // !sAlreadyFound.count(pMP)), xw, descriptor, the key frame's keypoint angle, mfMinDistance / mfMaxDistance.

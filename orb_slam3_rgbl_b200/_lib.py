@@ -87,6 +87,7 @@ SYMBOLS = {
     "rgbl_resident_upload_kitti": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "rgbl_resident_process": (_i, [_vp, _vp, C.POINTER(DepthParams), _vp]),
     "rgbl_resident_download": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "rgbl_fuse_search": (_i, [_vp, C.POINTER(FrameViewC), _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp]),
     "rgbl_distinctive_descriptors": (_i, [_vp, _i, _vp, _vp, _vp]),
     "rgbl_search_for_triangulation": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp,
                                            _i, _i, _i, _vp, _ip]),

@@ -274,6 +274,44 @@ int rgbl_pose_optimize(rgbl_ctx* ctx, const float pose_in[7], int n, const float
 }
 
 
+int rgbl_fuse_search(rgbl_ctx* ctx, const rgbl_frame_view* kf, const float Tcw[7], const float Ow[3], int n, const uint8_t* valid, const float* xw,
+                     const float* normal, const float* mf_min_dist, const float* mf_max_dist, const uint8_t* mp_desc, float th, int32_t* best_idx,
+                     int32_t* best_dist) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (c->chain_pending) { c->err = "a tracking chain is in flight (rgbl_resident_track_end not called)"; return RGBL_E_INVALID; }
+    if (!kf || !Tcw || !Ow || n < 0 || (n > 0 && (!valid || !xw || !normal || !mf_min_dist || !mf_max_dist || !mp_desc || !best_idx || !best_dist))) {
+        c->err = "null argument"; return RGBL_E_INVALID;
+    }
+    for (int i = 0; i < n; ++i) { best_idx[i] = -1; best_dist[i] = 256; }
+    if (n == 0 || kf->n == 0) return RGBL_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    FrameDev f;
+    int rc = upload_frame(c, kf, f); if (rc) return rc;
+    rc = ensure_queries(c, n); if (rc) return rc;
+    TrackBufs& t = c->trk;
+    GROW(t.e_idx, t.cap_e_idx, (size_t)2 * n);
+    CU(cudaMemcpyAsync(t.q_u8a, valid, n, cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.q_f3a, xw, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.q_f3b, normal, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.q_f[0], mf_min_dist, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.q_f[1], mf_max_dist, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(t.q_desc, mp_desc, (size_t)n * 32, cudaMemcpyHostToDevice, c->st));
+    float* hp = reinterpret_cast<float*>(c->h_scalars + 4);       // pinned staging (ints 4..13; [0] carries the frame size): pose + camera centre
+    for (int i = 0; i < 7; ++i) hp[i] = Tcw[i];
+    for (int i = 0; i < 3; ++i) hp[7 + i] = Ow[i];
+    CU(cudaMemcpyAsync(t.q_f[2], hp, 10 * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    launch_fuse_search(c->st, f, t.cell_start, t.csr_idx, n, t.q_u8a, t.q_f3a, t.q_f3b, t.q_f[0], t.q_f[1], t.q_desc, t.q_f[2], t.q_f[2] + 7, th,
+                       t.e_idx, t.e_idx + n);
+    stage_end(c, ST_MATCH, c->st, 2);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(best_idx, t.e_idx, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(best_dist, t.e_idx + n, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    prof_collect(c);
+    return RGBL_OK;
+}
+
 int rgbl_stereo_matches(rgbl_ctx* ctx, int slot_left, int slot_right, float mb, float mbf, float* depth, float* uright, int cap) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;

@@ -665,6 +665,77 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
 #endif
 }
 
+// ---- ORBmatcher::Fuse, the search part (src/ORBmatcher.cc:1176-1303): one warp per map point --------------------------
+struct FusePointsDev { int n; const uint8_t* valid; const float* xw; const float* normal; const float* mf_min; const float* mf_max; const uint8_t* desc; };
+
+__global__ void __launch_bounds__(256) fuse_search_kernel(FrameDev f, const int* __restrict__ cell_start, const int* __restrict__ csr_idx,
+                                                          FusePointsDev mp, const float* __restrict__ Tcw, const float* __restrict__ Ow, float th,
+                                                          int* __restrict__ best_idx, int* __restrict__ best_dist) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= mp.n) return;
+    unsigned best = 0xffffffffu;
+    if (mp.valid[q]) {
+        const float P[3] = {mp.xw[3 * q], mp.xw[3 * q + 1], mp.xw[3 * q + 2]};
+        float Pc[3];
+        se3f_rotate(Tcw, P, Pc);
+        Pc[0] = __fadd_rn(Pc[0], Tcw[4]); Pc[1] = __fadd_rn(Pc[1], Tcw[5]); Pc[2] = __fadd_rn(Pc[2], Tcw[6]);
+        bool ok = !(Pc[2] < 0.0f);
+        const float invz = __fdiv_rn(1.0f, Pc[2]);
+        const float u = __fadd_rn(__fdiv_rn(__fmul_rn(f.fx, Pc[0]), Pc[2]), f.cx);
+        const float v = __fadd_rn(__fdiv_rn(__fmul_rn(f.fy, Pc[1]), Pc[2]), f.cy);
+        ok = ok && (u >= f.min_x && u < f.max_x && v >= f.min_y && v < f.max_y);                     // KeyFrame::IsInImage
+        const float ur = __fsub_rn(u, __fmul_rn(f.bf, invz));
+        const float PO[3] = {__fsub_rn(P[0], Ow[0]), __fsub_rn(P[1], Ow[1]), __fsub_rn(P[2], Ow[2])};
+        const float dist3D = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(PO[0], PO[0]), __fmul_rn(PO[1], PO[1])), __fmul_rn(PO[2], PO[2])));
+        const float mf_max = mp.mf_max[q];
+        ok = ok && !(dist3D < __fmul_rn(0.8f, mp.mf_min[q]) || dist3D > __fmul_rn(1.2f, mf_max));
+        const float* Pn = mp.normal + 3 * q;
+        const float dotn = __fadd_rn(__fadd_rn(__fmul_rn(PO[0], Pn[0]), __fmul_rn(PO[1], Pn[1])), __fmul_rn(PO[2], Pn[2]));
+        ok = ok && !((double)dotn < 0.5 * (double)dist3D);
+        if (ok) {
+            const float ratio = __fdiv_rn(mf_max, dist3D);
+            const float lg = (float)log((double)ratio);          // correctly-rounded stand-in for glibc logf (as in frustum_kernel)
+            int level = (int)ceilf(__fdiv_rn(lg, f.log_scale_factor));
+            if (level < 0) level = 0; else if (level >= f.n_levels) level = f.n_levels - 1;
+            const float radius = __fmul_rn(th, f.scale[level]);
+            const CellRange cr = cell_range(f, u, v, radius);
+            if (cr.ok) {
+                const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(mp.desc + (size_t)q * 32));
+                const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(mp.desc + (size_t)q * 32) + 1);
+                for (int ix = cr.min_cx; ix <= cr.max_cx; ++ix) {
+                    const int b = cell_start[ix * kGridRows + cr.min_cy], e = cell_start[ix * kGridRows + cr.max_cy + 1];
+                    for (int p = b + lane; p < e; p += 32) {
+                        const int idx = csr_idx[p];
+                        const rgbl_keypoint kp = f.keys[idx];
+                        if (!(fabsf(__fsub_rn(kp.x, u)) < radius && fabsf(__fsub_rn(kp.y, v)) < radius)) continue;     // GetFeaturesInArea
+                        if (kp.octave < level - 1 || kp.octave > level) continue;
+                        const float sc = f.scale[kp.octave];
+                        const float inv_sigma2 = __fdiv_rn(1.0f, __fmul_rn(sc, sc));                                   // mvInvLevelSigma2
+                        const float ex = __fsub_rn(u, kp.x), ey = __fsub_rn(v, kp.y);
+                        const float urt = f.uright[idx];
+                        if (urt >= 0.f) {
+                            const float er = __fsub_rn(ur, urt);
+                            const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
+                            if ((double)__fmul_rn(e2, inv_sigma2) > 7.8) continue;
+                        } else {
+                            const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                            if ((double)__fmul_rn(e2, inv_sigma2) > 5.99) continue;
+                        }
+                        const int d = hamming256(d0, d1, f.desc + (size_t)idx * 32);
+                        best = min(best, ((unsigned)d << 20) | (unsigned)p);         // strict '<' in scan order = min of (dist, position)
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) {
+        best_idx[q] = best == 0xffffffffu ? -1 : csr_idx[best & kPosMask];
+        best_dist[q] = best == 0xffffffffu ? 256 : (int)(best >> 20);
+    }
+}
+
 // ---- Frame::isInFrustum for a list of local map points ----------------------------------------------
 __global__ void __launch_bounds__(256) frustum_kernel(FrameDev f, FrustumParams prm, int n, const float* __restrict__ xw,
                                                       const float* __restrict__ normal, const float* __restrict__ mf_min,
@@ -916,6 +987,14 @@ void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_sta
     search_reloc_collect_kernel<<<(rp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, rp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
     resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, rp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, obs_pos, rp.angle, 0.f,
                                        prm.check_orientation, prm.orb_dist, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes());
+}
+
+void launch_fuse_search(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, int n, const uint8_t* valid, const float* xw,
+                        const float* normal, const float* mf_min, const float* mf_max, const uint8_t* desc, const float* Tcw, const float* Ow, float th,
+                        int* best_idx, int* best_dist) {
+    if (n <= 0) return;
+    fuse_search_kernel<<<(n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, FusePointsDev{n, valid, xw, normal, mf_min, mf_max, desc}, Tcw, Ow, th,
+                                                  best_idx, best_dist);
 }
 
 void launch_chain_prep(cudaStream_t st, const rgbl_keypoint* kps, const float* depth, const int* n_ptr, const float* last_pose,

@@ -111,6 +111,9 @@ void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q
                        int* n_matches);
 void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const RelocPointsDev& rp,
                          const SearchRelocParams& prm, const uint8_t* obs_pos, MatchScratch s, uint8_t* state, int* match, int* n_matches);
+void launch_fuse_search(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, int n, const uint8_t* valid, const float* xw,
+                        const float* normal, const float* mf_min, const float* mf_max, const uint8_t* desc, const float* Tcw /*7, device*/,
+                        const float* Ow /*3, device*/, float th, int* best_idx, int* best_dist);
 void launch_chain_prep(cudaStream_t st, const rgbl_keypoint* kps, const float* depth, const int* n_ptr, const float* last_pose,
                        const float* cur_pose, const FrameDev& f, int mono, int cap, uint8_t* valid, float* xw, int* octave, float* angle,
                        uint8_t* obs_pos, int* flags, uint8_t* state_clear /* nullable: cap bytes zeroed */);

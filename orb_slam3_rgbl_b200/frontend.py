@@ -162,6 +162,19 @@ def compute_stereo_matches(extractor: "ORBextractor", images_lr, mb: float, mbf:
     return (kl, dl), (kr, dr), depth[:len(kl)].copy(), ur[:len(kl)].copy()
 
 
+def fuse_search(ctx: Context, kf: FrameView, Tcw, Ow, valid, xw, normal, mf_min_dist, mf_max_dist, mp_desc, th=3.0):
+    """Search part of ORBmatcher::Fuse(pKF, vpMapPoints, th) -> (bestIdx[n], bestDist[n])"""
+    Tcw = np.ascontiguousarray(Tcw, np.float32); Ow = np.ascontiguousarray(Ow, np.float32); valid = np.ascontiguousarray(valid, np.uint8)
+    xw = np.ascontiguousarray(xw, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+    mn = np.ascontiguousarray(mf_min_dist, np.float32); mx = np.ascontiguousarray(mf_max_dist, np.float32); d = np.ascontiguousarray(mp_desc, np.uint8)
+    n = len(valid)
+    bi = np.empty(max(n, 1), np.int32); bd = np.empty(max(n, 1), np.int32)
+    nz = lambda a: ptr(a) if a.size else None
+    check(lib().rgbl_fuse_search(ctx.handle, C.byref(kf.c), ptr(Tcw), ptr(Ow), n, nz(valid), nz(xw), nz(normal), nz(mn), nz(mx), nz(d), th, ptr(bi), ptr(bd)),
+          ctx.handle)
+    return bi[:n], bd[:n]
+
+
 def distinctive_descriptors(ctx: Context, obs_start, desc):
     """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (CSR of observed descriptors) -> best index per point"""
     obs_start = np.ascontiguousarray(obs_start, np.int32); desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)

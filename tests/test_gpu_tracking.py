@@ -93,6 +93,26 @@ def test_is_in_frustum_and_local_search(ctx, seq_frames):
     assert (match == rmatch).all() and n == rn
 
 
+def test_fuse_search(ctx, seq_frames):
+    """Search part of ORBmatcher::Fuse: best key-frame feature per map point (index and distance) identical to the oracle."""
+    seq, frames, sf = seq_frames
+    rng = np.random.default_rng(19)
+    xw, desc, normal, mn, mx = TD.local_map([frames[0], frames[2]], [seq.pose(0), seq.pose(2)], sf, rng)
+    kf = frames[1]
+    pose = seq.pose(1)
+    Ow = -pose[4:7].copy()                     # identity rotation in the synthetic sequence
+    ofv = oracle.FrameView(*TD.frame_view_args(kf, sf)); gfv = F.FrameView(*TD.frame_view_args(kf, sf))
+    valid = (rng.random(len(xw)) < 0.85).astype(np.uint8)
+    for th in (3.0, 2.5, 8.0):
+        rbi, rbd = oracle.fuse_search(ofv, pose, Ow, valid, xw, normal, mn, mx, desc, th)
+        gbi, gbd = F.fuse_search(ctx, gfv, pose, Ow, valid, xw, normal, mn, mx, desc, th)
+        assert np.array_equal(gbi, rbi) and np.array_equal(gbd, rbd), (int((gbi != rbi).sum()), int((gbd != rbd).sum()))
+        assert (rbi >= 0).sum() > 300 and (rbd[rbi >= 0] <= 50).sum() > 100
+        assert (rbi[valid == 0] == -1).all()
+    gbi, gbd = F.fuse_search(ctx, gfv, pose, Ow, valid[:0], xw[:0], normal[:0], mn[:0], mx[:0], desc[:0])
+    assert len(gbi) == 0
+
+
 def test_empty_inputs(ctx, seq_frames):
     seq, frames, sf = seq_frames
     cur = frames[1]

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "rgbl_ctx.h"
+#include "rgbl_device.cuh"
 
 namespace rgbl {
 
@@ -529,13 +530,20 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
     static const bool chain_timing = std::getenv("RGBL_CHAIN_TIMING") != nullptr;
     static cudaEvent_t tev[8] = {};
     if (chain_timing && !tev[0]) for (auto& e : tev) cudaEventCreate(&e);
+    // unprojection of frame j's keypoints (map points of the search in frame j + 1)
+    auto prep_of = [&](int j) {
+        ChainPrepDev cp{};
+        cp.kps = t.s_kps + (size_t)j * cap; cp.depth = t.s_depth + (size_t)j * cap; cp.n_ptr = t.s_nsel + j;
+        cp.fx = f.fx; cp.fy = f.fy; cp.cx = f.cx; cp.cy = f.cy; cp.mb = f.mb; cp.mono = mono; cp.cap = cap;
+        cp.valid = t.q_u8a; cp.xw = t.q_f3a; cp.octave = t.q_i; cp.angle = t.q_f[0]; cp.obs_pos = t.q_u8b; cp.flags = d_flags; cp.state_clear = t.state;
+        return cp;
+    };
     for (int k = 1; k < nF; ++k) {
         const bool tm = chain_timing && k == std::max(1, nF / 2);
         const size_t lo = (size_t)(k - 1) * cap, cu = (size_t)k * cap;
         const float* last_pose = t.ch_poses + 7 * (k - 1);
         if (tm) cudaEventRecord(tev[0], cs);
-        launch_chain_prep(cs, t.s_kps + lo, t.s_depth + lo, t.s_nsel + (k - 1), last_pose, last_pose, f, mono, cap,
-                          t.q_u8a, t.q_f3a, t.q_i, t.q_f[0], t.q_u8b, d_flags, t.state);
+        if (k == 1) launch_chain_prep(cs, prep_of(0), last_pose, last_pose);          // later frames: prepared by the previous pose kernel
         f.n = t.s_nsel + k; f.keys = t.s_kps + cu; f.uright = t.s_uright + cu; f.desc = t.s_desc + cu * 32;
         const int* cell_start = t.b_cell_start + (size_t)k * (kGridCols * kGridRows + 1);
         const int* csr_idx = t.b_csr_idx + cu;
@@ -543,15 +551,15 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
         SearchLastParams prm{};
         prm.th = th; prm.check_orientation = 1; prm.cur_pose_dev = last_pose; prm.flags_dev = d_flags;
         LastFrameDev lf{cap, t.q_u8a, t.q_f3a, t.s_desc + lo * 32, t.q_i, t.q_f[0], t.q_u8b};
-        launch_search_last(cs, f, cell_start, csr_idx, lf, prm, ms, t.state, t.match, d_nm + k);
-        if (tm) cudaEventRecord(tev[3], cs);
-        launch_chain_edges(cs, f.keys, f.uright, f.n, t.match, t.q_f3a, f, t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne);
-        if (tm) cudaEventRecord(tev[4], cs);
+        const ChainEdgesOut eo{t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne};
+        launch_search_last(cs, f, cell_start, csr_idx, lf, prm, ms, t.state, t.match, d_nm + k, &eo);     // + edges of the matches
+        if (tm) { cudaEventRecord(tev[3], cs); cudaEventRecord(tev[4], cs); }
         PoseProblemDev p{};
         p.n = 0; p.n_dev = d_ne; p.pose_in_dev = last_pose;
         p.xw = t.e_xw; p.obs = t.e_obs; p.inv_sigma2 = t.e_info; p.stereo = t.e_st;
         p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf;
-        launch_pose_optimize(cs, p, t.pose_work, t.e_lvl, t.e_out, t.ch_poses + 7 * k, d_ni + k);
+        const ChainPrepDev nxt = prep_of(k);
+        launch_pose_optimize(cs, p, t.pose_work, t.e_lvl, t.e_out, t.ch_poses + 7 * k, d_ni + k, (k + 1 < nF) ? &nxt : nullptr);
         if (tm) cudaEventRecord(tev[5], cs);
     }
     if (chain_timing) c->chain_timing_ev = tev;
@@ -561,7 +569,7 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
     CU(cudaMemcpyAsync(c->h_chain_i, t.ch_counts, ((size_t)nF * 2 + 4) * sizeof(int), cudaMemcpyDeviceToHost, cs));
     c->chain_pending = true;
     c->chain_frames = nF;
-    c->chain_launches = 1 + 5 * (nF - 1);
+    c->chain_launches = 2 + 3 * (nF - 1);
     return RGBL_OK;
 }
 
@@ -576,7 +584,7 @@ int rgbl_resident_track_end(rgbl_ctx* ctx, float* poses_out, int* n_matches, int
     const int nF = c->chain_frames;
     if (c->chain_timing_ev) {
         const cudaEvent_t* e = static_cast<const cudaEvent_t*>(c->chain_timing_ev);
-        const char* names[5] = {"chain_prep (+state clear)", "-", "search_last(collect+resolve)", "chain_edges", "pose_optimize"};
+        const char* names[5] = {"chain_prep (first frame only)", "-", "search_last(collect+resolve+edges)", "-", "pose_optimize"};
         for (int i = 0; i < 5; ++i) { float ms = 0; if (cudaEventElapsedTime(&ms, e[i], e[i + 1]) == cudaSuccess) std::fprintf(stderr, "[chain timing] %-30s %8.2f us\n", names[i], ms * 1e3f); }
         cudaGetLastError();
     }

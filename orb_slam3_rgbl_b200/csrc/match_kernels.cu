@@ -115,18 +115,6 @@ __device__ __forceinline__ CellRange cell_range(const FrameDev& f, float x, floa
     return c;
 }
 
-// Sophus::SE3f point action (so3.hpp:358-366, se3.hpp:321-324), float32, no FMA.
-__device__ __forceinline__ void se3f_rotate(const float* T, const float p[3], float out[3]) {
-    const float qx = T[0], qy = T[1], qz = T[2], qw = T[3];
-    float uv[3] = {__fsub_rn(__fmul_rn(qy, p[2]), __fmul_rn(qz, p[1])), __fsub_rn(__fmul_rn(qz, p[0]), __fmul_rn(qx, p[2])),
-                   __fsub_rn(__fmul_rn(qx, p[1]), __fmul_rn(qy, p[0]))};
-    uv[0] = __fadd_rn(uv[0], uv[0]); uv[1] = __fadd_rn(uv[1], uv[1]); uv[2] = __fadd_rn(uv[2], uv[2]);
-    const float c[3] = {__fsub_rn(__fmul_rn(qy, uv[2]), __fmul_rn(qz, uv[1])), __fsub_rn(__fmul_rn(qz, uv[0]), __fmul_rn(qx, uv[2])),
-                        __fsub_rn(__fmul_rn(qx, uv[1]), __fmul_rn(qy, uv[0]))};
-#pragma unroll
-    for (int i = 0; i < 3; ++i) out[i] = __fadd_rn(__fadd_rn(p[i], __fmul_rn(qw, uv[i])), c[i]);
-}
-
 // One warp scans the candidate cells of a query and appends every admissible candidate as
 // key = dist << 20 | csr_pos to the query's list (warp-aggregated append into a global pool).
 // `keep_max` = largest distance that can still influence the decision.
@@ -265,6 +253,14 @@ __global__ void __launch_bounds__(256) search_local_collect_kernel(FrameDev f, c
 // (best / second best with levels, ratio test).  state[f]: 0 free, 1 blocked (holds a point with
 // observations), 2 holds a 0-observation point (may be re-claimed).  match[f]: -1 untouched,
 // >= 0 query index, -2 cleared by the rotation check.
+// Optional tail of resolve_kernel for the resident tracking chain: the matched features become PoseOptimization edges in
+// keypoint order (what Optimizer::PoseOptimization's loop over pFrame->mvpMapPoints produces, src/Optimizer.cc:857-990).
+// Doing it here saves a launch per frame and reads the match table while it is still in shared memory.
+struct ChainEdgesDev {
+    const rgbl_keypoint* kps; const float* uright; const float* last_xw;
+    float* exw; float* eobs; float* einfo; uint8_t* est; int* eidx; int* n_edges;      // n_edges == nullptr: disabled
+};
+
 __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const int* __restrict__ n_q_dev, FrameDev f,
                                                        const int* __restrict__ csr_idx,
                                                        const uint32_t* __restrict__ lists, int list_cap,
@@ -275,7 +271,8 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
                                                        const float* __restrict__ f_angle, uint8_t* __restrict__ state,
                                                        int* __restrict__ minq, int* __restrict__ choice,
                                                        uint8_t* __restrict__ resolved, int* __restrict__ match,
-                                                       int* __restrict__ n_matches, int* __restrict__ rounds_out, int dyn_bytes) {
+                                                       int* __restrict__ n_matches, int* __restrict__ rounds_out, int dyn_bytes,
+                                                       ChainEdgesDev ce) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int hist[kHistoLength];
     __shared__ int keep_bin[3];
@@ -651,6 +648,39 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         __syncthreads();
         for (int i = tid; i < n_f; i += 1024) match[i] = mt[i];
     }
+    if (ce.n_edges) {                     // ordered compaction of the matched features into edges
+        __syncthreads();
+        const int lane = tid & 31, warp = tid >> 5;
+        if (tid == 0) s_total = 0;        // running edge count
+        __syncthreads();
+        for (int b = 0; b < n_f; b += 1024) {
+            const int i = b + tid;
+            const int m = (i < n_f) ? mt[i] : -1;
+            const int flag = m >= 0;
+            int incl = flag;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            int base = s_total;
+            for (int w = 0; w < warp; ++w) base += s_wsum[w];
+            if (flag) {
+                const int e = base + incl - 1;
+                const rgbl_keypoint kp = ce.kps[i];
+                ce.exw[3 * e] = ce.last_xw[3 * m]; ce.exw[3 * e + 1] = ce.last_xw[3 * m + 1]; ce.exw[3 * e + 2] = ce.last_xw[3 * m + 2];
+                const float ur = ce.uright[i];
+                ce.eobs[3 * e] = kp.x; ce.eobs[3 * e + 1] = kp.y; ce.eobs[3 * e + 2] = ur;
+                const float sc = f.scale[kp.octave];
+                ce.einfo[e] = __fdiv_rn(1.0f, __fmul_rn(sc, sc));            // mvInvLevelSigma2 (src/ORBextractor.cc:421-429)
+                ce.est[e] = ur >= 0.f;
+                ce.eidx[e] = i;
+            }
+            __syncthreads();
+            if (tid == 1023) s_total = base + incl;
+            __syncthreads();
+        }
+        if (tid == 0) *ce.n_edges = s_total;
+    }
     {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nm_local += __shfl_down_sync(0xffffffffu, nm_local, o);
@@ -849,46 +879,10 @@ __global__ void __launch_bounds__(256) search_reloc_collect_kernel(FrameDev f, c
 // ---- resident tracking chain (TrackWithMotionModel-style glue between the reference functions) ----------------
 // Every keypoint of the last frame that has a LiDAR depth acts as a map point: Frame::UnprojectStereo
 // (src/Frame.cc:1097-1112) with the last pose, descriptor = the keypoint's own descriptor.
-__global__ void __launch_bounds__(256) chain_prep_kernel(const rgbl_keypoint* __restrict__ kps, const float* __restrict__ depth,
-                                                         const int* __restrict__ n_ptr, const float* __restrict__ last_pose,
-                                                         const float* __restrict__ cur_pose, float fx, float fy, float cx, float cy,
-                                                         float mb, int mono, int cap, uint8_t* __restrict__ valid,
-                                                         float* __restrict__ xw, int* __restrict__ octave, float* __restrict__ angle,
-                                                         uint8_t* __restrict__ obs_pos, int* __restrict__ flags,
-                                                         uint8_t* __restrict__ state_clear) {
+__global__ void __launch_bounds__(256) chain_prep_kernel(ChainPrepDev cp, const float* __restrict__ last_pose, const float* __restrict__ cur_pose) {
     const int i = blockIdx.x * 256 + threadIdx.x;
-    if (state_clear && i < cap) state_clear[i] = 0;      // feature states of the search that follows (saves a memset node)
-    const float inv[4] = {-last_pose[0], -last_pose[1], -last_pose[2], last_pose[3]};
-    if (i == 0) {
-        // bForward / bBackward (src/ORBmatcher.cc:1686-1693): tlc = Tlw * (Tcw^-1).translation()
-        const float cinv[4] = {-cur_pose[0], -cur_pose[1], -cur_pose[2], cur_pose[3]};
-        const float nt[3] = {__fmul_rn(cur_pose[4], -1.f), __fmul_rn(cur_pose[5], -1.f), __fmul_rn(cur_pose[6], -1.f)};
-        float twc[3], r[3];
-        se3f_rotate(cinv, nt, twc);
-        se3f_rotate(last_pose, twc, r);
-        const float tlc_z = __fadd_rn(r[2], last_pose[6]);
-        flags[0] = (tlc_z > mb && !mono) ? 1 : 0;
-        flags[1] = (-tlc_z > mb && !mono) ? 1 : 0;
-    }
-    if (i >= cap) return;
-    uint8_t v = 0;
-    if (i < *n_ptr) {
-        const float z = depth[i];
-        const rgbl_keypoint kp = kps[i];
-        octave[i] = kp.octave; angle[i] = kp.angle; obs_pos[i] = 1;
-        if (z > 0.f) {
-            const float invfx = __fdiv_rn(1.0f, fx), invfy = __fdiv_rn(1.0f, fy);
-            const float pc[3] = {__fmul_rn(__fmul_rn(__fsub_rn(kp.x, cx), z), invfx), __fmul_rn(__fmul_rn(__fsub_rn(kp.y, cy), z), invfy), z};
-            // Twc * x3Dc with Twc = Tcw^-1 = (q*, q* (x) (-t))
-            const float nt[3] = {__fmul_rn(last_pose[4], -1.f), __fmul_rn(last_pose[5], -1.f), __fmul_rn(last_pose[6], -1.f)};
-            float ow[3], pr[3];
-            se3f_rotate(inv, nt, ow);
-            se3f_rotate(inv, pc, pr);
-            xw[3 * i] = __fadd_rn(pr[0], ow[0]); xw[3 * i + 1] = __fadd_rn(pr[1], ow[1]); xw[3 * i + 2] = __fadd_rn(pr[2], ow[2]);
-            v = 1;
-        }
-    }
-    valid[i] = v;
+    if (i == 0) chain_prep_flags(cp, last_pose, cur_pose);
+    if (i < cp.cap) chain_prep_item(cp, last_pose, i);
 }
 
 // ordered compaction of the matched features into PoseOptimization edges (keypoint order)
@@ -955,11 +949,13 @@ void launch_grid_build_batch(cudaStream_t st, const FrameDev& f, int n_frames, i
 }
 
 void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LastFrameDev& lf,
-                        const SearchLastParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches) {
+                        const SearchLastParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches,
+                        const ChainEdgesOut* edges) {
     if (lf.n <= 0) return;
     search_last_collect_kernel<<<(lf.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lf, prm, s.lists, s.list_cap, s.list_n, s.overflow);
     resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, lf.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lf.obs_pos, lf.angle, 0.f,
-                                       prm.check_orientation, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes());
+                                       prm.check_orientation, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(),
+                                       edges ? ChainEdgesDev{f.keys, f.uright, lf.xw, edges->exw, edges->eobs, edges->einfo, edges->est, edges->eidx, edges->n_edges} : ChainEdgesDev{});
 }
 
 void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LocalPointsDev& lp,
@@ -967,7 +963,7 @@ void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_sta
     if (lp.n <= 0) return;
     search_local_collect_kernel<<<(lp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
     resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(1, lp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lp.obs_pos, nullptr, prm.nn_ratio,
-                                       0, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes());
+                                       0, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{});
 }
 
 void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q_feat, const int* q_cbeg, const int* q_cend,
@@ -978,7 +974,7 @@ void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q
     bow_collect_kernel<<<(n_q + 7) / 8, 256, 0, st>>>(n_q, q_feat, q_cbeg, q_cend, kf_desc, f_desc, f_node_feat, keep_max, s.lists, s.list_cap,
                                                     s.list_n, s.overflow);
     resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(2, n_q, nullptr, f, f_node_feat, s.lists, s.list_cap, s.list_n, obs_pos, q_angle, nn_ratio,
-                                       check_orientation, 50 /* TH_LOW */, f_angle, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes());
+                                       check_orientation, 50 /* TH_LOW */, f_angle, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{});
 }
 
 void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const RelocPointsDev& rp,
@@ -986,7 +982,7 @@ void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_sta
     if (rp.n <= 0) return;
     search_reloc_collect_kernel<<<(rp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, rp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
     resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, rp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, obs_pos, rp.angle, 0.f,
-                                       prm.check_orientation, prm.orb_dist, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes());
+                                       prm.check_orientation, prm.orb_dist, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{});
 }
 
 void launch_fuse_search(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, int n, const uint8_t* valid, const float* xw,
@@ -997,11 +993,8 @@ void launch_fuse_search(cudaStream_t st, const FrameDev& f, const int* cell_star
                                                   best_idx, best_dist);
 }
 
-void launch_chain_prep(cudaStream_t st, const rgbl_keypoint* kps, const float* depth, const int* n_ptr, const float* last_pose,
-                       const float* cur_pose, const FrameDev& f, int mono, int cap, uint8_t* valid, float* xw, int* octave, float* angle,
-                       uint8_t* obs_pos, int* flags, uint8_t* state_clear) {
-    chain_prep_kernel<<<(cap + 255) / 256, 256, 0, st>>>(kps, depth, n_ptr, last_pose, cur_pose, f.fx, f.fy, f.cx, f.cy, f.mb, mono, cap,
-                                                       valid, xw, octave, angle, obs_pos, flags, state_clear);
+void launch_chain_prep(cudaStream_t st, const ChainPrepDev& cp, const float* last_pose, const float* cur_pose) {
+    chain_prep_kernel<<<(cp.cap + 255) / 256, 256, 0, st>>>(cp, last_pose, cur_pose);
 }
 
 void launch_chain_edges(cudaStream_t st, const rgbl_keypoint* kps, const float* uright, const int* n_ptr, const int* match,

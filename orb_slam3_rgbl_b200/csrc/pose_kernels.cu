@@ -236,7 +236,7 @@ __device__ constexpr bool kJnz[3][6] = {{true, true, true, true, false, true}, {
 
 __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblemDev p, double* __restrict__ work, uint8_t* __restrict__ level,
                                                             uint8_t* __restrict__ outlier, float* __restrict__ pose_out,
-                                                            int* __restrict__ n_inliers) {
+                                                            int* __restrict__ n_inliers, ChainPrepDev next) {
     __shared__ double red[kPoseWarps * kAcc];
     __shared__ double acc[kAcc];
     __shared__ Se3d s_est, s_init, s_cand[kMaxTrials];
@@ -253,9 +253,17 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
 #endif
     const float* pose_in = p.pose_in_dev ? p.pose_in_dev : p.pose_in;
 
+    // resident chain: with the final pose known, unproject this frame's LiDAR-depth keypoints for the next frame's search
+    auto prepare_next = [&]() {
+        if (!next.kps) return;
+        __syncthreads();                  // pose_out written by thread 0 / threads 0..6
+        if (tid == 0) chain_prep_flags(next, pose_out, pose_out);
+        for (int i = tid; i < next.cap; i += kPoseThreads) chain_prep_item(next, pose_out, i);
+    };
     if (n < 3) {                      // src/Optimizer.cc:996
         if (tid < 7) pose_out[tid] = pose_in[tid];
         if (tid == 0) *n_inliers = 0;
+        prepare_next();
         return;
     }
     const float delta_mono_f = sqrtf(5.991f), delta_stereo_f = sqrtf(7.815f);           // float deltaMono = sqrt(5.991)
@@ -516,11 +524,12 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
         printf("pose n=%d total=%lld build=%lld(%d) breduce=%lld solve=%lld eval=%lld(%d) evalred=%lld solve6=%lld\n", n, clock64() - t0_, tm[0], tc[0], tm[1], tm[2], tm[3], tc[1], tm[4], tm[5]);
 #endif
     }
+    prepare_next();
 }
 
 void launch_pose_optimize(cudaStream_t st, const PoseProblemDev& p, double* work, uint8_t* level, uint8_t* outlier,
-                          float* pose_out, int* n_inliers) {
-    pose_optimize_kernel<<<1, kPoseThreads, 0, st>>>(p, work, level, outlier, pose_out, n_inliers);
+                          float* pose_out, int* n_inliers, const ChainPrepDev* next) {
+    pose_optimize_kernel<<<1, kPoseThreads, 0, st>>>(p, work, level, outlier, pose_out, n_inliers, next ? *next : ChainPrepDev{});
 }
 
 }  // namespace rgbl

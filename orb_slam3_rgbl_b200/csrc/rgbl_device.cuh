@@ -137,5 +137,65 @@ RGBL_HD int fast_arc_strength16(int v, const int r[16]) {
     return kb > kd ? kb : kd;
 }
 
+#if defined(__CUDACC__)
+// Sophus::SE3f point action (so3.hpp:358-366, se3.hpp:321-324), float32, no FMA.
+__device__ __forceinline__ void se3f_rotate(const float* T, const float p[3], float out[3]) {
+    const float qx = T[0], qy = T[1], qz = T[2], qw = T[3];
+    float uv[3] = {__fsub_rn(__fmul_rn(qy, p[2]), __fmul_rn(qz, p[1])), __fsub_rn(__fmul_rn(qz, p[0]), __fmul_rn(qx, p[2])),
+                   __fsub_rn(__fmul_rn(qx, p[1]), __fmul_rn(qy, p[0]))};
+    uv[0] = __fadd_rn(uv[0], uv[0]); uv[1] = __fadd_rn(uv[1], uv[1]); uv[2] = __fadd_rn(uv[2], uv[2]);
+    const float c[3] = {__fsub_rn(__fmul_rn(qy, uv[2]), __fmul_rn(qz, uv[1])), __fsub_rn(__fmul_rn(qz, uv[0]), __fmul_rn(qx, uv[2])),
+                        __fsub_rn(__fmul_rn(qx, uv[1]), __fmul_rn(qy, uv[0]))};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[i] = __fadd_rn(__fadd_rn(p[i], __fmul_rn(qw, uv[i])), c[i]);
+}
+
+
+// ---- resident tracking chain: the previous frame's LiDAR-depth keypoints as map points -----------------------------------
+// Frame::UnprojectStereo (src/Frame.cc:1097-1112) with the frame's estimated pose, the bForward / bBackward test of
+// SearchByProjection (src/ORBmatcher.cc:1686-1693) and the per-point fields the search reads.  Shared by chain_prep_kernel and
+// the tail of pose_optimize_kernel (which prepares the next frame's search as soon as the pose is known: one launch less).
+struct ChainPrepDev {
+    const rgbl_keypoint* kps; const float* depth; const int* n_ptr;      // kps == nullptr: disabled
+    float fx, fy, cx, cy, mb; int mono, cap;
+    uint8_t* valid; float* xw; int* octave; float* angle; uint8_t* obs_pos; int* flags; uint8_t* state_clear;
+};
+
+__device__ __forceinline__ void chain_prep_flags(const ChainPrepDev& cp, const float* last_pose, const float* cur_pose) {
+    // tlc = Tlw * (Tcw^-1).translation()
+    const float cinv[4] = {-cur_pose[0], -cur_pose[1], -cur_pose[2], cur_pose[3]};
+    const float nt[3] = {__fmul_rn(cur_pose[4], -1.f), __fmul_rn(cur_pose[5], -1.f), __fmul_rn(cur_pose[6], -1.f)};
+    float twc[3], r[3];
+    se3f_rotate(cinv, nt, twc);
+    se3f_rotate(last_pose, twc, r);
+    const float tlc_z = __fadd_rn(r[2], last_pose[6]);
+    cp.flags[0] = (tlc_z > cp.mb && !cp.mono) ? 1 : 0;
+    cp.flags[1] = (-tlc_z > cp.mb && !cp.mono) ? 1 : 0;
+}
+
+__device__ __forceinline__ void chain_prep_item(const ChainPrepDev& cp, const float* last_pose, int i) {
+    if (cp.state_clear) cp.state_clear[i] = 0;           // feature states of the search that follows (saves a memset node)
+    uint8_t v = 0;
+    if (i < *cp.n_ptr) {
+        const float z = cp.depth[i];
+        const rgbl_keypoint kp = cp.kps[i];
+        cp.octave[i] = kp.octave; cp.angle[i] = kp.angle; cp.obs_pos[i] = 1;
+        if (z > 0.f) {
+            const float inv[4] = {-last_pose[0], -last_pose[1], -last_pose[2], last_pose[3]};
+            const float invfx = __fdiv_rn(1.0f, cp.fx), invfy = __fdiv_rn(1.0f, cp.fy);
+            const float pc[3] = {__fmul_rn(__fmul_rn(__fsub_rn(kp.x, cp.cx), z), invfx), __fmul_rn(__fmul_rn(__fsub_rn(kp.y, cp.cy), z), invfy), z};
+            // Twc * x3Dc with Twc = Tcw^-1 = (q*, q* (x) (-t))
+            const float nt[3] = {__fmul_rn(last_pose[4], -1.f), __fmul_rn(last_pose[5], -1.f), __fmul_rn(last_pose[6], -1.f)};
+            float ow[3], pr[3];
+            se3f_rotate(inv, nt, ow);
+            se3f_rotate(inv, pc, pr);
+            cp.xw[3 * i] = __fadd_rn(pr[0], ow[0]); cp.xw[3 * i + 1] = __fadd_rn(pr[1], ow[1]); cp.xw[3 * i + 2] = __fadd_rn(pr[2], ow[2]);
+            v = 1;
+        }
+    }
+    cp.valid[i] = v;
+}
+#endif  // __CUDACC__
+
 }  // namespace rgbl
 #endif

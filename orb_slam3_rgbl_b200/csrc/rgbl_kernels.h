@@ -101,8 +101,11 @@ struct MatchScratch { uint32_t* lists; int list_cap; int* list_n; int* minq; int
 void launch_grid_build(cudaStream_t st, const FrameDev& f, int* cell_start, int* csr_idx, int* kp_cell);
 // one CTA per frame: frame b reads f.n[b], f.keys + b * kp_stride and writes cell_start + b * (cells + 1), csr_idx / kp_cell + b * kp_stride
 void launch_grid_build_batch(cudaStream_t st, const FrameDev& f, int n_frames, int kp_stride, int* cell_start, int* csr_idx, int* kp_cell);
+// edges != nullptr: the resolution kernel also writes the matched features as PoseOptimization edges (resident tracking chain)
+struct ChainEdgesOut { float* exw; float* eobs; float* einfo; uint8_t* est; int* eidx; int* n_edges; };
 void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LastFrameDev& lf,
-                        const SearchLastParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches);
+                        const SearchLastParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches,
+                        const ChainEdgesOut* edges = nullptr);
 void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LocalPointsDev& lp,
                          const SearchLocalParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches);
 void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q_feat, const int* q_cbeg, const int* q_cend,
@@ -114,9 +117,9 @@ void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_sta
 void launch_fuse_search(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, int n, const uint8_t* valid, const float* xw,
                         const float* normal, const float* mf_min, const float* mf_max, const uint8_t* desc, const float* Tcw /*7, device*/,
                         const float* Ow /*3, device*/, float th, int* best_idx, int* best_dist);
-void launch_chain_prep(cudaStream_t st, const rgbl_keypoint* kps, const float* depth, const int* n_ptr, const float* last_pose,
-                       const float* cur_pose, const FrameDev& f, int mono, int cap, uint8_t* valid, float* xw, int* octave, float* angle,
-                       uint8_t* obs_pos, int* flags, uint8_t* state_clear /* nullable: cap bytes zeroed */);
+// ChainPrepDev (rgbl_device.cuh): unprojection of one frame's LiDAR-depth keypoints with its pose = the map points of the next search
+struct ChainPrepDev;
+void launch_chain_prep(cudaStream_t st, const ChainPrepDev& cp, const float* last_pose, const float* cur_pose);
 void launch_chain_edges(cudaStream_t st, const rgbl_keypoint* kps, const float* uright, const int* n_ptr, const int* match,
                         const float* last_xw, const FrameDev& f, float* exw, float* eobs, float* einfo, uint8_t* est, int* eidx, int* n_edges);
 void launch_frustum(cudaStream_t st, const FrameDev& f, const FrustumParams& prm, int n, const float* xw, const float* normal,
@@ -138,8 +141,9 @@ struct PoseProblemDev {
     float fx, fy, cx, cy, bf;
     float pose_in[7];
 };
+// next != nullptr: after the pose is final the kernel also runs the chain preparation of the NEXT frame's search with it
 void launch_pose_optimize(cudaStream_t st, const PoseProblemDev& p, double* work /* n*4 doubles */, uint8_t* level, uint8_t* outlier,
-                          float* pose_out /*7*/, int* n_inliers);
+                          float* pose_out /*7*/, int* n_inliers, const ChainPrepDev* next = nullptr);
 
 // bow_kernels.cu ------------------------------------------------------------------------------------
 struct VocabDev {                    // DBoW2 vocabulary, flattened (node 0 = root)

@@ -392,6 +392,47 @@ def main():
             lba["cpu"] = "oracle (dense Schur restatement of the g2o problem), one core"
             lba["max_pose_diff_vs_cpu"] = float(np.abs(gpo - rpo).max())
 
+    # ---- online use: ONE new frame at a time through the individual C-ABI calls a tracking thread makes (host buffers in and
+    # out of every call): Frame construction -> SearchByProjection(last frame) -> PoseOptimization.  Latency, not throughput.
+    online = None
+    if world == 1 and not args.no_bow:
+        def unproject_identity_rotation(fr, pose_):        # Frame::UnprojectStereo (src/Frame.cc:1097-1112); the synthetic camera does not rotate
+            f32 = np.float32
+            z = fr["dep"]; zz = np.where(z > 0, z, f32(1)).astype(f32)
+            x = ((fr["k"]["x"] - f32(S.KITTI_CX)) * zz * f32(1.0 / np.float32(S.KITTI_FX))).astype(f32)
+            y = ((fr["k"]["y"] - f32(S.KITTI_CY)) * zz * f32(1.0 / np.float32(S.KITTI_FY))).astype(f32)
+            return (np.stack([x, y, zz], 1) - np.asarray(pose_[4:7], f32)).astype(f32), (z > 0)
+
+        c1 = F.Context(S.KITTI_W, S.KITTI_H, 2000, max_batch=1, max_points=max_pts, device=local_rank)
+        matcher = F.ORBmatcher(c1, 0.9, True)
+        sfac = F.orb_tables(2000)["scale"][:8].astype(np.float32)
+        t_stage = np.zeros(3); n_on = 0; pose = seq.pose(0); last = None
+        for t in range(min(T, 14)):
+            t0 = time.perf_counter()
+            (k, d, dep, ur), = F.frame_rgbl_batch(c1, [imgs[t]], [pcs[t]], P, prm)
+            t1 = time.perf_counter()
+            cur = dict(k=k, d=d, dep=dep, ur=ur)
+            if last is not None:
+                xw, ok = unproject_identity_rotation(last, pose)
+                gfv = F.FrameView(k, ur, d, S.KITTI_W, S.KITTI_H, sfac, *CAM)
+                _, match = matcher.SearchByProjectionLastFrame(gfv, pose, pose, ok.astype(np.uint8), xw, last["d"], last["k"]["octave"],
+                                                               last["k"]["angle"], np.ones(len(ok), np.uint8), 15.0)
+                t2 = time.perf_counter()
+                m = np.nonzero(match >= 0)[0]
+                obs = np.stack([k["x"][m], k["y"][m], ur[m]], 1)
+                inv_s2 = (1.0 / sfac[k["octave"][m]] ** 2).astype(np.float32)
+                _, pose, _ = F.Optimizer.PoseOptimization(c1, pose, xw[match[m]], obs, inv_s2, (ur[m] >= 0).astype(np.uint8), *CAM)
+                t3 = time.perf_counter()
+                if t >= 3:
+                    t_stage += [t1 - t0, t2 - t1, t3 - t2]; n_on += 1
+            last = cur
+        c1.close()
+        if n_on:
+            ms = 1e3 * t_stage / n_on
+            online = {"per_frame_ms": float(ms.sum()), "frame_construction_ms": float(ms[0]), "search_by_projection_ms": float(ms[1]),
+                      "pose_optimization_ms": float(ms[2]), "frames": n_on,
+                      "note": "one frame per call, host arrays in and out of each C-ABI call, Python glue (unprojection, edge assembly in numpy) included"}
+
     if rank == 0:
         # roofline of the dominant kernel (per-stage CUDA-event time / launches, measured above)
         levels = []
@@ -466,7 +507,7 @@ def main():
                 "clocks": clocks, "roofline": roofline, "roofline_frame_construction": roofline_streaming, "kernels": kernels, "latency_bound_stages": other,
                 "tracking": {"matches_per_frame": float(np.mean(nm[1:])), "inliers_per_frame": float(np.mean(ni[1:])),
                              "pose_x_error_m_last_frame": float(abs(poses[-1, 4] - seq.pose(T - 1)[4]))},
-                "multi_sequence_capacity": multi, "compute_bow": bow, "local_bundle_adjustment": lba,
+                "multi_sequence_capacity": multi, "compute_bow": bow, "local_bundle_adjustment": lba, "online_single_frame": online,
                 "host_quadtree_ms_per_step": prof["_host_quadtree_ms"] / args.steps,
                 "wall_ms_per_step": wall_ms / args.steps}
         if world == 1 and not args.no_cpu_baseline:

@@ -253,12 +253,12 @@ def main():
         """k steps, software-pipelined the way the reference's tracking thread is: the frame construction of batch i
         (rgbl_resident_process) is issued while the tracking chain of batch i-1 still runs on the tracking stream; every
         batch is fully processed and its poses are read back; the last chain is drained inside the timed region."""
-        pending = False
-        for _ in range(k):
-            n = batch.process_resident()
-            if pending:
-                batch.track_end()
-            batch.track_begin(pose0, *CAM, th=15.0); pending = True
+        n = batch.process_resident()
+        batch.track_begin(pose0, *CAM, th=15.0)
+        for _ in range(k - 1):
+            n = batch.process_resident()                 # frame construction of the next batch while the chain runs
+            batch.track_begin(pose0, *CAM, th=15.0)      # queued behind the running chain: no host gap between two chains
+            batch.track_end()                            # poses of the oldest chain
         poses, nm, ni = batch.track_end()
         return n, poses, nm, ni
 
@@ -282,12 +282,12 @@ def main():
 
     # ---- end to end through the C ABI with host buffers ("e2e") ----
     def e2e_steps(k):
-        pending = False
-        for _ in range(k):
-            batch.run_e2e()                              # H2D inputs, kernels, D2H keypoints/descriptors/depths
-            if pending:
-                batch.track_end()                        # D2H poses + counts of the previous batch
-            batch.track_begin(pose0, *CAM, th=15.0); pending = True
+        batch.run_e2e()                                  # H2D inputs, kernels, D2H keypoints/descriptors/depths
+        batch.track_begin(pose0, *CAM, th=15.0)
+        for _ in range(k - 1):
+            batch.run_e2e()
+            batch.track_begin(pose0, *CAM, th=15.0)
+            batch.track_end()                            # D2H poses + counts of the oldest chain
         return batch.track_end()
 
     e2e_steps(2)

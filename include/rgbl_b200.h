@@ -298,10 +298,12 @@ int rgbl_resident_track(rgbl_ctx* ctx, const float pose0[7], float fx, float fy,
                         float* poses_out, int* n_matches, int* n_inliers);
 
 /* Asynchronous form of the same chain.  _begin copies the batch's frame outputs into chain-owned buffers, enqueues the chain
- * on the context's tracking stream and returns at once; _end blocks until it has finished and writes the results.  Between
- * the two calls rgbl_resident_process / rgbl_resident_upload may be called for the NEXT batch (frame construction of batch
- * i+1 then overlaps the tracking of batch i, as the tracking thread's pipeline does in the reference); every other
- * tracking entry point returns RGBL_E_INVALID until _end has been called.                                              */
+ * on the context's tracking stream and returns at once; _end blocks until the OLDEST queued chain has finished and writes its
+ * results.  Up to two chains may be queued (FIFO): between _begin and _end the caller runs rgbl_resident_process /
+ * rgbl_resident_upload / rgbl_frame_rgbl_batch for the NEXT batch and may already _begin its chain, which starts on the
+ * device the moment the previous one ends (frame construction of batch i+1 overlaps the tracking of batch i, as the tracking
+ * thread's pipeline does in the reference, and the device never waits for the host between two batches).  Every other
+ * tracking entry point returns RGBL_E_INVALID while a chain is in flight.                                                */
 int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono);
 int rgbl_resident_track_end(rgbl_ctx* ctx, float* poses_out, int* n_matches, int* n_inliers);
 

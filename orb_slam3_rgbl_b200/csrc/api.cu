@@ -43,8 +43,11 @@ static void release(Ctx* c) {
     if (c->d_pts_raw) cudaFree(c->d_pts_raw);
     if (c->st_trk) { cudaStreamSynchronize(c->st_trk); cudaStreamDestroy(c->st_trk); }
     if (c->ev_snap) cudaEventDestroy(c->ev_snap);
-    if (c->ev_chain_b) cudaEventDestroy(c->ev_chain_b);
-    if (c->ev_chain_e) cudaEventDestroy(c->ev_chain_e);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_chain_b[i]) cudaEventDestroy(c->ev_chain_b[i]);
+        if (c->ev_chain_e[i]) cudaEventDestroy(c->ev_chain_e[i]);
+        if (c->ev_chain_done[i]) cudaEventDestroy(c->ev_chain_done[i]);
+    }
     if (c->h_chain_f) cudaFreeHost(c->h_chain_f);
     if (c->h_chain_i) cudaFreeHost(c->h_chain_i);
     if (c->st) cudaStreamDestroy(c->st);

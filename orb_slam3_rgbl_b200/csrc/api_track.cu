@@ -462,8 +462,9 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
     if (!pose0) { c->err = "null argument"; return RGBL_E_INVALID; }
-    if (c->chain_pending) { c->err = "a tracking chain is already in flight: call rgbl_resident_track_end first"; return RGBL_E_INVALID; }
+    if (c->chain_pending >= 2) { c->err = "two tracking chains are already queued: call rgbl_resident_track_end first"; return RGBL_E_INVALID; }
     const int nF = c->last_frames, cap = c->cap_kp;
+    const int slot = (c->chain_head + c->chain_pending) & 1;
     if (nF < 1) { c->err = "nothing processed"; return RGBL_E_INVALID; }
     CU(cudaSetDevice(c->cfg.device));
     if (!c->st_trk) {
@@ -471,16 +472,19 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CU(cudaStreamCreateWithPriority(&c->st_trk, cudaStreamNonBlocking, hi));
         CU(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
-        CU(cudaEventCreate(&c->ev_chain_b));
-        CU(cudaEventCreate(&c->ev_chain_e));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreate(&c->ev_chain_b[i])); CU(cudaEventCreate(&c->ev_chain_e[i]));
+            CU(cudaEventCreateWithFlags(&c->ev_chain_done[i], cudaEventDisableTiming));
+        }
     }
     if (c->h_chain_cap < (size_t)nF) {
+        if (c->chain_pending) { c->err = "batch size grew while a chain is in flight"; return RGBL_E_INVALID; }
         if (c->h_chain_f) cudaFreeHost(c->h_chain_f);
         if (c->h_chain_i) cudaFreeHost(c->h_chain_i);
         c->h_chain_f = nullptr; c->h_chain_i = nullptr; c->h_chain_cap = 0;
         const size_t capF = (size_t)std::max(nF, c->cfg.max_batch);
-        CU(cudaMallocHost(&c->h_chain_f, (7 + capF * 7) * sizeof(float)));
-        CU(cudaMallocHost(&c->h_chain_i, (2 * capF + 4) * sizeof(int)));
+        CU(cudaMallocHost(&c->h_chain_f, 2 * (7 + capF * 7) * sizeof(float)));
+        CU(cudaMallocHost(&c->h_chain_i, 2 * (2 * capF + 4) * sizeof(int)));
         c->h_chain_cap = capF;
     }
     int rc = ensure_frame(c, cap); if (rc) return rc;
@@ -491,25 +495,35 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
     GROW(t.ch_poses, t.cap_ch_poses, (size_t)nF * 7); GROW(t.ch_counts, t.cap_ch_counts, (size_t)nF * 2 + 4);
     GROW(t.e_xw, t.cap_e_xw, (size_t)cap * 3); GROW(t.e_obs, t.cap_e_obs, (size_t)cap * 3); GROW(t.e_info, t.cap_e_info, cap);
     GROW(t.e_st, t.cap_e_st, cap); GROW(t.e_lvl, t.cap_e_lvl, cap); GROW(t.e_out, t.cap_e_out, cap); GROW(t.e_idx, t.cap_e_idx, cap);
-    GROW(t.s_kps, t.cap_s_kps, tot); GROW(t.s_desc, t.cap_s_desc, tot * 32); GROW(t.s_depth, t.cap_s_depth, tot);
-    GROW(t.s_uright, t.cap_s_uright, tot); GROW(t.s_nsel, t.cap_s_nsel, nF);
-    GROW(t.b_cell_start, t.cap_b_cell_start, (size_t)nF * (kGridCols * kGridRows + 1));
-    GROW(t.b_csr_idx, t.cap_b_csr_idx, tot); GROW(t.b_kp_cell, t.cap_b_kp_cell, tot);
+    // per-slot buffers: twice the size, the slot picks its half (sizes are those of the context's full batch so that the halves
+    // never move while a chain is in flight)
+    const size_t tot_full = (size_t)std::max(nF, c->cfg.max_batch) * cap, nF_full = (size_t)std::max(nF, c->cfg.max_batch);
+    const size_t cs_full = nF_full * (kGridCols * kGridRows + 1);
+    if (c->chain_pending && (t.cap_s_kps < 2 * tot_full || t.cap_b_cell_start < 2 * cs_full)) { c->err = "batch size grew while a chain is in flight"; return RGBL_E_INVALID; }
+    GROW(t.s_kps, t.cap_s_kps, 2 * tot_full); GROW(t.s_desc, t.cap_s_desc, 2 * tot_full * 32); GROW(t.s_depth, t.cap_s_depth, 2 * tot_full);
+    GROW(t.s_uright, t.cap_s_uright, 2 * tot_full); GROW(t.s_nsel, t.cap_s_nsel, 2 * nF_full);
+    GROW(t.b_cell_start, t.cap_b_cell_start, 2 * cs_full);
+    GROW(t.b_csr_idx, t.cap_b_csr_idx, 2 * tot_full); GROW(t.b_kp_cell, t.cap_b_kp_cell, 2 * tot_full);
+    rgbl_keypoint* s_kps = t.s_kps + slot * tot_full; uint8_t* s_desc = t.s_desc + slot * tot_full * 32;
+    float* s_depth = t.s_depth + slot * tot_full; float* s_uright = t.s_uright + slot * tot_full; int* s_nsel = t.s_nsel + slot * nF_full;
+    int* b_cell_start = t.b_cell_start + slot * cs_full; int* b_csr_idx = t.b_csr_idx + slot * tot_full; int* b_kp_cell = t.b_kp_cell + slot * tot_full;
+    float* h_f = c->h_chain_f + (size_t)slot * (7 + c->h_chain_cap * 7);
+    int* h_i = c->h_chain_i + (size_t)slot * (2 * c->h_chain_cap + 4);
 
     // snapshot on the frame-construction stream (ordered after the batch's kernels, before the next batch's)
-    CU(cudaMemcpyAsync(t.s_kps, c->d_kps, tot * sizeof(rgbl_keypoint), cudaMemcpyDeviceToDevice, c->st));
-    CU(cudaMemcpyAsync(t.s_desc, c->d_desc, tot * 32, cudaMemcpyDeviceToDevice, c->st));
-    CU(cudaMemcpyAsync(t.s_depth, c->d_depth, tot * sizeof(float), cudaMemcpyDeviceToDevice, c->st));
-    CU(cudaMemcpyAsync(t.s_uright, c->d_uright, tot * sizeof(float), cudaMemcpyDeviceToDevice, c->st));
-    CU(cudaMemcpyAsync(t.s_nsel, c->d_n_sel, (size_t)nF * sizeof(int), cudaMemcpyDeviceToDevice, c->st));
+    CU(cudaMemcpyAsync(s_kps, c->d_kps, tot * sizeof(rgbl_keypoint), cudaMemcpyDeviceToDevice, c->st));
+    CU(cudaMemcpyAsync(s_desc, c->d_desc, tot * 32, cudaMemcpyDeviceToDevice, c->st));
+    CU(cudaMemcpyAsync(s_depth, c->d_depth, tot * sizeof(float), cudaMemcpyDeviceToDevice, c->st));
+    CU(cudaMemcpyAsync(s_uright, c->d_uright, tot * sizeof(float), cudaMemcpyDeviceToDevice, c->st));
+    CU(cudaMemcpyAsync(s_nsel, c->d_n_sel, (size_t)nF * sizeof(int), cudaMemcpyDeviceToDevice, c->st));
     CU(cudaEventRecord(c->ev_snap, c->st));
     CU(cudaStreamWaitEvent(c->st_aux, c->ev_snap, 0));      // the aux stream writes depth / uright of the next batch
     cudaStream_t cs = c->st_trk;
     CU(cudaStreamWaitEvent(cs, c->ev_snap, 0));
 
-    for (int i = 0; i < 7; ++i) c->h_chain_f[i] = pose0[i];
-    if (c->prof_on) CU(cudaEventRecord(c->ev_chain_b, cs));
-    CU(cudaMemcpyAsync(t.ch_poses, c->h_chain_f, 7 * sizeof(float), cudaMemcpyHostToDevice, cs));
+    for (int i = 0; i < 7; ++i) h_f[i] = pose0[i];
+    if (c->prof_on) CU(cudaEventRecord(c->ev_chain_b[slot], cs));
+    CU(cudaMemcpyAsync(t.ch_poses, h_f, 7 * sizeof(float), cudaMemcpyHostToDevice, cs));
     CU(cudaMemsetAsync(t.ch_counts, 0, ((size_t)nF * 2 + 4) * sizeof(int), cs));
     int* d_nm = t.ch_counts; int* d_ni = t.ch_counts + nF; int* d_ne = t.ch_counts + 2 * nF; int* d_flags = t.ch_counts + 2 * nF + 1;
     int* d_ovf = t.ch_counts + 2 * nF + 2;
@@ -524,8 +538,8 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
     MatchScratch ms = scratch(c);
     ms.overflow = d_ovf;
     // the 64x48 grids do not depend on the poses: all frames in one launch (one CTA per frame)
-    f.n = t.s_nsel; f.keys = t.s_kps;
-    launch_grid_build_batch(cs, f, nF, cap, t.b_cell_start, t.b_csr_idx, t.b_kp_cell);
+    f.n = s_nsel; f.keys = s_kps;
+    launch_grid_build_batch(cs, f, nF, cap, b_cell_start, b_csr_idx, b_kp_cell);
     // RGBL_CHAIN_TIMING=1: CUDA events between the launches of the middle frame (warm, in-stream kernel times; stderr at _end)
     static const bool chain_timing = std::getenv("RGBL_CHAIN_TIMING") != nullptr;
     static cudaEvent_t tev[8] = {};
@@ -533,7 +547,7 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
     // unprojection of frame j's keypoints (map points of the search in frame j + 1)
     auto prep_of = [&](int j) {
         ChainPrepDev cp{};
-        cp.kps = t.s_kps + (size_t)j * cap; cp.depth = t.s_depth + (size_t)j * cap; cp.n_ptr = t.s_nsel + j;
+        cp.kps = s_kps + (size_t)j * cap; cp.depth = s_depth + (size_t)j * cap; cp.n_ptr = s_nsel + j;
         cp.fx = f.fx; cp.fy = f.fy; cp.cx = f.cx; cp.cy = f.cy; cp.mb = f.mb; cp.mono = mono; cp.cap = cap;
         cp.valid = t.q_u8a; cp.xw = t.q_f3a; cp.octave = t.q_i; cp.angle = t.q_f[0]; cp.obs_pos = t.q_u8b; cp.flags = d_flags; cp.state_clear = t.state;
         return cp;
@@ -544,13 +558,13 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
         const float* last_pose = t.ch_poses + 7 * (k - 1);
         if (tm) cudaEventRecord(tev[0], cs);
         if (k == 1) launch_chain_prep(cs, prep_of(0), last_pose, last_pose);          // later frames: prepared by the previous pose kernel
-        f.n = t.s_nsel + k; f.keys = t.s_kps + cu; f.uright = t.s_uright + cu; f.desc = t.s_desc + cu * 32;
-        const int* cell_start = t.b_cell_start + (size_t)k * (kGridCols * kGridRows + 1);
-        const int* csr_idx = t.b_csr_idx + cu;
+        f.n = s_nsel + k; f.keys = s_kps + cu; f.uright = s_uright + cu; f.desc = s_desc + cu * 32;
+        const int* cell_start = b_cell_start + (size_t)k * (kGridCols * kGridRows + 1);
+        const int* csr_idx = b_csr_idx + cu;
         if (tm) { cudaEventRecord(tev[1], cs); cudaEventRecord(tev[2], cs); }
         SearchLastParams prm{};
         prm.th = th; prm.check_orientation = 1; prm.cur_pose_dev = last_pose; prm.flags_dev = d_flags;
-        LastFrameDev lf{cap, t.q_u8a, t.q_f3a, t.s_desc + lo * 32, t.q_i, t.q_f[0], t.q_u8b};
+        LastFrameDev lf{cap, t.q_u8a, t.q_f3a, s_desc + lo * 32, t.q_i, t.q_f[0], t.q_u8b};
         const ChainEdgesOut eo{t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne};
         launch_search_last(cs, f, cell_start, csr_idx, lf, prm, ms, t.state, t.match, d_nm + k, &eo);     // + edges of the matches
         if (tm) { cudaEventRecord(tev[3], cs); cudaEventRecord(tev[4], cs); }
@@ -563,13 +577,14 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
         if (tm) cudaEventRecord(tev[5], cs);
     }
     if (chain_timing) c->chain_timing_ev = tev;
-    if (c->prof_on) CU(cudaEventRecord(c->ev_chain_e, cs));
+    if (c->prof_on) CU(cudaEventRecord(c->ev_chain_e[slot], cs));
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(c->h_chain_f + 7, t.ch_poses, (size_t)nF * 7 * sizeof(float), cudaMemcpyDeviceToHost, cs));
-    CU(cudaMemcpyAsync(c->h_chain_i, t.ch_counts, ((size_t)nF * 2 + 4) * sizeof(int), cudaMemcpyDeviceToHost, cs));
-    c->chain_pending = true;
-    c->chain_frames = nF;
-    c->chain_launches = 2 + 3 * (nF - 1);
+    CU(cudaMemcpyAsync(h_f + 7, t.ch_poses, (size_t)nF * 7 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    CU(cudaMemcpyAsync(h_i, t.ch_counts, ((size_t)nF * 2 + 4) * sizeof(int), cudaMemcpyDeviceToHost, cs));
+    CU(cudaEventRecord(c->ev_chain_done[slot], cs));
+    c->chain_frames[slot] = nF;
+    c->chain_launches[slot] = 2 + 3 * (nF - 1);
+    c->chain_pending += 1;
     return RGBL_OK;
 }
 
@@ -579,28 +594,32 @@ int rgbl_resident_track_end(rgbl_ctx* ctx, float* poses_out, int* n_matches, int
     if (!poses_out || !n_matches || !n_inliers) { c->err = "null argument"; return RGBL_E_INVALID; }
     if (!c->chain_pending) { c->err = "no tracking chain in flight"; return RGBL_E_INVALID; }
     CU(cudaSetDevice(c->cfg.device));
-    c->chain_pending = false;
-    CU(cudaStreamSynchronize(c->st_trk));
-    const int nF = c->chain_frames;
-    if (c->chain_timing_ev) {
+    const int slot = c->chain_head;
+    c->chain_head ^= 1;
+    c->chain_pending -= 1;
+    CU(cudaEventSynchronize(c->ev_chain_done[slot]));            // the oldest chain only: a younger one may still be running
+    const int nF = c->chain_frames[slot];
+    const float* h_f = c->h_chain_f + (size_t)slot * (7 + c->h_chain_cap * 7);
+    const int* h_i = c->h_chain_i + (size_t)slot * (2 * c->h_chain_cap + 4);
+    if (c->chain_timing_ev && c->chain_pending == 0) {
         const cudaEvent_t* e = static_cast<const cudaEvent_t*>(c->chain_timing_ev);
         const char* names[5] = {"chain_prep (first frame only)", "-", "search_last(collect+resolve+edges)", "-", "pose_optimize"};
-        for (int i = 0; i < 5; ++i) { float ms = 0; if (cudaEventElapsedTime(&ms, e[i], e[i + 1]) == cudaSuccess) std::fprintf(stderr, "[chain timing] %-30s %8.2f us\n", names[i], ms * 1e3f); }
+        for (int i = 0; i < 5; ++i) { float ms = 0; if (cudaEventElapsedTime(&ms, e[i], e[i + 1]) == cudaSuccess) std::fprintf(stderr, "[chain timing] %-36s %8.2f us\n", names[i], ms * 1e3f); }
         cudaGetLastError();
     }
-    std::memcpy(poses_out, c->h_chain_f + 7, (size_t)nF * 7 * sizeof(float));
-    std::memcpy(n_matches, c->h_chain_i, (size_t)nF * sizeof(int));
-    std::memcpy(n_inliers, c->h_chain_i + nF, (size_t)nF * sizeof(int));
-    c->total_launches += c->chain_launches;
+    std::memcpy(poses_out, h_f + 7, (size_t)nF * 7 * sizeof(float));
+    std::memcpy(n_matches, h_i, (size_t)nF * sizeof(int));
+    std::memcpy(n_inliers, h_i + nF, (size_t)nF * sizeof(int));
+    c->total_launches += c->chain_launches[slot];
     if (c->prof_on) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, c->ev_chain_b, c->ev_chain_e) == cudaSuccess) {
-            c->st_ms[ST_MATCH] += ms; c->st_calls[ST_MATCH] += 1; c->st_launches[ST_MATCH] += c->chain_launches;
+        if (cudaEventElapsedTime(&ms, c->ev_chain_b[slot], c->ev_chain_e[slot]) == cudaSuccess) {
+            c->st_ms[ST_MATCH] += ms; c->st_calls[ST_MATCH] += 1; c->st_launches[ST_MATCH] += c->chain_launches[slot];
         } else {
             cudaGetLastError();
         }
     }
-    if (c->h_chain_i[2 * nF + 2]) { c->err = "matcher candidate list overflow"; return RGBL_E_CAPACITY; }
+    if (h_i[2 * nF + 2]) { c->err = "matcher candidate list overflow"; return RGBL_E_CAPACITY; }
     return RGBL_OK;
 }
 
@@ -609,6 +628,7 @@ int rgbl_resident_track(rgbl_ctx* ctx, const float pose0[7], float fx, float fy,
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
     if (!pose0 || !poses_out || !n_matches || !n_inliers) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (c->chain_pending) { c->err = "a tracking chain is in flight (rgbl_resident_track_end not called)"; return RGBL_E_INVALID; }
     const int rc = rgbl_resident_track_begin(ctx, pose0, fx, fy, cx, cy, bf, th, mono);
     if (rc) return rc;
     return rgbl_resident_track_end(ctx, poses_out, n_matches, n_inliers);

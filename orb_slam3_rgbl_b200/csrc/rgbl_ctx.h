@@ -126,12 +126,16 @@ struct Ctx {
 
     // asynchronous tracking chain (rgbl_resident_track_begin / _end): own high-priority stream, pinned result staging
     cudaStream_t st_trk = nullptr;
-    cudaEvent_t ev_snap = nullptr, ev_chain_b = nullptr, ev_chain_e = nullptr;
-    bool chain_pending = false;
-    int chain_frames = 0, chain_launches = 0;
-    float* h_chain_f = nullptr;  // pinned: pose0 (7) | poses (max_batch * 7)
-    int* h_chain_i = nullptr;    // pinned: n_matches | n_inliers | overflow
-    size_t h_chain_cap = 0;
+    // Up to two chains may be queued (slots 0 / 1, FIFO): the second one is enqueued behind the first on the tracking stream,
+    // so the device never waits for the host between two batches.  Per slot: snapshot buffers (TrackBufs::s_*, b_*, carved by
+    // slot), pinned result staging, completion and profiling events.
+    cudaEvent_t ev_snap = nullptr, ev_chain_b[2] = {}, ev_chain_e[2] = {}, ev_chain_done[2] = {};
+    int chain_pending = 0;       // chains in flight (0..2)
+    int chain_head = 0;          // slot of the oldest chain in flight
+    int chain_frames[2] = {}, chain_launches[2] = {};
+    float* h_chain_f = nullptr;  // pinned, per slot: pose0 (7) | poses (cap * 7)
+    int* h_chain_i = nullptr;    // pinned, per slot: n_matches | n_inliers | n_edges, flags, overflow
+    size_t h_chain_cap = 0;      // frames per slot
     const void* chain_timing_ev = nullptr;   // RGBL_CHAIN_TIMING development aid
 
     int last_frames = 0;         // frames valid in the device buffers

@@ -192,14 +192,19 @@ def test_async_chain_overlapping_next_batch_is_identical():
         for _ in range(3):
             A.upload(); A.process_resident()
             A.track_begin(seqA.pose(0), *TD.CAM, th=15.0)
-            with pytest.raises(Exception):
-                A.track_begin(seqA.pose(0), *TD.CAM, th=15.0)       # one chain at a time
             B.upload(); nB = B.process_resident().copy()            # overwrites every frame buffer of the context
-            gotA = A.track_end()
-            B.track_begin(seqB.pose(0), *TD.CAM, th=15.0)
-            outB = B.download()                                     # D2H of B's frame outputs while B's chain runs
+            B.track_begin(seqB.pose(0), *TD.CAM, th=15.0)           # queued behind A's chain (second slot)
+            with pytest.raises(Exception):
+                B.track_begin(seqB.pose(0), *TD.CAM, th=15.0)       # at most two chains in flight
+            with pytest.raises(Exception):
+                B.track(seqB.pose(0), *TD.CAM, th=15.0)             # the synchronous form needs an empty queue
+            outB = B.download()                                     # D2H of B's frame outputs while the chains run
+            gotA = A.track_end()                                    # FIFO: the oldest chain first
+            A.upload(); A.process_resident()
+            A.track_begin(seqA.pose(0), *TD.CAM, th=15.0)           # slot of the chain just collected, behind B's
             gotB = B.track_end()
-            for got, ref in ((gotA, refA), (gotB, refB)):
+            gotA2 = A.track_end()
+            for got, ref in ((gotA, refA), (gotB, refB), (gotA2, refA)):
                 assert np.array_equal(got[0], ref[0]) and (got[1] == ref[1]).all() and (got[2] == ref[2]).all()
             assert [len(o[0]) for o in outB] == list(nB)
         with pytest.raises(Exception):

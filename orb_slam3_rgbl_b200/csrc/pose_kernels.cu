@@ -202,6 +202,7 @@ __device__ __forceinline__ void huber(double e2, double delta, float dsqr, doubl
 constexpr int kAcc = 28;      // 21 H + 6 b + 1 chi
 constexpr int kPoseThreads = 512, kPoseWarps = kPoseThreads / 32;
 constexpr int kMaxTrials = 10;    // g2o _maxTrialsAfterFailure
+constexpr int kCacheEdges = 1024; // edges whose camera-frame point is cached in shared memory (32 KB)
 
 // block-wide sum of kAcc doubles.  Inside a warp the 28 sums are folded with a halving butterfly: at distance h every lane
 // keeps one half of its slots and ships the other half to its partner, so 16+8+4+2+1 = 31 exchanges replace 28 x 5 and
@@ -237,11 +238,15 @@ __device__ constexpr bool kJnz[3][6] = {{true, true, true, true, false, true}, {
 __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblemDev p, double* __restrict__ work, uint8_t* __restrict__ level,
                                                             uint8_t* __restrict__ outlier, float* __restrict__ pose_out,
                                                             int* __restrict__ n_inliers, ChainPrepDev next) {
+    // camera-frame point and 1/z of every edge at the LAST evaluated trial.  When that trial was accepted (s_cache_ok) the
+    // estimate the next system is built at IS that trial: the build reads pc, 1/z (here) and the errors (work[]) instead of
+    // redoing the SE3 action and the reciprocal - the head of its FP64 dependency chain.
+    __shared__ double s_pc[4][kCacheEdges];
     __shared__ double red[kPoseWarps * kAcc];
     __shared__ double acc[kAcc];
     __shared__ Se3d s_est, s_init, s_cand[kMaxTrials];
     __shared__ double s_cinv[kMaxTrials], s_lambda, s_ni, s_current, s_ini;
-    __shared__ int s_nbad_lm, s_ok, s_cok[kMaxTrials], s_continue;
+    __shared__ int s_cache_ok, s_nbad_lm, s_ok, s_cok[kMaxTrials], s_continue;
     const int tid = threadIdx.x, n = p.n_dev ? *p.n_dev : p.n;
 #ifdef POSE_TIMING
     long long tm[6] = {0, 0, 0, 0, 0, 0}; int tc[3] = {0, 0, 0}; long long t0_ = clock64(), tA_;
@@ -310,6 +315,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
             Edge E;
             load_edge(T, k, E);
             if (!E.active) continue;
+            if (k < kCacheEdges) { s_pc[0][k] = E.pc[0]; s_pc[1][k] = E.pc[1]; s_pc[2][k] = E.pc[2]; s_pc[3][k] = E.invz; }
             work[3 * (size_t)k] = E.e[0]; work[3 * (size_t)k + 1] = E.e[1]; work[3 * (size_t)k + 2] = E.e[2];
             double chi = E.e[0] * (E.info * E.e[0]) + E.e[1] * (E.info * E.e[1]) + E.e[2] * (E.info * E.e[2]);
             if (robust) { double r0, r1; huber(chi, E.st ? ds : dm, E.st ? dsqr_s : dsqr_m, r0, r1); chi = r0; }
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
     };
 
     for (int it = 0; it < 4; ++it) {
-        if (tid == 0) { s_est = s_init; s_ok = 1; }
+        if (tid == 0) { s_est = s_init; s_ok = 1; s_cache_ok = 0; }
         __syncthreads();
         for (int iter = 0; iter < 10; ++iter) {
             if (!s_ok) break;
@@ -331,7 +337,13 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
                 const Se3d T = s_est;
                 for (int k = tid; k < n; k += kPoseThreads) {
                     Edge E;
-                    load_edge(T, k, E);
+                    if (s_cache_ok && k < kCacheEdges) {
+                        E.st = p.stereo[k] != 0; E.info = (double)p.inv_sigma2[k]; E.active = level[k] == 0;
+                        E.pc[0] = s_pc[0][k]; E.pc[1] = s_pc[1][k]; E.pc[2] = s_pc[2][k]; E.invz = s_pc[3][k];
+                        E.e[0] = work[3 * (size_t)k]; E.e[1] = work[3 * (size_t)k + 1]; E.e[2] = work[3 * (size_t)k + 2];
+                    } else {
+                        load_edge(T, k, E);
+                    }
                     if (!E.active) continue;
                     const bool st = E.st;
                     const double info = E.info, x = E.pc[0], y = E.pc[1], invz = E.invz, invz_2 = invz * invz;
@@ -453,9 +465,9 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
                                 double alpha = 1. - r21 * r21 * r21;
                                 alpha = fmin(alpha, 2. / 3.);
                                 const double sf = fmax(1. / 3., alpha);
-                                s_lambda *= sf; s_ni = 2; s_current = temp; s_est = s_cand[trial];
+                                s_lambda *= sf; s_ni = 2; s_current = temp; s_est = s_cand[trial]; s_cache_ok = 1;
                             } else {
-                                s_lambda *= s_ni; s_ni *= 2;          // the estimate is restored = left untouched
+                                s_lambda *= s_ni; s_ni *= 2; s_cache_ok = 0;       // the estimate is restored = left untouched
                             }
                             const int qmax = trial + 1;
                             const int cont = (rho < 0 && qmax < kMaxTrials) ? 1 : 0;

@@ -44,6 +44,7 @@ static void release(Ctx* c) {
     if (c->st_trk) { cudaStreamSynchronize(c->st_trk); cudaStreamDestroy(c->st_trk); }
     if (c->ev_snap) cudaEventDestroy(c->ev_snap);
     for (int i = 0; i < 2; ++i) {
+        if (c->chain_exec[i]) cudaGraphExecDestroy(c->chain_exec[i]);
         if (c->ev_chain_b[i]) cudaEventDestroy(c->ev_chain_b[i]);
         if (c->ev_chain_e[i]) cudaEventDestroy(c->ev_chain_e[i]);
         if (c->ev_chain_done[i]) cudaEventDestroy(c->ev_chain_done[i]);

@@ -13,9 +13,12 @@
 
 namespace rgbl {
 
+static unsigned long long g_scratch_generation = 1;      // bumped by every reallocation: cached chain graphs hold raw pointers
+
 template <class T>
 static bool grow(T** p, size_t* cap, size_t need) {
     if (need <= *cap) return true;
+    ++g_scratch_generation;
     if (*p) cudaFree(*p);
     *p = nullptr;
     const size_t n = need + need / 4 + 64;
@@ -522,65 +525,98 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
     CU(cudaStreamWaitEvent(cs, c->ev_snap, 0));
 
     for (int i = 0; i < 7; ++i) h_f[i] = pose0[i];
-    if (c->prof_on) CU(cudaEventRecord(c->ev_chain_b[slot], cs));
-    CU(cudaMemcpyAsync(t.ch_poses, h_f, 7 * sizeof(float), cudaMemcpyHostToDevice, cs));
-    CU(cudaMemsetAsync(t.ch_counts, 0, ((size_t)nF * 2 + 4) * sizeof(int), cs));
-    int* d_nm = t.ch_counts; int* d_ni = t.ch_counts + nF; int* d_ne = t.ch_counts + 2 * nF; int* d_flags = t.ch_counts + 2 * nF + 1;
-    int* d_ovf = t.ch_counts + 2 * nF + 2;
-    FrameDev f{};
-    f.min_x = 0.f; f.max_x = (float)c->cfg.width; f.min_y = 0.f; f.max_y = (float)c->cfg.height;      // k1 == 0: image bounds
-    f.inv_w = static_cast<float>(kGridCols) / static_cast<float>(f.max_x - f.min_x);
-    f.inv_h = static_cast<float>(kGridRows) / static_cast<float>(f.max_y - f.min_y);
-    f.n_levels = c->tab.nlevels;
-    for (int l = 0; l < f.n_levels; ++l) f.scale[l] = c->tab.scale[l];
-    f.fx = fx; f.fy = fy; f.cx = cx; f.cy = cy; f.bf = bf; f.mb = bf / fx;
-    f.log_scale_factor = std::log(c->cfg.orb.scale_factor);
-    MatchScratch ms = scratch(c);
-    ms.overflow = d_ovf;
-    // the 64x48 grids do not depend on the poses: all frames in one launch (one CTA per frame)
-    f.n = s_nsel; f.keys = s_kps;
-    launch_grid_build_batch(cs, f, nF, cap, b_cell_start, b_csr_idx, b_kp_cell);
     // RGBL_CHAIN_TIMING=1: CUDA events between the launches of the middle frame (warm, in-stream kernel times; stderr at _end)
     static const bool chain_timing = std::getenv("RGBL_CHAIN_TIMING") != nullptr;
+    static const bool chain_graphs = !(std::getenv("RGBL_CHAIN_GRAPH") && std::getenv("RGBL_CHAIN_GRAPH")[0] == '0');
     static cudaEvent_t tev[8] = {};
     if (chain_timing && !tev[0]) for (auto& e : tev) cudaEventCreate(&e);
-    // unprojection of frame j's keypoints (map points of the search in frame j + 1)
-    auto prep_of = [&](int j) {
-        ChainPrepDev cp{};
-        cp.kps = s_kps + (size_t)j * cap; cp.depth = s_depth + (size_t)j * cap; cp.n_ptr = s_nsel + j;
-        cp.fx = f.fx; cp.fy = f.fy; cp.cx = f.cx; cp.cy = f.cy; cp.mb = f.mb; cp.mono = mono; cp.cap = cap;
-        cp.valid = t.q_u8a; cp.xw = t.q_f3a; cp.octave = t.q_i; cp.angle = t.q_f[0]; cp.obs_pos = t.q_u8b; cp.flags = d_flags; cp.state_clear = t.state;
-        return cp;
+    // Everything the chain does on the tracking stream, ~3 launches per frame.  It is captured ONCE per slot into a CUDA graph and
+    // replayed: the launch commands then live in device memory, so the dependent-kernel sequence no longer fetches a command
+    // packet from the host over PCIe per launch (which the concurrent H2D uploads of the next batch were slowing down) and
+    // _begin costs one graph launch instead of ~100 kernel launches on the host.
+    auto enqueue_chain = [&]() -> int {
+        CU(cudaMemcpyAsync(t.ch_poses, h_f, 7 * sizeof(float), cudaMemcpyHostToDevice, cs));
+        CU(cudaMemsetAsync(t.ch_counts, 0, ((size_t)nF * 2 + 4) * sizeof(int), cs));
+        int* d_nm = t.ch_counts; int* d_ni = t.ch_counts + nF; int* d_ne = t.ch_counts + 2 * nF; int* d_flags = t.ch_counts + 2 * nF + 1;
+        int* d_ovf = t.ch_counts + 2 * nF + 2;
+        FrameDev f{};
+        f.min_x = 0.f; f.max_x = (float)c->cfg.width; f.min_y = 0.f; f.max_y = (float)c->cfg.height;      // k1 == 0: image bounds
+        f.inv_w = static_cast<float>(kGridCols) / static_cast<float>(f.max_x - f.min_x);
+        f.inv_h = static_cast<float>(kGridRows) / static_cast<float>(f.max_y - f.min_y);
+        f.n_levels = c->tab.nlevels;
+        for (int l = 0; l < f.n_levels; ++l) f.scale[l] = c->tab.scale[l];
+        f.fx = fx; f.fy = fy; f.cx = cx; f.cy = cy; f.bf = bf; f.mb = bf / fx;
+        f.log_scale_factor = std::log(c->cfg.orb.scale_factor);
+        MatchScratch ms = scratch(c);
+        ms.overflow = d_ovf;
+        // the 64x48 grids do not depend on the poses: all frames in one launch (one CTA per frame)
+        f.n = s_nsel; f.keys = s_kps;
+        launch_grid_build_batch(cs, f, nF, cap, b_cell_start, b_csr_idx, b_kp_cell);
+            // unprojection of frame j's keypoints (map points of the search in frame j + 1)
+        auto prep_of = [&](int j) {
+            ChainPrepDev cp{};
+            cp.kps = s_kps + (size_t)j * cap; cp.depth = s_depth + (size_t)j * cap; cp.n_ptr = s_nsel + j;
+            cp.fx = f.fx; cp.fy = f.fy; cp.cx = f.cx; cp.cy = f.cy; cp.mb = f.mb; cp.mono = mono; cp.cap = cap;
+            cp.valid = t.q_u8a; cp.xw = t.q_f3a; cp.octave = t.q_i; cp.angle = t.q_f[0]; cp.obs_pos = t.q_u8b; cp.flags = d_flags; cp.state_clear = t.state;
+            return cp;
+        };
+        for (int k = 1; k < nF; ++k) {
+            const bool tm = chain_timing && k == std::max(1, nF / 2);
+            const size_t lo = (size_t)(k - 1) * cap, cu = (size_t)k * cap;
+            const float* last_pose = t.ch_poses + 7 * (k - 1);
+            if (tm) cudaEventRecord(tev[0], cs);
+            if (k == 1) launch_chain_prep(cs, prep_of(0), last_pose, last_pose);          // later frames: prepared by the previous pose kernel
+            f.n = s_nsel + k; f.keys = s_kps + cu; f.uright = s_uright + cu; f.desc = s_desc + cu * 32;
+            const int* cell_start = b_cell_start + (size_t)k * (kGridCols * kGridRows + 1);
+            const int* csr_idx = b_csr_idx + cu;
+            if (tm) { cudaEventRecord(tev[1], cs); cudaEventRecord(tev[2], cs); }
+            SearchLastParams prm{};
+            prm.th = th; prm.check_orientation = 1; prm.cur_pose_dev = last_pose; prm.flags_dev = d_flags;
+            LastFrameDev lf{cap, t.q_u8a, t.q_f3a, s_desc + lo * 32, t.q_i, t.q_f[0], t.q_u8b};
+            const ChainEdgesOut eo{t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne};
+            launch_search_last(cs, f, cell_start, csr_idx, lf, prm, ms, t.state, t.match, d_nm + k, &eo);     // + edges of the matches
+            if (tm) { cudaEventRecord(tev[3], cs); cudaEventRecord(tev[4], cs); }
+            PoseProblemDev p{};
+            p.n = 0; p.n_dev = d_ne; p.pose_in_dev = last_pose;
+            p.xw = t.e_xw; p.obs = t.e_obs; p.inv_sigma2 = t.e_info; p.stereo = t.e_st;
+            p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf;
+            const ChainPrepDev nxt = prep_of(k);
+            launch_pose_optimize(cs, p, t.pose_work, t.e_lvl, t.e_out, t.ch_poses + 7 * k, d_ni + k, (k + 1 < nF) ? &nxt : nullptr);
+            if (tm) cudaEventRecord(tev[5], cs);
+        }
+        if (chain_timing) c->chain_timing_ev = tev;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(h_f + 7, t.ch_poses, (size_t)nF * 7 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        CU(cudaMemcpyAsync(h_i, t.ch_counts, ((size_t)nF * 2 + 4) * sizeof(int), cudaMemcpyDeviceToHost, cs));
+        return RGBL_OK;
     };
-    for (int k = 1; k < nF; ++k) {
-        const bool tm = chain_timing && k == std::max(1, nF / 2);
-        const size_t lo = (size_t)(k - 1) * cap, cu = (size_t)k * cap;
-        const float* last_pose = t.ch_poses + 7 * (k - 1);
-        if (tm) cudaEventRecord(tev[0], cs);
-        if (k == 1) launch_chain_prep(cs, prep_of(0), last_pose, last_pose);          // later frames: prepared by the previous pose kernel
-        f.n = s_nsel + k; f.keys = s_kps + cu; f.uright = s_uright + cu; f.desc = s_desc + cu * 32;
-        const int* cell_start = b_cell_start + (size_t)k * (kGridCols * kGridRows + 1);
-        const int* csr_idx = b_csr_idx + cu;
-        if (tm) { cudaEventRecord(tev[1], cs); cudaEventRecord(tev[2], cs); }
-        SearchLastParams prm{};
-        prm.th = th; prm.check_orientation = 1; prm.cur_pose_dev = last_pose; prm.flags_dev = d_flags;
-        LastFrameDev lf{cap, t.q_u8a, t.q_f3a, s_desc + lo * 32, t.q_i, t.q_f[0], t.q_u8b};
-        const ChainEdgesOut eo{t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne};
-        launch_search_last(cs, f, cell_start, csr_idx, lf, prm, ms, t.state, t.match, d_nm + k, &eo);     // + edges of the matches
-        if (tm) { cudaEventRecord(tev[3], cs); cudaEventRecord(tev[4], cs); }
-        PoseProblemDev p{};
-        p.n = 0; p.n_dev = d_ne; p.pose_in_dev = last_pose;
-        p.xw = t.e_xw; p.obs = t.e_obs; p.inv_sigma2 = t.e_info; p.stereo = t.e_st;
-        p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf;
-        const ChainPrepDev nxt = prep_of(k);
-        launch_pose_optimize(cs, p, t.pose_work, t.e_lvl, t.e_out, t.ch_poses + 7 * k, d_ni + k, (k + 1 < nF) ? &nxt : nullptr);
-        if (tm) cudaEventRecord(tev[5], cs);
+    // stage timing events stay outside the graph (events recorded by graph nodes cannot be used for cudaEventElapsedTime)
+    if (c->prof_on) CU(cudaEventRecord(c->ev_chain_b[slot], cs));
+    if (chain_graphs && !chain_timing) {
+        Ctx::ChainGraphKey key{nF, cap, mono, 0, th, fx, fy, cx, cy, bf, g_scratch_generation};
+        if (!c->chain_exec[slot] || std::memcmp(&key, &c->chain_key[slot], sizeof(key)) != 0) {
+            if (c->chain_exec[slot]) { cudaGraphExecDestroy(c->chain_exec[slot]); c->chain_exec[slot] = nullptr; }
+            prepare_match_kernels();
+            CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+            const int rc_cap = enqueue_chain();
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e_cap = cudaStreamEndCapture(cs, &graph);
+            if (rc_cap != RGBL_OK || e_cap != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                if (rc_cap == RGBL_OK) c->err = std::string("chain graph capture failed: ") + cudaGetErrorString(e_cap);
+                return rc_cap != RGBL_OK ? rc_cap : RGBL_E_CUDA;
+            }
+            const cudaError_t e_inst = cudaGraphInstantiate(&c->chain_exec[slot], graph, 0);
+            cudaGraphDestroy(graph);
+            if (e_inst != cudaSuccess) { c->chain_exec[slot] = nullptr; c->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e_inst); return RGBL_E_CUDA; }
+            c->chain_key[slot] = key;
+        }
+        CU(cudaGraphLaunch(c->chain_exec[slot], cs));
+    } else {
+        const int rc_q = enqueue_chain(); if (rc_q) return rc_q;
     }
-    if (chain_timing) c->chain_timing_ev = tev;
     if (c->prof_on) CU(cudaEventRecord(c->ev_chain_e[slot], cs));
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(h_f + 7, t.ch_poses, (size_t)nF * 7 * sizeof(float), cudaMemcpyDeviceToHost, cs));
-    CU(cudaMemcpyAsync(h_i, t.ch_counts, ((size_t)nF * 2 + 4) * sizeof(int), cudaMemcpyDeviceToHost, cs));
     CU(cudaEventRecord(c->ev_chain_done[slot], cs));
     c->chain_frames[slot] = nF;
     c->chain_launches[slot] = 2 + 3 * (nF - 1);

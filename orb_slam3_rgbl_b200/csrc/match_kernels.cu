@@ -939,6 +939,9 @@ static int resolve_dyn_bytes() {
     return kBytes;
 }
 
+// one-time function attributes of this file's kernels (call before capturing their launches into a CUDA graph)
+void prepare_match_kernels() { (void)resolve_dyn_bytes(); }
+
 void launch_grid_build(cudaStream_t st, const FrameDev& f, int* cell_start, int* csr_idx, int* kp_cell) {
     grid_build_kernel<<<1, 1024, 0, st>>>(f, 0, cell_start, csr_idx, kp_cell);
 }

@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
                 double scale = 0;
 #pragma unroll
                 for (int i = 0; i < 6; ++i) scale += x[i] * (lam * x[i] + acc[21 + i]);
-                s_cinv[w] = 1.0 / (scale + 1e-3);
+                s_cinv[w] = rcp_depth(scale + 1e-3);       // Newton reciprocal (<= 1 ulp): the IEEE division is ~20 dependent operations
                 Se3d E, Tn;
                 se3_exp(x, E);
                 se3_mul(E, s_est, Tn);

@@ -136,6 +136,10 @@ struct Ctx {
     float* h_chain_f = nullptr;  // pinned, per slot: pose0 (7) | poses (cap * 7)
     int* h_chain_i = nullptr;    // pinned, per slot: n_matches | n_inliers | n_edges, flags, overflow
     size_t h_chain_cap = 0;      // frames per slot
+    // the chain of a slot as an instantiated CUDA graph (re-captured when any launch parameter or scratch pointer changes)
+    struct ChainGraphKey { int nF, cap, mono, prof; float th, fx, fy, cx, cy, bf; unsigned long long generation; };
+    cudaGraphExec_t chain_exec[2] = {};
+    ChainGraphKey chain_key[2] = {};
     const void* chain_timing_ev = nullptr;   // RGBL_CHAIN_TIMING development aid
 
     int last_frames = 0;         // frames valid in the device buffers

@@ -98,6 +98,7 @@ struct SearchRelocParams { float cur_pose[7]; float Ow[3]; float th; int orb_dis
 struct FrustumParams { float Rcw[9], tcw[3], Ow[3], cos_limit; };
 struct MatchScratch { uint32_t* lists; int list_cap; int* list_n; int* minq; int* choice; uint8_t* resolved; int* overflow; int* rounds; };
 
+void prepare_match_kernels();
 void launch_grid_build(cudaStream_t st, const FrameDev& f, int* cell_start, int* csr_idx, int* kp_cell);
 // one CTA per frame: frame b reads f.n[b], f.keys + b * kp_stride and writes cell_start + b * (cells + 1), csr_idx / kp_cell + b * kp_stride
 void launch_grid_build_batch(cudaStream_t st, const FrameDev& f, int n_frames, int kp_stride, int* cell_start, int* csr_idx, int* kp_cell);

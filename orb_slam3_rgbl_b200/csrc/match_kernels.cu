@@ -126,13 +126,37 @@ __device__ __forceinline__ int warp_collect(const FrameDev& f, const int* __rest
     const int lane = threadIdx.x & 31;
     const bool check_levels = (min_level > 0) || (max_level >= 0);
     int count = 0;
-    for (int ix = cr.min_cx; ix <= cr.max_cx; ++ix) {
-        const int b = cell_start[ix * kGridRows + cr.min_cy], e = cell_start[ix * kGridRows + cr.max_cy + 1];
-        for (int p0 = b; p0 < e; p0 += 32) {
-            const int p = p0 + lane;
+    // The cell columns of the search window are contiguous CSR segments (column-major grid).  Walking them one by one costs a
+    // chain of dependent global loads per column (cell bounds -> index -> keypoint -> descriptor); instead the lanes fetch all
+    // segment bounds at once, scan their lengths and then stride over the CONCATENATED candidate range, so a typical window
+    // (3-7 columns, a few dozen candidates) is one or two trips.  Order of the candidates = ascending CSR position, as before.
+    const int ncol = cr.max_cx - cr.min_cx + 1;
+    for (int c0 = 0; c0 < ncol; c0 += 32) {
+        const int nc = min(32, ncol - c0);
+        int seg_b = 0, seg_len = 0;
+        if (lane < nc) {
+            const int ix = cr.min_cx + c0 + lane;
+            seg_b = cell_start[ix * kGridRows + cr.min_cy];
+            seg_len = cell_start[ix * kGridRows + cr.max_cy + 1] - seg_b;
+        }
+        int incl = seg_len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = min(t0 + lane, total - 1);
+            int lo = 0, hi = 31;                                  // first segment whose inclusive count exceeds t (uniform 5 steps)
+#pragma unroll
+            for (int step = 0; step < 5; ++step) {
+                const int mid = (lo + hi) >> 1;
+                const int v = __shfl_sync(0xffffffffu, incl, mid);
+                if (v > t) hi = mid; else lo = mid + 1;
+            }
+            const int sb = __shfl_sync(0xffffffffu, seg_b, lo), sl = __shfl_sync(0xffffffffu, seg_len, lo), si = __shfl_sync(0xffffffffu, incl, lo);
+            const int p = sb + (t - (si - sl));
             bool keep = false;
             uint32_t key = 0;
-            if (p < e) {
+            if (t0 + lane < total) {
                 const int idx = csr_idx[p];
                 const rgbl_keypoint kp = f.keys[idx];
                 bool ok = true;

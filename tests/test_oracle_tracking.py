@@ -58,3 +58,45 @@ def test_pose_oracle_converges_and_flags_outliers():
     assert n == len(out) - out.sum() and 0.25 < out.mean() < 0.4
     n2, pose2, _ = oracle.pose_optimize(p["pose0"], p["xw"][:2], p["obs"][:2], p["inv_s2"][:2], p["stereo"][:2], *TD.CAM)
     assert n2 == 0 and (pose2 == p["pose0"]).all()                  # < 3 correspondences (src/Optimizer.cc:996)
+
+
+def test_pose_oracle_result_is_a_stationary_point_of_the_stated_cost():
+    """Independent check of the LM restatement: the 4th optimisation round runs WITHOUT the robust kernel on the inlier set it
+    ends with (src/Optimizer.cc:1004-1012), so the returned pose must zero the gradient of sum_e e^T Omega e over the edges not
+    flagged as outliers.  The cost is restated here in numpy (float64) with a numeric SE3 perturbation - nothing shared with
+    oracle/pose_oracle.cpp."""
+    fx, fy, cx, cy, bf = TD.CAM
+
+    def qmul(a, b):
+        ax, ay, az, aw = a; bx, by, bz, bw = b
+        return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz, aw * bz + az * bw + ax * by - ay * bx,
+                         aw * bw - ax * bx - ay * by - az * bz])
+
+    def qrot(q, P):
+        v = q[:3]; uv = 2 * np.cross(v, P)
+        return P + q[3] * uv + np.cross(v, uv)
+
+    def cost(pose, pr, inl):
+        Pc = qrot(pose[:4], pr["xw"][inl].astype(np.float64)) + pose[4:]
+        u = fx * Pc[:, 0] / Pc[:, 2] + cx; v = fy * Pc[:, 1] / Pc[:, 2] + cy; ur = u - bf / Pc[:, 2]
+        o = pr["obs"][inl].astype(np.float64); st = pr["stereo"][inl] != 0; w = pr["inv_s2"][inl].astype(np.float64)
+        e2 = (o[:, 0] - u) ** 2 + (o[:, 1] - v) ** 2 + np.where(st, (o[:, 2] - ur) ** 2, 0.0)
+        return float((w * e2).sum())
+
+    for seed in (0, 3, 7):
+        pr = TD.pose_problem(seed, n=700, outlier_frac=0.2)
+        n_in, pose, out = oracle.pose_optimize(pr["pose0"], pr["xw"], pr["obs"], pr["inv_s2"], pr["stereo"], *TD.CAM)
+        inl = out == 0
+        pose = pose.astype(np.float64); pose[:4] /= np.linalg.norm(pose[:4])
+        c0 = cost(pose, pr, inl)
+        g = np.zeros(6); h = 1e-6
+        for i in range(6):
+            d = np.zeros(6); d[i] = h
+            def moved(sgn):
+                w = sgn * d[:3]; th = np.linalg.norm(w)
+                dq = np.r_[w / th * np.sin(th / 2), np.cos(th / 2)] if th > 0 else np.array([0, 0, 0, 1.0])
+                return np.r_[qmul(dq, pose[:4]), qrot(dq, pose[4:]) + sgn * d[3:]]
+            g[i] = (cost(moved(+1), pr, inl) - cost(moved(-1), pr, inl)) / (2 * h)
+        # scale: a 1 cm / 0.01 rad step must change the cost by far more than the gradient predicts (float32 pose output limits the zero)
+        step = np.array([1e-2] * 3 + [1e-2] * 3)
+        assert np.abs(g * step).max() < 2e-3 * max(c0, 1.0), (seed, g, c0)

@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(512) quadtree_kernel(const uint32_t* __restric
                                                        const int* __restrict__ frame_total, const LevelGeom* __restrict__ levels,
                                                        int n_levels, QtScratchDev scr, uint32_t* __restrict__ sel_lvl,
                                                        int* __restrict__ n_sel_lvl, const int* __restrict__ lvl_region,
-                                                       int cap_kp, int* __restrict__ status) {
+                                                       int cap_kp, int* __restrict__ status, int dyn_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     qt::Shared& s = *reinterpret_cast<qt::Shared*>(smem_raw);
     const int l = blockIdx.x, f = blockIdx.y;
@@ -24,8 +24,22 @@ __global__ void __launch_bounds__(512) quadtree_kernel(const uint32_t* __restric
     const LevelGeom lg = levels[l];
     qt::Scratch g;
     const int so = off + (f * n_levels + l);          // one extra scan slot per preceding tree
-    g.perm_a = scr.perm_a + off; g.perm_b = scr.perm_b + off; g.node_a = scr.node_a + off; g.node_b = scr.node_b + off;
-    g.scan = scr.scan + so; g.quad = scr.quad + off;
+    // The per-key arrays (two permutations, two node maps, packed scan counters, quadrants: 25 bytes per key) are walked by
+    // every subdivision pass with a dozen barrier-separated phases; in global memory each phase pays an L2 round trip.  They
+    // live in the rest of the CTA's shared memory whenever the level's candidates fit (falls back to the global scratch).
+    const size_t key_bytes = (size_t)(n + 1) * 8 + (size_t)n * (4 * 4 + 1) + 64;
+    if (sizeof(qt::Shared) + key_bytes <= (size_t)dyn_bytes) {
+        unsigned char* base = smem_raw + ((sizeof(qt::Shared) + 15) & ~(size_t)15);
+        g.scan = reinterpret_cast<unsigned long long*>(base); base += (size_t)(n + 1) * 8;
+        g.perm_a = reinterpret_cast<int*>(base); base += (size_t)n * 4;
+        g.perm_b = reinterpret_cast<int*>(base); base += (size_t)n * 4;
+        g.node_a = reinterpret_cast<int*>(base); base += (size_t)n * 4;
+        g.node_b = reinterpret_cast<int*>(base); base += (size_t)n * 4;
+        g.quad = base;
+    } else {
+        g.perm_a = scr.perm_a + off; g.perm_b = scr.perm_b + off; g.node_a = scr.node_a + off; g.node_b = scr.node_b + off;
+        g.scan = scr.scan + so; g.quad = scr.quad + off;
+    }
     uint32_t* out = sel_lvl + (size_t)f * cap_kp + lvl_region[l];
     const int region_cap = lvl_region[l + 1] - lvl_region[l];
     const int m = qt::distribute(s, dense + off, n, lg.max_bx - lg.min_bx, lg.max_by - lg.min_by, lg.quota, g, out, region_cap);
@@ -61,13 +75,20 @@ int quadtree_smem_bytes() { return (int)sizeof(qt::Shared); }
 int launch_quadtree(cudaStream_t st, const uint32_t* dense, const int* level_cnt, const int* frame_total, const LevelGeom* d_levels,
                     int n_levels, const QtScratchDev& scr, uint32_t* sel_lvl, int* n_sel_lvl, const int* lvl_region, int cap_kp,
                     int* status, SelKp* sel, int* n_sel, int n_frames) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(qt::Shared)) != cudaSuccess) return -1;
-        attr_set = true;
+    // all the opt-in shared memory of an SM: the tree state + (when they fit) the per-key arrays of the level
+    static int dyn_bytes = 0;
+    if (!dyn_bytes) {
+        int dev = 0, optin = 0;
+        cudaFuncAttributes fa{};
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+            cudaFuncGetAttributes(&fa, quadtree_kernel) != cudaSuccess) return -1;
+        const int avail = optin - (int)fa.sharedSizeBytes - 256;
+        if (avail < (int)sizeof(qt::Shared)) return -1;
+        if (cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, avail) != cudaSuccess) return -1;
+        dyn_bytes = avail;
     }
-    quadtree_kernel<<<dim3(n_levels, n_frames), 512, sizeof(qt::Shared), st>>>(dense, level_cnt, frame_total, d_levels, n_levels, scr,
-                                                                            sel_lvl, n_sel_lvl, lvl_region, cap_kp, status);
+    quadtree_kernel<<<dim3(n_levels, n_frames), 512, dyn_bytes, st>>>(dense, level_cnt, frame_total, d_levels, n_levels, scr,
+                                                                   sel_lvl, n_sel_lvl, lvl_region, cap_kp, status, dyn_bytes);
     sel_pack_kernel<<<n_frames, 256, 0, st>>>(sel_lvl, n_sel_lvl, lvl_region, n_levels, cap_kp, sel, n_sel);
     return 0;
 }

@@ -41,6 +41,7 @@ static void release(Ctx* c) {
     if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
     if (c->ev_blur) cudaEventDestroy(c->ev_blur);
     if (c->d_pts_raw) cudaFree(c->d_pts_raw);
+    if (c->map_arena) cudaFree(c->map_arena);
     if (c->st_trk) { cudaStreamSynchronize(c->st_trk); cudaStreamDestroy(c->st_trk); }
     if (c->ev_snap) cudaEventDestroy(c->ev_snap);
     for (int i = 0; i < 2; ++i) {

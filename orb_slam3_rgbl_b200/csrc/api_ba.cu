@@ -478,7 +478,7 @@ __global__ void ba_export_kernel(int n_poses, const Se3d* __restrict__ poses, co
     if (i < n3) pts_f[i] = (float)pts[i];
 }
 
-struct DevBuf {                 // one arena, carved up; freed on return
+struct DevBuf {                 // the context's mapping arena, carved up
     char* base = nullptr; size_t used = 0, cap = 0;
     template <class T> T* take(size_t n) { used = (used + 255) & ~(size_t)255; T* p = reinterpret_cast<T*>(base + used); used += n * sizeof(T); return p; }
 };
@@ -527,8 +527,8 @@ extern "C" int rgbl_local_bundle_adjustment(rgbl_ctx* ctx, int n_poses, const fl
     DevBuf a;
     a.cap = (size_t)n_edges * (kEdgeBlk * 8 + 3 * 8 + 4 + 4 + 12 + 1 + 4 + 8) + (size_t)n_points * (4 + 9 * 8 * 2 + 6 * 8 + 12 + 12) + (size_t)n_poses * (2 * 56 + 8 + 2 * 28) +
             (size_t)n_opt * (27 * 8 + 8 + 6 * 8 * 3) + (size_t)n * n * 8 + (size_t)n_part * 8 * 3 + (1 << 16);
-    if (cudaMalloc((void**)&a.base, a.cap) != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc failed (local BA)"; return RGBL_E_CUDA; }
-    struct Free { char* p; ~Free() { if (p) cudaFree(p); } } guard{a.base};
+    a.base = mapping_arena(c, a.cap);
+    if (!a.base) { c->err = "cudaMalloc failed (local BA)"; return RGBL_E_CUDA; }
     int* d_epoint = a.take<int>(n_edges); int* d_epose = a.take<int>(n_edges); float* d_obs = a.take<float>((size_t)3 * n_edges);
     uint8_t* d_stereo = a.take<uint8_t>(n_edges); float* d_info = a.take<float>(n_edges); uint8_t* d_erase = a.take<uint8_t>(n_edges);
     int* d_slot = a.take<int>(n_poses); int* d_ptstart = a.take<int>(n_points + 1); int* d_ptedges = a.take<int>(n_edges);

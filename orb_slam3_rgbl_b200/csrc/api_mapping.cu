@@ -161,7 +161,6 @@ __global__ void __launch_bounds__(1024) triangulation_finish_kernel(int n1, int 
 struct Arena {
     char* base = nullptr; size_t used = 0, cap = 0;
     template <class T> T* take(size_t n) { used = (used + 255) & ~(size_t)255; T* p = reinterpret_cast<T*>(base + used); used += n * sizeof(T); return p; }
-    ~Arena() { if (base) cudaFree(base); }
 };
 
 }  // namespace
@@ -182,7 +181,8 @@ int rgbl_distinctive_descriptors(rgbl_ctx* ctx, int n_points, const int32_t* obs
     CU(cudaSetDevice(c->cfg.device));
     Arena a;
     a.cap = (size_t)(n_points + 1) * 4 + (size_t)total * 32 + (size_t)n_points * 4 + 4096;
-    if (cudaMalloc((void**)&a.base, a.cap) != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc failed (distinctive descriptors)"; return RGBL_E_CUDA; }
+    a.base = mapping_arena(c, a.cap);
+    if (!a.base) { c->err = "cudaMalloc failed (distinctive descriptors)"; return RGBL_E_CUDA; }
     int* d_start = a.take<int>(n_points + 1); uint8_t* d_desc = a.take<uint8_t>((size_t)std::max(total, 1) * 32); int* d_best = a.take<int>(n_points);
     CU(cudaMemcpyAsync(d_start, obs_start, (size_t)(n_points + 1) * 4, cudaMemcpyHostToDevice, c->st));
     if (total) CU(cudaMemcpyAsync(d_desc, desc, (size_t)total * 32, cudaMemcpyHostToDevice, c->st));
@@ -235,7 +235,8 @@ int rgbl_search_for_triangulation(rgbl_ctx* ctx, int n1, const uint8_t* desc1, c
     CU(cudaSetDevice(c->cfg.device));
     Arena ar;
     ar.cap = (size_t)(n1 + n2) * (32 + sizeof(rgbl_keypoint) + 1 + 4 + 8) + (size_t)n_q * 12 + (size_t)n_csr2 * 4 + 16384;
-    if (cudaMalloc((void**)&ar.base, ar.cap) != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc failed (SearchForTriangulation)"; return RGBL_E_CUDA; }
+    ar.base = mapping_arena(c, ar.cap);
+    if (!ar.base) { c->err = "cudaMalloc failed (SearchForTriangulation)"; return RGBL_E_CUDA; }
     uint8_t* d_desc1 = ar.take<uint8_t>((size_t)n1 * 32); uint8_t* d_desc2 = ar.take<uint8_t>((size_t)n2 * 32);
     rgbl_keypoint* d_k1 = ar.take<rgbl_keypoint>(n1); rgbl_keypoint* d_k2 = ar.take<rgbl_keypoint>(n2);
     uint8_t* d_mp1 = ar.take<uint8_t>(n1); uint8_t* d_mp2 = ar.take<uint8_t>(n2); float* d_ur1 = ar.take<float>(n1); float* d_ur2 = ar.take<float>(n2);

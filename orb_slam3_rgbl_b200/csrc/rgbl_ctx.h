@@ -121,6 +121,9 @@ struct Ctx {
     int *d_n_sel_lvl = nullptr, *d_lvl_region = nullptr;
 
     TrackBufs trk;
+    // grow-only device arena of the mapping-thread entry points (local BA, SearchForTriangulation, distinctive descriptors): those
+    // calls are synchronous, so one buffer serves them in turn and no call pays a cudaMalloc / cudaFree (both synchronise)
+    char* map_arena = nullptr; size_t map_arena_cap = 0;
     int* h_scalars = nullptr;    // pinned, 16 ints
     int last_match_rounds = 0;
 
@@ -146,6 +149,18 @@ struct Ctx {
     int resident_frames = 0, resident_max_pts = 0;
     bool blur_valid = false;
 };
+
+// returns the context's mapping arena with at least `bytes` bytes (nullptr on allocation failure)
+inline char* mapping_arena(Ctx* c, size_t bytes) {
+    if (bytes > c->map_arena_cap) {
+        if (c->map_arena) cudaFree(c->map_arena);
+        c->map_arena = nullptr; c->map_arena_cap = 0;
+        const size_t want = bytes + bytes / 4 + (1 << 20);
+        if (cudaMalloc((void**)&c->map_arena, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        c->map_arena_cap = want;
+    }
+    return c->map_arena;
+}
 
 #define CU(call)                                                                                   \
     do {                                                                                           \

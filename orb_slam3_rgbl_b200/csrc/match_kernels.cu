@@ -909,45 +909,6 @@ __global__ void __launch_bounds__(256) chain_prep_kernel(ChainPrepDev cp, const 
     if (i < cp.cap) chain_prep_item(cp, last_pose, i);
 }
 
-// ordered compaction of the matched features into PoseOptimization edges (keypoint order)
-__global__ void __launch_bounds__(1024) chain_edges_kernel(const rgbl_keypoint* __restrict__ kps, const float* __restrict__ uright,
-                                                           const int* __restrict__ n_ptr, const int* __restrict__ match,
-                                                           const float* __restrict__ last_xw, FrameDev f, float* __restrict__ exw,
-                                                           float* __restrict__ eobs, float* __restrict__ einfo, uint8_t* __restrict__ est,
-                                                           int* __restrict__ eidx, int* __restrict__ n_edges) {
-    __shared__ int wsum[32];
-    __shared__ int carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = *n_ptr;
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    for (int b = 0; b < n; b += 1024) {
-        const int i = b + tid;
-        const int m = (i < n) ? match[i] : -1;
-        const int flag = m >= 0;
-        int incl = flag;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        int base = carry;
-        for (int w = 0; w < warp; ++w) base += wsum[w];
-        if (flag) {
-            const int e = base + incl - 1;
-            const rgbl_keypoint kp = kps[i];
-            exw[3 * e] = last_xw[3 * m]; exw[3 * e + 1] = last_xw[3 * m + 1]; exw[3 * e + 2] = last_xw[3 * m + 2];
-            const float ur = uright[i];
-            eobs[3 * e] = kp.x; eobs[3 * e + 1] = kp.y; eobs[3 * e + 2] = ur;
-            const float sc = f.scale[kp.octave];
-            einfo[e] = __fdiv_rn(1.0f, __fmul_rn(sc, sc));            // mvInvLevelSigma2 (src/ORBextractor.cc:421-429)
-            est[e] = ur >= 0.f;
-            eidx[e] = i;
-        }
-        __syncthreads();
-        if (tid == 1023) carry = base + incl;
-        __syncthreads();
-    }
-    if (tid == 0) *n_edges = carry;
-}
 
 // ---- launchers ---------------------------------------------------------------------------------------
 // dynamic shared memory of resolve_kernel (opt-in above 48 KB, set once per device)
@@ -1022,11 +983,6 @@ void launch_fuse_search(cudaStream_t st, const FrameDev& f, const int* cell_star
 
 void launch_chain_prep(cudaStream_t st, const ChainPrepDev& cp, const float* last_pose, const float* cur_pose) {
     chain_prep_kernel<<<(cp.cap + 255) / 256, 256, 0, st>>>(cp, last_pose, cur_pose);
-}
-
-void launch_chain_edges(cudaStream_t st, const rgbl_keypoint* kps, const float* uright, const int* n_ptr, const int* match,
-                        const float* last_xw, const FrameDev& f, float* exw, float* eobs, float* einfo, uint8_t* est, int* eidx, int* n_edges) {
-    chain_edges_kernel<<<1, 1024, 0, st>>>(kps, uright, n_ptr, match, last_xw, f, exw, eobs, einfo, est, eidx, n_edges);
 }
 
 void launch_frustum(cudaStream_t st, const FrameDev& f, const FrustumParams& prm, int n, const float* xw, const float* normal,

@@ -100,3 +100,59 @@ def test_pose_oracle_result_is_a_stationary_point_of_the_stated_cost():
         # scale: a 1 cm / 0.01 rad step must change the cost by far more than the gradient predicts (float32 pose output limits the zero)
         step = np.array([1e-2] * 3 + [1e-2] * 3)
         assert np.abs(g * step).max() < 2e-3 * max(c0, 1.0), (seed, g, c0)
+
+
+def test_fuse_search_oracle_vs_bruteforce(seq_frames):
+    """orc_fuse_search against a numpy restatement of ORBmatcher::Fuse's search loop (src/ORBmatcher.cc:1176-1303) with a
+    brute-force window scan instead of the grid."""
+    seq, frames, sf = seq_frames
+    rng = np.random.default_rng(4)
+    xw, desc, normal, mn, mx = TD.local_map([frames[0]], [seq.pose(0)], sf, rng)
+    kf = frames[1]; pose = seq.pose(1); Ow = -pose[4:7]
+    fv = oracle.FrameView(*TD.frame_view_args(kf, sf))
+    valid = (rng.random(len(xw)) < 0.9).astype(np.uint8)
+    th = 3.0
+    bi, bd = oracle.fuse_search(fv, pose, Ow, valid, xw, normal, mn, mx, desc, th)
+    fx, fy, cx, cy, bf = TD.CAM
+    f32 = np.float32
+    pop = np.array([bin(i).count("1") for i in range(256)], np.int32)
+    k = kf["k"]; ur = kf["ur"]
+    checked = 0
+    for i in range(0, len(xw), 7):
+        exp = (-1, 256)
+        if valid[i]:
+            Pc = (xw[i] + pose[4:7]).astype(f32)                  # identity rotation in the synthetic sequence
+            if Pc[2] >= 0:
+                u = f32(f32(f32(fx) * Pc[0]) / Pc[2]) + f32(cx); v = f32(f32(f32(fy) * Pc[1]) / Pc[2]) + f32(cy)
+                if 0 <= u < S.KITTI_W and 0 <= v < S.KITTI_H:
+                    PO = (xw[i] - Ow).astype(f32); d3 = f32(np.sqrt(f32(f32(PO[0] * PO[0] + PO[1] * PO[1]) + PO[2] * PO[2])))
+                    if not (d3 < f32(0.8) * mn[i] or d3 > f32(1.2) * mx[i]) and not (float(f32(f32(PO[0] * normal[i][0] + PO[1] * normal[i][1]) + PO[2] * normal[i][2])) < 0.5 * float(d3)):
+                        level = int(np.ceil(np.log(f32(mx[i] / d3)) / f32(np.log(1.2))))
+                        level = min(max(level, 0), 7)
+                        r = f32(th) * sf[level]; urp = u - f32(f32(bf) * f32(1 / Pc[2]))
+                        best = (256, -1)
+                        # candidates in the reference's order are irrelevant for a strict '<' minimum up to ties: compare sets of minima
+                        cand = []
+                        for j in range(len(k)):
+                            if not (abs(k["x"][j] - u) < r and abs(k["y"][j] - v) < r):
+                                continue
+                            if k["octave"][j] < level - 1 or k["octave"][j] > level:
+                                continue
+                            inv_s2 = f32(1) / f32(sf[k["octave"][j]] * sf[k["octave"][j]])
+                            ex = u - k["x"][j]; ey = v - k["y"][j]
+                            if ur[j] >= 0:
+                                er = urp - ur[j]
+                                if float(f32(f32(f32(ex * ex + ey * ey) + er * er) * inv_s2)) > 7.8:
+                                    continue
+                            elif float(f32(f32(ex * ex + ey * ey) * inv_s2)) > 5.99:
+                                continue
+                            cand.append((int(pop[desc[i] ^ kf["d"][j]].sum()), j))
+                        if cand:
+                            dmin = min(c[0] for c in cand)
+                            exp = ({j for d, j in cand if d == dmin}, dmin)
+        if exp[0] == -1:
+            assert bi[i] == -1 and bd[i] == 256
+        else:
+            assert bd[i] == exp[1] and bi[i] in exp[0]
+            checked += 1
+    assert checked > 20

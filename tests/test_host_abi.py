@@ -175,3 +175,15 @@ def test_block_quadtree_matches_oracle_random_ties(seed):
         ref = _oracle_quadtree(cand, w, h, budget)
         assert len(got) == len(ref)
         assert (got[:, 0] == ref["x"]).all() and (got[:, 1] == ref["y"]).all() and (got[:, 2] == ref["response"]).all()
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/rgbl_b200.h must compile as C99 and as C++11 on its own (no torch / CUDA types)."""
+    import subprocess
+    from pathlib import Path
+    hdr = Path(__file__).resolve().parent.parent / "include" / "rgbl_b200.h"
+    for cmd in (["gcc", "-std=c99", "-fsyntax-only", "-x", "c"], ["g++", "-std=c++11", "-fsyntax-only", "-x", "c++"]):
+        r = subprocess.run(cmd + [str(hdr)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    txt = hdr.read_text()
+    assert "torch" not in txt and "#include <cuda" not in txt and "cudaStream_t" not in txt      # no torch / CUDA types in the signatures

@@ -187,3 +187,22 @@ def test_header_is_plain_c():
         assert r.returncode == 0, r.stderr
     txt = hdr.read_text()
     assert "torch" not in txt and "#include <cuda" not in txt and "cudaStream_t" not in txt      # no torch / CUDA types in the signatures
+
+
+def test_plain_c_client_links_against_the_library(tmp_path):
+    """examples/abi_demo.c is a C99 program using nothing but include/rgbl_b200.h; it must compile, link against librgbl_b200.so and run:
+    on a box without a CUDA device rgbl_create reports RGBL_E_CUDA (exit code 3) - there is no CPU fallback."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    libdir = root / "orb_slam3_rgbl_b200"
+    exe = tmp_path / "abi_demo"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", f"-I{root / 'include'}", str(root / "examples" / "abi_demo.c"), f"-L{libdir}", "-lrgbl_b200",
+                        f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    import torch
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and "keypoints" in run.stdout, run.stdout + run.stderr
+    else:
+        assert run.returncode == 3 and "no CPU fallback" in run.stdout, run.stdout + run.stderr

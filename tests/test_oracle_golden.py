@@ -157,3 +157,44 @@ def test_other_upsamplers_live():
             dref[i] = d
     d, _u = oracle.depth_nearest_neighbor_pixel(raw, k, k, 100.0, float(R))
     assert (d == dref).all()
+
+
+@needs_cv2
+def test_descriptor_distance_is_cv2_norm_hamming():
+    """ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:2058-2074) is the bit count of the XOR = cv2.norm(a, b, NORM_HAMMING), which is
+    also what DBoW2's FORB::distance (FORB.cpp:81-101) computes; the matcher / BoW / mapping oracles all rest on it."""
+    import cv2 as _cv2
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (300, 32), dtype=np.uint8); b = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    b[:20] = a[:20]; b[20:40] = ~a[20:40]
+    for i in range(len(a)):
+        assert oracle.descriptor_distance(a[i], b[i]) == int(_cv2.norm(a[i], b[i], _cv2.NORM_HAMMING))
+    # the nearest descriptor found by cv2's brute-force matcher has the minimum oracle distance
+    bf = _cv2.BFMatcher(_cv2.NORM_HAMMING)
+    for m in bf.match(a[:50], b):
+        assert m.distance == min(oracle.descriptor_distance(a[m.queryIdx], x) for x in b)
+
+
+@needs_cv2
+def test_pose_oracle_agrees_with_cv2_solvepnp_on_an_inlier_only_problem():
+    """Independent solver check for the PoseOptimization restatement: on a monocular, outlier-free problem with unit information the
+    last (non-robust) round minimises the plain reprojection error, which is what cv2.solvePnP(SOLVEPNP_ITERATIVE) minimises."""
+    import cv2 as _cv2
+    import tracking_data as TD
+    fx, fy, cx, cy, bf = TD.CAM
+    for seed in (1, 2):
+        pr = TD.pose_problem(seed, n=400, outlier_frac=0.0, stereo_frac=0.0)
+        inv_s2 = np.ones(len(pr["xw"]), np.float32)
+        n_in, pose, out = oracle.pose_optimize(pr["pose0"], pr["xw"], pr["obs"], inv_s2, pr["stereo"], *TD.CAM)
+        keep = out == 0
+        K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64)
+        ok, rvec, tvec = _cv2.solvePnP(pr["xw"][keep].astype(np.float64), pr["obs"][keep, :2].astype(np.float64), K, None,
+                                       rvec=np.zeros((3, 1)), tvec=np.zeros((3, 1)), useExtrinsicGuess=True, flags=_cv2.SOLVEPNP_ITERATIVE)
+        assert ok
+        Rcv, _ = _cv2.Rodrigues(rvec)
+        x, y, z, w = pose[:4].astype(np.float64)
+        Ror = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                        [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        assert np.abs(Ror - Rcv).max() < 2e-4, np.abs(Ror - Rcv).max()
+        assert np.abs(pose[4:].astype(np.float64) - tvec.ravel()).max() < 5e-3, np.abs(pose[4:] - tvec.ravel()).max()
+        assert keep.mean() > 0.8          # the generator scales the pixel noise with the octave; with unit information the noisiest points are cut

@@ -1,0 +1,132 @@
+"""Model check of the matcher resolution scheme (orb_slam3_rgbl_b200/csrc/match_kernels.cu: resolve_kernel).  The reference's matchers
+are sequential greedy loops: map point q takes its best still-available frame feature and may block it for the points after it.  The
+device resolves them in rounds: every waiting query proposes itself at each available candidate (minimum index wins per feature), and a
+query becomes final when no lower-index waiting query can still interfere.  This test restates both in Python and lets hypothesis
+compare them on small random instances full of ties, including both processing orders inside a round (the device has a documented
+benign race on the state array inside one phase).  CPU only; it checks the ALGORITHM the kernel implements, the kernel itself is
+checked against the oracle on the GPU."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+TH_HIGH, TH_LOW = 100, 50
+
+
+def sequential(mode, lists, obs_pos, state0, lvl, ratio, th_accept):
+    """lists[q] = [(dist, pos, ft)] in scan order (ascending pos).  Returns (choice[q], state)."""
+    state = list(state0); choice = [-1] * len(lists)
+    for q, cand in enumerate(lists):
+        best = best2 = None
+        for (d, pos, ft) in cand:
+            if state[ft] == 1:
+                continue
+            key = (d, pos)
+            if mode == 0:
+                if best is None or key < best[0]:
+                    best = (key, ft)
+            else:
+                if best is None or key < best[0]:
+                    best2 = best; best = (key, ft)
+                elif best2 is None or key < best2[0]:
+                    best2 = (key, ft)
+        if best is None:
+            continue
+        bd = best[0][0]
+        accept = bd <= th_accept
+        if mode == 1 and accept and best2 is not None and lvl[best[1]] == lvl[best2[1]] and float(np.float32(bd)) > float(np.float32(ratio) * np.float32(best2[0][0])):
+            accept = False
+        if mode == 1 and accept and best2 is None:
+            pass                                                # bestDist2 = 256, bestLevel2 = -1: levels differ
+        if mode == 2 and accept:
+            bd2 = 256 if best2 is None else best2[0][0]
+            accept = float(np.float32(bd)) < float(np.float32(ratio) * np.float32(bd2))
+        if accept:
+            choice[q] = best[1]
+            if obs_pos[q]:
+                state[best[1]] = 1
+            elif state[best[1]] == 0:
+                state[best[1]] = 2
+    return choice, state
+
+
+def rounds(mode, lists, obs_pos, state0, lvl, ratio, th_accept, reverse):
+    state = list(state0); n_q = len(lists); choice = [-1] * n_q
+    resolved = [len(c) == 0 for c in lists]
+    for _ in range(4 * n_q + 4):
+        minq = {}
+        for q in range(n_q):
+            if resolved[q]:
+                continue
+            for (d, pos, ft) in lists[q]:
+                if state[ft] != 1:
+                    minq[ft] = min(minq.get(ft, 1 << 30), q)
+        waiting = False
+        order = range(n_q - 1, -1, -1) if reverse else range(n_q)
+        for q in order:
+            if resolved[q]:
+                continue
+            best = best2 = None; depends_ok = True
+            for (d, pos, ft) in lists[q]:
+                if state[ft] == 1:
+                    continue
+                if mode >= 1 and minq.get(ft) != q:
+                    depends_ok = False
+                key = (d, pos)
+                if mode == 0:
+                    if best is None or key < best[0]:
+                        best = (key, ft)
+                else:
+                    if best is None or key < best[0]:
+                        best2 = best; best = (key, ft)
+                    elif best2 is None or key < best2[0]:
+                        best2 = (key, ft)
+            if best is None:
+                resolved[q] = True
+                continue
+            final_ok = (minq.get(best[1]) == q) if mode == 0 else depends_ok
+            if not final_ok:
+                waiting = True
+                continue
+            resolved[q] = True
+            bd = best[0][0]
+            accept = bd <= th_accept
+            if mode == 1 and accept and best2 is not None and lvl[best[1]] == lvl[best2[1]] and float(np.float32(bd)) > float(np.float32(ratio) * np.float32(best2[0][0])):
+                accept = False
+            if mode == 2 and accept:
+                bd2 = 256 if best2 is None else best2[0][0]
+                accept = float(np.float32(bd)) < float(np.float32(ratio) * np.float32(bd2))
+            if accept:
+                choice[q] = best[1]
+                if obs_pos[q]:
+                    state[best[1]] = 1
+                elif state[best[1]] == 0:
+                    state[best[1]] = 2
+        if not waiting:
+            return choice, state
+    raise AssertionError("the rounds did not terminate")
+
+
+@st.composite
+def instance(draw):
+    n_f = draw(st.integers(1, 7)); n_q = draw(st.integers(1, 10))
+    lists = []
+    for _ in range(n_q):
+        fts = draw(st.lists(st.integers(0, n_f - 1), max_size=5, unique=True))
+        # pos == ft here (any injective scan order works); distances from a tiny alphabet -> many ties
+        lists.append(sorted([(draw(st.sampled_from([10, 10, 30, 50, 51, 100, 101])), ft, ft) for ft in fts], key=lambda c: c[1]))
+    obs_pos = draw(st.lists(st.booleans(), min_size=n_q, max_size=n_q))
+    state0 = draw(st.lists(st.sampled_from([0, 0, 0, 1]), min_size=n_f, max_size=n_f))
+    lvl = draw(st.lists(st.integers(0, 2), min_size=n_f, max_size=n_f))
+    ratio = draw(st.sampled_from([0.6, 0.8, 0.9, 1.0]))
+    return lists, obs_pos, state0, lvl, ratio
+
+
+@settings(max_examples=1200, deadline=None)
+@given(instance(), st.sampled_from([0, 1, 2]), st.booleans())
+def test_rounds_equal_the_sequential_greedy_matchers(inst, mode, reverse):
+    lists, obs_pos, state0, lvl, ratio = inst
+    if mode == 2:
+        obs_pos = [True] * len(obs_pos)          # SearchByBoW: every assignment blocks the feature (src/ORBmatcher.cc:296-297)
+    th = TH_LOW if mode == 2 else TH_HIGH
+    ref = sequential(mode, lists, obs_pos, state0, lvl, ratio, th)
+    got = rounds(mode, lists, obs_pos, state0, lvl, ratio, th, reverse)
+    assert got == ref

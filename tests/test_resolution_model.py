@@ -130,3 +130,43 @@ def test_rounds_equal_the_sequential_greedy_matchers(inst, mode, reverse):
     ref = sequential(mode, lists, obs_pos, state0, lvl, ratio, th)
     got = rounds(mode, lists, obs_pos, state0, lvl, ratio, th, reverse)
     assert got == ref
+
+
+def three_maxima_sequential(h):
+    """ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:2012-2053)."""
+    m1 = m2 = m3 = 0; i1 = i2 = i3 = -1
+    for i, s in enumerate(h):
+        if s > m1:
+            m3, m2, m1 = m2, m1, s; i3, i2, i1 = i2, i1, i
+        elif s > m2:
+            m3, m2 = m2, s; i3, i2 = i2, i
+        elif s > m3:
+            m3 = s; i3 = i
+    if np.float32(m2) < np.float32(0.1) * np.float32(m1):
+        i2 = i3 = -1
+    elif np.float32(m3) < np.float32(0.1) * np.float32(m1):
+        i3 = -1
+    return i1, i2, i3
+
+
+def three_maxima_argmax(h):
+    """What resolve_kernel / triangulation_finish_kernel do: three arg-max passes over count << 8 | (255 - index), empty bins excluded."""
+    keys = [((c << 8) | (255 - i)) if c > 0 else 0 for i, c in enumerate(h)]
+    top = []
+    for _ in range(3):
+        m = max(keys)
+        top.append((m >> 8, 255 - (m & 0xff) if m > 0 else -1))
+        if m > 0:
+            keys[keys.index(m)] = 0
+    (c1, i1), (c2, i2), (c3, i3) = top
+    if np.float32(c2) < np.float32(0.1) * np.float32(c1):
+        i2 = i3 = -1
+    elif np.float32(c3) < np.float32(0.1) * np.float32(c1):
+        i3 = -1
+    return i1, i2, i3
+
+
+@settings(max_examples=2000, deadline=None)
+@given(st.lists(st.sampled_from([0, 0, 0, 1, 2, 3, 5, 5, 9, 10, 50, 100]), min_size=30, max_size=30))
+def test_parallel_three_maxima_equals_the_sequential_scan(h):
+    assert three_maxima_argmax(h) == three_maxima_sequential(h)

@@ -170,3 +170,30 @@ def three_maxima_argmax(h):
 @given(st.lists(st.sampled_from([0, 0, 0, 1, 2, 3, 5, 5, 9, 10, 50, 100]), min_size=30, max_size=30))
 def test_parallel_three_maxima_equals_the_sequential_scan(h):
     assert three_maxima_argmax(h) == three_maxima_sequential(h)
+
+
+@settings(max_examples=2000, deadline=None)
+@given(st.lists(st.tuples(st.sampled_from([0, 10, 10, 30, 49, 50, 50, 51, 80]), st.booleans()), max_size=12))
+def test_triangulation_last_minimum_key(cands):
+    """SearchForTriangulation's scan (src/ORBmatcher.cc:1002-1080) keeps a candidate when dist <= TH_LOW, dist <= bestDist and the
+    geometric test passes; triangulation_search_kernel takes the minimum of dist << 20 | (0xfffff - position) over the passing ones."""
+    best, idx = TH_LOW, -1
+    for i, (d, ok) in enumerate(cands):
+        if d > TH_LOW or d > best:
+            continue
+        if ok:
+            idx, best = i, d
+    keys = [(d << 20) | (0xfffff - i) for i, (d, ok) in enumerate(cands) if ok and d <= TH_LOW]
+    got = (0xfffff - (min(keys) & 0xfffff)) if keys else -1
+    assert got == idx
+
+
+@settings(max_examples=1000, deadline=None)
+@given(st.lists(st.integers(0, 256), min_size=1, max_size=70))
+def test_median_by_histogram_rank(row):
+    """distinctive_kernel: the element std::sort leaves at index (int)(0.5 * (N - 1)) is the first histogram bin whose cumulative count
+    exceeds that rank."""
+    k = int(0.5 * (len(row) - 1))
+    hist = np.bincount(row, minlength=257)
+    cum = np.cumsum(hist)
+    assert int(np.argmax(cum > k)) == sorted(row)[k]

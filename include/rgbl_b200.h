@@ -341,6 +341,13 @@ int rgbl_quadtree_select_block_emulation(const int32_t* xys, int n, int min_x, i
                                          int32_t* out_xys, int cap);
 int rgbl_std_sort_emulation(const int32_t* size_ulx, int n, int32_t* perm_out);
 
+/* Test hook (host-only): the strip formulation of the per-cell FAST detection (fast_strip.cuh; src/ORBextractor.cc:805-868)
+ * executed phase-sequentially on the host for pyramid level `level` of a width x height image.  level_img: that level's
+ * pixels (row stride `stride`); strips hold at most max_cells (1..8) cells / max_width (78..264) px.  out_xys: n x 3
+ * (x, y relative to the FAST window origin (16, 16), cv score) in the reference's order.  Returns n or a negative status. */
+int rgbl_fast_strips_emulation(const rgbl_orb_params* orb, int width, int height, int level, const uint8_t* level_img, int stride,
+                               int max_cells, int max_width, int32_t* out_xys, int cap);
+
 #ifdef __cplusplus
 }
 #endif

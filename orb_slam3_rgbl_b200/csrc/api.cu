@@ -41,6 +41,7 @@ static void release(Ctx* c) {
     if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
     if (c->ev_blur) cudaEventDestroy(c->ev_blur);
     if (c->d_pts_raw) cudaFree(c->d_pts_raw);
+    if (c->d_strips) cudaFree(c->d_strips);
     if (c->map_arena) cudaFree(c->map_arena);
     if (c->st_trk) { cudaStreamSynchronize(c->st_trk); cudaStreamDestroy(c->st_trk); }
     if (c->ev_snap) cudaEventDestroy(c->ev_snap);
@@ -131,6 +132,15 @@ static int create(const rgbl_config* cfg, Ctx** out) {
         CUF(dmalloc(&c->qt_scr.scan, (size_t)c->dense_cap + (size_t)B * nl + 8));
         CUF(dmalloc(&c->qt_scr.quad, (size_t)c->dense_cap));
     }
+    {   // optional strip formulation of the FAST kernel
+        const char* env = getenv("RGBL_FAST_STRIPS");
+        if (env && env[0] == '1') {
+            build_fast_strips(c->cells, 8, 264, c->strips, c->strip_rows_cap, c->strip_list_cap);
+            CUF(dmalloc(&c->d_strips, c->strips.size()));
+            CUF(cudaMemcpy(c->d_strips, c->strips.data(), c->strips.size() * sizeof(StripInfo), cudaMemcpyHostToDevice));
+            c->fast_strips = true;
+        }
+    }
     CUF(dmalloc(&c->d_sel, (size_t)B * c->cap_kp));
     CUF(dmalloc(&c->d_n_sel, (size_t)B));
     CUF(dmalloc(&c->d_kps, (size_t)B * c->cap_kp));
@@ -203,8 +213,16 @@ static int run_extract(Ctx* c, int n_frames, const std::function<void()>& aux_wo
     launch_pyramid(c->st, c->d_pyr, c->frame_bytes, c->levels.data(), nl, c->d_coefs, n_frames);
     stage_end(c, ST_PYRAMID, c->st, nl - 1);
     stage_begin(c, ST_FAST, c->st);
-    launch_fast(c->st, c->d_pyr, c->frame_bytes, c->d_levels, c->d_cells, c->n_cells, c->cfg.orb.ini_th_fast,
-                c->cfg.orb.min_th_fast, c->d_slots, c->d_counts, c->d_overflow, n_frames);
+    if (c->fast_strips) {
+        if (launch_fast_strips(c->st, c->d_pyr, c->frame_bytes, c->d_levels, c->d_cells, c->n_cells, c->d_strips, (int)c->strips.size(),
+                               c->strip_rows_cap, c->strip_list_cap, c->cfg.orb.ini_th_fast, c->cfg.orb.min_th_fast, c->d_slots,
+                               c->d_counts, c->d_overflow, n_frames) != 0) {
+            c->err = "strip FAST kernel needs more shared memory than this device allows"; return RGBL_E_CUDA;
+        }
+    } else {
+        launch_fast(c->st, c->d_pyr, c->frame_bytes, c->d_levels, c->d_cells, c->n_cells, c->cfg.orb.ini_th_fast,
+                    c->cfg.orb.min_th_fast, c->d_slots, c->d_counts, c->d_overflow, n_frames);
+    }
     stage_end(c, ST_FAST, c->st, 1);
     stage_begin(c, ST_COMPACT, c->st);
     launch_compact(c->st, c->d_levels, nl, c->n_cells, c->d_slots, c->d_counts, c->d_cell_off, c->d_level_cnt,

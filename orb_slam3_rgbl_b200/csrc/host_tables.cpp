@@ -123,6 +123,29 @@ int build_geometry(int width, int height, const OrbTables& t, std::vector<LevelG
     return RGBL_OK;
 }
 
+void build_fast_strips(const std::vector<CellInfo>& cells, int max_cells, int max_width, std::vector<StripInfo>& strips, int& rows_max,
+                       int& tested_max) {
+    strips.clear(); rows_max = 0; tested_max = 0;
+    size_t i = 0;
+    while (i < cells.size()) {
+        const CellInfo& f = cells[i];
+        StripInfo s{};
+        s.first_cell = (int32_t)i; s.level = f.level; s.x0 = f.x0; s.y0 = f.y0; s.h = f.ch;
+        size_t j = i;
+        // cells of one row are consecutive in the table, share y0 / ch and their windows advance by wCell
+        while (j < cells.size() && (int)(j - i) < max_cells && cells[j].level == f.level && cells[j].y0 == f.y0 && cells[j].ch == f.ch &&
+               cells[j].x0 + cells[j].cw - f.x0 <= max_width)
+            ++j;
+        if (j == i) j = i + 1;                       // a single cell wider than max_width cannot happen (cw <= 78)
+        s.n_cells = (int16_t)(j - i);
+        s.w = (int16_t)(cells[j - 1].x0 + cells[j - 1].cw - f.x0);
+        strips.push_back(s);
+        rows_max = std::max(rows_max, (int)s.h);
+        if (s.w > 6 && s.h > 6) tested_max = std::max(tested_max, (s.w - 6) * (s.h - 6));
+        i = j;
+    }
+}
+
 int structuring_element(const char* kind, int ku, int kv, uint8_t* mask) {
     if (!kind || !mask || ku < 1 || kv < 1 || ku > 9 || kv > 9) return RGBL_E_INVALID;
     std::memset(mask, 0, (size_t)ku * kv);

@@ -116,6 +116,11 @@ struct Ctx {
 
     // device quad-tree (quadtree_kernels.cu)
     bool device_quadtree = false, host_counts_valid = false;
+    // strip formulation of the FAST kernel (fast_strip.cuh); selected with RGBL_FAST_STRIPS=1
+    bool fast_strips = false;
+    std::vector<StripInfo> strips;
+    StripInfo* d_strips = nullptr;
+    int strip_rows_cap = 0, strip_list_cap = 0;
     QtScratchDev qt_scr{};
     uint32_t* d_sel_lvl = nullptr;
     int *d_n_sel_lvl = nullptr, *d_lvl_region = nullptr;

@@ -42,6 +42,13 @@ struct CellInfo {
     int16_t pad;
 };
 
+// A run of consecutive FAST cells of one cell row, handled by one CTA of the strip kernel (fast_strip.cuh).
+struct StripInfo {
+    int32_t first_cell;        // index into the flat cell table
+    int16_t level, n_cells;
+    int16_t x0, y0, w, h;      // union of the cells' windows (level coordinates)
+};
+
 // Bilinear resize coefficient: source index and the two 11-bit weights.
 struct LinCoef {
     int16_t s;                 // left/top source index
@@ -61,6 +68,9 @@ struct OrbTables {
 int compute_orb_tables(const rgbl_orb_params& p, OrbTables& t);
 int build_geometry(int width, int height, const OrbTables& t, std::vector<LevelGeom>& levels,
                    std::vector<CellInfo>& cells, std::vector<LinCoef>& coefs, size_t& frame_bytes, std::string& err);
+// cells -> strips of at most max_cells cells and max_width px; returns the largest window height and tested-pixel count
+void build_fast_strips(const std::vector<CellInfo>& cells, int max_cells, int max_width, std::vector<StripInfo>& strips, int& rows_max,
+                       int& tested_max);
 int quadtree_select(const int32_t* xys, int n, int min_x, int max_x, int min_y, int max_y, int n_desired,
                     int32_t* out_idx, int cap);
 int structuring_element(const char* kind, int ku, int kv, uint8_t* mask);

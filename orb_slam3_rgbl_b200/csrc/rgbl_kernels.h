@@ -27,6 +27,10 @@ void launch_pyramid(cudaStream_t st, uint8_t* pyr, size_t frame_stride, const Le
 void launch_fast(cudaStream_t st, const uint8_t* pyr, size_t frame_stride, const LevelGeom* d_levels,
                  const CellInfo* d_cells, int n_cells, int ini_th, int min_th, uint32_t* slots, int* counts,
                  int* overflow, int n_frames);
+// fast_strip_kernels.cu: strip formulation of launch_fast (same outputs); returns -1 when the shared-memory request is refused
+int launch_fast_strips(cudaStream_t st, const uint8_t* pyr, size_t frame_stride, const LevelGeom* d_levels, const CellInfo* d_cells,
+                       int n_cells, const StripInfo* d_strips, int n_strips, int rows_cap, int list_cap, int ini_th, int min_th,
+                       uint32_t* slots, int* counts, int* overflow, int n_frames);
 void launch_compact(cudaStream_t st, const LevelGeom* d_levels, int n_levels, int n_cells, const uint32_t* slots,
                     const int* counts, int* cell_off, int* level_cnt, int* frame_total, uint32_t* dense, int dense_cap,
                     int* overflow, int n_frames);

@@ -206,3 +206,48 @@ def test_plain_c_client_links_against_the_library(tmp_path):
         assert run.returncode == 0 and "keypoints" in run.stdout, run.stdout + run.stderr
     else:
         assert run.returncode == 3 and "no CPU fallback" in run.stdout, run.stdout + run.stderr
+
+
+# ---- strip formulation of the per-cell FAST (fast_strip.cuh), executed on the host ----------------------------------------
+def _strip_fast(img_level, width, height, level, nfeatures=1500, scale=1.2, nlevels=8, ini_th=12, min_th=7, max_cells=8, max_width=264):
+    prm = L.OrbParams(nfeatures, scale, nlevels, ini_th, min_th)
+    lv = np.ascontiguousarray(img_level, np.uint8)
+    out = np.empty((1 << 18, 3), np.int32)
+    n = L.lib().rgbl_fast_strips_emulation(C.byref(prm), width, height, level, L.ptr(lv), lv.strides[0], max_cells, max_width, L.ptr(out), len(out))
+    assert n >= 0, n
+    return out[:n]
+
+
+@pytest.mark.parametrize("seed,size,ths,strip", [
+    (0, (900, 300), (20, 7), (8, 264)), (1, (900, 300), (20, 7), (3, 120)), (2, (1241, 376), (20, 7), (8, 264)),
+    (3, (640, 480), (12, 7), (5, 200)), (4, (501, 260), (40, 5), (1, 78)), (5, (752, 480), (20, 7), (8, 250)),
+    (6, (900, 300), (255, 60), (8, 264)), (7, (333, 250), (20, 7), (2, 264))])
+def test_fast_strips_match_the_oracle_cell_by_cell(seed, size, ths, strip):
+    """Every level of a real pyramid: same candidates, same scores, same (cell-major, row-major) order as the per-cell cv::FAST
+    restatement with the iniTh -> minTh fallback (src/ORBextractor.cc:805-868)."""
+    w, h = size
+    img = S.make_image(300 + seed, w, h)
+    ex = oracle.Extractor(1500, ini_th=ths[0], min_th=ths[1]); ex(img)
+    total = 0
+    for l in range(8):
+        got = _strip_fast(ex.level_image(l), w, h, l, ini_th=ths[0], min_th=ths[1], max_cells=strip[0], max_width=strip[1])
+        ref = ex.level_candidates(l)
+        assert got.shape == ref.shape, (l, got.shape, ref.shape)
+        assert (got == ref).all(), l
+        total += len(ref)
+    assert total > 200
+
+
+def test_fast_strips_on_flat_and_saturated_images():
+    for val in (0, 255, 128):
+        img = np.full((250, 333), val, np.uint8)
+        ex = oracle.Extractor(500); ex(img)
+        for l in range(8):
+            assert len(_strip_fast(ex.level_image(l), 333, 250, l, nfeatures=500)) == len(ex.level_candidates(l)) == 0
+    # checkerboard: many equal scores next to each other (NMS ties) and every cell needs the fallback decision
+    yy, xx = np.mgrid[0:240, 0:400]
+    img = (((xx // 5 + yy // 5) & 1) * 200 + 20).astype(np.uint8)
+    ex = oracle.Extractor(1000); ex(img)
+    for l in range(8):
+        got, ref = _strip_fast(ex.level_image(l), 400, 240, l, nfeatures=1000), ex.level_candidates(l)
+        assert got.shape == ref.shape and (got == ref).all(), l

@@ -121,6 +121,12 @@ bool solve6(const double Hin[6][6], const double bin[6], double x[6]) {
     return true;
 }
 
+#ifdef ORC_POSE_STUDY
+struct LM;
+void study_build_system(LM& lm, double H[6][6], double b[6]);
+bool study_solve6(const double H[6][6], const double b[6], double x[6]);
+#endif
+
 struct LM {
     std::vector<Edge>& edges;
     const Cam& cam;
@@ -165,7 +171,11 @@ struct LM {
         double current = active_robust_chi2(), temp = current;
         const double ini = current;
         double H[6][6], b[6];
+#ifdef ORC_POSE_STUDY      // tools/pose_precision_study.cpp only (alternative arithmetic for the normal equations); never set for liborb_oracle.so
+        study_build_system(*this, H, b);
+#else
         build_system(H, b);
+#endif
         if (iteration == 0) {
             double mx = 0;
             for (int j = 0; j < 6; ++j) mx = std::max(std::fabs(H[j][j]), mx);
@@ -177,7 +187,11 @@ struct LM {
             double Hl[6][6];
             for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) Hl[i][j] = H[i][j] + (i == j ? lambda : 0.0);
             double x[6] = {0, 0, 0, 0, 0, 0};
+#ifdef ORC_POSE_STUDY
+            const bool ok2 = study_solve6(Hl, b, x);
+#else
             const bool ok2 = solve6(Hl, b, x);
+#endif
             est = se3_mul(se3_exp(x), est);
             compute_active_errors();
             temp = active_robust_chi2();

@@ -170,6 +170,81 @@ __device__ __forceinline__ bool solve6(const double* Hsym /*21 upper*/, double l
     return true;
 }
 
+#ifndef POSE_MIXED_SOLVE
+#define POSE_MIXED_SOLVE 0
+#endif
+#if POSE_MIXED_SOLVE
+// Candidate for the next round (NOT the default, not yet run on a GPU): the same system solved by an unpivoted LDL^T in
+// float32 plus ONE step of iterative refinement with the residual formed in float64.  The serial solve is bound by the
+// latency of dependent operations, and a dependent float32 operation costs ~4 cycles against ~30 for float64; the
+// refinement step restores the accuracy ((cond * 2^-24)^2 relative).  tools/pose_precision_study.cpp: on 300 synthetic
+// tracking problems the float32 poses PoseOptimization returns are bit-identical to the float64 solve's in all 300 and no
+// outlier flag changes (without the refinement step 225 of 300 poses change, by up to 1.4e-5 m).
+__device__ __forceinline__ bool solve6_mixed(const double* Hsym /*21 upper*/, double lambda, const double* b, double* x) {
+    float L[6][6], dinv[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+            if (j >= i) L[j][i] = (float)(Hsym[i * 6 - (i * (i - 1)) / 2 + (j - i)] + ((i == j) ? lambda : 0.0));
+    bool positive = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const float d = L[k][k];
+        positive = positive && (d >= 0.f) && (d <= FLT_MAX);
+        dinv[k] = (d >= FLT_MIN && d <= FLT_MAX) ? __frcp_rn(d) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (i > k) {
+                const float aik = L[i][k], lik = aik * dinv[k];
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+                    if (j > k && j < i) L[i][j] -= aik * L[j][k];
+                L[i][i] -= aik * lik;
+                L[i][k] = lik;
+            }
+        }
+    }
+    if (!positive) return false;
+    double xs[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        float y[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {                       // residual b - (H + lambda I) x in float64 (x = 0 in the first pass)
+            double r = b[i];
+            if (pass) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int lo = i < j ? i : j, hi = i < j ? j : i;
+                    r = fma(-(Hsym[lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo)] + ((i == j) ? lambda : 0.0)), xs[j], r);
+                }
+            }
+            y[i] = (float)r;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+                if (i > k) y[i] -= L[i][k] * y[k];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) y[i] *= dinv[i];
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) {
+            const int j = 5 - jj;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+                if (i < j) y[i] -= L[j][i] * y[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xs[i] += (double)y[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = xs[i];
+    return true;
+}
+#endif
+
 // 1/sqrt(x) for a positive normal double: MUFU.RSQ64H seed + two Newton steps (7 dependent operations)
 __device__ __forceinline__ double rsqrt_newton(double x) {
     double y;
@@ -423,7 +498,11 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
 #ifdef POSE_TIMING
                 const long long ts_ = clock64();
 #endif
+#if POSE_MIXED_SOLVE
+                s_cok[w] = solve6_mixed(acc, lam, acc + 21, x) ? 1 : 0;
+#else
                 s_cok[w] = solve6(acc, lam, acc + 21, x) ? 1 : 0;
+#endif
 #ifdef POSE_TIMING
                 tm[5] += clock64() - ts_;
 #endif

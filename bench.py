@@ -396,7 +396,7 @@ def main():
     # out of every call): Frame construction -> SearchByProjection(last frame) -> PoseOptimization.  Latency, not throughput.
     online = None
     if world == 1 and not args.no_bow:
-        def unproject_identity_rotation(fr, pose_):        # Frame::UnprojectStereo (src/Frame.cc:1097-1112); the synthetic camera does not rotate
+        def unproject_identity_rotation(fr, pose_):        # Frame::UnprojectStereo (src/Frame.cc:1137-1150); the synthetic camera does not rotate
             f32 = np.float32
             z = fr["dep"]; zz = np.where(z > 0, z, f32(1)).astype(f32)
             x = ((fr["k"]["x"] - f32(S.KITTI_CX)) * zz * f32(1.0 / np.float32(S.KITTI_FX))).astype(f32)

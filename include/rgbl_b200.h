@@ -43,7 +43,7 @@ typedef struct {
     int32_t octave, class_id;
 } rgbl_keypoint;
 
-/* ORBextractor constructor arguments, include/ORBextractor.h:51-52, src/ORBextractor.cc:409-469. */
+/* ORBextractor constructor arguments, include/ORBextractor.h:48-49, src/ORBextractor.cc:409-469. */
 typedef struct {
     int32_t nfeatures;
     float scale_factor;
@@ -152,7 +152,7 @@ typedef struct {
 } rgbl_frame_view;
 
 /* ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, float th, bool bMono)
- * (include/ORBmatcher.h:53, src/ORBmatcher.cc:1676-1887).  Poses are Sophus::SE3f as (qx,qy,qz,qw,tx,ty,tz).
+ * (include/ORBmatcher.h:51, src/ORBmatcher.cc:1676-1887).  Poses are Sophus::SE3f as (qx,qy,qz,qw,tx,ty,tz).
  * Last-frame map points i = 0..n_last-1 in LastFrame order: valid[i] = mvpMapPoints[i] != NULL &&
  * !mvbOutlier[i]; xw = GetWorldPos(); mp_desc = GetDescriptor(); last_octave/last_angle = the last frame's
  * keypoint; obs_pos[i] = Observations() > 0.  cur_state[i2] (nullable = all free): 0 free, 1 holds a point
@@ -171,7 +171,7 @@ int rgbl_is_in_frustum(rgbl_ctx* ctx, const rgbl_frame_view* cur, const float Rc
                        uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, float* track_depth, int32_t* level, float* view_cos);
 
 /* ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, float th, bool bFarPoints, float thFarPoints)
- * (include/ORBmatcher.h:49, src/ORBmatcher.cc:43-213).  in_view[i] = mbTrackInView && !isBad(); the mTrack*
+ * (include/ORBmatcher.h:47, src/ORBmatcher.cc:43-213).  in_view[i] = mbTrackInView && !isBad(); the mTrack*
  * fields as filled by isInFrustum; nn_ratio = mfNNratio.  match/cur_state as above.                         */
 int rgbl_search_by_projection_local(rgbl_ctx* ctx, const rgbl_frame_view* cur, int n, const uint8_t* in_view, const float* proj_x,
                                     const float* proj_y, const float* proj_xr, const float* track_depth, const int32_t* level,
@@ -183,7 +183,7 @@ int rgbl_search_by_projection_local(rgbl_ctx* ctx, const rgbl_frame_view* cur, i
  * src/Frame.cc:122-125).  mb = mbf / fx, mbf = Camera.bf.  depth / uright [n_left] = mvDepth / mvuRight of the left frame. */
 int rgbl_stereo_matches(rgbl_ctx* ctx, int slot_left, int slot_right, float mb, float mbf, float* depth, float* uright, int cap);
 
-/* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (include/ORBmatcher.h:65,
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (include/ORBmatcher.h:68,
  * src/ORBmatcher.cc:223-425), Nleft == -1.  pKF->mFeatVec and F.mFeatVec (DBoW2::FeatureVector = std::map<NodeId,
  * vector<unsigned>>) are passed as CSR: ascending node ids, node_start[n_nodes+1], feature indices in vector order.
  * kf_valid[i] = vpMapPointsKF[i] != NULL && !isBad().  match[idxF] = key-frame feature index whose map point is assigned
@@ -195,7 +195,7 @@ int rgbl_search_by_bow(rgbl_ctx* ctx, int n_kf, const uint8_t* kf_desc, const fl
                        float nn_ratio, int check_orientation, int32_t* match, int* n_matches);
 
 /* ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, float th,
- * int ORBdist) (include/ORBmatcher.h:57, src/ORBmatcher.cc:1889-2010): relocalisation refinement.  Key-frame map points
+ * int ORBdist) (include/ORBmatcher.h:55, src/ORBmatcher.cc:1889-2010): relocalisation refinement.  Key-frame map points
  * i: valid[i] = pMP && !isBad() && !sAlreadyFound.count(pMP); kf_angle = pKF->mvKeysUn[i].angle; mf_min/max_dist =
  * mfMinDistance / mfMaxDistance.  cur_occupied[i2] != 0 <=> CurrentFrame.mvpMapPoints[i2] != NULL.  match as above.   */
 int rgbl_search_by_projection_reloc(rgbl_ctx* ctx, const rgbl_frame_view* cur, const float cur_pose[7], int n, const uint8_t* valid,
@@ -291,7 +291,7 @@ int rgbl_resident_compute_bow(rgbl_ctx* ctx, const rgbl_vocabulary* voc, int fra
 
 /* Resident tracking chain over the frames of the last batched call, entirely on the device: for t = 1..n-1
  * SearchByProjection(frame t, frame t-1, th) -> PoseOptimization, every LiDAR-depth keypoint of frame t-1 acting as a map
- * point (Frame::UnprojectStereo, src/Frame.cc:1097-1112, with the estimated pose of t-1; constant-pose motion model).
+ * point (Frame::UnprojectStereo, src/Frame.cc:1137-1150, with the estimated pose of t-1; constant-pose motion model).
  * This is harness glue around the two reference functions (Tracking::TrackWithMotionModel, src/Tracking.cc:2888-2981,
  * stays on the host in the drop-in).  poses_out[n][7], n_matches[n], n_inliers[n]; entry 0 = (pose0, 0, 0).           */
 int rgbl_resident_track(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono,

@@ -902,7 +902,7 @@ __global__ void __launch_bounds__(256) search_reloc_collect_kernel(FrameDev f, c
 
 // ---- resident tracking chain (TrackWithMotionModel-style glue between the reference functions) ----------------
 // Every keypoint of the last frame that has a LiDAR depth acts as a map point: Frame::UnprojectStereo
-// (src/Frame.cc:1097-1112) with the last pose, descriptor = the keypoint's own descriptor.
+// (src/Frame.cc:1137-1150) with the last pose, descriptor = the keypoint's own descriptor.
 __global__ void __launch_bounds__(256) chain_prep_kernel(ChainPrepDev cp, const float* __restrict__ last_pose, const float* __restrict__ cur_pose) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i == 0) chain_prep_flags(cp, last_pose, cur_pose);

@@ -152,7 +152,7 @@ __device__ __forceinline__ void se3f_rotate(const float* T, const float p[3], fl
 
 
 // ---- resident tracking chain: the previous frame's LiDAR-depth keypoints as map points -----------------------------------
-// Frame::UnprojectStereo (src/Frame.cc:1097-1112) with the frame's estimated pose, the bForward / bBackward test of
+// Frame::UnprojectStereo (src/Frame.cc:1137-1150) with the frame's estimated pose, the bForward / bBackward test of
 // SearchByProjection (src/ORBmatcher.cc:1686-1693) and the per-point fields the search reads.  Shared by chain_prep_kernel and
 // the tail of pose_optimize_kernel (which prepares the next frame's search as soon as the pose is known: one launch less).
 struct ChainPrepDev {

@@ -20,7 +20,7 @@ def extract_frames(seq, ts, nfeatures=2000):
 
 
 def unproject(fr, pose):
-    """Frame::UnprojectStereo for every keypoint with depth (src/Frame.cc:1097-1112): world points for an identity-rotation pose."""
+    """Frame::UnprojectStereo for every keypoint with depth (src/Frame.cc:1137-1150): world points for an identity-rotation pose."""
     k, z = fr["k"], fr["depth"]
     f32 = np.float32
     zz = np.where(z > 0, z, f32(1)).astype(f32)

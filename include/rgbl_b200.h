@@ -340,6 +340,10 @@ int rgbl_quadtree_select(const int32_t* xys, int n, int min_x, int max_x, int mi
 int rgbl_quadtree_select_block_emulation(const int32_t* xys, int n, int min_x, int max_x, int min_y, int max_y, int n_desired,
                                          int32_t* out_xys, int cap);
 int rgbl_std_sort_emulation(const int32_t* size_ulx, int n, int32_t* perm_out);
+/* The block-parallel formulation of that sort (mode 0; mode > 0: depth limit mode - 1, which forces the heapsort fallback) or,
+ * as ground truth, the C++ library's own std::sort with the reference's comparator (mode < 0).  n <= 1024.
+ * rgbl_quadtree_select_block_emulation runs its budgeted expansion with the block-parallel sort when n_desired < 0.       */
+int rgbl_std_sort_block_emulation(const int32_t* size_ulx, int n, int mode, int32_t* perm_out);
 
 /* Test hook (host-only): the strip formulation of the per-cell FAST detection (fast_strip.cuh; src/ORBextractor.cc:805-868)
  * executed phase-sequentially on the host for pyramid level `level` of a width x height image.  level_img: that level's

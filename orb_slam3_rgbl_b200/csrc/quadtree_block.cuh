@@ -181,6 +181,7 @@ struct Shared {
     SortItem open[2][kMaxNodes];   // expandable children: [cur] produced by the last pass, [1-cur] being built
     int open_slot[kMaxNodes * 4];  // per push index: position in the next open list, or -1
     int n_nodes, n_open, cur_tab, cur_open, n_div, total_push, n_keep, n_expand, scan_total, flag;
+    int block_sort;                // 1: block_std_sort (prepared, not yet run on a GPU), 0: one-thread std_sort
     int root_cnt[kMaxRoots + 1];
     unsigned long long scan_carry[1024 + 32];
 };
@@ -257,6 +258,145 @@ QT_BIG void scan_int(int* a, int n, int* total, Shared& s) {
     *total = run;
     (void)s;
 #endif
+}
+
+// ---- libstdc++ std::sort, block-parallel --------------------------------------------------------------------------
+// Produces exactly what std_sort() above produces (ties included), with the CTA instead of one thread:
+//   * __introsort_loop recurses on [cut, last) and loops on [first, cut): the ranges are disjoint, so all segments of one
+//     recursion depth can be partitioned at the same time (breadth first);
+//   * __unguarded_partition is a pairing: with L_1 < L_2 < ... the positions (ascending) whose value is not less than the
+//     pivot and R_1 > R_2 > ... the positions (descending) whose value is not greater, the sequential loop swaps
+//     (L_k, R_k) for k = 1..m, m = the number of k with L_k < R_k, and returns cut = min(L_{m+1}, R_m) (the pointers never
+//     revisit a swapped position, so the stoppers of the ORIGINAL segment decide).  Ranks come from one block scan of
+//     packed flags; the pairs swap in parallel;
+//   * __final_insertion_sort is an insertion sort (guarded or not), i.e. a STABLE sort of what the partitions left:
+//     computed as a rank sort (rank = smaller-or-equal elements before + smaller elements after);
+//   * a segment that exhausts the depth limit (heapsort in the reference; never seen on quad-tree inputs) makes the whole
+//     call fall back to the one-thread restatement on the saved input.
+// v: n items (shared memory); tmp: n items of scratch; the int scratch comes from fields of `s` that are dead between two
+// divide passes.  depth_limit < 0: the reference's 2 * floor(log2 n).
+struct SortSeg { short first, last, depth, m; };
+
+QT_BIG void block_std_sort(Shared& s, SortItem* v, SortItem* tmp, int n, int depth_limit) {
+    if (n <= 1) return;
+    int* const scanbuf = &s.cc[0][0];                       // n + 1 packed flags / prefixes
+    int* const posL = s.pushbase;                           // stoppers by rank, segment-relative slots
+    int* const posR = s.keepbase;
+    SortSeg* const seg[2] = {reinterpret_cast<SortSeg*>(&s.cc[0][0] + kMaxNodes + 8), reinterpret_cast<SortSeg*>(&s.cc[0][0] + kMaxNodes + 8) + 128};
+    int* const ctl = &s.cc[0][0] + kMaxNodes + 8 + 512;     // [0] segments of this level, [1] of the next, [2] fallback flag
+    QT_FOR(i, n) tmp[i] = v[i];                             // saved input for the fallback
+    QT_SINGLE {
+        int lg = 0;
+        for (int t = n; t > 1; t >>= 1) ++lg;
+        ctl[0] = 0; ctl[1] = 0; ctl[2] = 0;
+        if (n > 16) { seg[0][0].first = 0; seg[0][0].last = (short)n; seg[0][0].depth = (short)(depth_limit < 0 ? 2 * lg : depth_limit); ctl[0] = 1; }
+    }
+    QT_SYNC();
+    int cur = 0;
+    for (;;) {
+        const int ns = ctl[0];
+        if (ns == 0 || ctl[2]) break;
+        SortSeg* S = seg[cur];
+        SortSeg* Nx = seg[cur ^ 1];
+        QT_FOR(sg, ns) {                                    // pivot selection: __move_median_to_first(first, first+1, mid, last-1)
+            SortSeg& q = S[sg];
+            q.m = 0;
+            if (q.depth == 0) { ctl[2] = 1; }
+            else {
+                --q.depth;
+                const int first = q.first, a = first + 1, b = first + (q.last - first) / 2, c = q.last - 1;
+                if (item_less(v[a], v[b])) {
+                    if (item_less(v[b], v[c])) qs_swap(v, first, b);
+                    else if (item_less(v[a], v[c])) qs_swap(v, first, c);
+                    else qs_swap(v, first, a);
+                } else if (item_less(v[a], v[c])) qs_swap(v, first, a);
+                else if (item_less(v[b], v[c])) qs_swap(v, first, c);
+                else qs_swap(v, first, b);
+            }
+        }
+        QT_SYNC();
+        if (ctl[2]) break;
+        QT_FOR(i, n) {                                      // stopper flags: low half "not less than the pivot", high half "not greater"
+            int f = 0;
+            for (int sg = 0; sg < ns; ++sg)
+                if (i > S[sg].first && i < S[sg].last) {
+                    const SortItem piv = v[S[sg].first];
+                    f = (item_less(v[i], piv) ? 0 : 1) | (item_less(piv, v[i]) ? 0 : 0x10000);
+                    break;
+                }
+            scanbuf[i] = f;
+        }
+        QT_SYNC();
+        scan_int(scanbuf, n, &s.scan_total, s);
+        QT_SINGLE { scanbuf[n] = s.scan_total; }
+        QT_SYNC();
+        QT_FOR(i, n) {
+            const int e = scanbuf[i], f = scanbuf[i + 1] - e;
+            if (f) {
+                for (int sg = 0; sg < ns; ++sg)
+                    if (i > S[sg].first && i < S[sg].last) {
+                        const int base = S[sg].first + 1, e0 = scanbuf[base], e1 = scanbuf[S[sg].last];
+                        if (f & 0xffff) posL[base + ((e - e0) & 0xffff)] = i;
+                        if (f >> 16) posR[base + ((e1 - e0) >> 16) - 1 - ((e - e0) >> 16)] = i;
+                        break;
+                    }
+            }
+        }
+        QT_SYNC();
+        QT_FOR(i, n) {                                      // pair k of its segment: swap while L_k < R_k
+            for (int sg = 0; sg < ns; ++sg)
+                if (i > S[sg].first && i < S[sg].last) {
+                    const int base = S[sg].first + 1, k = i - base, d = scanbuf[S[sg].last] - scanbuf[base];
+                    const int nL = d & 0xffff, nR = d >> 16, np = nL < nR ? nL : nR;
+                    if (k < np && posL[base + k] < posR[base + k]) {
+                        qs_swap(v, posL[base + k], posR[base + k]);
+                        if (k + 1 >= np || !(posL[base + k + 1] < posR[base + k + 1])) S[sg].m = (short)(k + 1);
+                    }
+                    break;
+                }
+        }
+        QT_SYNC();
+        QT_FOR(sg, ns) {                                    // cut = min(L_{m+1}, R_m); children longer than 16 go to the next level
+            const SortSeg q = S[sg];
+            const int base = q.first + 1, d = scanbuf[q.last] - scanbuf[base], nL = d & 0xffff, m = q.m;
+            int cut = q.last;
+            if (m > 0) cut = posR[base + m - 1];
+            if (m < nL && posL[base + m] < cut) cut = posL[base + m];
+            for (int h = 0; h < 2; ++h) {
+                const int f = h ? q.first : cut, l = h ? cut : q.last;
+                if (l - f > 16) {
+#if QT_DEVICE
+                    const int slot = atomicAdd(&ctl[1], 1);
+#else
+                    const int slot = ctl[1]++;
+#endif
+                    Nx[slot].first = (short)f; Nx[slot].last = (short)l; Nx[slot].depth = q.depth; Nx[slot].m = 0;
+                }
+            }
+        }
+        QT_SYNC();
+        QT_SINGLE { ctl[0] = ctl[1]; ctl[1] = 0; }
+        QT_SYNC();
+        cur ^= 1;
+    }
+    if (ctl[2]) {                                           // depth limit reached somewhere: the reference heap-sorts that segment
+        QT_SYNC();
+        QT_FOR(i, n) v[i] = tmp[i];
+        QT_SYNC();
+        QT_SINGLE { std_sort(v, n); }
+        QT_SYNC();
+        return;
+    }
+    QT_FOR(i, n) {                                          // __final_insertion_sort == stable sort of the current order
+        const SortItem x = v[i];
+        int r = 0;
+        for (int j = 0; j < i; ++j) r += item_less(x, v[j]) ? 0 : 1;
+        for (int j = i + 1; j < n; ++j) r += item_less(v[j], x) ? 1 : 0;
+        tmp[r] = x;
+    }
+    QT_SYNC();
+    QT_FOR(i, n) v[i] = tmp[i];
+    QT_SYNC();
 }
 
 QT_FN int cand_x(unsigned int c) { return (int)(c & 0xfffu); }
@@ -385,8 +525,9 @@ QT_BIG int divide_pass(Shared& s, const unsigned int* cand, int n, Scratch g, in
 // out: packed candidates of the survivors in the reference's output order.  Returns the count (or -1 if the
 // configuration exceeds the on-chip capacities; the caller then uses the host implementation).
 QT_FN int distribute(Shared& s, const unsigned int* cand, int n, int width, int height, int N, Scratch g,
-                     unsigned int* out, int out_cap) {
+                     unsigned int* out, int out_cap, int block_sort = 0) {
     if (n <= 0) return 0;
+    QT_SINGLE { s.block_sort = block_sort; }
 #if QT_DEVICE
     const int n_ini = (int)roundf(static_cast<float>(width) / height);
 #else
@@ -468,7 +609,8 @@ QT_FN int distribute(Shared& s, const unsigned int* cand, int n, int width, int 
             while (!done) {
                 const int prev2 = s.n_nodes;
                 const int n_open = s.n_open;
-                QT_SINGLE { std_sort(s.open[s.cur_open], n_open); }
+                if (s.block_sort) block_std_sort(s, s.open[s.cur_open], s.open[s.cur_open ^ 1], n_open, -1);
+                else { QT_SINGLE { std_sort(s.open[s.cur_open], n_open); } }
                 QT_SYNC();
                 // child counts of every open node (they are all candidates for division)
                 {

@@ -1,6 +1,7 @@
 // Device quad-tree distribution (one CTA per (frame, level)) + packing of the per-level survivor lists into the
 // per-frame SelKp list the describe kernel consumes.  Algorithm: quadtree_block.cuh.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -13,7 +14,7 @@ __global__ void __launch_bounds__(512) quadtree_kernel(const uint32_t* __restric
                                                        const int* __restrict__ frame_total, const LevelGeom* __restrict__ levels,
                                                        int n_levels, QtScratchDev scr, uint32_t* __restrict__ sel_lvl,
                                                        int* __restrict__ n_sel_lvl, const int* __restrict__ lvl_region,
-                                                       int cap_kp, int* __restrict__ status, int dyn_bytes) {
+                                                       int cap_kp, int* __restrict__ status, int dyn_bytes, int block_sort) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     qt::Shared& s = *reinterpret_cast<qt::Shared*>(smem_raw);
     const int l = blockIdx.x, f = blockIdx.y;
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(512) quadtree_kernel(const uint32_t* __restric
     }
     uint32_t* out = sel_lvl + (size_t)f * cap_kp + lvl_region[l];
     const int region_cap = lvl_region[l + 1] - lvl_region[l];
-    const int m = qt::distribute(s, dense + off, n, lg.max_bx - lg.min_bx, lg.max_by - lg.min_by, lg.quota, g, out, region_cap);
+    const int m = qt::distribute(s, dense + off, n, lg.max_bx - lg.min_bx, lg.max_by - lg.min_by, lg.quota, g, out, region_cap, block_sort);
     if (threadIdx.x == 0) {
         if (m < 0 || m > region_cap) { atomicExch(status, 1); n_sel_lvl[f * RGBL_MAX_LEVELS + l] = 0; }
         else n_sel_lvl[f * RGBL_MAX_LEVELS + l] = m;
@@ -87,20 +88,22 @@ int launch_quadtree(cudaStream_t st, const uint32_t* dense, const int* level_cnt
         if (cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, avail) != cudaSuccess) return -1;
         dyn_bytes = avail;
     }
+    // RGBL_QT_BLOCK_SORT=1: the block-parallel std::sort of the budgeted expansion (host twin validated; not yet run on a GPU)
+    static const int block_sort = [] { const char* e = getenv("RGBL_QT_BLOCK_SORT"); return (e && e[0] == '1') ? 1 : 0; }();
     quadtree_kernel<<<dim3(n_levels, n_frames), 512, dyn_bytes, st>>>(dense, level_cnt, frame_total, d_levels, n_levels, scr,
-                                                                   sel_lvl, n_sel_lvl, lvl_region, cap_kp, status, dyn_bytes);
+                                                                   sel_lvl, n_sel_lvl, lvl_region, cap_kp, status, dyn_bytes, block_sort);
     sel_pack_kernel<<<n_frames, 256, 0, st>>>(sel_lvl, n_sel_lvl, lvl_region, n_levels, cap_kp, sel, n_sel);
     return 0;
 }
 
 // Host execution of the SAME block algorithm (phase-sequential): CPU validation of the device logic.
-int quadtree_block_host(const uint32_t* cand, int n, int width, int height, int N, uint32_t* out, int out_cap) {
+int quadtree_block_host(const uint32_t* cand, int n, int width, int height, int N, uint32_t* out, int out_cap, int block_sort) {
     std::vector<int> pa(n + 1), pb(n + 1), na(n + 1), nb(n + 1);
     std::vector<unsigned long long> scan(n + 2);
     std::vector<unsigned char> quad(n + 1);
     qt::Scratch g{pa.data(), pb.data(), na.data(), nb.data(), scan.data(), quad.data()};
     qt::Shared* s = new qt::Shared();
-    const int m = qt::distribute(*s, cand, n, width, height, N, g, out, out_cap);
+    const int m = qt::distribute(*s, cand, n, width, height, N, g, out, out_cap, block_sort);
     delete s;
     return m;
 }
@@ -115,7 +118,9 @@ int rgbl_quadtree_select_block_emulation(const int32_t* xys, int n, int min_x, i
     if (n < 0 || (n > 0 && !xys) || !out_xys) return RGBL_E_INVALID;
     std::vector<uint32_t> c(n), o(cap);
     for (int i = 0; i < n; ++i) c[i] = rgbl::pack_cand(xys[3 * i], xys[3 * i + 1], xys[3 * i + 2]);
-    const int m = rgbl::quadtree_block_host(c.data(), n, max_x - min_x, max_y - min_y, n_desired, o.data(), cap);
+    // n_desired < 0: run the block-parallel std::sort variant with |n_desired|
+    const int m = rgbl::quadtree_block_host(c.data(), n, max_x - min_x, max_y - min_y, n_desired < 0 ? -n_desired : n_desired, o.data(), cap,
+                                            n_desired < 0 ? 1 : 0);
     if (m < 0) return RGBL_E_UNSUPPORTED;
     if (m > cap) return RGBL_E_CAPACITY;
     for (int i = 0; i < m; ++i) { out_xys[3 * i] = (int)(o[i] & 0xfff); out_xys[3 * i + 1] = (int)((o[i] >> 12) & 0xfff); out_xys[3 * i + 2] = (int)(o[i] >> 24); }
@@ -127,6 +132,24 @@ int rgbl_std_sort_emulation(const int32_t* size_ulx, int n, int32_t* perm_out) {
     std::vector<rgbl::qt::SortItem> v(n);
     for (int i = 0; i < n; ++i) { v[i].size = size_ulx[2 * i]; v[i].ulx = size_ulx[2 * i + 1]; v[i].node = i; }
     rgbl::qt::std_sort(v.data(), n);
+    for (int i = 0; i < n; ++i) perm_out[i] = v[i].node;
+    return 0;
+}
+
+// test hook: the block-parallel formulation of the same sort (phase-sequential on the host) and, as ground truth, the
+// C++ library's own std::sort with the reference's comparator.  mode 0: block formulation with the reference depth limit,
+// mode > 0: block formulation with depth limit `mode - 1` (exercises the heapsort fallback), mode < 0: real std::sort.
+int rgbl_std_sort_block_emulation(const int32_t* size_ulx, int n, int mode, int32_t* perm_out) {
+    if (n < 0 || n > rgbl::qt::kMaxNodes || (n > 0 && (!size_ulx || !perm_out))) return RGBL_E_INVALID;
+    std::vector<rgbl::qt::SortItem> v(n + 1), tmp(n + 1);
+    for (int i = 0; i < n; ++i) { v[i].size = size_ulx[2 * i]; v[i].ulx = size_ulx[2 * i + 1]; v[i].node = i; }
+    if (mode < 0) {
+        std::sort(v.begin(), v.begin() + n, [](const rgbl::qt::SortItem& a, const rgbl::qt::SortItem& b) { return rgbl::qt::item_less(a, b); });
+    } else {
+        rgbl::qt::Shared* s = new rgbl::qt::Shared();
+        rgbl::qt::block_std_sort(*s, v.data(), tmp.data(), n, mode - 1);
+        delete s;
+    }
     for (int i = 0; i < n; ++i) perm_out[i] = v[i].node;
     return 0;
 }

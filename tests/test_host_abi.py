@@ -251,3 +251,46 @@ def test_fast_strips_on_flat_and_saturated_images():
     for l in range(8):
         got, ref = _strip_fast(ex.level_image(l), 400, 240, l, nfeatures=1000), ex.level_candidates(l)
         assert got.shape == ref.shape and (got == ref).all(), l
+
+
+# ---- block-parallel std::sort (quadtree_block.cuh: block_std_sort), executed on the host -----------------------------------
+def _sort_perm(su, mode):
+    perm = np.empty(len(su), np.int32)
+    assert L.lib().rgbl_std_sort_block_emulation(L.ptr(np.ascontiguousarray(su, np.int32)), len(su), mode, L.ptr(perm)) == 0
+    return perm
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_block_std_sort_equals_libstdcxx_sort_including_ties(seed):
+    """Same permutation as the C++ library's std::sort with compareNodes (src/ORBextractor.cc:538-553): the order of equal
+    (size, UL.x) pairs is decided by the introsort's swaps, which the block formulation has to reproduce exactly."""
+    rng = np.random.default_rng(900 + seed)
+    for n in [0, 1, 2, 15, 16, 17, 18, 33, 64, 100, 257, 430, 777, 1024][seed % 7::7] + [int(rng.integers(17, 1025))]:
+        k_size, k_x = [(3, 4), (8, 30), (40, 40), (2, 2), (1000, 1000)][seed % 5]
+        su = np.stack([rng.integers(2, 2 + k_size, n), rng.integers(0, k_x, n) * 37], 1).astype(np.int32)
+        if seed % 4 == 1:
+            su = su[np.lexsort((su[:, 1], su[:, 0]))]                  # already sorted
+        if seed % 4 == 2:
+            su = su[np.lexsort((su[:, 1], su[:, 0]))][::-1]            # reversed
+        ref = _sort_perm(su, -1)
+        assert (_sort_perm(su, 0) == ref).all(), n
+        serial = np.empty(n, np.int32)
+        L.lib().rgbl_std_sort_emulation(L.ptr(np.ascontiguousarray(su)), n, L.ptr(serial))
+        assert (serial == ref).all(), n
+        for forced in (1, 2, 4):                                       # depth limit 0, 1, 3: heapsort fallback path
+            assert (_sort_perm(su, forced) == ref).all(), (n, forced)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_block_quadtree_with_block_sort_matches_oracle(seed):
+    img = S.make_image(140 + seed, 900, 300)
+    ex = oracle.Extractor(1500); ex(img)
+    for l in range(8):
+        cand = ex.level_candidates(l)
+        h, w = ex.level_image(l).shape
+        n = int(ex.features_per_level[l])
+        out = np.empty((n + 64, 3), np.int32)
+        m = L.lib().rgbl_quadtree_select_block_emulation(L.ptr(np.ascontiguousarray(cand, np.int32)), len(cand), 16, w - 16, 16, h - 16, -n, L.ptr(out), len(out))
+        ref = ex.level_keypoints(l)
+        assert m == len(ref)
+        assert (out[:m, 0] + 16 == ref["x"]).all() and (out[:m, 1] + 16 == ref["y"]).all() and (out[:m, 2] == ref["response"]).all()

@@ -590,13 +590,24 @@ QT_FN int distribute(Shared& s, const unsigned int* cand, int n, int width, int 
         const int prev = s.n_nodes;
         {   // full pass: D = every node with more than one key, processed in list order
             const NodeTable& T = s.tab[s.cur_tab];
-            QT_SINGLE {
-                int r = 0;
-                for (int i = 0; i < prev; ++i) {
-                    if (T.end[i] - T.beg[i] > 1) { s.proc[i] = (short)r; s.by_rank[r] = (short)i; ++r; }
+            if (s.block_sort) {              // the same compaction through a block scan of the flags
+                QT_FOR(i, prev) s.pushbase[i] = (T.end[i] - T.beg[i] > 1) ? 1 : 0;
+                QT_SYNC();
+                scan_int(s.pushbase, prev, &s.n_div, s);
+                QT_SYNC();
+                QT_FOR(i, prev) {
+                    if (T.end[i] - T.beg[i] > 1) { const int r = s.pushbase[i]; s.proc[i] = (short)r; s.by_rank[r] = (short)i; }
                     else s.proc[i] = -1;
                 }
-                s.n_div = r;
+            } else {
+                QT_SINGLE {
+                    int r = 0;
+                    for (int i = 0; i < prev; ++i) {
+                        if (T.end[i] - T.beg[i] > 1) { s.proc[i] = (short)r; s.by_rank[r] = (short)i; ++r; }
+                        else s.proc[i] = -1;
+                    }
+                    s.n_div = r;
+                }
             }
             QT_SYNC();
         }
@@ -633,16 +644,37 @@ QT_FN int distribute(Shared& s, const unsigned int* cand, int n, int width, int 
                         s.pushes[nd] = (short)(((mask >> 0) & 1) + ((mask >> 1) & 1) + ((mask >> 2) & 1) + ((mask >> 3) & 1));
                     }
                     QT_SYNC();
-                    QT_SINGLE {
-                        int size2 = prev2, m = 0;
-                        for (int r = 0; r < n_open; ++r) {
-                            size2 += s.pushes[s.by_rank[r]] - 1;
-                            ++m;
-                            if (size2 >= N) break;
+                    if (s.block_sort) {
+                        // the list grows by pushes - 1 >= 0 per division: the sequential loop stops after the first rank
+                        // whose running size reaches N, i.e. m = 1 + #{r : size after r < N} (capped at n_open)
+                        QT_FOR(r, n_open) s.keepbase[r] = s.pushes[s.by_rank[r]] - 1;
+                        QT_SINGLE { s.n_div = 0; }
+                        QT_SYNC();
+                        scan_int(s.keepbase, n_open, &s.scan_total, s);
+                        QT_SYNC();
+                        QT_FOR(r, n_open) {
+                            const int incl = prev2 + ((r + 1 < n_open) ? s.keepbase[r + 1] : s.scan_total);
+                            const int incl_next = (r + 1 < n_open) ? prev2 + ((r + 2 < n_open) ? s.keepbase[r + 2] : s.scan_total) : N;
+                            if (r == 0 && incl >= N) s.n_div = 1;
+                            if (incl < N && incl_next >= N) s.n_div = (r + 2 < n_open) ? r + 2 : n_open;
                         }
-                        // nodes beyond the break are not divided in this iteration
-                        for (int r = m; r < n_open; ++r) s.proc[s.by_rank[r]] = -1;
-                        s.n_div = m;
+                        QT_SYNC();
+                        {
+                            const int m = s.n_div;
+                            QT_FOR(r, n_open) if (r >= m) s.proc[s.by_rank[r]] = -1;
+                        }
+                    } else {
+                        QT_SINGLE {
+                            int size2 = prev2, m = 0;
+                            for (int r = 0; r < n_open; ++r) {
+                                size2 += s.pushes[s.by_rank[r]] - 1;
+                                ++m;
+                                if (size2 >= N) break;
+                            }
+                            // nodes beyond the break are not divided in this iteration
+                            for (int r = m; r < n_open; ++r) s.proc[s.by_rank[r]] = -1;
+                            s.n_div = m;
+                        }
                     }
                     QT_SYNC();
                 }

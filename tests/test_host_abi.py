@@ -128,7 +128,7 @@ def test_quadtree_empty_and_single():
 # ---- device quad-tree logic, executed on the host (same source as the kernel: quadtree_block.cuh) ----
 
 def _block(cand, w, h, n):
-    out = np.empty((max(n + 3, 4 * max(1, round((w - 32) / (h - 32)))), 3), np.int32)
+    out = np.empty((max(abs(n) + 3, 4 * max(1, round((w - 32) / (h - 32)))), 3), np.int32)
     m = L.lib().rgbl_quadtree_select_block_emulation(L.ptr(np.ascontiguousarray(cand, np.int32)), len(cand), 16, w - 16, 16, h - 16, n, L.ptr(out), len(out))
     assert m >= 0
     return out[:m]
@@ -171,10 +171,11 @@ def test_block_quadtree_matches_oracle_random_ties(seed):
     sc = rng.integers(7, 12 if seed % 2 else 200, len(xy))
     cand = np.concatenate([xy, sc[:, None]], 1).astype(np.int32)
     for budget in (1, 5, 60, 434, 900):
-        got = _block(cand, w, h, budget)
         ref = _oracle_quadtree(cand, w, h, budget)
-        assert len(got) == len(ref)
-        assert (got[:, 0] == ref["x"]).all() and (got[:, 1] == ref["y"]).all() and (got[:, 2] == ref["response"]).all()
+        for mode in (1, -1):                 # -1: block-parallel std::sort and scan-based control loops (RGBL_QT_BLOCK_SORT=1 path)
+            got = _block(cand, w, h, mode * budget)
+            assert len(got) == len(ref)
+            assert (got[:, 0] == ref["x"]).all() and (got[:, 1] == ref["y"]).all() and (got[:, 2] == ref["response"]).all()
 
 
 def test_header_is_plain_c():

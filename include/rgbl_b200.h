@@ -352,6 +352,12 @@ int rgbl_std_sort_block_emulation(const int32_t* size_ulx, int n, int mode, int3
 int rgbl_fast_strips_emulation(const rgbl_orb_params* orb, int width, int height, int level, const uint8_t* level_img, int stride,
                                int max_cells, int max_width, int32_t* out_xys, int cap);
 
+/* Test hook (host-only): orientation (degrees) and 32-byte rBRIEF descriptor of n keypoints (xy: n x 2 level coordinates, at
+ * least 19 px from the border) of one pyramid level and its blurred copy, computed by the host twin of the staged describe
+ * kernel (describe_warp.cuh; IC_Angle src/ORBextractor.cc:76-103, computeOrbDescriptor :107-146).                          */
+int rgbl_describe_staged_emulation(const rgbl_orb_params* orb, const uint8_t* level_img, const uint8_t* blurred_img, int w, int h,
+                                   int stride, int n, const int32_t* xy, float* angle_out, uint8_t* desc_out);
+
 #ifdef __cplusplus
 }
 #endif

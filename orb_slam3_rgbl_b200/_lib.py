@@ -113,6 +113,7 @@ SYMBOLS = {
     "rgbl_quadtree_select_block_emulation": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i]),
     "rgbl_std_sort_emulation": (_i, [_vp, _i, _vp]),
     "rgbl_std_sort_block_emulation": (_i, [_vp, _i, _i, _vp]),
+    "rgbl_describe_staged_emulation": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rgbl_fast_strips_emulation": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _i]),
 }
 

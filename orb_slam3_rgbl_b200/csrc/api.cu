@@ -132,7 +132,9 @@ static int create(const rgbl_config* cfg, Ctx** out) {
         CUF(dmalloc(&c->qt_scr.scan, (size_t)c->dense_cap + (size_t)B * nl + 8));
         CUF(dmalloc(&c->qt_scr.quad, (size_t)c->dense_cap));
     }
-    {   // optional strip formulation of the FAST kernel
+    {   // optional strip formulation of the FAST kernel / staged describe kernel (prepared, not yet run on a GPU)
+        const char* envd = getenv("RGBL_DESCRIBE_STAGED");
+        c->describe_staged = envd && envd[0] == '1';
         const char* env = getenv("RGBL_FAST_STRIPS");
         if (env && env[0] == '1') {
             build_fast_strips(c->cells, 8, 264, c->strips, c->strip_rows_cap, c->strip_list_cap);
@@ -247,8 +249,9 @@ static int run_extract(Ctx* c, int n_frames, const std::function<void()>& aux_wo
         stage_end(c, ST_QUADTREE, c->st, 2);
         CU(cudaStreamWaitEvent(c->st, c->ev_blur, 0));
         stage_begin(c, ST_DESCRIBE, c->st);
-        launch_describe(c->st, c->d_pyr, c->d_blur, c->frame_bytes, c->d_levels, c->d_sel, c->d_n_sel, c->cap_kp, c->cap_kp,
-                        c->tab.umax, c->d_kps, c->d_desc, n_frames);
+        (c->describe_staged ? launch_describe_staged : launch_describe)(c->st, c->d_pyr, c->d_blur, c->frame_bytes, c->d_levels, c->d_sel,
+                                                                        c->d_n_sel, c->cap_kp, c->cap_kp, c->tab.umax, c->d_kps, c->d_desc,
+                                                                        n_frames);
         stage_end(c, ST_DESCRIBE, c->st, 1);
         CU(cudaGetLastError());
         c->last_frames = n_frames;
@@ -332,8 +335,8 @@ static int run_extract(Ctx* c, int n_frames, const std::function<void()>& aux_wo
     CU(cudaMemcpyAsync(c->d_n_sel, c->h_n_sel, (size_t)n_frames * sizeof(int), cudaMemcpyHostToDevice, c->st));
     CU(cudaStreamWaitEvent(c->st, c->ev_blur, 0));
     stage_begin(c, ST_DESCRIBE, c->st);
-    launch_describe(c->st, c->d_pyr, c->d_blur, c->frame_bytes, c->d_levels, c->d_sel, c->d_n_sel, c->cap_kp, max_n,
-                    c->tab.umax, c->d_kps, c->d_desc, n_frames);
+    (c->describe_staged ? launch_describe_staged : launch_describe)(c->st, c->d_pyr, c->d_blur, c->frame_bytes, c->d_levels, c->d_sel,
+                                                                    c->d_n_sel, c->cap_kp, max_n, c->tab.umax, c->d_kps, c->d_desc, n_frames);
     stage_end(c, ST_DESCRIBE, c->st, max_n > 0 ? 1 : 0);
     CU(cudaGetLastError());
     c->last_frames = n_frames;

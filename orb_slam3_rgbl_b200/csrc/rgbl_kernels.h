@@ -39,6 +39,10 @@ void launch_blur(cudaStream_t st, const uint8_t* pyr, uint8_t* blur, size_t fram
 void launch_describe(cudaStream_t st, const uint8_t* pyr, const uint8_t* blur, size_t frame_stride,
                      const LevelGeom* d_levels, const SelKp* sel, const int* n_sel, int cap, int max_n,
                      const int umax[16], rgbl_keypoint* kps, uint8_t* desc, int n_frames);
+// describe_warp_kernels.cu: launch_describe with the pixel neighbourhoods staged in shared memory (same outputs)
+void launch_describe_staged(cudaStream_t st, const uint8_t* pyr, const uint8_t* blur, size_t frame_stride, const LevelGeom* d_levels,
+                            const SelKp* sel, const int* n_sel, int cap, int max_n, const int umax[16], rgbl_keypoint* kps, uint8_t* desc,
+                            int n_frames);
 void launch_padded_level(cudaStream_t st, const uint8_t* pyr, size_t frame_stride, int frame, const LevelGeom& lg,
                          uint8_t* dst, int dst_pitch);
 

@@ -295,3 +295,33 @@ def test_block_quadtree_with_block_sort_matches_oracle(seed):
         ref = ex.level_keypoints(l)
         assert m == len(ref)
         assert (out[:m, 0] + 16 == ref["x"]).all() and (out[:m, 1] + 16 == ref["y"]).all() and (out[:m, 2] == ref["response"]).all()
+
+
+# ---- staged describe kernel (describe_warp.cuh), host twin ----------------------------------------------------------------
+@pytest.mark.parametrize("seed,size", [(0, (900, 300)), (1, (1241, 376)), (2, (640, 480)), (3, (333, 250))])
+def test_staged_describe_matches_the_oracle(seed, size):
+    """Angles (bit-exact floats) and descriptors of every keypoint of a real extraction, level by level."""
+    w, h = size
+    img = S.make_image(500 + seed, w, h)
+    ex = oracle.Extractor(1200)
+    kps, desc, _ = ex(img)
+    prm = L.OrbParams(1200, 1.2, 8, 12, 7)
+    base = 0
+    for l in range(8):
+        lv = ex.level_image(l)
+        bl = oracle.gaussian_blur7(lv)
+        kl = ex.level_keypoints(l)
+        n = len(kl)
+        if n == 0:
+            continue
+        xy = np.ascontiguousarray(np.stack([kl["x"], kl["y"]], 1).astype(np.int32))
+        ang = np.empty(n, np.float32); d = np.empty((n, 32), np.uint8)
+        rc = L.lib().rgbl_describe_staged_emulation(C.byref(prm), L.ptr(lv), L.ptr(bl), lv.shape[1], lv.shape[0], lv.strides[0], n,
+                                                    L.ptr(xy), L.ptr(ang), L.ptr(d))
+        assert rc == 0
+        ref = kps[base:base + n]
+        assert (ref["octave"] == l).all()
+        assert (ang.view(np.uint32) == np.ascontiguousarray(ref["angle"]).view(np.uint32)).all(), l
+        assert (d == desc[base:base + n]).all(), l
+        base += n
+    assert base == len(kps) > 500

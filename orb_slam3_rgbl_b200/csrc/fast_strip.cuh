@@ -292,7 +292,13 @@ FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo
                 if (s > m) {
                     const bool ini = s >= ini_th;
                     flags |= (ini ? 3u : 1u) << (8 * k);
-                    if (ini) misc[kAnyIni + cell] = 1;
+                    if (ini) {
+#if FS_DEVICE
+                        atomicOr(&misc[kAnyIni + cell], 1);     // several survivors of a cell may set it: keep racecheck clean
+#else
+                        misc[kAnyIni + cell] = 1;
+#endif
+                    }
                 }
             }
         }

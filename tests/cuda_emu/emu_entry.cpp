@@ -1,0 +1,101 @@
+// TEST INFRASTRUCTURE: C entry points that run the library's kernels (device code paths) on the CUDA-on-CPU shim.
+// The marshalling mirrors the host-twin hooks of the product library; the difference is that these go through the real
+// launchers (launch_fast_strips, launch_describe_staged, launch_quadtree) and therefore through the kernels' device branches.
+#include "cuda_runtime.h"
+
+#include "fast_strip_kernels.emu.cpp"
+#include "describe_warp_kernels.emu.cpp"
+#include "quadtree_kernels.emu.cpp"
+#include "pose_kernels.emu.cpp"          // compiled with -DPOSE_MIXED_SOLVE=1: the float32 solve + refinement variant
+
+using namespace rgbl;
+
+extern "C" {
+
+int emu_fast_strips(const rgbl_orb_params* orb, int width, int height, int level, const uint8_t* level_img, int stride, int max_cells,
+                    int max_width, int32_t* out_xys, int cap) {
+    OrbTables tab;
+    int rc = compute_orb_tables(*orb, tab);
+    if (rc) return rc;
+    std::vector<LevelGeom> levels; std::vector<CellInfo> cells; std::vector<LinCoef> coefs; size_t fb = 0; std::string err;
+    rc = build_geometry(width, height, tab, levels, cells, coefs, fb, err);
+    if (rc) return rc;
+    std::vector<StripInfo> strips; int rows_cap = 0, list_cap = 0;
+    build_fast_strips(cells, max_cells, max_width, strips, rows_cap, list_cap);
+    const LevelGeom& lg = levels[level];
+    std::vector<uint8_t> pyr(fb + 256, 0);
+    for (int y = 0; y < lg.h; ++y) std::memcpy(&pyr[lg.off + (size_t)y * lg.pitch], level_img + (size_t)y * stride, lg.w);
+    int first = -1, count = 0;
+    for (size_t i = 0; i < strips.size(); ++i) if (strips[i].level == level) { if (first < 0) first = (int)i; ++count; }
+    std::vector<uint32_t> slots(cells.size() * kCellCap);
+    std::vector<int> counts(cells.size(), 0);
+    int overflow = 0;
+    if (launch_fast_strips(nullptr, pyr.data(), fb, levels.data(), cells.data(), (int)cells.size(), strips.data() + first, count, rows_cap,
+                           list_cap, orb->ini_th_fast, orb->min_th_fast, slots.data(), counts.data(), &overflow, 1) != 0) return -100;
+    if (overflow) return RGBL_E_CAPACITY;
+    int n = 0;
+    for (int c = lg.cell_base; c < lg.cell_base + lg.n_cells; ++c)
+        for (int k = 0; k < counts[c]; ++k) {
+            if (n >= cap) return RGBL_E_CAPACITY;
+            const uint32_t p = slots[(size_t)c * kCellCap + k];
+            out_xys[3 * n] = (int)(p & 0xfff); out_xys[3 * n + 1] = (int)((p >> 12) & 0xfff); out_xys[3 * n + 2] = (int)(p >> 24);
+            ++n;
+        }
+    return n;
+}
+
+int emu_describe_staged(const rgbl_orb_params* orb, const uint8_t* level_img, const uint8_t* blurred_img, int w, int h, int stride, int n,
+                        const int32_t* xy, float* angle_out, uint8_t* desc_out) {
+    OrbTables tab;
+    const int rc = compute_orb_tables(*orb, tab);
+    if (rc) return rc;
+    LevelGeom lg{};
+    lg.w = w; lg.h = h; lg.pitch = (w + 63) & ~63; lg.off = 0; lg.scale = 1.f; lg.inv_scale = 1.f; lg.scaled_patch = kPatchSize;
+    const size_t fb = (size_t)lg.pitch * h;
+    std::vector<uint8_t> a(fb + 64, 0), b(fb + 64, 0);
+    for (int y = 0; y < h; ++y) { std::memcpy(&a[(size_t)y * lg.pitch], level_img + (size_t)y * stride, w); std::memcpy(&b[(size_t)y * lg.pitch], blurred_img + (size_t)y * stride, w); }
+    std::vector<SelKp> sel(n + 1);
+    for (int i = 0; i < n; ++i) { sel[i].x = (uint16_t)xy[2 * i]; sel[i].y = (uint16_t)xy[2 * i + 1]; sel[i].level = 0; sel[i].score = 0; sel[i].pad = 0; }
+    std::vector<rgbl_keypoint> kps(n + 1);
+    launch_describe_staged(nullptr, a.data(), b.data(), fb, &lg, sel.data(), &n, n, n, tab.umax, kps.data(), desc_out, 1);
+    for (int i = 0; i < n; ++i) angle_out[i] = kps[i].angle;
+    return 0;
+}
+
+// xys: n x 3 candidates (x, y relative to the FAST window origin, score) in the reference's order; out_xys: survivors in level
+// coordinates (+16) in the reference's output order.  The block-parallel sort is selected by RGBL_QT_BLOCK_SORT (read once).
+int emu_quadtree(const int32_t* xys, int n, int w, int h, int n_desired, int32_t* out_xys, int cap) {
+    LevelGeom lg{};
+    lg.w = w; lg.h = h; lg.min_bx = kFastBorder; lg.min_by = kFastBorder; lg.max_bx = w - kFastBorder; lg.max_by = h - kFastBorder;
+    lg.quota = n_desired;
+    std::vector<uint32_t> dense(n + 1);
+    for (int i = 0; i < n; ++i) dense[i] = pack_cand(xys[3 * i], xys[3 * i + 1], xys[3 * i + 2]);
+    int level_cnt[RGBL_MAX_LEVELS] = {n}, frame_total = n, lvl_region[2] = {0, cap}, status = 0, n_sel = 0, n_sel_lvl[RGBL_MAX_LEVELS] = {0};
+    std::vector<int> pa(n + 8), pb(n + 8), na(n + 8), nb(n + 8);
+    std::vector<unsigned long long> scan(n + 16);
+    std::vector<unsigned char> quad(n + 8);
+    QtScratchDev scr{pa.data(), pb.data(), na.data(), nb.data(), scan.data(), quad.data()};
+    std::vector<uint32_t> sel_lvl(cap + 8);
+    std::vector<SelKp> sel(cap + 8);
+    if (launch_quadtree(nullptr, dense.data(), level_cnt, &frame_total, &lg, 1, scr, sel_lvl.data(), n_sel_lvl, lvl_region, cap, &status,
+                        sel.data(), &n_sel, 1) != 0) return -100;
+    if (status) return RGBL_E_CAPACITY;
+    for (int i = 0; i < n_sel; ++i) { out_xys[3 * i] = sel[i].x; out_xys[3 * i + 1] = sel[i].y; out_xys[3 * i + 2] = sel[i].score; }
+    return n_sel;
+}
+
+// Optimizer::PoseOptimization on the emulated pose_optimize_kernel (one CTA of 512 threads); arguments as rgbl_pose_optimize.
+int emu_pose_optimize(const float pose_in[7], int n, const float* xw, const float* obs, const float* inv_sigma2, const uint8_t* stereo,
+                      float fx, float fy, float cx, float cy, float bf, float pose_out[7], uint8_t* outlier) {
+    PoseProblemDev p{};
+    p.n = n; p.n_dev = nullptr; p.pose_in_dev = nullptr; p.xw = xw; p.obs = obs; p.inv_sigma2 = inv_sigma2; p.stereo = stereo;
+    p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf;
+    for (int i = 0; i < 7; ++i) p.pose_in[i] = pose_in[i];
+    std::vector<double> work((size_t)n * 4 + 8);
+    std::vector<uint8_t> level(n + 8);
+    int n_inliers = 0;
+    launch_pose_optimize(nullptr, p, work.data(), level.data(), outlier, pose_out, &n_inliers, nullptr);
+    return n_inliers;
+}
+
+}  // extern "C"

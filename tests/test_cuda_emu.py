@@ -1,0 +1,96 @@
+"""The DEVICE code paths of the kernel variants that have not run on a GPU yet, executed on the CUDA-on-CPU shim
+(tests/cuda_emu: one OS thread per CUDA thread, real barriers, warp collectives as rendezvous) and compared with the oracle.
+The host twins (tests/test_host_abi.py) check the algorithms; this checks the device-only glue around them: shuffle scans,
+shared-memory atomics, warp reductions, dynamic shared-memory carving and the launch geometry."""
+import ctypes as C
+import importlib.util
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from orb_slam3_rgbl_b200 import _lib as L
+from orb_slam3_rgbl_b200 import synthetic as S
+
+HERE = Path(__file__).resolve().parent
+
+
+@pytest.fixture(scope="module")
+def emu():
+    os.environ["RGBL_QT_BLOCK_SORT"] = "1"          # read once by the emulated launch_quadtree
+    spec = importlib.util.spec_from_file_location("cuda_emu_build", HERE / "cuda_emu" / "build.py")
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    lib = C.CDLL(str(mod.build()))
+    vp, i = C.c_void_p, C.c_int
+    lib.emu_fast_strips.argtypes = [vp, i, i, i, vp, i, i, i, vp, i]
+    lib.emu_describe_staged.argtypes = [vp, vp, vp, i, i, i, i, vp, vp, vp]
+    lib.emu_quadtree.argtypes = [vp, i, i, i, i, vp, i]
+    return lib
+
+
+def test_strip_fast_kernel_device_path(emu):
+    w, h = 420, 240
+    img = S.make_image(77, w, h)
+    ex = oracle.Extractor(800); ex(img)
+    prm = L.OrbParams(800, 1.2, 8, 12, 7)
+    for l, (mc, mw) in zip((0, 2, 5), ((8, 264), (3, 130), (8, 264))):
+        lv = ex.level_image(l)
+        out = np.empty((1 << 15, 3), np.int32)
+        n = emu.emu_fast_strips(C.byref(prm), w, h, l, L.ptr(lv), lv.strides[0], mc, mw, L.ptr(out), len(out))
+        ref = ex.level_candidates(l)
+        assert n == len(ref) and (out[:n] == ref).all(), l
+
+
+def test_staged_describe_kernel_device_path(emu):
+    w, h = 420, 240
+    img = S.make_image(78, w, h)
+    ex = oracle.Extractor(300)
+    kps, desc, _ = ex(img)
+    prm = L.OrbParams(300, 1.2, 8, 12, 7)
+    base = 0
+    for l in range(8):
+        kl = ex.level_keypoints(l)
+        n = len(kl)
+        if l in (0, 3) and n:
+            lv = ex.level_image(l); bl = oracle.gaussian_blur7(lv)
+            xy = np.ascontiguousarray(np.stack([kl["x"], kl["y"]], 1).astype(np.int32))
+            ang = np.empty(n, np.float32); d = np.empty((n, 32), np.uint8)
+            assert emu.emu_describe_staged(C.byref(prm), L.ptr(lv), L.ptr(bl), lv.shape[1], lv.shape[0], lv.strides[0], n, L.ptr(xy), L.ptr(ang), L.ptr(d)) == 0
+            assert (ang.view(np.uint32) == np.ascontiguousarray(kps["angle"][base:base + n]).view(np.uint32)).all()
+            assert (d == desc[base:base + n]).all()
+        base += n
+
+
+def test_quadtree_kernel_with_block_sort_device_path(emu):
+    img = S.make_image(79, 700, 260)
+    ex = oracle.Extractor(1000); ex(img)
+    for l in (0, 4):
+        cand = np.ascontiguousarray(ex.level_candidates(l), np.int32)
+        hh, ww = ex.level_image(l).shape
+        nd = int(ex.features_per_level[l])
+        out = np.empty((nd + 64, 3), np.int32)
+        m = emu.emu_quadtree(L.ptr(cand), len(cand), ww, hh, nd, L.ptr(out), len(out))
+        ref = ex.level_keypoints(l)
+        assert m == len(ref)
+        assert (out[:m, 0] == ref["x"]).all() and (out[:m, 1] == ref["y"]).all() and (out[:m, 2] == ref["response"]).all()
+
+
+@pytest.mark.parametrize("seed,n", [(0, 300), (1, 520), (2, 40)])
+def test_pose_kernel_with_float32_solve_device_path(emu, seed, n):
+    """pose_optimize_kernel compiled with -DPOSE_MIXED_SOLVE=1 (float32 LDL^T + one refinement step with an FP64 residual) on
+    the emulator: 512 threads, butterfly reductions, speculative trial solves.  Same bar as the GPU parity test of the FP64
+    solve: pose within 1e-5 of the oracle, identical outlier flags and inlier count."""
+    import tracking_data as TD
+    p = TD.pose_problem(seed, n=n)
+    f32 = np.float32
+    pose0 = np.ascontiguousarray(p["pose0"], f32); xw = np.ascontiguousarray(p["xw"], f32); obs = np.ascontiguousarray(p["obs"], f32)
+    inv = np.ascontiguousarray(p["inv_s2"], f32); st = np.ascontiguousarray(p["stereo"], np.uint8)
+    emu.emu_pose_optimize.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                      C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    pose = np.empty(7, f32); out = np.empty(len(xw), np.uint8)
+    ni = emu.emu_pose_optimize(L.ptr(pose0), len(xw), L.ptr(xw), L.ptr(obs), L.ptr(inv), L.ptr(st), *[float(v) for v in TD.CAM], L.ptr(pose), L.ptr(out))
+    rn, rpose, rout = oracle.pose_optimize(p["pose0"], p["xw"], p["obs"], p["inv_s2"], p["stereo"], *TD.CAM)
+    assert ni == rn and (out == rout).all()
+    assert np.abs(pose - rpose).max() < 1e-5

@@ -516,6 +516,11 @@ int orc_extract(void* h, const uint8_t* img, int w, int hgt, int stride, int lap
     *n_out = 0;
     if (!img || w <= 0 || hgt <= 0) return -1;
     e->pyramid(img, w, hgt, stride);
+    // DistributeOctTree computes nIni = round(width / height) of the FAST window and divides by it (src/ORBextractor.cc:559-561):
+    // for a level taller than about twice its width nIni is 0 and the reference indexes an empty vector (undefined behaviour).
+    // The oracle refuses such images instead of restating a crash; the product reports RGBL_E_UNSUPPORTED for them.
+    for (int l = 0; l < e->nlevels; ++l)
+        if ((int)std::round(static_cast<float>(e->lw[l] - 32) / (e->lh[l] - 32)) < 1) return -5;
     e->keypoints();
     int total = 0;
     for (int l = 0; l < e->nlevels; ++l) total += (int)e->kps[l].size();

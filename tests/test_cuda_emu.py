@@ -43,6 +43,20 @@ def test_strip_fast_kernel_device_path(emu):
         assert n == len(ref) and (out[:n] == ref).all(), l
 
 
+def test_strip_fast_kernel_device_path_kitti_size(emu):
+    """Full-width strips (8 cells, 258 px) of the KITTI level-0 geometry, a threshold pair that makes most cells fall back to
+    minTh, and a tall-cell geometry (one cell row of 69 + 6 rows)."""
+    for (w, h), ths, l in (((1241, 376), (12, 7), 0), ((1241, 376), (60, 7), 1), ((640, 302), (12, 7), 6)):
+        img = S.make_image(91, w, h)
+        ex = oracle.Extractor(1000, ini_th=ths[0], min_th=ths[1]); ex(img)
+        prm = L.OrbParams(1000, 1.2, 8, ths[0], ths[1])
+        lv = ex.level_image(l)
+        out = np.empty((1 << 16, 3), np.int32)
+        n = emu.emu_fast_strips(C.byref(prm), w, h, l, L.ptr(lv), lv.strides[0], 8, 264, L.ptr(out), len(out))
+        ref = ex.level_candidates(l)
+        assert n == len(ref) and (out[:n] == ref).all(), (w, h, l)
+
+
 def test_staged_describe_kernel_device_path(emu):
     w, h = 420, 240
     img = S.make_image(78, w, h)

@@ -198,3 +198,12 @@ def test_pose_oracle_agrees_with_cv2_solvepnp_on_an_inlier_only_problem():
         assert np.abs(Ror - Rcv).max() < 2e-4, np.abs(Ror - Rcv).max()
         assert np.abs(pose[4:].astype(np.float64) - tvec.ravel()).max() < 5e-3, np.abs(pose[4:] - tvec.ravel()).max()
         assert keep.mean() > 0.8          # the generator scales the pixel noise with the octave; with unit information the noisiest points are cut
+
+
+def test_oracle_refuses_the_reference_division_by_zero_geometry():
+    """DistributeOctTree divides by nIni = round(window width / window height) (src/ORBextractor.cc:559-561); for portrait
+    pyramid levels that is 0 and the reference has undefined behaviour.  The oracle reports it instead of restating a crash."""
+    import pytest
+    from orb_slam3_rgbl_b200 import synthetic as S
+    with pytest.raises(RuntimeError):
+        oracle.Extractor(500)(S.make_image(1, 300, 560))

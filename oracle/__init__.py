@@ -441,6 +441,62 @@ def compute_bow(vocab: dict, desc, levelsup: int = 4):
     return (bw[:k.value].copy(), bv[:k.value].copy()), (fn[:m.value].copy(), fs[:m.value + 1].copy(), ff[:fs[m.value]].copy())
 
 
+# ---- the reference's own DBoW2 (oracle/_ref/libref_dbow2.so, compiled unmodified from /root/reference by `make -C oracle ref`) ----
+_REF_DBOW2 = _HERE / "_ref" / "libref_dbow2.so"
+_ref_dbow2 = None
+
+
+def ref_dbow2():
+    """-> ctypes handle of the reference's DBoW2 build, or None when it is neither prebuilt nor buildable (no /root/reference)."""
+    global _ref_dbow2
+    if _ref_dbow2 is None:
+        if not _REF_DBOW2.exists() and Path("/root/reference/Thirdparty/DBoW2").exists():
+            subprocess.run(["make", "-C", str(_HERE), "ref"], check=True, stdout=subprocess.DEVNULL)
+        if not _REF_DBOW2.exists():
+            return None
+        L = C.CDLL(str(_REF_DBOW2))
+        L.ref_voc_load_text.argtypes = [C.c_char_p]; L.ref_voc_load_text.restype = C.c_void_p
+        L.ref_voc_free.argtypes = [C.c_void_p]
+        L.ref_voc_size.argtypes = [C.c_void_p]; L.ref_voc_size.restype = C.c_int
+        L.ref_voc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_voc_transform.restype = C.c_int
+        _ref_dbow2 = L
+    return _ref_dbow2
+
+
+def write_vocabulary_text(vocab: dict, path, k: int) -> None:
+    """A flattened vocabulary (children stored in ascending node id order, ids breadth first) in the ORBvoc.txt format that
+    TemplatedVocabulary::loadFromTextFile reads (TemplatedVocabulary.h:1330-1424): header `k L scoring weighting`
+    (0 0 = L1_NORM, TF_IDF as in ORBvoc.txt), then one line per node 1..n-1: parent, is-leaf, 32 descriptor bytes, weight."""
+    cb, ci, nd, nw = vocab["child_begin"], vocab["child_index"], vocab["node_desc"], vocab["node_weight"]
+    n = len(nw)
+    parent = np.zeros(n, np.int64)
+    for i in range(n):
+        ch = ci[cb[i]:cb[i + 1]]
+        assert (np.diff(ch) > 0).all() and (ch > i).all(), "children must be in ascending id order after their parent"
+        parent[ch] = i
+    with open(path, "w") as f:
+        f.write(f"{k} {int(vocab['levels'])} 0 0\n")
+        lines = []
+        for i in range(1, n):
+            leaf = 1 if cb[i + 1] == cb[i] else 0
+            lines.append(f"{parent[i]} {leaf} " + " ".join(str(int(b)) for b in nd[i]) + f" {float(nw[i])!r}")
+        f.write("\n".join(lines))          # no trailing newline: the loader would read an empty last line as one more node
+
+
+def ref_compute_bow(voc_handle, desc, levelsup: int = 4):
+    """Frame::ComputeBoW through the reference's DBoW2 itself; same return layout as compute_bow."""
+    L = ref_dbow2()
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); n = len(desc)
+    bw = np.empty(max(n, 1), np.uint32); bv = np.empty(max(n, 1), np.float64)
+    fn = np.empty(max(n, 1), np.uint32); fs = np.empty(n + 2, np.int32); ff = np.empty(max(n, 1), np.int32)
+    k, m = C.c_int(0), C.c_int(0)
+    rc = L.ref_voc_transform(voc_handle, _p(desc), n, levelsup, len(bw), C.byref(k), _p(bw), _p(bv), len(fn), C.byref(m), _p(fn), _p(fs), _p(ff))
+    assert rc == 0
+    return (bw[:k.value].astype(np.int32), bv[:k.value].copy()), (fn[:m.value].astype(np.int32), fs[:m.value + 1].copy(), ff[:fs[m.value]].copy())
+
+
 def local_bundle_adjustment(poses, pose_fixed, points, e_point, e_pose, obs, stereo, inv_sigma2, fx, fy, cx, cy, bf, iterations=10):
     """Numerical core of Optimizer::LocalBundleAdjustment on a flat graph -> (poses[n,7], points[m,3], erase[n_edges], iterations, chi2)"""
     _late(lib())

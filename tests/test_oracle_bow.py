@@ -51,3 +51,30 @@ def test_oracle_equals_brute_force(seed, k, levels, ragged, n, levelsup):
         assert abs(bv.sum() - 1.0) < 1e-12 and (np.diff(bw) > 0).all() and (np.diff(fn) > 0).all()
         stopped = v["node_weight"][v["word_id"] >= 0] == 0
         assert len(ff) <= n and (stopped.any() or len(ff) == n)
+
+
+# ---- pinned against the reference's own DBoW2 (oracle/_ref/libref_dbow2.so = Thirdparty/DBoW2 compiled unmodified) -------------
+@pytest.mark.parametrize("seed,k,levels,ragged,levelsup", [(0, 10, 3, False, 2), (1, 8, 4, True, 3), (2, 10, 4, False, 4), (3, 5, 5, True, 4),
+                                                          (4, 10, 3, True, 1), (5, 3, 6, False, 4)])
+def test_bow_oracle_equals_the_reference_dbow2(tmp_path, seed, k, levels, ragged, levelsup):
+    """The synthetic vocabulary goes through the reference's text loader (ORBvoc.txt format) and its transform(); word ids,
+    node ids, feature lists must be identical and the BowVector values bit-identical doubles."""
+    ref = oracle.ref_dbow2()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_dbow2.so is not built and /root/reference is not available")
+    vocab = B.make_vocabulary(seed, k=k, levels=levels, ragged=ragged, shuffle_children=False)
+    path = tmp_path / "voc.txt"
+    oracle.write_vocabulary_text(vocab, path, k)
+    h = ref.ref_voc_load_text(str(path).encode())
+    assert h
+    try:
+        assert ref.ref_voc_size(h) == vocab["n_words"]
+        for n in (0, 1, 37, 1200):
+            desc = B.descriptors_near_words(vocab, n, 50 + seed) if n else np.zeros((0, 32), np.uint8)
+            (w, v), (fn, fs, ff) = oracle.compute_bow(vocab, desc, levelsup)
+            (rw, rv), (rfn, rfs, rff) = oracle.ref_compute_bow(h, desc, levelsup)
+            assert (w == rw).all() and len(w) == len(rw)
+            assert (v.view(np.uint64) == rv.view(np.uint64)).all()
+            assert (fn == rfn).all() and (fs == rfs).all() and (ff == rff).all()
+    finally:
+        ref.ref_voc_free(h)

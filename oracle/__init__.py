@@ -465,6 +465,41 @@ def ref_dbow2():
     return _ref_dbow2
 
 
+_REF_ORBEX = _HERE / "_ref" / "libref_orbextractor.so"
+_ref_orbex = None
+
+
+def ref_orbextractor():
+    """-> ctypes handle of the reference's own ORBextractor.cc build (oracle/ref_orbextractor_driver.cpp), or None."""
+    global _ref_orbex
+    if _ref_orbex is None:
+        if not _REF_ORBEX.exists() and Path("/root/reference/src/ORBextractor.cc").exists():
+            subprocess.run(["make", "-C", str(_HERE), "ref"], check=True, stdout=subprocess.DEVNULL)
+        if not _REF_ORBEX.exists():
+            return None
+        L = C.CDLL(str(_REF_ORBEX))
+        L.ref_orb_extract.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_orb_extract.restype = C.c_int
+        L.ref_orb_tables.argtypes = [C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_orb_tables.restype = C.c_int
+        _ref_orbex = L
+    return _ref_orbex
+
+
+def ref_orb_extract(img, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=12, min_th=7, lapping=(0, 0)):
+    """ORBextractor::operator() of the reference itself -> (keypoints[KP_DTYPE], descriptors, mono_index)."""
+    L = ref_orbextractor()
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = nfeatures + 64
+    kps = np.empty(cap, KP_DTYPE); desc = np.empty((cap, 32), np.uint8); n = C.c_int(0)
+    mono = L.ref_orb_extract(nfeatures, scale_factor, nlevels, ini_th, min_th, _p(img), img.shape[1], img.shape[0], img.strides[0],
+                             int(lapping[0]), int(lapping[1]), _p(kps), _p(desc), cap, C.byref(n))
+    if mono < -1:
+        raise RuntimeError(f"ref_orb_extract failed: {mono}")
+    return kps[:n.value].copy(), desc[:n.value].copy(), mono
+
+
 def write_vocabulary_text(vocab: dict, path, k: int) -> None:
     """A flattened vocabulary (children stored in ascending node id order, ids breadth first) in the ORBvoc.txt format that
     TemplatedVocabulary::loadFromTextFile reads (TemplatedVocabulary.h:1330-1424): header `k L scoring weighting`

@@ -207,3 +207,39 @@ def test_oracle_refuses_the_reference_division_by_zero_geometry():
     from orb_slam3_rgbl_b200 import synthetic as S
     with pytest.raises(RuntimeError):
         oracle.Extractor(500)(S.make_image(1, 300, 560))
+
+
+# ---- the extractor oracle against the reference's own ORBextractor.cc (oracle/_ref/libref_orbextractor.so) -----------------
+@pytest.mark.parametrize("seed,size,prm", [(0, (900, 300), (1500, 1.2, 8, 12, 7)), (1, (1241, 376), (2000, 1.2, 8, 20, 7)),
+                                          (2, (640, 480), (1000, 1.2, 8, 12, 7)), (3, (752, 480), (1200, 1.1, 6, 15, 5)),
+                                          (4, (500, 400), (300, 1.6, 4, 12, 7)), (5, (1241, 376), (5000, 1.2, 8, 7, 3))])
+def test_extractor_oracle_equals_the_reference_orbextractor(seed, size, prm):
+    """oracle.Extractor vs ORBextractor::operator() compiled unmodified from /root/reference/src/ORBextractor.cc (tables, pyramid
+    views, cell grid and fallback, DistributeOctTree with the real std::list / std::sort, IC_Angle, steered BRIEF, output order);
+    the OpenCV primitives under it are the oracle's restatements, pinned against python-cv2 by the tests above."""
+    import oracle as O
+    from orb_slam3_rgbl_b200 import synthetic as S
+    if O.ref_orbextractor() is None:
+        pytest.skip("oracle/_ref/libref_orbextractor.so is not built and /root/reference is not available")
+    w, h = size
+    img = S.make_image(700 + seed, w, h)
+    nf, sf, nl, ini, mn = prm
+    for lap in ((0, 0), (w // 3, w // 2)):
+        rk, rd, rmono = O.ref_orb_extract(img, nf, sf, nl, ini, mn, lap)
+        ok, od, omono = O.Extractor(nf, sf, nl, ini, mn)(img, lap)
+        assert len(ok) == len(rk) > 100 and omono == rmono
+        for f in ok.dtype.names:
+            assert (ok[f].view(np.uint32) == rk[f].view(np.uint32)).all(), f
+        assert (od == rd).all()
+
+
+def test_orb_tables_equal_the_reference_constructor():
+    import oracle as O
+    L = O.ref_orbextractor()
+    if L is None:
+        pytest.skip("reference build not available")
+    for nf, sf, nl in ((2000, 1.2, 8), (1000, 1.1, 6), (500, 2.0, 4), (1250, 1.44, 5)):
+        a, b, c, d = (np.empty(nl, np.float32) for _ in range(4))
+        assert L.ref_orb_tables(nf, sf, nl, O._p(a), O._p(b), O._p(c), O._p(d)) == nl
+        ex = O.Extractor(nf, sf, nl)
+        assert (ex.scale_factors.view(np.uint32) == a.view(np.uint32)).all() and (ex.inv_scale_factors.view(np.uint32) == b.view(np.uint32)).all()

@@ -108,3 +108,31 @@ def test_pose_kernel_with_float32_solve_device_path(emu, seed, n):
     rn, rpose, rout = oracle.pose_optimize(p["pose0"], p["xw"], p["obs"], p["inv_s2"], p["stereo"], *TD.CAM)
     assert ni == rn and (out == rout).all()
     assert np.abs(pose - rpose).max() < 1e-5
+
+
+def test_default_quadtree_kernel_device_path_in_a_fresh_process(emu):
+    """The shipped configuration (one-thread std::sort; RGBL_QT_BLOCK_SORT unset, which launch_quadtree reads once per process):
+    same emulated kernel, default mode.  Guards the default path against the edits made for the block mode."""
+    import subprocess, sys
+    code = r'''
+import ctypes as C, sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oracle
+from orb_slam3_rgbl_b200 import _lib as L, synthetic as S
+lib = C.CDLL(%r)
+lib.emu_quadtree.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+img = S.make_image(79, 700, 260)
+ex = oracle.Extractor(1000); ex(img)
+for l in (0, 5):
+    cand = np.ascontiguousarray(ex.level_candidates(l), np.int32)
+    hh, ww = ex.level_image(l).shape
+    nd = int(ex.features_per_level[l])
+    out = np.empty((nd + 64, 3), np.int32)
+    m = lib.emu_quadtree(L.ptr(cand), len(cand), ww, hh, nd, L.ptr(out), len(out))
+    ref = ex.level_keypoints(l)
+    assert m == len(ref) and (out[:m, 0] == ref["x"]).all() and (out[:m, 1] == ref["y"]).all() and (out[:m, 2] == ref["response"]).all()
+print("default-ok")
+''' % (str(HERE.parent), str(HERE), str(HERE / "cuda_emu" / "build" / "libcuda_emu.so"))
+    env = {k: v for k, v in os.environ.items() if k != "RGBL_QT_BLOCK_SORT"}
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "default-ok" in r.stdout, r.stderr[-2000:]

@@ -135,6 +135,8 @@ static int create(const rgbl_config* cfg, Ctx** out) {
     {   // optional strip formulation of the FAST kernel / staged describe kernel (prepared, not yet run on a GPU)
         const char* envd = getenv("RGBL_DESCRIBE_STAGED");
         c->describe_staged = envd && envd[0] == '1';
+        const char* envl = getenv("RGBL_DILATE_V2");
+        c->dilate_v2 = envl && envl[0] == '1';
         const char* env = getenv("RGBL_FAST_STRIPS");
         if (env && env[0] == '1') {
             build_fast_strips(c->cells, 8, 264, c->strips, c->strip_rows_cap, c->strip_list_cap);
@@ -369,7 +371,8 @@ static void run_depth_maps(Ctx* c, const DepthDev& dd, int n_frames, int max_pts
     stage_begin(c, ST_DEPTH_DILATE, st);
     const bool need_raw = dd.method == RGBL_DEPTH_AVERAGE_FILTERING || dd.method == RGBL_DEPTH_NEAREST_NEIGHBOR_PIXEL;
     float* raw_out = need_raw ? c->d_raw : raw;
-    launch_depth_resolve_dilate(st, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, dd, W, H, c->d_idx_map, c->stamp, raw_out, c->d_processed, n_frames);
+    (c->dilate_v2 ? launch_depth_resolve_dilate_v2 : launch_depth_resolve_dilate)(st, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, dd, W, H, c->d_idx_map,
+                                                                                  c->stamp, raw_out, c->d_processed, n_frames);
     int launches = 1;
     if (dd.method == RGBL_DEPTH_AVERAGE_FILTERING) { launch_depth_average_filter(st, c->d_raw, W, H, dd.avg_kernel, c->d_processed, n_frames); ++launches; }
     stage_end(c, ST_DEPTH_DILATE, st, launches);

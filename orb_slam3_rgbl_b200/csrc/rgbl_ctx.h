@@ -117,7 +117,7 @@ struct Ctx {
     // device quad-tree (quadtree_kernels.cu)
     bool device_quadtree = false, host_counts_valid = false;
     // strip formulation of the FAST kernel (fast_strip.cuh); selected with RGBL_FAST_STRIPS=1
-    bool fast_strips = false, describe_staged = false;   // RGBL_DESCRIBE_STAGED=1: describe_warp_kernels.cu
+    bool fast_strips = false, describe_staged = false, dilate_v2 = false;   // RGBL_DESCRIBE_STAGED=1: describe_warp_kernels.cu
     std::vector<StripInfo> strips;
     StripInfo* d_strips = nullptr;
     int strip_rows_cap = 0, strip_list_cap = 0;

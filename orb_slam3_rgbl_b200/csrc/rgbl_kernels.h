@@ -70,6 +70,9 @@ void launch_depth_project(cudaStream_t st, const float* pts, int pts_stride, con
 void launch_depth_resolve_dilate(cudaStream_t st, const float* pts, int pts_stride, const int* n_pts,
                                  const DepthDev& prm, int W, int H, const uint32_t* idx_map, uint32_t stamp,
                                  float* raw, float* processed, int n_frames);
+// depth_dilate_v2.cu: same outputs; empty tiles skip the structuring-element loop, taps as shared-memory offsets
+void launch_depth_resolve_dilate_v2(cudaStream_t st, const float* pts, int pts_stride, const int* n_pts, const DepthDev& prm, int W, int H,
+                                    const uint32_t* idx_map, uint32_t stamp, float* raw, float* processed, int n_frames);
 void launch_depth_average_filter(cudaStream_t st, const float* raw, int W, int H, int k, float* processed, int n_frames);
 void launch_depth_nn_pixel(cudaStream_t st, const float* raw, int W, int H, const rgbl_keypoint* kps, const rgbl_keypoint* kps_un,
                            const int* n_kp, int cap, int max_n, float bf, float R, float* depth, float* uright, int n_frames);

@@ -88,6 +88,8 @@ inline void emu_gather(unsigned long long v, unsigned long long out[32]) {      
 }
 inline unsigned __ballot_sync(unsigned, int pred) { unsigned long long a[32]; emu_gather(pred ? 1 : 0, a); unsigned r = 0; for (int l = 0; l < 32; ++l) r |= (unsigned)(a[l] & 1) << l; return r; }
 inline int __reduce_add_sync(unsigned, int v) { unsigned long long a[32]; emu_gather((unsigned long long)(long long)v, a); int s = 0; for (int l = 0; l < 32; ++l) s += (int)(long long)a[l]; return s; }
+inline unsigned __reduce_min_sync(unsigned, unsigned v) { unsigned long long a[32]; emu_gather(v, a); unsigned r = 0xffffffffu; for (int l = 0; l < 32; ++l) r = std::min(r, (unsigned)a[l]); return r; }
+inline unsigned __reduce_max_sync(unsigned, unsigned v) { unsigned long long a[32]; emu_gather(v, a); unsigned r = 0; for (int l = 0; l < 32; ++l) r = std::max(r, (unsigned)a[l]); return r; }
 inline int __syncthreads_or(int p) { static std::atomic<int> acc{0}; if (p) acc.store(1); __syncthreads(); const int r = acc.load(); __syncthreads(); if (threadIdx.x == 0) acc.store(0); __syncthreads(); return r; }
 
 template <class T> inline T __ldg(const T* p) { return *p; }
@@ -117,9 +119,12 @@ inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
 inline int __float2int_rn(float v) { return (int)lrintf(v); }
+inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
 using std::isfinite;
+using ::fmaxf;
 using std::min;
 using std::max;

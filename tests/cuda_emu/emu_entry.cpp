@@ -6,6 +6,8 @@
 #include "fast_strip_kernels.emu.cpp"
 #include "describe_warp_kernels.emu.cpp"
 #include "quadtree_kernels.emu.cpp"
+#include "depth_kernels.emu.cpp"
+#include "depth_dilate_v2.emu.cpp"
 #include "pose_kernels.emu.cpp"          // compiled with -DPOSE_MIXED_SOLVE=1: the float32 solve + refinement variant
 
 using namespace rgbl;
@@ -82,6 +84,21 @@ int emu_quadtree(const int32_t* xys, int n, int w, int h, int n_desired, int32_t
     if (status) return RGBL_E_CAPACITY;
     for (int i = 0; i < n_sel; ++i) { out_xys[3 * i] = sel[i].x; out_xys[3 * i + 1] = sel[i].y; out_xys[3 * i + 2] = sel[i].score; }
     return n_sel;
+}
+
+// ProjectPointcloudToImage + Upsample_InverseDilation: depth_project_kernel, then depth_resolve_dilate_kernel (v2 == 0) or
+// depth_resolve_dilate_v2_kernel.  pts: 4 x n planar (x | y | z | 1), mask ku x kv, outputs W x H floats.
+int emu_depth_dilate(const float* pts, int n, const float P[12], int W, int H, const uint8_t* mask, int ku, int kv, float min_d, float max_d,
+                     float inv_scale, int v2, float* raw_out, float* processed_out) {
+    DepthDev dd{};
+    std::memcpy(dd.P, P, 12 * sizeof(float));
+    dd.min_dist = min_d; dd.max_dist = max_d; dd.bf = 0; dd.inv_scale_m = max_d * inv_scale; dd.ku = ku; dd.kv = kv;
+    std::memcpy(dd.mask, mask, (size_t)ku * kv);
+    dd.method = RGBL_DEPTH_INVERSE_DILATION;
+    std::vector<uint32_t> idx((size_t)W * H, 0u);
+    launch_depth_project(nullptr, pts, 4 * n, &n, n, dd, W, H, idx.data(), 1u, 1);
+    (v2 ? launch_depth_resolve_dilate_v2 : launch_depth_resolve_dilate)(nullptr, pts, 4 * n, &n, dd, W, H, idx.data(), 1u, raw_out, processed_out, 1);
+    return 0;
 }
 
 // Optimizer::PoseOptimization on the emulated pose_optimize_kernel (one CTA of 512 threads); arguments as rgbl_pose_optimize.

@@ -136,3 +136,29 @@ print("default-ok")
     env = {k: v for k, v in os.environ.items() if k != "RGBL_QT_BLOCK_SORT"}
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "default-ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("v2", [0, 1])
+def test_depth_dilate_kernels_device_path(emu, v2):
+    """depth_project + depth_resolve_dilate (shipped, v2 = 0) and the variant with the empty-tile shortcut and shared-memory tap
+    offsets (v2 = 1) against the oracle's ProjectPointcloudToImage + Upsample_InverseDilation, bit for bit; the cloud covers
+    only the lower part of the image so that whole tiles are empty."""
+    W, H = 333, 150
+    P = S.lidar_projection_matrix().astype(np.float32)
+    pts = S.make_pointcloud(3, n_azimuth=500)
+    emu.emu_depth_dilate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float,
+                                     C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    # shift the projection so that the returns land inside this small image
+    P2 = P.copy(); P2[0, :] *= W / S.KITTI_W; P2[1, :] *= H / S.KITTI_H
+    for kind, k in (("diamond", 5), ("rectangle", 3), ("cross", 7)):
+        mask = S.structuring_element(kind, k)
+        raw_ref = oracle.depth_project(pts, P2, W, H)
+        ref = oracle.depth_inverse_dilation(raw_ref, mask)
+        p = np.ascontiguousarray(pts, np.float32)
+        raw = np.empty((H, W), np.float32); out = np.empty((H, W), np.float32)
+        m = np.ascontiguousarray(mask, np.uint8)
+        emu.emu_depth_dilate(L.ptr(p), p.shape[1], L.ptr(np.ascontiguousarray(P2.reshape(12))), W, H, L.ptr(m), m.shape[1], m.shape[0], 5.0, 200.0, 1.0,
+                             v2, L.ptr(raw), L.ptr(out))
+        assert (raw.view(np.uint32) == raw_ref.view(np.uint32)).all()
+        assert (out.view(np.uint32) == ref.view(np.uint32)).all(), kind
+        assert (raw_ref > 0).sum() > 200 and (raw_ref[: H // 4] > 0).sum() == 0

@@ -18,8 +18,9 @@ import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
     k = d["kernels"]
-    print("   value %.0f fps, e2e %.0f fps; fast %.3f ms, quadtree %.3f ms, describe %.3f ms per step" % (
-        d["value"], d["e2e"]["value"], k["fast"]["ms_per_step"], d["latency_bound_stages"]["quadtree"]["ms_per_step"], k["describe"]["ms_per_step"]))
+    print("   value %.0f fps, e2e %.0f fps; fast %.3f ms, quadtree %.3f ms, describe %.3f ms, dilate %.3f ms per step" % (
+        d["value"], d["e2e"]["value"], k["fast"]["ms_per_step"], d["latency_bound_stages"]["quadtree"]["ms_per_step"], k["describe"]["ms_per_step"],
+        k["depth_resolve_dilate"]["ms_per_step"]))
 except Exception as e:
     print("   no bench line:", e)
 PY
@@ -28,7 +29,8 @@ run baseline RGBL_NONE=0
 run fast_strips RGBL_FAST_STRIPS=1
 run describe_staged RGBL_DESCRIBE_STAGED=1
 run qt_block_sort RGBL_QT_BLOCK_SORT=1
-run all RGBL_FAST_STRIPS=1 RGBL_DESCRIBE_STAGED=1 RGBL_QT_BLOCK_SORT=1
+run dilate_v2 RGBL_DILATE_V2=1
+run all RGBL_FAST_STRIPS=1 RGBL_DESCRIBE_STAGED=1 RGBL_QT_BLOCK_SORT=1 RGBL_DILATE_V2=1
 # the LM variant is a compile-time switch: rebuild pose_kernels.o with it (one file, ~1 min), run the tracking tests, restore
 (
     cd orb_slam3_rgbl_b200/csrc || exit 1

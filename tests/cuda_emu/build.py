@@ -14,7 +14,7 @@ ROOT = HERE.parent.parent
 CSRC = ROOT / "orb_slam3_rgbl_b200" / "csrc"
 BUILD = HERE / "build"
 LIB = BUILD / "libcuda_emu.so"
-KERNEL_FILES = ["fast_strip_kernels.cu", "describe_warp_kernels.cu", "quadtree_kernels.cu", "pose_kernels.cu", "depth_kernels.cu", "depth_dilate_v2.cu"]
+KERNEL_FILES = ["orb_kernels.cu", "fast_strip_kernels.cu", "describe_warp_kernels.cu", "quadtree_kernels.cu", "pose_kernels.cu", "depth_kernels.cu", "depth_dilate_v2.cu"]
 HEADERS = ["fast_strip.cuh", "describe_warp.cuh", "quadtree_block.cuh", "rgbl_device.cuh", "rgbl_kernels.h", "rgbl_internal.h",
            "orb_pattern_31.inc"]
 HOST_FILES = ["host_tables.cpp", "quadtree_host.cpp"]

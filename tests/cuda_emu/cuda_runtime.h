@@ -25,13 +25,14 @@
 #define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static                 /* one CTA runs at a time */
 #define __constant__ static
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct float4 { float x, y, z, w; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 typedef int cudaError_t;
 typedef void* cudaStream_t;
 enum { cudaSuccess = 0 };

@@ -3,6 +3,7 @@
 // launchers (launch_fast_strips, launch_describe_staged, launch_quadtree) and therefore through the kernels' device branches.
 #include "cuda_runtime.h"
 
+#include "orb_kernels.emu.cpp"
 #include "fast_strip_kernels.emu.cpp"
 #include "describe_warp_kernels.emu.cpp"
 #include "quadtree_kernels.emu.cpp"
@@ -83,6 +84,64 @@ int emu_quadtree(const int32_t* xys, int n, int w, int h, int n_desired, int32_t
                         sel.data(), &n_sel, 1) != 0) return -100;
     if (status) return RGBL_E_CAPACITY;
     for (int i = 0; i < n_sel; ++i) { out_xys[3 * i] = sel[i].x; out_xys[3 * i + 1] = sel[i].y; out_xys[3 * i + 2] = sel[i].score; }
+    return n_sel;
+}
+
+// ORBextractor::operator() for one image through the device pipeline of api.cu's run_extract (device quad-tree mode):
+// pyramid -> FAST (per cell, or strips) -> compaction -> blur -> quad-tree -> describe (gathering, or staged).
+// variants: bit 0 = strip FAST, bit 1 = staged describe (the block-parallel quad-tree sort follows RGBL_QT_BLOCK_SORT).
+int emu_extract(const rgbl_orb_params* orb, const uint8_t* img, int width, int height, int stride, int variants, rgbl_keypoint* kps_out,
+                uint8_t* desc_out, int cap) {
+    OrbTables tab;
+    int rc = compute_orb_tables(*orb, tab);
+    if (rc) return rc;
+    std::vector<LevelGeom> levels; std::vector<CellInfo> cells; std::vector<LinCoef> coefs; size_t fb = 0; std::string err;
+    rc = build_geometry(width, height, tab, levels, cells, coefs, fb, err);
+    if (rc) return rc;
+    const int nl = tab.nlevels, n_cells = (int)cells.size();
+    std::vector<uint8_t> pyr(fb + 256, 0), blur(fb + 256, 0);
+    for (int y = 0; y < height; ++y) std::memcpy(&pyr[levels[0].off + (size_t)y * levels[0].pitch], img + (size_t)y * stride, width);
+    if (coefs.empty()) coefs.resize(1);
+    launch_pyramid(nullptr, pyr.data(), fb, levels.data(), nl, coefs.data(), 1);
+    std::vector<uint32_t> slots((size_t)n_cells * kCellCap);
+    std::vector<int> counts(n_cells, 0), cell_off(n_cells + 1, 0);
+    int level_cnt[RGBL_MAX_LEVELS] = {0}, frame_total = 0, overflow[4] = {0, 0, 0, 0};
+    if (variants & 1) {
+        std::vector<StripInfo> strips; int rows_cap = 0, list_cap = 0;
+        build_fast_strips(cells, 8, 264, strips, rows_cap, list_cap);
+        if (launch_fast_strips(nullptr, pyr.data(), fb, levels.data(), cells.data(), n_cells, strips.data(), (int)strips.size(), rows_cap, list_cap,
+                               orb->ini_th_fast, orb->min_th_fast, slots.data(), counts.data(), overflow, 1) != 0) return -100;
+    } else {
+        launch_fast(nullptr, pyr.data(), fb, levels.data(), cells.data(), n_cells, orb->ini_th_fast, orb->min_th_fast, slots.data(), counts.data(),
+                    overflow, 1);
+    }
+    const int dense_cap = std::max(32768, width * height / 8);
+    std::vector<uint32_t> dense(dense_cap + 8);
+    launch_compact(nullptr, levels.data(), nl, n_cells, slots.data(), counts.data(), cell_off.data(), level_cnt, &frame_total, dense.data(), dense_cap,
+                   overflow, 1);
+    if (overflow[0]) return RGBL_E_CAPACITY;
+    launch_blur(nullptr, pyr.data(), blur.data(), fb, levels.data(), nl, 1);
+    std::vector<int> region(nl + 1, 0);
+    for (int l = 0; l < nl; ++l) {
+        const LevelGeom& g = levels[l];
+        const int n_ini = (int)std::round(static_cast<float>(g.max_bx - g.min_bx) / (g.max_by - g.min_by));
+        region[l + 1] = region[l] + std::max(g.quota + 3, 4 * n_ini);
+    }
+    const int cap_kp = region[nl];
+    const int n = frame_total;
+    std::vector<int> pa(n + nl + 8), pb(n + nl + 8), na(n + nl + 8), nb(n + nl + 8);
+    std::vector<unsigned long long> scan(n + nl + 16);
+    std::vector<unsigned char> quad(n + nl + 8);
+    QtScratchDev scr{pa.data(), pb.data(), na.data(), nb.data(), scan.data(), quad.data()};
+    std::vector<uint32_t> sel_lvl(cap_kp + 8);
+    std::vector<SelKp> sel(cap_kp + 8);
+    int n_sel_lvl[RGBL_MAX_LEVELS] = {0}, status = 0, n_sel = 0;
+    if (launch_quadtree(nullptr, dense.data(), level_cnt, &frame_total, levels.data(), nl, scr, sel_lvl.data(), n_sel_lvl, region.data(), cap_kp,
+                        &status, sel.data(), &n_sel, 1) != 0) return -100;
+    if (status) return RGBL_E_CAPACITY;
+    if (n_sel > cap) return RGBL_E_CAPACITY;
+    ((variants & 2) ? launch_describe_staged : launch_describe)(nullptr, pyr.data(), blur.data(), fb, levels.data(), sel.data(), &n_sel, cap_kp, n_sel,
+                                                               tab.umax, kps_out, desc_out, 1);
     return n_sel;
 }
 

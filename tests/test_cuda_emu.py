@@ -162,3 +162,21 @@ def test_depth_dilate_kernels_device_path(emu, v2):
         assert (raw.view(np.uint32) == raw_ref.view(np.uint32)).all()
         assert (out.view(np.uint32) == ref.view(np.uint32)).all(), kind
         assert (raw_ref > 0).sum() > 200 and (raw_ref[: H // 4] > 0).sum() == 0
+
+
+@pytest.mark.parametrize("variants", [0, 3])
+def test_whole_extraction_pipeline_device_path(emu, variants):
+    """pyramid -> FAST -> compaction -> blur -> quad-tree -> describe through the real launchers on the emulator, shipped kernels
+    (variants = 0) and strip FAST + staged describe (variants = 3; the quad-tree runs its block-parallel sort in this process):
+    keypoints and descriptors equal the oracle's ORBextractor::operator() bit for bit."""
+    w, h = 260, 200
+    img = S.make_image(81, w, h)
+    prm = L.OrbParams(400, 1.2, 4, 12, 7)
+    ok, od, _ = oracle.Extractor(400, 1.2, 4, 12, 7)(img)
+    emu.emu_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    kps = np.empty(1024, oracle.KP_DTYPE); desc = np.empty((1024, 32), np.uint8)
+    n = emu.emu_extract(C.byref(prm), L.ptr(img), w, h, img.strides[0], variants, L.ptr(kps), L.ptr(desc), len(kps))
+    assert n == len(ok) > 150
+    for f in ok.dtype.names:
+        assert (kps[:n][f].view(np.uint32) == ok[f].view(np.uint32)).all(), f
+    assert (desc[:n] == od).all()

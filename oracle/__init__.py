@@ -500,6 +500,39 @@ def ref_orb_extract(img, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=12,
     return kps[:n.value].copy(), desc[:n.value].copy(), mono
 
 
+_REF_DEPTH = _HERE / "_ref" / "libref_depthmodule.so"
+_ref_depth = None
+
+
+def ref_depthmodule():
+    """-> ctypes handle of the reference's own DepthModule.cc build (oracle/ref_depthmodule_driver.cpp), or None."""
+    global _ref_depth
+    if _ref_depth is None:
+        if not _REF_DEPTH.exists() and Path("/root/reference/src/DepthModule.cc").exists():
+            subprocess.run(["make", "-C", str(_HERE), "ref"], check=True, stdout=subprocess.DEVNULL)
+        if not _REF_DEPTH.exists():
+            return None
+        L = C.CDLL(str(_REF_DEPTH))
+        L.ref_depth_from_pcd.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_depth_from_pcd.restype = C.c_int
+        _ref_depth = L
+    return _ref_depth
+
+
+def ref_depth_from_pcd(settings_path, pts4xn, W, H, kps_xy, kps_un_xy):
+    """DepthModule(settings).CalculateDepthFromPcd of the reference itself -> (P[3,4], raw, processed, mvDepth, mvuRight)."""
+    L = ref_depthmodule()
+    pts = np.ascontiguousarray(pts4xn, np.float32)
+    k = np.ascontiguousarray(kps_xy, np.float32).reshape(-1, 2); ku = np.ascontiguousarray(kps_un_xy, np.float32).reshape(-1, 2)
+    P = np.empty(12, np.float32); raw = np.empty((H, W), np.float32); proc = np.empty((H, W), np.float32)
+    d = np.empty(len(k), np.float32); u = np.empty(len(k), np.float32)
+    rc = L.ref_depth_from_pcd(str(settings_path).encode(), _p(pts), pts.shape[1], W, H, _p(k), _p(ku), len(k), _p(P), _p(raw), _p(proc), _p(d), _p(u))
+    if rc != 0:
+        raise RuntimeError(f"ref_depth_from_pcd failed: {rc}")
+    return P.reshape(3, 4), raw, proc, d, u
+
+
 def write_vocabulary_text(vocab: dict, path, k: int) -> None:
     """A flattened vocabulary (children stored in ascending node id order, ids breadth first) in the ORBvoc.txt format that
     TemplatedVocabulary::loadFromTextFile reads (TemplatedVocabulary.h:1330-1424): header `k L scoring weighting`

@@ -29,7 +29,7 @@ void resize(InputArray src_, OutputArray dst_, Size dsize, double, double, int) 
 
 static int reflect101(int p, int n) { if (p < 0) p = -p; if (p >= n) p = 2 * (n - 1) - p; return p; }
 
-void copyMakeBorder(InputArray src_, OutputArray dst_, int top, int bottom, int left, int right, int) {
+void copyMakeBorder(InputArray src_, OutputArray dst_, int top, int bottom, int left, int right, int, double) {
     Mat src = src_.getMat();
     dst_.create(src.rows + top + bottom, src.cols + left + right, src.type());
     Mat dst = dst_.getMat();

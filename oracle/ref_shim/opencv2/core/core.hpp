@@ -28,6 +28,7 @@
 
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_16U 2
 #define CV_32F 5
 #define CV_PI 3.1415926535897932384626433832795
 
@@ -64,8 +65,14 @@ public:
     Mat() : rows(0), cols(0), step(0), data(nullptr), type_(0) {}
     Mat(int r, int c, int type) : rows(0), cols(0), step(0), data(nullptr), type_(0) { create(r, c, type); }
     Mat(Size sz, int type) : rows(0), cols(0), step(0), data(nullptr), type_(0) { create(sz.height, sz.width, type); }
+    Mat(Size sz, int type, void* ext) : rows(sz.height), cols(sz.width), step(0), data((uchar*)ext), type_(type) { step = (size_t)cols * elemSize(); }   // user data, not owned
+    struct Expr;                                                 // result of an arithmetic expression (stand-in for cv::MatExpr)
+    Mat(const Expr& e);
+    Mat& operator=(const Expr& e);                               // evaluates INTO a matching allocation (row views!), like MatExpr assignment
+    Expr mul(const Mat& m) const;
+    void convertTo(Mat& dst, int type) const;
     int type() const { return type_; }
-    size_t elemSize() const { return type_ == CV_32F ? 4 : 1; }
+    size_t elemSize() const { return type_ == CV_32F ? 4 : (type_ == CV_16U ? 2 : 1); }
     size_t step1() const { return step / elemSize(); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     void release() { rows = cols = 0; step = 0; data = nullptr; buf_.reset(); }
@@ -76,6 +83,8 @@ public:
         data = buf_->data();
     }
     static Mat zeros(int r, int c, int type) { Mat m(r, c, type); return m; }
+    static Mat zeros(Size sz, int type) { Mat m(sz, type); return m; }
+    static Mat ones(int r, int c, int type);
     Mat clone() const { Mat m; if (!empty()) { m.create(rows, cols, type_); for (int y = 0; y < rows; ++y) memcpy(m.data + y * m.step, data + y * step, cols * elemSize()); } return m; }
     void copyTo(Mat dst) const { dst.create(rows, cols, type_); for (int y = 0; y < rows; ++y) memmove(dst.data + y * dst.step, data + y * step, cols * elemSize()); }
     Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
@@ -93,9 +102,26 @@ private:
     std::shared_ptr<std::vector<uchar> > buf_;
 };
 
+struct Mat::Expr { Mat m; };                                     // always an evaluated CV_32F (or source-typed) temporary
+inline Mat::Mat(const Expr& e) : rows(0), cols(0), step(0), data(nullptr), type_(0) { *this = e.m; }
+inline Mat& Mat::operator=(const Expr& e) {
+    if (data && rows == e.m.rows && cols == e.m.cols && type_ == e.m.type()) e.m.copyTo(*this);      // in place (e.g. M.row(0) = ...)
+    else *this = e.m;
+    return *this;
+}
+// arithmetic on CV_32F matrices; every operation is one float operation per element (what cv::arithm does for 32F), the matrix
+// product accumulates each dot product in double and rounds once (cv::gemm for CV_32F; pinned against cv2.gemm in the oracle tests)
+Mat::Expr operator*(const Mat& a, const Mat& b);
+Mat::Expr operator-(double s, const Mat& m);
+Mat::Expr operator/(double s, const Mat& m);
+Mat::Expr operator/(const Mat& m, double s);
+inline Mat::Expr operator/(double s, const Mat::Expr& e) { return s / e.m; }
+std::ostream& operator<<(std::ostream& os, const Mat& m);
+
 class _InputArray {
 public:
     _InputArray(const Mat& m) : m_(&m) {}
+    _InputArray(const Mat::Expr& e) : m_(&e.m) {}
     Mat getMat() const { return *m_; }
     bool empty() const { return m_->empty(); }
 private:
@@ -113,39 +139,65 @@ private:
 typedef const _InputArray& InputArray;
 typedef const _OutputArray& OutputArray;
 
-enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
+enum { BORDER_CONSTANT = 0, BORDER_REFLECT_101 = 4, BORDER_DEFAULT = 4, BORDER_ISOLATED = 16 };
 enum { INTER_LINEAR = 1 };
+enum { MORPH_RECT = 0, MORPH_CROSS = 1, MORPH_ELLIPSE = 2 };
+enum { THRESH_BINARY = 0, THRESH_BINARY_INV = 1, THRESH_TOZERO_INV = 4 };
+enum { DIST_L2 = 2, DIST_MASK_5 = 5 };
 
 // primitives: declared here, defined in oracle/ref_orbextractor_driver.cpp on the oracle's restatements
 void resize(InputArray src, OutputArray dst, Size dsize, double fx = 0, double fy = 0, int interpolation = INTER_LINEAR);
-void copyMakeBorder(InputArray src, OutputArray dst, int top, int bottom, int left, int right, int borderType);
+void copyMakeBorder(InputArray src, OutputArray dst, int top, int bottom, int left, int right, int borderType, double value = 0);
+double threshold(InputArray src, OutputArray dst, double thresh, double maxval, int type);
+void dilate(InputArray src, OutputArray dst, InputArray kernel, Point anchor = Point(-1, -1), int iterations = 1);
+Mat getStructuringElement(int shape, Size ksize);
+void filter2D(InputArray src, OutputArray dst, int ddepth, InputArray kernel, Point anchor = Point(-1, -1), double delta = 0, int borderType = BORDER_DEFAULT);
+void distanceTransform(InputArray src, OutputArray dst, OutputArray labels, int distanceType, int maskSize);
+void minMaxLoc(InputArray src, double* minVal, double* maxVal);
 void GaussianBlur(InputArray src, OutputArray dst, Size ksize, double sigmaX, double sigmaY = 0, int borderType = BORDER_REFLECT_101);
 void FAST(InputArray image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmaxSuppression = true);
 float fastAtan2(float y, float x);
 struct KeyPointsFilter { static void retainBest(std::vector<KeyPoint>& keypoints, int npoints); };     // only in the unused ComputeKeyPointsOld
 
+// cv::FileStorage stand-in: reads a plain text file of `key value` lines (what the tests write instead of a YAML settings file),
+// so that the reference's own parameter parsing runs (DepthModule::ParseRGBLParameters / ParseUpsamplingParameters).
 class FileNode {
 public:
     enum { NONE = 0, SEQ = 4, MAP = 5 };
+    FileNode() : has_(false) {}
+    explicit FileNode(const std::string& v) : has_(true), v_(v) {}
+    bool empty() const { return !has_; }
+    bool isReal() const { if (!has_) return false; char* e = nullptr; strtod(v_.c_str(), &e); return e && *e == 0 && !v_.empty(); }
+    double real() const { return has_ ? strtod(v_.c_str(), nullptr) : 0.0; }
     FileNode operator[](const char*) const { return FileNode(); }
     FileNode operator[](const std::string&) const { return FileNode(); }
     FileNode operator[](int) const { return FileNode(); }
     int type() const { return NONE; }
     size_t size() const { return 0; }
-    operator int() const { return 0; }
-    operator double() const { return 0.0; }
-    operator std::string() const { return std::string(); }
+    operator int() const { return (int)real(); }
+    operator float() const { return (float)real(); }
+    operator double() const { return real(); }
+    operator std::string() const { return v_; }
+private:
+    bool has_; std::string v_;
 };
 
 class FileStorage {
 public:
     enum { READ = 0, WRITE = 1 };
     FileStorage() {}
-    FileStorage(const std::string&, int) {}
-    bool isOpened() const { return false; }
+    FileStorage(const std::string& path, int mode) {
+        if (mode != READ) return;
+        std::ifstream f(path.c_str());
+        std::string k, v;
+        while (f >> k >> v) { keys_.push_back(k); vals_.push_back(v); }
+    }
+    bool isOpened() const { return !keys_.empty(); }
     void release() {}
-    FileNode operator[](const char*) const { return FileNode(); }
-    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](const std::string& k) const { for (size_t i = 0; i < keys_.size(); ++i) if (keys_[i] == k) return FileNode(vals_[i]); return FileNode(); }
+    FileNode operator[](const char* k) const { return (*this)[std::string(k)]; }
+private:
+    std::vector<std::string> keys_, vals_;
 };
 template <class T> inline FileStorage& operator<<(FileStorage& fs, const T&) { return fs; }
 

@@ -243,3 +243,38 @@ def test_orb_tables_equal_the_reference_constructor():
         assert L.ref_orb_tables(nf, sf, nl, O._p(a), O._p(b), O._p(c), O._p(d)) == nl
         ex = O.Extractor(nf, sf, nl)
         assert (ex.scale_factors.view(np.uint32) == a.view(np.uint32)).all() and (ex.inv_scale_factors.view(np.uint32) == b.view(np.uint32)).all()
+
+
+# ---- the DepthModule oracle against the reference's own DepthModule.cc (oracle/_ref/libref_depthmodule.so) ------------------
+@pytest.mark.parametrize("kind,k,seed", [("Diamond", 5, 0), ("Rectangle", 3, 1), ("Cross", 7, 2), ("Ellipse", 5, 3), ("Diamond", 9, 4)])
+def test_depth_oracle_equals_the_reference_depthmodule(tmp_path, kind, k, seed):
+    """The reference parses the settings itself (projection matrix K [R|t], limits, method, structuring element), projects the
+    cloud, runs Upsample_InverseDilation and GetFeatureDepthFromDepthMap; oracle.depth_from_pcd gets the reference's 12 projection
+    floats and must return the same RawDepthMap, ProcessedDepthMap, mvDepth and mvuRight bit for bit."""
+    import oracle as O
+    from orb_slam3_rgbl_b200 import synthetic as S
+    if O.ref_depthmodule() is None:
+        pytest.skip("oracle/_ref/libref_depthmodule.so is not built and /root/reference is not available")
+    K, Tr = S.camera_matrix(), S.KITTI_TR
+    lines = [f"Camera.fx {float(K[0, 0])!r}", f"Camera.fy {float(K[1, 1])!r}", f"Camera.cx {float(K[0, 2])!r}", f"Camera.cy {float(K[1, 2])!r}",
+             f"Camera.bf {float(S.KITTI_BF)!r}", "LiDAR.min_dist 5.0", "LiDAR.max_dist 200.0", "LiDAR.Method InverseDilation",
+             f"LiDAR.MethodInverseDilation.KernelType {kind}", f"LiDAR.MethodInverseDilation.KernelSize_u {k}.0",
+             f"LiDAR.MethodInverseDilation.KernelSize_v {k}.0"]
+    lines += [f"LiDAR.Tr{r + 1}{c + 1} {float(Tr[r, c])!r}" for r in range(3) for c in range(4)]
+    path = tmp_path / "settings.txt"; path.write_text("\n".join(lines) + "\n")
+    W, H = S.KITTI_W, S.KITTI_H
+    pts = S.make_pointcloud(10 + seed, n_azimuth=700)
+    rng = np.random.default_rng(seed)
+    kp = np.zeros(600, O.KP_DTYPE); kp["x"] = rng.integers(0, W, 600); kp["y"] = rng.integers(0, H, 600)
+    ku = kp.copy(); ku["x"] += rng.normal(0, 0.3, 600).astype(np.float32)
+    P, raw, proc, d, u = O.ref_depth_from_pcd(path, pts, W, H, np.stack([kp["x"], kp["y"]], 1), np.stack([ku["x"], ku["y"]], 1))
+    # ParseRGBLParameters stores K and Tr as float32 and multiplies them with cv::gemm (double accumulation, one rounding)
+    K4 = np.zeros((3, 4), np.float32); K4[:, :3] = K.astype(np.float32)
+    T4 = np.vstack([Tr.astype(np.float32), np.array([[0, 0, 0, 1]], np.float32)])
+    assert (P.view(np.uint32) == (K4.astype(np.float64) @ T4.astype(np.float64)).astype(np.float32).view(np.uint32)).all()
+    od, ou, oraw, oproc = O.depth_from_pcd(pts, P, W, H, S.structuring_element(kind.lower(), k), S.KITTI_BF, kp, ku)
+    assert (raw > 0).sum() > 3000
+    assert (oraw.view(np.uint32) == raw.view(np.uint32)).all()
+    assert (oproc.view(np.uint32) == proc.view(np.uint32)).all()
+    assert (od.view(np.uint32) == d.view(np.uint32)).all() and (ou.view(np.uint32) == u.view(np.uint32)).all()
+    assert (d > 0).sum() > 50

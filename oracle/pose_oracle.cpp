@@ -171,7 +171,7 @@ struct LM {
         double current = active_robust_chi2(), temp = current;
         const double ini = current;
         double H[6][6], b[6];
-#ifdef ORC_POSE_STUDY      // tools/pose_precision_study.cpp only (alternative arithmetic for the normal equations); never set for liborb_oracle.so
+#ifdef ORC_POSE_STUDY      // tests/tools/pose_precision_study.cpp only (alternative arithmetic for the normal equations); never set for liborb_oracle.so
         study_build_system(*this, H, b);
 #else
         build_system(H, b);

@@ -177,7 +177,7 @@ __device__ __forceinline__ bool solve6(const double* Hsym /*21 upper*/, double l
 // Candidate for the next round (NOT the default, not yet run on a GPU): the same system solved by an unpivoted LDL^T in
 // float32 plus ONE step of iterative refinement with the residual formed in float64.  The serial solve is bound by the
 // latency of dependent operations, and a dependent float32 operation costs ~4 cycles against ~30 for float64; the
-// refinement step restores the accuracy ((cond * 2^-24)^2 relative).  tools/pose_precision_study.cpp: on 300 synthetic
+// refinement step restores the accuracy ((cond * 2^-24)^2 relative).  tests/tools/pose_precision_study.cpp: on 300 synthetic
 // tracking problems the float32 poses PoseOptimization returns are bit-identical to the float64 solve's in all 300 and no
 // outlier flag changes (without the refinement step 225 of 300 poses change, by up to 1.4e-5 m).
 __device__ __forceinline__ bool solve6_mixed(const double* Hsym /*21 upper*/, double lambda, const double* b, double* x) {

@@ -1,14 +1,14 @@
 """Race check of the emulated kernels (tests/cuda_emu) under ThreadSanitizer: every conflicting pair of accesses that is not
 separated by a barrier / warp rendezvous is reported, whatever the timing.  Usage:
-    bash tools/emu_race_check.sh
+    bash tests/tools/emu_race_check.sh
 (builds tests/cuda_emu/build/libcuda_emu_tsan.so and runs this file under LD_PRELOAD=libtsan for: the extraction pipeline with
 the shipped kernels, with every prepared variant, and the dilation variant)."""
 import ctypes as C, os, sys, numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 os.environ["RGBL_QT_BLOCK_SORT"]="1"
 import oracle
 from orb_slam3_rgbl_b200 import _lib as L, synthetic as S
-lib=C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests/cuda_emu/build/libcuda_emu_tsan.so'))
+lib=C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'tests/cuda_emu/build/libcuda_emu_tsan.so'))
 which=sys.argv[1]
 if which=='extract':
     w,h=200,160; img=S.make_image(81,w,h); prm=L.OrbParams(200,1.2,3,12,7)

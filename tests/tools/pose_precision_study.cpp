@@ -1,14 +1,14 @@
 // Numerical study (CPU, test tooling): how far does PoseOptimization move when the per-edge Jacobian / normal-equation products
 // are formed in float32 (sums in float64), and when the 6x6 solve runs in float32 with iterative refinement?  The chi2 /
 // error evaluation that decides LM acceptance and the outlier flags stays in float64 in every variant.
-//   g++ -O2 -std=c++17 -ffp-contract=off -o /tmp/pose_study tools/pose_precision_study.cpp && /tmp/pose_study [problems]
+//   g++ -O2 -std=c++17 -ffp-contract=off -o /tmp/pose_study tests/tools/pose_precision_study.cpp && /tmp/pose_study [problems]
 // Reference arithmetic = oracle/pose_oracle.cpp (restatement of g2o's LM, src/Optimizer.cc:814-1114).
 #define ORC_POSE_STUDY 1
 #include <cstdio>
 #include <cstdlib>
 #include <random>
 
-#include "../oracle/pose_oracle.cpp"
+#include "../../oracle/pose_oracle.cpp"
 
 namespace {
 

@@ -40,6 +40,10 @@ def test_product_never_imports_oracle():
         if p.suffix in (".py", ".cu", ".cpp", ".h", ".cuh") and p.is_file():
             txt = p.read_text(errors="ignore")
             assert "import oracle" not in txt and "liborb_oracle" not in txt and "oracle/" not in txt, p
+    for p in (ROOT / "tools").rglob("*"):              # development tools that need the oracle live under tests/tools
+        if p.is_file() and p.suffix in (".py", ".sh", ".cpp"):
+            txt = p.read_text(errors="ignore")
+            assert "import oracle" not in txt and "liborb_oracle" not in txt and "_oracle.cpp" not in txt, p
 
 
 @pytest.mark.parametrize("nf,sf,nl", [(2000, 1.2, 8), (1000, 1.2, 8), (4000, 1.2, 8), (1200, 1.5, 5), (500, 1.1, 12)])

@@ -1,7 +1,7 @@
 """Stage-by-stage GPU-vs-oracle diagnostic (development aid; run under gpurun)."""
 import sys
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 import numpy as np
 import oracle
 from orb_slam3_rgbl_b200 import frontend as F, synthetic as S

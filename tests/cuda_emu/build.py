@@ -21,7 +21,7 @@ HOST_FILES = ["host_tables.cpp", "quadtree_host.cpp"]
 
 
 def _transform(text: str) -> str:
-    text = re.sub(r"extern __shared__ __align__\(16\) (\w+(?: \w+)?) (\w+)\[\];", r"alignas(16) static \1 \2[emu::kDynSmem];", text)
+    text = re.sub(r"extern __shared__ (?:__align__\(16\) )?(\w+(?: \w+)*) (\w+)\[\];", r"alignas(16) static \1 \2[emu::kDynSmem / sizeof(\1)];", text)
     text = re.sub(r"(\w+)<<<(.+?)>>>\((.*?)\);", r"emu::run(emu::cfg(\2), [&]() { \1(\3); });", text, flags=re.S)
     # the two approximate FP64 MUFU seeds of the LM kernel (results have 32 zero low mantissa bits, PTX ISA "rcp.approx.ftz.f64")
     text = re.sub(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;" : "=d"\((\w+)\) : "d"\((\w+)\)\);', r"\1 = emu::approx64(1.0 / \2);", text)
@@ -46,5 +46,51 @@ def build(force: bool = False) -> Path:
     return LIB
 
 
+FULL_LIB = BUILD / "librgbl_b200_emu.so"
+FULL_SRCS = ["api.cu", "api_track.cu", "quadtree_kernels.cu", "orb_kernels.cu", "fast_strip_kernels.cu", "describe_warp_kernels.cu", "depth_kernels.cu",
+             "depth_dilate_v2.cu", "stereo_kernels.cu", "match_kernels.cu", "bow_kernels.cu", "api_bow.cu", "api_ba.cu", "api_mapping.cu", "pose_kernels.cu",
+             "quadtree_host.cpp", "host_tables.cpp"]
+
+
+def build_full(force: bool = False, defines=()) -> Path:
+    """The WHOLE library (every .cu / .cpp of csrc/Makefile) against the shim: build/librgbl_b200_emu.so exports the C ABI of
+    include/rgbl_b200.h, so the -m gpu parity tests can run on the CPU (RGBL_LIB_PATH, see orb_slam3_rgbl_b200/_lib.py)."""
+    from concurrent.futures import ThreadPoolExecutor
+    hdrs = [f.name for f in CSRC.iterdir() if f.suffix in (".h", ".cuh", ".inc")]
+    srcs = [CSRC / f for f in FULL_SRCS + hdrs] + [HERE / "cuda_runtime.h", HERE / "emu_runtime.cpp", Path(__file__)]
+    if FULL_LIB.exists() and not force and all(FULL_LIB.stat().st_mtime > s.stat().st_mtime for s in srcs):
+        return FULL_LIB
+    full = BUILD / "full"
+    if full.exists():
+        shutil.rmtree(full)
+    full.mkdir(parents=True)
+    for f in FULL_SRCS + hdrs:
+        out = full / ((f[:-3] + ".emu.cpp") if f.endswith(".cu") else f)
+        out.write_text(_transform((CSRC / f).read_text()))
+    import os
+    san = ["-fsanitize=" + os.environ["EMU_SANITIZE"]] if os.environ.get("EMU_SANITIZE") else []      # address | thread (debugging aid)
+    flags = ["-std=c++20", "-O1", "-g", "-pthread", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes", f"-I{HERE}", f"-I{full}",
+             "-include", str(HERE / "cuda_runtime.h")] + list(defines) + san       # the shim first: __CUDA_ARCH__ must be set before any header
+    units = [full / ((f[:-3] + ".emu.cpp") if f.endswith(".cu") else f) for f in FULL_SRCS] + [HERE / "emu_runtime.cpp"]
+
+    def cc(u):
+        o = full / (u.name + ".o")
+        r = subprocess.run(["g++", *flags, "-c", "-o", str(o), str(u)], capture_output=True, text=True)
+        if r.returncode:
+            return RuntimeError(f"{u.name}:\n" + "\n".join(l for l in r.stderr.splitlines() if "error" in l)[:2500])
+        return o
+    with ThreadPoolExecutor(8) as ex:
+        objs = list(ex.map(cc, units))
+    errs = [o for o in objs if isinstance(o, Exception)]
+    if errs:
+        raise RuntimeError("\n".join(str(e) for e in errs))
+    subprocess.run(["g++", "-shared", "-pthread", *san, "-o", str(FULL_LIB), *map(str, objs)], check=True)
+    return FULL_LIB
+
+
 if __name__ == "__main__":
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "full":
+        print(build_full(force=True))
+        sys.exit(0)
     print(build(force=True))

@@ -91,11 +91,22 @@ inline unsigned __ballot_sync(unsigned, int pred) { unsigned long long a[32]; em
 inline int __reduce_add_sync(unsigned, int v) { unsigned long long a[32]; emu_gather((unsigned long long)(long long)v, a); int s = 0; for (int l = 0; l < 32; ++l) s += (int)(long long)a[l]; return s; }
 inline unsigned __reduce_min_sync(unsigned, unsigned v) { unsigned long long a[32]; emu_gather(v, a); unsigned r = 0xffffffffu; for (int l = 0; l < 32; ++l) r = std::min(r, (unsigned)a[l]); return r; }
 inline unsigned __reduce_max_sync(unsigned, unsigned v) { unsigned long long a[32]; emu_gather(v, a); unsigned r = 0; for (int l = 0; l < 32; ++l) r = std::max(r, (unsigned)a[l]); return r; }
+inline int __any_sync(unsigned, int pred) { return __ballot_sync(0xffffffffu, pred) != 0; }
+inline int __all_sync(unsigned, int pred) { return __ballot_sync(0xffffffffu, pred) == 0xffffffffu; }
+inline unsigned __match_any_sync(unsigned, int v) { unsigned long long a[32]; emu_gather((unsigned long long)(unsigned)v, a); unsigned r = 0; for (int l = 0; l < 32; ++l) if ((unsigned)a[l] == (unsigned)v) r |= 1u << l; return r; }
+inline int __syncthreads_count(int p) { static std::atomic<int> acc{0}; if (p) acc.fetch_add(1); __syncthreads(); const int r = acc.load(); __syncthreads(); if (threadIdx.x == 0) acc.store(0); __syncthreads(); return r; }
 inline int __syncthreads_or(int p) { static std::atomic<int> acc{0}; if (p) acc.store(1); __syncthreads(); const int r = acc.load(); __syncthreads(); if (threadIdx.x == 0) acc.store(0); __syncthreads(); return r; }
 
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicMin(int* p, int v) { int o = __atomic_load_n(p, __ATOMIC_RELAXED); while (o > v && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+inline int atomicMax(int* p, int v) { int o = __atomic_load_n(p, __ATOMIC_RELAXED); while (o < v && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline float atomicAdd(float* p, float v) { float o = *p, n; do { n = o + v; } while (!__atomic_compare_exchange(p, &o, &n, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)); return o; }
+inline double atomicAdd(double* p, double v) { double o = *p, n; do { n = o + v; } while (!__atomic_compare_exchange(p, &o, &n, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)); return o; }
+inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = __atomic_load_n(p, __ATOMIC_RELAXED); while (o < v && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} return o; }
@@ -119,6 +130,16 @@ inline float __fdiv_rn(float a, float b) { return a / b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+inline int __float2int_rd(float v) { return (int)floorf(v); }
+inline int __float2int_rz(float v) { return (int)v; }
+inline int __double2int_rn(double v) { return (int)lrint(v); }
+inline float __int2float_rn(int v) { return (float)v; }
+inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i); return r; }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __float2int_rn(float v) { return (int)lrintf(v); }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
@@ -129,3 +150,48 @@ using std::isfinite;
 using ::fmaxf;
 using std::min;
 using std::max;
+
+// ---- host-side runtime API: everything is synchronous (a launch returns when the grid has run), memory is host memory ----------
+typedef struct EmuEvent { double t; }* cudaEvent_t;
+typedef void* cudaGraph_t;
+typedef void* cudaGraphExec_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+enum cudaStreamCaptureMode { cudaStreamCaptureModeRelaxed = 2 };
+enum { cudaErrorNotSupported = 801 };
+inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = -1; return cudaSuccess; }
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)calloc(n + 256, 1); return *p ? cudaSuccess : 2; }
+template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)calloc(n + 256, 1); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = nullptr) {
+    for (size_t y = 0; y < h; ++y) memmove((char*)d + y * dp, (const char*)s + y * sp, w);
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = malloc(8); return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = malloc(8); return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+inline double emu_now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new EmuEvent{0}; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new EmuEvent{0}; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = emu_now_ms(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }
+// CUDA graphs are not emulated: capture is refused (the library replays the chain launch by launch when RGBL_CHAIN_GRAPH=0)
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t, unsigned long long = 0) { *e = nullptr; return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t, void*, void*, size_t) { *e = nullptr; return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }

@@ -5,6 +5,8 @@ thread_local uint3 threadIdx;
 uint3 blockIdx;
 dim3 blockDim, gridDim;
 namespace emu {
+// CUDA graphs are not emulated (cuda_runtime.h): make the library replay its tracking chain launch by launch
+static const int g_no_graphs = setenv("RGBL_CHAIN_GRAPH", "0", 1);
 Cta* g_cta = nullptr;
 thread_local int t_warp = 0, t_lane = 0;
 

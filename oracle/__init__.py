@@ -35,8 +35,13 @@ def build(force: bool = False) -> Path:
 _lib = None
 
 
+_lib_override = None          # set by reference_tracking(): the wrappers below then call the reference's own code
+
+
 def lib() -> C.CDLL:
     global _lib
+    if _lib_override is not None:
+        return _lib_override
     if _lib is None:
         if not _LIB_PATH.exists() or os.environ.get("ORACLE_REBUILD"):
             build()
@@ -612,3 +617,88 @@ def fuse_search(kf: FrameView, Tcw, Ow, valid, xw, normal, mf_min_dist, mf_max_d
     bi = np.empty(max(n, 1), np.int32); bd = np.empty(max(n, 1), np.int32)
     lib().orc_fuse_search(C.byref(kf.c), _p(Tcw), _p(Ow), n, _p(valid), _p(xw), _p(normal), _p(mn), _p(mx), _p(d), th, _p(bi), _p(bd))
     return bi[:n], bd[:n]
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's own tracking code (oracle/ref_tracking_driver.cpp -> _ref/libref_tracking.so): src/ORBmatcher.cc,
+# Optimizer::PoseOptimization over the reference's g2o, Frame::isInFrustum / GetFeaturesInArea / ComputeStereoMatches ...,
+# behind the same argument lists as the orc_* restatements.
+# ------------------------------------------------------------------------------------------------
+_REF_TRACK = _HERE / "_ref" / "libref_tracking.so"
+_ref_track = None
+_REF_TRACK_MIRRORED = ("descriptor_distance", "features_in_area", "search_by_projection_last", "is_in_frustum", "search_by_projection_local",
+                       "search_by_bow", "search_by_projection_reloc", "pose_optimize", "stereo_matches", "distinctive_descriptors")
+
+
+class _RefProxy:
+    """Resolves orc_<name> to ref_<name> of libref_tracking.so (same C signatures)."""
+
+    def __init__(self, L, fallback):
+        self._L = L
+        self._fallback = fallback
+
+    def __getattr__(self, name):
+        if not name.startswith("orc_"):
+            raise AttributeError(name)
+        if name[4:] in _REF_TRACK_MIRRORED:
+            return getattr(self._L, "ref_" + name[4:])
+        return getattr(self._fallback, name)            # helpers the reference library has no twin of (e.g. pyramid accessors)
+
+
+def ref_tracking():
+    """-> proxy of the reference's own matcher / pose / stereo code, or None when it is neither prebuilt nor buildable."""
+    global _ref_track
+    if _ref_track is None:
+        if not _REF_TRACK.exists() and Path("/root/reference/src/ORBmatcher.cc").exists():
+            subprocess.run(["make", "-C", str(_HERE), "-j8", "ref"], check=True, stdout=subprocess.DEVNULL)
+        if not _REF_TRACK.exists():
+            return None
+        o = lib(); _late(o)
+        L = C.CDLL(str(_REF_TRACK))
+        for name in _REF_TRACK_MIRRORED:
+            src, dst = getattr(o, "orc_" + name), getattr(L, "ref_" + name)
+            dst.argtypes = src.argtypes; dst.restype = src.restype
+        vp, i, f = C.c_void_p, C.c_int, C.c_float
+        L.ref_stereo_from_rgbd.argtypes = [i, vp, vp, vp, i, i, f, vp, vp]; L.ref_stereo_from_rgbd.restype = None
+        L.ref_unproject_stereo.argtypes = [vp, i, vp, vp, f, f, f, f, vp, vp]; L.ref_unproject_stereo.restype = None
+        _ref_track = _RefProxy(L, o)
+    return _ref_track
+
+
+class reference_tracking:
+    """with oracle.reference_tracking(): oracle.search_by_projection_last(...) etc. run the REFERENCE's code instead of the
+    restatement (same Python signatures, same arrays)."""
+
+    def __enter__(self):
+        global _lib_override
+        r = ref_tracking()
+        if r is None:
+            raise RuntimeError("oracle/_ref/libref_tracking.so is not available")
+        _late(lib())
+        _lib_override = r
+        return r
+
+    def __exit__(self, *exc):
+        global _lib_override
+        _lib_override = None
+        return False
+
+
+def ref_stereo_from_rgbd(kp_xy, kp_un_xy, depth_map, mbf):
+    """Frame::ComputeStereoFromRGBD of the reference itself -> (mvDepth, mvuRight)."""
+    L = ref_tracking()._L
+    k = np.ascontiguousarray(kp_xy, np.float32).reshape(-1, 2); ku = np.ascontiguousarray(kp_un_xy, np.float32).reshape(-1, 2)
+    dm = np.ascontiguousarray(depth_map, np.float32)
+    d = np.empty(len(k), np.float32); u = np.empty(len(k), np.float32)
+    L.ref_stereo_from_rgbd(len(k), _p(k), _p(ku), _p(dm), dm.shape[1], dm.shape[0], mbf, _p(d), _p(u))
+    return d, u
+
+
+def ref_unproject_stereo(pose, kp_un_xy, depth, fx, fy, cx, cy):
+    """Frame::UnprojectStereo of the reference itself for every keypoint -> (x3D[n,3], ok[n])."""
+    L = ref_tracking()._L
+    pose = np.ascontiguousarray(pose, np.float32); ku = np.ascontiguousarray(kp_un_xy, np.float32).reshape(-1, 2)
+    depth = np.ascontiguousarray(depth, np.float32)
+    x = np.empty((len(ku), 3), np.float32); ok = np.empty(len(ku), np.uint8)
+    L.ref_unproject_stereo(_p(pose), len(ku), _p(ku), _p(depth), fx, fy, cx, cy, _p(x), _p(ok))
+    return x, ok.astype(bool)

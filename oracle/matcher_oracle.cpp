@@ -98,9 +98,20 @@ inline void transform(const Pose& T, const float p[3], float out[3]) {
     rotate(T, p, r);
     out[0] = r[0] + T.tx; out[1] = r[1] + T.ty; out[2] = r[2] + T.tz;
 }
-// Tcw.inverse().translation() = so3().inverse() * (translation() * -1)   (se3.hpp inverse())
-inline void inverse_translation(const Pose& T, float out[3]) {
+// Eigen 3.3 (Ubuntu 20.04's libeigen3-dev, the reference's Dockerfile) adds the terms of a fixed-size dot product / squared norm /
+// matrix-product coefficient with its unrolled scalar reduction (Core/Redux.h redux_novec_unroller: halves, recursively):
+inline float sum3(float a, float b, float c) { return a + (b + c); }
+inline float sum4(float a, float b, float c, float d) { return (a + b) + (c + d); }
+// SO3f::inverse() = SO3f(unit_quaternion().conjugate()): the quaternion constructor normalises (so3.hpp:229-231, 481-487, 297-303)
+inline Pose inverse_rotation(const Pose& T) {
     Pose inv = T; inv.qx = -T.qx; inv.qy = -T.qy; inv.qz = -T.qz;
+    const float length = std::sqrt(sum4(inv.qx * inv.qx, inv.qy * inv.qy, inv.qz * inv.qz, inv.qw * inv.qw));
+    inv.qx /= length; inv.qy /= length; inv.qz /= length; inv.qw /= length;
+    return inv;
+}
+// Tcw.inverse().translation() = invR * (translation() * -1)   (se3.hpp:208-211)
+inline void inverse_translation(const Pose& T, float out[3]) {
+    const Pose inv = inverse_rotation(T);
     const float nt[3] = {T.tx * -1.f, T.ty * -1.f, T.tz * -1.f};
     rotate(inv, nt, out);
 }
@@ -238,8 +249,8 @@ void orc_is_in_frustum(const orc_frame_view* fv, const float* Rcw, const float* 
         in_view[i] = 0; px[i] = -1; py[i] = -1; pxr[i] = 0; depth[i] = 0; level[i] = 0; view_cos[i] = 0;
         const float* P = xw + 3 * i;
         float Pc[3];
-        for (int r = 0; r < 3; ++r) Pc[r] = ((Rcw[3 * r] * P[0] + Rcw[3 * r + 1] * P[1]) + Rcw[3 * r + 2] * P[2]) + tcw[r];
-        const float pc_dist = std::sqrt((Pc[0] * Pc[0] + Pc[1] * Pc[1]) + Pc[2] * Pc[2]);
+        for (int r = 0; r < 3; ++r) Pc[r] = sum3(Rcw[3 * r] * P[0], Rcw[3 * r + 1] * P[1], Rcw[3 * r + 2] * P[2]) + tcw[r];     // mRcw * P + mtcw
+        const float pc_dist = std::sqrt(sum3(Pc[0] * Pc[0], Pc[1] * Pc[1], Pc[2] * Pc[2]));
         const float z = Pc[2];
         const float invz = 1.0f / z;
         if (z < 0.0f) continue;
@@ -248,11 +259,11 @@ void orc_is_in_frustum(const orc_frame_view* fv, const float* Rcw, const float* 
         if (v < F.min_y || v > F.max_y) continue;
         px[i] = u; py[i] = v;
         const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
-        const float dist = std::sqrt((PO[0] * PO[0] + PO[1] * PO[1]) + PO[2] * PO[2]);
+        const float dist = std::sqrt(sum3(PO[0] * PO[0], PO[1] * PO[1], PO[2] * PO[2]));
         // GetMin/MaxDistanceInvariance: 0.8f*mfMinDistance, 1.2f*mfMaxDistance (src/MapPoint.cc:502-512)
         if (dist < 0.8f * mf_min_dist[i] || dist > 1.2f * mf_max_dist[i]) continue;
         const float* Pn = normal + 3 * i;
-        const float vc = ((PO[0] * Pn[0] + PO[1] * Pn[1]) + PO[2] * Pn[2]) / dist;
+        const float vc = sum3(PO[0] * Pn[0], PO[1] * Pn[1], PO[2] * Pn[2]) / dist;
         if (vc < cos_limit) continue;
         const float mf_max = mf_max_dist[i];      // MapPoint::PredictScale uses mfMaxDistance itself (src/MapPoint.cc:531-545)
         const float ratio = mf_max / dist;
@@ -393,10 +404,10 @@ void orc_fuse_search(const orc_frame_view* kf, const float Tcw_[7], const float 
         const float ur = u - F.bf * invz;
         const float max_d = 1.2f * mf_max_dist[i], min_d = 0.8f * mf_min_dist[i];           // Get{Max,Min}DistanceInvariance
         const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
-        const float dist3D = std::sqrt((PO[0] * PO[0] + PO[1] * PO[1]) + PO[2] * PO[2]);
+        const float dist3D = std::sqrt(sum3(PO[0] * PO[0], PO[1] * PO[1], PO[2] * PO[2]));
         if (dist3D < min_d || dist3D > max_d) continue;
         const float* Pn = normal + 3 * i;
-        if (((PO[0] * Pn[0] + PO[1] * Pn[1]) + PO[2] * Pn[2]) < 0.5 * dist3D) continue;
+        if (sum3(PO[0] * Pn[0], PO[1] * Pn[1], PO[2] * Pn[2]) < 0.5 * dist3D) continue;
         const float ratio = mf_max_dist[i] / dist3D;                                        // MapPoint::PredictScale(dist, KeyFrame*)
         int level = (int)std::ceil(std::log(ratio) / F.log_scale_factor);
         if (level < 0) level = 0; else if (level >= F.n_levels) level = F.n_levels - 1;
@@ -451,7 +462,7 @@ int orc_search_by_projection_reloc(const orc_frame_view* cur, const float cur_po
         if (u < F.min_x || u > F.max_x) continue;
         if (v < F.min_y || v > F.max_y) continue;
         const float PO[3] = {xw[3 * i] - Ow[0], xw[3 * i + 1] - Ow[1], xw[3 * i + 2] - Ow[2]};
-        const float dist3D = std::sqrt((PO[0] * PO[0] + PO[1] * PO[1]) + PO[2] * PO[2]);
+        const float dist3D = std::sqrt(sum3(PO[0] * PO[0], PO[1] * PO[1], PO[2] * PO[2]));
         if (dist3D < 0.8f * mf_min_dist[i] || dist3D > 1.2f * mf_max_dist[i]) continue;
         const float ratio = mf_max_dist[i] / dist3D;
         int pl = (int)std::ceil(std::log(ratio) / F.log_scale_factor);

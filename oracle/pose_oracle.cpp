@@ -8,8 +8,9 @@
 //   stereo pose-only edge    types/types_six_dof_expmap.cpp:339-404 (float invz in cam_project), .h:218-222
 //   mono pose-only edge      src/OptimizableTypes.cpp:49-63, include/OptimizableTypes.h:38-42, Pinhole.cpp:38-44,71-81
 // Eigen (un-vendored) pieces are restated: Quaterniond * Vector3d, Quaterniond(Matrix3d), 6x6 LDLT solve.
-// PARITY UNPINNED for this file: neither g2o nor Eigen can be built here and the reference ships no
-// golden vectors; the restatement is validated by convergence to ground truth and invariants only.
+// PINNED (round 2): tests/test_oracle_tracking_ref.py compares this file with the reference's own Optimizer::PoseOptimization body
+// (src/Optimizer.cc:814-1114) running on the reference's g2o, both compiled unmodified over a stand-in Eigen (oracle/ref_tracking_driver.cpp):
+// identical outlier flags and inlier counts, poses equal to 1e-6 on 8 problem families + degenerate sizes.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -268,7 +269,11 @@ int orc_pose_optimize(const float pose_in[7], int n, const float* xw, const floa
         }
         if (n < 10) break;
     }
-    pose_out[0] = (float)lm.est.r.x; pose_out[1] = (float)lm.est.r.y; pose_out[2] = (float)lm.est.r.z; pose_out[3] = (float)lm.est.r.w;
+    // Sophus::SE3<float> pose(rotation().cast<float>(), translation().cast<float>()) (src/Optimizer.cc:1108-1110): the SO3f quaternion
+    // constructor normalises in float, coeffs /= norm (so3.hpp:481-487, 297-303; Eigen's 4-term squared norm = (x2 + y2) + (z2 + w2))
+    float qf[4] = {(float)lm.est.r.x, (float)lm.est.r.y, (float)lm.est.r.z, (float)lm.est.r.w};
+    const float length = std::sqrt((qf[0] * qf[0] + qf[1] * qf[1]) + (qf[2] * qf[2] + qf[3] * qf[3]));
+    for (int i = 0; i < 4; ++i) pose_out[i] = qf[i] / length;
     pose_out[4] = (float)lm.est.t[0]; pose_out[5] = (float)lm.est.t[1]; pose_out[6] = (float)lm.est.t[2];
     return n - n_bad;
 }

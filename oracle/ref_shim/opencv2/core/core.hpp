@@ -49,6 +49,8 @@ template <class T> struct Point_ {
 typedef Point_<int> Point;
 typedef Point_<int> Point2i;
 typedef Point_<float> Point2f;
+template <class T> struct Point3_ { T x, y, z; Point3_() : x(0), y(0), z(0) {} Point3_(T a, T b, T c) : x(a), y(b), z(c) {} };
+typedef Point3_<float> Point3f;
 struct Size { int width, height; Size() : width(0), height(0) {} Size(int w, int h) : width(w), height(h) {} };
 struct Rect { int x, y, width, height; Rect() : x(0), y(0), width(0), height(0) {} Rect(int a, int b, int w, int h) : x(a), y(b), width(w), height(h) {} };
 
@@ -75,6 +77,7 @@ public:
     size_t elemSize() const { return type_ == CV_32F ? 4 : (type_ == CV_16U ? 2 : 1); }
     size_t step1() const { return step / elemSize(); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    size_t total() const { return (size_t)rows * cols; }
     void release() { rows = cols = 0; step = 0; data = nullptr; buf_.reset(); }
     void create(int r, int c, int type) {                       // keeps a matching allocation (OpenCV semantics)
         if (data && rows == r && cols == c && type_ == type) return;
@@ -102,6 +105,22 @@ private:
     std::shared_ptr<std::vector<uchar> > buf_;
 };
 
+// cv::Mat_<T>(r, c) << a, b, ...  (row-major comma initialiser; Pinhole::toK)
+template <class T> class Mat_ : public Mat {
+public:
+    Mat_(int r, int c) : Mat(r, c, sizeof(T) == 4 ? CV_32F : CV_8U), k_(0) {}
+    Mat_& operator<<(T v) { return (*this, v); }
+    Mat_& operator,(T v) { at<T>(k_ / cols, k_ % cols) = v; ++k_; return *this; }
+private:
+    int k_;
+};
+enum { NORM_L1 = 2, NORM_HAMMING = 6 };
+inline double norm(const Mat& a, const Mat& b, int normType) {      // NORM_L1 on CV_8U windows (Frame::ComputeStereoMatches)
+    assert(normType == NORM_L1 && a.type() == CV_8U && a.rows == b.rows && a.cols == b.cols); (void)normType;
+    int s = 0;
+    for (int y = 0; y < a.rows; ++y) { const uchar* pa = a.ptr(y); const uchar* pb = b.ptr(y); for (int x = 0; x < a.cols; ++x) s += abs((int)pa[x] - (int)pb[x]); }
+    return (double)s;
+}
 struct Mat::Expr { Mat m; };                                     // always an evaluated CV_32F (or source-typed) temporary
 inline Mat::Mat(const Expr& e) : rows(0), cols(0), step(0), data(nullptr), type_(0) { *this = e.m; }
 inline Mat& Mat::operator=(const Expr& e) {

@@ -132,13 +132,14 @@ static int create(const rgbl_config* cfg, Ctx** out) {
         CUF(dmalloc(&c->qt_scr.scan, (size_t)c->dense_cap + (size_t)B * nl + 8));
         CUF(dmalloc(&c->qt_scr.quad, (size_t)c->dense_cap));
     }
-    {   // optional strip formulation of the FAST kernel / staged describe kernel (prepared, not yet run on a GPU)
+    {   // strip FAST, staged describe, dilation with the empty-tile shortcut: measured on B200 in round 2 (profiles/r02_variants.md),
+        // bit-exact and faster, hence the defaults; RGBL_<NAME>=0 selects the round-1 kernel for A/B runs
         const char* envd = getenv("RGBL_DESCRIBE_STAGED");
-        c->describe_staged = envd && envd[0] == '1';
+        c->describe_staged = !(envd && envd[0] == '0');
         const char* envl = getenv("RGBL_DILATE_V2");
-        c->dilate_v2 = envl && envl[0] == '1';
+        c->dilate_v2 = !(envl && envl[0] == '0');
         const char* env = getenv("RGBL_FAST_STRIPS");
-        if (env && env[0] == '1') {
+        if (!(env && env[0] == '0')) {
             build_fast_strips(c->cells, 8, 264, c->strips, c->strip_rows_cap, c->strip_list_cap);
             CUF(dmalloc(&c->d_strips, c->strips.size()));
             CUF(cudaMemcpy(c->d_strips, c->strips.data(), c->strips.size() * sizeof(StripInfo), cudaMemcpyHostToDevice));

@@ -171,3 +171,26 @@ class PlaneSequence:
         velo = self.Tr_inv @ cam
         pts = np.stack([velo[0], velo[1], velo[2], np.ones(X.size)]).astype(np.float32)
         return np.ascontiguousarray(pts)
+
+
+def stereo_disparity_field(W: int = KITTI_W, H: int = KITTI_H) -> np.ndarray:
+    """Smooth, NON-uniform disparity (pixels) of a rectified pair, defined on the right image: near ground at the bottom of the image
+    (large disparity), far scene at the top, plus a slow lateral modulation.  4 ... ~30 px at KITTI size (= 97 m ... 13 m at bf 387)."""
+    y = np.linspace(0.0, 1.0, H)[:, None]
+    x = np.arange(W)[None, :]
+    return 4.0 + 22.0 * y * y + 3.0 * np.sin(x / 90.0) * (0.3 + y)
+
+
+def stereo_pair(seed: int, W: int = KITTI_W, H: int = KITTI_H):
+    """(left, right) uint8 images of a rectified stereo rig (BASELINE config C): right(x, y) = left(x + d(x, y), y),
+    bilinearly resampled, d = stereo_disparity_field; so a left keypoint at uL has its match near uL - d."""
+    margin = 48
+    tex = make_image(seed, W + margin, H).astype(np.float64)
+    left = tex[:, :W]
+    d = stereo_disparity_field(W, H)
+    xs = np.arange(W)[None, :] + d
+    x0 = np.floor(xs).astype(np.int64); fx = xs - x0
+    x0 = np.clip(x0, 0, W + margin - 2)
+    rows = np.arange(H)[:, None]
+    right = tex[rows, x0] * (1.0 - fx) + tex[rows, x0 + 1] * fx
+    return np.ascontiguousarray(np.clip(np.rint(left), 0, 255).astype(np.uint8)), np.ascontiguousarray(np.clip(np.rint(right), 0, 255).astype(np.uint8))

@@ -70,7 +70,7 @@ def pose_problem(seed, n=900, outlier_frac=0.3, stereo_frac=0.7):
     u = fx * Pc[:, 0] / Pc[:, 2] + cx; v = fy * Pc[:, 1] / Pc[:, 2] + cy; ur = u - bf / Pc[:, 2]
     lvl = rng.integers(0, 8, n); sig = 1.2 ** lvl
     obs = np.stack([u + rng.normal(0, 0.5, n) * sig, v + rng.normal(0, 0.5, n) * sig, ur + rng.normal(0, 0.5, n) * sig], 1)
-    stereo = (rng.random(n) < stereo_frac).astype(np.uint8); obs[stereo == 0, 2] = -1
+    stereo = ((rng.random(n) < stereo_frac) & (obs[:, 2] >= 0)).astype(np.uint8); obs[stereo == 0, 2] = -1     # the reference tells stereo by mvuRight >= 0
     oi = rng.choice(n, int(outlier_frac * n), replace=False)
     obs[oi, :2] += rng.uniform(-60, 60, (len(oi), 2))
     inv_s2 = (1.0 / sig ** 2).astype(np.float32)
@@ -93,16 +93,40 @@ def se3f_rotate(q, p):
     return ((p + qw * uv).astype(f32) + c).astype(f32)
 
 
+def se3f_inverse(pose):
+    """Sophus::SE3f::inverse() (se3.hpp:208-211): invR = SO3f(conjugate) - the quaternion constructor normalises in float
+    (so3.hpp:229-231, 481-487) - and translation invR * (t * -1).  -> (q_inv[4], t_inv[3]) float32."""
+    q = np.array([-pose[0], -pose[1], -pose[2], pose[3]], f32)
+    length = np.sqrt(f32(f32(q[0] * q[0]) + f32(q[1] * q[1])) + f32(f32(q[2] * q[2]) + f32(q[3] * q[3])))       # Eigen: (x2 + y2) + (z2 + w2)
+    q = (q / f32(length)).astype(f32)
+    nt = (np.asarray(pose[4:7], f32) * f32(-1.0)).astype(f32)[None, :]
+    return q, se3f_rotate(q, nt)[0]
+
+
+def quat_to_matrix_f32(q):
+    """Eigen QuaternionBase::toRotationMatrix in float32 (Geometry/Quaternion.h)."""
+    x, y, z, w = (f32(v) for v in q)
+    tx, ty, tz = f32(2) * x, f32(2) * y, f32(2) * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz = tx * x, ty * x, tz * x
+    tyy, tyz, tzz = ty * y, tz * y, tz * z
+    return np.array([[f32(1) - (tyy + tzz), txy - twz, txz + twy],
+                     [txy + twz, f32(1) - (txx + tzz), tyz - twx],
+                     [txz - twy, tyz + twx, f32(1) - (txx + tyy)]], f32)
+
+
 def chain_unproject(fr, pose):
+    """Frame::UnprojectStereo (src/Frame.cc:1137-1150) for every keypoint: x3D = mRwc * x3Dc + mOw with mRwc / mOw from
+    Frame::UpdatePoseMatrices (src/Frame.cc:562-569), float32, Eigen 3.3's product order r0*x + (r1*y + r2*z).
+    Pinned to the reference's own code by tests/test_oracle_tracking_ref.py::test_unproject_stereo."""
     k, z = fr["k"], fr["depth"]
     ok = z > 0
     zz = np.where(ok, z, f32(1)).astype(f32)
     invfx, invfy = f32(1.0) / f32(S.KITTI_FX), f32(1.0) / f32(S.KITTI_FY)
     pc = np.stack([((k["x"] - f32(S.KITTI_CX)) * zz).astype(f32) * invfx, ((k["y"] - f32(S.KITTI_CY)) * zz).astype(f32) * invfy, zz], 1).astype(f32)
-    inv = np.array([-pose[0], -pose[1], -pose[2], pose[3]], f32)
-    nt = (np.asarray(pose[4:7], f32) * f32(-1.0)).astype(f32)[None, :]
-    ow = se3f_rotate(inv, nt)
-    xw = (se3f_rotate(inv, pc) + ow).astype(f32)
+    q_inv, ow = se3f_inverse(pose)
+    R = quat_to_matrix_f32(q_inv)
+    xw = np.stack([(R[r, 0] * pc[:, 0] + (R[r, 1] * pc[:, 1] + R[r, 2] * pc[:, 2]).astype(f32)).astype(f32) + ow[r] for r in range(3)], 1).astype(f32)
     return xw, ok
 
 

@@ -627,7 +627,8 @@ def fuse_search(kf: FrameView, Tcw, Ow, valid, xw, normal, mf_min_dist, mf_max_d
 _REF_TRACK = _HERE / "_ref" / "libref_tracking.so"
 _ref_track = None
 _REF_TRACK_MIRRORED = ("descriptor_distance", "features_in_area", "search_by_projection_last", "is_in_frustum", "search_by_projection_local",
-                       "search_by_bow", "search_by_projection_reloc", "pose_optimize", "stereo_matches", "distinctive_descriptors")
+                       "search_by_bow", "search_by_projection_reloc", "pose_optimize", "stereo_matches", "distinctive_descriptors",
+                       "local_bundle_adjustment")
 
 
 class _RefProxy:
@@ -661,6 +662,10 @@ def ref_tracking():
         vp, i, f = C.c_void_p, C.c_int, C.c_float
         L.ref_stereo_from_rgbd.argtypes = [i, vp, vp, vp, i, i, f, vp, vp]; L.ref_stereo_from_rgbd.restype = None
         L.ref_unproject_stereo.argtypes = [vp, i, vp, vp, f, f, f, f, vp, vp]; L.ref_unproject_stereo.restype = None
+        L.ref_search_for_triangulation.argtypes = [vp, vp, f, f, f, f, i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp,
+                                                   i, vp, vp, i, i, i, vp, vp, vp]
+        L.ref_search_for_triangulation.restype = i
+        L.ref_fuse.argtypes = [C.POINTER(FrameViewC), vp, i, vp, vp, vp, vp, vp, vp, f, vp, vp]; L.ref_fuse.restype = i
         _ref_track = _RefProxy(L, o)
     return _ref_track
 
@@ -702,3 +707,33 @@ def ref_unproject_stereo(pose, kp_un_xy, depth, fx, fy, cx, cy):
     x = np.empty((len(ku), 3), np.float32); ok = np.empty(len(ku), np.uint8)
     L.ref_unproject_stereo(_p(pose), len(ku), _p(ku), _p(depth), fx, fy, cx, cy, _p(x), _p(ok))
     return x, ok.astype(bool)
+
+
+def ref_search_for_triangulation(T1w, T2w, cam, kf1: dict, kf2: dict, scale_factors2, level_sigma2_2, only_stereo=False, coarse=False, check_orientation=True):
+    """ORBmatcher::SearchForTriangulation of the reference itself for two key frames at poses T1w / T2w (qx..tz)
+    -> (nmatches, match12, F12[9] row-major, epipole[2]) - F12 and the epipole as the reference derives them from the poses."""
+    L = ref_tracking()._L
+    def unpack(k):
+        return (np.ascontiguousarray(k["desc"], np.uint8), np.ascontiguousarray(k["keys"]), np.ascontiguousarray(k["has_mp"], np.uint8),
+                np.ascontiguousarray(k["uright"], np.float32), np.ascontiguousarray(k["fv"][0], np.uint32), np.ascontiguousarray(k["fv"][1], np.int32),
+                np.ascontiguousarray(k["fv"][2], np.int32))
+    d1, k1, m1, u1, i1, s1, f1 = unpack(kf1); d2, k2, m2, u2, i2, s2, f2 = unpack(kf2)
+    T1w = np.ascontiguousarray(T1w, np.float32); T2w = np.ascontiguousarray(T2w, np.float32)
+    sf = np.ascontiguousarray(scale_factors2, np.float32); sg = np.ascontiguousarray(level_sigma2_2, np.float32)
+    match = np.empty(max(len(d1), 1), np.int32); F12 = np.empty(9, np.float32); ep = np.empty(2, np.float32)
+    nm = L.ref_search_for_triangulation(_p(T1w), _p(T2w), cam[0], cam[1], cam[2], cam[3], len(d1), _p(d1), _p(k1), _p(m1), _p(u1), len(i1), _p(i1), _p(s1), _p(f1),
+                                        len(d2), _p(d2), _p(k2), _p(m2), _p(u2), len(i2), _p(i2), _p(s2), _p(f2), len(sf), _p(sf), _p(sg),
+                                        int(only_stereo), int(coarse), int(check_orientation), _p(match), _p(F12), _p(ep))
+    return nm, match[:len(d1)], F12, ep
+
+
+def ref_fuse(kf: FrameView, Tcw, valid, xw, normal, mf_min_dist, mf_max_dist, mp_desc, th=3.0):
+    """ORBmatcher::Fuse(pKF, vpMapPoints, th) of the reference itself -> (nFused, best_idx[n] (-1 = not fused), Ow[3])."""
+    L = ref_tracking()._L
+    Tcw = np.ascontiguousarray(Tcw, np.float32); valid = np.ascontiguousarray(valid, np.uint8)
+    xw = np.ascontiguousarray(xw, np.float32); normal = np.ascontiguousarray(normal, np.float32)
+    mn = np.ascontiguousarray(mf_min_dist, np.float32); mx = np.ascontiguousarray(mf_max_dist, np.float32); d = np.ascontiguousarray(mp_desc, np.uint8)
+    n = len(valid)
+    bi = np.empty(max(n, 1), np.int32); Ow = np.empty(3, np.float32)
+    nf = L.ref_fuse(C.byref(kf.c), _p(Tcw), n, _p(valid), _p(xw), _p(normal), _p(mn), _p(mx), _p(d), th, _p(bi), _p(Ow))
+    return nf, bi[:n], Ow

@@ -91,10 +91,12 @@ public:
     bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }
     std::tuple<int, int> GetIndexInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) ? mObservations[pKF] : std::tuple<int, int>(-1, -1); }   // src/MapPoint.cc:411-418
     // bookkeeping the fusion / BA code calls after its search: recorded, not modelled
-    void Replace(MapPoint* pMP) { mpReplaced = pMP; }
+    void Replace(MapPoint* pMP) { mpReplaced = pMP; replaced_by.push_back(pMP); }
     void AddObservation(KeyFrame* pKF, int idx) { mObservations[pKF] = std::tuple<int, int>(idx, -1); ++nObs; }
     void EraseObservation(KeyFrame* pKF) { mObservations.erase(pKF); }
     void UpdateNormalAndDepth() {}
+    Map* GetMap() { return mpMap; }
+    Map* mpMap = nullptr;
 
     Eigen::Vector3f mWorldPos, mNormalVector;
     cv::Mat mDescriptor;
@@ -103,6 +105,7 @@ public:
     float mfMinDistance = 0, mfMaxDistance = 0;
     std::map<KeyFrame*, std::tuple<int, int>> mObservations;
     MapPoint* mpReplaced = nullptr;
+    std::vector<MapPoint*> replaced_by;          // every Replace() call, in order (the driver reads the fusion outcome from it)
     std::mutex mMutexPos, mMutexFeatures;
 };
 
@@ -192,6 +195,12 @@ public:
     MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
     void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }
     void EraseMapPointMatch(const int& idx) { mvpMapPoints[idx] = nullptr; }
+    void EraseMapPointMatch(MapPoint* pMP) { erased.push_back(pMP); for (auto& q : mvpMapPoints) if (q == pMP) q = nullptr; }      // src/KeyFrame.cc:365-379
+    std::vector<MapPoint*> erased;               // the driver reads the outcome of LocalBundleAdjustment from it
+    Map* GetMap() { return mpMap; }
+    Map* mpMap = nullptr;
+    std::vector<KeyFrame*> GetVectorCovisibleKeyFrames() { return mvpOrderedConnectedKeyFrames; }
+    std::vector<KeyFrame*> mvpOrderedConnectedKeyFrames;
     bool isBad() { return mbBad; }
     bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }   // src/KeyFrame.cc:750-753
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;      // body: src/KeyFrame.cc, extracted
@@ -202,13 +211,24 @@ class Map {
 public:
     void IncreaseChangeIndex() {}
     long unsigned int GetMaxKFid() { return 0; }
+    long unsigned int GetInitKFid() { return mnInitKFid; }
     bool IsInertial() { return false; }
     bool isImuInitialized() { return false; }
+    long unsigned int mnInitKFid = ~0ul;
+    std::set<long unsigned int> msOptKFs, msFixedKFs;
+    std::mutex mMutexMapUpdate;
+};
+
+class Verbose {                 // include/System.h:47-75
+public:
+    enum eLevel { VERBOSITY_QUIET = 0, VERBOSITY_NORMAL = 1, VERBOSITY_VERBOSE = 2, VERBOSITY_VERY_VERBOSE = 3, VERBOSITY_DEBUG = 4 };
+    static void PrintMess(std::string, eLevel) {}
 };
 
 class Optimizer {
 public:
     static int PoseOptimization(Frame* pFrame);                  // body: src/Optimizer.cc:814-1114, extracted
+    static void LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap, int& num_fixedKF, int& num_OptKF, int& num_MPs, int& num_edges);   // :1116-1499
 };
 
 }  // namespace ORB_SLAM3

@@ -24,6 +24,12 @@
 #include "Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.h"
 #include "Thirdparty/g2o/g2o/core/robust_kernel_impl.h"
 #include "Thirdparty/g2o/g2o/solvers/linear_solver_dense.h"
+#include "Thirdparty/g2o/g2o/types/types_sba.h"
+// g2o::LinearSolverEigen (solvers/linear_solver_eigen.h) wraps Eigen's sparse SimplicialLDLT with an AMD ordering, which the stand-in
+// Eigen does not have: Optimizer::LocalBundleAdjustment gets the same linear system solved by the dense LDLT instead (same solution up
+// to rounding; the BA comparison is tolerance-based).
+#define G2O_LINEAR_SOLVER_EIGEN_H
+namespace g2o { template <typename MatrixType> class LinearSolverEigen : public LinearSolverDense<MatrixType> {}; }
 #include "Thirdparty/g2o/g2o/types/types_six_dof_expmap.h"
 
 #include "ORBmatcher.cc"                    // found through -I/root/reference/src
@@ -357,6 +363,151 @@ void ref_distinctive_descriptors(int n, const int* obs_start, const uint8_t* des
         p.ComputeDistinctiveDescriptors();
         for (int j = 0; j < m; ++j) if (memcmp(p.mDescriptor.data, desc + 32 * (size_t)(obs_start[i] + j), 32) == 0) { best[i] = j; break; }
     }
+}
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (src/ORBmatcher.cc:907-1146) with
+// Pinhole::epipolarConstrain; key-frame arrays as orc_search_for_triangulation.  The reference derives the epipole and (inside
+// epipolarConstrain, per pair) F12 from the two poses: both are returned so that the restatement can be fed the same numbers.
+int ref_search_for_triangulation(const float T1w[7], const float T2w[7], float fx, float fy, float cx, float cy,
+                                 int n1, const uint8_t* desc1, const void* keys1_, const uint8_t* has_mp1, const float* uright1,
+                                 int nn1, const uint32_t* node_ids1, const int* node_start1, const int* node_feat1,
+                                 int n2, const uint8_t* desc2, const void* keys2_, const uint8_t* has_mp2, const float* uright2,
+                                 int nn2, const uint32_t* node_ids2, const int* node_start2, const int* node_feat2,
+                                 int n_levels, const float* scale_factors2, const float* level_sigma2_2,
+                                 int only_stereo, int coarse, int check_orientation, int32_t* match12, float* F12_out, float* ep_out) {
+    Pinhole cam(std::vector<float>{fx, fy, cx, cy});
+    MapPoint occupied;
+    auto fill = [&](KeyFrame& kf, const float T[7], int n, const uint8_t* desc, const void* keys_, const uint8_t* has_mp, const float* uright,
+                    int nn, const uint32_t* ids, const int* start, const int* feat) {
+        const RefKp* k = (const RefKp*)keys_;
+        kf.N = n; kf.NLeft = -1; kf.mpCamera = &cam; kf.mpCamera2 = nullptr;
+        kf.mvKeysUn.resize(n); kf.mvpMapPoints.assign(n, nullptr); kf.mvuRight.assign(uright, uright + n); kf.mDescriptors = desc_mat(desc, n);
+        for (int i = 0; i < n; ++i) {
+            kf.mvKeysUn[i] = cv::KeyPoint(cv::Point2f(k[i].x, k[i].y), k[i].size, k[i].angle, k[i].response, k[i].octave, k[i].class_id);
+            if (has_mp[i]) kf.mvpMapPoints[i] = &occupied;
+        }
+        kf.mvKeys = kf.mvKeysUn;
+        for (int a = 0; a < nn; ++a) for (int j = start[a]; j < start[a + 1]; ++j) kf.mFeatVec.addFeature(ids[a], (unsigned)feat[j]);
+        kf.SetPose(to_se3(T));
+    };
+    KeyFrame kf1, kf2;
+    fill(kf1, T1w, n1, desc1, keys1_, has_mp1, uright1, nn1, node_ids1, node_start1, node_feat1);
+    fill(kf2, T2w, n2, desc2, keys2_, has_mp2, uright2, nn2, node_ids2, node_start2, node_feat2);
+    kf2.mvScaleFactors.assign(scale_factors2, scale_factors2 + n_levels); kf2.mvLevelSigma2.assign(level_sigma2_2, level_sigma2_2 + n_levels);
+    kf1.mvScaleFactors = kf2.mvScaleFactors; kf1.mvLevelSigma2 = kf2.mvLevelSigma2;
+    {   // what the function computes at its top (:914-931) and epipolarConstrain per pair (Pinhole.cpp:108-112)
+        const Sophus::SE3f T12 = kf1.GetPose() * kf2.GetPoseInverse();
+        const Eigen::Matrix3f R12 = T12.rotationMatrix(); const Eigen::Vector3f t12 = T12.translation();
+        const Eigen::Matrix3f t12x = Sophus::SO3f::hat(t12), K1 = cam.toK_(), K2 = cam.toK_();
+        const Eigen::Matrix3f F12 = K1.transpose().inverse() * t12x * R12 * K2.inverse();
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) F12_out[3 * r + c] = F12(r, c);
+        const Eigen::Vector3f C2 = kf2.GetPose() * kf1.GetCameraCenter();
+        const Eigen::Vector2f ep = cam.project(C2);
+        ep_out[0] = ep(0); ep_out[1] = ep(1);
+    }
+    std::vector<std::pair<size_t, size_t>> pairs;
+    ORBmatcher matcher(0.6f, check_orientation != 0);
+    const int nm = matcher.SearchForTriangulation(&kf1, &kf2, pairs, only_stereo != 0, coarse != 0);
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    for (const auto& pr : pairs) match12[pr.first] = (int32_t)pr.second;
+    return nm;
+}
+
+// ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>&, th, bRight = false) (src/ORBmatcher.cc:1148-1330): the key frame's
+// members come from the frame view (KeyFrame = copy of the Frame's keypoints, grid, scale tables; src/KeyFrame.cc ctor).  Every
+// key-frame slot holds a placeholder map point without observations, so each fused point i ends in `slot.Replace(point i)`
+// (:1313-1318): best_idx[i] = that slot, -1 when the point was not fused (no candidate with bestDist <= TH_LOW).  Ow_out = the camera
+// centre the function uses (pKF->GetCameraCenter()).
+int ref_fuse(const ref_frame_view* kfv, const float Tcw[7], int n, const uint8_t* valid, const float* xw, const float* normal,
+             const float* mf_min_dist, const float* mf_max_dist, const uint8_t* mp_desc, float th, int* best_idx, float* Ow_out) {
+    FrameHolder h(kfv);
+    KeyFrame kf;
+    kf.N = kfv->n; kf.NLeft = -1; kf.mpCamera = &h.cam; kf.mpCamera2 = nullptr;
+    kf.mvKeysUn = h.F.mvKeysUn; kf.mvKeys = h.F.mvKeys; kf.mvuRight = h.F.mvuRight; kf.mDescriptors = h.F.mDescriptors;
+    kf.fx = kfv->fx; kf.fy = kfv->fy; kf.cx = kfv->cx; kf.cy = kfv->cy; kf.mbf = kfv->bf;
+    kf.mnMinX = (int)Frame::mnMinX; kf.mnMinY = (int)Frame::mnMinY; kf.mnMaxX = (int)Frame::mnMaxX; kf.mnMaxY = (int)Frame::mnMaxY;
+    kf.mfGridElementWidthInv = Frame::mfGridElementWidthInv; kf.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+    kf.mnScaleLevels = h.F.mnScaleLevels; kf.mfLogScaleFactor = h.F.mfLogScaleFactor;
+    kf.mvScaleFactors = h.F.mvScaleFactors; kf.mvLevelSigma2 = h.F.mvLevelSigma2; kf.mvInvLevelSigma2 = h.F.mvInvLevelSigma2;
+    kf.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t>>(FRAME_GRID_ROWS));
+    for (int i = 0; i < FRAME_GRID_COLS; ++i) for (int j = 0; j < FRAME_GRID_ROWS; ++j) kf.mGrid[i][j] = h.F.mGrid[i][j];
+    kf.SetPose(to_se3(Tcw));
+    const Eigen::Vector3f Ow = kf.GetCameraCenter();
+    Ow_out[0] = Ow(0); Ow_out[1] = Ow(1); Ow_out[2] = Ow(2);
+    std::vector<MapPoint> slots(kfv->n);
+    kf.mvpMapPoints.resize(kfv->n);
+    for (int i = 0; i < kfv->n; ++i) { slots[i].nObs = 0; kf.mvpMapPoints[i] = &slots[i]; }
+    std::vector<MapPoint> pts(n);
+    std::vector<MapPoint*> vp(n, nullptr);
+    for (int i = 0; i < n; ++i) {
+        best_idx[i] = -1;
+        if (!valid[i]) continue;
+        pts[i].mWorldPos = Eigen::Vector3f(xw[3 * i], xw[3 * i + 1], xw[3 * i + 2]);
+        pts[i].mNormalVector = Eigen::Vector3f(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]);
+        pts[i].mfMinDistance = mf_min_dist[i]; pts[i].mfMaxDistance = mf_max_dist[i];
+        pts[i].mDescriptor = desc_mat(mp_desc + 32 * i, 1);
+        pts[i].nObs = 1;
+        vp[i] = &pts[i];
+    }
+    ORBmatcher matcher(0.6f, true);
+    const int nf = matcher.Fuse(&kf, vp, th, false);
+    for (int s = 0; s < kfv->n; ++s)
+        for (MapPoint* p : slots[s].replaced_by) best_idx[(int)(p - pts.data())] = s;
+    return nf;
+}
+
+// Optimizer::LocalBundleAdjustment (src/Optimizer.cc:1116-1499) over the reference's g2o (Schur-complement block solver, LM), arguments
+// as orc_local_bundle_adjustment.  The key-frame graph is built so that the function finds: the non-fixed poses as the local key frames
+// (the first one plays pKF, the others its covisible key frames), the fixed poses as the "fixed cameras" that observe local points.
+// edge_erase[e] = the (key frame, map point) pair of edge e was put on vToErase.  Returns 0 (the LM iteration count is internal).
+int ref_local_bundle_adjustment(int n_poses, const float* poses, const uint8_t* pose_fixed, int n_points, const float* points, int n_edges,
+                                const int32_t* e_point, const int32_t* e_pose, const float* obs, const uint8_t* stereo,
+                                const float* inv_sigma2, float fx, float fy, float cx, float cy, float bf, int iterations,
+                                float* poses_out, float* points_out, uint8_t* edge_erase, double* final_chi2) {
+    (void)iterations; if (final_chi2) *final_chi2 = 0;
+    Pinhole cam(std::vector<float>{fx, fy, cx, cy});
+    Map map;
+    std::vector<KeyFrame> kfs(n_poses);
+    std::vector<MapPoint> mps(n_points);
+    for (int i = 0; i < n_poses; ++i) {
+        KeyFrame& k = kfs[i];
+        k.mnId = (unsigned long)i; k.mpMap = &map; k.mpCamera = &cam; k.mpCamera2 = nullptr; k.NLeft = -1;
+        k.fx = fx; k.fy = fy; k.cx = cx; k.cy = cy; k.mbf = bf;
+        k.SetPose(to_se3(poses + 7 * i));
+    }
+    for (int j = 0; j < n_points; ++j) {
+        mps[j].mnId = (unsigned long)j; mps[j].mpMap = &map;
+        mps[j].mWorldPos = Eigen::Vector3f(points[3 * j], points[3 * j + 1], points[3 * j + 2]);
+    }
+    for (int e = 0; e < n_edges; ++e) {          // one keypoint per observation, on its own pyramid level (so that mvInvLevelSigma2[octave] = inv_sigma2[e])
+        KeyFrame& k = kfs[e_pose[e]]; MapPoint& p = mps[e_point[e]];
+        const int idx = (int)k.mvKeysUn.size();
+        cv::KeyPoint kp; kp.pt = cv::Point2f(obs[3 * e], obs[3 * e + 1]); kp.octave = idx;
+        k.mvKeysUn.push_back(kp); k.mvuRight.push_back(stereo[e] ? obs[3 * e + 2] : -1.0f); k.mvInvLevelSigma2.push_back(inv_sigma2[e]);
+        k.mvpMapPoints.push_back(&p);
+        p.mObservations[&k] = std::tuple<int, int>(idx, -1);
+    }
+    KeyFrame* pKF = nullptr;
+    for (int i = 0; i < n_poses; ++i) if (!pose_fixed[i]) { if (!pKF) pKF = &kfs[i]; else pKF->mvpOrderedConnectedKeyFrames.push_back(&kfs[i]); }
+    for (int i = 0; i < n_poses; ++i) { std::memcpy(poses_out + 7 * i, poses + 7 * i, 7 * sizeof(float)); }
+    std::memcpy(points_out, points, (size_t)n_points * 3 * sizeof(float));
+    std::memset(edge_erase, 0, (size_t)n_edges);
+    if (!pKF) return 0;
+    pKF->mnId = (unsigned long)n_poses + 7;      // mnBALocalForKF markers compare against pKF->mnId: make it non-zero and unique
+    int nf = 0, no = 0, nm = 0, ne = 0;
+    Optimizer::LocalBundleAdjustment(pKF, nullptr, &map, nf, no, nm, ne);
+    for (int i = 0; i < n_poses; ++i) {
+        const Sophus::SE3f T = kfs[i].GetPose();
+        poses_out[7 * i] = T.unit_quaternion().x(); poses_out[7 * i + 1] = T.unit_quaternion().y(); poses_out[7 * i + 2] = T.unit_quaternion().z();
+        poses_out[7 * i + 3] = T.unit_quaternion().w();
+        for (int c = 0; c < 3; ++c) poses_out[7 * i + 4 + c] = T.translation()(c);
+    }
+    for (int j = 0; j < n_points; ++j) for (int c = 0; c < 3; ++c) points_out[3 * j + c] = mps[j].mWorldPos(c);
+    for (int e = 0; e < n_edges; ++e) {
+        const KeyFrame& k = kfs[e_pose[e]];
+        for (MapPoint* p : k.erased) if (p == &mps[e_point[e]]) edge_erase[e] = 1;
+    }
+    return 0;
 }
 
 }  // extern "C"

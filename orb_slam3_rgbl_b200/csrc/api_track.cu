@@ -95,6 +95,15 @@ static void h_rotate(const float* T, const float p[3], float out[3]) {
     for (int i = 0; i < 3; ++i) out[i] = (p[i] + qw * uv[i]) + cr[i];
 }
 
+// Tcw.inverse().translation(): SO3f(conjugate) normalises in float (so3.hpp:229-231, 481-487), then invR * (t * -1) (se3.hpp:208-211)
+static void h_inverse_translation(const float* T, float out[3]) {
+    float inv[4] = {-T[0], -T[1], -T[2], T[3]};
+    const float length = std::sqrt((inv[0] * inv[0] + inv[1] * inv[1]) + (inv[2] * inv[2] + inv[3] * inv[3]));      // Eigen 3.3: (x2 + y2) + (z2 + w2)
+    for (int i = 0; i < 4; ++i) inv[i] /= length;
+    const float nt[3] = {T[4] * -1.f, T[5] * -1.f, T[6] * -1.f};
+    h_rotate(inv, nt, out);
+}
+
 static int finish_search(Ctx* c, int n_frame, int32_t* match, int* n_matches) {
     TrackBufs& t = c->trk;
     stage_end(c, ST_MATCH, c->st, 3);
@@ -149,10 +158,8 @@ int rgbl_search_by_projection_last(rgbl_ctx* ctx, const rgbl_frame_view* cur, co
     std::memcpy(prm.cur_pose, cur_pose, 7 * sizeof(float));
     prm.th = th; prm.check_orientation = check_orientation; prm.cur_pose_dev = nullptr; prm.flags_dev = nullptr;
     {   // bForward / bBackward, src/ORBmatcher.cc:1686-1693
-        float inv[7] = {-cur_pose[0], -cur_pose[1], -cur_pose[2], cur_pose[3], 0, 0, 0};
-        const float nt[3] = {cur_pose[4] * -1.f, cur_pose[5] * -1.f, cur_pose[6] * -1.f};
         float twc[3], r[3];
-        h_rotate(inv, nt, twc);
+        h_inverse_translation(cur_pose, twc);
         h_rotate(last_pose, twc, r);
         const float tlc_z = r[2] + last_pose[6];
         prm.forward = (tlc_z > f.mb && !mono) ? 1 : 0;
@@ -441,9 +448,7 @@ int rgbl_search_by_projection_reloc(rgbl_ctx* ctx, const rgbl_frame_view* cur, c
     SearchRelocParams prm;
     std::memcpy(prm.cur_pose, cur_pose, 7 * sizeof(float));
     {   // Ow = Tcw.inverse().translation()
-        float inv[7] = {-cur_pose[0], -cur_pose[1], -cur_pose[2], cur_pose[3], 0, 0, 0};
-        const float nt[3] = {cur_pose[4] * -1.f, cur_pose[5] * -1.f, cur_pose[6] * -1.f};
-        h_rotate(inv, nt, prm.Ow);
+        h_inverse_translation(cur_pose, prm.Ow);
     }
     prm.th = th; prm.orb_dist = orb_dist; prm.check_orientation = check_orientation;
     RelocPointsDev rp{n, t.q_u8a, t.q_f3a, t.q_desc, t.q_f[0], t.q_f[4], t.q_f[5]};

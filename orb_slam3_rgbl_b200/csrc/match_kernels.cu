@@ -740,11 +740,11 @@ __global__ void __launch_bounds__(256) fuse_search_kernel(FrameDev f, const int*
         ok = ok && (u >= f.min_x && u < f.max_x && v >= f.min_y && v < f.max_y);                     // KeyFrame::IsInImage
         const float ur = __fsub_rn(u, __fmul_rn(f.bf, invz));
         const float PO[3] = {__fsub_rn(P[0], Ow[0]), __fsub_rn(P[1], Ow[1]), __fsub_rn(P[2], Ow[2])};
-        const float dist3D = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(PO[0], PO[0]), __fmul_rn(PO[1], PO[1])), __fmul_rn(PO[2], PO[2])));
+        const float dist3D = sqrtf(eig_sum3(__fmul_rn(PO[0], PO[0]), __fmul_rn(PO[1], PO[1]), __fmul_rn(PO[2], PO[2])));
         const float mf_max = mp.mf_max[q];
         ok = ok && !(dist3D < __fmul_rn(0.8f, mp.mf_min[q]) || dist3D > __fmul_rn(1.2f, mf_max));
         const float* Pn = mp.normal + 3 * q;
-        const float dotn = __fadd_rn(__fadd_rn(__fmul_rn(PO[0], Pn[0]), __fmul_rn(PO[1], Pn[1])), __fmul_rn(PO[2], Pn[2]));
+        const float dotn = eig_sum3(__fmul_rn(PO[0], Pn[0]), __fmul_rn(PO[1], Pn[1]), __fmul_rn(PO[2], Pn[2]));
         ok = ok && !((double)dotn < 0.5 * (double)dist3D);
         if (ok) {
             const float ratio = __fdiv_rn(mf_max, dist3D);
@@ -804,9 +804,8 @@ __global__ void __launch_bounds__(256) frustum_kernel(FrameDev f, FrustumParams 
     float Pc[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
-        Pc[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(prm.Rcw[3 * r], P[0]), __fmul_rn(prm.Rcw[3 * r + 1], P[1])),
-                                    __fmul_rn(prm.Rcw[3 * r + 2], P[2])), prm.tcw[r]);
-    const float pc_dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(Pc[0], Pc[0]), __fmul_rn(Pc[1], Pc[1])), __fmul_rn(Pc[2], Pc[2])));
+        Pc[r] = __fadd_rn(eig_sum3(__fmul_rn(prm.Rcw[3 * r], P[0]), __fmul_rn(prm.Rcw[3 * r + 1], P[1]), __fmul_rn(prm.Rcw[3 * r + 2], P[2])), prm.tcw[r]);
+    const float pc_dist = sqrtf(eig_sum3(__fmul_rn(Pc[0], Pc[0]), __fmul_rn(Pc[1], Pc[1]), __fmul_rn(Pc[2], Pc[2])));
     const float z = Pc[2];
     const float invz = __fdiv_rn(1.0f, z);
     bool ok = !(z < 0.0f);
@@ -817,10 +816,10 @@ __global__ void __launch_bounds__(256) frustum_kernel(FrameDev f, FrustumParams 
     if (ok) {
         ox = u; oy = v;
         const float PO[3] = {__fsub_rn(P[0], prm.Ow[0]), __fsub_rn(P[1], prm.Ow[1]), __fsub_rn(P[2], prm.Ow[2])};
-        const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(PO[0], PO[0]), __fmul_rn(PO[1], PO[1])), __fmul_rn(PO[2], PO[2])));
+        const float dist = sqrtf(eig_sum3(__fmul_rn(PO[0], PO[0]), __fmul_rn(PO[1], PO[1]), __fmul_rn(PO[2], PO[2])));
         if (!(dist < __fmul_rn(0.8f, mf_min[i]) || dist > __fmul_rn(1.2f, mf_max[i]))) {
             const float* Pn = normal + 3 * i;
-            const float vc = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(PO[0], Pn[0]), __fmul_rn(PO[1], Pn[1])), __fmul_rn(PO[2], Pn[2])), dist);
+            const float vc = __fdiv_rn(eig_sum3(__fmul_rn(PO[0], Pn[0]), __fmul_rn(PO[1], Pn[1]), __fmul_rn(PO[2], Pn[2])), dist);
             if (!(vc < prm.cos_limit)) {
                 const float ratio = __fdiv_rn(mf_max[i], dist);
                 const float lg = (float)log((double)ratio);          // correctly-rounded stand-in for glibc logf
@@ -880,7 +879,7 @@ __global__ void __launch_bounds__(256) search_reloc_collect_kernel(FrameDev f, c
         bool ok = !(u < f.min_x || u > f.max_x) && !(v < f.min_y || v > f.max_y);     // note: no positive-depth test in the reference
         if (ok) {
             const float PO[3] = {__fsub_rn(p[0], prm.Ow[0]), __fsub_rn(p[1], prm.Ow[1]), __fsub_rn(p[2], prm.Ow[2])};
-            const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(PO[0], PO[0]), __fmul_rn(PO[1], PO[1])), __fmul_rn(PO[2], PO[2])));
+            const float dist = sqrtf(eig_sum3(__fmul_rn(PO[0], PO[0]), __fmul_rn(PO[1], PO[1]), __fmul_rn(PO[2], PO[2])));
             if (!(dist < __fmul_rn(0.8f, rp.mf_min[q]) || dist > __fmul_rn(1.2f, rp.mf_max[q]))) {
                 const float ratio = __fdiv_rn(rp.mf_max[q], dist);
                 const float lg = (float)log((double)ratio);
@@ -906,7 +905,9 @@ __global__ void __launch_bounds__(256) search_reloc_collect_kernel(FrameDev f, c
 __global__ void __launch_bounds__(256) chain_prep_kernel(ChainPrepDev cp, const float* __restrict__ last_pose, const float* __restrict__ cur_pose) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i == 0) chain_prep_flags(cp, last_pose, cur_pose);
-    if (i < cp.cap) chain_prep_item(cp, last_pose, i);
+    float Rwc[9], Ow[3];
+    chain_pose_matrices(last_pose, Rwc, Ow);
+    if (i < cp.cap) chain_prep_item(cp, Rwc, Ow, i);
 }
 
 

@@ -338,7 +338,9 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
         if (!next.kps) return;
         __syncthreads();                  // pose_out written by thread 0 / threads 0..6
         if (tid == 0) chain_prep_flags(next, pose_out, pose_out);
-        for (int i = tid; i < next.cap; i += kPoseThreads) chain_prep_item(next, pose_out, i);
+        float Rwc[9], Ow[3];
+        chain_pose_matrices(pose_out, Rwc, Ow);
+        for (int i = tid; i < next.cap; i += kPoseThreads) chain_prep_item(next, Rwc, Ow, i);
     };
     if (n < 3) {                      // src/Optimizer.cc:996
         if (tid < 7) pose_out[tid] = pose_in[tid];
@@ -608,7 +610,10 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
     }
     if (tid == 0) {
         const Se3d T = s_est;
-        pose_out[0] = (float)T.qx; pose_out[1] = (float)T.qy; pose_out[2] = (float)T.qz; pose_out[3] = (float)T.qw;
+        // Sophus::SE3<float>(rotation().cast<float>(), ...) (src/Optimizer.cc:1108-1110): the SO3f quaternion constructor normalises in float
+        const float qf[4] = {(float)T.qx, (float)T.qy, (float)T.qz, (float)T.qw};
+        const float qlen = sqrtf(eig_sum4(__fmul_rn(qf[0], qf[0]), __fmul_rn(qf[1], qf[1]), __fmul_rn(qf[2], qf[2]), __fmul_rn(qf[3], qf[3])));
+        pose_out[0] = __fdiv_rn(qf[0], qlen); pose_out[1] = __fdiv_rn(qf[1], qlen); pose_out[2] = __fdiv_rn(qf[2], qlen); pose_out[3] = __fdiv_rn(qf[3], qlen);
         pose_out[4] = (float)T.tx; pose_out[5] = (float)T.ty; pose_out[6] = (float)T.tz;
         *n_inliers = n - n_bad;
 #ifdef POSE_TIMING

@@ -151,10 +151,40 @@ __device__ __forceinline__ void se3f_rotate(const float* T, const float p[3], fl
 }
 
 
+// Eigen 3.3 (the reference's Eigen: Ubuntu 20.04 libeigen3-dev) adds the terms of a fixed-size dot product / squared norm / product
+// coefficient with its unrolled scalar reduction (Core/Redux.h, redux_novec_unroller: halves, recursively).  Pinned against the
+// reference's own code over a stand-in Eigen with the same rule (tests/test_oracle_tracking_ref.py).
+__device__ __forceinline__ float eig_sum3(float a, float b, float c) { return __fadd_rn(a, __fadd_rn(b, c)); }
+__device__ __forceinline__ float eig_sum4(float a, float b, float c, float d) { return __fadd_rn(__fadd_rn(a, b), __fadd_rn(c, d)); }
+
+// Sophus::SE3f::inverse() (se3.hpp:208-211): invR = SO3f(conjugate), whose quaternion constructor normalises in float
+// (so3.hpp:229-231, 481-487, 297-303: coeffs /= norm), translation invR * (t * -1).  qinv = (x, y, z, w), tinv = 3 floats.
+__device__ __forceinline__ void se3f_inverse(const float* T, float qinv[4], float tinv[3]) {
+    qinv[0] = -T[0]; qinv[1] = -T[1]; qinv[2] = -T[2]; qinv[3] = T[3];
+    const float length = sqrtf(eig_sum4(__fmul_rn(qinv[0], qinv[0]), __fmul_rn(qinv[1], qinv[1]), __fmul_rn(qinv[2], qinv[2]), __fmul_rn(qinv[3], qinv[3])));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qinv[i] = __fdiv_rn(qinv[i], length);
+    const float nt[3] = {__fmul_rn(T[4], -1.f), __fmul_rn(T[5], -1.f), __fmul_rn(T[6], -1.f)};
+    se3f_rotate(qinv, nt, tinv);
+}
+
+// Eigen QuaternionBase::toRotationMatrix (Geometry/Quaternion.h), float32, row-major R[9]
+__device__ __forceinline__ void quatf_to_matrix(const float q[4], float R[9]) {
+    const float x = q[0], y = q[1], z = q[2], w = q[3];
+    const float tx = __fmul_rn(2.f, x), ty = __fmul_rn(2.f, y), tz = __fmul_rn(2.f, z);
+    const float twx = __fmul_rn(tx, w), twy = __fmul_rn(ty, w), twz = __fmul_rn(tz, w);
+    const float txx = __fmul_rn(tx, x), txy = __fmul_rn(ty, x), txz = __fmul_rn(tz, x);
+    const float tyy = __fmul_rn(ty, y), tyz = __fmul_rn(tz, y), tzz = __fmul_rn(tz, z);
+    R[0] = __fsub_rn(1.f, __fadd_rn(tyy, tzz)); R[1] = __fsub_rn(txy, twz); R[2] = __fadd_rn(txz, twy);
+    R[3] = __fadd_rn(txy, twz); R[4] = __fsub_rn(1.f, __fadd_rn(txx, tzz)); R[5] = __fsub_rn(tyz, twx);
+    R[6] = __fsub_rn(txz, twy); R[7] = __fadd_rn(tyz, twx); R[8] = __fsub_rn(1.f, __fadd_rn(txx, tyy));
+}
+
 // ---- resident tracking chain: the previous frame's LiDAR-depth keypoints as map points -----------------------------------
-// Frame::UnprojectStereo (src/Frame.cc:1137-1150) with the frame's estimated pose, the bForward / bBackward test of
-// SearchByProjection (src/ORBmatcher.cc:1686-1693) and the per-point fields the search reads.  Shared by chain_prep_kernel and
-// the tail of pose_optimize_kernel (which prepares the next frame's search as soon as the pose is known: one launch less).
+// Frame::UnprojectStereo (src/Frame.cc:1137-1150: x3D = mRwc * x3Dc + mOw, with mRwc / mOw from Frame::UpdatePoseMatrices
+// :562-569) with the frame's estimated pose, the bForward / bBackward test of SearchByProjection (src/ORBmatcher.cc:1686-1693)
+// and the per-point fields the search reads.  Shared by chain_prep_kernel and the tail of pose_optimize_kernel (which prepares
+// the next frame's search as soon as the pose is known: one launch less).
 struct ChainPrepDev {
     const rgbl_keypoint* kps; const float* depth; const int* n_ptr;      // kps == nullptr: disabled
     float fx, fy, cx, cy, mb; int mono, cap;
@@ -163,17 +193,22 @@ struct ChainPrepDev {
 
 __device__ __forceinline__ void chain_prep_flags(const ChainPrepDev& cp, const float* last_pose, const float* cur_pose) {
     // tlc = Tlw * (Tcw^-1).translation()
-    const float cinv[4] = {-cur_pose[0], -cur_pose[1], -cur_pose[2], cur_pose[3]};
-    const float nt[3] = {__fmul_rn(cur_pose[4], -1.f), __fmul_rn(cur_pose[5], -1.f), __fmul_rn(cur_pose[6], -1.f)};
-    float twc[3], r[3];
-    se3f_rotate(cinv, nt, twc);
+    float cinv[4], twc[3], r[3];
+    se3f_inverse(cur_pose, cinv, twc);
     se3f_rotate(last_pose, twc, r);
     const float tlc_z = __fadd_rn(r[2], last_pose[6]);
     cp.flags[0] = (tlc_z > cp.mb && !cp.mono) ? 1 : 0;
     cp.flags[1] = (-tlc_z > cp.mb && !cp.mono) ? 1 : 0;
 }
 
-__device__ __forceinline__ void chain_prep_item(const ChainPrepDev& cp, const float* last_pose, int i) {
+// Rwc (row-major) and Ow of a pose, once per CTA / caller (Frame::UpdatePoseMatrices)
+__device__ __forceinline__ void chain_pose_matrices(const float* pose, float Rwc[9], float Ow[3]) {
+    float qinv[4];
+    se3f_inverse(pose, qinv, Ow);
+    quatf_to_matrix(qinv, Rwc);
+}
+
+__device__ __forceinline__ void chain_prep_item(const ChainPrepDev& cp, const float Rwc[9], const float Ow[3], int i) {
     if (cp.state_clear) cp.state_clear[i] = 0;           // feature states of the search that follows (saves a memset node)
     uint8_t v = 0;
     if (i < *cp.n_ptr) {
@@ -181,15 +216,11 @@ __device__ __forceinline__ void chain_prep_item(const ChainPrepDev& cp, const fl
         const rgbl_keypoint kp = cp.kps[i];
         cp.octave[i] = kp.octave; cp.angle[i] = kp.angle; cp.obs_pos[i] = 1;
         if (z > 0.f) {
-            const float inv[4] = {-last_pose[0], -last_pose[1], -last_pose[2], last_pose[3]};
             const float invfx = __fdiv_rn(1.0f, cp.fx), invfy = __fdiv_rn(1.0f, cp.fy);
             const float pc[3] = {__fmul_rn(__fmul_rn(__fsub_rn(kp.x, cp.cx), z), invfx), __fmul_rn(__fmul_rn(__fsub_rn(kp.y, cp.cy), z), invfy), z};
-            // Twc * x3Dc with Twc = Tcw^-1 = (q*, q* (x) (-t))
-            const float nt[3] = {__fmul_rn(last_pose[4], -1.f), __fmul_rn(last_pose[5], -1.f), __fmul_rn(last_pose[6], -1.f)};
-            float ow[3], pr[3];
-            se3f_rotate(inv, nt, ow);
-            se3f_rotate(inv, pc, pr);
-            cp.xw[3 * i] = __fadd_rn(pr[0], ow[0]); cp.xw[3 * i + 1] = __fadd_rn(pr[1], ow[1]); cp.xw[3 * i + 2] = __fadd_rn(pr[2], ow[2]);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                cp.xw[3 * i + r] = __fadd_rn(eig_sum3(__fmul_rn(Rwc[3 * r], pc[0]), __fmul_rn(Rwc[3 * r + 1], pc[1]), __fmul_rn(Rwc[3 * r + 2], pc[2])), Ow[r]);
             v = 1;
         }
     }

@@ -47,7 +47,19 @@ def make_problem(seed, n_kf=8, n_fixed=2, n_points=600, outlier_frac=0.03, stere
             if out:
                 nu += rng.choice([-1, 1]) * rng.uniform(15, 60); nv += rng.choice([-1, 1]) * rng.uniform(10, 40)
             ur = (u - bf / pc[2] + rng.normal(0, 0.6 * sig)) if st else -1.0
+            if ur < 0:                 # the reference tells a stereo observation by mvuRight >= 0 (src/Optimizer.cc:1286-1311)
+                st, ur = False, -1.0
             e_point.append(j); e_pose.append(k); obs.append([u + nu, v + nv, ur]); stereo.append(st); inv_s2.append(1.0 / (sig * sig)); is_out.append(out)
+    # Optimizer::LocalBundleAdjustment only adjusts points seen from a LOCAL (non-fixed) key frame (src/Optimizer.cc:1133-1160): drop the
+    # others, as the gathering shim would
+    e_point = np.array(e_point, np.int64); e_pose = np.array(e_pose, np.int64)
+    local = np.zeros(n_points, bool); local[e_point[e_pose >= n_fixed]] = True
+    keep_e = local[e_point]
+    remap = np.cumsum(local) - 1
+    e_point = remap[e_point[keep_e]]; e_pose = e_pose[keep_e]
+    obs = [o for o, k in zip(obs, keep_e) if k]; stereo = [o for o, k in zip(stereo, keep_e) if k]
+    inv_s2 = [o for o, k in zip(inv_s2, keep_e) if k]; is_out = [o for o, k in zip(is_out, keep_e) if k]
+    pts = pts[local]
     init_poses = true_poses.copy()
     for k in range(n_fixed, n_kf):
         dq = np.concatenate([rng.normal(0, pose_noise[0], 3), [1.0]]); dq /= np.linalg.norm(dq)

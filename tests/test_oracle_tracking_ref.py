@@ -200,3 +200,71 @@ def test_distinctive_descriptors():
         if c == 0:
             continue
         assert (desc[start[i] + b0[i]] == desc[start[i] + b1[i]]).all()
+
+
+def test_search_for_triangulation():
+    """The reference's own SearchForTriangulation + Pinhole::epipolarConstrain vs the restatement, fed the F12 / epipole the reference
+    derives from the two key-frame poses."""
+    rng = np.random.default_rng(21)
+    n1, n2, n_nodes = 600, 650, 30
+    base = rng.integers(0, 256, (80, 32), dtype=np.uint8)
+
+    def frame(n):
+        which = rng.integers(0, len(base), n)
+        d = base[which] ^ (rng.integers(0, 256, (n, 32), dtype=np.uint8) & rng.integers(0, 256, (n, 32), dtype=np.uint8) & rng.integers(0, 256, (n, 32), dtype=np.uint8) & rng.integers(0, 256, (n, 32), dtype=np.uint8))
+        k = np.zeros(n, oracle.KP_DTYPE)
+        k["x"] = rng.uniform(0, 1241, n); k["y"] = rng.uniform(0, 376, n); k["octave"] = rng.integers(0, 8, n); k["angle"] = rng.uniform(0, 360, n)
+        node = which % n_nodes
+        order = np.argsort(node, kind="stable")
+        ids, start = np.unique(node[order], return_index=True)
+        fv = (ids.astype(np.uint32), np.r_[start, n].astype(np.int32), order.astype(np.int32))
+        return dict(desc=d, keys=k, has_mp=rng.random(n) < 0.3, uright=np.where(rng.random(n) < 0.5, rng.uniform(0, 1000, n), -1).astype(np.float32), fv=fv)
+
+    kf1, kf2 = frame(n1), frame(n2)
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32); sg = (sf * sf).astype(np.float32)
+    for trial in range(3):
+        T1w = rot_pose(rng, 1.0, 0.05); T2w = rot_pose(rng, 1.0, 0.05)
+        T1w[:4] /= np.linalg.norm(T1w[:4]); T2w[:4] /= np.linalg.norm(T2w[:4])
+        for only_stereo, coarse, ori in ((0, 1, 1), (1, 1, 0), (0, 0, 1), (1, 0, 1)):
+            n_ref, m_ref, F12, ep = oracle.ref_search_for_triangulation(T1w, T2w, TD.CAM, kf1, kf2, sf, sg, only_stereo, coarse, ori)
+            n_or, m_or = oracle.search_for_triangulation(kf1, kf2, F12, ep, sf, sg, only_stereo, coarse, ori)
+            assert n_ref == n_or and (m_ref == m_or).all(), (trial, only_stereo, coarse, ori, n_ref, n_or)
+            if coarse:
+                assert n_ref > 20
+
+
+def test_fuse(seq_frames):
+    """The reference's own ORBmatcher::Fuse (search + bookkeeping) vs the restated search: a point is fused into slot best_idx exactly
+    when the restatement's best Hamming distance is <= TH_LOW (src/ORBmatcher.cc:1306-1325)."""
+    seq, frames, sf = seq_frames
+    rng = np.random.default_rng(22)
+    xw, desc, normal, mn, mx = TD.local_map([frames[0]], [seq.pose(0)], sf, rng)
+    kf = frames[1]
+    fv = oracle.FrameView(*TD.frame_view_args(kf, sf))
+    for trial, th in enumerate((3.0, 4.0)):
+        pose = seq.pose(1).copy()
+        if trial:
+            pose = (pose + np.r_[rot_pose(rng, 0.0, 0.005)[:4] * [1, 1, 1, 0], rng.normal(0, 0.1, 3)]).astype(np.float32)
+            pose[:4] /= np.linalg.norm(pose[:4])
+        valid = (rng.random(len(xw)) < 0.9).astype(np.uint8)
+        nf, bi_ref, Ow = oracle.ref_fuse(fv, pose, valid, xw, normal, mn, mx, desc, th)
+        bi, bd = oracle.fuse_search(fv, pose, Ow, valid, xw, normal, mn, mx, desc, th)
+        exp = np.where(bd <= 50, bi, -1)
+        assert (exp == bi_ref).all(), (trial, int((exp != bi_ref).sum()))
+        assert nf == int((exp >= 0).sum()) and nf > 100
+
+
+@pytest.mark.parametrize("seed,kw", [(1, dict()), (2, dict(n_kf=12, n_fixed=3, n_points=900, outlier_frac=0.05)), (3, dict(n_kf=5, n_fixed=1, n_points=200, stereo_frac=1.0)),
+                                     (4, dict(n_kf=6, n_fixed=2, n_points=300, stereo_frac=0.0))])
+def test_local_bundle_adjustment(seed, kw):
+    """Optimizer::LocalBundleAdjustment's own body (src/Optimizer.cc:1116-1499) on the reference's g2o (Schur-complement block solver,
+    LM, EdgeSE3ProjectXYZ / EdgeStereoSE3ProjectXYZ, Huber) vs the dense restatement.  The reference solves the reduced system with a
+    sparse Cholesky (stood in for by the dense LDLT here) and walks the edges in map order, so the comparison is tolerance-based:
+    poses and points to 1e-4, identical erase decisions."""
+    import ba_data as D
+    p = D.make_problem(seed, **kw)
+    (po0, pt0, er0, it0, _), (po1, pt1, er1, _, _) = both(oracle.local_bundle_adjustment, *D.args(p))
+    assert np.abs(po0 - po1).max() < 1e-4, np.abs(po0 - po1).max()
+    assert np.abs(pt0 - pt1).max() < 1e-4, np.abs(pt0 - pt1).max()
+    assert (er0 == er1).all(), int((er0 != er1).sum())
+    assert np.array_equal(po1[p["pose_fixed"] != 0], p["poses"][p["pose_fixed"] != 0]) or np.abs(po1[p["pose_fixed"] != 0] - p["poses"][p["pose_fixed"] != 0]).max() < 1e-6

@@ -1,0 +1,20 @@
+#!/bin/bash
+# Round-2 measurement pass (run under gpurun, 1 GPU): GPU parity tests, bench line, ncu launch list of the same command, and ONE
+# `ncu --set full` capture per frame-construction / chain kernel.  Outputs under gpurun_out/r02/<tag>/ ; summarise here with
+# tools/ncu_report_all.py and copy what should be judged into profiles/.
+#   gpurun --timeout 1500 -- 'bash tools/profile_r02.sh <tag>'
+set -u
+tag=${1:-a}
+out=gpurun_out/r02/$tag; mkdir -p "$out"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$out/gpu.txt"; nproc >> "$out/gpu.txt"
+if [ "${SKIP_TESTS:-0}" != "1" ]; then
+  timeout 1200 python -m pytest tests -x -q -m gpu > "$out/pytest_gpu.log" 2>&1; echo "pytest exit $? ($(tail -1 "$out/pytest_gpu.log"))"
+fi
+timeout 600 python bench.py --steps 20 --warmup 3 > "$out/bench.json" 2> "$out/bench.err"; echo "bench exit $?"; tail -c 400 "$out/bench.json"; echo
+PROF="python bench.py --steps 2 --warmup 3 --batch 32 --no-cpu-baseline --no-bow --multi-sequences 0"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 500 --csv --log-file "$out/launches.csv" $PROF > "$out/launches_run.log" 2>&1
+echo "launch list exit $?"
+python tools/summarize_ncu_launches.py "$out/launches.csv" > "$out/launches_summary.csv" 2>/dev/null; head -20 "$out/launches_summary.csv"
+K='regex:(resize_level|fast_|cand_|blur_level|quadtree_kernel|sel_pack|describe|depth_project|depth_resolve|depth_gather|grid_build|search_last_collect|resolve_kernel|pose_optimize|chain_prep|fused_)'
+timeout 900 ncu --set full --clock-control none --import-source on -k "$K" -s 60 -c 70 -o "$out/all_kernels" -f $PROF > "$out/ncu_full.log" 2>&1
+echo "ncu full exit $?"; ls -la "$out"

@@ -307,6 +307,34 @@ int rgbl_resident_track(rgbl_ctx* ctx, const float pose0[7], float fx, float fy,
 int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono);
 int rgbl_resident_track_end(rgbl_ctx* ctx, float* poses_out, int* n_matches, int* n_inliers);
 
+/* The full per-frame tracking path of the reference for an RGB-L frame, and batches that continue one sequence:
+ *   TrackWithMotionModel (src/Tracking.cc:2888-2981): SearchByProjection(frame t, frame t-1, th_last) -> PoseOptimization -> outliers
+ *     discarded;
+ *   TrackLocalMap (src/Tracking.cc:2983-3050 with SearchLocalPoints :3377-3460), when local_map_frames = K > 0: Frame::isInFrustum over
+ *     the local map, SearchByProjection(frame t, local points, th_local, nn_ratio_local) -> PoseOptimization on all map points.  The
+ *     local map of this harness = the LiDAR-depth keypoints of the K frames before t-1, unprojected with their final poses, with
+ *     MapPoint::UpdateNormalAndDepth's normal / scale-invariance distances for one observation (src/MapPoint.cc:437-490); it lives on
+ *     the device as a ring (slot = frame counter mod K) and its points are searched in ring order.
+ * continue_sequence != 0: frame 0 of this batch is tracked against the LAST frame of the previous chain of this context (keypoints,
+ *   pose and local map stay in HBM), so consecutive batches form one sequence and every frame of the batch is tracked; pose0 is
+ *   ignored.  continue_sequence == 0 starts a sequence: frame 0 gets pose0 and the local map is emptied.
+ * th_last: 15 (7 for System::STEREO, src/Tracking.cc:2913-2917); th_local: 3 for RGB-L / RGB-D, else 1 (:3432-3436); nn_ratio_local 0.8. */
+typedef struct rgbl_chain_params {
+    float pose0[7];
+    float fx, fy, cx, cy, bf;
+    float th_last;
+    int mono;
+    int continue_sequence;
+    int local_map_frames;
+    float th_local;
+    float nn_ratio_local;
+} rgbl_chain_params;
+int rgbl_resident_track_begin2(rgbl_ctx* ctx, const rgbl_chain_params* prm);
+/* as rgbl_resident_track_end, plus (nullable) per frame: matches of the local search, inliers after the first PoseOptimization;
+ * n_inliers = inliers of the frame's last PoseOptimization.  Fails with RGBL_E_CAPACITY when the frame construction of the tracked
+ * batch overflowed a capacity (the keypoint sets were truncated) or a matcher candidate list overflowed.                        */
+int rgbl_resident_track_end2(rgbl_ctx* ctx, float* poses_out, int* n_matches, int* n_inliers, int* n_local_matches, int* n_inliers_first);
+
 /* Keypoint distribution (DistributeOctTree) runs on the device by default (one CTA per (frame, level)); on != 0
  * selects the host implementation instead (also: environment RGBL_HOST_QUADTREE=1).  Both are exact.           */
 int rgbl_set_host_quadtree(rgbl_ctx* ctx, int on);

@@ -33,7 +33,8 @@ static void release(Ctx* c) {
                    c->qt_scr.node_b, c->qt_scr.scan, c->qt_scr.quad, c->d_sel_lvl, c->d_n_sel_lvl, c->d_lvl_region};
     for (void* p : dev) if (p) cudaFree(p);
     c->trk.release();
-    void* host[] = {c->h_scalars, c->h_level_cnt, c->h_frame_total, c->h_overflow, c->h_n_sel, c->h_n_pts, c->h_dense, c->h_sel};
+    for (cudaEvent_t& e : c->chain_tev) if (e) cudaEventDestroy(e);
+    void* host[] = {c->h_chain_ovf, c->h_scalars, c->h_level_cnt, c->h_frame_total, c->h_overflow, c->h_n_sel, c->h_n_pts, c->h_dense, c->h_sel};
     for (void* p : host) if (p) cudaFreeHost(p);
     for (int i = 0; i < kNumStages; ++i) { if (c->ev_b[i]) cudaEventDestroy(c->ev_b[i]); if (c->ev_e[i]) cudaEventDestroy(c->ev_e[i]); }
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -167,6 +168,10 @@ static int create(const rgbl_config* cfg, Ctx** out) {
     c->scratch_bytes = (size_t)(cfg->width + 2 * kEdgeThreshold + 64) * (cfg->height + 2 * kEdgeThreshold);
     CUF(dmalloc(&c->d_scratch, c->scratch_bytes));
     CUF(hmalloc(&c->h_scalars, 16));
+    CUF(hmalloc(&c->h_chain_ovf, 4));
+    for (int i = 0; i < 4; ++i) c->h_chain_ovf[i] = 0;
+    c->chain_timing_on = std::getenv("RGBL_CHAIN_TIMING") != nullptr;
+    c->chain_graphs_on = !(std::getenv("RGBL_CHAIN_GRAPH") && std::getenv("RGBL_CHAIN_GRAPH")[0] == '0');
     CUF(hmalloc(&c->h_level_cnt, (size_t)B * RGBL_MAX_LEVELS));
     CUF(hmalloc(&c->h_frame_total, (size_t)B));
     CUF(hmalloc(&c->h_overflow, 4));

@@ -13,12 +13,13 @@
 
 namespace rgbl {
 
-static unsigned long long g_scratch_generation = 1;      // bumped by every reallocation: cached chain graphs hold raw pointers
+// every reallocation of tracking scratch bumps the owning context's generation: cached chain graphs hold raw pointers
+static thread_local unsigned long long* g_generation_sink = nullptr;
 
 template <class T>
 static bool grow(T** p, size_t* cap, size_t need) {
     if (need <= *cap) return true;
-    ++g_scratch_generation;
+    if (g_generation_sink) ++*g_generation_sink;
     if (*p) cudaFree(*p);
     *p = nullptr;
     const size_t n = need + need / 4 + 64;
@@ -27,7 +28,7 @@ static bool grow(T** p, size_t* cap, size_t need) {
     return true;
 }
 
-#define GROW(ptr, capvar, need) do { if (!grow(&(ptr), &(capvar), (size_t)(need))) { c->err = "cudaMalloc failed (tracking scratch)"; return RGBL_E_CUDA; } } while (0)
+#define GROW(ptr, capvar, need) do { g_generation_sink = &c->scratch_generation; if (!grow(&(ptr), &(capvar), (size_t)(need))) { c->err = "cudaMalloc failed (tracking scratch)"; return RGBL_E_CUDA; } } while (0)
 
 static int ensure_frame(Ctx* c, int n_frame) {
     TrackBufs& t = c->trk;
@@ -243,7 +244,7 @@ int rgbl_search_by_projection_local(rgbl_ctx* ctx, const rgbl_frame_view* cur, i
     prm.use_factor = (th != 1.0) ? 1 : 0;                                         // bFactor, src/ORBmatcher.cc:47
     // a second-best beyond TH_HIGH / nnratio can never reject: best <= TH_HIGH < nnratio * second
     prm.keep_max = std::min(256, (int)std::floor((float)100 / nn_ratio) + 1);
-    LocalPointsDev lp{n, t.q_u8a, t.q_f[0], t.q_f[1], t.q_f[2], t.q_f[3], t.q_i, t.q_f[4], t.q_desc, t.q_u8b};
+    LocalPointsDev lp{n, nullptr, t.q_u8a, t.q_f[0], t.q_f[1], t.q_f[2], t.q_f[3], t.q_i, t.q_f[4], t.q_desc, t.q_u8b};
     if (n == 0) { CU(cudaMemsetAsync(t.match, 0xff, (size_t)std::max(cur->n, 1) * sizeof(int), c->st)); CU(cudaMemsetAsync(t.scalars + 1, 0, 2 * sizeof(int), c->st)); }
     launch_search_local(c->st, f, t.cell_start, t.csr_idx, lp, prm, scratch(c), t.state, t.match, t.scalars + 1);
     return finish_search(c, cur->n, match, n_matches);
@@ -458,22 +459,33 @@ int rgbl_search_by_projection_reloc(rgbl_ctx* ctx, const rgbl_frame_view* cur, c
     return finish_search(c, cur->n, match, n_matches);
 }
 
+}  // extern "C" (re-opened below)
+
 /* Resident tracking chain over the frames of the last rgbl_resident_process / rgbl_frame_rgbl_batch call, entirely on the
- * device (no host round trip per frame): for t = 1..n-1  SearchByProjection(frame t, frame t-1) -> PoseOptimization, with
- * every LiDAR-depth keypoint of frame t-1 acting as a map point (Frame::UnprojectStereo with the estimated pose of t-1)
- * and the constant-pose motion model.  poses_out[n][7], n_matches[n], n_inliers[n] (entry 0 = pose0, 0, 0).           */
+ * device (no host round trip per frame).  Per frame t (the reference's Tracking::Track for an RGB-L frame, src/Tracking.cc):
+ *   TrackWithMotionModel (:2888-2981): SearchByProjection(frame t, frame t-1, th_last) -> PoseOptimization -> discard outliers,
+ *     every LiDAR-depth keypoint of frame t-1 acting as a map point (Frame::UnprojectStereo with the final pose of t-1), constant-pose
+ *     motion model;
+ *   TrackLocalMap (:2983-3050, SearchLocalPoints :3377-3460), when local_map_frames = K > 0: isInFrustum over the local map (the
+ *     points of the K frames before t-1), SearchByProjection(frame t, local points, th_local), PoseOptimization on all map points.
+ * continue_sequence: frame 0 of the batch is tracked against the last frame of the previous chain of this context (its keypoints,
+ * pose and the local map stay on the device), so consecutive batches form ONE sequence.                                        */
 // The chain is asynchronous: _begin snapshots the batch's frame outputs into chain-owned buffers (a ~5 MB device copy),
 // enqueues the whole per-frame chain on the context's high-priority tracking stream and returns; _end waits for it and
 // hands the poses out.  Between the two calls the caller may run rgbl_resident_process on the NEXT batch: its kernels
 // fill the SMs the single-CTA chain kernels leave idle (the chain is a latency-bound sequence of small launches).
-int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono) {
-    Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    if (!c) return RGBL_E_INVALID;
-    if (!pose0) { c->err = "null argument"; return RGBL_E_INVALID; }
+static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
+    const rgbl_chain_params P = cp_;
+    const float fx = P.fx, fy = P.fy, cx = P.cx, cy = P.cy, bf = P.bf, th = P.th_last;
+    const int mono = P.mono, K = std::max(P.local_map_frames, 0);
     if (c->chain_pending >= 2) { c->err = "two tracking chains are already queued: call rgbl_resident_track_end first"; return RGBL_E_INVALID; }
     const int nF = c->last_frames, cap = c->cap_kp;
     const int slot = (c->chain_head + c->chain_pending) & 1;
     if (nF < 1) { c->err = "nothing processed"; return RGBL_E_INVALID; }
+    if (K > 16) { c->err = "local_map_frames > 16"; return RGBL_E_INVALID; }
+    const bool cont = P.continue_sequence != 0;
+    if (cont && !c->chain_has_carry) { c->err = "continue_sequence without a previous chain on this context"; return RGBL_E_INVALID; }
+    if (cont && (c->carry_K != K || c->carry_cap != cap)) { c->err = "continue_sequence: local_map_frames / keypoint capacity differ from the previous chain"; return RGBL_E_INVALID; }
     CU(cudaSetDevice(c->cfg.device));
     if (!c->st_trk) {
         int lo = 0, hi = 0;
@@ -485,6 +497,7 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
             CU(cudaEventCreateWithFlags(&c->ev_chain_done[i], cudaEventDisableTiming));
         }
     }
+    const size_t n_counts = (size_t)4 * nF + 8;          // n_matches | n_inliers | n_local_matches | n_inliers_first | ne, ne2, flags[2], overflow, nq
     if (c->h_chain_cap < (size_t)nF) {
         if (c->chain_pending) { c->err = "batch size grew while a chain is in flight"; return RGBL_E_INVALID; }
         if (c->h_chain_f) cudaFreeHost(c->h_chain_f);
@@ -492,17 +505,29 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
         c->h_chain_f = nullptr; c->h_chain_i = nullptr; c->h_chain_cap = 0;
         const size_t capF = (size_t)std::max(nF, c->cfg.max_batch);
         CU(cudaMallocHost(&c->h_chain_f, 2 * (7 + capF * 7) * sizeof(float)));
-        CU(cudaMallocHost(&c->h_chain_i, 2 * (2 * capF + 4) * sizeof(int)));
+        CU(cudaMallocHost(&c->h_chain_i, 2 * (4 * capF + 8) * sizeof(int)));
         c->h_chain_cap = capF;
     }
     int rc = ensure_frame(c, cap); if (rc) return rc;
-    rc = ensure_queries(c, cap); if (rc) return rc;
+    const int n_lq = std::max(K * cap, 1);                // local-search queries (compacted, at most every ring point)
+    rc = ensure_queries(c, std::max(cap, n_lq)); if (rc) return rc;
     TrackBufs& t = c->trk;
     const size_t tot = (size_t)nF * cap;
     GROW(t.pose_work, t.cap_pose_work, (size_t)cap * 3);
-    GROW(t.ch_poses, t.cap_ch_poses, (size_t)nF * 7); GROW(t.ch_counts, t.cap_ch_counts, (size_t)nF * 2 + 4);
+    GROW(t.ch_poses, t.cap_ch_poses, (size_t)nF * 7 + 7); GROW(t.ch_counts, t.cap_ch_counts, n_counts);
     GROW(t.e_xw, t.cap_e_xw, (size_t)cap * 3); GROW(t.e_obs, t.cap_e_obs, (size_t)cap * 3); GROW(t.e_info, t.cap_e_info, cap);
     GROW(t.e_st, t.cap_e_st, cap); GROW(t.e_lvl, t.cap_e_lvl, cap); GROW(t.e_out, t.cap_e_out, cap); GROW(t.e_idx, t.cap_e_idx, cap);
+    // carried last frame of the sequence + the local map ring (persist across chains of this context)
+    GROW(t.c_kps, t.cap_c_kps, cap); GROW(t.c_desc, t.cap_c_desc, (size_t)cap * 32); GROW(t.c_depth, t.cap_c_depth, cap);
+    GROW(t.c_misc, t.cap_c_misc, 16);                     // int n_sel | float pose[7] (as raw 32-bit words) | ring count
+    if (K > 0) {
+        const size_t nr = (size_t)K * cap;
+        if (cont && (t.cap_r_valid < nr)) { c->err = "local map ring missing"; return RGBL_E_INVALID; }
+        GROW(t.r_valid, t.cap_r_valid, nr); GROW(t.r_xw, t.cap_r_xw, nr * 3); GROW(t.r_normal, t.cap_r_normal, nr * 3);
+        GROW(t.r_min, t.cap_r_min, nr); GROW(t.r_max, t.cap_r_max, nr); GROW(t.r_desc, t.cap_r_desc, nr * 32);
+        GROW(t.lq_u8, t.cap_lq_u8, 2 * (size_t)n_lq); GROW(t.lq_f, t.cap_lq_f, 5 * (size_t)n_lq); GROW(t.lq_i, t.cap_lq_i, 2 * (size_t)n_lq);
+        GROW(t.lq_desc, t.cap_lq_desc, (size_t)n_lq * 32); GROW(t.match_local, t.cap_match_local, cap);
+    }
     // per-slot buffers: twice the size, the slot picks its half (sizes are those of the context's full batch so that the halves
     // never move while a chain is in flight)
     const size_t tot_full = (size_t)std::max(nF, c->cfg.max_batch) * cap, nF_full = (size_t)std::max(nF, c->cfg.max_batch);
@@ -516,7 +541,7 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
     float* s_depth = t.s_depth + slot * tot_full; float* s_uright = t.s_uright + slot * tot_full; int* s_nsel = t.s_nsel + slot * nF_full;
     int* b_cell_start = t.b_cell_start + slot * cs_full; int* b_csr_idx = t.b_csr_idx + slot * tot_full; int* b_kp_cell = t.b_kp_cell + slot * tot_full;
     float* h_f = c->h_chain_f + (size_t)slot * (7 + c->h_chain_cap * 7);
-    int* h_i = c->h_chain_i + (size_t)slot * (2 * c->h_chain_cap + 4);
+    int* h_i = c->h_chain_i + (size_t)slot * (4 * c->h_chain_cap + 8);
 
     // snapshot on the frame-construction stream (ordered after the batch's kernels, before the next batch's)
     CU(cudaMemcpyAsync(s_kps, c->d_kps, tot * sizeof(rgbl_keypoint), cudaMemcpyDeviceToDevice, c->st));
@@ -524,26 +549,38 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
     CU(cudaMemcpyAsync(s_depth, c->d_depth, tot * sizeof(float), cudaMemcpyDeviceToDevice, c->st));
     CU(cudaMemcpyAsync(s_uright, c->d_uright, tot * sizeof(float), cudaMemcpyDeviceToDevice, c->st));
     CU(cudaMemcpyAsync(s_nsel, c->d_n_sel, (size_t)nF * sizeof(int), cudaMemcpyDeviceToDevice, c->st));
+    // the frame-construction overflow flags of THIS batch travel with the chain (checked in _end)
+    CU(cudaMemcpyAsync(c->h_chain_ovf + 2 * slot, c->d_overflow, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CU(cudaEventRecord(c->ev_snap, c->st));
     CU(cudaStreamWaitEvent(c->st_aux, c->ev_snap, 0));      // the aux stream writes depth / uright of the next batch
     cudaStream_t cs = c->st_trk;
     CU(cudaStreamWaitEvent(cs, c->ev_snap, 0));
 
-    for (int i = 0; i < 7; ++i) h_f[i] = pose0[i];
+    for (int i = 0; i < 7; ++i) h_f[i] = P.pose0[i];
     // RGBL_CHAIN_TIMING=1: CUDA events between the launches of the middle frame (warm, in-stream kernel times; stderr at _end)
-    static const bool chain_timing = std::getenv("RGBL_CHAIN_TIMING") != nullptr;
-    static const bool chain_graphs = !(std::getenv("RGBL_CHAIN_GRAPH") && std::getenv("RGBL_CHAIN_GRAPH")[0] == '0');
-    static cudaEvent_t tev[8] = {};
-    if (chain_timing && !tev[0]) for (auto& e : tev) cudaEventCreate(&e);
-    // Everything the chain does on the tracking stream, ~3 launches per frame.  It is captured ONCE per slot into a CUDA graph and
+    const bool chain_timing = c->chain_timing_on;
+    const bool chain_graphs = c->chain_graphs_on;
+    cudaEvent_t* tev = c->chain_tev;
+    if (chain_timing && !tev[0]) for (int i = 0; i < 8; ++i) cudaEventCreate(&tev[i]);
+    int* c_nsel = reinterpret_cast<int*>(t.c_misc);
+    float* c_pose = reinterpret_cast<float*>(t.c_misc) + 1;
+    int* r_count = reinterpret_cast<int*>(t.c_misc) + 8;
+    int n_launches = 0;
+    // Everything the chain does on the tracking stream.  It is captured ONCE per slot into a CUDA graph and
     // replayed: the launch commands then live in device memory, so the dependent-kernel sequence no longer fetches a command
     // packet from the host over PCIe per launch (which the concurrent H2D uploads of the next batch were slowing down) and
-    // _begin costs one graph launch instead of ~100 kernel launches on the host.
+    // _begin costs one graph launch instead of hundreds of kernel launches on the host.
     auto enqueue_chain = [&]() -> int {
-        CU(cudaMemcpyAsync(t.ch_poses, h_f, 7 * sizeof(float), cudaMemcpyHostToDevice, cs));
-        CU(cudaMemsetAsync(t.ch_counts, 0, ((size_t)nF * 2 + 4) * sizeof(int), cs));
-        int* d_nm = t.ch_counts; int* d_ni = t.ch_counts + nF; int* d_ne = t.ch_counts + 2 * nF; int* d_flags = t.ch_counts + 2 * nF + 1;
-        int* d_ovf = t.ch_counts + 2 * nF + 2;
+        n_launches = 0;
+        float* poses = t.ch_poses;                 // frame k -> poses + 7 k
+        float* pose_tmp = t.ch_poses + 7 * (size_t)nF;      // pose after TrackWithMotionModel (input of the second PoseOptimization)
+        CU(cudaMemsetAsync(t.ch_counts, 0, n_counts * sizeof(int), cs));
+        if (!cont) {
+            CU(cudaMemcpyAsync(poses, h_f, 7 * sizeof(float), cudaMemcpyHostToDevice, cs));
+            if (K > 0) { CU(cudaMemsetAsync(t.r_valid, 0, (size_t)K * cap, cs)); CU(cudaMemsetAsync(r_count, 0, sizeof(int), cs)); }
+        }
+        int* d_nm = t.ch_counts; int* d_ni = t.ch_counts + nF; int* d_nml = t.ch_counts + 2 * nF; int* d_ni1 = t.ch_counts + 3 * nF;
+        int* d_ne = t.ch_counts + 4 * nF; int* d_ne2 = d_ne + 1; int* d_flags = d_ne + 2; int* d_ovf = d_ne + 4; int* d_nq = d_ne + 5;
         FrameDev f{};
         f.min_x = 0.f; f.max_x = (float)c->cfg.width; f.min_y = 0.f; f.max_y = (float)c->cfg.height;      // k1 == 0: image bounds
         f.inv_w = static_cast<float>(kGridCols) / static_cast<float>(f.max_x - f.min_x);
@@ -556,49 +593,87 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
         ms.overflow = d_ovf;
         // the 64x48 grids do not depend on the poses: all frames in one launch (one CTA per frame)
         f.n = s_nsel; f.keys = s_kps;
-        launch_grid_build_batch(cs, f, nF, cap, b_cell_start, b_csr_idx, b_kp_cell);
-            // unprojection of frame j's keypoints (map points of the search in frame j + 1)
+        launch_grid_build_batch(cs, f, nF, cap, b_cell_start, b_csr_idx, b_kp_cell); ++n_launches;
+        // unprojection of frame j's keypoints (map points of the search in frame j + 1); j == -1: the carried frame
         auto prep_of = [&](int j) {
             ChainPrepDev cp{};
-            cp.kps = s_kps + (size_t)j * cap; cp.depth = s_depth + (size_t)j * cap; cp.n_ptr = s_nsel + j;
+            if (j < 0) { cp.kps = t.c_kps; cp.depth = t.c_depth; cp.n_ptr = c_nsel; }
+            else { cp.kps = s_kps + (size_t)j * cap; cp.depth = s_depth + (size_t)j * cap; cp.n_ptr = s_nsel + j; }
             cp.fx = f.fx; cp.fy = f.fy; cp.cx = f.cx; cp.cy = f.cy; cp.mb = f.mb; cp.mono = mono; cp.cap = cap;
             cp.valid = t.q_u8a; cp.xw = t.q_f3a; cp.octave = t.q_i; cp.angle = t.q_f[0]; cp.obs_pos = t.q_u8b; cp.flags = d_flags; cp.state_clear = t.state;
             return cp;
         };
-        for (int k = 1; k < nF; ++k) {
+        LocalRingDev ring{K, cap, t.r_valid, t.r_xw, t.r_normal, t.r_min, t.r_max, t.r_desc, r_count};
+        LocalQueriesDev lq{};
+        if (K > 0) {
+            lq.cap = n_lq; lq.n = d_nq; lq.in_view = t.lq_u8; lq.obs_pos = t.lq_u8 + n_lq;
+            lq.proj_x = t.lq_f; lq.proj_y = t.lq_f + n_lq; lq.proj_xr = t.lq_f + 2 * (size_t)n_lq; lq.depth = t.lq_f + 3 * (size_t)n_lq;
+            lq.view_cos = t.lq_f + 4 * (size_t)n_lq; lq.level = t.lq_i; lq.src = t.lq_i + n_lq; lq.desc = t.lq_desc;
+        }
+        const int k0 = cont ? 0 : 1;
+        for (int k = k0; k < nF; ++k) {
             const bool tm = chain_timing && k == std::max(1, nF / 2);
-            const size_t lo = (size_t)(k - 1) * cap, cu = (size_t)k * cap;
-            const float* last_pose = t.ch_poses + 7 * (k - 1);
+            const size_t cu = (size_t)k * cap;
+            const float* last_pose = (k == 0) ? c_pose : poses + 7 * (size_t)(k - 1);
+            const uint8_t* last_desc = (k == 0) ? t.c_desc : s_desc + (size_t)(k - 1) * cap * 32;
             if (tm) cudaEventRecord(tev[0], cs);
-            if (k == 1) launch_chain_prep(cs, prep_of(0), last_pose, last_pose);          // later frames: prepared by the previous pose kernel
+            if (k == k0) { launch_chain_prep(cs, prep_of(k - 1), last_pose, last_pose); ++n_launches; }   // later frames: prepared by the previous pose kernel
             f.n = s_nsel + k; f.keys = s_kps + cu; f.uright = s_uright + cu; f.desc = s_desc + cu * 32;
             const int* cell_start = b_cell_start + (size_t)k * (kGridCols * kGridRows + 1);
             const int* csr_idx = b_csr_idx + cu;
-            if (tm) { cudaEventRecord(tev[1], cs); cudaEventRecord(tev[2], cs); }
+            if (tm) cudaEventRecord(tev[1], cs);
             SearchLastParams prm{};
             prm.th = th; prm.check_orientation = 1; prm.cur_pose_dev = last_pose; prm.flags_dev = d_flags;
-            LastFrameDev lf{cap, t.q_u8a, t.q_f3a, s_desc + lo * 32, t.q_i, t.q_f[0], t.q_u8b};
+            LastFrameDev lf{cap, t.q_u8a, t.q_f3a, last_desc, t.q_i, t.q_f[0], t.q_u8b};
             const ChainEdgesOut eo{t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne};
-            launch_search_last(cs, f, cell_start, csr_idx, lf, prm, ms, t.state, t.match, d_nm + k, &eo);     // + edges of the matches
-            if (tm) { cudaEventRecord(tev[3], cs); cudaEventRecord(tev[4], cs); }
+            launch_search_last(cs, f, cell_start, csr_idx, lf, prm, ms, t.state, t.match, d_nm + k, &eo); n_launches += 2;   // + edges of the matches
+            if (tm) cudaEventRecord(tev[2], cs);
             PoseProblemDev p{};
             p.n = 0; p.n_dev = d_ne; p.pose_in_dev = last_pose;
             p.xw = t.e_xw; p.obs = t.e_obs; p.inv_sigma2 = t.e_info; p.stereo = t.e_st;
             p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf;
             const ChainPrepDev nxt = prep_of(k);
-            launch_pose_optimize(cs, p, t.pose_work, t.e_lvl, t.e_out, t.ch_poses + 7 * k, d_ni + k, (k + 1 < nF) ? &nxt : nullptr);
-            if (tm) cudaEventRecord(tev[5], cs);
+            if (K == 0) {
+                launch_pose_optimize(cs, p, t.pose_work, t.e_lvl, t.e_out, poses + 7 * (size_t)k, d_ni + k, (k + 1 < nF) ? &nxt : nullptr); ++n_launches;
+                if (tm) { cudaEventRecord(tev[3], cs); cudaEventRecord(tev[4], cs); cudaEventRecord(tev[5], cs); cudaEventRecord(tev[6], cs); }
+            } else {
+                launch_pose_optimize(cs, p, t.pose_work, t.e_lvl, t.e_out, pose_tmp, d_ni1 + k, nullptr); ++n_launches;
+                if (tm) cudaEventRecord(tev[3], cs);
+                // TrackLocalMap: outlier discard + isInFrustum + ordered compaction, local search, edges of all map points, second optimisation
+                launch_tlm_prepare(cs, f, pose_tmp, ring, 0.5f, d_ne, t.e_idx, t.e_out, t.state, t.match, lq); ++n_launches;
+                LocalPointsDev lp{n_lq, d_nq, lq.in_view, lq.proj_x, lq.proj_y, lq.proj_xr, lq.depth, lq.level, lq.view_cos, lq.desc, lq.obs_pos};
+                SearchLocalParams sl{};
+                sl.th = P.th_local; sl.nn_ratio = P.nn_ratio_local; sl.th_far = 0.f; sl.use_factor = (P.th_local != 1.0f) ? 1 : 0; sl.far_points = 0; sl.keep_max = std::min(256, (int)std::floor((float)100 / P.nn_ratio_local) + 1);
+                launch_search_local(cs, f, cell_start, csr_idx, lp, sl, ms, t.state, t.match_local, d_nml + k); n_launches += 2;
+                if (tm) cudaEventRecord(tev[4], cs);
+                const ChainEdgesOut eo2{t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne2};
+                launch_tlm_edges(cs, f, t.match, t.q_f3a, t.match_local, lq.src, ring, eo2, d_nml + k, cap, t.q_u8a, t.q_i, last_desc, last_pose); ++n_launches;
+                if (tm) cudaEventRecord(tev[5], cs);
+                PoseProblemDev p2 = p;
+                p2.n_dev = d_ne2; p2.pose_in_dev = pose_tmp;
+                launch_pose_optimize(cs, p2, t.pose_work, t.e_lvl, t.e_out, poses + 7 * (size_t)k, d_ni + k, (k + 1 < nF) ? &nxt : nullptr); ++n_launches;
+                if (tm) cudaEventRecord(tev[6], cs);
+            }
         }
+        // carry the last frame of this batch (keypoints, depths, descriptors, pose) for a continuing chain
+        const size_t lo = (size_t)(nF - 1) * cap;
+        CU(cudaMemcpyAsync(t.c_kps, s_kps + lo, (size_t)cap * sizeof(rgbl_keypoint), cudaMemcpyDeviceToDevice, cs));
+        CU(cudaMemcpyAsync(t.c_desc, s_desc + lo * 32, (size_t)cap * 32, cudaMemcpyDeviceToDevice, cs));
+        CU(cudaMemcpyAsync(t.c_depth, s_depth + lo, (size_t)cap * sizeof(float), cudaMemcpyDeviceToDevice, cs));
+        CU(cudaMemcpyAsync(c_nsel, s_nsel + (nF - 1), sizeof(int), cudaMemcpyDeviceToDevice, cs));
+        CU(cudaMemcpyAsync(c_pose, poses + 7 * (size_t)(nF - 1), 7 * sizeof(float), cudaMemcpyDeviceToDevice, cs));
         if (chain_timing) c->chain_timing_ev = tev;
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(h_f + 7, t.ch_poses, (size_t)nF * 7 * sizeof(float), cudaMemcpyDeviceToHost, cs));
-        CU(cudaMemcpyAsync(h_i, t.ch_counts, ((size_t)nF * 2 + 4) * sizeof(int), cudaMemcpyDeviceToHost, cs));
+        CU(cudaMemcpyAsync(h_f + 7, poses, (size_t)nF * 7 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        CU(cudaMemcpyAsync(h_i, t.ch_counts, n_counts * sizeof(int), cudaMemcpyDeviceToHost, cs));
         return RGBL_OK;
     };
     // stage timing events stay outside the graph (events recorded by graph nodes cannot be used for cudaEventElapsedTime)
     if (c->prof_on) CU(cudaEventRecord(c->ev_chain_b[slot], cs));
     if (chain_graphs && !chain_timing) {
-        Ctx::ChainGraphKey key{nF, cap, mono, 0, th, fx, fy, cx, cy, bf, g_scratch_generation};
+        Ctx::ChainGraphKey key{};
+        key.nF = nF; key.cap = cap; key.mono = mono; key.cont = cont ? 1 : 0; key.K = K; key.th = th; key.th_local = P.th_local; key.nn_local = P.nn_ratio_local;
+        key.fx = fx; key.fy = fy; key.cx = cx; key.cy = cy; key.bf = bf; key.generation = c->scratch_generation;
         if (!c->chain_exec[slot] || std::memcmp(&key, &c->chain_key[slot], sizeof(key)) != 0) {
             if (c->chain_exec[slot]) { cudaGraphExecDestroy(c->chain_exec[slot]); c->chain_exec[slot] = nullptr; }
             prepare_match_kernels();
@@ -616,7 +691,9 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
             cudaGraphDestroy(graph);
             if (e_inst != cudaSuccess) { c->chain_exec[slot] = nullptr; c->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e_inst); return RGBL_E_CUDA; }
             c->chain_key[slot] = key;
+            c->chain_graph_launches[slot] = n_launches;
         }
+        n_launches = c->chain_graph_launches[slot];
         CU(cudaGraphLaunch(c->chain_exec[slot], cs));
     } else {
         const int rc_q = enqueue_chain(); if (rc_q) return rc_q;
@@ -624,12 +701,34 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
     if (c->prof_on) CU(cudaEventRecord(c->ev_chain_e[slot], cs));
     CU(cudaEventRecord(c->ev_chain_done[slot], cs));
     c->chain_frames[slot] = nF;
-    c->chain_launches[slot] = 2 + 3 * (nF - 1);
+    c->chain_first[slot] = cont ? 0 : 1;
+    c->chain_launches[slot] = n_launches;
     c->chain_pending += 1;
+    c->chain_has_carry = true; c->carry_K = K; c->carry_cap = cap;
     return RGBL_OK;
 }
 
-int rgbl_resident_track_end(rgbl_ctx* ctx, float* poses_out, int* n_matches, int* n_inliers) {
+extern "C" {
+
+int rgbl_resident_track_begin2(rgbl_ctx* ctx, const rgbl_chain_params* prm) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!prm) { c->err = "null argument"; return RGBL_E_INVALID; }
+    return chain_begin(c, *prm);
+}
+
+int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!pose0) { c->err = "null argument"; return RGBL_E_INVALID; }
+    rgbl_chain_params p{};
+    std::memcpy(p.pose0, pose0, 7 * sizeof(float));
+    p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf; p.th_last = th; p.mono = mono;
+    p.continue_sequence = 0; p.local_map_frames = 0; p.th_local = 3.f; p.nn_ratio_local = 0.8f;
+    return chain_begin(c, p);
+}
+
+int rgbl_resident_track_end2(rgbl_ctx* ctx, float* poses_out, int* n_matches, int* n_inliers, int* n_local_matches, int* n_inliers_first) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
     if (!poses_out || !n_matches || !n_inliers) { c->err = "null argument"; return RGBL_E_INVALID; }
@@ -641,17 +740,20 @@ int rgbl_resident_track_end(rgbl_ctx* ctx, float* poses_out, int* n_matches, int
     CU(cudaEventSynchronize(c->ev_chain_done[slot]));            // the oldest chain only: a younger one may still be running
     const int nF = c->chain_frames[slot];
     const float* h_f = c->h_chain_f + (size_t)slot * (7 + c->h_chain_cap * 7);
-    const int* h_i = c->h_chain_i + (size_t)slot * (2 * c->h_chain_cap + 4);
+    const int* h_i = c->h_chain_i + (size_t)slot * (4 * c->h_chain_cap + 8);
     if (c->chain_timing_ev && c->chain_pending == 0) {
         const cudaEvent_t* e = static_cast<const cudaEvent_t*>(c->chain_timing_ev);
-        const char* names[5] = {"chain_prep (first frame only)", "-", "search_last(collect+resolve+edges)", "-", "pose_optimize"};
-        for (int i = 0; i < 5; ++i) { float ms = 0; if (cudaEventElapsedTime(&ms, e[i], e[i + 1]) == cudaSuccess) std::fprintf(stderr, "[chain timing] %-36s %8.2f us\n", names[i], ms * 1e3f); }
+        const char* names[6] = {"chain_prep (first frame only)", "search_last (collect+resolve+edges)", "pose_optimize #1", "tlm_prepare + search_local", "tlm_edges", "pose_optimize #2"};
+        for (int i = 0; i < 6; ++i) { float ms = 0; if (cudaEventElapsedTime(&ms, e[i], e[i + 1]) == cudaSuccess) std::fprintf(stderr, "[chain timing] %-36s %8.2f us\n", names[i], ms * 1e3f); }
         cudaGetLastError();
     }
     std::memcpy(poses_out, h_f + 7, (size_t)nF * 7 * sizeof(float));
     std::memcpy(n_matches, h_i, (size_t)nF * sizeof(int));
     std::memcpy(n_inliers, h_i + nF, (size_t)nF * sizeof(int));
+    if (n_local_matches) std::memcpy(n_local_matches, h_i + 2 * nF, (size_t)nF * sizeof(int));
+    if (n_inliers_first) std::memcpy(n_inliers_first, h_i + 3 * nF, (size_t)nF * sizeof(int));
     c->total_launches += c->chain_launches[slot];
+    c->chain_tracked_frames += nF - c->chain_first[slot];
     if (c->prof_on) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->ev_chain_b[slot], c->ev_chain_e[slot]) == cudaSuccess) {
@@ -660,8 +762,15 @@ int rgbl_resident_track_end(rgbl_ctx* ctx, float* poses_out, int* n_matches, int
             cudaGetLastError();
         }
     }
-    if (h_i[2 * nF + 2]) { c->err = "matcher candidate list overflow"; return RGBL_E_CAPACITY; }
+    if (h_i[4 * nF + 4]) { c->err = "matcher candidate list overflow"; return RGBL_E_CAPACITY; }
+    // capacity overflow of the frame construction that produced this batch (FAST cell slots, candidate buffer, quad-tree): the chain
+    // ran on truncated keypoint sets
+    if (c->h_chain_ovf[2 * slot] || c->h_chain_ovf[2 * slot + 1]) { c->err = "frame-construction capacity overflow in the batch this chain tracked"; return RGBL_E_CAPACITY; }
     return RGBL_OK;
+}
+
+int rgbl_resident_track_end(rgbl_ctx* ctx, float* poses_out, int* n_matches, int* n_inliers) {
+    return rgbl_resident_track_end2(ctx, poses_out, n_matches, n_inliers, nullptr, nullptr);
 }
 
 int rgbl_resident_track(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono,

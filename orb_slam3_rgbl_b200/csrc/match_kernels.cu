@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) search_local_collect_kernel(FrameDev f, c
                                                                    int list_cap, int* __restrict__ list_n,
                                                                    int* __restrict__ overflow) {
     const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (q >= lp.n) return;
+    if (q >= (lp.n_dev ? min(*lp.n_dev, lp.n) : lp.n)) return;
     int count = 0;
     bool active = lp.in_view[q] != 0;
     if (active && prm.far_points && lp.depth[q] > prm.th_far) active = false;
@@ -799,37 +799,9 @@ __global__ void __launch_bounds__(256) frustum_kernel(FrameDev f, FrustumParams 
                                                       int* __restrict__ level, float* __restrict__ view_cos) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
-    uint8_t iv = 0; float ox = -1.f, oy = -1.f, oxr = 0.f, od = 0.f, ovc = 0.f; int ol = 0;
     const float P[3] = {xw[3 * i], xw[3 * i + 1], xw[3 * i + 2]};
-    float Pc[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-        Pc[r] = __fadd_rn(eig_sum3(__fmul_rn(prm.Rcw[3 * r], P[0]), __fmul_rn(prm.Rcw[3 * r + 1], P[1]), __fmul_rn(prm.Rcw[3 * r + 2], P[2])), prm.tcw[r]);
-    const float pc_dist = sqrtf(eig_sum3(__fmul_rn(Pc[0], Pc[0]), __fmul_rn(Pc[1], Pc[1]), __fmul_rn(Pc[2], Pc[2])));
-    const float z = Pc[2];
-    const float invz = __fdiv_rn(1.0f, z);
-    bool ok = !(z < 0.0f);
-    const float u = __fadd_rn(__fdiv_rn(__fmul_rn(f.fx, Pc[0]), Pc[2]), f.cx);
-    const float v = __fadd_rn(__fdiv_rn(__fmul_rn(f.fy, Pc[1]), Pc[2]), f.cy);
-    if (ok && (u < f.min_x || u > f.max_x)) ok = false;
-    if (ok && (v < f.min_y || v > f.max_y)) ok = false;
-    if (ok) {
-        ox = u; oy = v;
-        const float PO[3] = {__fsub_rn(P[0], prm.Ow[0]), __fsub_rn(P[1], prm.Ow[1]), __fsub_rn(P[2], prm.Ow[2])};
-        const float dist = sqrtf(eig_sum3(__fmul_rn(PO[0], PO[0]), __fmul_rn(PO[1], PO[1]), __fmul_rn(PO[2], PO[2])));
-        if (!(dist < __fmul_rn(0.8f, mf_min[i]) || dist > __fmul_rn(1.2f, mf_max[i]))) {
-            const float* Pn = normal + 3 * i;
-            const float vc = __fdiv_rn(eig_sum3(__fmul_rn(PO[0], Pn[0]), __fmul_rn(PO[1], Pn[1]), __fmul_rn(PO[2], Pn[2])), dist);
-            if (!(vc < prm.cos_limit)) {
-                const float ratio = __fdiv_rn(mf_max[i], dist);
-                const float lg = (float)log((double)ratio);          // correctly-rounded stand-in for glibc logf
-                int ns = (int)ceilf(__fdiv_rn(lg, f.log_scale_factor));
-                if (ns < 0) ns = 0; else if (ns >= f.n_levels) ns = f.n_levels - 1;
-                iv = 1; oxr = __fsub_rn(u, __fmul_rn(f.bf, invz)); od = pc_dist; ol = ns; ovc = vc;
-            }
-        }
-    }
-    in_view[i] = iv; px[i] = ox; py[i] = oy; pxr[i] = oxr; depth[i] = od; level[i] = ol; view_cos[i] = ovc;
+    const FrustumOut o = frustum_point(f, prm, P, normal + 3 * i, mf_min[i], mf_max[i]);
+    in_view[i] = o.in_view; px[i] = o.px; py[i] = o.py; pxr[i] = o.pxr; depth[i] = o.depth; level[i] = o.level; view_cos[i] = o.view_cos;
 }
 
 // ---- SearchByBoW(KF, F): candidates = the F features of the same vocabulary node -----------------------------------
@@ -951,7 +923,7 @@ void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_sta
                          const SearchLocalParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches) {
     if (lp.n <= 0) return;
     search_local_collect_kernel<<<(lp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
-    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(1, lp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lp.obs_pos, nullptr, prm.nn_ratio,
+    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(1, lp.n, lp.n_dev, f, csr_idx, s.lists, s.list_cap, s.list_n, lp.obs_pos, nullptr, prm.nn_ratio,
                                        0, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{});
 }
 

@@ -50,13 +50,24 @@ struct TrackBufs {
     float *s_depth = nullptr, *s_uright = nullptr; size_t cap_s_depth = 0, cap_s_uright = 0;
     int* s_nsel = nullptr; size_t cap_s_nsel = 0;
     int *b_cell_start = nullptr, *b_csr_idx = nullptr, *b_kp_cell = nullptr; size_t cap_b_cell_start = 0, cap_b_csr_idx = 0, cap_b_kp_cell = 0;
+    // state that persists between the chains of one sequence: the carried last frame and the local map ring (chain_kernels.cu)
+    rgbl_keypoint* c_kps = nullptr; size_t cap_c_kps = 0;
+    uint8_t* c_desc = nullptr; size_t cap_c_desc = 0;
+    float* c_depth = nullptr; size_t cap_c_depth = 0;
+    uint32_t* c_misc = nullptr; size_t cap_c_misc = 0;      // n_sel | pose[7] | ring frame counter
+    uint8_t *r_valid = nullptr, *r_desc = nullptr; size_t cap_r_valid = 0, cap_r_desc = 0;
+    float *r_xw = nullptr, *r_normal = nullptr, *r_min = nullptr, *r_max = nullptr; size_t cap_r_xw = 0, cap_r_normal = 0, cap_r_min = 0, cap_r_max = 0;
+    uint8_t *lq_u8 = nullptr, *lq_desc = nullptr; size_t cap_lq_u8 = 0, cap_lq_desc = 0;
+    float* lq_f = nullptr; size_t cap_lq_f = 0;
+    int *lq_i = nullptr, *match_local = nullptr; size_t cap_lq_i = 0, cap_match_local = 0;
     // ComputeBoW
     int *bw_i = nullptr; size_t cap_bw_i = 0;            // f_word | f_node | bow_word | fv_node | fv_start | fv_feature | scratch | counts
     double* bw_d = nullptr; size_t cap_bw_d = 0;         // f_weight | bow_value
     void release() {
         void* all[] = {keys, uright, desc, csr_idx, kp_cell, cell_start, state, match, minq, scalars, lists, list_n, choice, resolved,
                        q_u8a, q_u8b, q_desc, q_f3a, q_f3b, q_f[0], q_f[1], q_f[2], q_f[3], q_f[4], q_f[5], q_f[6], q_i, pose_work, ch_poses, ch_counts, e_xw, e_obs, e_info, e_st, e_lvl, e_out, e_idx,
-                       s_kps, s_desc, s_depth, s_uright, s_nsel, b_cell_start, b_csr_idx, b_kp_cell, bw_i, bw_d};
+                       s_kps, s_desc, s_depth, s_uright, s_nsel, b_cell_start, b_csr_idx, b_kp_cell, bw_i, bw_d,
+                       c_kps, c_desc, c_depth, c_misc, r_valid, r_desc, r_xw, r_normal, r_min, r_max, lq_u8, lq_desc, lq_f, lq_i, match_local};
         for (void* p : all) if (p) cudaFree(p);
     }
 };
@@ -140,12 +151,18 @@ struct Ctx {
     cudaEvent_t ev_snap = nullptr, ev_chain_b[2] = {}, ev_chain_e[2] = {}, ev_chain_done[2] = {};
     int chain_pending = 0;       // chains in flight (0..2)
     int chain_head = 0;          // slot of the oldest chain in flight
-    int chain_frames[2] = {}, chain_launches[2] = {};
+    int chain_frames[2] = {}, chain_launches[2] = {}, chain_first[2] = {}, chain_graph_launches[2] = {};
+    long chain_tracked_frames = 0;               // frames that went through the chain (frame 0 of a non-continuing chain is given, not tracked)
+    bool chain_has_carry = false; int carry_K = 0, carry_cap = 0;
+    int* h_chain_ovf = nullptr;                  // pinned, per slot: the two frame-construction overflow flags of the tracked batch
+    unsigned long long scratch_generation = 1;   // bumped by every reallocation of this context's tracking scratch
+    bool chain_timing_on = false, chain_graphs_on = true;   // RGBL_CHAIN_TIMING / RGBL_CHAIN_GRAPH, read at rgbl_create
+    cudaEvent_t chain_tev[8] = {};
     float* h_chain_f = nullptr;  // pinned, per slot: pose0 (7) | poses (cap * 7)
-    int* h_chain_i = nullptr;    // pinned, per slot: n_matches | n_inliers | n_edges, flags, overflow
+    int* h_chain_i = nullptr;    // pinned, per slot: n_matches | n_inliers | n_local_matches | n_inliers_first | n_edges x2, flags[2], overflow, n_queries
     size_t h_chain_cap = 0;      // frames per slot
     // the chain of a slot as an instantiated CUDA graph (re-captured when any launch parameter or scratch pointer changes)
-    struct ChainGraphKey { int nF, cap, mono, prof; float th, fx, fy, cx, cy, bf; unsigned long long generation; };
+    struct ChainGraphKey { int nF, cap, mono, cont, K; float th, th_local, nn_local, fx, fy, cx, cy, bf; unsigned long long generation; };
     cudaGraphExec_t chain_exec[2] = {};
     ChainGraphKey chain_key[2] = {};
     const void* chain_timing_ev = nullptr;   // RGBL_CHAIN_TIMING development aid

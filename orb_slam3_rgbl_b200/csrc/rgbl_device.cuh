@@ -180,6 +180,43 @@ __device__ __forceinline__ void quatf_to_matrix(const float q[4], float R[9]) {
     R[6] = __fsub_rn(txz, twy); R[7] = __fadd_rn(tyz, twx); R[8] = __fsub_rn(1.f, __fadd_rn(txx, tyy));
 }
 
+// ---- Frame::isInFrustum (src/Frame.cc:602-664, Nleft == -1) + MapPoint::PredictScale (src/MapPoint.cc:531-545) for one map point.
+// Float32, Eigen 3.3's reduction order for mRcw * P, norm() and dot(); pinned against the reference's own function body
+// (tests/test_oracle_tracking_ref.py::test_is_in_frustum_and_search_local).
+struct FrustumOut { uint8_t in_view; float px, py, pxr, depth, view_cos; int level; };
+template <class FrameT, class PrmT>
+__device__ __forceinline__ FrustumOut frustum_point(const FrameT& f, const PrmT& prm, const float P[3], const float* Pn, float mf_min, float mf_max) {
+    FrustumOut o; o.in_view = 0; o.px = -1.f; o.py = -1.f; o.pxr = 0.f; o.depth = 0.f; o.view_cos = 0.f; o.level = 0;
+    float Pc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        Pc[r] = __fadd_rn(eig_sum3(__fmul_rn(prm.Rcw[3 * r], P[0]), __fmul_rn(prm.Rcw[3 * r + 1], P[1]), __fmul_rn(prm.Rcw[3 * r + 2], P[2])), prm.tcw[r]);
+    const float pc_dist = sqrtf(eig_sum3(__fmul_rn(Pc[0], Pc[0]), __fmul_rn(Pc[1], Pc[1]), __fmul_rn(Pc[2], Pc[2])));
+    const float z = Pc[2];
+    const float invz = __fdiv_rn(1.0f, z);
+    bool ok = !(z < 0.0f);
+    const float u = __fadd_rn(__fdiv_rn(__fmul_rn(f.fx, Pc[0]), Pc[2]), f.cx);
+    const float v = __fadd_rn(__fdiv_rn(__fmul_rn(f.fy, Pc[1]), Pc[2]), f.cy);
+    if (ok && (u < f.min_x || u > f.max_x)) ok = false;
+    if (ok && (v < f.min_y || v > f.max_y)) ok = false;
+    if (ok) {
+        o.px = u; o.py = v;
+        const float PO[3] = {__fsub_rn(P[0], prm.Ow[0]), __fsub_rn(P[1], prm.Ow[1]), __fsub_rn(P[2], prm.Ow[2])};
+        const float dist = sqrtf(eig_sum3(__fmul_rn(PO[0], PO[0]), __fmul_rn(PO[1], PO[1]), __fmul_rn(PO[2], PO[2])));
+        if (!(dist < __fmul_rn(0.8f, mf_min) || dist > __fmul_rn(1.2f, mf_max))) {
+            const float vc = __fdiv_rn(eig_sum3(__fmul_rn(PO[0], Pn[0]), __fmul_rn(PO[1], Pn[1]), __fmul_rn(PO[2], Pn[2])), dist);
+            if (!(vc < prm.cos_limit)) {
+                const float ratio = __fdiv_rn(mf_max, dist);
+                const float lg = (float)log((double)ratio);          // correctly-rounded stand-in for glibc logf
+                int ns = (int)ceilf(__fdiv_rn(lg, f.log_scale_factor));
+                if (ns < 0) ns = 0; else if (ns >= f.n_levels) ns = f.n_levels - 1;
+                o.in_view = 1; o.pxr = __fsub_rn(u, __fmul_rn(f.bf, invz)); o.depth = pc_dist; o.level = ns; o.view_cos = vc;
+            }
+        }
+    }
+    return o;
+}
+
 // ---- resident tracking chain: the previous frame's LiDAR-depth keypoints as map points -----------------------------------
 // Frame::UnprojectStereo (src/Frame.cc:1137-1150: x3D = mRwc * x3Dc + mOw, with mRwc / mOw from Frame::UpdatePoseMatrices
 // :562-569) with the frame's estimated pose, the bForward / bBackward test of SearchByProjection (src/ORBmatcher.cc:1686-1693)

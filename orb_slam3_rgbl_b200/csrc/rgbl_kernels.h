@@ -98,7 +98,8 @@ struct LastFrameDev {                // LastFrame.mvpMapPoints as flat arrays (d
     const uint8_t* valid; const float* xw; const uint8_t* desc; const int* octave; const float* angle; const uint8_t* obs_pos;
 };
 struct LocalPointsDev {              // vpMapPoints with the mTrack* fields isInFrustum fills
-    int n;
+    int n;                           // query capacity of the launch; n_dev (if non-null) = the number of queries, read on the device
+    const int* n_dev;
     const uint8_t* in_view; const float *proj_x, *proj_y, *proj_xr, *depth; const int* level; const float* view_cos;
     const uint8_t* desc; const uint8_t* obs_pos;
 };
@@ -135,6 +136,22 @@ void launch_chain_prep(cudaStream_t st, const ChainPrepDev& cp, const float* las
 void launch_frustum(cudaStream_t st, const FrameDev& f, const FrustumParams& prm, int n, const float* xw, const float* normal,
                     const float* mf_min, const float* mf_max, uint8_t* in_view, float* px, float* py, float* pxr, float* depth,
                     int* level, float* view_cos);
+
+// chain_kernels.cu: TrackLocalMap half of the resident tracking chain ----------------------------------
+struct LocalRingDev {                // local map of the chain: K frame slots x cap points, slot = frames inserted so far mod K
+    int K, cap;
+    uint8_t* valid; float* xw; float* normal; float* mf_min; float* mf_max; uint8_t* desc;
+    int* count;                      // frames inserted so far (device)
+};
+struct LocalQueriesDev {             // the in-frustum local map points, compacted in ring order (= vpMapPoints of the local search)
+    int cap; int* n;
+    uint8_t* in_view; uint8_t* obs_pos; float *proj_x, *proj_y, *proj_xr, *depth; int* level; float* view_cos; uint8_t* desc; int* src;
+};
+void launch_tlm_prepare(cudaStream_t st, const FrameDev& f, const float* pose, const LocalRingDev& ring, float cos_limit, const int* n_edges,
+                        const int* e_idx, const uint8_t* e_outlier, uint8_t* state, int* match_last, const LocalQueriesDev& lq);
+void launch_tlm_edges(cudaStream_t st, const FrameDev& f, const int* match_last, const float* last_xw, const int* match_local, const int* lq_src,
+                      const LocalRingDev& ring, const ChainEdgesOut& eo, int* n_local_matches, int n_last_cap, const uint8_t* last_valid,
+                      const int* last_octave, const uint8_t* last_desc, const float* last_pose);
 
 // stereo_kernels.cu --------------------------------------------------------------------------------
 struct StereoFrameDev { const int* n; const rgbl_keypoint* keys; const uint8_t* desc; float scale[RGBL_MAX_LEVELS], inv_scale[RGBL_MAX_LEVELS]; };

@@ -440,6 +440,24 @@ class Optimizer:
         return ni.value, out, outlier[:n]
 
 
+class ChainParams(C.Structure):
+    """rgbl_chain_params (include/rgbl_b200.h)."""
+    _fields_ = [("pose0", C.c_float * 7), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("th_last", C.c_float), ("mono", C.c_int), ("continue_sequence", C.c_int), ("local_map_frames", C.c_int),
+                ("th_local", C.c_float), ("nn_ratio_local", C.c_float)]
+
+
+def make_chain_params(pose0, fx, fy, cx, cy, bf, th_last=15.0, mono=False, continue_sequence=False, local_map_frames=0, th_local=3.0,
+                      nn_ratio_local=0.8) -> ChainParams:
+    p = ChainParams()
+    for i, v in enumerate(np.asarray(pose0, np.float32).reshape(7)):
+        p.pose0[i] = float(v)
+    p.fx, p.fy, p.cx, p.cy, p.bf = fx, fy, cx, cy, bf
+    p.th_last = th_last; p.mono = int(mono); p.continue_sequence = int(continue_sequence); p.local_map_frames = int(local_map_frames)
+    p.th_local = th_local; p.nn_ratio_local = nn_ratio_local
+    return p
+
+
 class RgblBatch:
     """Reusable (pinned if torch+CUDA are available) host buffers for rgbl_frame_rgbl_batch / the resident API."""
 
@@ -515,6 +533,31 @@ class RgblBatch:
         poses = np.empty((self.nF, 7), np.float32); nm = np.zeros(self.nF, np.int32); ni = np.zeros(self.nF, np.int32)
         check(lib().rgbl_resident_track_end(c.handle, ptr(poses), ptr(nm), ptr(ni)), c.handle)
         return poses, nm, ni
+
+    def track_begin2(self, prm: ChainParams):
+        """rgbl_resident_track_begin2: TrackWithMotionModel + (local_map_frames > 0) TrackLocalMap per frame; continue_sequence
+        tracks frame 0 of this batch against the last frame of the previous chain of this context."""
+        check(lib().rgbl_resident_track_begin2(self.ctx.handle, C.byref(prm)), self.ctx.handle)
+
+    def track_end2(self):
+        """-> dict(poses[nF,7], n_matches, n_inliers, n_local_matches, n_inliers_first) of the oldest queued chain"""
+        nF = self.nF
+        out = dict(poses=np.empty((nF, 7), np.float32), n_matches=np.zeros(nF, np.int32), n_inliers=np.zeros(nF, np.int32),
+                   n_local_matches=np.zeros(nF, np.int32), n_inliers_first=np.zeros(nF, np.int32))
+        check(lib().rgbl_resident_track_end2(self.ctx.handle, ptr(out["poses"]), ptr(out["n_matches"]), ptr(out["n_inliers"]),
+                                             ptr(out["n_local_matches"]), ptr(out["n_inliers_first"])), self.ctx.handle)
+        return out
+
+    def set_inputs(self, images, clouds):
+        """Refill the (pinned) input buffers with another batch of the same shape."""
+        assert len(images) == self.nF
+        for f in range(self.nF):
+            self.img[f] = images[f]
+            n = clouds[f].shape[1]
+            assert 4 * n <= self.pts.shape[1]
+            self.pts[f, :4 * n] = np.ascontiguousarray(clouds[f], np.float32).reshape(-1)
+            self.npts[f] = n
+        self.h2d_bytes = int(self.nF * self.W * self.H + 4 * 4 * int(self.npts.sum()))
 
     def download(self):
         c = self.ctx

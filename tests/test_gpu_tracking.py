@@ -174,6 +174,59 @@ def test_resident_tracking_chain_matches_oracle_chain():
     assert (nm[1:] > 200).all() and (ni[1:] > 150).all()
 
 
+@pytest.mark.parametrize("K", [2, 0])
+def test_full_tracking_chain_continuous_sequence(K):
+    """rgbl_resident_track_begin2: TrackWithMotionModel + TrackLocalMap per frame (SearchByProjection(last) -> PoseOptimization ->
+    outlier discard -> isInFrustum over the local-map ring -> SearchByProjection(local) -> PoseOptimization), three batches forming ONE
+    sequence (the last frame, its pose and the local map are carried on the device; the second and third chains are queued two deep),
+    vs the same chain composed from the reference-pinned oracle functions."""
+    T, nB = 5, 3
+    seq = S.PlaneSequence(31, T * nB + 1)
+    c = F.Context(S.KITTI_W, S.KITTI_H, 2000, max_batch=T, max_points=seq.cloud(0).shape[1])
+    got = []
+    try:
+        prm = F.make_depth_params(bf=S.KITTI_BF)
+        batches = [F.RgblBatch(c, [seq.image(t) for t in range(b * T, (b + 1) * T)], [seq.cloud(t) for t in range(b * T, (b + 1) * T)], seq.P, prm, pinned=False)
+                   for b in range(nB)]
+        cp = lambda cont: F.make_chain_params(seq.pose(0), *TD.CAM, th_last=15.0, continue_sequence=cont, local_map_frames=K, th_local=3.0)
+        batches[0].upload(); batches[0].process_resident(); batches[0].track_begin2(cp(False))
+        batches[1].upload(); batches[1].process_resident(); batches[1].track_begin2(cp(True))       # queued behind the first chain
+        got.append(batches[0].track_end2())
+        batches[2].upload(); batches[2].process_resident(); batches[2].track_begin2(cp(True))
+        got.append(batches[1].track_end2()); got.append(batches[2].track_end2())
+    finally:
+        c.close()
+    frames, sf = TD.extract_frames(seq, list(range(T * nB)))
+    state = None
+    for b in range(nB):
+        rp, rnm, rni, rnl, rni1, state = TD.oracle_chain2(frames[b * T:(b + 1) * T], sf, seq.pose(0), K=K, state=state)
+        g = got[b]
+        if b == 0:
+            # identical inputs -> identical decisions, poses to FP64-solver rounding
+            assert (g["n_matches"] == rnm).all(), (b, g["n_matches"], rnm)
+            assert (g["n_local_matches"] == rnl).all(), (b, g["n_local_matches"], rnl)
+            if K:
+                assert (g["n_inliers_first"] == rni1).all(), (b, g["n_inliers_first"], rni1)
+            assert (g["n_inliers"] == rni).all(), (b, g["n_inliers"], rni)
+            assert np.abs(g["poses"] - rp).max() < 2e-5
+        else:
+            # Later frames no longer see identical inputs: the kernel's LM (unpivoted LDL^T, Newton reciprocals, FMA) and the oracle's
+            # agree to ~1e-9 per call, which now and then rounds a float32 pose component differently; the next frame's map points then
+            # differ in their last bits, and g2o's discrete stopping rules (nBad / rho tests, src: optimization_algorithm_levenberg.cpp)
+            # turn that into pose differences of the size of its convergence tolerance (1e-5 .. 1e-4), after which single borderline
+            # matches flip.  Observed: counts within +-2, poses within 2e-4.  The carried state itself is checked by the exact equality
+            # of the first frames after the hand-over (frame 0 of the continuing batch is matched against the carried frame).
+            assert np.abs(g["n_matches"] - rnm).max() <= 5 and np.abs(g["n_local_matches"] - rnl).max() <= 8, (b, g["n_matches"], rnm, g["n_local_matches"], rnl)
+            assert np.abs(g["n_inliers"] - rni).max() <= 8, (b, g["n_inliers"], rni)
+            assert np.abs(g["poses"] - rp).max() < 2e-3
+            if b == 1:
+                assert g["n_matches"][0] == rnm[0] and g["n_inliers"][0] == rni[0]          # hand-over frame: carried keypoints, pose, local map
+        for t in range(T):
+            assert abs(g["poses"][t, 4] - seq.pose(b * T + t)[4]) < 0.03
+    if K:
+        assert got[2]["n_local_matches"].min() > 50          # the local map contributes matches once it holds frames
+
+
 def test_async_chain_overlapping_next_batch_is_identical():
     """rgbl_resident_track_begin/_end: the chain of batch A keeps running on its own stream (on its snapshot of A's frame
     outputs) while batch B is uploaded and processed in the same context; both chains must equal the synchronous results,

@@ -150,6 +150,86 @@ def oracle_chain(frames, sf, pose0, th=15.0):
     return np.stack(poses), np.array(nms), np.array(nis)
 
 
+def _sum3(a, b, c):
+    """Eigen 3.3's 3-term reduction a + (b + c), float32."""
+    return (a + (b + c).astype(f32)).astype(f32)
+
+
+def pose_matrices(pose):
+    """Frame::UpdatePoseMatrices (src/Frame.cc:562-569) in float32: (mRcw, mtcw, mOw)."""
+    R = quat_to_matrix_f32(np.asarray(pose[:4], f32))
+    _, ow = se3f_inverse(pose)
+    return R, np.asarray(pose[4:7], f32), ow
+
+
+def local_points_of(fr, pose, sf):
+    """The LiDAR-depth keypoints of a frame as local map points: world position (Frame::UnprojectStereo with the frame's final pose),
+    normal and scale-invariance distances of MapPoint::UpdateNormalAndDepth for one observation (src/MapPoint.cc:437-490):
+    normal = PC / |PC|, mfMaxDistance = |PC| * scale[octave], mfMinDistance = mfMaxDistance / scale[nLevels - 1].  float32, Eigen order."""
+    xw, ok = chain_unproject(fr, pose)
+    _, ow = se3f_inverse(pose)
+    pc = (xw - ow[None, :]).astype(f32)
+    dist = np.sqrt(_sum3(pc[:, 0] * pc[:, 0], pc[:, 1] * pc[:, 1], pc[:, 2] * pc[:, 2])).astype(f32)
+    dist_safe = np.where(ok, dist, f32(1))
+    normal = (pc / dist_safe[:, None]).astype(f32)
+    mx = (dist * sf[fr["k"]["octave"]]).astype(f32)
+    mn = (mx / sf[len(sf) - 1]).astype(f32)
+    return dict(valid=ok, xw=xw, normal=normal, mn=mn, mx=mx, desc=fr["d"])
+
+
+def oracle_chain2(frames, sf, pose0, K=3, th_last=15.0, th_local=3.0, nn_ratio=0.8, state=None):
+    """The chain of rgbl_resident_track_begin2 composed from the (reference-pinned) oracle functions, frame by frame:
+    SearchByProjection(last) -> PoseOptimization -> discard outliers -> isInFrustum over the local map ring -> SearchByProjection(local)
+    -> PoseOptimization on all map points.  `state` (returned as last element) carries the last frame, its pose and the ring into the
+    next batch (continue_sequence).  -> (poses, n_matches, n_inliers, n_local_matches, n_inliers_first, state)"""
+    if state is None:
+        ring = [None] * max(K, 1); count = 0
+        last, last_pose = frames[0], np.asarray(pose0, f32)
+        poses, out = [last_pose], [(0, 0, 0, 0)]
+        todo = frames[1:]
+    else:
+        ring, count, last, last_pose = state["ring"], state["count"], state["last"], state["pose"]
+        poses, out = [], []
+        todo = frames
+    for cur in todo:
+        xw, ok = chain_unproject(last, last_pose)
+        fv = oracle.FrameView(*frame_view_args(cur, sf))
+        nm, match = oracle.search_by_projection_last(fv, last_pose, last_pose, ok.astype(np.uint8), xw, last["d"], last["k"]["octave"], last["k"]["angle"],
+                                                     np.ones(len(ok), np.uint8), th_last)
+        m = np.nonzero(match >= 0)[0]
+
+        def edges(idx, pts):
+            obs = np.stack([cur["k"]["x"][idx], cur["k"]["y"][idx], cur["ur"][idx]], 1).astype(f32)
+            s = sf[cur["k"]["octave"][idx]]
+            return pts, obs, (f32(1.0) / (s * s).astype(f32)).astype(f32), (cur["ur"][idx] >= 0).astype(np.uint8)
+
+        ni1, pose1, outl = oracle.pose_optimize(last_pose, *edges(m, xw[match[m]]), *CAM)
+        if K == 0:
+            pose2, ni2, nml = pose1, ni1, 0
+        else:
+            keep = m[outl == 0]                                         # outliers are discarded (src/Tracking.cc:2944-2966)
+            cur_state = np.zeros(len(cur["k"]), np.uint8); cur_state[keep] = 1
+            slots = [r for r in ring if r is not None]
+            if slots:
+                lp = {k: np.concatenate([r[k] for r in ring if r is not None]) for k in ("valid", "xw", "normal", "mn", "mx", "desc")}
+                v = lp["valid"]
+                R, tcw, ow = pose_matrices(pose1)
+                tr = oracle.is_in_frustum(fv, R, tcw, ow, lp["xw"][v], lp["normal"][v], lp["mn"][v], lp["mx"][v], 0.5)
+                nml, ml = oracle.search_by_projection_local(fv, tr, lp["desc"][v], np.ones(int(v.sum()), np.uint8), th_local, nn_ratio, False, 0.0, cur_state)
+                lxw = lp["xw"][v]
+            else:
+                nml, ml, lxw = 0, np.full(len(cur["k"]), -1, np.int32), np.zeros((0, 3), f32)
+            src_last = np.full(len(cur["k"]), -1, np.int64); src_last[keep] = match[keep]
+            idx = np.nonzero((src_last >= 0) | (ml >= 0))[0]            # keypoint order = Optimizer::PoseOptimization's edge order
+            pts = np.where((src_last[idx] >= 0)[:, None], xw[np.maximum(src_last[idx], 0)], lxw[np.maximum(ml[idx], 0)] if len(lxw) else xw[np.maximum(src_last[idx], 0)]).astype(f32)
+            ni2, pose2, _ = oracle.pose_optimize(pose1, *edges(idx, pts), *CAM)
+            ring[count % K] = local_points_of(last, last_pose, sf); count += 1      # the last frame's points join the local map
+        poses.append(pose2); out.append((nm, ni2, nml, ni1))
+        last, last_pose = cur, pose2
+    o = np.array(out, np.int64).reshape(-1, 4)
+    return np.stack(poses), o[:, 0], o[:, 1], o[:, 2], o[:, 3], dict(ring=ring, count=count, last=last, pose=last_pose)
+
+
 def pseudo_feature_vector(desc, n_bits=6):
     """Stand-in for DBoW2's FeatureVector (node -> feature indices): node id = a few stable descriptor bits.  Returns the
     CSR triple (ascending node ids, node_start, feature indices in ascending feature order, like Frame::ComputeBoW)."""

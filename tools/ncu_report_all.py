@@ -1,10 +1,10 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep holding many `--set full` captures: one block of key metrics per kernel NAME (the first launch of each, or
-the longest with --longest).  Usage (here, no GPU needed):  python tools/ncu_report_all.py gpurun_out/r02/a/all_kernels.ncu-rep > profiles/r02_ncu_full_all.txt"""
+the longest with --longest).  Usage (no GPU needed):  python tools/ncu_report_all.py <all_kernels.ncu-rep | its `--page raw --csv` export> [--longest] > profiles/r02_ncu_full_all.txt"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]
 longest = "--longest" in sys.argv
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 ki = hdr.index("Kernel Name")

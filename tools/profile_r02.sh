@@ -15,6 +15,15 @@ PROF="python bench.py --steps 2 --warmup 3 --batch 32 --no-cpu-baseline --no-bow
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 500 --csv --log-file "$out/launches.csv" $PROF > "$out/launches_run.log" 2>&1
 echo "launch list exit $?"
 python tools/summarize_ncu_launches.py "$out/launches.csv" > "$out/launches_summary.csv" 2>/dev/null; head -20 "$out/launches_summary.csv"
-K='regex:(resize_level|fast_|cand_|blur_level|quadtree_kernel|sel_pack|describe|depth_project|depth_resolve|depth_gather|grid_build|search_last_collect|resolve_kernel|pose_optimize|chain_prep|fused_)'
-timeout 900 ncu --set full --clock-control none --import-source on -k "$K" -s 60 -c 70 -o "$out/all_kernels" -f $PROF > "$out/ncu_full.log" 2>&1
-echo "ncu full exit $?"; ls -la "$out"
+# two passes, the .ncu-rep files stay on the box (tens of MB): only their raw pages (CSV, one row per launch) come back
+K1='regex:(resize_level|fast_|cand_|blur_level|quadtree_kernel|sel_pack|describe|depth_project|depth_resolve|depth_gather|grid_build|level_fused)'
+K2='regex:(search_last_collect|search_local_collect|resolve_kernel|pose_optimize|chain_prep|tlm_)'
+timeout 900 ncu --set full --clock-control none -k "$K1" -s 62 -c 31 -o /tmp/fc_kernels -f $PROF > "$out/ncu_full.log" 2>&1
+echo "ncu full (frame construction) exit $?"
+timeout 900 ncu --set full --clock-control none -k "$K2" -s 40 -c 16 -o /tmp/chain_kernels -f $PROF >> "$out/ncu_full.log" 2>&1
+echo "ncu full (chain) exit $?"
+ncu -i /tmp/fc_kernels.ncu-rep --page raw --csv > "$out/fc_kernels_raw.csv" 2>> "$out/ncu_full.log"
+ncu -i /tmp/chain_kernels.ncu-rep --page raw --csv > "$out/chain_kernels_raw.csv" 2>> "$out/ncu_full.log"
+python tools/ncu_report_all.py "$out/fc_kernels_raw.csv" --longest > "$out/ncu_full_all.txt" 2>> "$out/ncu_full.log"
+python tools/ncu_report_all.py "$out/chain_kernels_raw.csv" --longest >> "$out/ncu_full_all.txt" 2>> "$out/ncu_full.log"
+ls -la "$out"; du -sh gpurun_out

@@ -1,18 +1,24 @@
 #!/usr/bin/env python3
 """bench.py — RGB-L front-end frames/s on KITTI-sized synthetic frames (BASELINE.json metric).
 
-A "step" = one batch of T consecutive frames of a synthetic RGB-L sequence (1241x376 image + 120k Velodyne
-points each, nFeatures=2000, 8 levels: BASELINE.json configs[1]) through the whole hot path: pyramid -> FAST ->
-quad-tree -> orientation + rBRIEF -> LiDAR projection -> inverse dilation -> per-keypoint depth (batched), then per
-frame SearchByProjection(last frame) -> PoseOptimization (serial in time, on the device).
+A "step" = one batch of T consecutive frames of ONE continuous synthetic RGB-L sequence through the whole per-frame hot path of the
+reference's tracking thread (System::TrackRGBL -> Frame::Frame -> Tracking::Track):
+  frame construction : 8-level pyramid -> FAST per cell -> quad-tree -> orientation + rBRIEF || LiDAR projection -> inverse dilation ->
+                       per-keypoint depth  (all T frames of the batch at once)
+  tracking, per frame: TrackWithMotionModel = SearchByProjection(last frame, th 15) -> PoseOptimization -> outlier discard, then
+                       TrackLocalMap = isInFrustum over the local map -> SearchByProjection(local points, th 3) -> PoseOptimization
+                       (serial in time, on the device; the local map = the points of the K frames before the last one)
+The batches of a run continue one sequence: M*T distinct frames (a closed loop, so any number of steps stays continuous), every
+counted frame is tracked; the last frame, its pose and the local map are carried on the device between batches.
 
-  value : frames/s with the batch already resident in HBM (rgbl_resident_process), CUDA-event timed
-  e2e   : frames/s through the public C ABI with pinned HOST buffers (rgbl_frame_rgbl_batch):
-          H2D of images + clouds and D2H of keypoints/descriptors/depths inside the timed region
-  --impl reference : the CPU restatement of the reference path (oracle/) on all host cores
+  value : frames/s, inputs resident in HBM (staged device slots), CUDA events around K steps driven by ONE native call
+          (rgbl_track_sequence, resident mode)
+  e2e   : frames/s through the same public call with pinned HOST buffers: H2D of images + clouds and D2H of every frame's keypoints /
+          descriptors / depths and poses inside the timed region
+  --impl reference : the CPU restatement of the reference path (oracle/) on every host core: one independent sequence per core
 
-Multi-GPU: independent sequences shard across ranks (weak scaling, no data-path collective); one
-all_reduce(MAX) of the elapsed time for the throughput report.
+--config picks the headline workload (default B = BASELINE configs[1]); the other configs are reported as side blocks of the same line.
+Multi-GPU: independent sequences shard across ranks (weak scaling, no data-path collective); one all_reduce(MAX) for the report.
 """
 from __future__ import annotations
 
@@ -34,7 +40,24 @@ from orb_slam3_rgbl_b200 import synthetic as S  # noqa: E402
 
 METRIC = "rgbl_frontend_frames_per_sec_kitti_1241x376"
 UNIT = "frames/s"
-WORKLOAD = "KITTI-00-like synthetic RGB-L sequence: 1241x376 + 120k Velodyne pts/frame, nFeatures=2000, 8 levels (configs[1]); frame construction + SearchByProjection(last) + PoseOptimization"
+KITTI_CAM = (S.KITTI_FX, S.KITTI_FY, S.KITTI_CX, S.KITTI_CY, S.KITTI_BF)
+CONFIGS = {
+    # BASELINE.json configs[0..3]
+    "A": dict(label="configs[0]: KITTI-00 RGB-L single frame at a time, 1241x376 + ~120k pts, nFeatures=1000 (latency case)",
+              W=1241, H=376, nfeat=1000, n_az=1875, T=1, M=8, K=3, cam=KITTI_CAM),
+    "B": dict(label="configs[1]: KITTI-00-like continuous RGB-L sequence, 1241x376 + 120k Velodyne pts/frame, nFeatures=2000, 8 levels",
+              W=1241, H=376, nfeat=2000, n_az=1875, T=32, M=4, K=3, cam=KITTI_CAM),
+    "C": dict(label="configs[2]: stereo pairs 1241x376, nFeatures=2000: ORBextractor x2 + Frame::ComputeStereoMatches (no LiDAR path)",
+              W=1241, H=376, nfeat=2000, T=16, cam=KITTI_CAM),
+    "D": dict(label="configs[3]: synthetic 1920x1080 RGB-L sequence, 200k LiDAR pts/frame, nFeatures=4000",
+              W=1920, H=1080, nfeat=4000, n_az=3125, T=8, M=4, K=3, cam=(1100.0, 1100.0, 960.0, 540.0, 153.0)),
+}
+TH_LAST, TH_LOCAL = 15.0, 3.0          # src/Tracking.cc:2913-2917 (RGB-L is not System::STEREO), :3432-3436
+
+
+def workload_string(cfg):
+    return (cfg["label"] + "; frame construction + TrackWithMotionModel (SearchByProjection(last) + PoseOptimization) + TrackLocalMap "
+            "(isInFrustum + SearchByProjection(local map) + PoseOptimization) per frame, one continuous sequence")
 
 
 def algorithmic_bytes(levels_wh, n_cand, n_kp, n_pts, W, H, n_in):
@@ -47,6 +70,7 @@ def algorithmic_bytes(levels_wh, n_cand, n_kp, n_pts, W, H, n_in):
         "fast": Ssum + 8 * n_cand,
         "compact": 8 * n_cand,
         "blur": 2 * Ssum,
+        "quadtree": 8 * n_cand,
         "describe": n_kp * (749 + 512 + 32 + 28),
         "depth_project": 16 * n_pts + 4 * n_in,
         "depth_resolve_dilate": 8 * A + 4 * A,   # read index/raw map once, write Processed (+ the zero-fill the reference does)
@@ -99,107 +123,249 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_batch_inputs(rank: int, T: int):
-    """T consecutive frames of the synthetic sequence `rank` (plane world): images, clouds, P, pose0."""
-    seq = S.PlaneSequence(1000 + rank, T + 1)
-    return [seq.image(t) for t in range(T)], [seq.cloud(t) for t in range(T)], seq
+def make_sequence(cfg, seed):
+    """The looped plane sequence of a config: M*T distinct frames, back at the start after one loop."""
+    n = cfg["M"] * cfg["T"]
+    loop = n if n % 2 == 0 else 0
+    return S.PlaneSequence(seed, n, W=cfg["W"], H=cfg["H"], n_azimuth=cfg["n_az"], loop=loop, cam=cfg["cam"])
 
 
-CAM = (S.KITTI_FX, S.KITTI_FY, S.KITTI_CX, S.KITTI_CY, S.KITTI_BF)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/), else None
-TRAFFIC = {"fast": 42294016 + 183552}   # profiles/r01_ncu_full_fast_cells_kernel.txt (32-frame launch)
+# ------------------------------------------------------------------------------------------------------------------------------
+# CPU legs: the oracle (scalar C++ restatement, pinned to the reference's own code) driven like the reference's tracking thread
+# ------------------------------------------------------------------------------------------------------------------------------
+class CpuSequence:
+    """One sequence on one host thread: Frame construction + TrackWithMotionModel + TrackLocalMap per frame (oracle/chain.py)."""
+
+    def __init__(self, cfg, seq, frames_cache=None):
+        import oracle
+        self.cfg, self.seq = cfg, seq
+        self.ex = oracle.Extractor(cfg["nfeat"])
+        self.sf = self.ex.scale_factors.copy()
+        self.mask = S.structuring_element("diamond", 5)
+        self.state = None
+        self.t = 0
+        self.cache = frames_cache if frames_cache is not None else {}
+
+    def inputs(self, t):
+        n = self.cfg["M"] * self.cfg["T"]
+        i = t % n
+        if i not in self.cache:
+            self.cache[i] = (self.seq.image(i), self.seq.cloud(i))
+        return self.cache[i]
+
+    def advance(self, n_frames):
+        import oracle
+        from oracle import chain
+        cfg, cam = self.cfg, self.cfg["cam"]
+        for _ in range(n_frames):
+            img, pts = self.inputs(self.t)
+            k, d, _ = self.ex(img)
+            dep, ur, _, _ = oracle.depth_from_pcd(pts, self.seq.P, cfg["W"], cfg["H"], self.mask, cam[4], k, k)
+            fr = dict(k=k, d=d, depth=dep, ur=ur)
+            if self.state is None:
+                out = chain.oracle_chain2([fr], self.sf, self.seq.pose(0), cfg["W"], cfg["H"], cam, K=cfg["K"], th_last=TH_LAST, th_local=TH_LOCAL)
+            else:
+                out = chain.oracle_chain2([fr], self.sf, None, cfg["W"], cfg["H"], cam, K=cfg["K"], th_last=TH_LAST, th_local=TH_LOCAL, state=self.state)
+            self.state = out[-1]
+            self.t += 1
+        return n_frames
 
 
-def cpu_track_step(fv_args_cur, last, pose, sf):
-    """oracle SearchByProjection(last frame) + PoseOptimization for one frame (same glue as rgbl_resident_track)."""
-    import oracle
-    import tracking_data as TD
-    xw, ok = TD.chain_unproject(last, pose)
-    fv = oracle.FrameView(*fv_args_cur)
-    cur_k, cur_ur = fv_args_cur[0], fv_args_cur[1]
-    nm, match = oracle.search_by_projection_last(fv, pose, pose, ok.astype(np.uint8), xw, last["d"], last["k"]["octave"], last["k"]["angle"],
-                                                 np.ones(len(ok), np.uint8), 15.0)
-    m = np.nonzero(match >= 0)[0]
-    obs = np.stack([cur_k["x"][m], cur_k["y"][m], cur_ur[m]], 1).astype(np.float32)
-    sc = sf[cur_k["octave"][m]]
-    inv_s2 = (np.float32(1.0) / (sc * sc).astype(np.float32)).astype(np.float32)
-    st = (cur_ur[m] >= 0).astype(np.uint8)
-    ni, pose2, _ = oracle.pose_optimize(pose, xw[match[m]], obs, inv_s2, st, *CAM)
-    return pose2
-
-
-def cpu_frame(ex, img, pts, P, mask):
-    """Frame construction on the CPU: ORBextractor::operator() + DepthModule::CalculateDepthFromPcd (oracle)."""
-    import oracle
-    k, d, _ = ex(img)
-    dep, ur, _, _ = oracle.depth_from_pcd(pts, P, S.KITTI_W, S.KITTI_H, mask, S.KITTI_BF, k, k)
-    return dict(k=k, d=d, depth=dep, ur=ur)
-
-
-def cpu_baseline_single(imgs, pcs, seq, budget_s=12.0):
-    """Oracle (port) on ONE host core over a bounded sample of the same workload (frame construction + tracking)."""
-    import oracle
-    sys.path.insert(0, str(ROOT / "tests"))
-    ex = oracle.Extractor(2000)
-    sf = ex.scale_factors.copy()
-    mask = S.structuring_element("diamond", 5)
-    last = cpu_frame(ex, imgs[0], pcs[0], seq.P, mask)            # warm-up / frame 0
-    pose = seq.pose(0)
+def cpu_baseline_single(cfg, budget_s=12.0):
+    """Oracle (port) on ONE host core over a bounded sample of the same workload (inputs generated before the clock starts)."""
+    small = dict(cfg); small["M"], small["T"] = 1, 32                     # a 32-frame closed loop of the same sequence
+    seq = make_sequence(small, 1000)
+    cache = {i: (seq.image(i), seq.cloud(i)) for i in range(32)}
+    cs = CpuSequence(small, seq, frames_cache=cache)
+    cs.advance(2)                               # warm-up (first frame has nothing to track)
     n, t0 = 0, time.perf_counter()
     while True:
-        t = 1 + n % (len(imgs) - 1)
-        if t == 1:
-            last = cpu_frame(ex, imgs[0], pcs[0], seq.P, mask); pose = seq.pose(0); n += 1
-        cur = cpu_frame(ex, imgs[t], pcs[t], seq.P, mask)
-        pose = cpu_track_step((cur["k"], cur["ur"], cur["d"], S.KITTI_W, S.KITTI_H, sf) + CAM, last, pose, sf)
-        last = cur
-        n += 1
+        n += cs.advance(1)
         el = time.perf_counter() - t0
         if el > budget_s or n >= 400:
             break
     return n / el, n
 
 
+_WORKER = {}
+
+
+def _ref_worker_init(cfg_key, seed):
+    cfg = CONFIGS[cfg_key]
+    _WORKER["cs"] = CpuSequence(cfg, make_sequence(cfg, seed), frames_cache=_WORKER.get("cache"))
+    _WORKER["cs"].advance(2)
+
+
+def _ref_worker_step(n_frames):
+    return _WORKER["cs"].advance(n_frames)
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU restatement with every host thread it can use (rank 0 only)."""
+    """--impl reference: the CPU restatement on every host core (rank 0 only).  The reference's tracking thread is serial per sequence
+    (extract -> depth -> track, one frame after the other), so all cores = one independent sequence per core, each advancing
+    frames_per_seq frames per step."""
     if rank != 0:
         return
-    import oracle
-    from concurrent.futures import ThreadPoolExecutor
-    sys.path.insert(0, str(ROOT / "tests"))
+    import multiprocessing as mp
+    cfg = CONFIGS[args.config]
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    frames_per_step = max(8, min(2 * cores, 32))
-    imgs, pcs, seq = make_batch_inputs(0, frames_per_step)
-    mask = S.structuring_element("diamond", 5)
-    exs = [oracle.Extractor(2000) for _ in range(cores)]
-    sf = exs[0].scale_factors.copy()
-
-    def work(i):
-        return cpu_frame(exs[i % cores], imgs[i % len(imgs)], pcs[i % len(pcs)], seq.P, mask)
-
-    def step(pool):
-        # frame construction is independent per frame (all threads); the tracking chain is serial in time
-        frs = list(pool.map(work, range(frames_per_step)))
-        pose = seq.pose(0)
-        for t in range(1, len(frs)):
-            pose = cpu_track_step((frs[t]["k"], frs[t]["ur"], frs[t]["d"], S.KITTI_W, S.KITTI_H, sf) + CAM, frs[t - 1], pose, sf)
-
-    with ThreadPoolExecutor(cores) as pool:
-        for _ in range(args.warmup):
-            step(pool)
+    frames_per_seq = 2
+    # every worker walks the same synthetic frames (its own tracker state): build them once, before the fork
+    seq = make_sequence(cfg, 1000)
+    n_distinct = min(cfg["M"] * cfg["T"], 16)
+    _WORKER["cache"] = {i: (seq.image(i), seq.cloud(i)) for i in range(n_distinct)}
+    cfg_small = dict(cfg); cfg_small["M"], cfg_small["T"] = n_distinct, 1
+    CONFIGS["_ref"] = cfg_small
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_ref_worker_init, initargs=("_ref", 1000)) as pool:
+        def step():
+            return sum(pool.map(_ref_worker_step, [frames_per_seq] * cores, chunksize=1))
+        for _ in range(max(args.warmup, 1)):
+            step()
         t0 = time.perf_counter()
+        frames = 0
         for _ in range(args.steps):
-            step(pool)
+            frames += step()
         el = time.perf_counter() - t0
-    fps = frames_per_step * args.steps / el
+    fps = frames / el
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": frames_per_step},
-            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{frames_per_step} frames/step x {args.steps} steps, oracle (C++ restatement, scalar): frame construction on {cores} threads, tracking chain serial"},
+            "config": {"workload": workload_string(cfg), "frames_per_step": frames_per_seq * cores, "sequences": cores, "frames_per_sequence_per_step": frames_per_seq},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "cores_used": cores, "kind": "port",
+                             "sample": f"{cores} independent sequences (one process per core) x {frames_per_seq} frames per step x {args.steps} steps; oracle = scalar C++ "
+                                       "restatement pinned to the reference's own ORBextractor.cc / DepthModule.cc / ORBmatcher.cc / Optimizer::PoseOptimization + g2o "
+                                       "(the reference itself needs OpenCV/Eigen/Pangolin/Boost and cannot be built here)"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# GPU legs
+# ------------------------------------------------------------------------------------------------------------------------------
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each stage's kernel(s), from the committed ncu --set full captures."""
+    p = ROOT / "profiles" / "r02_ncu_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            pass
+    return {}
+
+
+def measure_rgbl(F, torch, cfg, rank, local_rank, steps, warmup, rep, want_detail):
+    """Headline measurement of an RGB-L config -> dict."""
+    T, M, W, H = cfg["T"], cfg["M"], cfg["W"], cfg["H"]
+    cam = cfg["cam"]
+    seq = make_sequence(cfg, 1000 + rank)
+    clouds0 = seq.cloud(0)
+    max_pts = clouds0.shape[1]
+    ctx = F.Context(W, H, cfg["nfeat"], max_batch=T, max_points=max_pts, device=local_rank)
+    prm = F.make_depth_params(bf=cam[4])
+    runner = F.SequenceRunner(ctx, seq.P, prm, T, W, H, max_pts, M, pinned=True)
+    for m in range(M):
+        runner.set_batch(m, [seq.image(m * T + f) for f in range(T)], [seq.cloud(m * T + f) for f in range(T)])
+        runner.stage(m, m)
+    chain = lambda cont: F.make_chain_params(seq.pose(0), *cam, th_last=TH_LAST, continue_sequence=cont, local_map_frames=cfg["K"], th_local=TH_LOCAL)
+
+    def barrier():
+        rep.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value"): K steps = ONE native call, inputs in staged HBM slots ----
+    runner.reserve(steps, False)
+    runner.run(chain(False), max(warmup, 1), first=0, resident_slots=M)
+    first = max(warmup, 1) % M
+    ctx.profile_enable(1); ctx.profile_reset()
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    ctx.timer_mark(0)
+    t0 = time.perf_counter()
+    out = runner.run(chain(True), steps, first=first, resident_slots=M)
+    ctx.timer_mark(1)
+    dev_ms = ctx.timer_elapsed_ms()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    prof = ctx.profile_read()
+    ctx.profile_enable(0)
+    stats = dict(matches_per_frame=float(out["n_matches"].mean()), local_matches_per_frame=float(out["n_local_matches"].mean()),
+                 inliers_per_frame=float(out["n_inliers"].mean()))
+    last_t = (first + steps) * T - 1
+    stats["pose_x_error_m_last_frame"] = float(abs(out["poses"][-1, 4] - seq.pose(last_t)[4]))
+    rank_ms = dev_ms / steps
+    dev_ms_max = rep.max_over_ranks(dev_ms)
+    res = dict(frames_per_step=T, ms_per_step=dev_ms_max / steps, rank_ms_per_step=rank_ms, wall_ms_per_step=wall_ms / steps, tracking=stats,
+               clocks=clocks, gpu_launches=int(prof["_total_launches"]), chain_ms_per_step=prof.get("match", {}).get("ms", 0.0) / max(steps, 1))
+
+    # ---- end to end through the same call with pinned host buffers ("e2e") ----
+    e2e_steps = min(steps, 20)
+    runner.reserve(e2e_steps, True)                 # pinned result buffers of the timed call
+    runner.run(chain(True), e2e_steps, first=(first + steps) % M, resident_slots=0, want_frames=True)      # warm-up of the same shape
+    barrier()
+    t0 = time.perf_counter()
+    runner.run(chain(True), e2e_steps, first=(first + steps + e2e_steps) % M, resident_slots=0, want_frames=True)
+    barrier()
+    e2e_ms = rep.max_over_ranks(1e3 * (time.perf_counter() - t0))
+    res["e2e"] = dict(ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps, h2d_bytes_per_step=runner.h2d_bytes_per_batch(), d2h_bytes_per_step=runner.d2h_bytes_per_batch(True))
+
+    if want_detail:
+        # ---- per-stage kernel times WITHOUT stream overlap (profile mode 2), frame construction only ----
+        batch = F.RgblBatch(ctx, [seq.image(f) for f in range(T)], [seq.cloud(f) for f in range(T)], seq.P, prm, pinned=False)
+        batch.upload()
+        for _ in range(3):
+            n_kp = batch.process_resident()
+        ctx.profile_enable(2); ctx.profile_reset()
+        iters = 10
+        for _ in range(iters):
+            n_kp = batch.process_resident()
+        prof2 = ctx.profile_read()
+        ctx.profile_enable(0)
+        t = F.orb_tables(cfg["nfeat"])
+        levels = [(int(np.rint(np.float32(W) * t["inv_scale"][l])), int(np.rint(np.float32(H) * t["inv_scale"][l]))) for l in range(8)]
+        n_cand = 0
+        try:
+            ex = F.ORBextractor(cfg["nfeat"], 1.2, 8, 12, 7, W, H, ctx=ctx)
+            n_cand = int(np.mean([sum(len(ex.level_candidates(l, f)) for l in range(8)) for f in range(min(T, 4))]))
+        except Exception:
+            pass
+        P64 = seq.P.astype(np.float64); Q = P64 @ clouds0.astype(np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u, v = Q[0] / Q[2], Q[1] / Q[2]
+        n_in = int(((u > 0) & (u < W) & (v > 0) & (v < H) & (Q[2] > 5) & (Q[2] < 200)).sum())        # measured, not assumed
+        per_frame = algorithmic_bytes(levels, n_cand, float(np.mean(n_kp)), max_pts, W, H, n_in)
+        res["detail"] = dict(prof=prof2, iters=iters, per_frame=per_frame, n_cand=n_cand, n_in=n_in, n_kp=float(np.mean(n_kp)), levels=levels)
+    ctx.close()
+    return res
+
+
+def measure_stereo(F, torch, cfg, local_rank, steps):
+    """configs[2]: per stereo pair ORBextractor on left + right (one batch of 2T images) + Frame::ComputeStereoMatches.  -> dict"""
+    T, W, H = cfg["T"], cfg["W"], cfg["H"]
+    pairs = [S.stereo_pair(500 + i, W, H) for i in range(min(T, 4))]
+    imgs = []
+    for i in range(T):
+        l, r = pairs[i % len(pairs)]
+        imgs += [l, r]
+    ex = F.ORBextractor(cfg["nfeat"], 1.2, 8, 12, 7, W, H, max_batch=2 * T)
+    mb, mbf = float(np.float32(cfg["cam"][4]) / np.float32(cfg["cam"][0])), float(cfg["cam"][4])
+    try:
+        def step():
+            kd = ex.extract_batch(imgs)                     # H2D of the 2T images, D2H of all keypoints / descriptors
+            return [F.stereo_matches_slots(ex, 2 * i, 2 * i + 1, len(kd[2 * i][0]), mb, mbf) for i in range(T)]
+        step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            outs = step()
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0) / steps
+        matched = float(np.mean([(d > 0).sum() for d, _ in outs]))
+    finally:
+        ex.ctx.close()
+    return dict(pairs_per_step=T, ms_per_step=ms, value=T / (ms * 1e-3), unit="stereo pairs/s", matched_per_pair=matched,
+                timing="host wall clock around K steps with device synchronisation on both sides; host images uploaded every step (H2D inside)")
 
 
 def main():
@@ -208,12 +374,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="frames per step (per GPU)")
+    ap.add_argument("--config", default="B", choices=["A", "B", "D"], help="headline workload (BASELINE.json configs[0], [1], [3]); C (stereo) is a side block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-bow", action="store_true", help="skip the ComputeBoW side measurement")
-    ap.add_argument("--multi-sequences", type=int, default=4, help="extra capacity figure: independent sequences tracked concurrently on one GPU (N=1 only; 0/1 = skip)")
+    ap.add_argument("--no-side", action="store_true", help="skip the side blocks (other configs, ComputeBoW, local BA, capacity)")
+    ap.add_argument("--no-bow", action="store_true", help="alias of --no-side")
+    ap.add_argument("--batch", type=int, default=0, help="override frames per step of the headline config")
+    ap.add_argument("--multi-sequences", type=int, default=0, help="(kept for old command lines; ignored)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.no_side = args.no_side or args.no_bow
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -231,116 +400,105 @@ def main():
     from orb_slam3_rgbl_b200.dist import Reporter
     rep = Reporter("nccl", torch.device("cuda", local_rank))      # sequences shard over ranks; NCCL only for the report
 
-    T = args.batch
-    imgs, pcs, seq = make_batch_inputs(rank, T)
-    P = seq.P
-    max_pts = max(p.shape[1] for p in pcs)
-    ctx = F.Context(S.KITTI_W, S.KITTI_H, 2000, max_batch=T, max_points=max_pts, device=local_rank)
-    prm = F.make_depth_params(bf=S.KITTI_BF)
-    batch = F.RgblBatch(ctx, imgs, pcs, P, prm, pinned=True)
+    cfg = dict(CONFIGS[args.config])
+    if args.batch > 0:
+        cfg["T"] = args.batch
+    T = cfg["T"]
+    main_res = measure_rgbl(F, torch, cfg, rank, local_rank, args.steps, args.warmup, rep, want_detail=(rank == 0))
+    rank_ms = rep.gather_floats(main_res["rank_ms_per_step"]) if hasattr(rep, "gather_floats") else [main_res["rank_ms_per_step"]]
+    fps = world * T / (main_res["ms_per_step"] * 1e-3)
+    e2e_fps = world * T / (main_res["e2e"]["ms_per_step"] * 1e-3)
 
-    def barrier():
-        rep.barrier()
-        torch.cuda.synchronize()
+    side = {}
+    bow = lba = None
+    if world == 1 and not args.no_side:
+        for key in ("A", "D"):
+            if key == args.config:
+                continue
+            c2 = CONFIGS[key]
+            st = 60 if key == "A" else 6
+            r = measure_rgbl(F, torch, c2, rank, local_rank, st, 3, rep, want_detail=False)
+            side[key] = {"workload": c2["label"], "frames_per_step": c2["T"], "value": c2["T"] / (r["ms_per_step"] * 1e-3), "unit": UNIT,
+                         "ms_per_step": r["ms_per_step"], "e2e": {"value": c2["T"] / (r["e2e"]["ms_per_step"] * 1e-3), "unit": UNIT,
+                                                                  "ms_per_step": r["e2e"]["ms_per_step"], "h2d_bytes_per_step": r["e2e"]["h2d_bytes_per_step"],
+                                                                  "d2h_bytes_per_step": r["e2e"]["d2h_bytes_per_step"]},
+                         "tracking": r["tracking"]}
+        if args.config != "C":
+            try:
+                side["C"] = dict(workload=CONFIGS["C"]["label"], **measure_stereo(F, torch, CONFIGS["C"], local_rank, 5))
+            except Exception as e:          # noqa: BLE001
+                side["C"] = {"error": str(e)}
+        bow, lba = side_bow_lba(F, torch, local_rank, not args.no_cpu_baseline)
 
-    max_over_ranks = rep.max_over_ranks
+    if rank == 0:
+        d = main_res["detail"]
+        peaks_path = ROOT / "MEASURED_PEAKS.json"
+        if peaks_path.exists():
+            peak = float(json.loads(peaks_path.read_text())["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)"
+        else:
+            peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
+        traffic = load_traffic()
+        kernels = {}
+        fc_ms = 0.0; fc_bytes = 0.0
+        for name, st in d["prof"].items():
+            if name.startswith("_") or st["calls"] == 0 or name not in d["per_frame"]:
+                continue
+            ms_per_call = st["ms"] / st["calls"]
+            launches = st["launches"] / st["calls"]
+            bytes_step = d["per_frame"][name] * T
+            gbs = bytes_step / (ms_per_call * 1e-3) / 1e9
+            kernels[name] = {"ms_per_step": ms_per_call, "launches_per_step": launches, "algorithmic_MB_per_step": bytes_step / 1e6,
+                             "achieved_GBs": gbs, "frac": gbs / peak, "traffic_MB_per_step": traffic.get(name)}
+            fc_ms += ms_per_call; fc_bytes += bytes_step
+        frame_construction = {"ms_per_step_serial": fc_ms, "algorithmic_MB_per_step": fc_bytes / 1e6, "achieved_GBs": fc_bytes / (fc_ms * 1e-3) / 1e9 if fc_ms else None,
+                              "frac": fc_bytes / (fc_ms * 1e-3) / 1e9 / peak if fc_ms else None,
+                              "note": "sum of the un-overlapped stage times of one batch (rgbl_profile_enable(ctx, 2)); in the pipeline these kernels run beside the tracking chain"}
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+        roofline = None
+        if dom:
+            kd = kernels[dom]
+            lpk = max(kd["launches_per_step"], 1)
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": kd["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": kd["frac"],
+                        "traffic": (kd["traffic_MB_per_step"] * 1e6 / lpk) if kd["traffic_MB_per_step"] else None, "peak_source": peak_src,
+                        "avg_launch_ms": kd["ms_per_step"] / lpk, "algorithmic_bytes_per_launch": kd["algorithmic_MB_per_step"] * 1e6 / lpk,
+                        "note": "dominant frame-construction kernel, timed without stream overlap; the step itself is bound by the serial tracking chain (see tracking_chain)"}
+        chain_ms = main_res["chain_ms_per_step"]
+        working_set_mb = (2 * 1.74 + 4 * 4 * 120000 / 1e6 + 2 * 4 * cfg["W"] * cfg["H"] / 1e6) * T * cfg["M"]
+        line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic",
+                "config": {"workload": workload_string(cfg), "frames_per_step_per_gpu": T, "frames_per_step": T, "parallelism": f"sequences sharded x{world}",
+                           "distinct_frames": cfg["M"] * T, "local_map_frames": cfg["K"],
+                           "l2": f"inputs larger than L2: {cfg['M']} staged batches, ~{working_set_mb:.0f} MB of inputs + intermediates cycled vs 126 MB L2",
+                           "timing": "CUDA events on the library stream around ONE rgbl_track_sequence call of K steps, max over ranks",
+                           "pipeline": "chains queued two deep on the tracking stream; frame construction (and, end to end, the copies) of batch i+1 overlap the tracking of batch i; every frame of every step is tracked (continue_sequence)"},
+                "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": main_res["e2e"]["h2d_bytes_per_step"], "d2h_bytes_per_step": main_res["e2e"]["d2h_bytes_per_step"],
+                        "ms_per_step": main_res["e2e"]["ms_per_step"], "steps": main_res["e2e"]["steps"]},
+                "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"], "roofline": roofline, "frame_construction": frame_construction, "kernels": kernels,
+                "tracking_chain": {"ms_per_step": chain_ms, "us_per_frame": 1e3 * chain_ms / T, "bound": "latency (serial in time; single-CTA resolution and FP64 LM kernels)",
+                                   **main_res["tracking"]},
+                "per_rank_ms_per_step": {"min": float(min(rank_ms)), "max": float(max(rank_ms))},
+                "configs": side, "compute_bow": bow, "local_bundle_adjustment": lba,
+                "measured_inputs": {"fast_candidates_per_frame": d["n_cand"], "lidar_points_in_image": d["n_in"], "keypoints_per_frame": d["n_kp"]},
+                "wall_ms_per_step": main_res["wall_ms_per_step"]}
+        if world == 1 and not args.no_cpu_baseline:
+            v, n = cpu_baseline_single(cfg)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"{n} frames of the same workload on one core: oracle (scalar C++ restatement of ORBextractor + DepthModule + both SearchByProjection "
+                                              "+ isInFrustum + 2x PoseOptimization, -O3), pinned to the reference's own sources compiled here"}
+        print(json.dumps(line))
+    rep.close()
 
-    # ---- device-resident throughput ("value") ----
-    batch.upload()
-    pose0 = seq.pose(0)
 
-    def device_steps(k):
-        """k steps, software-pipelined the way the reference's tracking thread is: the frame construction of batch i
-        (rgbl_resident_process) is issued while the tracking chain of batch i-1 still runs on the tracking stream; every
-        batch is fully processed and its poses are read back; the last chain is drained inside the timed region."""
-        n = batch.process_resident()
-        batch.track_begin(pose0, *CAM, th=15.0)
-        for _ in range(k - 1):
-            n = batch.process_resident()                 # frame construction of the next batch while the chain runs
-            batch.track_begin(pose0, *CAM, th=15.0)      # queued behind the running chain: no host gap between two chains
-            batch.track_end()                            # poses of the oldest chain
-        poses, nm, ni = batch.track_end()
-        return n, poses, nm, ni
-
-    device_steps(args.warmup)
-    ctx.profile_enable(True); ctx.profile_reset()
-    sampler = ClockSampler(local_rank); sampler.start()
-    barrier()
-    ctx.timer_mark(0)
-    t0 = time.perf_counter()
-    n_kp, poses, nm, ni = device_steps(args.steps)
-    n_kp = n_kp.copy()
-    ctx.timer_mark(1)
-    dev_ms = ctx.timer_elapsed_ms()
-    barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t0)
-    clocks = sampler.stop()
-    prof = ctx.profile_read()
-    ctx.profile_enable(False)
-    dev_ms = max_over_ranks(dev_ms)
-    fps = world * T * args.steps / (dev_ms * 1e-3)
-
-    # ---- end to end through the C ABI with host buffers ("e2e") ----
-    def e2e_steps(k):
-        batch.run_e2e()                                  # H2D inputs, kernels, D2H keypoints/descriptors/depths
-        batch.track_begin(pose0, *CAM, th=15.0)
-        for _ in range(k - 1):
-            batch.run_e2e()
-            batch.track_begin(pose0, *CAM, th=15.0)
-            batch.track_end()                            # D2H poses + counts of the oldest chain
-        return batch.track_end()
-
-    e2e_steps(2)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps(args.steps)
-    barrier()
-    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
-    e2e_fps = world * T * args.steps / (e2e_ms * 1e-3)
-    d2h = batch.d2h_bytes()
-
-    # ---- capacity: several independent sequences on ONE GPU (extra information, not the headline: configs[1] is one
-    # sequence per GPU).  A single sequence is bound by the latency of its serial tracking chain (one SM busy); chains of
-    # different sequences run side by side on their own streams until the frame construction saturates the device.
-    multi = None
-    if world == 1 and args.multi_sequences > 1:
-        nS = args.multi_sequences
-        ctxs, batches, pose0s = [ctx], [batch], [pose0]
-        for sidx in range(1, nS):
-            im2, pc2, seq2 = make_batch_inputs(100 + sidx, T)
-            c2 = F.Context(S.KITTI_W, S.KITTI_H, 2000, max_batch=T, max_points=max(p.shape[1] for p in pc2), device=local_rank)
-            b2 = F.RgblBatch(c2, im2, pc2, seq2.P, prm, pinned=False)
-            b2.upload()
-            ctxs.append(c2); batches.append(b2); pose0s.append(seq2.pose(0))
-        batch.upload()
-
-        def multi_rounds(k):
-            pend = [False] * nS
-            for _ in range(k):
-                for i in range(nS):
-                    batches[i].process_resident()
-                    if pend[i]:
-                        batches[i].track_end()
-                    batches[i].track_begin(pose0s[i], *CAM, th=15.0); pend[i] = True
-            return [batches[i].track_end() for i in range(nS)]
-
-        multi_rounds(2)
-        torch.cuda.synchronize()
-        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        t0 = time.perf_counter()
-        res = multi_rounds(args.steps)
-        torch.cuda.synchronize()
-        ms = 1e3 * (time.perf_counter() - t0)
-        multi = {"sequences_per_gpu": nS, "value": nS * T * args.steps / (ms * 1e-3), "unit": UNIT, "ms_per_round": ms / args.steps,
-                 "timing": "host wall clock around K rounds with device synchronisation on both sides (several library streams)",
-                 "inliers_per_frame": [float(np.mean(r[2][1:])) for r in res]}
-        for c2 in ctxs[1:]:
-            c2.close()
-
-    # ---- Frame::ComputeBoW (SURVEY 8(f) row 1; keyframes only in the reference, reported on its own, not part of `value`) ----
-    bow = None
-    if world == 1 and not args.no_bow:
+def side_bow_lba(F, torch, local_rank, with_cpu):
+    """Frame::ComputeBoW and Optimizer::LocalBundleAdjustment (SURVEY 8(f) rows 1-2; key-frame / mapping-thread work, reported on their own)."""
+    cfg = CONFIGS["B"]
+    seq = make_sequence(cfg, 77)
+    T = 4
+    ctx = F.Context(cfg["W"], cfg["H"], cfg["nfeat"], max_batch=T, max_points=seq.cloud(0).shape[1], device=local_rank)
+    bow = lba = None
+    try:
+        batch = F.RgblBatch(ctx, [seq.image(f) for f in range(T)], [seq.cloud(f) for f in range(T)], seq.P, F.make_depth_params(bf=cfg["cam"][4]), pinned=False)
         k_, L_ = 10, 6                                     # the shape of ORBvoc.txt (k = 10, L = 6: 1 111 111 nodes)
         nn = (k_ ** (L_ + 1) - 1) // (k_ - 1)
         rng = np.random.default_rng(7)
@@ -352,171 +510,39 @@ def main():
         nw = np.zeros(nn, np.float64); nw[inner:] = rng.uniform(0.5, 12.0, nn - inner)
         voc = F.ORBVocabulary(ctx, cb, ci, nd, nw, wid, L_)
         batch.upload(); batch.process_resident()
-        for f in range(3):
+        for f in range(T):
             voc.transform_resident(f)
         t0 = time.perf_counter()
-        res = [voc.transform_resident(f) for f in range(T)]
-        gpu_ms = 1e3 * (time.perf_counter() - t0) / T
+        res = [voc.transform_resident(f % T) for f in range(16)]
+        gpu_ms = 1e3 * (time.perf_counter() - t0) / 16
         voc.close()
         bow = {"gpu_ms_per_frame": gpu_ms, "words_per_frame": float(np.mean([len(r[0][0]) for r in res])),
-               "vocabulary": f"synthetic k={k_} L={L_} ({nn} nodes, {nn * 32 / 1e6:.0f} MB of node descriptors), TF-IDF / L1, levelsup 4",
+               "vocabulary": f"synthetic k={k_} L={L_} ({nn} nodes), TF-IDF / L1, levelsup 4",
                "timing": "host wall clock per rgbl_resident_compute_bow call (descriptors already in HBM; includes the D2H of both maps)"}
-        if not args.no_cpu_baseline:
+        if with_cpu:
             from oracle import compute_bow as cpu_bow
             vd = dict(child_begin=cb, child_index=ci, node_desc=nd, node_weight=nw, word_id=wid, levels=L_)
-            descs = [o[1] for o in batch.download()[:4]]
+            descs = [o[1] for o in batch.download()[:2]]
             t0 = time.perf_counter()
             for dsc in descs:
                 cpu_bow(vd, dsc)
             bow["cpu_ms_per_frame"] = 1e3 * (time.perf_counter() - t0) / len(descs)
-            bow["cpu"] = "oracle (std::map restatement of DBoW2 transform), one core"
-
-    # ---- Optimizer::LocalBundleAdjustment (mapping thread, reported on its own) ----
-    lba = None
-    if world == 1 and not args.no_bow:
-        sys.path.insert(0, str(ROOT / "tests"))
-        import ba_data
-        prob = ba_data.make_problem(42, n_kf=20, n_fixed=4, n_points=2500, outlier_frac=0.02)
-        F.local_bundle_adjustment(ctx, *ba_data.args(prob))
+        prob = S.make_ba_problem(42, n_kf=20, n_fixed=4, n_points=2500, outlier_frac=0.02)
+        F.local_bundle_adjustment(ctx, *S.ba_args(prob))
         t0 = time.perf_counter()
         for _ in range(3):
-            gpo, gpt, ger, git = F.local_bundle_adjustment(ctx, *ba_data.args(prob))
-        gpu_ms = 1e3 * (time.perf_counter() - t0) / 3
-        lba = {"gpu_ms": gpu_ms, "key_frames": 20, "fixed": 4, "points": 2500, "edges": int(len(prob["e_point"])), "lm_iterations": int(git),
-               "timing": "host wall clock per rgbl_local_bundle_adjustment call with host arrays (uploads, ~12 launches + one scalar read-back per LM trial, downloads)"}
-        if not args.no_cpu_baseline:
+            gpo, gpt, ger, git = F.local_bundle_adjustment(ctx, *S.ba_args(prob))
+        lba = {"gpu_ms": 1e3 * (time.perf_counter() - t0) / 3, "key_frames": 20, "fixed": 4, "points": int(len(prob["points"])), "edges": int(len(prob["e_point"])),
+               "lm_iterations": int(git), "timing": "host wall clock per rgbl_local_bundle_adjustment call with host arrays"}
+        if with_cpu:
             from oracle import local_bundle_adjustment as cpu_lba
             t0 = time.perf_counter()
-            rpo = cpu_lba(*ba_data.args(prob))[0]
+            rpo = cpu_lba(*S.ba_args(prob))[0]
             lba["cpu_ms"] = 1e3 * (time.perf_counter() - t0)
-            lba["cpu"] = "oracle (dense Schur restatement of the g2o problem), one core"
             lba["max_pose_diff_vs_cpu"] = float(np.abs(gpo - rpo).max())
-
-    # ---- online use: ONE new frame at a time through the individual C-ABI calls a tracking thread makes (host buffers in and
-    # out of every call): Frame construction -> SearchByProjection(last frame) -> PoseOptimization.  Latency, not throughput.
-    online = None
-    if world == 1 and not args.no_bow:
-        def unproject_identity_rotation(fr, pose_):        # Frame::UnprojectStereo (src/Frame.cc:1137-1150); the synthetic camera does not rotate
-            f32 = np.float32
-            z = fr["dep"]; zz = np.where(z > 0, z, f32(1)).astype(f32)
-            x = ((fr["k"]["x"] - f32(S.KITTI_CX)) * zz * f32(1.0 / np.float32(S.KITTI_FX))).astype(f32)
-            y = ((fr["k"]["y"] - f32(S.KITTI_CY)) * zz * f32(1.0 / np.float32(S.KITTI_FY))).astype(f32)
-            return (np.stack([x, y, zz], 1) - np.asarray(pose_[4:7], f32)).astype(f32), (z > 0)
-
-        c1 = F.Context(S.KITTI_W, S.KITTI_H, 2000, max_batch=1, max_points=max_pts, device=local_rank)
-        matcher = F.ORBmatcher(c1, 0.9, True)
-        sfac = F.orb_tables(2000)["scale"][:8].astype(np.float32)
-        t_stage = np.zeros(3); n_on = 0; pose = seq.pose(0); last = None
-        for t in range(min(T, 14)):
-            t0 = time.perf_counter()
-            (k, d, dep, ur), = F.frame_rgbl_batch(c1, [imgs[t]], [pcs[t]], P, prm)
-            t1 = time.perf_counter()
-            cur = dict(k=k, d=d, dep=dep, ur=ur)
-            if last is not None:
-                xw, ok = unproject_identity_rotation(last, pose)
-                gfv = F.FrameView(k, ur, d, S.KITTI_W, S.KITTI_H, sfac, *CAM)
-                _, match = matcher.SearchByProjectionLastFrame(gfv, pose, pose, ok.astype(np.uint8), xw, last["d"], last["k"]["octave"],
-                                                               last["k"]["angle"], np.ones(len(ok), np.uint8), 15.0)
-                t2 = time.perf_counter()
-                m = np.nonzero(match >= 0)[0]
-                obs = np.stack([k["x"][m], k["y"][m], ur[m]], 1)
-                inv_s2 = (1.0 / sfac[k["octave"][m]] ** 2).astype(np.float32)
-                _, pose, _ = F.Optimizer.PoseOptimization(c1, pose, xw[match[m]], obs, inv_s2, (ur[m] >= 0).astype(np.uint8), *CAM)
-                t3 = time.perf_counter()
-                if t >= 3:
-                    t_stage += [t1 - t0, t2 - t1, t3 - t2]; n_on += 1
-            last = cur
-        c1.close()
-        if n_on:
-            ms = 1e3 * t_stage / n_on
-            online = {"per_frame_ms": float(ms.sum()), "frame_construction_ms": float(ms[0]), "search_by_projection_ms": float(ms[1]),
-                      "pose_optimization_ms": float(ms[2]), "frames": n_on,
-                      "note": "one frame per call, host arrays in and out of each C-ABI call, Python glue (unprojection, edge assembly in numpy) included"}
-
-    if rank == 0:
-        # roofline of the dominant kernel (per-stage CUDA-event time / launches, measured above)
-        levels = []
-        from orb_slam3_rgbl_b200 import _lib
-        t = F.orb_tables(2000)
-        for l in range(8):
-            levels.append((int(np.rint(np.float32(S.KITTI_W) * t["inv_scale"][l])), int(np.rint(np.float32(S.KITTI_H) * t["inv_scale"][l]))))
-        # candidates: measure from the last processed batch
-        n_cand = 0
-        try:
-            ex = F.ORBextractor(2000, 1.2, 8, 12, 7, S.KITTI_W, S.KITTI_H, ctx=ctx)
-            n_cand = int(np.mean([sum(len(ex.level_candidates(l, f)) for l in range(8)) for f in range(min(T, 4))]))
-        except Exception:
-            pass
-        n_in = int(0.13 * max_pts)
-        per_frame = algorithmic_bytes(levels, n_cand, float(np.mean(n_kp)), max_pts, S.KITTI_W, S.KITTI_H, n_in)
-        peaks_path = ROOT / "MEASURED_PEAKS.json"
-        if peaks_path.exists():
-            peak = float(json.loads(peaks_path.read_text())["hbm_gbs"]); peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)"
-        else:
-            peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
-        kernels = {}
-        other = {}
-        for name, st in prof.items():
-            if name.startswith("_") or st["calls"] == 0:
-                continue
-            if name not in per_frame:
-                other[name] = {"ms_per_step": st["ms"] / args.steps, "launches_per_step": st["launches"] / args.steps}
-                continue
-            ms_per_call = st["ms"] / st["calls"]
-            gbs = per_frame[name] * T / (ms_per_call * 1e-3) / 1e9
-            kernels[name] = {"ms_per_step": ms_per_call, "launches_per_step": st["launches"] / st["calls"],
-                             "algorithmic_MB_per_step": per_frame[name] * T / 1e6, "achieved_GBs": gbs, "frac": gbs / peak}
-        def roof(name, kd, note=None):
-            r = {"bound": "hbm", "kernel": name, "achieved": kd["achieved_GBs"], "peak": peak, "unit": "GB/s",
-                 "frac": kd["frac"], "traffic": TRAFFIC.get(name), "peak_source": peak_src,
-                 "avg_launch_ms": kd["ms_per_step"] / max(kd["launches_per_step"], 1),
-                 "algorithmic_bytes_per_launch": kd["algorithmic_MB_per_step"] * 1e6 / max(kd["launches_per_step"], 1)}
-            if note:
-                r["note"] = note
-            return r
-
-        # tracking chain (grid + collect + resolve + edges + PoseOptimization per frame): 64 B per evaluated descriptor pair
-        # and 64 B per edge per LM evaluation; latency-bound by construction (serial in time, one CTA)
-        if "match" in other:
-            pairs = 30000.0; evals = 60.0
-            bytes_step = (T - 1) * (64.0 * pairs + 64.0 * float(np.mean(nm[1:])) * evals)
-            ms = other["match"]["ms_per_step"]
-            kernels["tracking_chain"] = {"ms_per_step": ms, "launches_per_step": other["match"]["launches_per_step"],
-                                         "algorithmic_MB_per_step": bytes_step / 1e6, "achieved_GBs": bytes_step / (ms * 1e-3) / 1e9,
-                                         "frac": bytes_step / (ms * 1e-3) / 1e9 / peak}
-        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
-        roofline = None
-        if dom:
-            roofline = roof(dom, kernels[dom], "latency-bound serial chain (pose_optimize_kernel ~80 % of it): one persistent CTA per frame, FP64 LM"
-                            if dom == "tracking_chain" else None)
-        stream = {k: v for k, v in kernels.items() if k != "tracking_chain"}
-        dom_s = max(stream, key=lambda k: stream[k]["ms_per_step"]) if stream else None
-        roofline_streaming = roof(dom_s, stream[dom_s], "dominant frame-construction kernel; FAST is ALU/issue-bound (see DESIGN.md 4)") if dom_s else None
-        working_set_mb = (2 * 1.74 + 4 * 4 * max_pts / 1e6 + 2 * 4 * S.KITTI_W * S.KITTI_H / 1e6) * T
-        line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD,
-                           "frames_per_step_per_gpu": T, "parallelism": f"sequences sharded x{world}",
-                           "l2": f"inputs larger than L2: ~{working_set_mb:.0f} MB touched per step vs 126 MB L2",
-                           "timing": "CUDA events on the library stream around K steps, max over ranks",
-                           "pipeline": "frame construction of batch i+1 overlaps the tracking chain of batch i (two streams); the last chain drains inside the timed region; per-stage times below are measured under that overlap"},
-                "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": batch.h2d_bytes, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": int(prof["_total_launches"]),
-                "clocks": clocks, "roofline": roofline, "roofline_frame_construction": roofline_streaming, "kernels": kernels, "latency_bound_stages": other,
-                "tracking": {"matches_per_frame": float(np.mean(nm[1:])), "inliers_per_frame": float(np.mean(ni[1:])),
-                             "pose_x_error_m_last_frame": float(abs(poses[-1, 4] - seq.pose(T - 1)[4]))},
-                "multi_sequence_capacity": multi, "compute_bow": bow, "local_bundle_adjustment": lba, "online_single_frame": online,
-                "host_quadtree_ms_per_step": prof["_host_quadtree_ms"] / args.steps,
-                "wall_ms_per_step": wall_ms / args.steps}
-        if world == 1 and not args.no_cpu_baseline:
-            v, n = cpu_baseline_single(imgs, pcs, seq)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"{n} frames of the same workload, oracle (C++ restatement of ORBextractor + DepthModule + SearchByProjection + PoseOptimization, scalar, -O3) on one core"}
-        print(json.dumps(line))
-    ctx.close()
-    rep.close()
+    finally:
+        ctx.close()
+    return bow, lba
 
 
 if __name__ == "__main__":

@@ -335,6 +335,29 @@ int rgbl_resident_track_begin2(rgbl_ctx* ctx, const rgbl_chain_params* prm);
  * batch overflowed a capacity (the keypoint sets were truncated) or a matcher candidate list overflowed.                        */
 int rgbl_resident_track_end2(rgbl_ctx* ctx, float* poses_out, int* n_matches, int* n_inliers, int* n_local_matches, int* n_inliers_first);
 
+/* ---- Sequence runner: the loop of Examples/RGB-L/rgbl_kitti.cc:84-133 (load frame -> SLAM.TrackRGBL -> pose) for many frames per
+ * call, entirely native.  Per batch of frames_per_batch consecutive frames: inputs -> frame construction -> tracking chain
+ * (rgbl_chain_params; batches after the first continue the sequence) -> poses.  The chains are queued two deep, so the frame
+ * construction (and host<->device copies) of batch b+1 overlap the tracking of batch b and the device never waits for the caller.
+ *   host-input mode   gray != NULL: gray / pts4xn / n_pts hold one entry per frame of the call ([n_batches * frames_per_batch]);
+ *                     pinned host memory makes the copies asynchronous;
+ *   resident mode     gray == NULL: batch b processes the staged slot (first_slot + b) % n_slots (rgbl_resident_stage uploads a batch
+ *                     into a device slot once; up to 8 slots) - device throughput without host->device input traffic.
+ * Outputs (host, one entry per frame of the call): poses[.][7], n_matches, n_inliers (after the frame's last PoseOptimization),
+ * n_local_matches (nullable).  kps != NULL additionally returns the frame-construction outputs of every frame ([.][cap] arrays, cap =
+ * rgbl_keypoint_capacity(); n_kp[.] valid entries per frame).                                                                      */
+typedef struct rgbl_sequence_io {
+    int n_batches, frames_per_batch;
+    int width, height, stride;
+    const uint8_t* const* gray; const float* const* pts4xn; const int* n_pts;
+    int n_slots, first_slot;
+    float* poses; int* n_matches; int* n_inliers; int* n_local_matches;
+    rgbl_keypoint* kps; uint8_t* desc; float* depth; float* uright; int cap; int* n_kp;
+} rgbl_sequence_io;
+int rgbl_resident_stage(rgbl_ctx* ctx, int slot, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
+                        const float* const* pts4xn, const int* n_pts);
+int rgbl_track_sequence(rgbl_ctx* ctx, const float P[12], const rgbl_depth_params* prm, const rgbl_chain_params* chain, const rgbl_sequence_io* io);
+
 /* Keypoint distribution (DistributeOctTree) runs on the device by default (one CTA per (frame, level)); on != 0
  * selects the host implementation instead (also: environment RGBL_HOST_QUADTREE=1).  Both are exact.           */
 int rgbl_set_host_quadtree(rgbl_ctx* ctx, int on);
@@ -345,7 +368,9 @@ int rgbl_timer_mark(rgbl_ctx* ctx, int which);
 int rgbl_timer_elapsed_ms(rgbl_ctx* ctx, double* ms);
 
 /* ---- profiling: CUDA-event time per stage on the launching streams, kernel launch counts.  The
- * reference's counterpart is REGISTER_TIMES (include/Settings.h:24, src/Frame.cc:311-319).          */
+ * reference's counterpart is REGISTER_TIMES (include/Settings.h:24, src/Frame.cc:311-319).  on = 1: as the pipeline runs (the blur /
+ * depth-map work of the auxiliary stream overlaps FAST's successors, so stage times overlap too); on = 2: the auxiliary stream is
+ * joined before the quad-tree, so that no two kernels of the context run at the same time and every stage time is its own.   */
 int rgbl_profile_enable(rgbl_ctx* ctx, int on);
 int rgbl_profile_reset(rgbl_ctx* ctx);
 int rgbl_profile_num_stages(void);

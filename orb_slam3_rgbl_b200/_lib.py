@@ -100,6 +100,8 @@ SYMBOLS = {
     "rgbl_resident_track_begin": (_i, [_vp, _vp, _f, _f, _f, _f, _f, _f, _i]),
     "rgbl_resident_track_end": (_i, [_vp, _vp, _vp, _vp]),
     "rgbl_resident_track_begin2": (_i, [_vp, _vp]),
+    "rgbl_resident_stage": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "rgbl_track_sequence": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "rgbl_resident_track_end2": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "rgbl_set_host_quadtree": (_i, [_vp, _i]),
     "rgbl_timer_mark": (_i, [_vp, _i]),

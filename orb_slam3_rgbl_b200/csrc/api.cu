@@ -52,6 +52,7 @@ static void release(Ctx* c) {
         if (c->ev_chain_e[i]) cudaEventDestroy(c->ev_chain_e[i]);
         if (c->ev_chain_done[i]) cudaEventDestroy(c->ev_chain_done[i]);
     }
+    for (Ctx::StageSlot& sl : c->stage) { if (sl.img) cudaFree(sl.img); if (sl.pts) cudaFree(sl.pts); if (sl.n_pts) cudaFree(sl.n_pts); }
     if (c->h_chain_f) cudaFreeHost(c->h_chain_f);
     if (c->h_chain_i) cudaFreeHost(c->h_chain_i);
     if (c->st) cudaStreamDestroy(c->st);
@@ -247,6 +248,7 @@ static int run_extract(Ctx* c, int n_frames, const std::function<void()>& aux_wo
     stage_end(c, ST_BLUR, c->st_aux, nl);
     if (aux_work) aux_work();
     CU(cudaEventRecord(c->ev_blur, c->st_aux));
+    if (c->prof_serial) CU(cudaStreamWaitEvent(c->st, c->ev_blur, 0));      // rgbl_profile_enable(ctx, 2): no kernel of this context overlaps another
     if (c->device_quadtree) {
         // Fully on-device keypoint distribution: no host round trip between FAST and describe.
         stage_begin(c, ST_QUADTREE, c->st);
@@ -760,6 +762,119 @@ int rgbl_resident_process(rgbl_ctx* ctx, const float P[12], const rgbl_depth_par
     return RGBL_OK;
 }
 
+/* ---- sequence runner: many consecutive batches of ONE sequence per host call ------------------------------------------------------
+ * The per-batch calls above return to the caller between batches; with a slow caller (Python, several ranks on one host) the device
+ * waits for the host.  rgbl_track_sequence keeps the whole loop native: per batch  inputs (host buffers, or a staged device slot) ->
+ * frame construction -> tracking chain (queued two deep on the tracking stream, continue_sequence from the second batch on) -> poses
+ * (and, if asked for, the frame-construction outputs) back to the host.  Nothing synchronises with the device until a chain's results
+ * are collected, one batch behind.                                                                                                   */
+int rgbl_resident_stage(rgbl_ctx* ctx, int slot, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
+                        const float* const* pts4xn, const int* n_pts) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!gray || !pts4xn || !n_pts) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (slot < 0 || slot >= Ctx::kMaxStageSlots) { c->err = "stage slot out of range"; return RGBL_E_INVALID; }
+    if (!c->d_pts) { c->err = "context was created with max_points == 0"; return RGBL_E_INVALID; }
+    int rc = check_batch_args(c, n_frames, width, height, stride); if (rc) return rc;
+    CU(cudaSetDevice(c->cfg.device));
+    const LevelGeom& l0 = c->levels[0];
+    const size_t img_bytes = (size_t)l0.pitch * c->cfg.height, pts_floats = (size_t)4 * c->cfg.max_points;
+    Ctx::StageSlot& sl = c->stage[slot];
+    if (!sl.img) {
+        if (cudaMalloc((void**)&sl.img, (size_t)c->cfg.max_batch * img_bytes) != cudaSuccess ||
+            cudaMalloc((void**)&sl.pts, (size_t)c->cfg.max_batch * pts_floats * sizeof(float)) != cudaSuccess ||
+            cudaMalloc((void**)&sl.n_pts, (size_t)c->cfg.max_batch * sizeof(int)) != cudaSuccess) {
+            cudaGetLastError(); c->err = "cudaMalloc failed (stage slot)"; return RGBL_E_CUDA;
+        }
+    }
+    int max_pts = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        if (!gray[f]) { c->err = "empty image"; return RGBL_E_EMPTY; }
+        if (n_pts[f] < 0 || n_pts[f] > c->cfg.max_points || (n_pts[f] && !pts4xn[f])) { c->err = "bad point cloud"; return RGBL_E_CAPACITY; }
+        max_pts = std::max(max_pts, n_pts[f]);
+        CU(cudaMemcpy2DAsync(sl.img + (size_t)f * img_bytes, l0.pitch, gray[f], stride, c->cfg.width, c->cfg.height, cudaMemcpyHostToDevice, c->st));
+        if (n_pts[f]) CU(cudaMemcpyAsync(sl.pts + (size_t)f * pts_floats, pts4xn[f], (size_t)4 * n_pts[f] * sizeof(float), cudaMemcpyHostToDevice, c->st));
+    }
+    sl.h_n_pts.assign(n_pts, n_pts + n_frames);
+    CU(cudaMemcpyAsync(sl.n_pts, sl.h_n_pts.data(), (size_t)n_frames * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    sl.n_frames = n_frames; sl.max_pts = max_pts;
+    return RGBL_OK;
+}
+
+// staged slot -> the context's working input buffers (device-to-device, ~76 MB per 32 KITTI frames: tens of microseconds)
+static int restage(Ctx* c, int slot) {
+    const Ctx::StageSlot& sl = c->stage[slot];
+    if (!sl.img || sl.n_frames < 1) { c->err = "stage slot is empty"; return RGBL_E_INVALID; }
+    const LevelGeom& l0 = c->levels[0];
+    const size_t img_bytes = (size_t)l0.pitch * c->cfg.height, pts_floats = (size_t)4 * c->cfg.max_points;
+    for (int f = 0; f < sl.n_frames; ++f)
+        CU(cudaMemcpyAsync(c->d_pyr + (size_t)f * c->frame_bytes + l0.off, sl.img + (size_t)f * img_bytes, img_bytes, cudaMemcpyDeviceToDevice, c->st));
+    CU(cudaMemcpyAsync(c->d_pts, sl.pts, (size_t)sl.n_frames * pts_floats * sizeof(float), cudaMemcpyDeviceToDevice, c->st_aux));
+    CU(cudaMemcpyAsync(c->d_n_pts, sl.n_pts, (size_t)sl.n_frames * sizeof(int), cudaMemcpyDeviceToDevice, c->st_aux));
+    for (int f = 0; f < sl.n_frames; ++f) c->h_n_pts[f] = sl.h_n_pts[f];
+    c->resident_frames = sl.n_frames; c->resident_max_pts = sl.max_pts;
+    return RGBL_OK;
+}
+
+int rgbl_track_sequence(rgbl_ctx* ctx, const float P[12], const rgbl_depth_params* prm, const rgbl_chain_params* chain, const rgbl_sequence_io* io) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!P || !prm || !chain || !io || !io->poses || !io->n_matches || !io->n_inliers) { c->err = "null argument"; return RGBL_E_INVALID; }
+    const int T = io->frames_per_batch, nb = io->n_batches;
+    if (T < 1 || T > c->cfg.max_batch || nb < 1) { c->err = "bad batch geometry"; return RGBL_E_INVALID; }
+    if (c->chain_pending) { c->err = "a tracking chain is in flight (rgbl_resident_track_end not called)"; return RGBL_E_INVALID; }
+    const bool host_in = io->gray != nullptr;
+    if (host_in) {
+        if (!io->pts4xn || !io->n_pts) { c->err = "null argument"; return RGBL_E_INVALID; }
+        int rc = check_batch_args(c, T, io->width, io->height, io->stride); if (rc) return rc;
+    } else if (io->n_slots < 1 || io->n_slots > Ctx::kMaxStageSlots) { c->err = "resident mode needs 1..8 staged slots"; return RGBL_E_INVALID; }
+    const bool want_frames = io->kps != nullptr;
+    if (want_frames && (!io->desc || !io->depth || !io->uright || !io->n_kp || io->cap != c->cap_kp)) {
+        c->err = "frame outputs need kps, desc, depth, uright, n_kp and cap == rgbl_keypoint_capacity()"; return RGBL_E_INVALID;
+    }
+    CU(cudaSetDevice(c->cfg.device));
+    rgbl_chain_params cp = *chain;
+    int collected = 0;
+    auto collect = [&]() -> int {
+        const size_t o = (size_t)collected * T;
+        const int rc = rgbl_resident_track_end2(ctx, io->poses + o * 7, io->n_matches + o, io->n_inliers + o,
+                                                io->n_local_matches ? io->n_local_matches + o : nullptr, nullptr);
+        ++collected;
+        return rc;
+    };
+    for (int b = 0; b < nb; ++b) {
+        int max_pts = 0, rc;
+        if (host_in) {
+            rc = upload_rgbl(c, T, io->gray + (size_t)b * T, io->stride, io->pts4xn + (size_t)b * T, io->n_pts + (size_t)b * T, &max_pts);
+        } else {
+            rc = restage(c, (io->first_slot + b) % io->n_slots); max_pts = c->resident_max_pts;
+            if (!rc && c->resident_frames != T) { c->err = "staged slot holds a different number of frames"; rc = RGBL_E_INVALID; }
+        }
+        if (rc) { while (c->chain_pending) collect(); return rc; }
+        rc = process_rgbl(c, T, max_pts, P, prm);
+        if (rc < 0) { while (c->chain_pending) collect(); return rc; }
+        if (want_frames) {        // whole [T][cap] arrays + counts, asynchronously behind the batch's kernels
+            const size_t o = (size_t)b * T, n = (size_t)T * c->cap_kp;
+            CU(cudaMemcpyAsync(io->kps + o * io->cap, c->d_kps, n * sizeof(rgbl_keypoint), cudaMemcpyDeviceToHost, c->st));
+            CU(cudaMemcpyAsync(io->desc + o * io->cap * 32, c->d_desc, n * 32, cudaMemcpyDeviceToHost, c->st));
+            CU(cudaMemcpyAsync(io->depth + o * io->cap, c->d_depth, n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+            CU(cudaMemcpyAsync(io->uright + o * io->cap, c->d_uright, n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+            CU(cudaMemcpyAsync(io->n_kp + o, c->d_n_sel, (size_t)T * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        }
+        cp.continue_sequence = (b > 0 || chain->continue_sequence) ? 1 : 0;
+        rc = rgbl_resident_track_begin2(ctx, &cp);
+        if (rc) { while (c->chain_pending) collect(); return rc; }
+        if (c->chain_pending == 2) { rc = collect(); if (rc) { while (c->chain_pending) collect(); return rc; } }
+    }
+    int rc_all = RGBL_OK;
+    while (c->chain_pending) { const int rc = collect(); if (rc && !rc_all) rc_all = rc; }
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaStreamSynchronize(c->st_aux));
+    prof_collect(c);
+    return rc_all;
+}
+
 int rgbl_resident_download(rgbl_ctx* ctx, rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
@@ -803,6 +918,7 @@ int rgbl_profile_enable(rgbl_ctx* ctx, int on) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
     c->prof_on = on != 0;
+    c->prof_serial = on == 2;
     return RGBL_OK;
 }
 int rgbl_profile_reset(rgbl_ctx* ctx) {

@@ -115,7 +115,7 @@ struct Ctx {
     SelKp* h_sel = nullptr;
 
     // profiling (rgbl_profile_*): CUDA events on the launching stream around every stage
-    bool prof_on = false;
+    bool prof_on = false, prof_serial = false;   // prof_serial: stage timings without stream overlap (the aux-stream work is joined before the quad-tree)
     cudaEvent_t ev_b[kNumStages] = {}, ev_e[kNumStages] = {};
     bool st_used[kNumStages] = {};
     int st_pending_launches[kNumStages] = {};
@@ -166,6 +166,11 @@ struct Ctx {
     cudaGraphExec_t chain_exec[2] = {};
     ChainGraphKey chain_key[2] = {};
     const void* chain_timing_ev = nullptr;   // RGBL_CHAIN_TIMING development aid
+
+    // staged input slots of the sequence runner (rgbl_resident_stage / rgbl_track_sequence): level-0 planes + clouds of whole batches
+    static constexpr int kMaxStageSlots = 8;
+    struct StageSlot { uint8_t* img = nullptr; float* pts = nullptr; int* n_pts = nullptr; std::vector<int> h_n_pts; int n_frames = 0, max_pts = 0; };
+    StageSlot stage[kMaxStageSlots];
 
     int last_frames = 0;         // frames valid in the device buffers
     int resident_frames = 0, resident_max_pts = 0;

@@ -56,6 +56,16 @@ class Reporter:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t.item())
 
+    def gather_floats(self, x: float):
+        """x of every rank, as a list (rank order)."""
+        if not self.dist:
+            return [x]
+        import torch
+        t = self._tensor([x])
+        out = [torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     def throughput(self, frames_this_rank: int, elapsed_s_this_rank: float) -> float:
         """Whole-job frames/s = all frames of all ranks / the slowest rank's time."""
         return self.sum_over_ranks(float(frames_this_rank)) / self.max_over_ranks(elapsed_s_this_rank)

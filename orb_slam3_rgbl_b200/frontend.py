@@ -162,6 +162,14 @@ def compute_stereo_matches(extractor: "ORBextractor", images_lr, mb: float, mbf:
     return (kl, dl), (kr, dr), depth[:len(kl)].copy(), ur[:len(kl)].copy()
 
 
+def stereo_matches_slots(extractor: "ORBextractor", slot_left: int, slot_right: int, n_left: int, mb: float, mbf: float):
+    """Frame::ComputeStereoMatches between two frames of the last batched extraction (rgbl_stereo_matches) -> (mvDepth, mvuRight)"""
+    cap = extractor.ctx.cap
+    depth = np.empty(cap, np.float32); ur = np.empty(cap, np.float32)
+    check(lib().rgbl_stereo_matches(extractor.ctx.handle, slot_left, slot_right, mb, mbf, ptr(depth), ptr(ur), cap), extractor.ctx.handle)
+    return depth[:n_left].copy(), ur[:n_left].copy()
+
+
 def fuse_search(ctx: Context, kf: FrameView, Tcw, Ow, valid, xw, normal, mf_min_dist, mf_max_dist, mp_desc, th=3.0):
     """Search part of ORBmatcher::Fuse(pKF, vpMapPoints, th) -> (bestIdx[n], bestDist[n])"""
     Tcw = np.ascontiguousarray(Tcw, np.float32); Ow = np.ascontiguousarray(Ow, np.float32); valid = np.ascontiguousarray(valid, np.uint8)
@@ -563,6 +571,95 @@ class RgblBatch:
         c = self.ctx
         check(lib().rgbl_resident_download(c.handle, ptr(self.kps), ptr(self.desc), ptr(self.depth), ptr(self.uright), self.cap, ptr(self.n)), c.handle)
         return [(self.kps[f, :self.n[f]], self.desc[f, :self.n[f]], self.depth[f, :self.n[f]], self.uright[f, :self.n[f]]) for f in range(self.nF)]
+
+
+class SequenceIO(C.Structure):
+    """rgbl_sequence_io (include/rgbl_b200.h)."""
+    _fields_ = [("n_batches", C.c_int), ("frames_per_batch", C.c_int), ("width", C.c_int), ("height", C.c_int), ("stride", C.c_int),
+                ("gray", C.c_void_p), ("pts4xn", C.c_void_p), ("n_pts", C.c_void_p), ("n_slots", C.c_int), ("first_slot", C.c_int),
+                ("poses", C.c_void_p), ("n_matches", C.c_void_p), ("n_inliers", C.c_void_p), ("n_local_matches", C.c_void_p),
+                ("kps", C.c_void_p), ("desc", C.c_void_p), ("depth", C.c_void_p), ("uright", C.c_void_p), ("cap", C.c_int), ("n_kp", C.c_void_p)]
+
+
+class SequenceRunner:
+    """rgbl_track_sequence: many consecutive batches of one RGB-L sequence per native call (the loop of Examples/RGB-L/rgbl_kitti.cc).
+    Holds M batches of T frames in pinned host buffers (and, after stage(), in device slots); batches are visited round-robin."""
+
+    def __init__(self, ctx: Context, P, depth_params: DepthParams, T: int, W: int, H: int, max_points: int, n_host_batches: int, pinned=True):
+        self.ctx, self.T, self.W, self.H, self.M, self.maxn = ctx, T, W, H, n_host_batches, max_points
+        alloc = _pinned_alloc if pinned else (lambda shape, dt: np.empty(shape, dt))
+        self._alloc = alloc
+        self.img = alloc((self.M, T, H, W), np.uint8)
+        self.pts = alloc((self.M, T, 4 * max_points), np.float32)
+        self.npts = np.zeros((self.M, T), np.int32)
+        self.P = np.ascontiguousarray(P, np.float32).reshape(12)
+        self.prm = depth_params
+        self._out = None
+
+    def set_batch(self, m: int, images, clouds):
+        for f in range(self.T):
+            self.img[m, f] = images[f]
+            n = clouds[f].shape[1]
+            self.pts[m, f, :4 * n] = np.ascontiguousarray(clouds[f], np.float32).reshape(-1)
+            self.npts[m, f] = n
+
+    def stage(self, slot: int, m: int):
+        """Upload host batch m into device slot `slot` (rgbl_resident_stage)."""
+        ia = (C.c_void_p * self.T)(*[self.img[m, f].ctypes.data for f in range(self.T)])
+        pa = (C.c_void_p * self.T)(*[self.pts[m, f].ctypes.data for f in range(self.T)])
+        n = np.ascontiguousarray(self.npts[m])
+        check(lib().rgbl_resident_stage(self.ctx.handle, slot, self.T, ia, self.W, self.H, self.W, pa, ptr(n)), self.ctx.handle)
+
+    def _outputs(self, nb, want_frames):
+        n = nb * self.T
+        key = (n, want_frames)
+        if self._out is None or self._out[0] != key:
+            a = self._alloc
+            o = dict(poses=a((n, 7), np.float32), n_matches=a((n,), np.int32), n_inliers=a((n,), np.int32), n_local_matches=a((n,), np.int32))
+            if want_frames:
+                cap = self.ctx.cap
+                o.update(kps=a((n, cap), KP_DTYPE), desc=a((n, cap, 32), np.uint8), depth=a((n, cap), np.float32), uright=a((n, cap), np.float32),
+                         n_kp=a((n,), np.int32))
+            self._out = (key, o)
+        return self._out[1]
+
+    def reserve(self, n_batches: int, want_frames: bool):
+        """Allocate the (pinned) output buffers of a later run() of this size now (page-locking ~100 MB takes tens of ms)."""
+        self._outputs(n_batches, want_frames)
+
+    def run(self, chain: ChainParams, n_batches: int, first: int = 0, resident_slots: int = 0, want_frames: bool = False):
+        """n_batches batches starting at host batch / device slot `first` (round-robin).  resident_slots > 0: inputs come from the staged
+        device slots; else from the pinned host buffers (H2D inside the call).  -> dict of per-frame outputs (views of reused buffers)."""
+        T = self.T
+        o = self._outputs(n_batches, want_frames)
+        io = SequenceIO()
+        io.n_batches, io.frames_per_batch, io.width, io.height, io.stride = n_batches, T, self.W, self.H, self.W
+        keep = []
+        if resident_slots > 0:
+            io.gray = None; io.pts4xn = None; io.n_pts = None; io.n_slots = resident_slots; io.first_slot = first % resident_slots
+        else:
+            idx = [(first + b) % self.M for b in range(n_batches)]
+            ga = (C.c_void_p * (n_batches * T))(*[self.img[m, f].ctypes.data for m in idx for f in range(T)])
+            pa = (C.c_void_p * (n_batches * T))(*[self.pts[m, f].ctypes.data for m in idx for f in range(T)])
+            na = np.ascontiguousarray(np.concatenate([self.npts[m] for m in idx]).astype(np.int32))
+            keep += [ga, pa, na]
+            io.gray = C.cast(ga, C.c_void_p); io.pts4xn = C.cast(pa, C.c_void_p); io.n_pts = na.ctypes.data
+        io.poses = o["poses"].ctypes.data; io.n_matches = o["n_matches"].ctypes.data; io.n_inliers = o["n_inliers"].ctypes.data
+        io.n_local_matches = o["n_local_matches"].ctypes.data
+        if want_frames:
+            io.kps = o["kps"].ctypes.data; io.desc = o["desc"].ctypes.data; io.depth = o["depth"].ctypes.data; io.uright = o["uright"].ctypes.data
+            io.cap = self.ctx.cap; io.n_kp = o["n_kp"].ctypes.data
+        check(lib().rgbl_track_sequence(self.ctx.handle, ptr(self.P), C.byref(self.prm), C.byref(chain), C.byref(io)), self.ctx.handle)
+        return o
+
+    def h2d_bytes_per_batch(self) -> float:
+        return float(self.T * self.W * self.H + 16.0 * self.npts.sum() / self.M)
+
+    def d2h_bytes_per_batch(self, want_frames: bool) -> float:
+        b = self.T * (7 * 4 + 3 * 4)
+        if want_frames:
+            b += self.T * (self.ctx.cap * (28 + 32 + 4 + 4) + 4)
+        return float(b)
 
 
 _pinned_keep = []

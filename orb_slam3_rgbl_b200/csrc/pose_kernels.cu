@@ -1,8 +1,11 @@
-// Optimizer::PoseOptimization (src/Optimizer.cc:814-1114) as ONE persistent CTA per frame: the whole
-// 4 x (<= 10 Levenberg-Marquardt iterations x <= 10 trials) schedule of g2o runs on the device in FP64
-// with no host round trip.  Threads stride over the edges; J^T W J (21 unique entries), J^T W r (6) and
-// the robust chi2 are reduced with warp shuffles + a fixed 8-way shared-memory tree (deterministic);
-// thread 0 does the 6x6 pivoted LDL^T solve, the SE3 exponential update and the LM bookkeeping.
+// Optimizer::PoseOptimization (src/Optimizer.cc:814-1114) as ONE thread-block CLUSTER of 4 CTAs (4 SMs) per frame: the whole
+// 4 x (<= 10 Levenberg-Marquardt iterations x <= 10 trials) schedule of g2o runs on the device in FP64 with no host round trip.
+// The ~500-800 edges of a frame are strided over the 4 x 256 threads of the cluster (one pass; the per-edge Jacobian / J^T W J work
+// is bound by the FP64 issue rate of an SM, so four SMs cut it four ways).  J^T W J (21 unique entries), J^T W r (6) and the robust
+// chi2 are reduced inside each CTA with warp shuffles + a fixed shared-memory tree, the four partial sums are exchanged through
+// distributed shared memory (each CTA stores its 28 sums into every CTA's exchange slot, one barrier.cluster) and added in rank order
+// by every CTA, so all four hold bit-identical systems and take the LM decisions redundantly: no broadcast, two cluster barriers per
+// LM trial.  In each CTA, lane 0 of warp w solves the damped 6x6 system of trial w (LDL^T), applies the SE3 exponential update.
 // g2o semantics reproduced (Thirdparty/g2o/g2o/: core/optimization_algorithm_levenberg.cpp:61-185,
 // core/base_unary_edge.hpp:43-72, core/robust_kernel_impl.cpp:65-91, types/se3quat.h:104-110,214-254,280-285,
 // types/types_six_dof_expmap.cpp:339-404; src/OptimizableTypes.cpp:49-63):
@@ -14,11 +17,14 @@
 //   * every round restarts from the frame's initial pose; inlier edges are classified with the error of
 //     the LAST evaluated trial (g2o does not recompute it), outlier edges are recomputed.
 #include <cfloat>
+#include <cooperative_groups.h>
 
 #include "rgbl_device.cuh"
 #include "rgbl_kernels.h"
 
 namespace rgbl {
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -170,81 +176,6 @@ __device__ __forceinline__ bool solve6(const double* Hsym /*21 upper*/, double l
     return true;
 }
 
-#ifndef POSE_MIXED_SOLVE
-#define POSE_MIXED_SOLVE 0
-#endif
-#if POSE_MIXED_SOLVE
-// Candidate for the next round (NOT the default, not yet run on a GPU): the same system solved by an unpivoted LDL^T in
-// float32 plus ONE step of iterative refinement with the residual formed in float64.  The serial solve is bound by the
-// latency of dependent operations, and a dependent float32 operation costs ~4 cycles against ~30 for float64; the
-// refinement step restores the accuracy ((cond * 2^-24)^2 relative).  tests/tools/pose_precision_study.cpp: on 300 synthetic
-// tracking problems the float32 poses PoseOptimization returns are bit-identical to the float64 solve's in all 300 and no
-// outlier flag changes (without the refinement step 225 of 300 poses change, by up to 1.4e-5 m).
-__device__ __forceinline__ bool solve6_mixed(const double* Hsym /*21 upper*/, double lambda, const double* b, double* x) {
-    float L[6][6], dinv[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 6; ++j)
-            if (j >= i) L[j][i] = (float)(Hsym[i * 6 - (i * (i - 1)) / 2 + (j - i)] + ((i == j) ? lambda : 0.0));
-    bool positive = true;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        const float d = L[k][k];
-        positive = positive && (d >= 0.f) && (d <= FLT_MAX);
-        dinv[k] = (d >= FLT_MIN && d <= FLT_MAX) ? __frcp_rn(d) : 0.f;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            if (i > k) {
-                const float aik = L[i][k], lik = aik * dinv[k];
-#pragma unroll
-                for (int j = 0; j < 6; ++j)
-                    if (j > k && j < i) L[i][j] -= aik * L[j][k];
-                L[i][i] -= aik * lik;
-                L[i][k] = lik;
-            }
-        }
-    }
-    if (!positive) return false;
-    double xs[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        float y[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {                       // residual b - (H + lambda I) x in float64 (x = 0 in the first pass)
-            double r = b[i];
-            if (pass) {
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    const int lo = i < j ? i : j, hi = i < j ? j : i;
-                    r = fma(-(Hsym[lo * 6 - (lo * (lo - 1)) / 2 + (hi - lo)] + ((i == j) ? lambda : 0.0)), xs[j], r);
-                }
-            }
-            y[i] = (float)r;
-        }
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-                if (i > k) y[i] -= L[i][k] * y[k];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) y[i] *= dinv[i];
-#pragma unroll
-        for (int jj = 0; jj < 5; ++jj) {
-            const int j = 5 - jj;
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-                if (i < j) y[i] -= L[j][i] * y[j];
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) xs[i] += (double)y[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) x[i] = xs[i];
-    return true;
-}
-#endif
-
 // 1/sqrt(x) for a positive normal double: MUFU.RSQ64H seed + two Newton steps (7 dependent operations)
 __device__ __forceinline__ double rsqrt_newton(double x) {
     double y;
@@ -275,14 +206,70 @@ __device__ __forceinline__ void huber(double e2, double delta, float dsqr, doubl
 }
 
 constexpr int kAcc = 28;      // 21 H + 6 b + 1 chi
-constexpr int kPoseThreads = 512, kPoseWarps = kPoseThreads / 32;
-constexpr int kMaxTrials = 10;    // g2o _maxTrialsAfterFailure
-constexpr int kCacheEdges = 1024; // edges whose camera-frame point is cached in shared memory (32 KB)
+constexpr int kPoseCtas = 4;      // CTAs (SMs) of the cluster that optimises one frame
+constexpr int kPoseThreads = 256, kPoseWarps = kPoseThreads / 32, kPoseStride = kPoseCtas * kPoseThreads;
+constexpr int kMaxTrials = 10;    // g2o _maxTrialsAfterFailure (warps 0..7 solve trials 0..7, warps 0..1 also 8..9)
+constexpr int kCacheEdges = 512;  // edges PER CTA whose camera-frame point is cached in shared memory (16 KB)
 
-// block-wide sum of kAcc doubles.  Inside a warp the 28 sums are folded with a halving butterfly: at distance h every lane
+// ---- cluster-wide sums without a cluster barrier ----------------------------------------------------------------------------------
+// barrier.cluster costs ~1.3k cycles here (measured with clock64: arrival skew of four SMs + the L1 invalidation its acquire implies),
+// 58 times per call.  Instead every CTA pushes its partial sums straight into the other CTAs' shared memory with st.async, which
+// also signals the RECEIVER's mbarrier (complete_tx): a CTA only waits for the 4 x n x 8 bytes addressed to itself.  Exchanges are
+// numbered; exchange s uses buffer / mbarrier s & 1, so a CTA that runs ahead writes into the other buffer (it cannot run two
+// exchanges ahead: it needs everybody's data of exchange s + 1 first, and those are sent after exchange s was read).  All CTAs add
+// the four partials in rank order: bit-identical totals everywhere.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+struct ClusterXchg {
+    double (*buf)[kPoseCtas][32];     // [2][kPoseCtas][32], shared
+    unsigned long long* mbar;         // [2], shared
+    unsigned rank, seq;
+    __device__ __forceinline__ void init() {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[0])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[1])));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    // thread t < n_vals contributes v (its CTA's partial of value t); afterwards out[t] (shared) holds the cluster total, for all threads
+    __device__ __forceinline__ void sum(double v, int n_vals, double* out) {
+        const unsigned b = seq & 1, parity = (seq >> 1) & 1;
+        ++seq;
+        const uint32_t mb = smem_u32(&mbar[b]);
+        if (threadIdx.x == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(kPoseCtas * n_vals * 8) : "memory");
+        if ((int)threadIdx.x < n_vals) {
+            const uint32_t slot = smem_u32(&buf[b][rank][threadIdx.x]);
+#pragma unroll
+            for (unsigned r = 0; r < kPoseCtas; ++r)
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                             :: "r"(mapa_u32(slot, r)), "l"(__double_as_longlong(v)), "r"(mapa_u32(mb, r)) : "memory");
+        }
+        if (threadIdx.x < 32) {
+            uint32_t done = 0, spins = 0;
+            while (!done) {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+                if (!done && ++spins > (1u << 24)) __trap();      // a lost exchange must fail loudly, not hang the device
+            }
+            if ((int)threadIdx.x < n_vals) {
+                double t = buf[b][0][threadIdx.x];
+#pragma unroll
+                for (int r = 1; r < kPoseCtas; ++r) t += buf[b][r][threadIdx.x];
+                out[threadIdx.x] = t;
+            }
+        }
+        __syncthreads();
+    }
+};
+
+// cluster-wide sum of kAcc doubles.  Inside a warp the 28 sums are folded with a halving butterfly: at distance h every lane
 // keeps one half of its slots and ships the other half to its partner, so 16+8+4+2+1 = 31 exchanges replace 28 x 5 and
-// lane L ends up with the warp total of slot L.  The warp totals are then added in warp order (fixed tree: deterministic).
-__device__ __forceinline__ void block_reduce(double* v /* 32 slots, 28..31 zero */, double* smem /* warps*kAcc */, double* out /* kAcc, shared */) {
+// lane L ends up with the warp total of slot L.  The warp totals are added in warp order, the CTA totals go through ClusterXchg.
+__device__ __forceinline__ void cluster_reduce(ClusterXchg& xc, double* v /* 32 slots, 28..31 zero */, double* smem /* warps*kAcc */, double* out /* kAcc, shared */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int h = 16; h >= 1; h >>= 1) {
@@ -296,13 +283,12 @@ __device__ __forceinline__ void block_reduce(double* v /* 32 slots, 28..31 zero 
     }
     if (lane < kAcc) smem[warp * kAcc + lane] = v[0];
     __syncthreads();
+    double s = 0;
     if (threadIdx.x < kAcc) {
-        double s = 0;
 #pragma unroll
         for (int w = 0; w < kPoseWarps; ++w) s += smem[w * kAcc + threadIdx.x];
-        out[threadIdx.x] = s;
     }
-    __syncthreads();
+    xc.sum(s, kAcc, out);
 }
 
 // structural zeros shared by the mono and the stereo Jacobian (d(u)/d(ty) = d(v)/d(tx) = d(ur)/d(ty) = 0)
@@ -310,7 +296,7 @@ __device__ constexpr bool kJnz[3][6] = {{true, true, true, true, false, true}, {
 
 }  // namespace
 
-__global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblemDev p, double* __restrict__ work, uint8_t* __restrict__ level,
+__global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblemDev p, double* __restrict__ work, uint8_t* __restrict__ level,
                                                             uint8_t* __restrict__ outlier, float* __restrict__ pose_out,
                                                             int* __restrict__ n_inliers, ChainPrepDev next) {
     // camera-frame point and 1/z of every edge at the LAST evaluated trial.  When that trial was accepted (s_cache_ok) the
@@ -319,10 +305,20 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
     __shared__ double s_pc[4][kCacheEdges];
     __shared__ double red[kPoseWarps * kAcc];
     __shared__ double acc[kAcc];
+    __shared__ __align__(16) double xchg_buf[2][kPoseCtas][32];      // partial sums of the four CTAs (written remotely by st.async)
+    __shared__ __align__(8) unsigned long long xchg_mbar[2];
+    __shared__ double s_tot[2];
+    __shared__ float s_posef[7];
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    ClusterXchg xc{xchg_buf, xchg_mbar, rank, 0u};
+    xc.init();
+    cluster.sync();                       // every CTA's mbarriers are initialised before anyone sends
     __shared__ Se3d s_est, s_init, s_cand[kMaxTrials];
     __shared__ double s_cinv[kMaxTrials], s_lambda, s_ni, s_current, s_ini;
     __shared__ int s_cache_ok, s_nbad_lm, s_ok, s_cok[kMaxTrials], s_continue;
     const int tid = threadIdx.x, n = p.n_dev ? *p.n_dev : p.n;
+    const int gtid = (int)rank * kPoseThreads + tid;
 #ifdef POSE_TIMING
     long long tm[6] = {0, 0, 0, 0, 0, 0}; int tc[3] = {0, 0, 0}; long long t0_ = clock64(), tA_;
 #define TM_START() tA_ = clock64()
@@ -334,17 +330,21 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
     const float* pose_in = p.pose_in_dev ? p.pose_in_dev : p.pose_in;
 
     // resident chain: with the final pose known, unproject this frame's LiDAR-depth keypoints for the next frame's search
+    // (s_posef = the frame's final float32 pose, computed identically by every CTA; the work is split over the cluster)
     auto prepare_next = [&]() {
-        if (!next.kps) return;
-        __syncthreads();                  // pose_out written by thread 0 / threads 0..6
-        if (tid == 0) chain_prep_flags(next, pose_out, pose_out);
-        float Rwc[9], Ow[3];
-        chain_pose_matrices(pose_out, Rwc, Ow);
-        for (int i = tid; i < next.cap; i += kPoseThreads) chain_prep_item(next, Rwc, Ow, i);
+        __syncthreads();                  // s_posef written by thread 0
+        if (rank == 0 && tid < 7) pose_out[tid] = s_posef[tid];
+        if (next.kps) {
+            if (rank == 0 && tid == 0) chain_prep_flags(next, s_posef, s_posef);
+            float Rwc[9], Ow[3];
+            chain_pose_matrices(s_posef, Rwc, Ow);
+            for (int i = gtid; i < next.cap; i += kPoseStride) chain_prep_item(next, Rwc, Ow, i);
+        }
+        cluster.sync();                   // no CTA may exit while another can still address its shared memory
     };
     if (n < 3) {                      // src/Optimizer.cc:996
-        if (tid < 7) pose_out[tid] = pose_in[tid];
-        if (tid == 0) *n_inliers = 0;
+        if (tid < 7) s_posef[tid] = pose_in[tid];
+        if (rank == 0 && tid == 0) *n_inliers = 0;
         prepare_next();
         return;
     }
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
         normalize_rotation(T);
         s_init = T;
     }
-    for (int k = tid; k < n; k += kPoseThreads) { level[k] = 0; outlier[k] = 0; }
+    for (int k = gtid; k < n; k += kPoseStride) { level[k] = 0; outlier[k] = 0; }       // every edge belongs to one thread of the cluster for the whole kernel
     __syncthreads();
     bool robust = true;
     int n_bad = 0;
@@ -388,11 +388,11 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
     // evaluates errors of the active edges at pose T, stores them, returns this thread's partial robust chi2
     auto eval_errors = [&](const Se3d& T, double& chi_part) {
         chi_part = 0;
-        for (int k = tid; k < n; k += kPoseThreads) {
+        for (int k = gtid, lc = tid; k < n; k += kPoseStride, lc += kPoseThreads) {
             Edge E;
             load_edge(T, k, E);
             if (!E.active) continue;
-            if (k < kCacheEdges) { s_pc[0][k] = E.pc[0]; s_pc[1][k] = E.pc[1]; s_pc[2][k] = E.pc[2]; s_pc[3][k] = E.invz; }
+            if (lc < kCacheEdges) { s_pc[0][lc] = E.pc[0]; s_pc[1][lc] = E.pc[1]; s_pc[2][lc] = E.pc[2]; s_pc[3][lc] = E.invz; }
             work[3 * (size_t)k] = E.e[0]; work[3 * (size_t)k + 1] = E.e[1]; work[3 * (size_t)k + 2] = E.e[2];
             double chi = E.e[0] * (E.info * E.e[0]) + E.e[1] * (E.info * E.e[1]) + E.e[2] * (E.info * E.e[2]);
             if (robust) { double r0, r1; huber(chi, E.st ? ds : dm, E.st ? dsqr_s : dsqr_m, r0, r1); chi = r0; }
@@ -412,11 +412,11 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
             TM_START();
             {
                 const Se3d T = s_est;
-                for (int k = tid; k < n; k += kPoseThreads) {
+                for (int k = gtid, lc = tid; k < n; k += kPoseStride, lc += kPoseThreads) {
                     Edge E;
-                    if (s_cache_ok && k < kCacheEdges) {
+                    if (s_cache_ok && lc < kCacheEdges) {
                         E.st = p.stereo[k] != 0; E.info = (double)p.inv_sigma2[k]; E.active = level[k] == 0;
-                        E.pc[0] = s_pc[0][k]; E.pc[1] = s_pc[1][k]; E.pc[2] = s_pc[2][k]; E.invz = s_pc[3][k];
+                        E.pc[0] = s_pc[0][lc]; E.pc[1] = s_pc[1][lc]; E.pc[2] = s_pc[2][lc]; E.invz = s_pc[3][lc];
                         E.e[0] = work[3 * (size_t)k]; E.e[1] = work[3 * (size_t)k + 1]; E.e[2] = work[3 * (size_t)k + 2];
                     } else {
                         load_edge(T, k, E);
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
                 }
             }
             TM_ADD(0);
-            block_reduce(v, red, acc);
+            cluster_reduce(xc, v, red, acc);
             TM_ADD(1);
 #ifdef POSE_TIMING
             tc[0]++;
@@ -477,8 +477,8 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
             // are independent: lane 0 of warp w solves trial w while the other warps would idle anyway, and a retry then
             // costs one error evaluation instead of a serial solve + exp. ----
             TM_START();
-            if ((tid & 31) == 0 && (tid >> 5) < kMaxTrials) {
-                const int w = tid >> 5;
+            if ((tid & 31) < 2 && (tid >> 5) + kPoseWarps * (tid & 31) < kMaxTrials) {
+                const int w = (tid >> 5) + kPoseWarps * (tid & 31);        // trial w: lane w / 8 of warp w % 8
                 // lambda of trial w = lambda * nu * 2nu * ... (w factors); nu is a power of two, so this is one exponent shift
                 // (lambda0 = 1e-5 * max diag(H) and nu = 2 at iteration 0 of a round: every solver lane derives them itself
                 // from the reduced system, thread 0 also publishes them, so no barrier is needed before this stage)
@@ -500,11 +500,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
 #ifdef POSE_TIMING
                 const long long ts_ = clock64();
 #endif
-#if POSE_MIXED_SOLVE
-                s_cok[w] = solve6_mixed(acc, lam, acc + 21, x) ? 1 : 0;
-#else
                 s_cok[w] = solve6(acc, lam, acc + 21, x) ? 1 : 0;
-#endif
 #ifdef POSE_TIMING
                 tm[5] += clock64() - ts_;
 #endif
@@ -533,35 +529,37 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
                     for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
                     if (lane == 0) red[warp] = x;
                     __syncthreads();
+                    double s = 0.0;
                     if (warp == 0) {
-                        double s = lane < kPoseWarps ? red[lane] : 0.0;
+                        s = lane < kPoseWarps ? red[lane] : 0.0;
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-                        if (lane == 0) {
-                            double temp = s;
-                            if (!s_cok[trial]) temp = DBL_MAX;
-                            const double rho = (s_current - temp) * s_cinv[trial];
-                            if (rho > 0 && isfinite(temp)) {
-                                const double r21 = 2 * rho - 1;
-                                double alpha = 1. - r21 * r21 * r21;
-                                alpha = fmin(alpha, 2. / 3.);
-                                const double sf = fmax(1. / 3., alpha);
-                                s_lambda *= sf; s_ni = 2; s_current = temp; s_est = s_cand[trial]; s_cache_ok = 1;
-                            } else {
-                                s_lambda *= s_ni; s_ni *= 2; s_cache_ok = 0;       // the estimate is restored = left untouched
+                    }
+                    xc.sum(s, 1, s_tot);
+                    if (tid == 0) {            // every CTA takes the decision from the same four partials: identical everywhere
+                        double temp = s_tot[0];
+                        if (!s_cok[trial]) temp = DBL_MAX;
+                        const double rho = (s_current - temp) * s_cinv[trial];
+                        if (rho > 0 && isfinite(temp)) {
+                            const double r21 = 2 * rho - 1;
+                            double alpha = 1. - r21 * r21 * r21;
+                            alpha = fmin(alpha, 2. / 3.);
+                            const double sf = fmax(1. / 3., alpha);
+                            s_lambda *= sf; s_ni = 2; s_current = temp; s_est = s_cand[trial]; s_cache_ok = 1;
+                        } else {
+                            s_lambda *= s_ni; s_ni *= 2; s_cache_ok = 0;       // the estimate is restored = left untouched
+                        }
+                        const int qmax = trial + 1;
+                        const int cont = (rho < 0 && qmax < kMaxTrials) ? 1 : 0;
+                        s_continue = cont;
+                        if (!cont) {                              // end of this LM iteration: g2o's stop tests
+                            int ok = 1;
+                            if (qmax == kMaxTrials || rho == 0) ok = 0;
+                            else {
+                                if ((s_ini - s_current) * 1e3 < s_ini) s_nbad_lm += 1; else s_nbad_lm = 0;
+                                if (s_nbad_lm >= 3) ok = 0;
                             }
-                            const int qmax = trial + 1;
-                            const int cont = (rho < 0 && qmax < kMaxTrials) ? 1 : 0;
-                            s_continue = cont;
-                            if (!cont) {                              // end of this LM iteration: g2o's stop tests
-                                int ok = 1;
-                                if (qmax == kMaxTrials || rho == 0) ok = 0;
-                                else {
-                                    if ((s_ini - s_current) * 1e3 < s_ini) s_nbad_lm += 1; else s_nbad_lm = 0;
-                                    if (s_nbad_lm >= 3) ok = 0;
-                                }
-                                s_ok = ok;
-                            }
+                            s_ok = ok;
                         }
                     }
                     __syncthreads();
@@ -577,7 +575,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
         {
             const Se3d T = s_est;
             int bad = 0;
-            for (int k = tid; k < n; k += kPoseThreads) {
+            for (int k = gtid; k < n; k += kPoseStride) {
                 const bool st = p.stereo[k] != 0;
                 const double info = (double)p.inv_sigma2[k];
                 double e0, e1, e2 = 0;
@@ -596,14 +594,14 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
                 else { outlier[k] = 0; level[k] = 0; }
             }
             __syncthreads();
-            // block sum of `bad`
+            // cluster sum of `bad`
             __shared__ int s_bad;
             if (tid == 0) s_bad = 0;
             __syncthreads();
             if (bad) atomicAdd(&s_bad, bad);
             __syncthreads();
-            n_bad = s_bad;
-            __syncthreads();
+            xc.sum((double)s_bad, 1, s_tot + 1);
+            n_bad = (int)s_tot[1];
         }
         if (it == 2) robust = false;
         if (n < 10) break;
@@ -613,11 +611,11 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
         // Sophus::SE3<float>(rotation().cast<float>(), ...) (src/Optimizer.cc:1108-1110): the SO3f quaternion constructor normalises in float
         const float qf[4] = {(float)T.qx, (float)T.qy, (float)T.qz, (float)T.qw};
         const float qlen = sqrtf(eig_sum4(__fmul_rn(qf[0], qf[0]), __fmul_rn(qf[1], qf[1]), __fmul_rn(qf[2], qf[2]), __fmul_rn(qf[3], qf[3])));
-        pose_out[0] = __fdiv_rn(qf[0], qlen); pose_out[1] = __fdiv_rn(qf[1], qlen); pose_out[2] = __fdiv_rn(qf[2], qlen); pose_out[3] = __fdiv_rn(qf[3], qlen);
-        pose_out[4] = (float)T.tx; pose_out[5] = (float)T.ty; pose_out[6] = (float)T.tz;
-        *n_inliers = n - n_bad;
+        s_posef[0] = __fdiv_rn(qf[0], qlen); s_posef[1] = __fdiv_rn(qf[1], qlen); s_posef[2] = __fdiv_rn(qf[2], qlen); s_posef[3] = __fdiv_rn(qf[3], qlen);
+        s_posef[4] = (float)T.tx; s_posef[5] = (float)T.ty; s_posef[6] = (float)T.tz;
+        if (rank == 0) *n_inliers = n - n_bad;
 #ifdef POSE_TIMING
-        printf("pose n=%d total=%lld build=%lld(%d) breduce=%lld solve=%lld eval=%lld(%d) evalred=%lld solve6=%lld\n", n, clock64() - t0_, tm[0], tc[0], tm[1], tm[2], tm[3], tc[1], tm[4], tm[5]);
+        if (rank == 0) printf("pose n=%d total=%lld build=%lld(%d) breduce=%lld solve=%lld eval=%lld(%d) evalred=%lld solve6=%lld\n", n, clock64() - t0_, tm[0], tc[0], tm[1], tm[2], tm[3], tc[1], tm[4], tm[5]);
 #endif
     }
     prepare_next();
@@ -625,7 +623,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(PoseProblem
 
 void launch_pose_optimize(cudaStream_t st, const PoseProblemDev& p, double* work, uint8_t* level, uint8_t* outlier,
                           float* pose_out, int* n_inliers, const ChainPrepDev* next) {
-    pose_optimize_kernel<<<1, kPoseThreads, 0, st>>>(p, work, level, outlier, pose_out, n_inliers, next ? *next : ChainPrepDev{});
+    pose_optimize_kernel<<<kPoseCtas, kPoseThreads, 0, st>>>(p, work, level, outlier, pose_out, n_inliers, next ? *next : ChainPrepDev{});
 }
 
 }  // namespace rgbl

@@ -17,7 +17,9 @@
 #define CONVERTER_H
 #define GEOMETRIC_TOOLS_H
 #define TwoViewReconstruction_H
+#ifndef RGBL_B200_SHIM
 #define ORBEXTRACTOR_H
+#endif
 #define OPTIMIZER_H
 #define G2OTYPES_H
 
@@ -60,10 +62,14 @@ class Frame;
 class KeyFrame;
 class Map;
 
+#ifndef RGBL_B200_SHIM            // the binding test compiles shim/ORBextractor.h and shim/Optimizer_b200.cc instead
 class ORBextractor {            // ComputeStereoMatches reads the two pyramids (include/ORBextractor.h:83)
 public:
     std::vector<cv::Mat> mvImagePyramid;
 };
+#else
+class ORBextractor;
+#endif
 
 class MapPoint {
 public:
@@ -84,6 +90,8 @@ public:
     int Observations() { return nObs; }
     float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }          // src/MapPoint.cc:502-506
     float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }          // src/MapPoint.cc:508-512
+    float GetMinDistance() { return mfMinDistance; }                            // the two getters the binding adds to include/MapPoint.h
+    float GetMaxDistance() { return mfMaxDistance; }
     int PredictScale(const float& currentDist, KeyFrame* pKF);                 // bodies: src/MapPoint.cc, extracted
     int PredictScale(const float& currentDist, Frame* pF);
     void ComputeDistinctiveDescriptors();

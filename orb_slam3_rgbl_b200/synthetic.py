@@ -262,6 +262,8 @@ def make_ba_problem(seed, n_kf=8, n_fixed=2, n_points=600, outlier_frac=0.03, st
     # others, as the gathering shim would
     e_point = np.array(e_point, np.int64); e_pose = np.array(e_pose, np.int64)
     local = np.zeros(n_points, bool); local[e_point[e_pose >= n_fixed]] = True
+    if n_fixed >= n_kf:
+        local[:] = True          # no local key frame at all (structure-only adjustment): keep the graph as generated
     keep_e = local[e_point]
     remap = np.cumsum(local) - 1
     e_point = remap[e_point[keep_e]]; e_pose = e_pose[keep_e]

@@ -91,7 +91,7 @@ def test_binding_equals_the_oracle_on_a_tracked_frame(tmp_path):
         assert (g["d"] == o["d"]).all() and (g["depth"] == o["depth"]).all() and (g["ur"] == o["ur"]).all()
     last, cur = frames
     assert hd == oracle.descriptor_distance(last["d"][0], cur["d"][0])
-    ex = oracle.Extractor(2000); ex(seq.image(1))
+    ex = oracle.Extractor(2000); ex(seq.image(0))               # the driver probes the pyramid right after the first frame
     assert pyr0_w == seq.W and pyr7_h == ex.level_image(7).shape[0] and pyr_probe == int(ex.level_image(1)[10, 10])
     p0 = seq.pose(0)
     xw, ok = TD.chain_unproject(last, p0)

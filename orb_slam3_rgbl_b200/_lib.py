@@ -100,6 +100,7 @@ SYMBOLS = {
     "rgbl_resident_track_begin": (_i, [_vp, _vp, _f, _f, _f, _f, _f, _f, _i]),
     "rgbl_resident_track_end": (_i, [_vp, _vp, _vp, _vp]),
     "rgbl_resident_track_begin2": (_i, [_vp, _vp]),
+    "rgbl_depth_from_map": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp]),
     "rgbl_resident_stage": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "rgbl_track_sequence": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "rgbl_resident_track_end2": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),

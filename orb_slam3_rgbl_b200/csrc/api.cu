@@ -633,6 +633,38 @@ int rgbl_depth_from_pcd(rgbl_ctx* ctx, const float* pts4xn, int n_pts, const flo
     return RGBL_OK;
 }
 
+/* Frame::ComputeStereoFromRGBD (src/Frame.cc:1074-1095), the depth association of System::TrackRGBD: d = imDepth(kp.y, kp.x) at the
+ * DISTORTED keypoint (C-style truncation of the float coordinates), mvDepth = d and mvuRight = kpUn.x - mbf / d where d > 0, else -1.
+ * The gather runs on the device: the depth image (H x W float32, already scaled by DepthMapFactor, src/Tracking.cc:1568) is uploaded
+ * into the context's processed-depth plane and read by the same kernel that serves DepthModule::GetFeatureDepthFromDepthMap.        */
+int rgbl_depth_from_map(rgbl_ctx* ctx, const float* depth_map, int width, int height, int stride_floats, float bf, const rgbl_keypoint* kps,
+                        const rgbl_keypoint* kps_un, int n_kp, float* depth, float* uright) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!depth_map || n_kp < 0 || (n_kp > 0 && (!kps || !kps_un || !depth || !uright))) { c->err = "null argument"; return RGBL_E_INVALID; }
+    if (width != c->cfg.width || height != c->cfg.height || stride_floats < width) { c->err = "image size does not match the context"; return RGBL_E_INVALID; }
+    if (!c->d_processed) { c->err = "context was created with max_points == 0 (no depth planes)"; return RGBL_E_INVALID; }
+    if (n_kp > c->cap_kp) { c->err = "n_kp exceeds keypoint capacity"; return RGBL_E_CAPACITY; }
+    if (n_kp == 0) return RGBL_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    int* h_nkp = c->h_overflow;
+    *h_nkp = n_kp;
+    CU(cudaMemcpy2DAsync(c->d_processed, (size_t)width * sizeof(float), depth_map, (size_t)stride_floats * sizeof(float), (size_t)width * sizeof(float), height,
+                         cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(c->d_n_kp_in, h_nkp, sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(c->d_kps_in, kps, (size_t)n_kp * sizeof(rgbl_keypoint), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(c->d_kps_un, kps_un, (size_t)n_kp * sizeof(rgbl_keypoint), cudaMemcpyHostToDevice, c->st));
+    stage_begin(c, ST_DEPTH_GATHER, c->st);
+    launch_depth_gather(c->st, c->d_processed, width, height, c->d_kps_in, c->d_kps_un, c->d_n_kp_in, c->cap_kp, n_kp, bf, c->d_depth, c->d_uright, 1);
+    stage_end(c, ST_DEPTH_GATHER, c->st, 1);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(depth, c->d_depth, (size_t)n_kp * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaMemcpyAsync(uright, c->d_uright, (size_t)n_kp * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    prof_collect(c);
+    return RGBL_OK;
+}
+
 static int check_batch_args(Ctx* c, int n_frames, int width, int height, int stride) {
     if (width <= 0 || height <= 0) { c->err = "empty image"; return RGBL_E_EMPTY; }
     if (width != c->cfg.width || height != c->cfg.height || stride < width) { c->err = "image size does not match the context"; return RGBL_E_INVALID; }

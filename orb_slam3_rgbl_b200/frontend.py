@@ -162,6 +162,16 @@ def compute_stereo_matches(extractor: "ORBextractor", images_lr, mb: float, mbf:
     return (kl, dl), (kr, dr), depth[:len(kl)].copy(), ur[:len(kl)].copy()
 
 
+def compute_stereo_from_rgbd(ctx: Context, depth_map, kps, kps_un, bf: float):
+    """Frame::ComputeStereoFromRGBD (src/Frame.cc:1074-1095): depth image H x W float32 + keypoints -> (mvDepth, mvuRight)"""
+    dm = np.ascontiguousarray(depth_map, np.float32)
+    kps = np.ascontiguousarray(kps, KP_DTYPE); kps_un = np.ascontiguousarray(kps_un, KP_DTYPE)
+    n = len(kps)
+    depth = np.empty(max(n, 1), np.float32); ur = np.empty(max(n, 1), np.float32)
+    check(lib().rgbl_depth_from_map(ctx.handle, ptr(dm), dm.shape[1], dm.shape[0], dm.shape[1], bf, ptr(kps), ptr(kps_un), n, ptr(depth), ptr(ur)), ctx.handle)
+    return depth[:n], ur[:n]
+
+
 def stereo_matches_slots(extractor: "ORBextractor", slot_left: int, slot_right: int, n_left: int, mb: float, mbf: float):
     """Frame::ComputeStereoMatches between two frames of the last batched extraction (rgbl_stereo_matches) -> (mvDepth, mvuRight)"""
     cap = extractor.ctx.cap

@@ -48,10 +48,11 @@ class Config(C.Structure):
 
 def build(force: bool = False) -> Path:
     """Compile librgbl_b200.so in-tree with nvcc for sm_100a (see csrc/Makefile)."""
-    cmd = ["make", "-C", str(CSRC)] + (["-B"] if force else [])
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("building librgbl_b200.so failed:\n" + r.stdout)
+    for target in ([], ["testing"]):          # the product library, then the test-only twin library (csrc/rgbl_testing.h)
+        cmd = ["make", "-j4", "-C", str(CSRC)] + target + (["-B"] if force else [])
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building librgbl_b200.so failed:\n" + r.stdout)
     return LIB_PATH
 
 
@@ -114,13 +115,36 @@ SYMBOLS = {
     "rgbl_profile_read": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "rgbl_profile_totals": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "rgbl_descriptor_distance": (_i, [_vp, _vp]),
+}
+
+
+# TEST INFRASTRUCTURE (csrc/rgbl_testing.h): host twins of device algorithms, exported by the separate librgbl_b200_testing.so only
+TESTING_SYMBOLS = {
     "rgbl_quadtree_select": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i]),
     "rgbl_quadtree_select_block_emulation": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i]),
     "rgbl_std_sort_emulation": (_i, [_vp, _i, _vp]),
     "rgbl_std_sort_block_emulation": (_i, [_vp, _i, _i, _vp]),
     "rgbl_describe_staged_emulation": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rgbl_fast_strips_emulation": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _i]),
+    "rgbl_orb_tables": None,          # plus the product's host-only table helper (same source file), bound like the product's
 }
+TESTING_LIB_PATH = LIB_PATH.with_name("librgbl_b200_testing.so")
+_testing_lib = None
+
+
+def testing_lib() -> C.CDLL:
+    global _testing_lib
+    if _testing_lib is None:
+        if not TESTING_LIB_PATH.exists():
+            raise RuntimeError(f"{TESTING_LIB_PATH} is missing: run `make -C orb_slam3_rgbl_b200/csrc testing`")
+        L = C.CDLL(str(TESTING_LIB_PATH))
+        for name, sig in TESTING_SYMBOLS.items():
+            res, args = sig if sig else SYMBOLS[name]
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _testing_lib = L
+    return _testing_lib
 
 
 def lib() -> C.CDLL:

@@ -8,6 +8,9 @@
 
 #include "describe_warp.cuh"
 #include "rgbl_kernels.h"
+#ifdef RGBL_TESTING_EXPORTS
+#include "rgbl_testing.h"
+#endif
 
 namespace rgbl {
 
@@ -92,6 +95,7 @@ void describe_staged_host(const uint8_t* img, const uint8_t* blur, int pitch, in
 
 }  // namespace rgbl
 
+#ifdef RGBL_TESTING_EXPORTS        // test hooks: only in librgbl_b200_testing.so (csrc/rgbl_testing.h)
 extern "C" {
 
 // test hook: orientation (degrees) and 32-byte descriptor of n keypoints (x, y in level coordinates, >= 19 px from the border)
@@ -116,3 +120,4 @@ int rgbl_describe_staged_emulation(const rgbl_orb_params* orb, const uint8_t* le
 }
 
 }  // extern "C"
+#endif  // RGBL_TESTING_EXPORTS

@@ -7,6 +7,9 @@
 
 #include "fast_strip.cuh"
 #include "rgbl_kernels.h"
+#ifdef RGBL_TESTING_EXPORTS
+#include "rgbl_testing.h"
+#endif
 
 namespace rgbl {
 
@@ -60,6 +63,7 @@ void fast_strips_host(const uint8_t* level_img, int pitch, const LevelGeom& lg, 
 
 }  // namespace rgbl
 
+#ifdef RGBL_TESTING_EXPORTS        // test hooks: only in librgbl_b200_testing.so (csrc/rgbl_testing.h)
 extern "C" {
 
 // test hook: strip FAST of pyramid level `level` of a width x height image, run on the host.  level_img: that level's pixels
@@ -101,3 +105,4 @@ int rgbl_fast_strips_emulation(const rgbl_orb_params* orb, int width, int height
 }
 
 }  // extern "C"
+#endif  // RGBL_TESTING_EXPORTS

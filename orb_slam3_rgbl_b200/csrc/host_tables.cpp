@@ -214,10 +214,12 @@ int rgbl_descriptor_distance(const uint8_t a[32], const uint8_t b[32]) {
     return d;
 }
 
+#ifdef RGBL_TESTING_EXPORTS        // test hook: only in librgbl_b200_testing.so (csrc/rgbl_testing.h)
 int rgbl_quadtree_select(const int32_t* xys, int n, int min_x, int max_x, int min_y, int max_y, int n_desired,
                          int32_t* out_idx, int cap) {
     if (n < 0 || (n > 0 && !xys) || !out_idx || max_x <= min_x || max_y <= min_y) return RGBL_E_INVALID;
     return rgbl::quadtree_select(xys, n, min_x, max_x, min_y, max_y, n_desired, out_idx, cap);
 }
+#endif
 
 }  // extern "C"

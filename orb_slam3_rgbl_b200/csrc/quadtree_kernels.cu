@@ -7,6 +7,9 @@
 
 #include "quadtree_block.cuh"
 #include "rgbl_kernels.h"
+#ifdef RGBL_TESTING_EXPORTS
+#include "rgbl_testing.h"
+#endif
 
 namespace rgbl {
 
@@ -111,6 +114,7 @@ int quadtree_block_host(const uint32_t* cand, int n, int width, int height, int 
 
 }  // namespace rgbl
 
+#ifdef RGBL_TESTING_EXPORTS        // test hooks: only in librgbl_b200_testing.so (csrc/rgbl_testing.h)
 extern "C" {
 
 // test hook: the block algorithm run on the host; xys n x 3 (x, y, score) like rgbl_quadtree_select
@@ -156,3 +160,4 @@ int rgbl_std_sort_block_emulation(const int32_t* size_ulx, int n, int mode, int3
 }
 
 }  // extern "C"
+#endif  // RGBL_TESTING_EXPORTS

@@ -9,7 +9,6 @@
 #include "quadtree_kernels.emu.cpp"
 #include "depth_kernels.emu.cpp"
 #include "depth_dilate_v2.emu.cpp"
-#include "pose_kernels.emu.cpp"          // compiled with -DPOSE_MIXED_SOLVE=1: the float32 solve + refinement variant
 
 using namespace rgbl;
 
@@ -158,20 +157,6 @@ int emu_depth_dilate(const float* pts, int n, const float P[12], int W, int H, c
     launch_depth_project(nullptr, pts, 4 * n, &n, n, dd, W, H, idx.data(), 1u, 1);
     (v2 ? launch_depth_resolve_dilate_v2 : launch_depth_resolve_dilate)(nullptr, pts, 4 * n, &n, dd, W, H, idx.data(), 1u, raw_out, processed_out, 1);
     return 0;
-}
-
-// Optimizer::PoseOptimization on the emulated pose_optimize_kernel (one CTA of 512 threads); arguments as rgbl_pose_optimize.
-int emu_pose_optimize(const float pose_in[7], int n, const float* xw, const float* obs, const float* inv_sigma2, const uint8_t* stereo,
-                      float fx, float fy, float cx, float cy, float bf, float pose_out[7], uint8_t* outlier) {
-    PoseProblemDev p{};
-    p.n = n; p.n_dev = nullptr; p.pose_in_dev = nullptr; p.xw = xw; p.obs = obs; p.inv_sigma2 = inv_sigma2; p.stereo = stereo;
-    p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf;
-    for (int i = 0; i < 7; ++i) p.pose_in[i] = pose_in[i];
-    std::vector<double> work((size_t)n * 4 + 8);
-    std::vector<uint8_t> level(n + 8);
-    int n_inliers = 0;
-    launch_pose_optimize(nullptr, p, work.data(), level.data(), outlier, pose_out, &n_inliers, nullptr);
-    return n_inliers;
 }
 
 }  // extern "C"

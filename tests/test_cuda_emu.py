@@ -91,25 +91,6 @@ def test_quadtree_kernel_with_block_sort_device_path(emu):
         assert (out[:m, 0] == ref["x"]).all() and (out[:m, 1] == ref["y"]).all() and (out[:m, 2] == ref["response"]).all()
 
 
-@pytest.mark.parametrize("seed,n", [(0, 300), (1, 520), (2, 40)])
-def test_pose_kernel_with_float32_solve_device_path(emu, seed, n):
-    """pose_optimize_kernel compiled with -DPOSE_MIXED_SOLVE=1 (float32 LDL^T + one refinement step with an FP64 residual) on
-    the emulator: 512 threads, butterfly reductions, speculative trial solves.  Same bar as the GPU parity test of the FP64
-    solve: pose within 1e-5 of the oracle, identical outlier flags and inlier count."""
-    import tracking_data as TD
-    p = TD.pose_problem(seed, n=n)
-    f32 = np.float32
-    pose0 = np.ascontiguousarray(p["pose0"], f32); xw = np.ascontiguousarray(p["xw"], f32); obs = np.ascontiguousarray(p["obs"], f32)
-    inv = np.ascontiguousarray(p["inv_s2"], f32); st = np.ascontiguousarray(p["stereo"], np.uint8)
-    emu.emu_pose_optimize.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
-                                      C.c_float, C.c_float, C.c_void_p, C.c_void_p]
-    pose = np.empty(7, f32); out = np.empty(len(xw), np.uint8)
-    ni = emu.emu_pose_optimize(L.ptr(pose0), len(xw), L.ptr(xw), L.ptr(obs), L.ptr(inv), L.ptr(st), *[float(v) for v in TD.CAM], L.ptr(pose), L.ptr(out))
-    rn, rpose, rout = oracle.pose_optimize(p["pose0"], p["xw"], p["obs"], p["inv_s2"], p["stereo"], *TD.CAM)
-    assert ni == rn and (out == rout).all()
-    assert np.abs(pose - rpose).max() < 1e-5
-
-
 def test_default_quadtree_kernel_device_path_in_a_fresh_process(emu):
     """The shipped configuration (one-thread std::sort; RGBL_QT_BLOCK_SORT unset, which launch_quadtree reads once per process):
     same emulated kernel, default mode.  Guards the default path against the edits made for the block mode."""

@@ -78,7 +78,7 @@ def test_descriptor_distance_is_popcount():
 
 def _quadtree(cand, w, h, n):
     out = np.empty(max(n + 3, 4 * max(1, round((w - 32) / (h - 32)))), np.int32)
-    m = L.lib().rgbl_quadtree_select(L.ptr(np.ascontiguousarray(cand, np.int32)), len(cand), 16, w - 16, 16, h - 16, n, L.ptr(out), len(out))
+    m = L.testing_lib().rgbl_quadtree_select(L.ptr(np.ascontiguousarray(cand, np.int32)), len(cand), 16, w - 16, 16, h - 16, n, L.ptr(out), len(out))
     assert m >= 0
     return out[:m]
 
@@ -133,7 +133,7 @@ def test_quadtree_empty_and_single():
 
 def _block(cand, w, h, n):
     out = np.empty((max(abs(n) + 3, 4 * max(1, round((w - 32) / (h - 32)))), 3), np.int32)
-    m = L.lib().rgbl_quadtree_select_block_emulation(L.ptr(np.ascontiguousarray(cand, np.int32)), len(cand), 16, w - 16, 16, h - 16, n, L.ptr(out), len(out))
+    m = L.testing_lib().rgbl_quadtree_select_block_emulation(L.ptr(np.ascontiguousarray(cand, np.int32)), len(cand), 16, w - 16, 16, h - 16, n, L.ptr(out), len(out))
     assert m >= 0
     return out[:m]
 
@@ -146,7 +146,7 @@ def test_std_sort_restatement_matches_python_reference_order_on_distinct_keys():
         keys = rng.permutation(n * 2)[:n]
         su = np.stack([keys, np.zeros(n, np.int64)], 1).astype(np.int32)
         perm = np.empty(max(n, 1), np.int32)
-        L.lib().rgbl_std_sort_emulation(L.ptr(np.ascontiguousarray(su)), n, L.ptr(perm))
+        L.testing_lib().rgbl_std_sort_emulation(L.ptr(np.ascontiguousarray(su)), n, L.ptr(perm))
         assert (keys[perm[:n]] == np.sort(keys)).all()
 
 
@@ -218,7 +218,7 @@ def _strip_fast(img_level, width, height, level, nfeatures=1500, scale=1.2, nlev
     prm = L.OrbParams(nfeatures, scale, nlevels, ini_th, min_th)
     lv = np.ascontiguousarray(img_level, np.uint8)
     out = np.empty((1 << 18, 3), np.int32)
-    n = L.lib().rgbl_fast_strips_emulation(C.byref(prm), width, height, level, L.ptr(lv), lv.strides[0], max_cells, max_width, L.ptr(out), len(out))
+    n = L.testing_lib().rgbl_fast_strips_emulation(C.byref(prm), width, height, level, L.ptr(lv), lv.strides[0], max_cells, max_width, L.ptr(out), len(out))
     assert n >= 0, n
     return out[:n]
 
@@ -261,7 +261,7 @@ def test_fast_strips_on_flat_and_saturated_images():
 # ---- block-parallel std::sort (quadtree_block.cuh: block_std_sort), executed on the host -----------------------------------
 def _sort_perm(su, mode):
     perm = np.empty(len(su), np.int32)
-    assert L.lib().rgbl_std_sort_block_emulation(L.ptr(np.ascontiguousarray(su, np.int32)), len(su), mode, L.ptr(perm)) == 0
+    assert L.testing_lib().rgbl_std_sort_block_emulation(L.ptr(np.ascontiguousarray(su, np.int32)), len(su), mode, L.ptr(perm)) == 0
     return perm
 
 
@@ -280,7 +280,7 @@ def test_block_std_sort_equals_libstdcxx_sort_including_ties(seed):
         ref = _sort_perm(su, -1)
         assert (_sort_perm(su, 0) == ref).all(), n
         serial = np.empty(n, np.int32)
-        L.lib().rgbl_std_sort_emulation(L.ptr(np.ascontiguousarray(su)), n, L.ptr(serial))
+        L.testing_lib().rgbl_std_sort_emulation(L.ptr(np.ascontiguousarray(su)), n, L.ptr(serial))
         assert (serial == ref).all(), n
         for forced in (1, 2, 4):                                       # depth limit 0, 1, 3: heapsort fallback path
             assert (_sort_perm(su, forced) == ref).all(), (n, forced)
@@ -295,7 +295,7 @@ def test_block_quadtree_with_block_sort_matches_oracle(seed):
         h, w = ex.level_image(l).shape
         n = int(ex.features_per_level[l])
         out = np.empty((n + 64, 3), np.int32)
-        m = L.lib().rgbl_quadtree_select_block_emulation(L.ptr(np.ascontiguousarray(cand, np.int32)), len(cand), 16, w - 16, 16, h - 16, -n, L.ptr(out), len(out))
+        m = L.testing_lib().rgbl_quadtree_select_block_emulation(L.ptr(np.ascontiguousarray(cand, np.int32)), len(cand), 16, w - 16, 16, h - 16, -n, L.ptr(out), len(out))
         ref = ex.level_keypoints(l)
         assert m == len(ref)
         assert (out[:m, 0] + 16 == ref["x"]).all() and (out[:m, 1] + 16 == ref["y"]).all() and (out[:m, 2] == ref["response"]).all()
@@ -320,7 +320,7 @@ def test_staged_describe_matches_the_oracle(seed, size):
             continue
         xy = np.ascontiguousarray(np.stack([kl["x"], kl["y"]], 1).astype(np.int32))
         ang = np.empty(n, np.float32); d = np.empty((n, 32), np.uint8)
-        rc = L.lib().rgbl_describe_staged_emulation(C.byref(prm), L.ptr(lv), L.ptr(bl), lv.shape[1], lv.shape[0], lv.strides[0], n,
+        rc = L.testing_lib().rgbl_describe_staged_emulation(C.byref(prm), L.ptr(lv), L.ptr(bl), lv.shape[1], lv.shape[0], lv.strides[0], n,
                                                     L.ptr(xy), L.ptr(ang), L.ptr(d))
         assert rc == 0
         ref = kps[base:base + n]

@@ -140,6 +140,8 @@ static int create(const rgbl_config* cfg, Ctx** out) {
         c->describe_staged = !(envd && envd[0] == '0');
         const char* envl = getenv("RGBL_DILATE_V2");
         c->dilate_v2 = !(envl && envl[0] == '0');
+        const char* envt = getenv("RGBL_LEVEL_TMA");
+        c->level_tma = !(envt && envt[0] == '0') && make_level_tensor_maps(c->d_pyr, c->frame_bytes, B, c->levels.data(), nl, &c->level_tms) == 0;
         const char* env = getenv("RGBL_FAST_STRIPS");
         if (!(env && env[0] == '0')) {
             build_fast_strips(c->cells, 8, 264, c->strips, c->strip_rows_cap, c->strip_list_cap);
@@ -221,8 +223,10 @@ static int upload_images(Ctx* c, int n_frames, const uint8_t* const* gray, int s
 static int run_extract(Ctx* c, int n_frames, const std::function<void()>& aux_work = nullptr) {
     const int nl = c->tab.nlevels;
     stage_begin(c, ST_PYRAMID, c->st);
-    launch_pyramid(c->st, c->d_pyr, c->frame_bytes, c->levels.data(), nl, c->d_coefs, n_frames);
-    stage_end(c, ST_PYRAMID, c->st, nl - 1);
+    // fused TMA tile kernel: level l's launch writes blur(l) and level l+1 (the separate blur stage below is then empty)
+    const bool fused_levels = c->level_tma && launch_level_tiles(c->st, c->level_tms, c->d_pyr, c->d_blur, c->frame_bytes, c->levels.data(), nl, c->d_coefs, n_frames) == 0;
+    if (!fused_levels) launch_pyramid(c->st, c->d_pyr, c->frame_bytes, c->levels.data(), nl, c->d_coefs, n_frames);
+    stage_end(c, ST_PYRAMID, c->st, fused_levels ? nl : nl - 1);
     stage_begin(c, ST_FAST, c->st);
     if (c->fast_strips) {
         if (launch_fast_strips(c->st, c->d_pyr, c->frame_bytes, c->d_levels, c->d_cells, c->n_cells, c->d_strips, (int)c->strips.size(),
@@ -244,8 +248,8 @@ static int run_extract(Ctx* c, int n_frames, const std::function<void()>& aux_wo
     CU(cudaEventRecord(c->ev_pyr, c->st));
     CU(cudaStreamWaitEvent(c->st_aux, c->ev_pyr, 0));
     stage_begin(c, ST_BLUR, c->st_aux);
-    launch_blur(c->st_aux, c->d_pyr, c->d_blur, c->frame_bytes, c->levels.data(), nl, n_frames);
-    stage_end(c, ST_BLUR, c->st_aux, nl);
+    if (!fused_levels) launch_blur(c->st_aux, c->d_pyr, c->d_blur, c->frame_bytes, c->levels.data(), nl, n_frames);
+    stage_end(c, ST_BLUR, c->st_aux, fused_levels ? 0 : nl);
     if (aux_work) aux_work();
     CU(cudaEventRecord(c->ev_blur, c->st_aux));
     if (c->prof_serial) CU(cudaStreamWaitEvent(c->st, c->ev_blur, 0));      // rgbl_profile_enable(ctx, 2): no kernel of this context overlaps another

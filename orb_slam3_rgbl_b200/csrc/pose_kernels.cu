@@ -1,10 +1,10 @@
-// Optimizer::PoseOptimization (src/Optimizer.cc:814-1114) as ONE thread-block CLUSTER of 4 CTAs (4 SMs) per frame: the whole
+// Optimizer::PoseOptimization (src/Optimizer.cc:814-1114) as ONE thread-block CLUSTER of 8 CTAs (8 SMs) per frame: the whole
 // 4 x (<= 10 Levenberg-Marquardt iterations x <= 10 trials) schedule of g2o runs on the device in FP64 with no host round trip.
-// The ~500-800 edges of a frame are strided over the 4 x 256 threads of the cluster (one pass; the per-edge Jacobian / J^T W J work
-// is bound by the FP64 issue rate of an SM, so four SMs cut it four ways).  J^T W J (21 unique entries), J^T W r (6) and the robust
-// chi2 are reduced inside each CTA with warp shuffles + a fixed shared-memory tree, the four partial sums are exchanged through
+// The ~500-800 edges of a frame are strided over the 8 x 128 threads of the cluster (one pass; the per-edge Jacobian / J^T W J work
+// is bound by the FP64 issue rate of an SM, so eight SMs cut it eight ways).  J^T W J (21 unique entries), J^T W r (6) and the robust
+// chi2 are reduced inside each CTA with warp shuffles + a fixed shared-memory tree, the partial sums of the CTAs are exchanged through
 // distributed shared memory (each CTA stores its 28 sums into every CTA's exchange slot, one barrier.cluster) and added in rank order
-// by every CTA, so all four hold bit-identical systems and take the LM decisions redundantly: no broadcast, two cluster barriers per
+// by every CTA, so all of them hold bit-identical systems and take the LM decisions redundantly: no broadcast, two cluster barriers per
 // LM trial.  In each CTA, lane 0 of warp w solves the damped 6x6 system of trial w (LDL^T), applies the SE3 exponential update.
 // g2o semantics reproduced (Thirdparty/g2o/g2o/: core/optimization_algorithm_levenberg.cpp:61-185,
 // core/base_unary_edge.hpp:43-72, core/robust_kernel_impl.cpp:65-91, types/se3quat.h:104-110,214-254,280-285,
@@ -206,18 +206,27 @@ __device__ __forceinline__ void huber(double e2, double delta, float dsqr, doubl
 }
 
 constexpr int kAcc = 28;      // 21 H + 6 b + 1 chi
-constexpr int kPoseCtas = 4;      // CTAs (SMs) of the cluster that optimises one frame
-constexpr int kPoseThreads = 256, kPoseWarps = kPoseThreads / 32, kPoseStride = kPoseCtas * kPoseThreads;
-constexpr int kMaxTrials = 10;    // g2o _maxTrialsAfterFailure (warps 0..7 solve trials 0..7, warps 0..1 also 8..9)
+// Cluster shape, measured on B200 through the whole resident chain (tools/pose_variants.sh, us per tracked frame incl. both searches):
+//   4 x 256: 313   8 x 128: 293   8 x 256: 317   16 x 64: 300   16 x 128: 299.
+// The build / evaluation passes are bound by one SM's FP64 issue rate (~400 DFMA per edge), so 8 SMs with half the threads each
+// halve them; beyond 8 CTAs the exchange of partial sums costs what the passes gain.
+#ifndef POSE_CTAS
+#define POSE_CTAS 8
+#define POSE_THREADS 128
+#endif
+constexpr int kPoseCtas = POSE_CTAS;      // CTAs (SMs) of the cluster that optimises one frame
+constexpr int kPoseThreads = POSE_THREADS, kPoseWarps = kPoseThreads / 32, kPoseStride = kPoseCtas * kPoseThreads;
+constexpr int kMaxTrials = 10;    // g2o _maxTrialsAfterFailure (lane l of warp w solves trial w + kPoseWarps * l)
+constexpr int kSolveLanes = (kMaxTrials + kPoseWarps - 1) / kPoseWarps;
 constexpr int kCacheEdges = 512;  // edges PER CTA whose camera-frame point is cached in shared memory (16 KB)
 
 // ---- cluster-wide sums without a cluster barrier ----------------------------------------------------------------------------------
 // barrier.cluster costs ~1.3k cycles here (measured with clock64: arrival skew of four SMs + the L1 invalidation its acquire implies),
 // 58 times per call.  Instead every CTA pushes its partial sums straight into the other CTAs' shared memory with st.async, which
-// also signals the RECEIVER's mbarrier (complete_tx): a CTA only waits for the 4 x n x 8 bytes addressed to itself.  Exchanges are
+// also signals the RECEIVER's mbarrier (complete_tx): a CTA only waits for the kPoseCtas x n x 8 bytes addressed to itself.  Exchanges are
 // numbered; exchange s uses buffer / mbarrier s & 1, so a CTA that runs ahead writes into the other buffer (it cannot run two
 // exchanges ahead: it needs everybody's data of exchange s + 1 first, and those are sent after exchange s was read).  All CTAs add
-// the four partials in rank order: bit-identical totals everywhere.
+// the partials in rank order: bit-identical totals everywhere.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -305,7 +314,7 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
     __shared__ double s_pc[4][kCacheEdges];
     __shared__ double red[kPoseWarps * kAcc];
     __shared__ double acc[kAcc];
-    __shared__ __align__(16) double xchg_buf[2][kPoseCtas][32];      // partial sums of the four CTAs (written remotely by st.async)
+    __shared__ __align__(16) double xchg_buf[2][kPoseCtas][32];      // partial sums of the CTAs (written remotely by st.async)
     __shared__ __align__(8) unsigned long long xchg_mbar[2];
     __shared__ double s_tot[2];
     __shared__ float s_posef[7];
@@ -477,7 +486,7 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
             // are independent: lane 0 of warp w solves trial w while the other warps would idle anyway, and a retry then
             // costs one error evaluation instead of a serial solve + exp. ----
             TM_START();
-            if ((tid & 31) < 2 && (tid >> 5) + kPoseWarps * (tid & 31) < kMaxTrials) {
+            if ((tid & 31) < kSolveLanes && (tid >> 5) + kPoseWarps * (tid & 31) < kMaxTrials) {
                 const int w = (tid >> 5) + kPoseWarps * (tid & 31);        // trial w: lane w / 8 of warp w % 8
                 // lambda of trial w = lambda * nu * 2nu * ... (w factors); nu is a power of two, so this is one exponent shift
                 // (lambda0 = 1e-5 * max diag(H) and nu = 2 at iteration 0 of a round: every solver lane derives them itself
@@ -536,7 +545,7 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
                         for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
                     }
                     xc.sum(s, 1, s_tot);
-                    if (tid == 0) {            // every CTA takes the decision from the same four partials: identical everywhere
+                    if (tid == 0) {            // every CTA takes the decision from the same partials: identical everywhere
                         double temp = s_tot[0];
                         if (!s_cok[trial]) temp = DBL_MAX;
                         const double rho = (s_current - temp) * s_cinv[trial];
@@ -623,6 +632,10 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
 
 void launch_pose_optimize(cudaStream_t st, const PoseProblemDev& p, double* work, uint8_t* level, uint8_t* outlier,
                           float* pose_out, int* n_inliers, const ChainPrepDev* next) {
+    if (kPoseCtas > 8) {              // cluster sizes above 8 are not portable: opt in once
+        static const cudaError_t opt_in = cudaFuncSetAttribute(pose_optimize_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        (void)opt_in;
+    }
     pose_optimize_kernel<<<kPoseCtas, kPoseThreads, 0, st>>>(p, work, level, outlier, pose_out, n_inliers, next ? *next : ChainPrepDev{});
 }
 

@@ -51,7 +51,7 @@ FULL_SRCS = ["api.cu", "api_track.cu", "quadtree_kernels.cu", "orb_kernels.cu", 
              "depth_dilate_v2.cu", "stereo_kernels.cu", "match_kernels.cu", "bow_kernels.cu", "api_bow.cu", "api_ba.cu", "api_mapping.cu", "chain_kernels.cu",
              "quadtree_host.cpp", "host_tables.cpp"]
 # pose_kernels.cu is NOT emulated since round 2: the LM kernel is a 4-CTA thread-block cluster exchanging partial sums with
-# st.async + mbarrier (PTX); emu_pose_stub.cpp aborts with a message if the emulated library reaches PoseOptimization.
+# st.async + mbarrier (PTX); emu_stubs.cpp aborts with a message if the emulated library reaches PoseOptimization.
 
 
 def build_full(force: bool = False, defines=()) -> Path:
@@ -73,7 +73,7 @@ def build_full(force: bool = False, defines=()) -> Path:
     san = ["-fsanitize=" + os.environ["EMU_SANITIZE"]] if os.environ.get("EMU_SANITIZE") else []      # address | thread (debugging aid)
     flags = ["-std=c++20", "-O1", "-g", "-pthread", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes", f"-I{HERE}", f"-I{full}",
              "-include", str(HERE / "cuda_runtime.h"), "-DRGBL_TESTING_EXPORTS"] + list(defines) + san       # the shim first: __CUDA_ARCH__ must be set before any header
-    units = [full / ((f[:-3] + ".emu.cpp") if f.endswith(".cu") else f) for f in FULL_SRCS] + [HERE / "emu_runtime.cpp", HERE / "emu_pose_stub.cpp"]
+    units = [full / ((f[:-3] + ".emu.cpp") if f.endswith(".cu") else f) for f in FULL_SRCS] + [HERE / "emu_runtime.cpp", HERE / "emu_stubs.cpp"]
 
     def cc(u):
         o = full / (u.name + ".o")

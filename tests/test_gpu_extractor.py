@@ -158,3 +158,34 @@ def test_compute_stereo_matches():
     assert (gd == rd).all() and (gu == ru).all(), f"{(gd != rd).sum()} depths differ"
     ok = rd > 0
     assert ok.sum() > 800 and abs(np.median(kl["x"][ok] - ru[ok]) - 5.0) < 0.05
+
+
+@pytest.mark.parametrize("W,H,scale,nlevels", [(S.KITTI_W, S.KITTI_H, 1.2, 8), (641, 481, 1.2, 8), (752, 480, 1.44, 5), (515, 389, 2.0, 3), (1920, 1080, 1.2, 8)])
+def test_fused_tma_level_kernel_equals_oracle_and_two_pass_kernels(W, H, scale, nlevels, monkeypatch):
+    """level_tma_kernels.cu (TMA box loads + IDP4A/IDP2A blur + resize from the same tile) against the oracle's cv::resize /
+    cv::GaussianBlur restatements and against the two-pass kernels (RGBL_LEVEL_TMA=0), every level, every frame slot of a batch:
+    sizes with partial edge tiles in both directions, widths that are not multiples of 4, other level ratios."""
+    imgs = [S.make_image(60 + i, W, H, n_rects=150) for i in range(3)]
+    ref = oracle.Extractor(1000, scale, nlevels)
+    outs = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("RGBL_LEVEL_TMA", tma)
+        ex = F.ORBextractor(1000, scale, nlevels, 12, 7, W, H, max_batch=3)
+        try:
+            res = ex.extract_batch(imgs)
+            outs[tma] = [[(ex.level_image(l, f), ex.blurred_level(l, f)) for l in range(nlevels)] for f in range(3)]
+            for img, (k, d) in zip(imgs, res):
+                rk, rd, _ = ref(img)
+                _cmp_kps(k, rk)
+                assert (d == rd).all()
+        finally:
+            ex.ctx.close()
+    for f in range(3):
+        ref(imgs[f])
+        for l in range(nlevels):
+            a, ab = outs["1"][f][l]
+            b, bb = outs["0"][f][l]
+            r = ref.level_image(l)
+            assert a.shape == r.shape and (a == r).all(), f"frame {f} level {l}: pyramid mismatches {(a != r).sum()}"
+            assert (ab == oracle.gaussian_blur7(r)).all(), f"frame {f} level {l}: blur mismatches {(ab != oracle.gaussian_blur7(r)).sum()}"
+            assert (a == b).all() and (ab == bb).all()

@@ -20,7 +20,9 @@ __global__ void __launch_bounds__(512) quadtree_kernel(const uint32_t* __restric
                                                        int cap_kp, int* __restrict__ status, int dyn_bytes, int block_sort) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     qt::Shared& s = *reinterpret_cast<qt::Shared*>(smem_raw);
-    const int l = blockIdx.x, f = blockIdx.y;
+    // level-major block order: with one CTA per SM (the key arrays take the whole shared memory) a batch is more than one wave, and a
+    // level's run time grows with its candidate count - the long level-0 trees start first, the short ones fill the tail
+    const int l = blockIdx.y, f = blockIdx.x;
     int off = 0;
     for (int k = 0; k < f; ++k) off += frame_total[k];
     for (int k = 0; k < l; ++k) off += level_cnt[f * RGBL_MAX_LEVELS + k];
@@ -94,7 +96,7 @@ int launch_quadtree(cudaStream_t st, const uint32_t* dense, const int* level_cnt
     // block-parallel std::sort of the budgeted expansion: measured on B200 in round 2 (0.44 -> 0.27 ms per 32 frames), the default;
     // RGBL_QT_BLOCK_SORT=0 selects the one-thread sort
     static const int block_sort = [] { const char* e = getenv("RGBL_QT_BLOCK_SORT"); return (e && e[0] == '0') ? 0 : 1; }();
-    quadtree_kernel<<<dim3(n_levels, n_frames), 512, dyn_bytes, st>>>(dense, level_cnt, frame_total, d_levels, n_levels, scr,
+    quadtree_kernel<<<dim3(n_frames, n_levels), 512, dyn_bytes, st>>>(dense, level_cnt, frame_total, d_levels, n_levels, scr,
                                                                    sel_lvl, n_sel_lvl, lvl_region, cap_kp, status, dyn_bytes, block_sort);
     sel_pack_kernel<<<n_frames, 256, 0, st>>>(sel_lvl, n_sel_lvl, lvl_region, n_levels, cap_kp, sel, n_sel);
     return 0;

@@ -93,6 +93,23 @@ FS_FN uint32_t sub2(uint32_t a, uint32_t b) {                 // per-half wrappi
 #endif
 }
 
+FS_FN uint32_t shl8(uint32_t prev, uint32_t cur) {             // bytes of `cur` moved up one position, byte 3 of `prev` shifted in: byte k = pixel k-1
+#if FS_DEVICE
+    return __funnelshift_l(prev, cur, 8);
+#else
+    return (cur << 8) | (prev >> 24);
+#endif
+}
+FS_FN uint32_t shr8(uint32_t cur, uint32_t next) {             // byte k = pixel k+1
+#if FS_DEVICE
+    return __funnelshift_r(cur, next, 8);
+#else
+    return (cur >> 8) | (next << 24);
+#endif
+}
+FS_FN uint32_t even_bytes(uint32_t w) { return w & 0x00ff00ffu; }          // bytes 0, 2 widened to 16x2
+FS_FN uint32_t odd_bytes(uint32_t w) { return (w >> 8) & 0x00ff00ffu; }    // bytes 1, 3
+
 // Flattened 2-D iteration (y, x) over ny x nx items without a division per item: item i = FS_TID + k * FS_NT.
 struct Iter2D { int i, n, y, x, q, r, nx; };
 FS_FN Iter2D it_begin(int ny, int nx) {
@@ -228,6 +245,20 @@ FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo
         misc[kAnyIni + k] = 0;
     }
     if (FS_TID == 0) misc[kNList] = 0;
+    // per tile word: 0x00 in the bytes whose pixel is the first (lmask) / last (rmask) tested column of a cell - the NMS of that pixel
+    // does not look at its left / right neighbours (they belong to another cv::FAST call).  cnt[] is free until P4.
+    uint32_t* lmask = reinterpret_cast<uint32_t*>(cnt);
+    uint32_t* rmask = lmask + PW;
+    FS_FOR(c, PW) {
+        uint32_t lm = 0xffffffffu, rm = 0xffffffffu;
+        for (int k = 0; k < n_cells; ++k) {
+            const CellInfo ci = cells[si.first_cell + k];
+            const int L = ci.x0 - si.x0 + a + 3, R1 = ci.x0 - si.x0 + a + ci.cw - 4;
+            if ((L >> 2) == c) lm &= ~(0xffu << (8 * (L & 3)));
+            if (R1 >= 0 && (R1 >> 2) == c) rm &= ~(0xffu << (8 * (R1 & 3)));
+        }
+        lmask[c] = lm; rmask[c] = rm;
+    }
     FS_SYNC();
 
     const int ny = h > 6 ? h - 6 : 0;                      // tested rows [3, h-3)
@@ -272,37 +303,55 @@ FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo
     FS_SYNC();
 
     // ---- P3: 3x3 non-maximum suppression inside each cell's tested region; flags (1 = survivor at minTh, 3 = also at iniTh)
-    //          overwrite the (no longer needed) pixel tile --------------------------------------------------------------------
-    for (Iter2D it = it_begin(ny, nxw); it.i < it.n; it_next(it)) {
-        const int row = it.y + 3, c = wb + it.x;
-        const uint32_t wsc = sc32[row * PW + c];
-        uint32_t flags = 0;
-        if (wsc) {
+    //          overwrite the (no longer needed) pixel tile.  Four pixels per item, branch-free: the eight neighbour scores of the
+    //          word's pixels are byte-shifted copies of nine score words; byte maxima are taken on even / odd bytes widened to 16x2
+    //          (VIMNMX.U16x2), "s > m" and "s >= iniTh" are bit 8 of s + 255 - m and s + 256 - iniTh per half. -------------------
+    {
+        const uint32_t ini2 = (uint32_t)(ini_th < 0 ? 0 : (ini_th > 256 ? 256 : ini_th)) * 0x00010001u;   // scores are <= 255
+        for (Iter2D it = it_begin(ny, nxw); it.i < it.n; it_next(it)) {
+            const int row = it.y + 3, c = wb + it.x;
+            const uint32_t* q = sc32 + row * PW + c;
+            const uint32_t mid = q[0];
+            uint32_t flags = 0;
+            if (mid) {
+                const uint32_t up = q[-PW], dn = q[PW];
+                const uint32_t l0 = shl8(q[-PW - 1], up), l1 = shl8(q[-1], mid), l2 = shl8(q[PW - 1], dn);
+                const uint32_t r0 = shr8(up, q[-PW + 1]), r1 = shr8(mid, q[1]), r2 = shr8(dn, q[PW + 1]);
+                const uint32_t lm = lmask[c], rm = rmask[c];
+                uint32_t res[2];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int s = (wsc >> (8 * k)) & 0xff;
-                if (!s) continue;
-                const int x = 4 * c + k;
-                int cell = 0;
-                while (cell < n_cells - 1 && x >= misc[kCellR + cell]) ++cell;
-                const uint8_t* q = sc + row * P + x;
-                int m = imax(q[-P], q[P]);
-                if (x > misc[kCellL + cell]) m = imax(m, imax(imax(q[-1], q[-P - 1]), q[P - 1]));
-                if (x < misc[kCellR + cell] - 1) m = imax(m, imax(imax(q[1], q[-P + 1]), q[P + 1]));
-                if (s > m) {
-                    const bool ini = s >= ini_th;
-                    flags |= (ini ? 3u : 1u) << (8 * k);
-                    if (ini) {
+                for (int o = 0; o < 2; ++o) {              // o = 0: pixels 0, 2 of the word; o = 1: pixels 1, 3
+#define RGBL_H(w) (o ? odd_bytes(w) : even_bytes(w))
+                    const uint32_t ml = max2(max2(RGBL_H(l0), RGBL_H(l1)), RGBL_H(l2)) & RGBL_H(lm);
+                    const uint32_t mr = max2(max2(RGBL_H(r0), RGBL_H(r1)), RGBL_H(r2)) & RGBL_H(rm);
+                    const uint32_t m = max2(max2(RGBL_H(up), RGBL_H(dn)), max2(ml, mr));
+                    const uint32_t sv = RGBL_H(mid);
+#undef RGBL_H
+                    const uint32_t gt = ((sv + 0x00ff00ffu - m) >> 8) & 0x00010001u;          // s > m  (s > m >= 0 implies s > 0)
+                    const uint32_t ge = ((sv + 0x01000100u - ini2) >> 8) & 0x00010001u;       // s >= iniTh
+                    res[o] = gt | ((gt & ge) << 1);
+                }
+                flags = res[0] | (res[1] << 8);
+                uint32_t ini = flags & 0x02020202u;
+                while (ini) {                              // rare: a survivor at iniTh marks its cell
 #if FS_DEVICE
-                        atomicOr(&misc[kAnyIni + cell], 1);     // several survivors of a cell may set it: keep racecheck clean
+                    const int k = (__ffs(ini) - 1) >> 3;
 #else
-                        misc[kAnyIni + cell] = 1;
+                    int k = 0; while (!((ini >> (8 * k)) & 0xff)) ++k;
 #endif
-                    }
+                    ini &= ~(0xffu << (8 * k));
+                    const int x = 4 * c + k;
+                    int cell = 0;
+                    while (cell < n_cells - 1 && x >= misc[kCellR + cell]) ++cell;
+#if FS_DEVICE
+                    atomicOr(&misc[kAnyIni + cell], 1);     // several survivors of a cell may set it: keep racecheck clean
+#else
+                    misc[kAnyIni + cell] = 1;
+#endif
                 }
             }
+            tile32[row * PW + c] = flags;
         }
-        tile32[row * PW + c] = flags;
     }
     FS_SYNC();
 

@@ -227,6 +227,17 @@ int rgbl_resident_upload(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray
  * row of ones) happens on the device.  The reference reads at most 1 000 000 floats (250 000 points) per file.             */
 int rgbl_resident_upload_kitti(rgbl_ctx* ctx, int n_frames, const uint8_t* const* gray, int width, int height, int stride,
                                const float* const* xyzr, const int* n_pts);
+/* Same with the images as the PNG FILES' BYTES: replaces `imRGB = cv::imread(file, cv::IMREAD_UNCHANGED)` (Examples/RGB-L/rgbl_kitti.cc:87)
+ * and Tracking::GrabImageRGBL's cvtColor to gray (src/Tracking.cc:1567-1580).  camera_rgb = Camera.RGB of the settings file (mbRGB: 1 ->
+ * COLOR_RGB2GRAY / RGBA2GRAY, 0 -> COLOR_BGR2GRAY / BGRA2GRAY, applied to imread's B, G, R(, A) channel order like the reference does).
+ * The host walks the chunks and inflates the zlib stream (entropy decoding is serial); scanline reconstruction (None / Sub / Up / Average /
+ * Paeth) and the gray conversion run on the device and write level 0 of the frame slots.  Supported: 8-bit gray / RGB / RGBA,
+ * non-interlaced, image size = the context's (RGBL_E_UNSUPPORTED / RGBL_E_INVALID otherwise; corrupt streams are RGBL_E_INVALID).     */
+int rgbl_resident_upload_kitti_png(rgbl_ctx* ctx, int n_frames, const uint8_t* const* png, const size_t* png_bytes, int camera_rgb,
+                                   const float* const* xyzr, const int* n_pts);
+/* The decode alone: gray_out[f] = what the reference's mImGray holds for PNG stream f (height x width bytes, row stride `stride`). */
+int rgbl_decode_png_gray(rgbl_ctx* ctx, int n_frames, const uint8_t* const* png, const size_t* png_bytes, int camera_rgb, uint8_t* const* gray_out,
+                         int stride);
 int rgbl_resident_process(rgbl_ctx* ctx, const float P[12], const rgbl_depth_params* prm, int* n_out /* nullable */);
 int rgbl_resident_download(rgbl_ctx* ctx, rgbl_keypoint* kps, uint8_t* desc, float* depth, float* uright, int cap, int* n_out);
 

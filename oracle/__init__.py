@@ -737,3 +737,21 @@ def ref_fuse(kf: FrameView, Tcw, valid, xw, normal, mf_min_dist, mf_max_dist, mp
     bi = np.empty(max(n, 1), np.int32); Ow = np.empty(3, np.float32)
     nf = L.ref_fuse(C.byref(kf.c), _p(Tcw), n, _p(valid), _p(xw), _p(normal), _p(mn), _p(mx), _p(d), th, _p(bi), _p(Ow))
     return nf, bi[:n], Ow
+
+
+def png_decode_gray(png: bytes, camera_rgb: bool = True):
+    """cv::imread(IMREAD_UNCHANGED) of a PNG stream + Tracking::GrabImageRGBL's cvtColor to gray (png_oracle.cpp)
+    -> (gray[h, w] u8, pixels[h, w(, c)] u8 in FILE order R, G, B[, A])."""
+    buf = np.frombuffer(png, np.uint8)
+    w, h, ch = C.c_int(0), C.c_int(0), C.c_int(0)
+    L = lib()
+    L.orc_png_decode_gray.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    rc = L.orc_png_decode_gray(_p(buf), len(buf), int(bool(camera_rgb)), C.byref(w), C.byref(h), C.byref(ch), None, 0, None, 0)
+    if rc:
+        raise ValueError(f"orc_png_decode_gray: {rc}")
+    gray = np.empty((h.value, w.value), np.uint8)
+    px = np.empty((h.value, w.value, ch.value), np.uint8)
+    rc = L.orc_png_decode_gray(_p(buf), len(buf), int(bool(camera_rgb)), C.byref(w), C.byref(h), C.byref(ch), _p(gray), gray.size, _p(px), px.size)
+    if rc:
+        raise ValueError(f"orc_png_decode_gray: {rc}")
+    return gray, (px[..., 0] if ch.value == 1 else px)

@@ -86,6 +86,8 @@ SYMBOLS = {
     "rgbl_pose_optimize": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _vp, _vp, _ip]),
     "rgbl_resident_upload": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "rgbl_resident_upload_kitti": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "rgbl_resident_upload_kitti_png": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "rgbl_decode_png_gray": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i]),
     "rgbl_resident_process": (_i, [_vp, _vp, C.POINTER(DepthParams), _vp]),
     "rgbl_resident_download": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "rgbl_fuse_search": (_i, [_vp, C.POINTER(FrameViewC), _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp]),

@@ -42,6 +42,11 @@ static void release(Ctx* c) {
     if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
     if (c->ev_blur) cudaEventDestroy(c->ev_blur);
     if (c->d_pts_raw) cudaFree(c->d_pts_raw);
+    if (c->d_png_raw) cudaFree(c->d_png_raw);
+    if (c->d_png_band) cudaFree(c->d_png_band);
+    if (c->d_png_status) cudaFree(c->d_png_status);
+    if (c->h_png_raw) cudaFreeHost(c->h_png_raw);
+    if (c->h_png_status) cudaFreeHost(c->h_png_status);
     if (c->d_strips) cudaFree(c->d_strips);
     if (c->map_arena) cudaFree(c->map_arena);
     if (c->st_trk) { cudaStreamSynchronize(c->st_trk); cudaStreamDestroy(c->st_trk); }
@@ -690,7 +695,7 @@ static int upload_rgbl(Ctx* c, int n_frames, const uint8_t* const* gray, int str
     }
     int max_pts = 0;
     for (int f = 0; f < n_frames; ++f) {
-        if (!gray[f]) { c->err = "empty image"; return RGBL_E_EMPTY; }
+        if (gray && !gray[f]) { c->err = "empty image"; return RGBL_E_EMPTY; }
         if (n_pts[f] < 0 || n_pts[f] > c->cfg.max_points || (n_pts[f] && !pts4xn[f])) { c->err = "bad point cloud"; return RGBL_E_CAPACITY; }
         max_pts = std::max(max_pts, n_pts[f]);
     }
@@ -701,11 +706,42 @@ static int upload_rgbl(Ctx* c, int n_frames, const uint8_t* const* gray, int str
     }
     CU(cudaMemcpyAsync(c->d_n_pts, c->h_n_pts, (size_t)n_frames * sizeof(int), cudaMemcpyHostToDevice, c->st_aux));
     if (layout == 1 && max_pts > 0) launch_deinterleave_xyzr(c->st_aux, c->d_pts_raw, c->d_pts, 4 * c->cfg.max_points, c->d_n_pts, max_pts, n_frames);
-    int rc = upload_images(c, n_frames, gray, stride, c->st);
-    if (rc) return rc;
+    if (gray) { int rc = upload_images(c, n_frames, gray, stride, c->st); if (rc) return rc; }      // else: level 0 was written by decode_png_to_level0
     c->resident_frames = n_frames;
     c->resident_max_pts = max_pts;
     *max_pts_out = max_pts;
+    return RGBL_OK;
+}
+
+// cv::imread(PNG, IMREAD_UNCHANGED) + cvtColor to gray (Examples/RGB-L/rgbl_kitti.cc:87, src/Tracking.cc:1567-1580) into level 0 of the
+// frame slots 0..n_frames-1: host inflate into pinned staging, H2D of the filtered scanlines, reconstruction + gray on the device.
+static int decode_png_to_level0(Ctx* c, int n_frames, const uint8_t* const* png, const size_t* png_bytes, int camera_rgb, cudaStream_t st) {
+    const int w = c->cfg.width, h = c->cfg.height;
+    if (!c->d_png_raw) {
+        c->png_raw_stride = (((size_t)w * 4 + 1) * h + 255) & ~(size_t)255;
+        const size_t total = c->png_raw_stride * c->cfg.max_batch;
+        if (cudaMalloc((void**)&c->d_png_raw, total) != cudaSuccess || cudaMallocHost((void**)&c->h_png_raw, total) != cudaSuccess ||
+            cudaMalloc((void**)&c->d_png_band, (size_t)c->cfg.max_batch * w * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMalloc((void**)&c->d_png_status, sizeof(int)) != cudaSuccess || cudaMallocHost((void**)&c->h_png_status, sizeof(int)) != cudaSuccess) {
+            cudaGetLastError(); c->err = "allocation of the PNG staging buffers failed"; return RGBL_E_CUDA;
+        }
+        CU(cudaMemset(c->d_png_status, 0, sizeof(int)));
+    }
+    for (int f = 0; f < n_frames; ++f) if (!png[f] || !png_bytes[f]) { c->err = "empty image"; return RGBL_E_EMPTY; }
+    int ch = 0;
+    std::string perr;
+    const int prc = png_inflate_batch(n_frames, png, png_bytes, w, h, c->h_png_raw, c->png_raw_stride, &ch, perr);
+    if (prc) { c->err = perr; return prc == -2 ? RGBL_E_UNSUPPORTED : RGBL_E_INVALID; }
+    const size_t used = ((size_t)w * ch + 1) * h;
+    for (int f = 0; f < n_frames; ++f)
+        CU(cudaMemcpyAsync(c->d_png_raw + (size_t)f * c->png_raw_stride, c->h_png_raw + (size_t)f * c->png_raw_stride, used, cudaMemcpyHostToDevice, st));
+    launch_png_unfilter_gray(st, c->d_png_raw, c->png_raw_stride, w, h, ch, camera_rgb, c->d_pyr, c->frame_bytes, c->levels[0], c->d_png_band, c->d_png_status, n_frames);
+    CU(cudaMemcpyAsync(c->h_png_status, c->d_png_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));          // the staging buffer is free again, and a bad scanline filter byte is an error of THIS call
+    if (*c->h_png_status) {
+        CU(cudaMemsetAsync(c->d_png_status, 0, sizeof(int), st));
+        c->err = "corrupt PNG: scanline filter type above 4"; return RGBL_E_INVALID;
+    }
     return RGBL_OK;
 }
 
@@ -783,6 +819,38 @@ int rgbl_resident_upload_kitti(rgbl_ctx* ctx, int n_frames, const uint8_t* const
     return RGBL_OK;
 }
 
+int rgbl_resident_upload_kitti_png(rgbl_ctx* ctx, int n_frames, const uint8_t* const* png, const size_t* png_bytes, int camera_rgb,
+                                   const float* const* xyzr, const int* n_pts) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!png || !png_bytes || !xyzr || !n_pts) { c->err = "null argument"; return RGBL_E_INVALID; }
+    int rc = check_batch_args(c, n_frames, c->cfg.width, c->cfg.height, c->cfg.width); if (rc) return rc;
+    CU(cudaSetDevice(c->cfg.device));
+    rc = decode_png_to_level0(c, n_frames, png, png_bytes, camera_rgb, c->st); if (rc) return rc;
+    int max_pts = 0;
+    rc = upload_rgbl(c, n_frames, nullptr, 0, xyzr, n_pts, &max_pts, 1); if (rc) return rc;
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaStreamSynchronize(c->st_aux));
+    return RGBL_OK;
+}
+
+int rgbl_decode_png_gray(rgbl_ctx* ctx, int n_frames, const uint8_t* const* png, const size_t* png_bytes, int camera_rgb, uint8_t* const* gray_out,
+                         int stride) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RGBL_E_INVALID;
+    if (!png || !png_bytes || !gray_out) { c->err = "null argument"; return RGBL_E_INVALID; }
+    int rc = check_batch_args(c, n_frames, c->cfg.width, c->cfg.height, stride); if (rc) return rc;
+    CU(cudaSetDevice(c->cfg.device));
+    rc = decode_png_to_level0(c, n_frames, png, png_bytes, camera_rgb, c->st); if (rc) return rc;
+    const LevelGeom& l0 = c->levels[0];
+    for (int f = 0; f < n_frames; ++f) {
+        if (!gray_out[f]) { c->err = "null output image"; return RGBL_E_INVALID; }
+        CU(cudaMemcpy2DAsync(gray_out[f], stride, c->d_pyr + (size_t)f * c->frame_bytes + l0.off, l0.pitch, l0.w, l0.h, cudaMemcpyDeviceToHost, c->st));
+    }
+    CU(cudaStreamSynchronize(c->st));
+    return RGBL_OK;
+}
+
 int rgbl_resident_process(rgbl_ctx* ctx, const float P[12], const rgbl_depth_params* prm, int* n_out) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
@@ -825,7 +893,7 @@ int rgbl_resident_stage(rgbl_ctx* ctx, int slot, int n_frames, const uint8_t* co
     }
     int max_pts = 0;
     for (int f = 0; f < n_frames; ++f) {
-        if (!gray[f]) { c->err = "empty image"; return RGBL_E_EMPTY; }
+        if (gray && !gray[f]) { c->err = "empty image"; return RGBL_E_EMPTY; }
         if (n_pts[f] < 0 || n_pts[f] > c->cfg.max_points || (n_pts[f] && !pts4xn[f])) { c->err = "bad point cloud"; return RGBL_E_CAPACITY; }
         max_pts = std::max(max_pts, n_pts[f]);
         CU(cudaMemcpy2DAsync(sl.img + (size_t)f * img_bytes, l0.pitch, gray[f], stride, c->cfg.width, c->cfg.height, cudaMemcpyHostToDevice, c->st));

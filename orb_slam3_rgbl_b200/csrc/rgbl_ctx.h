@@ -102,6 +102,12 @@ struct Ctx {
     uint8_t* d_desc = nullptr;
     float* d_pts = nullptr;
     float* d_pts_raw = nullptr;   // lazily allocated: raw (x, y, z, r) records awaiting de-interleave
+    // png_kernels.cu (lazily allocated): inflated-but-still-filtered scanlines, pinned + device, one slot of png_raw_stride bytes per frame;
+    // the reconstructed row above each 512-row band; status word (bad filter type)
+    uint8_t *h_png_raw = nullptr, *d_png_raw = nullptr;
+    uint32_t* d_png_band = nullptr;
+    int *d_png_status = nullptr, *h_png_status = nullptr;
+    size_t png_raw_stride = 0;
     int* d_n_pts = nullptr;
     uint32_t* d_idx_map = nullptr;
     float *d_raw = nullptr, *d_processed = nullptr, *d_depth = nullptr, *d_uright = nullptr;

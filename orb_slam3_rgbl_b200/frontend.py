@@ -81,6 +81,19 @@ def orb_tables(nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=12, min_th=7)
     return dict(scale=sc, inv_scale=inv, sigma2=s2, inv_sigma2=is2, features_per_level=q, umax=um)
 
 
+def decode_png_gray(ctx: "Context", png_list, camera_rgb=True):
+    """cv::imread(IMREAD_UNCHANGED) + Tracking::GrabImageRGBL's cvtColor for a batch of PNG streams (rgbl_decode_png_gray)
+    -> list of gray images (height x width u8)."""
+    n = len(png_list)
+    bufs = [np.frombuffer(b, np.uint8) for b in png_list]
+    pa = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+    sizes = (C.c_size_t * n)(*[len(b) for b in bufs])
+    outs = [np.empty((ctx.height, ctx.width), np.uint8) for _ in range(n)]
+    oa = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    check(lib().rgbl_decode_png_gray(ctx.handle, n, pa, sizes, int(bool(camera_rgb)), oa, ctx.width), ctx.handle)
+    return outs
+
+
 class ORBextractor:
     """ORB_SLAM3::ORBextractor drop-in (src/ORBextractor.cc)."""
 
@@ -524,6 +537,18 @@ class RgblBatch:
         npts = np.array([len(r) for r in raw], np.int32)
         arr = (C.c_void_p * self.nF)(*[r.ctypes.data for r in raw])
         check(lib().rgbl_resident_upload_kitti(c.handle, self.nF, self.ia, self.W, self.H, self.W, arr, ptr(npts)), c.handle)
+
+    def upload_kitti_png(self, png_list, xyzr_list, camera_rgb=True):
+        """Resident upload with the images as PNG FILE BYTES (cv::imread + cvtColor to gray on the way, rgbl_resident_upload_kitti_png)
+        and the clouds as raw KITTI .bin records."""
+        c = self.ctx
+        raw = [np.ascontiguousarray(r, np.float32).reshape(-1, 4) for r in xyzr_list]
+        npts = np.array([len(r) for r in raw], np.int32)
+        arr = (C.c_void_p * self.nF)(*[r.ctypes.data for r in raw])
+        bufs = [np.frombuffer(b, np.uint8) for b in png_list]
+        pa = (C.c_void_p * self.nF)(*[b.ctypes.data for b in bufs])
+        sizes = (C.c_size_t * self.nF)(*[len(b) for b in bufs])
+        check(lib().rgbl_resident_upload_kitti_png(c.handle, self.nF, pa, sizes, int(bool(camera_rgb)), arr, ptr(npts)), c.handle)
 
     def process_resident(self):
         c = self.ctx

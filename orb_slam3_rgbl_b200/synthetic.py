@@ -287,3 +287,51 @@ def make_ba_problem(seed, n_kf=8, n_fixed=2, n_points=600, outlier_frac=0.03, st
 
 def ba_args(p):
     return (p["poses"], p["pose_fixed"], p["points"], p["e_point"], p["e_pose"], p["obs"], p["stereo"], p["inv_sigma2"], *p["cam"])
+
+
+# ---- PNG streams (the input of cv::imread at Examples/RGB-L/rgbl_kitti.cc:87) -------------------------------------------------------
+def encode_png(img: np.ndarray, filters=None, idat_chunk: int = 1 << 16, level: int = 6) -> bytes:
+    """A PNG file (8-bit gray / RGB / RGBA, non-interlaced) of `img` (H x W or H x W x {3,4}, samples in FILE order R, G, B[, A]).
+    `filters`: one filter type 0..4 (None, Sub, Up, Average, Paeth) per row, default = all five cycling, so that decoders are
+    exercised on every type; the zlib stream is split over IDAT chunks of `idat_chunk` bytes."""
+    import struct
+    import zlib
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    ctype = {1: 0, 3: 2, 4: 6}[ch]
+    rows = img.reshape(h, w * ch).astype(np.int16)
+    if filters is None:
+        filters = np.arange(h) % 5
+    filters = np.asarray(filters, np.int64)
+    a = np.zeros_like(rows); a[:, ch:] = rows[:, :-ch]                       # left
+    b = np.zeros_like(rows); b[1:] = rows[:-1]                               # up
+    c = np.zeros_like(rows); c[1:, ch:] = rows[:-1, :-ch]                    # upper left
+    p = a + b - c
+    pa, pb, pc = np.abs(p - a), np.abs(p - b), np.abs(p - c)
+    paeth = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, b, c))
+    pred = np.stack([np.zeros_like(rows), a, b, (a + b) >> 1, paeth])[filters, np.arange(h)]
+    raw = np.empty((h, w * ch + 1), np.uint8)
+    raw[:, 0] = filters
+    raw[:, 1:] = ((rows - pred) & 0xff).astype(np.uint8)
+    z = zlib.compress(raw.tobytes(), level)
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0))
+    for i in range(0, len(z), idat_chunk):
+        out += chunk(b"IDAT", z[i:i + idat_chunk])
+    return out + chunk(b"IEND", b"")
+
+
+def colorize(gray: np.ndarray, seed: int = 0, alpha: bool = False) -> np.ndarray:
+    """A colour image (file order R, G, B[, A]) whose channels are different smooth remappings of a synthetic gray image."""
+    rng = np.random.default_rng(seed)
+    g = gray.astype(np.float64)
+    H, W = gray.shape
+    tint = [_upsample_bilinear(rng.random((max(2, H // 64 + 2), max(2, W // 64 + 2))), H, W) for _ in range(3)]
+    chans = [np.clip(g * (0.6 + 0.8 * t) + 20.0 * (t - 0.5), 0, 255).astype(np.uint8) for t in tint]
+    if alpha:
+        chans.append(rng.integers(0, 256, gray.shape, dtype=np.uint8))
+    return np.stack(chans, -1)

@@ -48,7 +48,7 @@ def build(force: bool = False) -> Path:
 
 FULL_LIB = BUILD / "librgbl_b200_emu.so"
 FULL_SRCS = ["api.cu", "api_track.cu", "quadtree_kernels.cu", "orb_kernels.cu", "fast_strip_kernels.cu", "describe_warp_kernels.cu", "depth_kernels.cu",
-             "depth_dilate_v2.cu", "stereo_kernels.cu", "match_kernels.cu", "bow_kernels.cu", "api_bow.cu", "api_ba.cu", "api_mapping.cu", "chain_kernels.cu",
+             "depth_dilate_v2.cu", "stereo_kernels.cu", "match_kernels.cu", "bow_kernels.cu", "api_bow.cu", "api_ba.cu", "api_mapping.cu", "chain_kernels.cu", "png_kernels.cu",
              "quadtree_host.cpp", "host_tables.cpp"]
 # pose_kernels.cu is NOT emulated since round 2: the LM kernel is a 4-CTA thread-block cluster exchanging partial sums with
 # st.async + mbarrier (PTX); emu_stubs.cpp aborts with a message if the emulated library reaches PoseOptimization.
@@ -86,7 +86,7 @@ def build_full(force: bool = False, defines=()) -> Path:
     errs = [o for o in objs if isinstance(o, Exception)]
     if errs:
         raise RuntimeError("\n".join(str(e) for e in errs))
-    subprocess.run(["g++", "-shared", "-pthread", *san, "-o", str(FULL_LIB), *map(str, objs)], check=True)
+    subprocess.run(["g++", "-shared", "-pthread", *san, "-o", str(FULL_LIB), *map(str, objs), "-lz"], check=True)
     return FULL_LIB
 
 

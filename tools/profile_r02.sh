@@ -16,7 +16,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 
 echo "launch list exit $?"
 python tools/summarize_ncu_launches.py "$out/launches.csv" > "$out/launches_summary.csv" 2>/dev/null; head -20 "$out/launches_summary.csv"
 # two passes, the .ncu-rep files stay on the box (tens of MB): only their raw pages (CSV, one row per launch) come back
-K1='regex:(resize_level|fast_|cand_|blur_level|quadtree_kernel|sel_pack|describe|depth_project|depth_resolve|depth_gather|grid_build|level_fused)'
+K1='regex:(resize_level|fast_|cand_|blur_level|quadtree_kernel|sel_pack|describe|depth_project|depth_resolve|depth_gather|grid_build|level_tile)'
 K2='regex:(search_last_collect|search_local_collect|resolve_kernel|pose_optimize|chain_prep|tlm_)'
 timeout 900 ncu --set full --clock-control none -k "$K1" -s 62 -c 31 -o /tmp/fc_kernels -f $PROF > "$out/ncu_full.log" 2>&1
 echo "ncu full (frame construction) exit $?"

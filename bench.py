@@ -429,6 +429,10 @@ def main():
             except Exception as e:          # noqa: BLE001
                 side["C"] = {"error": str(e)}
         bow, lba = side_bow_lba(F, torch, local_rank, not args.no_cpu_baseline)
+        try:
+            side["png_input"] = side_png(F, torch, local_rank, not args.no_cpu_baseline)
+        except Exception as e:          # noqa: BLE001
+            side["png_input"] = {"error": str(e)}
 
     if rank == 0:
         d = main_res["detail"]
@@ -488,6 +492,37 @@ def main():
                                               "+ isInFrustum + 2x PoseOptimization, -O3), pinned to the reference's own sources compiled here"}
         print(json.dumps(line))
     rep.close()
+
+
+def side_png(F, torch, local_rank, with_cpu):
+    """The image input step in front of the path (SURVEY 8(f) row 4: cv::imread of the KITTI PNG + cvtColor to gray), reported on its own."""
+    cfg = CONFIGS["B"]
+    T = 32
+    ctx = F.Context(cfg["W"], cfg["H"], cfg["nfeat"], max_batch=T, device=local_rank)
+    try:
+        pngs = [S.encode_png(S.colorize(S.make_image(500 + f % 4, cfg["W"], cfg["H"]), f)) for f in range(T)]
+        F.decode_png_gray(ctx, pngs, True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); reps = 5
+        for _ in range(reps):
+            F.decode_png_gray(ctx, pngs, True)
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        out = {"workload": f"{T} RGB PNG files of {cfg['W']}x{cfg['H']} (all five scanline filters), {sum(map(len, pngs)) / T / 1e6:.2f} MB each", "ms_per_batch": ms,
+               "frames_per_s": T / (ms * 1e-3),
+               "timing": "host wall clock per rgbl_decode_png_gray call: parallel zlib inflate on the host, H2D of the filtered scanlines, reconstruction + cvtColor on the device, D2H of the gray images"}
+        if with_cpu:
+            try:
+                import cv2
+                cv2.setNumThreads(1)
+                t0 = time.perf_counter()
+                for b in pngs[:8]:
+                    m = cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_UNCHANGED); cv2.cvtColor(m, cv2.COLOR_RGB2GRAY)
+                out["cpu_reference"] = {"frames_per_s": 8 / (time.perf_counter() - t0), "cores": 1, "kind": "reference (python-cv2 = OpenCV imgcodecs + libpng, the reference's own reader)"}
+            except Exception:           # noqa: BLE001
+                pass
+        return out
+    finally:
+        ctx.close()
 
 
 def side_bow_lba(F, torch, local_rank, with_cpu):

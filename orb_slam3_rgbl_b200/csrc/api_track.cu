@@ -525,8 +525,13 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
         if (cont && (t.cap_r_valid < nr)) { c->err = "local map ring missing"; return RGBL_E_INVALID; }
         GROW(t.r_valid, t.cap_r_valid, nr); GROW(t.r_xw, t.cap_r_xw, nr * 3); GROW(t.r_normal, t.cap_r_normal, nr * 3);
         GROW(t.r_min, t.cap_r_min, nr); GROW(t.r_max, t.cap_r_max, nr); GROW(t.r_desc, t.cap_r_desc, nr * 32);
-        GROW(t.lq_u8, t.cap_lq_u8, 2 * (size_t)n_lq); GROW(t.lq_f, t.cap_lq_f, 5 * (size_t)n_lq); GROW(t.lq_i, t.cap_lq_i, 2 * (size_t)n_lq);
+        GROW(t.lq_u8, t.cap_lq_u8, 2 * (size_t)n_lq); GROW(t.lq_f, t.cap_lq_f, 8 * (size_t)n_lq); GROW(t.lq_i, t.cap_lq_i, 2 * (size_t)n_lq);
         GROW(t.lq_desc, t.cap_lq_desc, (size_t)n_lq * 32); GROW(t.match_local, t.cap_match_local, cap);
+        if (!t.lookback) {
+            GROW(t.lookback, t.cap_lookback, tlm_lookback_ints());
+            CU(cudaMemsetAsync(t.lookback, 0, t.cap_lookback * sizeof(int), c->st));     // ordered before the chain by ev_snap below
+        }
+        if ((n_lq + 255) / 256 + 1 > 1024) { c->err = "local map too large for the compaction slots (local_map_frames x keypoint capacity > 261 k)"; return RGBL_E_UNSUPPORTED; }
     }
     // per-slot buffers: twice the size, the slot picks its half (sizes are those of the context's full batch so that the halves
     // never move while a chain is in flight)
@@ -608,7 +613,7 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
         if (K > 0) {
             lq.cap = n_lq; lq.n = d_nq; lq.in_view = t.lq_u8; lq.obs_pos = t.lq_u8 + n_lq;
             lq.proj_x = t.lq_f; lq.proj_y = t.lq_f + n_lq; lq.proj_xr = t.lq_f + 2 * (size_t)n_lq; lq.depth = t.lq_f + 3 * (size_t)n_lq;
-            lq.view_cos = t.lq_f + 4 * (size_t)n_lq; lq.level = t.lq_i; lq.src = t.lq_i + n_lq; lq.desc = t.lq_desc;
+            lq.view_cos = t.lq_f + 4 * (size_t)n_lq; lq.xw = t.lq_f + 5 * (size_t)n_lq; lq.level = t.lq_i; lq.src = t.lq_i + n_lq; lq.desc = t.lq_desc;
         }
         const int k0 = cont ? 0 : 1;
         for (int k = k0; k < nF; ++k) {
@@ -640,14 +645,14 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
                 launch_pose_optimize(cs, p, t.pose_work, t.e_lvl, t.e_out, pose_tmp, d_ni1 + k, nullptr); ++n_launches;
                 if (tm) cudaEventRecord(tev[3], cs);
                 // TrackLocalMap: outlier discard + isInFrustum + ordered compaction, local search, edges of all map points, second optimisation
-                launch_tlm_prepare(cs, f, pose_tmp, ring, 0.5f, d_ne, t.e_idx, t.e_out, t.state, t.match, lq); ++n_launches;
+                launch_tlm_prepare(cs, f, pose_tmp, ring, 0.5f, d_ne, t.e_idx, t.e_out, t.state, t.match, lq, t.lookback, d_ovf); ++n_launches;
                 LocalPointsDev lp{n_lq, d_nq, lq.in_view, lq.proj_x, lq.proj_y, lq.proj_xr, lq.depth, lq.level, lq.view_cos, lq.desc, lq.obs_pos};
                 SearchLocalParams sl{};
                 sl.th = P.th_local; sl.nn_ratio = P.nn_ratio_local; sl.th_far = 0.f; sl.use_factor = (P.th_local != 1.0f) ? 1 : 0; sl.far_points = 0; sl.keep_max = std::min(256, (int)std::floor((float)100 / P.nn_ratio_local) + 1);
-                launch_search_local(cs, f, cell_start, csr_idx, lp, sl, ms, t.state, t.match_local, d_nml + k); n_launches += 2;
+                launch_search_local(cs, f, cell_start, csr_idx, lp, sl, ms, t.state, t.match_local, t.scalars + 1); n_launches += 2;      // d_nml + k is accumulated by tlm_edges
                 if (tm) cudaEventRecord(tev[4], cs);
                 const ChainEdgesOut eo2{t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne2};
-                launch_tlm_edges(cs, f, t.match, t.q_f3a, t.match_local, lq.src, ring, eo2, d_nml + k, cap, t.q_u8a, t.q_i, last_desc, last_pose); ++n_launches;
+                launch_tlm_edges(cs, f, t.match, t.q_f3a, t.match_local, lq.xw, ring, eo2, d_nml + k, cap, t.q_u8a, t.q_i, last_desc, last_pose, t.lookback, d_ovf); ++n_launches;
                 if (tm) cudaEventRecord(tev[5], cs);
                 PoseProblemDev p2 = p;
                 p2.n_dev = d_ne2; p2.pose_in_dev = pose_tmp;
@@ -762,6 +767,7 @@ int rgbl_resident_track_end2(rgbl_ctx* ctx, float* poses_out, int* n_matches, in
             cudaGetLastError();
         }
     }
+    if (h_i[4 * nF + 4] == 9) { c->err = "TrackLocalMap compaction: a CTA waited in vain for its predecessors (chain_kernels.cu)"; return RGBL_E_CUDA; }
     if (h_i[4 * nF + 4]) { c->err = "matcher candidate list overflow"; return RGBL_E_CAPACITY; }
     // capacity overflow of the frame construction that produced this batch (FAST cell slots, candidate buffer, quad-tree): the chain
     // ran on truncated keypoint sets

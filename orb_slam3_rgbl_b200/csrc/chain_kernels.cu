@@ -16,169 +16,228 @@
 namespace rgbl {
 namespace {
 
-// block-wide ordered compaction helper: exclusive position of `flag` among the 1024 threads + running base
-struct BlockScan {
-    int* wsum; int* total;
-    __device__ __forceinline__ int run(int flag, int tid, int& new_total) {
-        const int lane = tid & 31, warp = tid >> 5;
-        int incl = flag;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        int base = *total;
-        for (int w = 0; w < warp; ++w) base += wsum[w];
-        int all = *total;
-        for (int w = 0; w < 32; ++w) all += wsum[w];
-        new_total = all;
-        return base + incl - 1;           // position of this thread's element if flag == 1
-    }
-};
+// ---- ordered compaction over SEVERAL CTAs in one launch: "publish and look back" -------------------------------------------------
+// The single-CTA versions of the two kernels below walked their input in chunks of 1024 with three block barriers and one round of
+// dependent global loads per chunk (31 us / 16 us per frame on a B200, all of it latency).  Here every CTA handles one chunk, publishes
+// its count in a slot array and reads the counts of the CTAs before it: one global round trip instead of a chain of them.
+//   slot value 0 = not published yet, count + 1 otherwise; the CTA that takes the LAST ticket of `done` (after its own look-back, so every
+//   reader is through) zeroes the slots and the ticket counter again: the array is clean for the next launch on the stream.
+// CTAs of a 1-D grid start in index order and the grids here are a few dozen CTAs, so a CTA only ever waits for CTAs that are already
+// running; the wait is bounded all the same (a stuck wait raises the chain's overflow flag instead of hanging the GPU).
+constexpr int kTlmThreads = 256;
+constexpr int kLbSlots = 1024;             // capacity of one slot array (CTAs per launch)
+constexpr int kSpinLimit = 1 << 22;
 
-__global__ void __launch_bounds__(1024) tlm_prepare_kernel(FrameDev f, const float* __restrict__ pose, LocalRingDev ring, float cos_limit,
-                                                           const int* __restrict__ n_edges, const int* __restrict__ e_idx,
-                                                           const uint8_t* __restrict__ e_outlier, uint8_t* __restrict__ state,
-                                                           int* __restrict__ match_last, LocalQueriesDev lq) {
-    __shared__ float s_R[9], s_t[3], s_Ow[3];
-    __shared__ int s_wsum[32];
-    __shared__ int s_total;
-    const int tid = threadIdx.x;
-    // slot states for the local search: a slot is occupied exactly when it holds a map point of the first search that survived the
-    // rotation check (match >= 0; the resolution kernel keeps its working states on chip) ...
-    const int n_f = *f.n;
-    for (int i = tid; i < n_f; i += 1024) state[i] = match_last[i] >= 0 ? 1 : 0;
-    __syncthreads();
-    // ... and was not an outlier of the first PoseOptimization: those slots are free again (mvpMapPoints[i] = NULL, src/Tracking.cc:2951-2953)
-    const int ne = *n_edges;
-    for (int e = tid; e < ne; e += 1024)
-        if (e_outlier[e]) { const int i = e_idx[e]; state[i] = 0; match_last[i] = -1; }
-    if (tid == 0) {
-        // Frame::SetPose -> UpdatePoseMatrices (src/Frame.cc:562-569): mRcw = mTcw.rotationMatrix(), mtcw, mOw = Twc.translation()
-        const float q[4] = {pose[0], pose[1], pose[2], pose[3]};
-        float R[9]; quatf_to_matrix(q, R);
-        float qinv[4], ow[3];
-        se3f_inverse(pose, qinv, ow);
-        for (int i = 0; i < 9; ++i) s_R[i] = R[i];
-        for (int i = 0; i < 3; ++i) { s_t[i] = pose[4 + i]; s_Ow[i] = ow[i]; }
-        s_total = 0;
+struct Lookback { int* slots; int* done; int* fail; };
+
+__device__ __forceinline__ int lb_load(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// called by every thread of the CTA after `count` (the CTA's total, valid in thread 0) is known; returns the sum of the counts of all
+// CTAs with a smaller index among the first `n_part` CTAs.  Two block barriers.
+__device__ __forceinline__ int lb_exclusive_base(const Lookback& lb, int count, int* s_base) {
+    const int tid = threadIdx.x, b = blockIdx.x;
+    if (tid == 0) atomicExch(lb.slots + b, count + 1);
+    if (tid < 32) {
+        int sum = 0;
+        for (int j = tid; j < b; j += 32) {
+            int v = lb_load(lb.slots + j), spins = 0;
+            while (v == 0 && ++spins < kSpinLimit) v = lb_load(lb.slots + j);
+            if (v == 0) { atomicExch(lb.fail, 9); v = 1; }
+            sum += v - 1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (tid == 0) *s_base = sum;
     }
     __syncthreads();
-    FrustumParams prm;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) prm.Rcw[i] = s_R[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { prm.tcw[i] = s_t[i]; prm.Ow[i] = s_Ow[i]; }
-    prm.cos_limit = cos_limit;
-    const int n_ring = ring.K * ring.cap;
-    BlockScan scan{s_wsum, &s_total};
-    for (int b = 0; b < n_ring; b += 1024) {
-        const int p = b + tid;
-        FrustumOut o{};
-        int flag = 0;
-        if (p < n_ring && ring.valid[p]) {
-            const float P[3] = {ring.xw[3 * p], ring.xw[3 * p + 1], ring.xw[3 * p + 2]};
-            o = frustum_point(f, prm, P, ring.normal + 3 * p, ring.mf_min[p], ring.mf_max[p]);
-            flag = o.in_view;
-        }
-        int total = 0;
-        const int pos = scan.run(flag, tid, total);
-        if (flag && pos < lq.cap) {
-            lq.in_view[pos] = 1; lq.obs_pos[pos] = 1;
-            lq.proj_x[pos] = o.px; lq.proj_y[pos] = o.py; lq.proj_xr[pos] = o.pxr; lq.depth[pos] = o.depth; lq.level[pos] = o.level;
-            lq.view_cos[pos] = o.view_cos; lq.src[pos] = p;
-            const uint4* d = reinterpret_cast<const uint4*>(ring.desc + (size_t)p * 32);
-            uint4* dd = reinterpret_cast<uint4*>(lq.desc + (size_t)pos * 32);
-            dd[0] = d[0]; dd[1] = d[1];
-        }
-        __syncthreads();
-        if (tid == 0) s_total = total;
-        __syncthreads();
-    }
-    if (tid == 0) *lq.n = min(s_total, lq.cap);
+    return *s_base;
 }
 
-__global__ void __launch_bounds__(1024) tlm_edges_kernel(FrameDev f, const int* __restrict__ match_last, const float* __restrict__ last_xw,
-                                                         const int* __restrict__ match_local, const int* __restrict__ lq_src,
-                                                         LocalRingDev ring, ChainEdgesOut eo, int* __restrict__ n_local_matches,
-                                                         // hand-over of the last frame's points into the local map
-                                                         int n_last_cap, const uint8_t* __restrict__ last_valid, const int* __restrict__ last_octave,
-                                                         const uint8_t* __restrict__ last_desc, const float* __restrict__ last_pose) {
-    __shared__ int s_wsum[32];
-    __shared__ int s_total, s_nloc;
-    __shared__ float s_Ow[3];
-    const int tid = threadIdx.x;
-    const int n_f = *f.n;
-    if (tid == 0) {
-        s_total = 0; s_nloc = 0;
-        float qinv[4], ow[3];
-        se3f_inverse(last_pose, qinv, ow);                 // KeyFrame::GetCameraCenter of the frame the points were created from
-        s_Ow[0] = ow[0]; s_Ow[1] = ow[1]; s_Ow[2] = ow[2];
-    }
+// ticket after the CTA is done with the slot array; true for the CTA that has to clean up (call from ONE thread)
+__device__ __forceinline__ bool lb_last_ticket(int* counter, int n_part) { return atomicAdd(counter, 1) == n_part - 1; }
+
+// warp-ballot block scan for kTlmThreads threads: exclusive position of `flag` inside the CTA, CTA total in `total` (all threads)
+__device__ __forceinline__ int block_rank(int flag, int* s_wsum, int& total) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_wsum[warp] = __popc(m);
     __syncthreads();
-    BlockScan scan{s_wsum, &s_total};
-    int nloc = 0;
-    for (int b = 0; b < n_f; b += 1024) {
-        const int i = b + tid;
-        const int ma = (i < n_f) ? match_last[i] : -1;
-        const int mb = (i < n_f && ma < 0) ? match_local[i] : -1;
-        const int flag = (ma >= 0 || mb >= 0) ? 1 : 0;
-        if (mb >= 0) ++nloc;
-        int total = 0;
-        const int e = scan.run(flag, tid, total);
-        if (flag) {
-            const float* x = (ma >= 0) ? (last_xw + 3 * (size_t)ma) : (ring.xw + 3 * (size_t)lq_src[mb]);
-            const rgbl_keypoint kp = f.keys[i];
-            eo.exw[3 * e] = x[0]; eo.exw[3 * e + 1] = x[1]; eo.exw[3 * e + 2] = x[2];
-            const float ur = f.uright[i];
-            eo.eobs[3 * e] = kp.x; eo.eobs[3 * e + 1] = kp.y; eo.eobs[3 * e + 2] = ur;
-            const float sc = f.scale[kp.octave];
-            eo.einfo[e] = __fdiv_rn(1.0f, __fmul_rn(sc, sc));                  // mvInvLevelSigma2 (src/ORBextractor.cc:421-429)
-            eo.est[e] = ur >= 0.f;
-            eo.eidx[e] = i;
-        }
+    int base = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < kTlmThreads / 32; ++w) { const int v = s_wsum[w]; all += v; if (w < warp) base += v; }
+    total = all;
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
+// grid = n_blocks frustum CTAs (one ring point per thread) + ONE extra CTA (the last) for the slot states of the local search.
+__global__ void __launch_bounds__(kTlmThreads) tlm_prepare_kernel(FrameDev f, const float* __restrict__ pose, LocalRingDev ring, float cos_limit,
+                                                                  const int* __restrict__ n_edges, const int* __restrict__ e_idx,
+                                                                  const uint8_t* __restrict__ e_outlier, uint8_t* __restrict__ state,
+                                                                  int* __restrict__ match_last, LocalQueriesDev lq, Lookback lb) {
+    __shared__ int s_wsum[kTlmThreads / 32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x;
+    const int n_part = (int)gridDim.x - 1;
+    if ((int)blockIdx.x == n_part) {
+        // slot states for the local search: a slot is occupied exactly when it holds a map point of the first search that survived the
+        // rotation check (match >= 0; the resolution kernel keeps its working states on chip) ...
+        const int n_f = *f.n;
+        for (int i = tid; i < n_f; i += kTlmThreads) state[i] = match_last[i] >= 0 ? 1 : 0;
         __syncthreads();
-        if (tid == 0) s_total = total;
-        __syncthreads();
+        // ... and was not an outlier of the first PoseOptimization: those slots are free again (mvpMapPoints[i] = NULL, src/Tracking.cc:2951-2953)
+        const int ne = *n_edges;
+        for (int e = tid; e < ne; e += kTlmThreads)
+            if (e_outlier[e]) { const int i = e_idx[e]; state[i] = 0; match_last[i] = -1; }
+        return;
     }
-    if (nloc) atomicAdd(&s_nloc, nloc);
-    // the last frame's points become local map points (ring slot = frames inserted so far mod K); the search above has already read the ring
-    const int slot = (*ring.count) % ring.K;
-    const size_t base = (size_t)slot * ring.cap;
-    for (int j = tid; j < ring.cap; j += 1024) {
-        uint8_t v = 0;
-        if (j < n_last_cap && last_valid[j]) {
-            const float P[3] = {last_xw[3 * j], last_xw[3 * j + 1], last_xw[3 * j + 2]};
-            const float PC[3] = {__fsub_rn(P[0], s_Ow[0]), __fsub_rn(P[1], s_Ow[1]), __fsub_rn(P[2], s_Ow[2])};
+    // Frame::SetPose -> UpdatePoseMatrices (src/Frame.cc:562-569): mRcw = mTcw.rotationMatrix(), mtcw, mOw = Twc.translation(); every thread
+    // derives them from the 7 pose floats itself (a few dozen operations) rather than waiting for one thread behind a barrier
+    FrustumParams prm;
+    {
+        float T[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) T[i] = pose[i];
+        quatf_to_matrix(T, prm.Rcw);
+        float qinv[4];
+        se3f_inverse(T, qinv, prm.Ow);
+        prm.tcw[0] = T[4]; prm.tcw[1] = T[5]; prm.tcw[2] = T[6];
+        prm.cos_limit = cos_limit;
+    }
+    const int n_ring = ring.K * ring.cap;
+    const int p = (int)blockIdx.x * kTlmThreads + tid;
+    FrustumOut o{};
+    int flag = 0;
+    float P[3] = {0.f, 0.f, 0.f};
+    if (p < n_ring && ring.valid[p]) {
+        P[0] = ring.xw[3 * p]; P[1] = ring.xw[3 * p + 1]; P[2] = ring.xw[3 * p + 2];
+        o = frustum_point(f, prm, P, ring.normal + 3 * p, ring.mf_min[p], ring.mf_max[p]);
+        flag = o.in_view;
+    }
+    int total = 0;
+    const int rank = block_rank(flag, s_wsum, total);
+    const int base = lb_exclusive_base(lb, total, &s_base);
+    const int pos = base + rank;
+    if (flag && pos < lq.cap) {
+        lq.in_view[pos] = 1; lq.obs_pos[pos] = 1;
+        lq.proj_x[pos] = o.px; lq.proj_y[pos] = o.py; lq.proj_xr[pos] = o.pxr; lq.depth[pos] = o.depth; lq.level[pos] = o.level;
+        lq.view_cos[pos] = o.view_cos; lq.src[pos] = p;
+        lq.xw[3 * pos] = P[0]; lq.xw[3 * pos + 1] = P[1]; lq.xw[3 * pos + 2] = P[2];      // tlm_edges reads the point here, not in the ring
+        const uint4* d = reinterpret_cast<const uint4*>(ring.desc + (size_t)p * 32);
+        uint4* dd = reinterpret_cast<uint4*>(lq.desc + (size_t)pos * 32);
+        dd[0] = d[0]; dd[1] = d[1];
+    }
+    if (tid == 0) {
+        if ((int)blockIdx.x == n_part - 1) *lq.n = min(base + total, lq.cap);
+        if (lb_last_ticket(lb.done, n_part)) {
+            for (int j = 0; j < n_part; ++j) lb.slots[j] = 0;
+            *lb.done = 0;
+        }
+    }
+}
+
+// grid = ceil(cap / kTlmThreads) CTAs: thread i owns feature i of the current frame (edge phase) and point i of the last frame (hand-over)
+__global__ void __launch_bounds__(kTlmThreads) tlm_edges_kernel(FrameDev f, const int* __restrict__ match_last, const float* __restrict__ last_xw,
+                                                                const int* __restrict__ match_local, const float* __restrict__ lq_xw,
+                                                                LocalRingDev ring, ChainEdgesOut eo, int* __restrict__ n_local_matches,
+                                                                // hand-over of the last frame's points into the local map
+                                                                int n_last_cap, const uint8_t* __restrict__ last_valid, const int* __restrict__ last_octave,
+                                                                const uint8_t* __restrict__ last_desc, const float* __restrict__ last_pose, Lookback lb) {
+    __shared__ int s_wsum[kTlmThreads / 32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x;
+    const int n_part = (int)gridDim.x;
+    const int i = (int)blockIdx.x * kTlmThreads + tid;
+    const int n_f = *f.n;
+    const int ring_count = *ring.count;
+    // everything the hand-over needs is loaded up front, next to the edge phase's own loads: one round of global latency for both
+    uint8_t lv = 0;
+    float P[3] = {0.f, 0.f, 0.f};
+    int loct = 0;
+    uint4 ld0{0u, 0u, 0u, 0u}, ld1 = ld0;
+    if (i < ring.cap && i < n_last_cap && last_valid[i]) {
+        lv = 1;
+        P[0] = last_xw[3 * i]; P[1] = last_xw[3 * i + 1]; P[2] = last_xw[3 * i + 2];
+        loct = last_octave[i];
+        ld0 = reinterpret_cast<const uint4*>(last_desc + (size_t)i * 32)[0];
+        ld1 = reinterpret_cast<const uint4*>(last_desc + (size_t)i * 32)[1];
+    }
+    float Ow[3];
+    {
+        float T[7], qinv[4];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) T[k] = last_pose[k];
+        se3f_inverse(T, qinv, Ow);                         // KeyFrame::GetCameraCenter of the frame the points were created from
+    }
+    const int ma = (i < n_f) ? match_last[i] : -1;
+    const int mb = (i < n_f && ma < 0) ? match_local[i] : -1;
+    const int flag = (ma >= 0 || mb >= 0) ? 1 : 0;
+    float x[3] = {0.f, 0.f, 0.f}, ur = 0.f;
+    rgbl_keypoint kp{};
+    if (flag) {
+        const float* xs = (ma >= 0) ? (last_xw + 3 * (size_t)ma) : (lq_xw + 3 * (size_t)mb);
+        x[0] = xs[0]; x[1] = xs[1]; x[2] = xs[2];
+        kp = f.keys[i];
+        ur = f.uright[i];
+    }
+    int total = 0;
+    const int rank = block_rank(flag, s_wsum, total);
+    const unsigned mloc = __ballot_sync(0xffffffffu, mb >= 0);
+    if ((tid & 31) == 0 && mloc) atomicAdd(n_local_matches, __popc(mloc));
+    const int base = lb_exclusive_base(lb, total, &s_base);
+    if (flag) {
+        const int e = base + rank;
+        eo.exw[3 * e] = x[0]; eo.exw[3 * e + 1] = x[1]; eo.exw[3 * e + 2] = x[2];
+        eo.eobs[3 * e] = kp.x; eo.eobs[3 * e + 1] = kp.y; eo.eobs[3 * e + 2] = ur;
+        const float sc = f.scale[kp.octave];
+        eo.einfo[e] = __fdiv_rn(1.0f, __fmul_rn(sc, sc));                  // mvInvLevelSigma2 (src/ORBextractor.cc:421-429)
+        eo.est[e] = ur >= 0.f;
+        eo.eidx[e] = i;
+    }
+    if (tid == 0 && (int)blockIdx.x == n_part - 1) *eo.n_edges = base + total;
+    // The ring slot that takes the last frame's points is still part of THIS frame's local map, but nothing in this kernel reads the ring:
+    // the edges take their points from the query copy tlm_prepare made (lq_xw), so the hand-over needs no grid-wide barrier.
+    // the last frame's points become local map points (ring slot = frames inserted so far mod K)
+    if (i < ring.cap) {
+        const size_t p = (size_t)(ring_count % ring.K) * ring.cap + i;
+        if (lv) {
+            const float PC[3] = {__fsub_rn(P[0], Ow[0]), __fsub_rn(P[1], Ow[1]), __fsub_rn(P[2], Ow[2])};
             const float dist = sqrtf(eig_sum3(__fmul_rn(PC[0], PC[0]), __fmul_rn(PC[1], PC[1]), __fmul_rn(PC[2], PC[2])));
-            const size_t p = base + j;
             ring.xw[3 * p] = P[0]; ring.xw[3 * p + 1] = P[1]; ring.xw[3 * p + 2] = P[2];
             ring.normal[3 * p] = __fdiv_rn(PC[0], dist); ring.normal[3 * p + 1] = __fdiv_rn(PC[1], dist); ring.normal[3 * p + 2] = __fdiv_rn(PC[2], dist);
-            const float mx = __fmul_rn(dist, f.scale[last_octave[j]]);
+            const float mx = __fmul_rn(dist, f.scale[loct]);
             ring.mf_max[p] = mx;
             ring.mf_min[p] = __fdiv_rn(mx, f.scale[f.n_levels - 1]);
-            const uint4* d = reinterpret_cast<const uint4*>(last_desc + (size_t)j * 32);
             uint4* dd = reinterpret_cast<uint4*>(ring.desc + p * 32);
-            dd[0] = d[0]; dd[1] = d[1];
-            v = 1;
+            dd[0] = ld0; dd[1] = ld1;
         }
-        ring.valid[base + j] = v;
+        ring.valid[p] = lv;
     }
-    __syncthreads();
-    if (tid == 0) { *eo.n_edges = s_total; *n_local_matches = s_nloc; *ring.count = *ring.count + 1; }
+    if (tid == 0 && lb_last_ticket(lb.done, n_part)) {           // every CTA has read ring.count and finished its look-back
+        for (int j = 0; j < n_part; ++j) lb.slots[j] = 0;
+        *lb.done = 0;
+        *ring.count = ring_count + 1;
+    }
 }
 
 }  // namespace
 
+// lb: 2 * (kLbSlots + 8) zero-initialised ints owned by the caller (one half per kernel); fail: the chain's overflow flag
+int tlm_lookback_ints() { return 2 * (kLbSlots + 8); }
+
 void launch_tlm_prepare(cudaStream_t st, const FrameDev& f, const float* pose, const LocalRingDev& ring, float cos_limit, const int* n_edges,
-                        const int* e_idx, const uint8_t* e_outlier, uint8_t* state, int* match_last, const LocalQueriesDev& lq) {
-    tlm_prepare_kernel<<<1, 1024, 0, st>>>(f, pose, ring, cos_limit, n_edges, e_idx, e_outlier, state, match_last, lq);
+                        const int* e_idx, const uint8_t* e_outlier, uint8_t* state, int* match_last, const LocalQueriesDev& lq, int* lb, int* fail) {
+    const int n_part = (ring.K * ring.cap + kTlmThreads - 1) / kTlmThreads;
+    const Lookback l{lb, lb + kLbSlots, fail};
+    tlm_prepare_kernel<<<n_part + 1, kTlmThreads, 0, st>>>(f, pose, ring, cos_limit, n_edges, e_idx, e_outlier, state, match_last, lq, l);
 }
 
-void launch_tlm_edges(cudaStream_t st, const FrameDev& f, const int* match_last, const float* last_xw, const int* match_local, const int* lq_src,
+void launch_tlm_edges(cudaStream_t st, const FrameDev& f, const int* match_last, const float* last_xw, const int* match_local, const float* lq_xw,
                       const LocalRingDev& ring, const ChainEdgesOut& eo, int* n_local_matches, int n_last_cap, const uint8_t* last_valid,
-                      const int* last_octave, const uint8_t* last_desc, const float* last_pose) {
-    tlm_edges_kernel<<<1, 1024, 0, st>>>(f, match_last, last_xw, match_local, lq_src, ring, eo, n_local_matches, n_last_cap, last_valid,
-                                         last_octave, last_desc, last_pose);
+                      const int* last_octave, const uint8_t* last_desc, const float* last_pose, int* lb, int* fail) {
+    const int n_part = (ring.cap + kTlmThreads - 1) / kTlmThreads;
+    const Lookback l{lb + kLbSlots + 8, lb + 2 * kLbSlots + 8, fail};
+    tlm_edges_kernel<<<n_part, kTlmThreads, 0, st>>>(f, match_last, last_xw, match_local, lq_xw, ring, eo, n_local_matches, n_last_cap, last_valid,
+                                                     last_octave, last_desc, last_pose, l);
 }
 
 }  // namespace rgbl

@@ -60,6 +60,7 @@ struct TrackBufs {
     uint8_t *lq_u8 = nullptr, *lq_desc = nullptr; size_t cap_lq_u8 = 0, cap_lq_desc = 0;
     float* lq_f = nullptr; size_t cap_lq_f = 0;
     int *lq_i = nullptr, *match_local = nullptr; size_t cap_lq_i = 0, cap_match_local = 0;
+    int* lookback = nullptr; size_t cap_lookback = 0;     // slot arrays of the multi-CTA compactions (chain_kernels.cu), kept zero between launches
     // ComputeBoW
     int *bw_i = nullptr; size_t cap_bw_i = 0;            // f_word | f_node | bow_word | fv_node | fv_start | fv_feature | scratch | counts
     double* bw_d = nullptr; size_t cap_bw_d = 0;         // f_weight | bow_value
@@ -67,7 +68,7 @@ struct TrackBufs {
         void* all[] = {keys, uright, desc, csr_idx, kp_cell, cell_start, state, match, minq, scalars, lists, list_n, choice, resolved,
                        q_u8a, q_u8b, q_desc, q_f3a, q_f3b, q_f[0], q_f[1], q_f[2], q_f[3], q_f[4], q_f[5], q_f[6], q_i, pose_work, ch_poses, ch_counts, e_xw, e_obs, e_info, e_st, e_lvl, e_out, e_idx,
                        s_kps, s_desc, s_depth, s_uright, s_nsel, b_cell_start, b_csr_idx, b_kp_cell, bw_i, bw_d,
-                       c_kps, c_desc, c_depth, c_misc, r_valid, r_desc, r_xw, r_normal, r_min, r_max, lq_u8, lq_desc, lq_f, lq_i, match_local};
+                       c_kps, c_desc, c_depth, c_misc, r_valid, r_desc, r_xw, r_normal, r_min, r_max, lq_u8, lq_desc, lq_f, lq_i, match_local, lookback};
         for (void* p : all) if (p) cudaFree(p);
     }
 };

@@ -158,12 +158,16 @@ struct LocalRingDev {                // local map of the chain: K frame slots x 
 struct LocalQueriesDev {             // the in-frustum local map points, compacted in ring order (= vpMapPoints of the local search)
     int cap; int* n;
     uint8_t* in_view; uint8_t* obs_pos; float *proj_x, *proj_y, *proj_xr, *depth; int* level; float* view_cos; uint8_t* desc; int* src;
+    float* xw;                       // world coordinates of the compacted points (read by tlm_edges instead of the ring)
 };
 void launch_tlm_prepare(cudaStream_t st, const FrameDev& f, const float* pose, const LocalRingDev& ring, float cos_limit, const int* n_edges,
-                        const int* e_idx, const uint8_t* e_outlier, uint8_t* state, int* match_last, const LocalQueriesDev& lq);
-void launch_tlm_edges(cudaStream_t st, const FrameDev& f, const int* match_last, const float* last_xw, const int* match_local, const int* lq_src,
+                        const int* e_idx, const uint8_t* e_outlier, uint8_t* state, int* match_last, const LocalQueriesDev& lq, int* lookback, int* fail);
+void launch_tlm_edges(cudaStream_t st, const FrameDev& f, const int* match_last, const float* last_xw, const int* match_local, const float* lq_xw,
                       const LocalRingDev& ring, const ChainEdgesOut& eo, int* n_local_matches, int n_last_cap, const uint8_t* last_valid,
-                      const int* last_octave, const uint8_t* last_desc, const float* last_pose);
+                      const int* last_octave, const uint8_t* last_desc, const float* last_pose, int* lookback, int* fail);
+// both kernels compact over several CTAs in one launch; `lookback` = tlm_lookback_ints() ZERO-INITIALISED ints (the kernels leave them zero),
+// `fail` = a device flag set to 9 if a CTA ever waited in vain; *n_local_matches must be 0 at the launch of tlm_edges (it accumulates)
+int tlm_lookback_ints();
 
 // stereo_kernels.cu --------------------------------------------------------------------------------
 struct StereoFrameDev { const int* n; const rgbl_keypoint* keys; const uint8_t* desc; float scale[RGBL_MAX_LEVELS], inv_scale[RGBL_MAX_LEVELS]; };

@@ -90,6 +90,29 @@ def build_full(force: bool = False, defines=()) -> Path:
     return FULL_LIB
 
 
+TLM_CHECK = BUILD / "tlm_check"
+
+
+def build_tlm_check(force: bool = False) -> Path:
+    """tlm_check.cpp + chain_kernels.cu against the shim -> an executable comparing the multi-CTA TrackLocalMap glue kernels with a
+    serial restatement (tests/test_cuda_emu.py::test_tlm_kernels_device_path)."""
+    hdrs = [f.name for f in CSRC.iterdir() if f.suffix in (".h", ".cuh", ".inc")]
+    srcs = [CSRC / f for f in ["chain_kernels.cu"] + hdrs] + [HERE / "cuda_runtime.h", HERE / "emu_runtime.cpp", HERE / "tlm_check.cpp", Path(__file__)]
+    if TLM_CHECK.exists() and not force and all(TLM_CHECK.stat().st_mtime > s.stat().st_mtime for s in srcs):
+        return TLM_CHECK
+    d = BUILD / "tlm"
+    if d.exists():
+        shutil.rmtree(d)
+    d.mkdir(parents=True)
+    for f in ["chain_kernels.cu"] + hdrs:
+        out = d / ((f[:-3] + ".emu.cpp") if f.endswith(".cu") else f)
+        out.write_text(_transform((CSRC / f).read_text()))
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes", f"-I{HERE}", f"-I{d}", "-include", str(HERE / "cuda_runtime.h"),
+           "-o", str(TLM_CHECK), str(HERE / "tlm_check.cpp"), str(d / "chain_kernels.emu.cpp"), str(HERE / "emu_runtime.cpp")]
+    subprocess.run(cmd, check=True)
+    return TLM_CHECK
+
+
 if __name__ == "__main__":
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == "full":

@@ -161,3 +161,15 @@ def test_whole_extraction_pipeline_device_path(emu, variants):
     for f in ok.dtype.names:
         assert (kps[:n][f].view(np.uint32) == ok[f].view(np.uint32)).all(), f
     assert (desc[:n] == od).all()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_tlm_kernels_device_path(seed):
+    """The multi-CTA TrackLocalMap glue kernels (chain_kernels.cu: ordered compaction by 'publish and look back', the in-kernel grid
+    barrier before the ring hand-over, self-cleaning slot arrays) against a serial restatement (tests/cuda_emu/tlm_check.cpp)."""
+    import subprocess
+    spec = importlib.util.spec_from_file_location("cuda_emu_build", HERE / "cuda_emu" / "build.py")
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    exe = mod.build_tlm_check()
+    r = subprocess.run([str(exe), str(seed)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -50,6 +50,40 @@ RGBL_HD void stage_words(int lane, int n_lanes, const uint8_t* img, int pitch, i
     }
 }
 
+// The same copy for one warp with compile-time sizes: ALL loads of the lane are issued before the first store (a lane owns
+// ceil(ROWS * WORDS / 32) words), so a warp keeps ~20 independent global loads in flight instead of one or two - the kernel is bound
+// by the latency of these gathers, not by their bytes (ncu: long-scoreboard stalls, ~1 TB/s with every SM full of warps).
+template <int ROWS, int WORDS>
+struct StagedWords { uint32_t v[(ROWS * WORDS + 31) / 32]; };
+template <int ROWS, int WORDS>
+RGBL_HD void stage_load(int lane, const uint8_t* img, int pitch, int x_first, int y_first, StagedWords<ROWS, WORDS>& out) {
+    const int base = x_first & ~3;
+#pragma unroll
+    for (int t = 0; t < (ROWS * WORDS + 31) / 32; ++t) {
+        const int it = lane + 32 * t;
+        const int r = it / WORDS, w = it - r * WORDS;
+        const int col = base + 4 * w;
+        uint32_t v = 0;
+        if (it < ROWS * WORDS && col + 4 <= pitch) {
+            const uint8_t* p = img + (size_t)(y_first + r) * pitch + col;
+#if defined(__CUDA_ARCH__)
+            v = __ldg(reinterpret_cast<const uint32_t*>(p));
+#else
+            v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+#endif
+        }
+        out.v[t] = v;
+    }
+}
+template <int ROWS, int WORDS>
+RGBL_HD void stage_store(int lane, const StagedWords<ROWS, WORDS>& in, uint32_t* dst) {
+#pragma unroll
+    for (int t = 0; t < (ROWS * WORDS + 31) / 32; ++t) {
+        const int it = lane + 32 * t;
+        if (it < ROWS * WORDS) dst[it] = in.v[t];
+    }
+}
+
 // lane <-> column u = lane - 15 of the disc: partial m10 = u * sum_v I(u, v), partial m01 = sum_v v * I(u, v) over the rows
 // whose half width umax[|v|] covers the column (the reference walks the same pixels row pair by row pair, :86-100)
 RGBL_HD void centroid_partial(int lane, const uint32_t* patch, int align, const int* umax, int* m10, int* m01) {

@@ -36,8 +36,14 @@ __global__ void __launch_bounds__(256) describe_staged_kernel(const uint8_t* __r
     const size_t lvl = (size_t)frame * frame_stride + lg.off;
     uint32_t* patch = sm[warp];
     uint32_t* win = patch + dw::kPatchRows * dw::kPatchWords;
-    dw::stage_words(lane, 32, pyr + lvl, lg.pitch, kp.x - kHalfPatch, kp.y - kHalfPatch, dw::kPatchRows, dw::kPatchWords, patch);
-    dw::stage_words(lane, 32, blur + lvl, lg.pitch, kp.x - dw::kWinR, kp.y - dw::kWinR, dw::kWinRows, dw::kWinWords, win);
+    {
+        dw::StagedWords<dw::kPatchRows, dw::kPatchWords> rp;
+        dw::StagedWords<dw::kWinRows, dw::kWinWords> rw;
+        dw::stage_load(lane, pyr + lvl, lg.pitch, kp.x - kHalfPatch, kp.y - kHalfPatch, rp);
+        dw::stage_load(lane, blur + lvl, lg.pitch, kp.x - dw::kWinR, kp.y - dw::kWinR, rw);
+        dw::stage_store(lane, rp, patch);
+        dw::stage_store(lane, rw, win);
+    }
     __syncwarp();
     int m10, m01;
     dw::centroid_partial(lane, patch, (kp.x - kHalfPatch) & 3, umax.v, &m10, &m01);

@@ -47,7 +47,7 @@ constexpr int kMaxRows = 78;           // window height limit (the same limit bu
 constexpr int kCntInts = kMaxCells * (kMaxRows - 6) + 8;
 // misc[] layout
 constexpr int kNList = 0, kAnyIni = 1, kCellL = kAnyIni + kMaxCells, kCellR = kCellL + kMaxCells, kWarpSums = kCellR + kMaxCells,
-              kMiscInts = kWarpSums + 32;
+              kNWords = kWarpSums + 32, kMiscInts = kNWords + 1;
 
 // ---- packed 16x2 helpers (VIMNMX.S16x2 / VIADD.16x2 / PRMT on sm_100a; plain C on the host) ------------------------------
 FS_FN uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -216,9 +216,9 @@ FS_FN void exclusive_scan(int* v, int n, int* warp_sums) {
 }
 
 // One strip of one frame.  lvl: this frame's level origin; tile / sc: rows_cap x kPitch bytes each (16-byte aligned);
-// list: one entry per tested pixel of the strip; cnt: kCntInts; misc: kMiscInts.
+// list: one entry per tested pixel of the strip; words: one entry per tile word (rows_cap * kPitch / 4); cnt: kCntInts; misc: kMiscInts.
 FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo* cells, int min_bx, int min_by, int ini_th, int min_th,
-               uint8_t* tile, uint8_t* sc, uint16_t* list, int* cnt, int* misc, uint32_t* slots, int* counts, int* overflow) {
+               uint8_t* tile, uint8_t* sc, uint16_t* list, uint16_t* words, int* cnt, int* misc, uint32_t* slots, int* counts, int* overflow) {
     constexpr int P = kPitch, PW = kPitch / 4;
     uint32_t* tile32 = reinterpret_cast<uint32_t*>(tile);
     uint32_t* sc32 = reinterpret_cast<uint32_t*>(sc);
@@ -244,7 +244,7 @@ FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo
         misc[kCellR + k] = ci.x0 - si.x0 + a + ci.cw - 3;
         misc[kAnyIni + k] = 0;
     }
-    if (FS_TID == 0) misc[kNList] = 0;
+    if (FS_TID == 0) { misc[kNList] = 0; misc[kNWords] = 0; }
     // per tile word: 0x00 in the bytes whose pixel is the first (lmask) / last (rmask) tested column of a cell - the NMS of that pixel
     // does not look at its left / right neighbours (they belong to another cv::FAST call).  cnt[] is free until P4.
     uint32_t* lmask = reinterpret_cast<uint32_t*>(cnt);
@@ -289,31 +289,48 @@ FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo
     }
     FS_SYNC();
 
-    // ---- P2: arc strength of the listed pixels (dense over the CTA) ---------------------------------------------------
+    // ---- P2: arc strength of the listed pixels (dense over the CTA).  A corner's score goes into the score map with an OR on its
+    //          word (the map was cleared in P0, every byte is written once); the pixel that finds the word still empty appends the
+    //          word to a second list, so that P3 runs densely over the words that hold a score at all (about one in five) instead of
+    //          branching around the others with every warp paying for the full path. ------------------------------------------------
     {
         const int nl = misc[kNList];
         FS_FOR(j, (nl + 1) >> 1) {                         // two listed pixels per item, packed 16x2
             const int pa = list[2 * j], pb = (2 * j + 1 < nl) ? list[2 * j + 1] : pa;
             int sa, sb;
             score_pair(tile, pa, pb, min_th, &sa, &sb);
-            sc[pa] = (uint8_t)sa;
-            if (pb != pa) sc[pb] = (uint8_t)sb;
+            if (pb == pa) sb = 0;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int pp = u ? pb : pa, sv = u ? sb : sa;
+                if (sv == 0) continue;
+                const uint32_t add = (uint32_t)sv << (8 * (pp & 3));
+#if FS_DEVICE
+                const uint32_t old = atomicOr(&sc32[pp >> 2], add);
+                if (!old) words[atomicAdd(&misc[kNWords], 1)] = (uint16_t)(pp >> 2);
+#else
+                const uint32_t old = sc32[pp >> 2];
+                sc32[pp >> 2] = old | add;
+                if (!old) words[misc[kNWords]++] = (uint16_t)(pp >> 2);
+#endif
+            }
         }
     }
     FS_SYNC();
 
     // ---- P3: 3x3 non-maximum suppression inside each cell's tested region; flags (1 = survivor at minTh, 3 = also at iniTh)
-    //          overwrite the (no longer needed) pixel tile.  Four pixels per item, branch-free: the eight neighbour scores of the
+    //          overwrite the (no longer needed) pixel tile words of the score-carrying words.  Four pixels per item, branch-free: the eight neighbour scores of the
     //          word's pixels are byte-shifted copies of nine score words; byte maxima are taken on even / odd bytes widened to 16x2
     //          (VIMNMX.U16x2), "s > m" and "s >= iniTh" are bit 8 of s + 255 - m and s + 256 - iniTh per half. -------------------
     {
         const uint32_t ini2 = (uint32_t)(ini_th < 0 ? 0 : (ini_th > 256 ? 256 : ini_th)) * 0x00010001u;   // scores are <= 255
-        for (Iter2D it = it_begin(ny, nxw); it.i < it.n; it_next(it)) {
-            const int row = it.y + 3, c = wb + it.x;
-            const uint32_t* q = sc32 + row * PW + c;
+        const int n_words = misc[kNWords];
+        FS_FOR(j, n_words) {
+            const int wi = words[j], row = wi / PW, c = wi - row * PW;
+            const uint32_t* q = sc32 + wi;
             const uint32_t mid = q[0];
             uint32_t flags = 0;
-            if (mid) {
+            {
                 const uint32_t up = q[-PW], dn = q[PW];
                 const uint32_t l0 = shl8(q[-PW - 1], up), l1 = shl8(q[-1], mid), l2 = shl8(q[PW - 1], dn);
                 const uint32_t r0 = shr8(up, q[-PW + 1]), r1 = shr8(mid, q[1]), r2 = shr8(dn, q[PW + 1]);
@@ -350,7 +367,7 @@ FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo
 #endif
                 }
             }
-            tile32[row * PW + c] = flags;
+            tile32[wi] = flags;              // only the words of the list hold flags; the others still hold pixels (P4 looks at sc32 first)
         }
     }
     FS_SYNC();
@@ -364,7 +381,7 @@ FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo
         int n = 0;
         if (R > L)
             for (int wd = L >> 2; wd <= (R - 1) >> 2; ++wd)
-                n += popc(tile32[row * PW + wd] & sel & byte_range_mask(L - 4 * wd, R - 4 * wd));
+                if (sc32[row * PW + wd]) n += popc(tile32[row * PW + wd] & sel & byte_range_mask(L - 4 * wd, R - 4 * wd));
         cnt[it] = n;
     }
     FS_SYNC();
@@ -377,7 +394,7 @@ FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo
         uint32_t* out = slots + (size_t)(si.first_cell + k) * kCellCap;
         if (R > L)
             for (int wd = L >> 2; wd <= (R - 1) >> 2; ++wd) {
-                uint32_t f = tile32[row * PW + wd] & sel & byte_range_mask(L - 4 * wd, R - 4 * wd);
+                uint32_t f = sc32[row * PW + wd] ? (tile32[row * PW + wd] & sel & byte_range_mask(L - 4 * wd, R - 4 * wd)) : 0u;
                 while (f) {
 #if FS_DEVICE
                     const int b = (__ffs(f) - 1) >> 3;

@@ -377,23 +377,45 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         }
         // one thread per ENTRY (a query's list may hold dozens of candidates: a per-query loop would serialise its chains of
         // dependent global loads list -> csr -> keypoint); the owning query is found by bisection of the offsets
+        // Four entries per thread and trip: the chain list -> csr -> keypoint is three dependent global loads, so the bisections and
+        // each load level of the four entries are issued together and their latencies overlap (E / 1024 is 2-4 on KITTI frames).
         const float factor = 1.0f / kHistoLength;
-        for (int en = tid; en < E; en += 1024) {
-            int lo = 0, hi = n_q;                          // largest q with s_off[q] <= en
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= en) lo = mid; else hi = mid; }
-            const int q = lo;
-            const uint32_t key = lists[(size_t)q * list_cap + (en - s_off[q])];
-            const int ft = csr_idx[key & kPosMask];
-            unsigned oc = 0, bin = 0;
-            if (mode == 1) oc = (unsigned)f.keys[ft].octave & 0xffu;
-            if (orient) {
-                float rot = __fsub_rn(q_angle[q], f_angle ? f_angle[ft] : f.keys[ft].angle);
-                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                int b = (int)roundf(__fmul_rn(rot, factor));
-                if (b == kHistoLength) b = 0;
-                bin = (unsigned)b & 0xffu;
+        for (int en0 = tid; en0 < E; en0 += 4096) {
+            int qq[4], ftt[4]; uint32_t kk[4]; unsigned occ[4]; float fa[4], qa[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int en = en0 + u * 1024;
+                int lo = 0, hi = n_q;                      // largest q with s_off[q] <= en
+                if (en < E) while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= en) lo = mid; else hi = mid; }
+                qq[u] = lo;
             }
-            s_ent[en] = ((unsigned long long)key << 32) | (bin << 24) | (oc << 16) | (unsigned)ft;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int en = en0 + u * 1024; kk[u] = (en < E) ? lists[(size_t)qq[u] * list_cap + (en - s_off[qq[u]])] : 0u; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int en = en0 + u * 1024; ftt[u] = (en < E) ? csr_idx[kk[u] & kPosMask] : 0; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int en = en0 + u * 1024;
+                occ[u] = 0; fa[u] = 0.f; qa[u] = 0.f;
+                if (en < E) {
+                    if (mode == 1) occ[u] = (unsigned)f.keys[ftt[u]].octave & 0xffu;
+                    if (orient) { fa[u] = f_angle ? f_angle[ftt[u]] : f.keys[ftt[u]].angle; qa[u] = q_angle[qq[u]]; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int en = en0 + u * 1024;
+                if (en >= E) continue;
+                unsigned bin = 0;
+                if (orient) {
+                    float rot = __fsub_rn(qa[u], fa[u]);
+                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                    int b = (int)roundf(__fmul_rn(rot, factor));
+                    if (b == kHistoLength) b = 0;
+                    bin = (unsigned)b & 0xffu;
+                }
+                s_ent[en] = ((unsigned long long)kk[u] << 32) | (bin << 24) | (occ[u] << 16) | (unsigned)ftt[u];
+            }
         }
         __syncthreads();
         RQ(2);
@@ -495,16 +517,17 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             __syncthreads();
             n_act = s_cnt[0];
         }
-        while (n_act > 32) {
+        // One round by the first T threads of the CTA (T a multiple of 32); `sync` is the barrier of exactly those threads.
+        auto round = [&](const int T, auto sync) {
             int* mq = s_minq + (size_t)cur * n_f;
             int* mq_next = s_minq + (size_t)(cur ^ 1) * n_f;
             const int* lst = s_list + (size_t)cur * n_q;
             int* lst_next = s_list + (size_t)(cur ^ 1) * n_q;
             if (tid == 0) s_cnt[cur ^ 1] = 0;
-            for (int i = tid; i < n_f; i += 1024) mq_next[i] = 0x7fffffff;
-            for (int i = tid; i < n_act; i += 1024) propose(lst[i], mq);
-            __syncthreads();
-            for (int i0 = 0; i0 < n_act; i0 += 1024) {
+            for (int i = tid; i < n_f; i += T) mq_next[i] = 0x7fffffff;
+            for (int i = tid; i < n_act; i += T) propose(lst[i], mq);
+            sync();
+            for (int i0 = 0; i0 < n_act; i0 += T) {
                 const int i = i0 + tid;
                 const int q = i < n_act ? lst[i] : -1;
                 const bool w = q >= 0 && decide(q, mq);
@@ -516,9 +539,15 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             }
             ++rounds;
             cur ^= 1;
-            __syncthreads();
+            sync();
             n_act = s_cnt[cur];
-        }
+        };
+        // After the first round or two only a few hundred queries still wait (those with contested candidates), so the rounds
+        // continue on a TEAM of kTeam threads with a named barrier of that size: a barrier over 8 warps costs a fraction of one
+        // over 32, and the other 24 warps just park at the CTA barrier below.  <= 32 waiting queries: warp 0 alone, as before.
+        constexpr int kTeam = 256;
+        while (n_act > kTeam) round(1024, [] { __syncthreads(); });
+        if (tid < kTeam) while (n_act > 32) round(kTeam, [] { team_sync(kTeam); });
         if (n_act > 0 && tid < 32) {
             int* mq = s_minq + (size_t)cur * n_f;     // a fully cleared table; the tail clears only what it touches
             const int q0 = tid < n_act ? s_list[(size_t)cur * n_q + tid] : -1;
@@ -673,37 +702,57 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         for (int i = tid; i < n_f; i += 1024) match[i] = mt[i];
     }
     if (ce.n_edges) {                     // ordered compaction of the matched features into edges
+        // Two chunks of 1024 features per trip (a KITTI frame is one trip): everything an edge needs is loaded for both chunks before the
+        // positions are known, so the trip pays ONE round of global latency; the positions come from warp ballots and a 64-entry scan.
+        __shared__ int s_wcnt[2][32];
         __syncthreads();
         const int lane = tid & 31, warp = tid >> 5;
-        if (tid == 0) s_total = 0;        // running edge count
-        __syncthreads();
-        for (int b = 0; b < n_f; b += 1024) {
-            const int i = b + tid;
-            const int m = (i < n_f) ? mt[i] : -1;
-            const int flag = m >= 0;
-            int incl = flag;
+        int run = 0;                      // edges before this trip (same value in every thread)
+        for (int b = 0; b < n_f; b += 2048) {
+            int m[2]; float kx[2], ky[2], ur[2], xw[2][3]; int oc[2]; unsigned bal[2];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            if (lane == 31) s_wsum[warp] = incl;
+            for (int c = 0; c < 2; ++c) { const int i = b + c * 1024 + tid; m[c] = (i < n_f) ? mt[i] : -1; }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int i = b + c * 1024 + tid;
+                kx[c] = ky[c] = ur[c] = xw[c][0] = xw[c][1] = xw[c][2] = 0.f; oc[c] = 0;
+                if (m[c] >= 0) {
+                    kx[c] = ce.kps[i].x; ky[c] = ce.kps[i].y; oc[c] = ce.kps[i].octave; ur[c] = ce.uright[i];
+                    xw[c][0] = ce.last_xw[3 * m[c]]; xw[c][1] = ce.last_xw[3 * m[c] + 1]; xw[c][2] = ce.last_xw[3 * m[c] + 2];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) { bal[c] = __ballot_sync(0xffffffffu, m[c] >= 0); if (lane == 0) s_wcnt[c][warp] = __popc(bal[c]); }
             __syncthreads();
-            int base = s_total;
-            for (int w = 0; w < warp; ++w) base += s_wsum[w];
-            if (flag) {
-                const int e = base + incl - 1;
-                const rgbl_keypoint kp = ce.kps[i];
-                ce.exw[3 * e] = ce.last_xw[3 * m]; ce.exw[3 * e + 1] = ce.last_xw[3 * m + 1]; ce.exw[3 * e + 2] = ce.last_xw[3 * m + 2];
-                const float ur = ce.uright[i];
-                ce.eobs[3 * e] = kp.x; ce.eobs[3 * e + 1] = kp.y; ce.eobs[3 * e + 2] = ur;
-                const float sc = f.scale[kp.octave];
-                ce.einfo[e] = __fdiv_rn(1.0f, __fmul_rn(sc, sc));            // mvInvLevelSigma2 (src/ORBextractor.cc:421-429)
-                ce.est[e] = ur >= 0.f;
-                ce.eidx[e] = i;
+            if (warp == 0) {              // exclusive scan of the 64 warp counts in chunk-major order
+                const int v0 = s_wcnt[0][lane], v1 = s_wcnt[1][lane];
+                int i0 = v0, i1 = v1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                    if (lane >= o) { i0 += t0; i1 += t1; }
+                }
+                const int tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+                s_wcnt[0][lane] = i0 - v0; s_wcnt[1][lane] = tot0 + i1 - v1;
+                if (lane == 0) s_total = tot0 + tot1;
             }
             __syncthreads();
-            if (tid == 1023) s_total = base + incl;
-            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (m[c] < 0) continue;
+                const int i = b + c * 1024 + tid;
+                const int e = run + s_wcnt[c][warp] + __popc(bal[c] & ((1u << lane) - 1u));
+                ce.exw[3 * e] = xw[c][0]; ce.exw[3 * e + 1] = xw[c][1]; ce.exw[3 * e + 2] = xw[c][2];
+                ce.eobs[3 * e] = kx[c]; ce.eobs[3 * e + 1] = ky[c]; ce.eobs[3 * e + 2] = ur[c];
+                const float sc = f.scale[oc[c]];
+                ce.einfo[e] = __fdiv_rn(1.0f, __fmul_rn(sc, sc));            // mvInvLevelSigma2 (src/ORBextractor.cc:421-429)
+                ce.est[e] = ur[c] >= 0.f;
+                ce.eidx[e] = i;
+            }
+            run += s_total;
+            __syncthreads();              // s_wcnt / s_total are rewritten by the next trip
         }
-        if (tid == 0) *ce.n_edges = s_total;
+        if (tid == 0) *ce.n_edges = run;
     }
     {
 #pragma unroll

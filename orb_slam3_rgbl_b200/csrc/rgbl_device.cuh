@@ -180,6 +180,15 @@ __device__ __forceinline__ void quatf_to_matrix(const float q[4], float R[9]) {
     R[6] = __fsub_rn(txz, twy); R[7] = __fadd_rn(tyz, twx); R[8] = __fsub_rn(1.f, __fadd_rn(txx, tyy));
 }
 
+// barrier of the first `nthreads` threads of a CTA (a multiple of 32; named barrier 1), for phases that only a few warps take part in
+__device__ __forceinline__ void team_sync(int nthreads) {
+#ifdef RGBL_CUDA_EMU
+    emu::named_barrier(nthreads);
+#else
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+#endif
+}
+
 // ---- Frame::isInFrustum (src/Frame.cc:602-664, Nleft == -1) + MapPoint::PredictScale (src/MapPoint.cc:531-545) for one map point.
 // Float32, Eigen 3.3's reduction order for mRcw * P, norm() and dot(); pinned against the reference's own function body
 // (tests/test_oracle_tracking_ref.py::test_is_in_frustum_and_search_local).

@@ -17,6 +17,7 @@
 #include <vector>
 
 #define __CUDA_ARCH__ 1000
+#define RGBL_CUDA_EMU 1
 #define __CUDACC__ 1
 #define __global__
 #define __device__
@@ -50,6 +51,7 @@ struct Cta {
     std::unique_ptr<std::barrier<>> bar;
     std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
     std::vector<std::array<unsigned long long, 32>> slot;
+    std::atomic<int> nb_count{0}, nb_gen{0};      // named barrier of a subset of the CTA's threads (team_sync)
 };
 extern Cta* g_cta;
 extern thread_local int t_warp, t_lane;
@@ -58,6 +60,12 @@ inline Cfg cfg(dim3 g, dim3 b, size_t smem = 0, cudaStream_t = nullptr) { return
 void run(const Cfg& c, const std::function<void()>& body);
 inline double approx64(double v) { unsigned long long u; std::memcpy(&u, &v, 8); u &= 0xffffffff00000000ull; std::memcpy(&v, &u, 8); return v; }
 inline void warp_sync() { g_cta->warp_bar[t_warp]->arrive_and_wait(); }
+inline void named_barrier(int n) {
+    Cta* c = g_cta;
+    const int gen = c->nb_gen.load();
+    if (c->nb_count.fetch_add(1) + 1 == n) { c->nb_count.store(0); c->nb_gen.fetch_add(1); }
+    else while (c->nb_gen.load() == gen) std::this_thread::yield();
+}
 template <class T> inline T exchange(T v, int src_lane) {       // every lane publishes v, reads lane src_lane's value
     unsigned long long raw = 0;
     std::memcpy(&raw, &v, sizeof(T));

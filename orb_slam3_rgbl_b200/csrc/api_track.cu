@@ -649,10 +649,11 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
                 LocalPointsDev lp{n_lq, d_nq, lq.in_view, lq.proj_x, lq.proj_y, lq.proj_xr, lq.depth, lq.level, lq.view_cos, lq.desc, lq.obs_pos};
                 SearchLocalParams sl{};
                 sl.th = P.th_local; sl.nn_ratio = P.nn_ratio_local; sl.th_far = 0.f; sl.use_factor = (P.th_local != 1.0f) ? 1 : 0; sl.far_points = 0; sl.keep_max = std::min(256, (int)std::floor((float)100 / P.nn_ratio_local) + 1);
-                launch_search_local(cs, f, cell_start, csr_idx, lp, sl, ms, t.state, t.match_local, t.scalars + 1); n_launches += 2;      // d_nml + k is accumulated by tlm_edges
-                if (tm) cudaEventRecord(tev[4], cs);
+                // the resolution kernel of the local search also writes the edge list of the second optimisation and hands the last frame's points to the ring
                 const ChainEdgesOut eo2{t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne2};
-                launch_tlm_edges(cs, f, t.match, t.q_f3a, t.match_local, lq.xw, ring, eo2, d_nml + k, cap, t.q_u8a, t.q_i, last_desc, last_pose, t.lookback, d_ovf); ++n_launches;
+                const ChainTlmTail tail{t.match, t.q_f3a, lq.xw, ring, eo2, d_nml + k, cap, t.q_u8a, t.q_i, last_desc, last_pose};
+                launch_search_local(cs, f, cell_start, csr_idx, lp, sl, ms, t.state, t.match_local, t.scalars + 1, &tail); n_launches += 2;
+                if (tm) cudaEventRecord(tev[4], cs);
                 if (tm) cudaEventRecord(tev[5], cs);
                 PoseProblemDev p2 = p;
                 p2.n_dev = d_ne2; p2.pose_in_dev = pose_tmp;
@@ -748,7 +749,7 @@ int rgbl_resident_track_end2(rgbl_ctx* ctx, float* poses_out, int* n_matches, in
     const int* h_i = c->h_chain_i + (size_t)slot * (4 * c->h_chain_cap + 8);
     if (c->chain_timing_ev && c->chain_pending == 0) {
         const cudaEvent_t* e = static_cast<const cudaEvent_t*>(c->chain_timing_ev);
-        const char* names[6] = {"chain_prep (first frame only)", "search_last (collect+resolve+edges)", "pose_optimize #1", "tlm_prepare + search_local", "tlm_edges", "pose_optimize #2"};
+        const char* names[6] = {"chain_prep (first frame only)", "search_last (collect+resolve+edges)", "pose_optimize #1", "tlm_prepare + search_local (+edges, hand-over)", "-", "pose_optimize #2"};
         for (int i = 0; i < 6; ++i) { float ms = 0; if (cudaEventElapsedTime(&ms, e[i], e[i + 1]) == cudaSuccess) std::fprintf(stderr, "[chain timing] %-36s %8.2f us\n", names[i], ms * 1e3f); }
         cudaGetLastError();
     }

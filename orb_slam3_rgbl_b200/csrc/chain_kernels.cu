@@ -1,13 +1,12 @@
 // Resident tracking chain, TrackLocalMap half (src/Tracking.cc:2983-3050, 3377-3460): after TrackWithMotionModel's
 // SearchByProjection(last frame) + PoseOptimization, the reference discards the outliers, projects the local map points that are not
 // matched yet (Frame::isInFrustum, src/Frame.cc:602-664), searches them (ORBmatcher::SearchByProjection(F, vpMapPoints, th),
-// src/ORBmatcher.cc:43-213) and runs PoseOptimization again on all the frame's map points.  The two single-CTA kernels below are the
+// src/ORBmatcher.cc:43-213) and runs PoseOptimization again on all the frame's map points.  The kernel below is the
 // device-side glue between those reference functions (the functions themselves are match_kernels.cu / pose_kernels.cu):
 //   tlm_prepare_kernel : outlier discard (src/Tracking.cc:2944-2966) -> isInFrustum over the local map -> ORDERED compaction of the
 //                        visible points into the query arrays of the local search (the order of vpMapPoints decides ties);
-//   tlm_edges_kernel   : PoseOptimization's edge list in keypoint order from (inliers of the first search) + (local matches)
-//                        (src/Optimizer.cc:857-990), and the hand-over of the last frame's points into the local map
-//                        (MapPoint::UpdateNormalAndDepth, src/MapPoint.cc:437-490, one observation).
+//   (PoseOptimization's edge list in keypoint order from (inliers of the first search) + (local matches), src/Optimizer.cc:857-990, and the
+//    hand-over of the last frame's points into the local map are the tail of the local search's resolution kernel: match_kernels.cu, ChainTlmDev.)
 // The local map of the harness is a ring of the K frames before the last one, each contributing its LiDAR-depth keypoints unprojected
 // with the frame's final pose; slot = frame counter mod K, points inside a slot in keypoint order.
 #include "rgbl_kernels.h"
@@ -121,7 +120,7 @@ __global__ void __launch_bounds__(kTlmThreads) tlm_prepare_kernel(FrameDev f, co
         lq.in_view[pos] = 1; lq.obs_pos[pos] = 1;
         lq.proj_x[pos] = o.px; lq.proj_y[pos] = o.py; lq.proj_xr[pos] = o.pxr; lq.depth[pos] = o.depth; lq.level[pos] = o.level;
         lq.view_cos[pos] = o.view_cos; lq.src[pos] = p;
-        lq.xw[3 * pos] = P[0]; lq.xw[3 * pos + 1] = P[1]; lq.xw[3 * pos + 2] = P[2];      // tlm_edges reads the point here, not in the ring
+        lq.xw[3 * pos] = P[0]; lq.xw[3 * pos + 1] = P[1]; lq.xw[3 * pos + 2] = P[2];      // the edge list takes the point from here, not from the ring
         const uint4* d = reinterpret_cast<const uint4*>(ring.desc + (size_t)p * 32);
         uint4* dd = reinterpret_cast<uint4*>(lq.desc + (size_t)pos * 32);
         dd[0] = d[0]; dd[1] = d[1];
@@ -135,109 +134,16 @@ __global__ void __launch_bounds__(kTlmThreads) tlm_prepare_kernel(FrameDev f, co
     }
 }
 
-// grid = ceil(cap / kTlmThreads) CTAs: thread i owns feature i of the current frame (edge phase) and point i of the last frame (hand-over)
-__global__ void __launch_bounds__(kTlmThreads) tlm_edges_kernel(FrameDev f, const int* __restrict__ match_last, const float* __restrict__ last_xw,
-                                                                const int* __restrict__ match_local, const float* __restrict__ lq_xw,
-                                                                LocalRingDev ring, ChainEdgesOut eo, int* __restrict__ n_local_matches,
-                                                                // hand-over of the last frame's points into the local map
-                                                                int n_last_cap, const uint8_t* __restrict__ last_valid, const int* __restrict__ last_octave,
-                                                                const uint8_t* __restrict__ last_desc, const float* __restrict__ last_pose, Lookback lb) {
-    __shared__ int s_wsum[kTlmThreads / 32];
-    __shared__ int s_base;
-    const int tid = threadIdx.x;
-    const int n_part = (int)gridDim.x;
-    const int i = (int)blockIdx.x * kTlmThreads + tid;
-    const int n_f = *f.n;
-    const int ring_count = *ring.count;
-    // everything the hand-over needs is loaded up front, next to the edge phase's own loads: one round of global latency for both
-    uint8_t lv = 0;
-    float P[3] = {0.f, 0.f, 0.f};
-    int loct = 0;
-    uint4 ld0{0u, 0u, 0u, 0u}, ld1 = ld0;
-    if (i < ring.cap && i < n_last_cap && last_valid[i]) {
-        lv = 1;
-        P[0] = last_xw[3 * i]; P[1] = last_xw[3 * i + 1]; P[2] = last_xw[3 * i + 2];
-        loct = last_octave[i];
-        ld0 = reinterpret_cast<const uint4*>(last_desc + (size_t)i * 32)[0];
-        ld1 = reinterpret_cast<const uint4*>(last_desc + (size_t)i * 32)[1];
-    }
-    float Ow[3];
-    {
-        float T[7], qinv[4];
-#pragma unroll
-        for (int k = 0; k < 7; ++k) T[k] = last_pose[k];
-        se3f_inverse(T, qinv, Ow);                         // KeyFrame::GetCameraCenter of the frame the points were created from
-    }
-    const int ma = (i < n_f) ? match_last[i] : -1;
-    const int mb = (i < n_f && ma < 0) ? match_local[i] : -1;
-    const int flag = (ma >= 0 || mb >= 0) ? 1 : 0;
-    float x[3] = {0.f, 0.f, 0.f}, ur = 0.f;
-    rgbl_keypoint kp{};
-    if (flag) {
-        const float* xs = (ma >= 0) ? (last_xw + 3 * (size_t)ma) : (lq_xw + 3 * (size_t)mb);
-        x[0] = xs[0]; x[1] = xs[1]; x[2] = xs[2];
-        kp = f.keys[i];
-        ur = f.uright[i];
-    }
-    int total = 0;
-    const int rank = block_rank(flag, s_wsum, total);
-    const unsigned mloc = __ballot_sync(0xffffffffu, mb >= 0);
-    if ((tid & 31) == 0 && mloc) atomicAdd(n_local_matches, __popc(mloc));
-    const int base = lb_exclusive_base(lb, total, &s_base);
-    if (flag) {
-        const int e = base + rank;
-        eo.exw[3 * e] = x[0]; eo.exw[3 * e + 1] = x[1]; eo.exw[3 * e + 2] = x[2];
-        eo.eobs[3 * e] = kp.x; eo.eobs[3 * e + 1] = kp.y; eo.eobs[3 * e + 2] = ur;
-        const float sc = f.scale[kp.octave];
-        eo.einfo[e] = __fdiv_rn(1.0f, __fmul_rn(sc, sc));                  // mvInvLevelSigma2 (src/ORBextractor.cc:421-429)
-        eo.est[e] = ur >= 0.f;
-        eo.eidx[e] = i;
-    }
-    if (tid == 0 && (int)blockIdx.x == n_part - 1) *eo.n_edges = base + total;
-    // The ring slot that takes the last frame's points is still part of THIS frame's local map, but nothing in this kernel reads the ring:
-    // the edges take their points from the query copy tlm_prepare made (lq_xw), so the hand-over needs no grid-wide barrier.
-    // the last frame's points become local map points (ring slot = frames inserted so far mod K)
-    if (i < ring.cap) {
-        const size_t p = (size_t)(ring_count % ring.K) * ring.cap + i;
-        if (lv) {
-            const float PC[3] = {__fsub_rn(P[0], Ow[0]), __fsub_rn(P[1], Ow[1]), __fsub_rn(P[2], Ow[2])};
-            const float dist = sqrtf(eig_sum3(__fmul_rn(PC[0], PC[0]), __fmul_rn(PC[1], PC[1]), __fmul_rn(PC[2], PC[2])));
-            ring.xw[3 * p] = P[0]; ring.xw[3 * p + 1] = P[1]; ring.xw[3 * p + 2] = P[2];
-            ring.normal[3 * p] = __fdiv_rn(PC[0], dist); ring.normal[3 * p + 1] = __fdiv_rn(PC[1], dist); ring.normal[3 * p + 2] = __fdiv_rn(PC[2], dist);
-            const float mx = __fmul_rn(dist, f.scale[loct]);
-            ring.mf_max[p] = mx;
-            ring.mf_min[p] = __fdiv_rn(mx, f.scale[f.n_levels - 1]);
-            uint4* dd = reinterpret_cast<uint4*>(ring.desc + p * 32);
-            dd[0] = ld0; dd[1] = ld1;
-        }
-        ring.valid[p] = lv;
-    }
-    if (tid == 0 && lb_last_ticket(lb.done, n_part)) {           // every CTA has read ring.count and finished its look-back
-        for (int j = 0; j < n_part; ++j) lb.slots[j] = 0;
-        *lb.done = 0;
-        *ring.count = ring_count + 1;
-    }
-}
-
 }  // namespace
 
-// lb: 2 * (kLbSlots + 8) zero-initialised ints owned by the caller (one half per kernel); fail: the chain's overflow flag
-int tlm_lookback_ints() { return 2 * (kLbSlots + 8); }
+// lb: kLbSlots + 8 zero-initialised ints owned by the caller; fail: the chain's overflow flag
+int tlm_lookback_ints() { return kLbSlots + 8; }
 
 void launch_tlm_prepare(cudaStream_t st, const FrameDev& f, const float* pose, const LocalRingDev& ring, float cos_limit, const int* n_edges,
                         const int* e_idx, const uint8_t* e_outlier, uint8_t* state, int* match_last, const LocalQueriesDev& lq, int* lb, int* fail) {
     const int n_part = (ring.K * ring.cap + kTlmThreads - 1) / kTlmThreads;
     const Lookback l{lb, lb + kLbSlots, fail};
     tlm_prepare_kernel<<<n_part + 1, kTlmThreads, 0, st>>>(f, pose, ring, cos_limit, n_edges, e_idx, e_outlier, state, match_last, lq, l);
-}
-
-void launch_tlm_edges(cudaStream_t st, const FrameDev& f, const int* match_last, const float* last_xw, const int* match_local, const float* lq_xw,
-                      const LocalRingDev& ring, const ChainEdgesOut& eo, int* n_local_matches, int n_last_cap, const uint8_t* last_valid,
-                      const int* last_octave, const uint8_t* last_desc, const float* last_pose, int* lb, int* fail) {
-    const int n_part = (ring.cap + kTlmThreads - 1) / kTlmThreads;
-    const Lookback l{lb + kLbSlots + 8, lb + 2 * kLbSlots + 8, fail};
-    tlm_edges_kernel<<<n_part, kTlmThreads, 0, st>>>(f, match_last, last_xw, match_local, lq_xw, ring, eo, n_local_matches, n_last_cap, last_valid,
-                                                     last_octave, last_desc, last_pose, l);
 }
 
 }  // namespace rgbl

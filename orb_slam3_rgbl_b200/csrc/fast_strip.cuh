@@ -216,9 +216,10 @@ FS_FN void exclusive_scan(int* v, int n, int* warp_sums) {
 }
 
 // One strip of one frame.  lvl: this frame's level origin; tile / sc: rows_cap x kPitch bytes each (16-byte aligned);
-// list: one entry per tested pixel of the strip; words: one entry per tile word (rows_cap * kPitch / 4); cnt: kCntInts; misc: kMiscInts.
+// list: list_cap entries, one per tested pixel of the strip (the list of score-carrying words grows down from its end); cnt: kCntInts;
+// misc: kMiscInts.
 FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo* cells, int min_bx, int min_by, int ini_th, int min_th,
-               uint8_t* tile, uint8_t* sc, uint16_t* list, uint16_t* words, int* cnt, int* misc, uint32_t* slots, int* counts, int* overflow) {
+               uint8_t* tile, uint8_t* sc, uint16_t* list, int list_cap, int* cnt, int* misc, uint32_t* slots, int* counts, int* overflow) {
     constexpr int P = kPitch, PW = kPitch / 4;
     uint32_t* tile32 = reinterpret_cast<uint32_t*>(tile);
     uint32_t* sc32 = reinterpret_cast<uint32_t*>(sc);
@@ -292,14 +293,24 @@ FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo
     // ---- P2: arc strength of the listed pixels (dense over the CTA).  A corner's score goes into the score map with an OR on its
     //          word (the map was cleared in P0, every byte is written once); the pixel that finds the word still empty appends the
     //          word to a second list, so that P3 runs densely over the words that hold a score at all (about one in five) instead of
-    //          branching around the others with every warp paying for the full path. ------------------------------------------------
+    //          branching around the others with every warp paying for the full path.  The word list grows DOWN from the end of the
+    //          pixel list's buffer (an own buffer cost a resident CTA per SM): that is safe when both lists fit, nl + min(nl, words)
+    //          <= list_cap, which only a window where nearly every pixel passes the high-speed test violates - then P3 walks all words. --
+    const int nl = misc[kNList];
+    const int n_tested_words = ny * nxw;
+    const bool dense_nms = nl + (nl < n_tested_words ? nl : n_tested_words) <= list_cap;
+    uint16_t* words_top = list + list_cap - 1;             // word k of the second list = words_top[-k]
     {
-        const int nl = misc[kNList];
         FS_FOR(j, (nl + 1) >> 1) {                         // two listed pixels per item, packed 16x2
             const int pa = list[2 * j], pb = (2 * j + 1 < nl) ? list[2 * j + 1] : pa;
             int sa, sb;
             score_pair(tile, pa, pb, min_th, &sa, &sb);
             if (pb == pa) sb = 0;
+            if (!dense_nms) {
+                sc[pa] = (uint8_t)sa;
+                if (pb != pa) sc[pb] = (uint8_t)sb;
+                continue;
+            }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int pp = u ? pb : pa, sv = u ? sb : sa;
@@ -307,11 +318,11 @@ FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo
                 const uint32_t add = (uint32_t)sv << (8 * (pp & 3));
 #if FS_DEVICE
                 const uint32_t old = atomicOr(&sc32[pp >> 2], add);
-                if (!old) words[atomicAdd(&misc[kNWords], 1)] = (uint16_t)(pp >> 2);
+                if (!old) words_top[-atomicAdd(&misc[kNWords], 1)] = (uint16_t)(pp >> 2);
 #else
                 const uint32_t old = sc32[pp >> 2];
                 sc32[pp >> 2] = old | add;
-                if (!old) words[misc[kNWords]++] = (uint16_t)(pp >> 2);
+                if (!old) words_top[-(misc[kNWords]++)] = (uint16_t)(pp >> 2);
 #endif
             }
         }
@@ -324,9 +335,7 @@ FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo
     //          (VIMNMX.U16x2), "s > m" and "s >= iniTh" are bit 8 of s + 255 - m and s + 256 - iniTh per half. -------------------
     {
         const uint32_t ini2 = (uint32_t)(ini_th < 0 ? 0 : (ini_th > 256 ? 256 : ini_th)) * 0x00010001u;   // scores are <= 255
-        const int n_words = misc[kNWords];
-        FS_FOR(j, n_words) {
-            const int wi = words[j], row = wi / PW, c = wi - row * PW;
+        auto nms_word = [&](const int wi, const int c) {
             const uint32_t* q = sc32 + wi;
             const uint32_t mid = q[0];
             uint32_t flags = 0;
@@ -367,7 +376,19 @@ FS_FN void run(const uint8_t* lvl, int pitch, const StripInfo si, const CellInfo
 #endif
                 }
             }
-            tile32[wi] = flags;              // only the words of the list hold flags; the others still hold pixels (P4 looks at sc32 first)
+            tile32[wi] = flags;              // dense form: only the listed words hold flags, the others still pixels (P4 looks at sc32 first)
+        };
+        if (dense_nms) {
+            const int n_words = misc[kNWords];
+            FS_FOR(j, n_words) {
+                const int wi = words_top[-j], row = wi / PW;
+                nms_word(wi, wi - row * PW);
+            }
+        } else {
+            for (Iter2D it = it_begin(ny, nxw); it.i < it.n; it_next(it)) {
+                const int wi = (it.y + 3) * PW + wb + it.x;
+                if (sc32[wi]) nms_word(wi, wb + it.x); else tile32[wi] = 0;
+            }
         }
     }
     FS_SYNC();

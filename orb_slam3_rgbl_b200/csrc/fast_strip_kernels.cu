@@ -13,10 +13,9 @@
 
 namespace rgbl {
 
-// dynamic shared memory: tile | score map | survivor list | score-word list | counts | misc
-static size_t words_bytes(int rows_cap) { return (((size_t)rows_cap * (fs::kPitch / 4) * 2 + 15) & ~(size_t)15); }
+// dynamic shared memory: tile | score map | survivor list (+ score-word list from its end) | counts | misc
 static size_t strip_smem_bytes(int rows_cap, int list_cap) {
-    return 2 * (size_t)rows_cap * fs::kPitch + (((size_t)list_cap * 2 + 15) & ~(size_t)15) + words_bytes(rows_cap) + (size_t)(fs::kCntInts + fs::kMiscInts) * sizeof(int);
+    return 2 * (size_t)rows_cap * fs::kPitch + (((size_t)list_cap * 2 + 15) & ~(size_t)15) + (size_t)(fs::kCntInts + fs::kMiscInts) * sizeof(int);
 }
 
 __global__ void __launch_bounds__(256) fast_strips_kernel(const uint8_t* __restrict__ pyr, size_t frame_stride,
@@ -28,13 +27,12 @@ __global__ void __launch_bounds__(256) fast_strips_kernel(const uint8_t* __restr
     uint8_t* tile = smem;
     uint8_t* sc = tile + (size_t)rows_cap * fs::kPitch;
     uint16_t* list = reinterpret_cast<uint16_t*>(sc + (size_t)rows_cap * fs::kPitch);
-    uint16_t* words = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(list) + (((size_t)list_cap * 2 + 15) & ~(size_t)15));
-    int* cnt = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(words) + (((size_t)rows_cap * (fs::kPitch / 4) * 2 + 15) & ~(size_t)15));
+    int* cnt = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(list) + (((size_t)list_cap * 2 + 15) & ~(size_t)15));
     int* misc = cnt + fs::kCntInts;
     const StripInfo si = strips[blockIdx.x];
     const LevelGeom lg = levels[si.level];
     const int frame = blockIdx.y;
-    fs::run(pyr + (size_t)frame * frame_stride + lg.off, lg.pitch, si, cells, lg.min_bx, lg.min_by, ini_th, min_th, tile, sc, list, words, cnt,
+    fs::run(pyr + (size_t)frame * frame_stride + lg.off, lg.pitch, si, cells, lg.min_bx, lg.min_by, ini_th, min_th, tile, sc, list, list_cap, cnt,
             misc, slots + (size_t)frame * n_cells * kCellCap, counts + (size_t)frame * n_cells, overflow);
 }
 
@@ -53,13 +51,13 @@ void fast_strips_host(const uint8_t* level_img, int pitch, const LevelGeom& lg, 
                       const std::vector<StripInfo>& strips, int rows_cap, int list_cap, int ini_th, int min_th, uint32_t* slots,
                       int* counts, int* overflow) {
     std::vector<uint32_t> tile((size_t)rows_cap * fs::kPitch / 4 + 4), sc((size_t)rows_cap * fs::kPitch / 4 + 4);
-    std::vector<uint16_t> list((size_t)list_cap + 4), words((size_t)rows_cap * (fs::kPitch / 4) + 4);
+    std::vector<uint16_t> list((size_t)list_cap + 4);
     std::vector<int> cnt(fs::kCntInts), misc(fs::kMiscInts);
     for (const StripInfo& si : strips) {
         if (si.level != cells[lg.cell_base].level) continue;
         // stale contents on purpose: the device tile is not cleared between CTAs either
         fs::run(level_img, pitch, si, cells.data(), lg.min_bx, lg.min_by, ini_th, min_th, reinterpret_cast<uint8_t*>(tile.data()),
-                reinterpret_cast<uint8_t*>(sc.data()), list.data(), words.data(), cnt.data(), misc.data(), slots, counts, overflow);
+                reinterpret_cast<uint8_t*>(sc.data()), list.data(), list_cap, cnt.data(), misc.data(), slots, counts, overflow);
     }
 }
 

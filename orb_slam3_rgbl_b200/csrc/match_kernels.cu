@@ -25,6 +25,8 @@ constexpr int kGridCells = kGridCols * kGridRows;
 constexpr int kThHigh = 100;          // ORBmatcher::TH_HIGH
 constexpr int kHistoLength = 30;      // ORBmatcher::HISTO_LENGTH
 constexpr uint32_t kPosMask = (1u << 20) - 1u;
+constexpr int kListUnsorted = 1 << 30;        // flag in list_n[q]: the list is in scan order, not ascending by key (more than 32 candidates)
+constexpr int kListCountMask = kListUnsorted - 1;
 
 // ---- grid --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int kp_stride, int* __restrict__ cell_start /*kGridCells+1*/,
@@ -185,6 +187,22 @@ __device__ __forceinline__ int warp_collect(const FrameDev& f, const int* __rest
     return count;
 }
 
+// The resolution reads a query's candidates best first (ascending key = distance, then scan position): called by the whole warp after
+// its list is complete, sorts lists of <= 32 keys in place by ranking (keys of one list are unique) and returns the value for list_n[q].
+__device__ __forceinline__ int warp_finish_list(uint32_t* __restrict__ list, int count, int list_cap) {
+    const int n = min(count, list_cap);
+    if (n <= 1) return n;
+    if (n > 32) return n | kListUnsorted;
+    const int lane = threadIdx.x & 31;
+    __syncwarp();                                       // the list was written by other lanes of this warp
+    const uint32_t k = lane < n ? list[lane] : 0xffffffffu;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (__shfl_sync(0xffffffffu, k, j) < k) ? 1 : 0;
+    __syncwarp();
+    if (lane < n) list[rank] = k;
+    return n;
+}
+
 // ---- SearchByProjection(CurrentFrame, LastFrame): candidate phase --------------------------------
 __global__ void __launch_bounds__(256) search_last_collect_kernel(FrameDev f, const int* __restrict__ cell_start,
                                                                   const int* __restrict__ csr_idx, LastFrameDev lf,
@@ -229,8 +247,9 @@ __global__ void __launch_bounds__(256) search_last_collect_kernel(FrameDev f, co
             }
         }
     }
+    const int ln = warp_finish_list(lists + (size_t)q * list_cap, count, list_cap);
     if (lane == 0) {
-        list_n[q] = min(count, list_cap);
+        list_n[q] = ln;
         if (count > list_cap) atomicExch(overflow, 3);
     }
 }
@@ -266,8 +285,9 @@ __global__ void __launch_bounds__(256) search_local_collect_kernel(FrameDev f, c
                                  });
         }
     }
+    const int ln = warp_finish_list(lists + (size_t)q * list_cap, count, list_cap);
     if (lane == 0) {
-        list_n[q] = min(count, list_cap);
+        list_n[q] = ln;
         if (count > list_cap) atomicExch(overflow, 3);
     }
 }
@@ -284,6 +304,17 @@ struct ChainEdgesDev {
     const rgbl_keypoint* kps; const float* uright; const float* last_xw;
     float* exw; float* eobs; float* einfo; uint8_t* est; int* eidx; int* n_edges;      // n_edges == nullptr: disabled
 };
+// TrackLocalMap form of that tail (local search of the chain): the edge list of the SECOND PoseOptimization = (inliers of the first search)
+// + (local matches) in keypoint order (src/Optimizer.cc:857-990), and the hand-over of the last frame's points into the local map ring
+// (MapPoint::UpdateNormalAndDepth with one observation, src/MapPoint.cc:437-490; ring slot = frames inserted so far mod K).  The edges
+// take local points from the query copy tlm_prepare made (lq_xw), so overwriting a ring slot here cannot disturb them.
+struct ChainTlmDev {
+    const int* match_last;           // nullptr: disabled.  Feature -> point of the last frame (outliers of the first optimisation cleared)
+    const float* lq_xw;              // world coordinates of the compacted local queries
+    LocalRingDev ring;
+    int* n_local_matches;
+    int n_last_cap; const uint8_t* last_valid; const int* last_octave; const uint8_t* last_desc; const float* last_pose;
+};
 
 __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const int* __restrict__ n_q_dev, FrameDev f,
                                                        const int* __restrict__ csr_idx,
@@ -296,7 +327,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
                                                        int* __restrict__ minq, int* __restrict__ choice,
                                                        uint8_t* __restrict__ resolved, int* __restrict__ match,
                                                        int* __restrict__ n_matches, int* __restrict__ rounds_out, int dyn_bytes,
-                                                       ChainEdgesDev ce) {
+                                                       ChainEdgesDev ce, ChainTlmDev tl) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int hist[kHistoLength];
     __shared__ int keep_bin[3];
@@ -324,7 +355,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
     const int per = (n_q + 1023) >> 10;
     const int qb = min(n_q, tid * per), qe = min(n_q, qb + per);
     int mine = 0;
-    for (int q = qb; q < qe; ++q) mine += list_n[q];
+    for (int q = qb; q < qe; ++q) mine += list_n[q] & kListCountMask;
     int incl = mine;
     {
         const int lane = tid & 31, warp = tid >> 5;
@@ -344,7 +375,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
     }
     RQ(1);
     const int E = s_total;
-    const size_t need = (size_t)12 * n_f + (size_t)4 * (n_q + 1) + (size_t)8 * (E + 4) + (size_t)12 * n_q + (size_t)n_f + (size_t)2 * n_q + 64;
+    const size_t need = (size_t)12 * n_f + (size_t)4 * (n_q + 1) + (size_t)12 * (E + 4) + (size_t)12 * n_q + (size_t)n_f + (size_t)2 * n_q + 64;
     const bool on_chip = n_f <= 65535 && need <= (size_t)dyn_bytes;
     const bool orient = mode != 1 && check_orientation;
     int rounds = 0, nm_local = 0;          // nm_local: accepted minus rotation-rejected matches of this thread
@@ -359,20 +390,21 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         int* s_off = s_match + n_f;
         int* s_choice = s_off + n_q + 1;
         int* s_list = s_choice + n_q;                    // two compact lists of waiting queries
-        uint8_t* s_state = reinterpret_cast<uint8_t*>(s_list + 2 * (size_t)n_q);
-        uint8_t* s_res = s_state + n_f;    // bit 0: resolved, bit 1: the query's point has observations
+        int* s_entq = s_list + 2 * (size_t)n_q;          // owning query of every entry (the proposal phase runs one thread per ENTRY)
+        uint8_t* s_state = reinterpret_cast<uint8_t*>(s_entq + E + 4);
+        uint8_t* s_res = s_state + n_f;    // bit 0: resolved, bit 1: the query's point has observations, bit 2: list not sorted by key
         uint8_t* s_bin = s_res + n_q;
         ch = s_choice; bins = s_bin; mt = s_match;
         {
             int o = incl - mine;
-            for (int q = qb; q < qe; ++q) { s_off[q] = o; o += list_n[q]; }
+            for (int q = qb; q < qe; ++q) { s_off[q] = o; o += list_n[q] & kListCountMask; }
             if (tid == 1023) s_off[n_q] = E;
         }
         for (int i = tid; i < n_f; i += 1024) { s_state[i] = state[i]; s_match[i] = -1; }
         if (tid < 4) s_ent[E + tid] = 0xffffffff00000000ull;     // padding: worst key, feature 0
         __syncthreads();
         for (int q = tid; q < n_q; q += 1024) {
-            s_res[q] = (uint8_t)((s_off[q + 1] == s_off[q] ? 1 : 0) | (obs_pos[q] ? 2 : 0));
+            s_res[q] = (uint8_t)((s_off[q + 1] == s_off[q] ? 1 : 0) | (obs_pos[q] ? 2 : 0) | ((list_n[q] & kListUnsorted) ? 4 : 0));
             s_choice[q] = -1;
         }
         // one thread per ENTRY (a query's list may hold dozens of candidates: a per-query loop would serialise its chains of
@@ -415,6 +447,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
                     bin = (unsigned)b & 0xffu;
                 }
                 s_ent[en] = ((unsigned long long)kk[u] << 32) | (bin << 24) | (occ[u] << 16) | (unsigned)ftt[u];
+                s_entq[en] = qq[u];
             }
         }
         __syncthreads();
@@ -436,41 +469,38 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         };
         // phase 2: best (and second best) available candidate; final when no lower-index waiting query can still interfere.
         // Returns true while the query has to wait for another round.
+        // A query's decision depends on its best and second-best AVAILABLE candidates only (the set of available candidates can only
+        // shrink until its turn, so if no lower-index waiting query proposes at those two they are still its best two then): with the
+        // list sorted by key the scan stops at the second available entry - typically after two or three of them; lists of more than 32
+        // candidates (left in scan order) are read to the end.  tests/test_resolution_model.py checks this rule against the sequential loops.
         auto decide = [&](int q, const int* mq) -> bool {
             const uint8_t flags = s_res[q];
             uint32_t best = 0xffffffffu, best2 = 0xffffffffu;
-            int lvl = -1, lvl2 = -1, fb = -1, bb = 0;
-            bool depends_ok = true;
+            int lvl = -1, lvl2 = -1, fb = -1, bb = 0, fb2 = -1;
             const int e = s_off[q + 1];
-            for (int k = s_off[q]; k < e; k += kChunk) {
-                unsigned long long en[kChunk]; uint8_t st[kChunk]; int mv[kChunk];
-#pragma unroll
-                for (int u = 0; u < kChunk; ++u) en[u] = (k + u < e) ? s_ent[k + u] : 0xffffffff00000000ull;
-#pragma unroll
-                for (int u = 0; u < kChunk; ++u) st[u] = (k + u < e) ? s_state[(unsigned)en[u] & 0xffffu] : (uint8_t)1;
-                if (mode >= 1) {
-#pragma unroll
-                    for (int u = 0; u < kChunk; ++u) mv[u] = (st[u] != 1) ? mq[(unsigned)en[u] & 0xffffu] : q;
+            if (!(flags & 4)) {
+                for (int k = s_off[q]; k < e; ++k) {
+                    const unsigned long long en = s_ent[k];
+                    const int ft = (int)((unsigned)en & 0xffffu);
+                    if (s_state[ft] == 1) continue;
+                    if (fb < 0) { best = (uint32_t)(en >> 32); fb = ft; bb = (int)(((unsigned)en >> 24) & 0xffu); lvl = (int)(((unsigned)en >> 16) & 0xffu); if (mode == 0) break; }
+                    else { best2 = (uint32_t)(en >> 32); fb2 = ft; lvl2 = (int)(((unsigned)en >> 16) & 0xffu); break; }
                 }
-#pragma unroll
-                for (int u = 0; u < kChunk; ++u) {
-                    if (st[u] == 1) continue;
-                    const uint32_t key = (uint32_t)(en[u] >> 32);
-                    const int ft = (int)((unsigned)en[u] & 0xffffu);
-                    if (mode >= 1 && mv[u] != q) depends_ok = false;
-                    const int eb = (int)(((unsigned)en[u] >> 24) & 0xffu);
-                    if (mode == 0) {
-                        if (key < best) { best = key; fb = ft; bb = eb; }
-                    } else {
-                        const int oc = (int)(((unsigned)en[u] >> 16) & 0xffu);
-                        if (key < best) { best2 = best; lvl2 = lvl; best = key; lvl = oc; fb = ft; bb = eb; }
-                        else if (key < best2) { best2 = key; lvl2 = oc; }
-                    }
+            } else {
+                for (int k = s_off[q]; k < e; ++k) {
+                    const unsigned long long en = s_ent[k];
+                    const int ft = (int)((unsigned)en & 0xffffu);
+                    if (s_state[ft] == 1) continue;
+                    const uint32_t key = (uint32_t)(en >> 32);
+                    const int oc = (int)(((unsigned)en >> 16) & 0xffu);
+                    if (key < best) { best2 = best; lvl2 = lvl; fb2 = fb; best = key; lvl = oc; fb = ft; bb = (int)(((unsigned)en >> 24) & 0xffu); }
+                    else if (key < best2) { best2 = key; lvl2 = oc; fb2 = ft; }
                 }
+                if (mode == 0) { best2 = 0xffffffffu; fb2 = -1; }
             }
+            const bool depends_ok = fb >= 0 && mq[fb] == q && (fb2 < 0 || mq[fb2] == q);
             if (best == 0xffffffffu) { s_res[q] = flags | 1; return false; }
-            const bool final_ok = (mode == 0) ? (mq[fb] == q) : depends_ok;
-            if (!final_ok) return true;
+            if (!depends_ok) return true;
             s_res[q] = flags | 1;
             const int bd = (int)(best >> 20);
             bool accept = bd <= th_accept;
@@ -517,17 +547,25 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             __syncthreads();
             n_act = s_cnt[0];
         }
-        // One round by the first T threads of the CTA (T a multiple of 32); `sync` is the barrier of exactly those threads.
-        auto round = [&](const int T, auto sync) {
+        // Block rounds.  Proposal phase: one thread per ENTRY (a per-query loop makes every warp wait for its longest list; measured, the
+        // rounds cost ~4 k cycles each that way) - an entry of a waiting query whose feature is still available proposes its query.
+        // Decision phase: over a COMPACT list of the waiting queries (packed, round r touches ceil(waiting / 32) warps); the proposal
+        // table is double buffered, the idle copy is cleared while the live one is read.  <= 32 waiting queries: warp 0 finishes alone.
+        while (n_act > 32) {
             int* mq = s_minq + (size_t)cur * n_f;
             int* mq_next = s_minq + (size_t)(cur ^ 1) * n_f;
             const int* lst = s_list + (size_t)cur * n_q;
             int* lst_next = s_list + (size_t)(cur ^ 1) * n_q;
             if (tid == 0) s_cnt[cur ^ 1] = 0;
-            for (int i = tid; i < n_f; i += T) mq_next[i] = 0x7fffffff;
-            for (int i = tid; i < n_act; i += T) propose(lst[i], mq);
-            sync();
-            for (int i0 = 0; i0 < n_act; i0 += T) {
+            for (int i = tid; i < n_f; i += 1024) mq_next[i] = 0x7fffffff;
+#pragma unroll 4
+            for (int en = tid; en < E; en += 1024) {
+                const int q = s_entq[en];
+                const int ft = (int)((unsigned)s_ent[en] & 0xffffu);
+                if (!(s_res[q] & 1) && s_state[ft] != 1) atomicMin(&mq[ft], q);
+            }
+            __syncthreads();
+            for (int i0 = 0; i0 < n_act; i0 += 1024) {
                 const int i = i0 + tid;
                 const int q = i < n_act ? lst[i] : -1;
                 const bool w = q >= 0 && decide(q, mq);
@@ -539,15 +577,9 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             }
             ++rounds;
             cur ^= 1;
-            sync();
+            __syncthreads();
             n_act = s_cnt[cur];
-        };
-        // After the first round or two only a few hundred queries still wait (those with contested candidates), so the rounds
-        // continue on a TEAM of kTeam threads with a named barrier of that size: a barrier over 8 warps costs a fraction of one
-        // over 32, and the other 24 warps just park at the CTA barrier below.  <= 32 waiting queries: warp 0 alone, as before.
-        constexpr int kTeam = 256;
-        while (n_act > kTeam) round(1024, [] { __syncthreads(); });
-        if (tid < kTeam) while (n_act > 32) round(kTeam, [] { team_sync(kTeam); });
+        }
         if (n_act > 0 && tid < 32) {
             int* mq = s_minq + (size_t)cur * n_f;     // a fully cleared table; the tail clears only what it touches
             const int q0 = tid < n_act ? s_list[(size_t)cur * n_q + tid] : -1;
@@ -575,7 +607,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         __syncthreads();
     } else {
     for (int i = tid; i < n_f; i += 1024) match[i] = -1;
-    for (int q = tid; q < n_q; q += 1024) { choice[q] = -1; resolved[q] = (list_n[q] == 0); }
+    for (int q = tid; q < n_q; q += 1024) { choice[q] = -1; resolved[q] = ((list_n[q] & kListCountMask) == 0); }
     __syncthreads();
     for (;;) {
         bool any_unresolved = false;
@@ -584,7 +616,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         for (int q = tid; q < n_q; q += 1024) {
             if (resolved[q]) continue;
             const uint32_t* l = lists + (size_t)q * list_cap;
-            const int n = list_n[q];
+            const int n = list_n[q] & kListCountMask;
             for (int k = 0; k < n; ++k) {
                 const int ft = csr_idx[l[k] & kPosMask];
                 if (state[ft] != 1) atomicMin(&minq[ft], q);
@@ -594,7 +626,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         for (int q = tid; q < n_q; q += 1024) {
             if (resolved[q]) continue;
             const uint32_t* l = lists + (size_t)q * list_cap;
-            const int n = list_n[q];
+            const int n = list_n[q] & kListCountMask;
             uint32_t best = 0xffffffffu, best2 = 0xffffffffu;     // smallest / second smallest (dist, order) keys
             int lvl = -1, lvl2 = -1;
             bool depends_ok = true;
@@ -703,22 +735,74 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
     }
     if (ce.n_edges) {                     // ordered compaction of the matched features into edges
         // Two chunks of 1024 features per trip (a KITTI frame is one trip): everything an edge needs is loaded for both chunks before the
-        // positions are known, so the trip pays ONE round of global latency; the positions come from warp ballots and a 64-entry scan.
+        // positions are known, so the trip pays ONE round of global latency (two in the TrackLocalMap form, whose first-search matches
+        // live in global memory); the positions come from warp ballots and a 64-entry scan.
         __shared__ int s_wcnt[2][32];
+        __shared__ int s_nloc;
+        const bool tlm = tl.match_last != nullptr;
+        if (tid == 0) s_nloc = 0;
         __syncthreads();
         const int lane = tid & 31, warp = tid >> 5;
-        int run = 0;                      // edges before this trip (same value in every thread)
-        for (int b = 0; b < n_f; b += 2048) {
-            int m[2]; float kx[2], ky[2], ur[2], xw[2][3]; int oc[2]; unsigned bal[2];
+        if (tlm) {
+            // the last frame's points become local map points; every value is loaded before the first store of the loop body
+            const int ring_count = *tl.ring.count;
+            float Ow[3];
+            {
+                float T[7], qinv[4];
 #pragma unroll
-            for (int c = 0; c < 2; ++c) { const int i = b + c * 1024 + tid; m[c] = (i < n_f) ? mt[i] : -1; }
+                for (int k = 0; k < 7; ++k) T[k] = tl.last_pose[k];
+                se3f_inverse(T, qinv, Ow);                 // KeyFrame::GetCameraCenter of the frame the points were created from
+            }
+            const size_t base = (size_t)(ring_count % tl.ring.K) * tl.ring.cap;
+            for (int j = tid; j < tl.ring.cap; j += 1024) {
+                uint8_t v = 0;
+                if (j < tl.n_last_cap && tl.last_valid[j]) {
+                    const float P[3] = {ce.last_xw[3 * j], ce.last_xw[3 * j + 1], ce.last_xw[3 * j + 2]};
+                    const int loct = tl.last_octave[j];
+                    const uint4 d0 = reinterpret_cast<const uint4*>(tl.last_desc + (size_t)j * 32)[0];
+                    const uint4 d1 = reinterpret_cast<const uint4*>(tl.last_desc + (size_t)j * 32)[1];
+                    const float PC[3] = {__fsub_rn(P[0], Ow[0]), __fsub_rn(P[1], Ow[1]), __fsub_rn(P[2], Ow[2])};
+                    const float dist = sqrtf(eig_sum3(__fmul_rn(PC[0], PC[0]), __fmul_rn(PC[1], PC[1]), __fmul_rn(PC[2], PC[2])));
+                    const size_t p = base + j;
+                    tl.ring.xw[3 * p] = P[0]; tl.ring.xw[3 * p + 1] = P[1]; tl.ring.xw[3 * p + 2] = P[2];
+                    tl.ring.normal[3 * p] = __fdiv_rn(PC[0], dist); tl.ring.normal[3 * p + 1] = __fdiv_rn(PC[1], dist); tl.ring.normal[3 * p + 2] = __fdiv_rn(PC[2], dist);
+                    const float mx = __fmul_rn(dist, f.scale[loct]);
+                    tl.ring.mf_max[p] = mx;
+                    tl.ring.mf_min[p] = __fdiv_rn(mx, f.scale[f.n_levels - 1]);
+                    uint4* dd = reinterpret_cast<uint4*>(tl.ring.desc + p * 32);
+                    dd[0] = d0; dd[1] = d1;
+                    v = 1;
+                }
+                tl.ring.valid[base + j] = v;
+            }
+            if (tid == 0) *tl.ring.count = ring_count + 1;
+        }
+        int run = 0, nloc = 0;            // edges before this trip (same value in every thread); local matches of this thread
+        for (int b = 0; b < n_f; b += 2048) {
+            int m[2]; float kx[2], ky[2], ur[2], xw[2][3]; int oc[2]; unsigned bal[2]; const float* src[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int i = b + c * 1024 + tid;
+                m[c] = -1; src[c] = ce.last_xw;
+                if (i < n_f) {
+                    if (tlm) {
+                        const int ma = tl.match_last[i];
+                        const int mb = ma < 0 ? mt[i] : -1;
+                        if (mb >= 0) ++nloc;
+                        m[c] = ma >= 0 ? ma : mb;
+                        if (ma < 0) src[c] = tl.lq_xw;
+                    } else {
+                        m[c] = mt[i];
+                    }
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const int i = b + c * 1024 + tid;
                 kx[c] = ky[c] = ur[c] = xw[c][0] = xw[c][1] = xw[c][2] = 0.f; oc[c] = 0;
                 if (m[c] >= 0) {
                     kx[c] = ce.kps[i].x; ky[c] = ce.kps[i].y; oc[c] = ce.kps[i].octave; ur[c] = ce.uright[i];
-                    xw[c][0] = ce.last_xw[3 * m[c]]; xw[c][1] = ce.last_xw[3 * m[c] + 1]; xw[c][2] = ce.last_xw[3 * m[c] + 2];
+                    xw[c][0] = src[c][3 * m[c]]; xw[c][1] = src[c][3 * m[c] + 1]; xw[c][2] = src[c][3 * m[c] + 2];
                 }
             }
 #pragma unroll
@@ -752,7 +836,13 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             run += s_total;
             __syncthreads();              // s_wcnt / s_total are rewritten by the next trip
         }
-        if (tid == 0) *ce.n_edges = run;
+        if (tlm) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nloc += __shfl_down_sync(0xffffffffu, nloc, o);
+            if (lane == 0 && nloc) atomicAdd(&s_nloc, nloc);
+            __syncthreads();
+        }
+        if (tid == 0) { *ce.n_edges = run; if (tlm) *tl.n_local_matches = s_nloc; }
     }
     {
 #pragma unroll
@@ -878,7 +968,8 @@ __global__ void __launch_bounds__(256) bow_collect_kernel(int n_q, const int* __
         if (keep) { const int o = count + __popc(m & ((1u << lane) - 1u)); if (o < list_cap) list[o] = key; }
         count += __popc(m);
     }
-    if (lane == 0) { list_n[q] = min(count, list_cap); if (count > list_cap) atomicExch(overflow, 3); }
+    const int ln = warp_finish_list(lists + (size_t)q * list_cap, count, list_cap);
+    if (lane == 0) { list_n[q] = ln; if (count > list_cap) atomicExch(overflow, 3); }
 }
 
 // ---- SearchByProjection(CurrentFrame, KeyFrame, sAlreadyFound, th, ORBdist): candidate phase -------------------------
@@ -917,7 +1008,8 @@ __global__ void __launch_bounds__(256) search_reloc_collect_kernel(FrameDev f, c
             }
         }
     }
-    if (lane == 0) { list_n[q] = min(count, list_cap); if (count > list_cap) atomicExch(overflow, 3); }
+    const int ln = warp_finish_list(lists + (size_t)q * list_cap, count, list_cap);
+    if (lane == 0) { list_n[q] = ln; if (count > list_cap) atomicExch(overflow, 3); }
 }
 
 // ---- resident tracking chain (TrackWithMotionModel-style glue between the reference functions) ----------------
@@ -965,15 +1057,21 @@ void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_star
     search_last_collect_kernel<<<(lf.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lf, prm, s.lists, s.list_cap, s.list_n, s.overflow);
     resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, lf.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lf.obs_pos, lf.angle, 0.f,
                                        prm.check_orientation, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(),
-                                       edges ? ChainEdgesDev{f.keys, f.uright, lf.xw, edges->exw, edges->eobs, edges->einfo, edges->est, edges->eidx, edges->n_edges} : ChainEdgesDev{});
+                                       edges ? ChainEdgesDev{f.keys, f.uright, lf.xw, edges->exw, edges->eobs, edges->einfo, edges->est, edges->eidx, edges->n_edges} : ChainEdgesDev{}, ChainTlmDev{});
 }
 
 void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LocalPointsDev& lp,
-                         const SearchLocalParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches) {
+                         const SearchLocalParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches, const ChainTlmTail* tail) {
     if (lp.n <= 0) return;
     search_local_collect_kernel<<<(lp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
+    ChainEdgesDev ce{};
+    ChainTlmDev tl{};
+    if (tail) {
+        ce = ChainEdgesDev{f.keys, f.uright, tail->last_xw, tail->edges.exw, tail->edges.eobs, tail->edges.einfo, tail->edges.est, tail->edges.eidx, tail->edges.n_edges};
+        tl = ChainTlmDev{tail->match_last, tail->lq_xw, tail->ring, tail->n_local_matches, tail->n_last_cap, tail->last_valid, tail->last_octave, tail->last_desc, tail->last_pose};
+    }
     resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(1, lp.n, lp.n_dev, f, csr_idx, s.lists, s.list_cap, s.list_n, lp.obs_pos, nullptr, prm.nn_ratio,
-                                       0, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{});
+                                       0, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ce, tl);
 }
 
 void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q_feat, const int* q_cbeg, const int* q_cend,
@@ -984,7 +1082,7 @@ void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q
     bow_collect_kernel<<<(n_q + 7) / 8, 256, 0, st>>>(n_q, q_feat, q_cbeg, q_cend, kf_desc, f_desc, f_node_feat, keep_max, s.lists, s.list_cap,
                                                     s.list_n, s.overflow);
     resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(2, n_q, nullptr, f, f_node_feat, s.lists, s.list_cap, s.list_n, obs_pos, q_angle, nn_ratio,
-                                       check_orientation, 50 /* TH_LOW */, f_angle, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{});
+                                       check_orientation, 50 /* TH_LOW */, f_angle, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{}, ChainTlmDev{});
 }
 
 void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const RelocPointsDev& rp,
@@ -992,7 +1090,7 @@ void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_sta
     if (rp.n <= 0) return;
     search_reloc_collect_kernel<<<(rp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, rp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
     resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, rp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, obs_pos, rp.angle, 0.f,
-                                       prm.check_orientation, prm.orb_dist, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{});
+                                       prm.check_orientation, prm.orb_dist, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{}, ChainTlmDev{});
 }
 
 void launch_fuse_search(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, int n, const uint8_t* valid, const float* xw,

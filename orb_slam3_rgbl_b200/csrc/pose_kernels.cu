@@ -265,10 +265,15 @@ struct ClusterXchg {
                 if (!done && ++spins > (1u << 24)) __trap();      // a lost exchange must fail loudly, not hang the device
             }
             if ((int)threadIdx.x < n_vals) {
-                double t = buf[b][0][threadIdx.x];
+                // pairwise tree in a fixed order (the same in every CTA): depth log2(kPoseCtas) dependent FP64 additions instead of kPoseCtas - 1
+                double t[kPoseCtas];
 #pragma unroll
-                for (int r = 1; r < kPoseCtas; ++r) t += buf[b][r][threadIdx.x];
-                out[threadIdx.x] = t;
+                for (int r = 0; r < kPoseCtas; ++r) t[r] = buf[b][r][threadIdx.x];
+#pragma unroll
+                for (int st = 1; st < kPoseCtas; st <<= 1)
+#pragma unroll
+                    for (int r = 0; r + st < kPoseCtas; r += 2 * st) t[r] += t[r + st];
+                out[threadIdx.x] = t[0];
             }
         }
         __syncthreads();
@@ -294,8 +299,14 @@ __device__ __forceinline__ void cluster_reduce(ClusterXchg& xc, double* v /* 32 
     __syncthreads();
     double s = 0;
     if (threadIdx.x < kAcc) {
+        double t[kPoseWarps];
 #pragma unroll
-        for (int w = 0; w < kPoseWarps; ++w) s += smem[w * kAcc + threadIdx.x];
+        for (int w = 0; w < kPoseWarps; ++w) t[w] = smem[w * kAcc + threadIdx.x];
+#pragma unroll
+        for (int st = 1; st < kPoseWarps; st <<= 1)
+#pragma unroll
+            for (int w = 0; w + st < kPoseWarps; w += 2 * st) t[w] += t[w + st];
+        s = t[0];
     }
     xc.sum(s, kAcc, out);
 }
@@ -539,10 +550,15 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
                     if (lane == 0) red[warp] = x;
                     __syncthreads();
                     double s = 0.0;
-                    if (warp == 0) {
-                        s = lane < kPoseWarps ? red[lane] : 0.0;
+                    if (warp == 0) {           // the few warp totals: a pairwise tree read by broadcast, not five more shuffle steps
+                        double t[kPoseWarps];
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+                        for (int w = 0; w < kPoseWarps; ++w) t[w] = red[w];
+#pragma unroll
+                        for (int st = 1; st < kPoseWarps; st <<= 1)
+#pragma unroll
+                            for (int w = 0; w + st < kPoseWarps; w += 2 * st) t[w] += t[w + st];
+                        s = t[0];
                     }
                     xc.sum(s, 1, s_tot);
                     if (tid == 0) {            // every CTA takes the decision from the same partials: identical everywhere

@@ -131,8 +131,10 @@ struct ChainEdgesOut { float* exw; float* eobs; float* einfo; uint8_t* est; int*
 void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LastFrameDev& lf,
                         const SearchLastParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches,
                         const ChainEdgesOut* edges = nullptr);
+struct LocalRingDev;
+struct ChainTlmTail;                 // below (chain_kernels.cu section): TrackLocalMap tail of the resolution kernel
 void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LocalPointsDev& lp,
-                         const SearchLocalParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches);
+                         const SearchLocalParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches, const ChainTlmTail* tail = nullptr);
 void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q_feat, const int* q_cbeg, const int* q_cend,
                        const uint8_t* kf_desc, const uint8_t* f_desc, const float* q_angle, const float* f_angle, const int* f_node_feat,
                        float nn_ratio, int keep_max, int check_orientation, const uint8_t* obs_pos, MatchScratch s, uint8_t* state, int* match,
@@ -158,15 +160,18 @@ struct LocalRingDev {                // local map of the chain: K frame slots x 
 struct LocalQueriesDev {             // the in-frustum local map points, compacted in ring order (= vpMapPoints of the local search)
     int cap; int* n;
     uint8_t* in_view; uint8_t* obs_pos; float *proj_x, *proj_y, *proj_xr, *depth; int* level; float* view_cos; uint8_t* desc; int* src;
-    float* xw;                       // world coordinates of the compacted points (read by tlm_edges instead of the ring)
+    float* xw;                       // world coordinates of the compacted points (read by the edge-list tail instead of the ring)
 };
 void launch_tlm_prepare(cudaStream_t st, const FrameDev& f, const float* pose, const LocalRingDev& ring, float cos_limit, const int* n_edges,
                         const int* e_idx, const uint8_t* e_outlier, uint8_t* state, int* match_last, const LocalQueriesDev& lq, int* lookback, int* fail);
-void launch_tlm_edges(cudaStream_t st, const FrameDev& f, const int* match_last, const float* last_xw, const int* match_local, const float* lq_xw,
-                      const LocalRingDev& ring, const ChainEdgesOut& eo, int* n_local_matches, int n_last_cap, const uint8_t* last_valid,
-                      const int* last_octave, const uint8_t* last_desc, const float* last_pose, int* lookback, int* fail);
-// both kernels compact over several CTAs in one launch; `lookback` = tlm_lookback_ints() ZERO-INITIALISED ints (the kernels leave them zero),
-// `fail` = a device flag set to 9 if a CTA ever waited in vain; *n_local_matches must be 0 at the launch of tlm_edges (it accumulates)
+// TrackLocalMap tail of the local search's resolution kernel (match_kernels.cu): the edge list of the second PoseOptimization from (inliers
+// of the first search) + (local matches), and the hand-over of the last frame's points into the ring.  *n_local_matches is written.
+struct ChainTlmTail {
+    const int* match_last; const float* last_xw; const float* lq_xw; LocalRingDev ring; ChainEdgesOut edges; int* n_local_matches;
+    int n_last_cap; const uint8_t* last_valid; const int* last_octave; const uint8_t* last_desc; const float* last_pose;
+};
+// tlm_prepare compacts over several CTAs in one launch; `lookback` = tlm_lookback_ints() ZERO-INITIALISED ints (the kernel leaves them zero),
+// `fail` = a device flag set to 9 if a CTA ever waited in vain
 int tlm_lookback_ints();
 
 // stereo_kernels.cu --------------------------------------------------------------------------------

@@ -258,6 +258,22 @@ def test_fast_strips_on_flat_and_saturated_images():
         assert got.shape == ref.shape and (got == ref).all(), l
 
 
+def test_fast_strips_when_every_pixel_passes_the_high_speed_test():
+    """Vertical stripes of period 6 (plus noise): p[-3] and p[+3] differ from every pixel by ~200, so the high-speed test passes
+    everywhere and the list of listed pixels fills its buffer - the strip kernel then cannot put its second list (score-carrying
+    words) into the same buffer and walks all words in the NMS phase instead."""
+    rng = np.random.default_rng(77)
+    yy, xx = np.mgrid[0:260, 0:420]
+    img = (((xx % 6) < 3) * 200 + 20 + rng.integers(0, 30, xx.shape)).astype(np.uint8)
+    ex = oracle.Extractor(1000); ex(img)
+    total = 0
+    for l in range(8):
+        got, ref = _strip_fast(ex.level_image(l), 420, 260, l, nfeatures=1000), ex.level_candidates(l)
+        assert got.shape == ref.shape and (got == ref).all(), l
+        total += len(ref)
+    assert total > 100
+
+
 # ---- block-parallel std::sort (quadtree_block.cuh: block_std_sort), executed on the host -----------------------------------
 def _sort_perm(su, mode):
     perm = np.empty(len(su), np.int32)

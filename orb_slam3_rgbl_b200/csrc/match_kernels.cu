@@ -21,10 +21,27 @@
 
 namespace rgbl {
 
+bool& chain_launch_pdl() { static thread_local bool on = false; return on; }
+
 constexpr int kGridCells = kGridCols * kGridRows;
 constexpr int kThHigh = 100;          // ORBmatcher::TH_HIGH
 constexpr int kHistoLength = 30;      // ORBmatcher::HISTO_LENGTH
 constexpr uint32_t kPosMask = (1u << 20) - 1u;
+// A candidate entry, as the collect kernels write it and the resolution reads it: hi word = key (distance << 20 | scan position: ascending key =
+// the reference's preference order incl. ties), lo word = rotation bin << 24 | octave << 20 | frame feature (< 2^20).
+typedef unsigned long long MatchEntry;
+__device__ __forceinline__ MatchEntry ent_make(uint32_t key, unsigned bin, unsigned oc, unsigned ft) { return ((MatchEntry)key << 32) | (bin << 24) | ((oc & 0xfu) << 20) | ft; }
+__device__ __forceinline__ uint32_t ent_key(MatchEntry e) { return (uint32_t)(e >> 32); }
+__device__ __forceinline__ int ent_ft(MatchEntry e) { return (int)((unsigned)e & 0xfffffu); }
+__device__ __forceinline__ int ent_oc(MatchEntry e) { return (int)(((unsigned)e >> 20) & 0xfu); }
+__device__ __forceinline__ int ent_bin(MatchEntry e) { return (int)((unsigned)e >> 24); }
+__device__ __forceinline__ unsigned rotation_bin(float q_angle, float f_angle) {          // src/ORBmatcher.cc:1820-1828 (rot, bin = round(rot * factor))
+    float rot = __fsub_rn(q_angle, f_angle);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int b = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+    if (b == 30) b = 0;
+    return (unsigned)b & 0xffu;
+}
 constexpr int kListUnsorted = 1 << 30;        // flag in list_n[q]: the list is in scan order, not ascending by key (more than 32 candidates)
 constexpr int kListCountMask = kListUnsorted - 1;
 
@@ -124,7 +141,8 @@ template <class Filter>
 __device__ __forceinline__ int warp_collect(const FrameDev& f, const int* __restrict__ cell_start,
                                             const int* __restrict__ csr_idx, const CellRange cr, float x, float y,
                                             float r, int min_level, int max_level, const uint4 d0, const uint4 d1,
-                                            int keep_max, uint32_t* __restrict__ list, int list_cap, Filter admit) {
+                                            int keep_max, MatchEntry* __restrict__ list, int list_cap, Filter admit,
+                                            bool want_bin = false, float q_angle = 0.f) {
     const int lane = threadIdx.x & 31;
     const bool check_levels = (min_level > 0) || (max_level >= 0);
     int count = 0;
@@ -157,7 +175,7 @@ __device__ __forceinline__ int warp_collect(const FrameDev& f, const int* __rest
             const int sb = __shfl_sync(0xffffffffu, seg_b, lo), sl = __shfl_sync(0xffffffffu, seg_len, lo), si = __shfl_sync(0xffffffffu, incl, lo);
             const int p = sb + (t - (si - sl));
             bool keep = false;
-            uint32_t key = 0;
+            MatchEntry key = 0;
             if (t0 + lane < total) {
                 const int idx = csr_idx[p];
                 const rgbl_keypoint kp = f.keys[idx];
@@ -173,7 +191,10 @@ __device__ __forceinline__ int warp_collect(const FrameDev& f, const int* __rest
                 if (ok) ok = admit(idx);
                 if (ok) {
                     const int d = hamming256(d0, d1, f.desc + (size_t)idx * 32);
-                    if (d <= keep_max) { keep = true; key = ((uint32_t)d << 20) | (uint32_t)p; }
+                    if (d <= keep_max) {
+                        keep = true;
+                        key = ent_make(((uint32_t)d << 20) | (uint32_t)p, want_bin ? rotation_bin(q_angle, kp.angle) : 0u, (unsigned)kp.octave, (unsigned)idx);
+                    }
                 }
             }
             const uint32_t m = __ballot_sync(0xffffffffu, keep);
@@ -189,13 +210,13 @@ __device__ __forceinline__ int warp_collect(const FrameDev& f, const int* __rest
 
 // The resolution reads a query's candidates best first (ascending key = distance, then scan position): called by the whole warp after
 // its list is complete, sorts lists of <= 32 keys in place by ranking (keys of one list are unique) and returns the value for list_n[q].
-__device__ __forceinline__ int warp_finish_list(uint32_t* __restrict__ list, int count, int list_cap) {
+__device__ __forceinline__ int warp_finish_list(MatchEntry* __restrict__ list, int count, int list_cap) {
     const int n = min(count, list_cap);
     if (n <= 1) return n;
     if (n > 32) return n | kListUnsorted;
     const int lane = threadIdx.x & 31;
     __syncwarp();                                       // the list was written by other lanes of this warp
-    const uint32_t k = lane < n ? list[lane] : 0xffffffffu;
+    const MatchEntry k = lane < n ? list[lane] : ~0ull;
     int rank = 0;
     for (int j = 0; j < n; ++j) rank += (__shfl_sync(0xffffffffu, k, j) < k) ? 1 : 0;
     __syncwarp();
@@ -206,9 +227,10 @@ __device__ __forceinline__ int warp_finish_list(uint32_t* __restrict__ list, int
 // ---- SearchByProjection(CurrentFrame, LastFrame): candidate phase --------------------------------
 __global__ void __launch_bounds__(256) search_last_collect_kernel(FrameDev f, const int* __restrict__ cell_start,
                                                                   const int* __restrict__ csr_idx, LastFrameDev lf,
-                                                                  SearchLastParams prm, uint32_t* __restrict__ lists,
+                                                                  SearchLastParams prm, MatchEntry* __restrict__ lists,
                                                                   int list_cap, int* __restrict__ list_n,
                                                                   int* __restrict__ overflow) {
+    pdl_wait(); pdl_trigger();
     const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= lf.n) return;
     int count = 0;
@@ -243,7 +265,7 @@ __global__ void __launch_bounds__(256) search_last_collect_kernel(FrameDev f, co
                                          const float urt = uright[idx];
                                          if (urt > 0.f) { if (fabsf(__fsub_rn(ur, urt)) > radius) return false; }
                                          return true;
-                                     });
+                                     }, prm.check_orientation != 0, lf.angle[q]);
             }
         }
     }
@@ -255,11 +277,48 @@ __global__ void __launch_bounds__(256) search_last_collect_kernel(FrameDev f, co
 }
 
 // ---- SearchByProjection(F, vpMapPoints): candidate phase ---------------------------------------------
+// Resident chain only (ho.ring.valid != nullptr): the first CTAs of the grid also hand the LAST frame's points over to the local map ring
+// (MapPoint::UpdateNormalAndDepth with one observation, src/MapPoint.cc:437-490; ring slot = frames inserted so far mod K) - a streaming
+// copy of ~100 bytes per point that a single CTA (the resolution kernel's tail, where it used to be) pays 4 us for.  Nothing in this
+// kernel or in the resolution reads the ring (the edges take local points from the query copy), the frame counter is advanced afterwards.
+struct RingHandOverDev {
+    LocalRingDev ring; const float* last_xw; int n_last_cap; const uint8_t* last_valid; const int* last_octave; const uint8_t* last_desc; const float* last_pose;
+};
+
 __global__ void __launch_bounds__(256) search_local_collect_kernel(FrameDev f, const int* __restrict__ cell_start,
                                                                    const int* __restrict__ csr_idx, LocalPointsDev lp,
-                                                                   SearchLocalParams prm, uint32_t* __restrict__ lists,
+                                                                   SearchLocalParams prm, MatchEntry* __restrict__ lists,
                                                                    int list_cap, int* __restrict__ list_n,
-                                                                   int* __restrict__ overflow) {
+                                                                   int* __restrict__ overflow, RingHandOverDev ho) {
+    pdl_wait(); pdl_trigger();
+    if (ho.ring.valid) {
+        const int j = blockIdx.x * 256 + threadIdx.x;
+        if (j < ho.ring.cap) {
+            const size_t p = (size_t)(*ho.ring.count % ho.ring.K) * ho.ring.cap + j;
+            uint8_t v = 0;
+            if (j < ho.n_last_cap && ho.last_valid[j]) {
+                const float P[3] = {ho.last_xw[3 * j], ho.last_xw[3 * j + 1], ho.last_xw[3 * j + 2]};
+                const int loct = ho.last_octave[j];
+                const uint4 d0 = reinterpret_cast<const uint4*>(ho.last_desc + (size_t)j * 32)[0];
+                const uint4 d1 = reinterpret_cast<const uint4*>(ho.last_desc + (size_t)j * 32)[1];
+                float T[7], qinv[4], Ow[3];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) T[k] = ho.last_pose[k];
+                se3f_inverse(T, qinv, Ow);                 // KeyFrame::GetCameraCenter of the frame the points were created from
+                const float PC[3] = {__fsub_rn(P[0], Ow[0]), __fsub_rn(P[1], Ow[1]), __fsub_rn(P[2], Ow[2])};
+                const float dist = sqrtf(eig_sum3(__fmul_rn(PC[0], PC[0]), __fmul_rn(PC[1], PC[1]), __fmul_rn(PC[2], PC[2])));
+                ho.ring.xw[3 * p] = P[0]; ho.ring.xw[3 * p + 1] = P[1]; ho.ring.xw[3 * p + 2] = P[2];
+                ho.ring.normal[3 * p] = __fdiv_rn(PC[0], dist); ho.ring.normal[3 * p + 1] = __fdiv_rn(PC[1], dist); ho.ring.normal[3 * p + 2] = __fdiv_rn(PC[2], dist);
+                const float mx = __fmul_rn(dist, f.scale[loct]);
+                ho.ring.mf_max[p] = mx;
+                ho.ring.mf_min[p] = __fdiv_rn(mx, f.scale[f.n_levels - 1]);
+                uint4* dd = reinterpret_cast<uint4*>(ho.ring.desc + p * 32);
+                dd[0] = d0; dd[1] = d1;
+                v = 1;
+            }
+            ho.ring.valid[p] = v;
+        }
+    }
     const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= (lp.n_dev ? min(*lp.n_dev, lp.n) : lp.n)) return;
     int count = 0;
@@ -305,20 +364,17 @@ struct ChainEdgesDev {
     float* exw; float* eobs; float* einfo; uint8_t* est; int* eidx; int* n_edges;      // n_edges == nullptr: disabled
 };
 // TrackLocalMap form of that tail (local search of the chain): the edge list of the SECOND PoseOptimization = (inliers of the first search)
-// + (local matches) in keypoint order (src/Optimizer.cc:857-990), and the hand-over of the last frame's points into the local map ring
-// (MapPoint::UpdateNormalAndDepth with one observation, src/MapPoint.cc:437-490; ring slot = frames inserted so far mod K).  The edges
-// take local points from the query copy tlm_prepare made (lq_xw), so overwriting a ring slot here cannot disturb them.
+// + (local matches) in keypoint order (src/Optimizer.cc:857-990); the edges take local points from the query copy tlm_prepare made (lq_xw).
+// It also advances the ring's frame counter (the points of the last frame were copied into the ring by the collect kernel, RingHandOverDev).
 struct ChainTlmDev {
     const int* match_last;           // nullptr: disabled.  Feature -> point of the last frame (outliers of the first optimisation cleared)
     const float* lq_xw;              // world coordinates of the compacted local queries
-    LocalRingDev ring;
+    int* ring_count;                 // frames inserted into the local map ring so far
     int* n_local_matches;
-    int n_last_cap; const uint8_t* last_valid; const int* last_octave; const uint8_t* last_desc; const float* last_pose;
 };
 
 __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const int* __restrict__ n_q_dev, FrameDev f,
-                                                       const int* __restrict__ csr_idx,
-                                                       const uint32_t* __restrict__ lists, int list_cap,
+                                                       const MatchEntry* __restrict__ lists, int list_cap,
                                                        const int* __restrict__ list_n,
                                                        const uint8_t* __restrict__ obs_pos,
                                                        const float* __restrict__ q_angle, float nn_ratio,
@@ -328,18 +384,19 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
                                                        uint8_t* __restrict__ resolved, int* __restrict__ match,
                                                        int* __restrict__ n_matches, int* __restrict__ rounds_out, int dyn_bytes,
                                                        ChainEdgesDev ce, ChainTlmDev tl) {
+    pdl_wait(); pdl_trigger();
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int hist[kHistoLength];
     __shared__ int keep_bin[3];
     __shared__ int s_nm;
     __shared__ int s_wsum[32];
     __shared__ int s_total;
-    __shared__ int s_cnt[2];
+    __shared__ int s_cnt[3];
 #ifdef RESOLVE_DEBUG
 #endif
     const int tid = threadIdx.x;
 #ifdef RESOLVE_DEBUG
-    long long tq[6]; tq[0] = clock64();
+    long long tq[12]; for (int i_ = 0; i_ < 12; ++i_) tq[i_] = 0; tq[0] = clock64(); int dbg_block_rounds = 0;
 #define RQ(i) tq[i] = clock64()
 #else
 #define RQ(i)
@@ -375,45 +432,46 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
     }
     RQ(1);
     const int E = s_total;
-    const size_t need = (size_t)12 * n_f + (size_t)4 * (n_q + 1) + (size_t)12 * (E + 4) + (size_t)12 * n_q + (size_t)n_f + (size_t)2 * n_q + 64;
-    const bool on_chip = n_f <= 65535 && need <= (size_t)dyn_bytes;
+    const size_t need = (size_t)12 * (n_f + 1) + (size_t)4 * (n_q + 1) + (size_t)12 * (E + 4) + (size_t)12 * n_q + (size_t)n_f + (size_t)3 * n_q + 64;
+    const bool on_chip = need <= (size_t)dyn_bytes;
     const bool orient = mode != 1 && check_orientation;
     int rounds = 0, nm_local = 0;          // nm_local: accepted minus rotation-rejected matches of this thread
     int* ch = choice;                      // chosen feature per query (shared memory on the on-chip path)
     uint8_t* bins = resolved;              // rotation bin per query (the global flags array is free after the rounds)
     int* mt = match;                       // match table (shared memory on the on-chip path, written out at the end)
     if (on_chip) {
-        // entry = key << 32 | rotation bin << 24 | octave << 16 | feature: one 64-bit load per candidate
         unsigned long long* s_ent = reinterpret_cast<unsigned long long*>(dyn);
-        int* s_minq = reinterpret_cast<int*>(s_ent + E + 4);
-        int* s_match = s_minq + 2 * (size_t)n_f;        // after the two proposal tables
+        int* s_ioff = reinterpret_cast<int*>(s_ent + E + 4);   // inverse index: the queries that list feature ft are s_iq[s_ioff[ft] .. s_ioff[ft + 1])
+        int* s_icur = s_ioff + n_f + 1;                  // per feature: entry count (fill), then the write cursor of the scatter pass
+        int* s_iq = s_icur + n_f;
+        int* s_match = s_iq + E + 4;
         int* s_off = s_match + n_f;
         int* s_choice = s_off + n_q + 1;
         int* s_list = s_choice + n_q;                    // two compact lists of waiting queries
-        int* s_entq = s_list + 2 * (size_t)n_q;          // owning query of every entry (the proposal phase runs one thread per ENTRY)
-        uint8_t* s_state = reinterpret_cast<uint8_t*>(s_entq + E + 4);
+        uint8_t* s_state = reinterpret_cast<uint8_t*>(s_list + 2 * (size_t)n_q);
         uint8_t* s_res = s_state + n_f;    // bit 0: resolved, bit 1: the query's point has observations, bit 2: list not sorted by key
-        uint8_t* s_bin = s_res + n_q;
+        uint8_t* s_stamp = s_res + n_q;    // 0: waiting, r + 1: became final in round r (ONE byte, so a reader sees "waiting" or the round, never a mix)
+        uint8_t* s_bin = s_stamp + n_q;
         ch = s_choice; bins = s_bin; mt = s_match;
         {
             int o = incl - mine;
             for (int q = qb; q < qe; ++q) { s_off[q] = o; o += list_n[q] & kListCountMask; }
             if (tid == 1023) s_off[n_q] = E;
         }
-        for (int i = tid; i < n_f; i += 1024) { s_state[i] = state[i]; s_match[i] = -1; }
+        for (int i = tid; i < n_f; i += 1024) { s_state[i] = state[i]; s_match[i] = -1; s_icur[i] = 0; }
         if (tid < 4) s_ent[E + tid] = 0xffffffff00000000ull;     // padding: worst key, feature 0
         __syncthreads();
         for (int q = tid; q < n_q; q += 1024) {
-            s_res[q] = (uint8_t)((s_off[q + 1] == s_off[q] ? 1 : 0) | (obs_pos[q] ? 2 : 0) | ((list_n[q] & kListUnsorted) ? 4 : 0));
+            const bool empty = s_off[q + 1] == s_off[q];
+            s_res[q] = (uint8_t)((empty ? 1 : 0) | (obs_pos[q] ? 2 : 0) | ((list_n[q] & kListUnsorted) ? 4 : 0));
+            s_stamp[q] = empty ? 1 : 0;      // "final before round 0"
             s_choice[q] = -1;
         }
-        // one thread per ENTRY (a query's list may hold dozens of candidates: a per-query loop would serialise its chains of
-        // dependent global loads list -> csr -> keypoint); the owning query is found by bisection of the offsets
-        // Four entries per thread and trip: the chain list -> csr -> keypoint is three dependent global loads, so the bisections and
-        // each load level of the four entries are issued together and their latencies overlap (E / 1024 is 2-4 on KITTI frames).
-        const float factor = 1.0f / kHistoLength;
+        // one thread per ENTRY: the owning query is found by bisection of the offsets, the entry itself is ONE load - the collect
+        // kernels (many CTAs) already gathered feature index, octave and rotation bin; here, on a single SM, every dependent level
+        // of scattered global loads cost ~3 k cycles (measured: the three-level gather list -> csr -> keypoint was 9-15 k).
         for (int en0 = tid; en0 < E; en0 += 4096) {
-            int qq[4], ftt[4]; uint32_t kk[4]; unsigned occ[4]; float fa[4], qa[4];
+            int qq[4]; MatchEntry ee[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int en = en0 + u * 1024;
@@ -422,86 +480,94 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
                 qq[u] = lo;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int en = en0 + u * 1024; kk[u] = (en < E) ? lists[(size_t)qq[u] * list_cap + (en - s_off[qq[u]])] : 0u; }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { const int en = en0 + u * 1024; ftt[u] = (en < E) ? csr_idx[kk[u] & kPosMask] : 0; }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int en = en0 + u * 1024;
-                occ[u] = 0; fa[u] = 0.f; qa[u] = 0.f;
-                if (en < E) {
-                    if (mode == 1) occ[u] = (unsigned)f.keys[ftt[u]].octave & 0xffu;
-                    if (orient) { fa[u] = f_angle ? f_angle[ftt[u]] : f.keys[ftt[u]].angle; qa[u] = q_angle[qq[u]]; }
-                }
-            }
+            for (int u = 0; u < 4; ++u) { const int en = en0 + u * 1024; ee[u] = (en < E) ? lists[(size_t)qq[u] * list_cap + (en - s_off[qq[u]])] : 0ull; }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int en = en0 + u * 1024;
                 if (en >= E) continue;
-                unsigned bin = 0;
-                if (orient) {
-                    float rot = __fsub_rn(qa[u], fa[u]);
-                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                    int b = (int)roundf(__fmul_rn(rot, factor));
-                    if (b == kHistoLength) b = 0;
-                    bin = (unsigned)b & 0xffu;
-                }
-                s_ent[en] = ((unsigned long long)kk[u] << 32) | (bin << 24) | (occ[u] << 16) | (unsigned)ftt[u];
-                s_entq[en] = qq[u];
+                s_ent[en] = ee[u];
+                atomicAdd(&s_icur[ent_ft(ee[u])], 1);          // entries per feature, for the inverse index below
             }
         }
         __syncthreads();
         RQ(2);
-        // phase 1 of a round: every waiting query proposes itself (min index wins) at each still-available candidate feature
-        constexpr int kChunk = 4;
-        auto propose = [&](int q, int* mq) {
-            const int e = s_off[q + 1];
-            for (int k = s_off[q]; k < e; k += kChunk) {          // kChunk entries in flight: the chain entry -> state -> atomic is all latency
-                unsigned long long en[kChunk]; uint8_t st[kChunk];
+        // ---- inverse index feature -> queries.  The first formulation rebuilt a proposal table with one shared-memory atomicMin per
+        // entry in EVERY round; shared atomics on scattered addresses retire at 2 cycles per lane (measured: a round cost ~2 E cycles,
+        // 4-7 k).  The index is built once (a count in the fill loop, a scan over the features, one scatter pass) and a round is then
+        // reads only: "does a lower-index query that still waits list this feature".
+        {
+            const int perf = (n_f + 1023) >> 10;
+            const int fb_ = min(n_f, tid * perf), fe_ = min(n_f, fb_ + perf);
+            int mine_f = 0;
+            for (int i = fb_; i < fe_; ++i) mine_f += s_icur[i];
+            int incl_f = mine_f;
+            const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-                for (int u = 0; u < kChunk; ++u) en[u] = (k + u < e) ? s_ent[k + u] : 0xffffffff00000000ull;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl_f, o); if (lane >= o) incl_f += t; }
+            if (lane == 31) s_wsum[warp] = incl_f;
+            __syncthreads();
+            if (warp == 0) {
+                int v = s_wsum[lane], w = v;
 #pragma unroll
-                for (int u = 0; u < kChunk; ++u) st[u] = (k + u < e) ? s_state[(unsigned)en[u] & 0xffffu] : (uint8_t)1;
-#pragma unroll
-                for (int u = 0; u < kChunk; ++u)
-                    if (st[u] != 1) atomicMin(&mq[(unsigned)en[u] & 0xffffu], q);
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+                s_wsum[lane] = w - v;
             }
-        };
+            __syncthreads();
+            int o = incl_f - mine_f + s_wsum[warp];
+            for (int i = fb_; i < fe_; ++i) { const int c = s_icur[i]; s_ioff[i] = o; s_icur[i] = o; o += c; }
+            if (tid == 1023) s_ioff[n_f] = E;
+            __syncthreads();
+            for (int q = tid; q < n_q; q += 1024) {          // scatter by QUERY: its entries are consecutive, the query index is known
+                const int e = s_off[q + 1];
+                for (int k = s_off[q]; k < e; ++k) s_iq[atomicAdd(&s_icur[ent_ft(s_ent[k])], 1)] = q;
+            }
+            __syncthreads();
+        }
+        RQ(5);
         // phase 2: best (and second best) available candidate; final when no lower-index waiting query can still interfere.
         // Returns true while the query has to wait for another round.
         // A query's decision depends on its best and second-best AVAILABLE candidates only (the set of available candidates can only
         // shrink until its turn, so if no lower-index waiting query proposes at those two they are still its best two then): with the
         // list sorted by key the scan stops at the second available entry - typically after two or three of them; lists of more than 32
         // candidates (left in scan order) are read to the end.  tests/test_resolution_model.py checks this rule against the sequential loops.
-        auto decide = [&](int q, const int* mq) -> bool {
+        // `stamp_now` = round + 1: a query that became final in THIS round still counts as waiting for the others (decisions of a round are
+        // taken against the state of the waiting set at its start, like the proposal table of the first formulation)
+        auto lower_waiting = [&](int ft, int q, int stamp_now) -> bool {
+            const int e = s_ioff[ft + 1];
+            for (int k = s_ioff[ft]; k < e; ++k) {
+                const int o = s_iq[k];
+                if (o < q) { const int st = s_stamp[o]; if (st == 0 || st == stamp_now) return true; }
+            }
+            return false;
+        };
+        auto decide = [&](int q, int stamp_now) -> bool {
             const uint8_t flags = s_res[q];
             uint32_t best = 0xffffffffu, best2 = 0xffffffffu;
             int lvl = -1, lvl2 = -1, fb = -1, bb = 0, fb2 = -1;
             const int e = s_off[q + 1];
             if (!(flags & 4)) {
                 for (int k = s_off[q]; k < e; ++k) {
-                    const unsigned long long en = s_ent[k];
-                    const int ft = (int)((unsigned)en & 0xffffu);
+                    const MatchEntry en = s_ent[k];
+                    const int ft = ent_ft(en);
                     if (s_state[ft] == 1) continue;
-                    if (fb < 0) { best = (uint32_t)(en >> 32); fb = ft; bb = (int)(((unsigned)en >> 24) & 0xffu); lvl = (int)(((unsigned)en >> 16) & 0xffu); if (mode == 0) break; }
-                    else { best2 = (uint32_t)(en >> 32); fb2 = ft; lvl2 = (int)(((unsigned)en >> 16) & 0xffu); break; }
+                    if (fb < 0) { best = ent_key(en); fb = ft; bb = ent_bin(en); lvl = ent_oc(en); if (mode == 0) break; }
+                    else { best2 = ent_key(en); fb2 = ft; lvl2 = ent_oc(en); break; }
                 }
             } else {
                 for (int k = s_off[q]; k < e; ++k) {
-                    const unsigned long long en = s_ent[k];
-                    const int ft = (int)((unsigned)en & 0xffffu);
+                    const MatchEntry en = s_ent[k];
+                    const int ft = ent_ft(en);
                     if (s_state[ft] == 1) continue;
-                    const uint32_t key = (uint32_t)(en >> 32);
-                    const int oc = (int)(((unsigned)en >> 16) & 0xffu);
-                    if (key < best) { best2 = best; lvl2 = lvl; fb2 = fb; best = key; lvl = oc; fb = ft; bb = (int)(((unsigned)en >> 24) & 0xffu); }
+                    const uint32_t key = ent_key(en);
+                    const int oc = ent_oc(en);
+                    if (key < best) { best2 = best; lvl2 = lvl; fb2 = fb; best = key; lvl = oc; fb = ft; bb = ent_bin(en); }
                     else if (key < best2) { best2 = key; lvl2 = oc; fb2 = ft; }
                 }
                 if (mode == 0) { best2 = 0xffffffffu; fb2 = -1; }
             }
-            const bool depends_ok = fb >= 0 && mq[fb] == q && (fb2 < 0 || mq[fb2] == q);
-            if (best == 0xffffffffu) { s_res[q] = flags | 1; return false; }
-            if (!depends_ok) return true;
-            s_res[q] = flags | 1;
+            if (best == 0xffffffffu) { s_res[q] = flags | 1; s_stamp[q] = (uint8_t)stamp_now; return false; }
+            if (lower_waiting(fb, q, stamp_now) || (fb2 >= 0 && lower_waiting(fb2, q, stamp_now))) return true;
+            s_res[q] = flags | 1; s_stamp[q] = (uint8_t)stamp_now;
             const int bd = (int)(best >> 20);
             bool accept = bd <= th_accept;
             if (mode == 1 && accept) {
@@ -517,7 +583,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
                 // This write races with the state reads of other queries deciding in the same phase (compute-sanitizer
                 // racecheck reports it); it is benign: only 0/2 -> 1 matters to a reader, and a query q' that reads state[fb]
                 // has fb in its list, so it proposed there too and the winner q satisfies q < q'.  If q' sees the old value
-                // it waits one more round (minq[fb] = q != q') and then sees 1; if it sees the new value it skips fb now,
+                // it waits one more round (q is a lower query listing fb that was waiting when the round began) and then sees 1; if it sees the new value it skips fb now,
                 // exactly what the sequential scan does after q took fb.  Either way q' ends with the same feature.
                 if (flags & 2) s_state[fb] = 1; else if (s_state[fb] == 0) s_state[fb] = 2;
                 ++nm_local;
@@ -525,15 +591,12 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             return false;
         };
 
-        // Block rounds over a COMPACT list of the waiting queries (two barriers per round; the proposal table is double
-        // buffered: the idle copy is cleared while the live one is read).  Why the list: a warp pays for the longest candidate
-        // list among its lanes, so with the waiting queries scattered over all 32 warps every warp ran the full loop in every
-        // round (measured: the rounds were issue-bound, not latency-bound); packed, round r touches ceil(waiting / 32) warps.
-        // A 1024-thread barrier costs ~500 cycles, so once <= 32 queries wait warp 0 finishes alone with warp-level syncs.
+        // Block rounds over a COMPACT list of the waiting queries (one barrier per round): a warp pays for its slowest lane, so with the
+        // waiting queries scattered over all 32 warps every warp would run the full decision in every round; packed, round r touches
+        // ceil(waiting / 32) warps.  Once <= 32 queries wait, warp 0 finishes alone with warp-level syncs.
         int cur = 0, n_act;
         {
-            if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
-            for (int i = tid; i < n_f; i += 1024) s_minq[i] = 0x7fffffff;
+            if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; }
             __syncthreads();
             for (int q0 = 0; q0 < n_q; q0 += 1024) {
                 const int q = q0 + tid;
@@ -547,57 +610,49 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             __syncthreads();
             n_act = s_cnt[0];
         }
-        // Block rounds.  Proposal phase: one thread per ENTRY (a per-query loop makes every warp wait for its longest list; measured, the
-        // rounds cost ~4 k cycles each that way) - an entry of a waiting query whose feature is still available proposes its query.
-        // Decision phase: over a COMPACT list of the waiting queries (packed, round r touches ceil(waiting / 32) warps); the proposal
-        // table is double buffered, the idle copy is cleared while the live one is read.  <= 32 waiting queries: warp 0 finishes alone.
-        while (n_act > 32) {
-            int* mq = s_minq + (size_t)cur * n_f;
-            int* mq_next = s_minq + (size_t)(cur ^ 1) * n_f;
+        int stamp = 2;                           // round r carries stamp r + 2 (1 = "final before the first round"); re-based before it reaches 255
+        auto rebase = [&](bool whole_block) {
+            if (stamp < 250) return;
+            if (whole_block) { for (int q = tid; q < n_q; q += 1024) if (s_stamp[q]) s_stamp[q] = 1; __syncthreads(); }
+            else { for (int q = tid; q < n_q; q += 32) if (s_stamp[q]) s_stamp[q] = 1; __syncwarp(); }
+            stamp = 2;
+        };
+        // Three rotating counters: round ri appends to s_cnt[(ri + 1) % 3] (zero since round ri - 1), everybody reads it after the barrier,
+        // and s_cnt[(ri + 2) % 3] - last read after the barrier of round ri - 2 - is cleared meanwhile: one barrier per round suffices.
+        for (int ri = 0; n_act > 32; ++ri) {
+            rebase(true);
             const int* lst = s_list + (size_t)cur * n_q;
             int* lst_next = s_list + (size_t)(cur ^ 1) * n_q;
-            if (tid == 0) s_cnt[cur ^ 1] = 0;
-            for (int i = tid; i < n_f; i += 1024) mq_next[i] = 0x7fffffff;
-#pragma unroll 4
-            for (int en = tid; en < E; en += 1024) {
-                const int q = s_entq[en];
-                const int ft = (int)((unsigned)s_ent[en] & 0xffffu);
-                if (!(s_res[q] & 1) && s_state[ft] != 1) atomicMin(&mq[ft], q);
-            }
-            __syncthreads();
+            int* out_cnt = &s_cnt[(ri + 1) % 3];
+            if (tid == 0) s_cnt[(ri + 2) % 3] = 0;
             for (int i0 = 0; i0 < n_act; i0 += 1024) {
                 const int i = i0 + tid;
                 const int q = i < n_act ? lst[i] : -1;
-                const bool w = q >= 0 && decide(q, mq);
+                const bool w = q >= 0 && decide(q, stamp);
                 const unsigned m = __ballot_sync(0xffffffffu, w);
                 int base = 0;
-                if ((tid & 31) == 0 && m) base = atomicAdd(&s_cnt[cur ^ 1], __popc(m));
+                if ((tid & 31) == 0 && m) base = atomicAdd(out_cnt, __popc(m));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (w) lst_next[base + __popc(m & ((1u << (tid & 31)) - 1u))] = q;
             }
-            ++rounds;
+            ++rounds; ++stamp;
             cur ^= 1;
             __syncthreads();
-            n_act = s_cnt[cur];
+            n_act = *out_cnt;
         }
+        RQ(6);
+#ifdef RESOLVE_DEBUG
+        dbg_block_rounds = rounds;
+#endif
         if (n_act > 0 && tid < 32) {
-            int* mq = s_minq + (size_t)cur * n_f;     // a fully cleared table; the tail clears only what it touches
-            const int q0 = tid < n_act ? s_list[(size_t)cur * n_q + tid] : -1;
-            int q = q0;
+            int q = tid < n_act ? s_list[(size_t)cur * n_q + tid] : -1;
             for (;;) {
-                if (q >= 0) propose(q, mq);
-                __syncwarp();
+                rebase(false);
                 bool waiting = false;
-                if (q >= 0) waiting = decide(q, mq);
-                ++rounds;
+                if (q >= 0) waiting = decide(q, stamp);
+                ++rounds; ++stamp;
                 if (!__any_sync(0xffffffffu, waiting)) break;
                 if (!waiting) q = -1;
-                // clear every proposal of this round, also those of the queries that just finished: a stale index of a
-                // resolved query would keep its features "claimed" forever
-                if (q0 >= 0) {
-                    const int e = s_off[q0 + 1];
-                    for (int k = s_off[q0]; k < e; ++k) mq[(unsigned)s_ent[k] & 0xffffu] = 0x7fffffff;
-                }
                 __syncwarp();
             }
         }
@@ -615,41 +670,38 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         __syncthreads();
         for (int q = tid; q < n_q; q += 1024) {
             if (resolved[q]) continue;
-            const uint32_t* l = lists + (size_t)q * list_cap;
+            const MatchEntry* l = lists + (size_t)q * list_cap;
             const int n = list_n[q] & kListCountMask;
             for (int k = 0; k < n; ++k) {
-                const int ft = csr_idx[l[k] & kPosMask];
+                const int ft = ent_ft(l[k]);
                 if (state[ft] != 1) atomicMin(&minq[ft], q);
             }
         }
         __syncthreads();
         for (int q = tid; q < n_q; q += 1024) {
             if (resolved[q]) continue;
-            const uint32_t* l = lists + (size_t)q * list_cap;
+            const MatchEntry* l = lists + (size_t)q * list_cap;
             const int n = list_n[q] & kListCountMask;
             uint32_t best = 0xffffffffu, best2 = 0xffffffffu;     // smallest / second smallest (dist, order) keys
-            int lvl = -1, lvl2 = -1;
+            int lvl = -1, lvl2 = -1, fb = -1;
             bool depends_ok = true;
             for (int k = 0; k < n; ++k) {
-                const uint32_t key = l[k];
-                const int ft = csr_idx[key & kPosMask];
+                const uint32_t key = ent_key(l[k]);
+                const int ft = ent_ft(l[k]);
                 if (state[ft] == 1) continue;
                 if (mode >= 1 && minq[ft] != q) depends_ok = false;
-                const int d = (int)(key >> 20);
                 if (mode == 0) {
-                    if (key < best) best = key;
+                    if (key < best) { best = key; fb = ft; }
                 } else {
                     // reference scan order = ascending csr position; emulate "dist < bestDist" / "else if dist < bestDist2"
                     // order-independently: best = min by (dist, pos); second = min dist among the rest (level of the
                     // FIRST candidate in scan order reaching that distance)
-                    const int oc = (mode == 1) ? f.keys[ft].octave : 0;
-                    if (key < best) { best2 = best; lvl2 = lvl; best = key; lvl = oc; }
+                    const int oc = ent_oc(l[k]);
+                    if (key < best) { best2 = best; lvl2 = lvl; best = key; lvl = oc; fb = ft; }
                     else if (key < best2) { best2 = key; lvl2 = oc; }
-                    (void)d;
                 }
             }
             if (best == 0xffffffffu) { resolved[q] = 1; continue; }
-            const int fb = csr_idx[best & kPosMask];
             const bool final_ok = (mode == 0) ? (minq[fb] == q) : depends_ok;
             if (!final_ok) { any_unresolved = true; continue; }
             resolved[q] = 1;
@@ -683,7 +735,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             const int q = q0 + tid;
             const int c = q < n_q ? ch[q] : -1;
             const bool valid = c >= 0;
-            int bin = 64 + (tid & 31);                      // unique key for lanes without a match
+            int bin = 63;                                   // lanes without a match share one key (MATCH.ANY iterates over the distinct values of a warp)
             if (valid) {
                 if (on_chip) {
                     bin = bins[q];                          // computed with the candidate entry
@@ -729,10 +781,12 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             if (bin != keep_bin[0] && bin != keep_bin[1] && bin != keep_bin[2]) { mt[c] = -2; --nm_local; }
         }
     }
+    RQ(7);
     if (on_chip) {
         __syncthreads();
         for (int i = tid; i < n_f; i += 1024) match[i] = mt[i];
     }
+    RQ(8);
     if (ce.n_edges) {                     // ordered compaction of the matched features into edges
         // Two chunks of 1024 features per trip (a KITTI frame is one trip): everything an edge needs is loaded for both chunks before the
         // positions are known, so the trip pays ONE round of global latency (two in the TrackLocalMap form, whose first-search matches
@@ -743,40 +797,8 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         if (tid == 0) s_nloc = 0;
         __syncthreads();
         const int lane = tid & 31, warp = tid >> 5;
-        if (tlm) {
-            // the last frame's points become local map points; every value is loaded before the first store of the loop body
-            const int ring_count = *tl.ring.count;
-            float Ow[3];
-            {
-                float T[7], qinv[4];
-#pragma unroll
-                for (int k = 0; k < 7; ++k) T[k] = tl.last_pose[k];
-                se3f_inverse(T, qinv, Ow);                 // KeyFrame::GetCameraCenter of the frame the points were created from
-            }
-            const size_t base = (size_t)(ring_count % tl.ring.K) * tl.ring.cap;
-            for (int j = tid; j < tl.ring.cap; j += 1024) {
-                uint8_t v = 0;
-                if (j < tl.n_last_cap && tl.last_valid[j]) {
-                    const float P[3] = {ce.last_xw[3 * j], ce.last_xw[3 * j + 1], ce.last_xw[3 * j + 2]};
-                    const int loct = tl.last_octave[j];
-                    const uint4 d0 = reinterpret_cast<const uint4*>(tl.last_desc + (size_t)j * 32)[0];
-                    const uint4 d1 = reinterpret_cast<const uint4*>(tl.last_desc + (size_t)j * 32)[1];
-                    const float PC[3] = {__fsub_rn(P[0], Ow[0]), __fsub_rn(P[1], Ow[1]), __fsub_rn(P[2], Ow[2])};
-                    const float dist = sqrtf(eig_sum3(__fmul_rn(PC[0], PC[0]), __fmul_rn(PC[1], PC[1]), __fmul_rn(PC[2], PC[2])));
-                    const size_t p = base + j;
-                    tl.ring.xw[3 * p] = P[0]; tl.ring.xw[3 * p + 1] = P[1]; tl.ring.xw[3 * p + 2] = P[2];
-                    tl.ring.normal[3 * p] = __fdiv_rn(PC[0], dist); tl.ring.normal[3 * p + 1] = __fdiv_rn(PC[1], dist); tl.ring.normal[3 * p + 2] = __fdiv_rn(PC[2], dist);
-                    const float mx = __fmul_rn(dist, f.scale[loct]);
-                    tl.ring.mf_max[p] = mx;
-                    tl.ring.mf_min[p] = __fdiv_rn(mx, f.scale[f.n_levels - 1]);
-                    uint4* dd = reinterpret_cast<uint4*>(tl.ring.desc + p * 32);
-                    dd[0] = d0; dd[1] = d1;
-                    v = 1;
-                }
-                tl.ring.valid[base + j] = v;
-            }
-            if (tid == 0) *tl.ring.count = ring_count + 1;
-        }
+        if (tlm && tid == 0) *tl.ring_count = *tl.ring_count + 1;      // the points of the last frame were handed over by the collect kernel
+        RQ(9);
         int run = 0, nloc = 0;            // edges before this trip (same value in every thread); local matches of this thread
         for (int b = 0; b < n_f; b += 2048) {
             int m[2]; float kx[2], ky[2], ur[2], xw[2][3]; int oc[2]; unsigned bal[2]; const float* src[2];
@@ -852,8 +874,8 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
     __syncthreads();
     if (tid == 0) { *n_matches = s_nm; if (rounds_out) *rounds_out = rounds; }
 #ifdef RESOLVE_DEBUG
-    if (tid == 0) printf("resolve mode=%d n_q=%d n_f=%d E=%d on_chip=%d rounds=%d nm=%d | scan=%lld fill=%lld rounds=%lld epilogue=%lld\n", mode, n_q, n_f, E, (int)on_chip, rounds, s_nm,
-                         tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], clock64() - tq[3]);
+    if (tid == 0) printf("resolve mode=%d n_q=%d n_f=%d E=%d on_chip=%d rounds=%d (block %d) nm=%d | scan=%lld fill=%lld index=%lld rounds=%lld (block %lld tail %lld) epilogue=%lld (owner+orient %lld, match out %lld, hand-over %lld, edges+rest %lld)\n", mode, n_q, n_f, E, (int)on_chip, rounds, dbg_block_rounds, s_nm,
+                         tq[1] - tq[0], tq[2] - tq[1], tq[5] - tq[2], tq[3] - tq[5], tq[6] - tq[5], tq[3] - tq[6], clock64() - tq[3], tq[7] - tq[3], tq[8] - tq[7], tq[9] ? tq[9] - tq[8] : 0, clock64() - (tq[9] ? tq[9] : tq[8]));
 
 #endif
 }
@@ -947,22 +969,25 @@ __global__ void __launch_bounds__(256) frustum_kernel(FrameDev f, FrustumParams 
 __global__ void __launch_bounds__(256) bow_collect_kernel(int n_q, const int* __restrict__ q_feat, const int* __restrict__ q_cbeg,
                                                           const int* __restrict__ q_cend, const uint8_t* __restrict__ kf_desc,
                                                           const uint8_t* __restrict__ f_desc, const int* __restrict__ f_node_feat,
-                                                          int keep_max, uint32_t* __restrict__ lists, int list_cap,
+                                                          const float* __restrict__ q_angle, const float* __restrict__ f_angle, int check_orientation,
+                                                          int keep_max, MatchEntry* __restrict__ lists, int list_cap,
                                                           int* __restrict__ list_n, int* __restrict__ overflow) {
     const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= n_q) return;
     const uint8_t* dq = kf_desc + (size_t)q_feat[q] * 32;
     const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(dq)), d1 = __ldg(reinterpret_cast<const uint4*>(dq) + 1);
     const int b = q_cbeg[q], e = q_cend[q];
-    uint32_t* list = lists + (size_t)q * list_cap;
+    MatchEntry* list = lists + (size_t)q * list_cap;
+    const float qa = check_orientation ? q_angle[q] : 0.f;
     int count = 0;
     for (int p0 = b; p0 < e; p0 += 32) {
         const int p = p0 + lane;
         bool keep = false;
-        uint32_t key = 0;
+        MatchEntry key = 0;
         if (p < e) {
-            const int d = hamming256(d0, d1, f_desc + (size_t)f_node_feat[p] * 32);
-            if (d <= keep_max) { keep = true; key = ((uint32_t)d << 20) | (uint32_t)p; }
+            const int ft = f_node_feat[p];
+            const int d = hamming256(d0, d1, f_desc + (size_t)ft * 32);
+            if (d <= keep_max) { keep = true; key = ent_make(((uint32_t)d << 20) | (uint32_t)p, check_orientation ? rotation_bin(qa, f_angle[ft]) : 0u, 0u, (unsigned)ft); }
         }
         const uint32_t m = __ballot_sync(0xffffffffu, keep);
         if (keep) { const int o = count + __popc(m & ((1u << lane) - 1u)); if (o < list_cap) list[o] = key; }
@@ -975,7 +1000,7 @@ __global__ void __launch_bounds__(256) bow_collect_kernel(int n_q, const int* __
 // ---- SearchByProjection(CurrentFrame, KeyFrame, sAlreadyFound, th, ORBdist): candidate phase -------------------------
 __global__ void __launch_bounds__(256) search_reloc_collect_kernel(FrameDev f, const int* __restrict__ cell_start,
                                                                    const int* __restrict__ csr_idx, RelocPointsDev rp,
-                                                                   SearchRelocParams prm, uint32_t* __restrict__ lists,
+                                                                   SearchRelocParams prm, MatchEntry* __restrict__ lists,
                                                                    int list_cap, int* __restrict__ list_n,
                                                                    int* __restrict__ overflow) {
     const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -1003,7 +1028,7 @@ __global__ void __launch_bounds__(256) search_reloc_collect_kernel(FrameDev f, c
                     const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(rp.desc + (size_t)q * 32));
                     const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(rp.desc + (size_t)q * 32) + 1);
                     count = warp_collect(f, cell_start, csr_idx, cr, u, v, radius, pl - 1, pl + 1, d0, d1, prm.orb_dist,
-                                         lists + (size_t)q * list_cap, list_cap, [](int) { return true; });
+                                         lists + (size_t)q * list_cap, list_cap, [](int) { return true; }, prm.check_orientation != 0, rp.angle[q]);
                 }
             }
         }
@@ -1054,24 +1079,30 @@ void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_star
                         const SearchLastParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches,
                         const ChainEdgesOut* edges) {
     if (lf.n <= 0) return;
-    search_last_collect_kernel<<<(lf.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lf, prm, s.lists, s.list_cap, s.list_n, s.overflow);
-    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, lf.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, lf.obs_pos, lf.angle, 0.f,
-                                       prm.check_orientation, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(),
+    const bool pdl = chain_launch_pdl();
+    launch_kernel(search_last_collect_kernel, dim3((lf.n + 7) / 8), dim3(256), 0, st, pdl, f, cell_start, csr_idx, lf, prm, s.lists, s.list_cap, s.list_n, s.overflow);
+    launch_kernel(resolve_kernel, dim3(1), dim3(1024), (size_t)resolve_dyn_bytes(), st, pdl, 0, lf.n, (const int*)nullptr, f, s.lists, s.list_cap, s.list_n, lf.obs_pos, lf.angle, 0.f,
+                                       prm.check_orientation, kThHigh, (const float*)nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(),
                                        edges ? ChainEdgesDev{f.keys, f.uright, lf.xw, edges->exw, edges->eobs, edges->einfo, edges->est, edges->eidx, edges->n_edges} : ChainEdgesDev{}, ChainTlmDev{});
 }
 
 void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const LocalPointsDev& lp,
                          const SearchLocalParams& prm, MatchScratch s, uint8_t* state, int* match, int* n_matches, const ChainTlmTail* tail) {
     if (lp.n <= 0) return;
-    search_local_collect_kernel<<<(lp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, lp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
+    RingHandOverDev ho{};
+    if (tail) ho = RingHandOverDev{tail->ring, tail->last_xw, tail->n_last_cap, tail->last_valid, tail->last_octave, tail->last_desc, tail->last_pose};
+    const int n_q_cta = (lp.n + 7) / 8, n_ho_cta = tail ? (tail->ring.cap + 255) / 256 : 0;
+    const int n_cta = n_q_cta > n_ho_cta ? n_q_cta : n_ho_cta;
+    const bool pdl = chain_launch_pdl();
+    launch_kernel(search_local_collect_kernel, dim3(n_cta), dim3(256), 0, st, pdl, f, cell_start, csr_idx, lp, prm, s.lists, s.list_cap, s.list_n, s.overflow, ho);
     ChainEdgesDev ce{};
     ChainTlmDev tl{};
     if (tail) {
         ce = ChainEdgesDev{f.keys, f.uright, tail->last_xw, tail->edges.exw, tail->edges.eobs, tail->edges.einfo, tail->edges.est, tail->edges.eidx, tail->edges.n_edges};
-        tl = ChainTlmDev{tail->match_last, tail->lq_xw, tail->ring, tail->n_local_matches, tail->n_last_cap, tail->last_valid, tail->last_octave, tail->last_desc, tail->last_pose};
+        tl = ChainTlmDev{tail->match_last, tail->lq_xw, tail->ring.count, tail->n_local_matches};
     }
-    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(1, lp.n, lp.n_dev, f, csr_idx, s.lists, s.list_cap, s.list_n, lp.obs_pos, nullptr, prm.nn_ratio,
-                                       0, kThHigh, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ce, tl);
+    launch_kernel(resolve_kernel, dim3(1), dim3(1024), (size_t)resolve_dyn_bytes(), st, pdl, 1, lp.n, lp.n_dev, f, s.lists, s.list_cap, s.list_n, lp.obs_pos, (const float*)nullptr, prm.nn_ratio,
+                                       0, kThHigh, (const float*)nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ce, tl);
 }
 
 void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q_feat, const int* q_cbeg, const int* q_cend,
@@ -1079,9 +1110,9 @@ void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q
                        float nn_ratio, int keep_max, int check_orientation, const uint8_t* obs_pos, MatchScratch s, uint8_t* state, int* match,
                        int* n_matches) {
     if (n_q <= 0) return;
-    bow_collect_kernel<<<(n_q + 7) / 8, 256, 0, st>>>(n_q, q_feat, q_cbeg, q_cend, kf_desc, f_desc, f_node_feat, keep_max, s.lists, s.list_cap,
+    bow_collect_kernel<<<(n_q + 7) / 8, 256, 0, st>>>(n_q, q_feat, q_cbeg, q_cend, kf_desc, f_desc, f_node_feat, q_angle, f_angle, check_orientation, keep_max, s.lists, s.list_cap,
                                                     s.list_n, s.overflow);
-    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(2, n_q, nullptr, f, f_node_feat, s.lists, s.list_cap, s.list_n, obs_pos, q_angle, nn_ratio,
+    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(2, n_q, nullptr, f, s.lists, s.list_cap, s.list_n, obs_pos, q_angle, nn_ratio,
                                        check_orientation, 50 /* TH_LOW */, f_angle, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{}, ChainTlmDev{});
 }
 
@@ -1089,7 +1120,7 @@ void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_sta
                          const SearchRelocParams& prm, const uint8_t* obs_pos, MatchScratch s, uint8_t* state, int* match, int* n_matches) {
     if (rp.n <= 0) return;
     search_reloc_collect_kernel<<<(rp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, rp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
-    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, rp.n, nullptr, f, csr_idx, s.lists, s.list_cap, s.list_n, obs_pos, rp.angle, 0.f,
+    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, rp.n, nullptr, f, s.lists, s.list_cap, s.list_n, obs_pos, rp.angle, 0.f,
                                        prm.check_orientation, prm.orb_dist, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{}, ChainTlmDev{});
 }
 

@@ -28,7 +28,7 @@ struct TrackBufs {
     int* match = nullptr; size_t cap_match = 0;
     int* minq = nullptr; size_t cap_minq = 0;
     int* scalars = nullptr; size_t cap_scalars = 0;
-    uint32_t* lists = nullptr; size_t cap_lists = 0;
+    unsigned long long* lists = nullptr; size_t cap_lists = 0;
     int* list_n = nullptr; size_t cap_listn = 0;
     int* choice = nullptr; size_t cap_choice = 0;
     uint8_t* resolved = nullptr; size_t cap_resolved = 0;

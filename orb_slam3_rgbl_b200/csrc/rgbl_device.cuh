@@ -180,6 +180,22 @@ __device__ __forceinline__ void quatf_to_matrix(const float q[4], float R[9]) {
     R[6] = __fsub_rn(txz, twy); R[7] = __fadd_rn(tyz, twx); R[8] = __fsub_rn(1.f, __fadd_rn(txx, tyy));
 }
 
+// Programmatic dependent launch (PDL): the kernels of the resident tracking chain are launched with the programmatic-stream-serialization
+// attribute, so a kernel's CTAs are scheduled while its predecessor still runs and wait HERE until the predecessor's grid has completed
+// and its memory is visible; the predecessor releases them early with pdl_trigger().  What is gained is the launch latency between two
+// dependent kernels (a frame is a chain of 7).  Both are no-ops for a kernel launched the ordinary way.  Rule: pdl_wait() is the first
+// statement of every chain kernel, unconditionally (a CTA that returned without waiting would let the NEXT kernel overtake).
+__device__ __forceinline__ void pdl_wait() {
+#ifndef RGBL_CUDA_EMU
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger() {
+#ifndef RGBL_CUDA_EMU
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 // barrier of the first `nthreads` threads of a CTA (a multiple of 32; named barrier 1), for phases that only a few warps take part in
 __device__ __forceinline__ void team_sync(int nthreads) {
 #ifdef RGBL_CUDA_EMU

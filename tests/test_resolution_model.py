@@ -48,12 +48,20 @@ def sequential(mode, lists, obs_pos, state0, lvl, ratio, th_accept):
     return choice, state
 
 
-def rounds(mode, lists, obs_pos, state0, lvl, ratio, th_accept, reverse, top2=True):
+def rounds(mode, lists, obs_pos, state0, lvl, ratio, th_accept, reverse, top2=True, inverse=False):
     """top2: a query depends only on its best and second-best AVAILABLE candidates (what the kernel does since round 2: lists sorted
     by key, the scan stops at the second available entry); False: on every available candidate (the first formulation)."""
     state = list(state0); n_q = len(lists); choice = [-1] * n_q
     resolved = [len(c) == 0 for c in lists]
+    # inverse=True: what the kernel does since round 2 - no per-round proposal table; a query is blocked at feature ft when a lower-index
+    # query that lists ft was still waiting when the round BEGAN (queries that become final during the round still count), and the
+    # availability of ft is read live (it may already reflect decisions taken earlier in the same round)
+    listing = {}
+    for q, cand in enumerate(lists):
+        for (_, _, ft) in cand:
+            listing.setdefault(ft, []).append(q)
     for _ in range(4 * n_q + 4):
+        waiting_at_start = [not r for r in resolved]
         minq = {}
         for q in range(n_q):
             if resolved[q]:
@@ -86,7 +94,12 @@ def rounds(mode, lists, obs_pos, state0, lvl, ratio, th_accept, reverse, top2=Tr
                 continue
             if top2:
                 depends_ok = minq.get(best[1]) == q and (best2 is None or minq.get(best2[1]) == q)
-            final_ok = (minq.get(best[1]) == q) if mode == 0 else depends_ok
+            if inverse:
+                blocked = lambda ft: any(o < q and waiting_at_start[o] for o in listing.get(ft, []))
+                depends_ok = not blocked(best[1]) and (best2 is None or not blocked(best2[1]))
+                if mode == 0:
+                    depends_ok = not blocked(best[1])
+            final_ok = depends_ok if (inverse or mode != 0) else (minq.get(best[1]) == q)
             if not final_ok:
                 waiting = True
                 continue
@@ -135,6 +148,7 @@ def test_rounds_equal_the_sequential_greedy_matchers(inst, mode, reverse):
     got = rounds(mode, lists, obs_pos, state0, lvl, ratio, th, reverse)
     assert got == ref
     assert rounds(mode, lists, obs_pos, state0, lvl, ratio, th, reverse, top2=False) == ref
+    assert rounds(mode, lists, obs_pos, state0, lvl, ratio, th, reverse, inverse=True) == ref
 
 
 def three_maxima_sequential(h):

@@ -180,6 +180,7 @@ static int create(const rgbl_config* cfg, Ctx** out) {
     for (int i = 0; i < 4; ++i) c->h_chain_ovf[i] = 0;
     c->chain_timing_on = std::getenv("RGBL_CHAIN_TIMING") != nullptr;
     c->chain_graphs_on = !(std::getenv("RGBL_CHAIN_GRAPH") && std::getenv("RGBL_CHAIN_GRAPH")[0] == '0');
+    c->chain_pdl_on = !(std::getenv("RGBL_CHAIN_PDL") && std::getenv("RGBL_CHAIN_PDL")[0] == '0');
     CUF(hmalloc(&c->h_level_cnt, (size_t)B * RGBL_MAX_LEVELS));
     CUF(hmalloc(&c->h_frame_total, (size_t)B));
     CUF(hmalloc(&c->h_overflow, 4));

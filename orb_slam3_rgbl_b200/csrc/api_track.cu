@@ -35,6 +35,10 @@ static int ensure_frame(Ctx* c, int n_frame) {
     GROW(t.keys, t.cap_keys, n_frame); GROW(t.uright, t.cap_uright, n_frame); GROW(t.desc, t.cap_desc, (size_t)n_frame * 32);
     GROW(t.csr_idx, t.cap_csr, n_frame); GROW(t.kp_cell, t.cap_kpcell, n_frame); GROW(t.state, t.cap_state, n_frame);
     GROW(t.match, t.cap_match, n_frame); GROW(t.minq, t.cap_minq, n_frame);
+    if ((size_t)n_frame > t.cap_inv_cnt) {                    // per-feature entry counters of the collect kernels: zero between launches
+        GROW(t.inv_cnt, t.cap_inv_cnt, n_frame);
+        CU(cudaMemsetAsync(t.inv_cnt, 0, t.cap_inv_cnt * sizeof(int), c->st));
+    }
     GROW(t.cell_start, t.cap_cellstart, kGridCols * kGridRows + 1);
     GROW(t.scalars, t.cap_scalars, 16);
     return RGBL_OK;
@@ -42,7 +46,7 @@ static int ensure_frame(Ctx* c, int n_frame) {
 
 static int ensure_queries(Ctx* c, int n_q) {
     TrackBufs& t = c->trk;
-    GROW(t.lists, t.cap_lists, (size_t)n_q * kMatchListCap); GROW(t.list_n, t.cap_listn, n_q);
+    GROW(t.lists, t.cap_lists, (size_t)n_q * kMatchListCap); GROW(t.list_slots, t.cap_list_slots, (size_t)n_q * kMatchListCap); GROW(t.list_n, t.cap_listn, n_q);
     GROW(t.choice, t.cap_choice, n_q); GROW(t.resolved, t.cap_resolved, n_q);
     GROW(t.q_u8a, t.cap_q_u8a, n_q); GROW(t.q_u8b, t.cap_q_u8b, n_q); GROW(t.q_desc, t.cap_q_desc, (size_t)n_q * 32);
     GROW(t.q_f3a, t.cap_q_f3a, (size_t)n_q * 3); GROW(t.q_f3b, t.cap_q_f3b, (size_t)n_q * 3);
@@ -83,7 +87,7 @@ static MatchScratch scratch(Ctx* c) {
     TrackBufs& t = c->trk;
     MatchScratch s;
     s.lists = t.lists; s.list_cap = kMatchListCap; s.list_n = t.list_n; s.minq = t.minq; s.choice = t.choice; s.resolved = t.resolved;
-    s.overflow = c->d_overflow; s.rounds = t.scalars + 2;
+    s.overflow = c->d_overflow; s.rounds = t.scalars + 2; s.slots = t.list_slots; s.inv_cnt = t.inv_cnt;
     return s;
 }
 
@@ -684,7 +688,9 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
             if (c->chain_exec[slot]) { cudaGraphExecDestroy(c->chain_exec[slot]); c->chain_exec[slot] = nullptr; }
             prepare_match_kernels();
             CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+            chain_launch_pdl() = c->chain_pdl_on;           // programmatic dependent launches between the chain's kernels (rgbl_device.cuh: pdl_wait)
             const int rc_cap = enqueue_chain();
+            chain_launch_pdl() = false;
             cudaGraph_t graph = nullptr;
             const cudaError_t e_cap = cudaStreamEndCapture(cs, &graph);
             if (rc_cap != RGBL_OK || e_cap != cudaSuccess || !graph) {
@@ -702,7 +708,10 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
         n_launches = c->chain_graph_launches[slot];
         CU(cudaGraphLaunch(c->chain_exec[slot], cs));
     } else {
-        const int rc_q = enqueue_chain(); if (rc_q) return rc_q;
+        chain_launch_pdl() = c->chain_pdl_on;
+        const int rc_q = enqueue_chain();
+        chain_launch_pdl() = false;
+        if (rc_q) return rc_q;
     }
     if (c->prof_on) CU(cudaEventRecord(c->ev_chain_e[slot], cs));
     CU(cudaEventRecord(c->ev_chain_done[slot], cs));

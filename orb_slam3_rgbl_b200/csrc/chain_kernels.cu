@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(kTlmThreads) tlm_prepare_kernel(FrameDev f, co
                                                                   const int* __restrict__ n_edges, const int* __restrict__ e_idx,
                                                                   const uint8_t* __restrict__ e_outlier, uint8_t* __restrict__ state,
                                                                   int* __restrict__ match_last, LocalQueriesDev lq, Lookback lb) {
+    pdl_wait(); pdl_trigger();
     __shared__ int s_wsum[kTlmThreads / 32];
     __shared__ int s_base;
     const int tid = threadIdx.x;
@@ -143,7 +144,7 @@ void launch_tlm_prepare(cudaStream_t st, const FrameDev& f, const float* pose, c
                         const int* e_idx, const uint8_t* e_outlier, uint8_t* state, int* match_last, const LocalQueriesDev& lq, int* lb, int* fail) {
     const int n_part = (ring.K * ring.cap + kTlmThreads - 1) / kTlmThreads;
     const Lookback l{lb, lb + kLbSlots, fail};
-    tlm_prepare_kernel<<<n_part + 1, kTlmThreads, 0, st>>>(f, pose, ring, cos_limit, n_edges, e_idx, e_outlier, state, match_last, lq, l);
+    launch_kernel(tlm_prepare_kernel, dim3(n_part + 1), dim3(kTlmThreads), 0, st, chain_launch_pdl(), f, pose, ring, cos_limit, n_edges, e_idx, e_outlier, state, match_last, lq, l);
 }
 
 }  // namespace rgbl

@@ -21,8 +21,6 @@
 
 namespace rgbl {
 
-bool& chain_launch_pdl() { static thread_local bool on = false; return on; }
-
 constexpr int kGridCells = kGridCols * kGridRows;
 constexpr int kThHigh = 100;          // ORBmatcher::TH_HIGH
 constexpr int kHistoLength = 30;      // ORBmatcher::HISTO_LENGTH
@@ -42,6 +40,13 @@ __device__ __forceinline__ unsigned rotation_bin(float q_angle, float f_angle) {
     if (b == 30) b = 0;
     return (unsigned)b & 0xffu;
 }
+// where a collect kernel writes the candidates of query q: entries + (parallel) the slot of each entry in its feature's inverse list
+struct ListOut {
+    MatchEntry* lists; uint16_t* slots; int list_cap; int* list_n;
+    int* inv_cnt;                    // per frame feature: entries listing it so far (global atomics here, many CTAs: the single-CTA resolution
+                                     // then builds its inverse index feature -> queries without any shared-memory atomic; zero between launches)
+    int* overflow;
+};
 constexpr int kListUnsorted = 1 << 30;        // flag in list_n[q]: the list is in scan order, not ascending by key (more than 32 candidates)
 constexpr int kListCountMask = kListUnsorted - 1;
 
@@ -141,8 +146,11 @@ template <class Filter>
 __device__ __forceinline__ int warp_collect(const FrameDev& f, const int* __restrict__ cell_start,
                                             const int* __restrict__ csr_idx, const CellRange cr, float x, float y,
                                             float r, int min_level, int max_level, const uint4 d0, const uint4 d1,
-                                            int keep_max, MatchEntry* __restrict__ list, int list_cap, Filter admit,
+                                            int keep_max, const ListOut& out, int q, Filter admit,
                                             bool want_bin = false, float q_angle = 0.f) {
+    MatchEntry* __restrict__ list = out.lists + (size_t)q * out.list_cap;
+    uint16_t* __restrict__ slots = out.slots + (size_t)q * out.list_cap;
+    const int list_cap = out.list_cap;
     const int lane = threadIdx.x & 31;
     const bool check_levels = (min_level > 0) || (max_level >= 0);
     int count = 0;
@@ -200,7 +208,7 @@ __device__ __forceinline__ int warp_collect(const FrameDev& f, const int* __rest
             const uint32_t m = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 const int o = count + __popc(m & ((1u << lane) - 1u));
-                if (o < list_cap) list[o] = key;
+                if (o < list_cap) { list[o] = key; slots[o] = (uint16_t)atomicAdd(&out.inv_cnt[ent_ft(key)], 1); }       // only stored entries count
             }
             count += __popc(m);
         }
@@ -210,26 +218,27 @@ __device__ __forceinline__ int warp_collect(const FrameDev& f, const int* __rest
 
 // The resolution reads a query's candidates best first (ascending key = distance, then scan position): called by the whole warp after
 // its list is complete, sorts lists of <= 32 keys in place by ranking (keys of one list are unique) and returns the value for list_n[q].
-__device__ __forceinline__ int warp_finish_list(MatchEntry* __restrict__ list, int count, int list_cap) {
-    const int n = min(count, list_cap);
+__device__ __forceinline__ int warp_finish_list(const ListOut& lo, int q, int count) {
+    MatchEntry* __restrict__ list = lo.lists + (size_t)q * lo.list_cap;
+    uint16_t* __restrict__ slots = lo.slots + (size_t)q * lo.list_cap;
+    const int n = min(count, lo.list_cap);
     if (n <= 1) return n;
     if (n > 32) return n | kListUnsorted;
     const int lane = threadIdx.x & 31;
     __syncwarp();                                       // the list was written by other lanes of this warp
     const MatchEntry k = lane < n ? list[lane] : ~0ull;
+    const uint16_t sl = lane < n ? slots[lane] : (uint16_t)0;
     int rank = 0;
     for (int j = 0; j < n; ++j) rank += (__shfl_sync(0xffffffffu, k, j) < k) ? 1 : 0;
     __syncwarp();
-    if (lane < n) list[rank] = k;
+    if (lane < n) { list[rank] = k; slots[rank] = sl; }
     return n;
 }
 
 // ---- SearchByProjection(CurrentFrame, LastFrame): candidate phase --------------------------------
 __global__ void __launch_bounds__(256) search_last_collect_kernel(FrameDev f, const int* __restrict__ cell_start,
                                                                   const int* __restrict__ csr_idx, LastFrameDev lf,
-                                                                  SearchLastParams prm, MatchEntry* __restrict__ lists,
-                                                                  int list_cap, int* __restrict__ list_n,
-                                                                  int* __restrict__ overflow) {
+                                                                  SearchLastParams prm, ListOut out) {
     pdl_wait(); pdl_trigger();
     const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= lf.n) return;
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(256) search_last_collect_kernel(FrameDev f, co
                 const float ur = __fsub_rn(u, __fmul_rn(f.bf, invzc));
                 const float* uright = f.uright;
                 count = warp_collect(f, cell_start, csr_idx, cr, u, v, radius, lo, hi, d0, d1, kThHigh,
-                                     lists + (size_t)q * list_cap, list_cap, [&](int idx) {
+                                     out, q, [&](int idx) {
                                          const float urt = uright[idx];
                                          if (urt > 0.f) { if (fabsf(__fsub_rn(ur, urt)) > radius) return false; }
                                          return true;
@@ -269,10 +278,10 @@ __global__ void __launch_bounds__(256) search_last_collect_kernel(FrameDev f, co
             }
         }
     }
-    const int ln = warp_finish_list(lists + (size_t)q * list_cap, count, list_cap);
+    const int ln = warp_finish_list(out, q, count);
     if (lane == 0) {
-        list_n[q] = ln;
-        if (count > list_cap) atomicExch(overflow, 3);
+        out.list_n[q] = ln;
+        if (count > out.list_cap) atomicExch(out.overflow, 3);
     }
 }
 
@@ -287,9 +296,7 @@ struct RingHandOverDev {
 
 __global__ void __launch_bounds__(256) search_local_collect_kernel(FrameDev f, const int* __restrict__ cell_start,
                                                                    const int* __restrict__ csr_idx, LocalPointsDev lp,
-                                                                   SearchLocalParams prm, MatchEntry* __restrict__ lists,
-                                                                   int list_cap, int* __restrict__ list_n,
-                                                                   int* __restrict__ overflow, RingHandOverDev ho) {
+                                                                   SearchLocalParams prm, ListOut out, RingHandOverDev ho) {
     pdl_wait(); pdl_trigger();
     if (ho.ring.valid) {
         const int j = blockIdx.x * 256 + threadIdx.x;
@@ -337,17 +344,17 @@ __global__ void __launch_bounds__(256) search_local_collect_kernel(FrameDev f, c
             const float xr = lp.proj_xr[q];
             const float* uright = f.uright;
             count = warp_collect(f, cell_start, csr_idx, cr, x, y, rad, pl - 1, pl, d0, d1, prm.keep_max,
-                                 lists + (size_t)q * list_cap, list_cap, [&](int idx) {
+                                 out, q, [&](int idx) {
                                      const float urt = uright[idx];
                                      if (urt > 0.f) { if (fabsf(__fsub_rn(xr, urt)) > rad) return false; }
                                      return true;
                                  });
         }
     }
-    const int ln = warp_finish_list(lists + (size_t)q * list_cap, count, list_cap);
+    const int ln = warp_finish_list(out, q, count);
     if (lane == 0) {
-        list_n[q] = ln;
-        if (count > list_cap) atomicExch(overflow, 3);
+        out.list_n[q] = ln;
+        if (count > out.list_cap) atomicExch(out.overflow, 3);
     }
 }
 
@@ -374,8 +381,7 @@ struct ChainTlmDev {
 };
 
 __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const int* __restrict__ n_q_dev, FrameDev f,
-                                                       const MatchEntry* __restrict__ lists, int list_cap,
-                                                       const int* __restrict__ list_n,
+                                                       ListOut lo,
                                                        const uint8_t* __restrict__ obs_pos,
                                                        const float* __restrict__ q_angle, float nn_ratio,
                                                        int check_orientation, int th_accept,
@@ -385,13 +391,16 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
                                                        int* __restrict__ n_matches, int* __restrict__ rounds_out, int dyn_bytes,
                                                        ChainEdgesDev ce, ChainTlmDev tl) {
     pdl_wait(); pdl_trigger();
+    const MatchEntry* __restrict__ lists = lo.lists;
+    const int list_cap = lo.list_cap;
+    const int* __restrict__ list_n = lo.list_n;
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int hist[kHistoLength];
     __shared__ int keep_bin[3];
     __shared__ int s_nm;
     __shared__ int s_wsum[32];
     __shared__ int s_total;
-    __shared__ int s_cnt[3];
+    __shared__ int s_cnt[2];
 #ifdef RESOLVE_DEBUG
 #endif
     const int tid = threadIdx.x;
@@ -432,7 +441,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
     }
     RQ(1);
     const int E = s_total;
-    const size_t need = (size_t)12 * (n_f + 1) + (size_t)4 * (n_q + 1) + (size_t)12 * (E + 4) + (size_t)12 * n_q + (size_t)n_f + (size_t)3 * n_q + 64;
+    const size_t need = (size_t)12 * (n_f + 1) + (size_t)4 * (n_q + 1) + (size_t)12 * (E + 4) + (size_t)12 * n_q + (size_t)n_f + (size_t)2 * n_q + 64;
     const bool on_chip = need <= (size_t)dyn_bytes;
     const bool orient = mode != 1 && check_orientation;
     int rounds = 0, nm_local = 0;          // nm_local: accepted minus rotation-rejected matches of this thread
@@ -442,7 +451,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
     if (on_chip) {
         unsigned long long* s_ent = reinterpret_cast<unsigned long long*>(dyn);
         int* s_ioff = reinterpret_cast<int*>(s_ent + E + 4);   // inverse index: the queries that list feature ft are s_iq[s_ioff[ft] .. s_ioff[ft + 1])
-        int* s_icur = s_ioff + n_f + 1;                  // per feature: entry count (fill), then the write cursor of the scatter pass
+        int* s_icur = s_ioff + n_f + 1;                  // per feature: entry count (from the collect kernel), later the lowest waiting lister
         int* s_iq = s_icur + n_f;
         int* s_match = s_iq + E + 4;
         int* s_off = s_match + n_f;
@@ -450,51 +459,25 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         int* s_list = s_choice + n_q;                    // two compact lists of waiting queries
         uint8_t* s_state = reinterpret_cast<uint8_t*>(s_list + 2 * (size_t)n_q);
         uint8_t* s_res = s_state + n_f;    // bit 0: resolved, bit 1: the query's point has observations, bit 2: list not sorted by key
-        uint8_t* s_stamp = s_res + n_q;    // 0: waiting, r + 1: became final in round r (ONE byte, so a reader sees "waiting" or the round, never a mix)
-        uint8_t* s_bin = s_stamp + n_q;
+        uint8_t* s_bin = s_res + n_q;
         ch = s_choice; bins = s_bin; mt = s_match;
         {
             int o = incl - mine;
             for (int q = qb; q < qe; ++q) { s_off[q] = o; o += list_n[q] & kListCountMask; }
             if (tid == 1023) s_off[n_q] = E;
         }
-        for (int i = tid; i < n_f; i += 1024) { s_state[i] = state[i]; s_match[i] = -1; s_icur[i] = 0; }
+        for (int i = tid; i < n_f; i += 1024) { s_state[i] = state[i]; s_match[i] = -1; s_icur[i] = lo.inv_cnt[i]; lo.inv_cnt[i] = 0; }      // the counts are clean for the next launch
         if (tid < 4) s_ent[E + tid] = 0xffffffff00000000ull;     // padding: worst key, feature 0
         __syncthreads();
         for (int q = tid; q < n_q; q += 1024) {
             const bool empty = s_off[q + 1] == s_off[q];
             s_res[q] = (uint8_t)((empty ? 1 : 0) | (obs_pos[q] ? 2 : 0) | ((list_n[q] & kListUnsorted) ? 4 : 0));
-            s_stamp[q] = empty ? 1 : 0;      // "final before round 0"
             s_choice[q] = -1;
         }
-        // one thread per ENTRY: the owning query is found by bisection of the offsets, the entry itself is ONE load - the collect
-        // kernels (many CTAs) already gathered feature index, octave and rotation bin; here, on a single SM, every dependent level
-        // of scattered global loads cost ~3 k cycles (measured: the three-level gather list -> csr -> keypoint was 9-15 k).
-        for (int en0 = tid; en0 < E; en0 += 4096) {
-            int qq[4]; MatchEntry ee[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int en = en0 + u * 1024;
-                int lo = 0, hi = n_q;                      // largest q with s_off[q] <= en
-                if (en < E) while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= en) lo = mid; else hi = mid; }
-                qq[u] = lo;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { const int en = en0 + u * 1024; ee[u] = (en < E) ? lists[(size_t)qq[u] * list_cap + (en - s_off[qq[u]])] : 0ull; }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int en = en0 + u * 1024;
-                if (en >= E) continue;
-                s_ent[en] = ee[u];
-                atomicAdd(&s_icur[ent_ft(ee[u])], 1);          // entries per feature, for the inverse index below
-            }
-        }
-        __syncthreads();
-        RQ(2);
-        // ---- inverse index feature -> queries.  The first formulation rebuilt a proposal table with one shared-memory atomicMin per
-        // entry in EVERY round; shared atomics on scattered addresses retire at 2 cycles per lane (measured: a round cost ~2 E cycles,
-        // 4-7 k).  The index is built once (a count in the fill loop, a scan over the features, one scatter pass) and a round is then
-        // reads only: "does a lower-index query that still waits list this feature".
+        // ---- inverse index feature -> queries (who lists this feature), built WITHOUT shared-memory atomics: the collect kernels counted
+        // the entries per feature with global atomics (many CTAs, negligible there) and gave every entry its slot; here a scan of the
+        // counts and one pass over the entries.  (Shared atomics on scattered addresses retire at 2 cycles per lane: the first formulation's
+        // per-round atomicMin proposals cost ~2 E cycles per round, an index built with them ~4 E.)
         {
             const int perf = (n_f + 1023) >> 10;
             const int fb_ = min(n_f, tid * perf), fe_ = min(n_f, fb_ + perf);
@@ -504,6 +487,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl_f, o); if (lane >= o) incl_f += t; }
+            __syncthreads();                                 // s_wsum is still read by the offsets scan above
             if (lane == 31) s_wsum[warp] = incl_f;
             __syncthreads();
             if (warp == 0) {
@@ -514,44 +498,58 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             }
             __syncthreads();
             int o = incl_f - mine_f + s_wsum[warp];
-            for (int i = fb_; i < fe_; ++i) { const int c = s_icur[i]; s_ioff[i] = o; s_icur[i] = o; o += c; }
-            if (tid == 1023) s_ioff[n_f] = E;
-            __syncthreads();
-            for (int q = tid; q < n_q; q += 1024) {          // scatter by QUERY: its entries are consecutive, the query index is known
-                const int e = s_off[q + 1];
-                for (int k = s_off[q]; k < e; ++k) s_iq[atomicAdd(&s_icur[ent_ft(s_ent[k])], 1)] = q;
-            }
+            for (int i = fb_; i < fe_; ++i) { s_ioff[i] = o; o += s_icur[i]; }
+            if (tid == 1023) s_ioff[n_f] = o;
             __syncthreads();
         }
-        RQ(5);
-        // phase 2: best (and second best) available candidate; final when no lower-index waiting query can still interfere.
-        // Returns true while the query has to wait for another round.
-        // A query's decision depends on its best and second-best AVAILABLE candidates only (the set of available candidates can only
-        // shrink until its turn, so if no lower-index waiting query proposes at those two they are still its best two then): with the
-        // list sorted by key the scan stops at the second available entry - typically after two or three of them; lists of more than 32
-        // candidates (left in scan order) are read to the end.  tests/test_resolution_model.py checks this rule against the sequential loops.
-        // `stamp_now` = round + 1: a query that became final in THIS round still counts as waiting for the others (decisions of a round are
-        // taken against the state of the waiting set at its start, like the proposal table of the first formulation)
-        auto lower_waiting = [&](int ft, int q, int stamp_now) -> bool {
-            const int e = s_ioff[ft + 1];
-            for (int k = s_ioff[ft]; k < e; ++k) {
-                const int o = s_iq[k];
-                if (o < q) { const int st = s_stamp[o]; if (st == 0 || st == stamp_now) return true; }
+        // one thread per ENTRY: the owning query is found by bisection of the offsets, the entry itself is ONE load (+ its slot) - the
+        // collect kernels already gathered feature index, octave and rotation bin; here, on a single SM, every dependent level of
+        // scattered global loads costs ~3 k cycles (measured: the three-level gather list -> csr -> keypoint was 9-15 k).
+        for (int en0 = tid; en0 < E; en0 += 4096) {
+            int qq[4]; MatchEntry ee[4]; int sl[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int en = en0 + u * 1024;
+                int lo_ = 0, hi = n_q;                      // largest q with s_off[q] <= en
+                if (en < E) while (hi - lo_ > 1) { const int mid = (lo_ + hi) >> 1; if (s_off[mid] <= en) lo_ = mid; else hi = mid; }
+                qq[u] = lo_;
             }
-            return false;
-        };
-        auto decide = [&](int q, int stamp_now) -> bool {
-            const uint8_t flags = s_res[q];
-            uint32_t best = 0xffffffffu, best2 = 0xffffffffu;
-            int lvl = -1, lvl2 = -1, fb = -1, bb = 0, fb2 = -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int en = en0 + u * 1024;
+                const size_t at = (size_t)qq[u] * list_cap + (en - s_off[qq[u]]);
+                ee[u] = (en < E) ? lists[at] : 0ull;
+                sl[u] = (en < E) ? (int)lo.slots[at] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int en = en0 + u * 1024;
+                if (en >= E) continue;
+                s_ent[en] = ee[u];
+                s_iq[s_ioff[ent_ft(ee[u])] + sl[u]] = qq[u];
+            }
+        }
+        __syncthreads();
+        RQ(2);
+        RQ(5);
+        // ---- rounds.  Phase A (thread per FEATURE): the lowest-index query that still waits among those listing the feature - what the
+        // atomicMin proposals of the first formulation computed, now a read-only walk over the feature's (short) inverse list.
+        // Phase B (thread per waiting QUERY): its best and second-best AVAILABLE candidates; the set of available candidates can only shrink
+        // until the query's turn, so if it is the lowest waiting lister of those two they are still its best two then and the decision
+        // is final (tests/test_resolution_model.py checks this rule against the sequential loops).  With the list sorted by key the scan
+        // stops at the second available entry; lists of more than 32 candidates (left in scan order) are read to the end.
+        int* s_minq = s_icur;                    // the scatter cursors are dead after the index is built
+        struct Pick { uint32_t best, best2; int lvl, lvl2, fb, fb2, bb; };
+        auto pick = [&](int q) -> Pick {         // reads only
+            Pick P{0xffffffffu, 0xffffffffu, -1, -1, -1, -1, 0};
             const int e = s_off[q + 1];
-            if (!(flags & 4)) {
+            if (!(s_res[q] & 4)) {
                 for (int k = s_off[q]; k < e; ++k) {
                     const MatchEntry en = s_ent[k];
                     const int ft = ent_ft(en);
                     if (s_state[ft] == 1) continue;
-                    if (fb < 0) { best = ent_key(en); fb = ft; bb = ent_bin(en); lvl = ent_oc(en); if (mode == 0) break; }
-                    else { best2 = ent_key(en); fb2 = ft; lvl2 = ent_oc(en); break; }
+                    if (P.fb < 0) { P.best = ent_key(en); P.fb = ft; P.bb = ent_bin(en); P.lvl = ent_oc(en); if (mode == 0) break; }
+                    else { P.best2 = ent_key(en); P.fb2 = ft; P.lvl2 = ent_oc(en); break; }
                 }
             } else {
                 for (int k = s_off[q]; k < e; ++k) {
@@ -560,43 +558,45 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
                     if (s_state[ft] == 1) continue;
                     const uint32_t key = ent_key(en);
                     const int oc = ent_oc(en);
-                    if (key < best) { best2 = best; lvl2 = lvl; fb2 = fb; best = key; lvl = oc; fb = ft; bb = ent_bin(en); }
-                    else if (key < best2) { best2 = key; lvl2 = oc; fb2 = ft; }
+                    if (key < P.best) { P.best2 = P.best; P.lvl2 = P.lvl; P.fb2 = P.fb; P.best = key; P.lvl = oc; P.fb = ft; P.bb = ent_bin(en); }
+                    else if (key < P.best2) { P.best2 = key; P.lvl2 = oc; P.fb2 = ft; }
                 }
-                if (mode == 0) { best2 = 0xffffffffu; fb2 = -1; }
+                if (mode == 0) { P.best2 = 0xffffffffu; P.fb2 = -1; }
             }
-            if (best == 0xffffffffu) { s_res[q] = flags | 1; s_stamp[q] = (uint8_t)stamp_now; return false; }
-            if (lower_waiting(fb, q, stamp_now) || (fb2 >= 0 && lower_waiting(fb2, q, stamp_now))) return true;
-            s_res[q] = flags | 1; s_stamp[q] = (uint8_t)stamp_now;
-            const int bd = (int)(best >> 20);
+            return P;
+        };
+        auto commit = [&](int q, const Pick& P) {    // the query is final: accept / reject tests and the state update
+            const uint8_t flags = s_res[q];
+            s_res[q] = flags | 1;
+            if (P.fb < 0) return;
+            const int bd = (int)(P.best >> 20);
             bool accept = bd <= th_accept;
             if (mode == 1 && accept) {
-                const int bd2 = (best2 == 0xffffffffu) ? 256 : (int)(best2 >> 20);
-                if (lvl == lvl2 && (float)bd > __fmul_rn(nn_ratio, (float)bd2)) accept = false;
+                const int bd2 = (P.best2 == 0xffffffffu) ? 256 : (int)(P.best2 >> 20);
+                if (P.lvl == P.lvl2 && (float)bd > __fmul_rn(nn_ratio, (float)bd2)) accept = false;
             }
             if (mode == 2 && accept) {            // SearchByBoW: bestDist1 < mfNNratio * bestDist2 (src/ORBmatcher.cc:324)
-                const int bd2 = (best2 == 0xffffffffu) ? 256 : (int)(best2 >> 20);
+                const int bd2 = (P.best2 == 0xffffffffu) ? 256 : (int)(P.best2 >> 20);
                 accept = (float)bd < __fmul_rn(nn_ratio, (float)bd2);
             }
             if (accept) {
-                s_choice[q] = fb; s_bin[q] = (uint8_t)bb;
-                // This write races with the state reads of other queries deciding in the same phase (compute-sanitizer
-                // racecheck reports it); it is benign: only 0/2 -> 1 matters to a reader, and a query q' that reads state[fb]
-                // has fb in its list, so it proposed there too and the winner q satisfies q < q'.  If q' sees the old value
-                // it waits one more round (q is a lower query listing fb that was waiting when the round began) and then sees 1; if it sees the new value it skips fb now,
-                // exactly what the sequential scan does after q took fb.  Either way q' ends with the same feature.
-                if (flags & 2) s_state[fb] = 1; else if (s_state[fb] == 0) s_state[fb] = 2;
+                s_choice[q] = P.fb; s_bin[q] = (uint8_t)P.bb;
+                atomicMax(&s_match[P.fb], q);            // owner of a feature = the last (highest-index) query that chose it
+                // In a block round this write races with the state reads of other queries deciding in the same phase (compute-sanitizer
+                // racecheck reports it); it is benign: only 0/2 -> 1 matters to a reader, and a query q' that reads state[fb] has fb in
+                // its list, and the winner q < q' was the lowest waiting lister of fb when the round began.  If q' sees the old value it
+                // waits one more round (s_minq[fb] = q != q') and then sees 1; if it sees the new value it skips fb now, exactly what
+                // the sequential scan does after q took fb.  Either way q' ends with the same feature.
+                if (flags & 2) s_state[P.fb] = 1; else if (s_state[P.fb] == 0) s_state[P.fb] = 2;
                 ++nm_local;
             }
-            return false;
         };
 
-        // Block rounds over a COMPACT list of the waiting queries (one barrier per round): a warp pays for its slowest lane, so with the
-        // waiting queries scattered over all 32 warps every warp would run the full decision in every round; packed, round r touches
-        // ceil(waiting / 32) warps.  Once <= 32 queries wait, warp 0 finishes alone with warp-level syncs.
+        // Block rounds over a COMPACT list of the waiting queries: a warp pays for its slowest lane, so with the waiting queries scattered
+        // over all 32 warps every warp would run the full decision in every round; packed, round r touches ceil(waiting / 32) warps.
         int cur = 0, n_act;
         {
-            if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; }
+            if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
             __syncthreads();
             for (int q0 = 0; q0 < n_q; q0 += 1024) {
                 const int q = q0 + tid;
@@ -610,50 +610,68 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             __syncthreads();
             n_act = s_cnt[0];
         }
-        int stamp = 2;                           // round r carries stamp r + 2 (1 = "final before the first round"); re-based before it reaches 255
-        auto rebase = [&](bool whole_block) {
-            if (stamp < 250) return;
-            if (whole_block) { for (int q = tid; q < n_q; q += 1024) if (s_stamp[q]) s_stamp[q] = 1; __syncthreads(); }
-            else { for (int q = tid; q < n_q; q += 32) if (s_stamp[q]) s_stamp[q] = 1; __syncwarp(); }
-            stamp = 2;
-        };
-        // Three rotating counters: round ri appends to s_cnt[(ri + 1) % 3] (zero since round ri - 1), everybody reads it after the barrier,
-        // and s_cnt[(ri + 2) % 3] - last read after the barrier of round ri - 2 - is cleared meanwhile: one barrier per round suffices.
-        for (int ri = 0; n_act > 32; ++ri) {
-            rebase(true);
+        while (n_act > 32) {
             const int* lst = s_list + (size_t)cur * n_q;
             int* lst_next = s_list + (size_t)(cur ^ 1) * n_q;
-            int* out_cnt = &s_cnt[(ri + 1) % 3];
-            if (tid == 0) s_cnt[(ri + 2) % 3] = 0;
-            for (int i0 = 0; i0 < n_act; i0 += 1024) {
+            if (tid == 0) s_cnt[cur ^ 1] = 0;
+            for (int ft = tid; ft < n_f; ft += 1024) {           // phase A
+                int m = 0x7fffffff;
+                if (s_state[ft] != 1) {
+                    const int e = s_ioff[ft + 1];
+                    for (int k = s_ioff[ft]; k < e; ++k) { const int o = s_iq[k]; if (!(s_res[o] & 1)) m = min(m, o); }
+                }
+                s_minq[ft] = m;
+            }
+            __syncthreads();
+            for (int i0 = 0; i0 < n_act; i0 += 1024) {           // phase B
                 const int i = i0 + tid;
                 const int q = i < n_act ? lst[i] : -1;
-                const bool w = q >= 0 && decide(q, stamp);
+                bool w = false;
+                if (q >= 0) {
+                    const Pick P = pick(q);
+                    w = P.fb >= 0 && (s_minq[P.fb] != q || (P.fb2 >= 0 && s_minq[P.fb2] != q));
+                    if (!w) commit(q, P);
+                }
                 const unsigned m = __ballot_sync(0xffffffffu, w);
                 int base = 0;
-                if ((tid & 31) == 0 && m) base = atomicAdd(out_cnt, __popc(m));
+                if ((tid & 31) == 0 && m) base = atomicAdd(&s_cnt[cur ^ 1], __popc(m));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (w) lst_next[base + __popc(m & ((1u << (tid & 31)) - 1u))] = q;
             }
-            ++rounds; ++stamp;
+            ++rounds;
             cur ^= 1;
             __syncthreads();
-            n_act = *out_cnt;
+            n_act = s_cnt[cur];
         }
         RQ(6);
 #ifdef RESOLVE_DEBUG
         dbg_block_rounds = rounds;
 #endif
+        // <= 32 waiting queries: warp 0 finishes alone.  A lane checks its (at most two) features' inverse lists itself; checks and commits
+        // of a round are separated by warp syncs, so every check sees the state the round began with.
         if (n_act > 0 && tid < 32) {
             int q = tid < n_act ? s_list[(size_t)cur * n_q + tid] : -1;
             for (;;) {
-                rebase(false);
                 bool waiting = false;
-                if (q >= 0) waiting = decide(q, stamp);
-                ++rounds; ++stamp;
-                if (!__any_sync(0xffffffffu, waiting)) break;
-                if (!waiting) q = -1;
+                Pick P{};
+                if (q >= 0) {
+                    P = pick(q);
+                    bool blocked = false;
+                    if (P.fb >= 0) {
+                        const int e = s_ioff[P.fb + 1];
+                        for (int k = s_ioff[P.fb]; k < e; ++k) { const int o = s_iq[k]; blocked |= (o < q) && !(s_res[o] & 1); }
+                    }
+                    if (P.fb2 >= 0) {
+                        const int e = s_ioff[P.fb2 + 1];
+                        for (int k = s_ioff[P.fb2]; k < e; ++k) { const int o = s_iq[k]; blocked |= (o < q) && !(s_res[o] & 1); }
+                    }
+                    waiting = blocked;
+                }
                 __syncwarp();
+                if (q >= 0 && !waiting) { commit(q, P); q = -1; }
+                ++rounds;
+                __syncwarp();
+                if (!__any_sync(0xffffffffu, waiting)) break;
             }
         }
         __syncthreads();
@@ -661,7 +679,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         for (int i = tid; i < n_f; i += 1024) state[i] = s_state[i];
         __syncthreads();
     } else {
-    for (int i = tid; i < n_f; i += 1024) match[i] = -1;
+    for (int i = tid; i < n_f; i += 1024) { match[i] = -1; lo.inv_cnt[i] = 0; }
     for (int q = tid; q < n_q; q += 1024) { choice[q] = -1; resolved[q] = ((list_n[q] & kListCountMask) == 0); }
     __syncthreads();
     for (;;) {
@@ -725,8 +743,8 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         if (!__syncthreads_or(any_unresolved)) break;
     }
     }
-    // owner of a feature = the last (highest-index) query that chose it
-    for (int q = tid; q < n_q; q += 1024) if (ch[q] >= 0) atomicMax(&mt[ch[q]], q);
+    // owner of a feature = the last (highest-index) query that chose it (the on-chip rounds record it when a query commits)
+    if (!on_chip) for (int q = tid; q < n_q; q += 1024) if (ch[q] >= 0) atomicMax(&mt[ch[q]], q);
     if (orient) {
         for (int b = tid; b < kHistoLength; b += 1024) hist[b] = 0;
         __syncthreads();
@@ -970,14 +988,15 @@ __global__ void __launch_bounds__(256) bow_collect_kernel(int n_q, const int* __
                                                           const int* __restrict__ q_cend, const uint8_t* __restrict__ kf_desc,
                                                           const uint8_t* __restrict__ f_desc, const int* __restrict__ f_node_feat,
                                                           const float* __restrict__ q_angle, const float* __restrict__ f_angle, int check_orientation,
-                                                          int keep_max, MatchEntry* __restrict__ lists, int list_cap,
-                                                          int* __restrict__ list_n, int* __restrict__ overflow) {
+                                                          int keep_max, ListOut out) {
     const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= n_q) return;
     const uint8_t* dq = kf_desc + (size_t)q_feat[q] * 32;
     const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(dq)), d1 = __ldg(reinterpret_cast<const uint4*>(dq) + 1);
     const int b = q_cbeg[q], e = q_cend[q];
-    MatchEntry* list = lists + (size_t)q * list_cap;
+    MatchEntry* list = out.lists + (size_t)q * out.list_cap;
+    uint16_t* slots = out.slots + (size_t)q * out.list_cap;
+    const int list_cap = out.list_cap;
     const float qa = check_orientation ? q_angle[q] : 0.f;
     int count = 0;
     for (int p0 = b; p0 < e; p0 += 32) {
@@ -987,22 +1006,23 @@ __global__ void __launch_bounds__(256) bow_collect_kernel(int n_q, const int* __
         if (p < e) {
             const int ft = f_node_feat[p];
             const int d = hamming256(d0, d1, f_desc + (size_t)ft * 32);
-            if (d <= keep_max) { keep = true; key = ent_make(((uint32_t)d << 20) | (uint32_t)p, check_orientation ? rotation_bin(qa, f_angle[ft]) : 0u, 0u, (unsigned)ft); }
+            if (d <= keep_max) {
+                keep = true;
+                key = ent_make(((uint32_t)d << 20) | (uint32_t)p, check_orientation ? rotation_bin(qa, f_angle[ft]) : 0u, 0u, (unsigned)ft);
+            }
         }
         const uint32_t m = __ballot_sync(0xffffffffu, keep);
-        if (keep) { const int o = count + __popc(m & ((1u << lane) - 1u)); if (o < list_cap) list[o] = key; }
+        if (keep) { const int o = count + __popc(m & ((1u << lane) - 1u)); if (o < list_cap) { list[o] = key; slots[o] = (uint16_t)atomicAdd(&out.inv_cnt[ent_ft(key)], 1); } }
         count += __popc(m);
     }
-    const int ln = warp_finish_list(lists + (size_t)q * list_cap, count, list_cap);
-    if (lane == 0) { list_n[q] = ln; if (count > list_cap) atomicExch(overflow, 3); }
+    const int ln = warp_finish_list(out, q, count);
+    if (lane == 0) { out.list_n[q] = ln; if (count > out.list_cap) atomicExch(out.overflow, 3); }
 }
 
 // ---- SearchByProjection(CurrentFrame, KeyFrame, sAlreadyFound, th, ORBdist): candidate phase -------------------------
 __global__ void __launch_bounds__(256) search_reloc_collect_kernel(FrameDev f, const int* __restrict__ cell_start,
                                                                    const int* __restrict__ csr_idx, RelocPointsDev rp,
-                                                                   SearchRelocParams prm, MatchEntry* __restrict__ lists,
-                                                                   int list_cap, int* __restrict__ list_n,
-                                                                   int* __restrict__ overflow) {
+                                                                   SearchRelocParams prm, ListOut out) {
     const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= rp.n) return;
     int count = 0;
@@ -1028,13 +1048,13 @@ __global__ void __launch_bounds__(256) search_reloc_collect_kernel(FrameDev f, c
                     const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(rp.desc + (size_t)q * 32));
                     const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(rp.desc + (size_t)q * 32) + 1);
                     count = warp_collect(f, cell_start, csr_idx, cr, u, v, radius, pl - 1, pl + 1, d0, d1, prm.orb_dist,
-                                         lists + (size_t)q * list_cap, list_cap, [](int) { return true; }, prm.check_orientation != 0, rp.angle[q]);
+                                         out, q, [](int) { return true; }, prm.check_orientation != 0, rp.angle[q]);
                 }
             }
         }
     }
-    const int ln = warp_finish_list(lists + (size_t)q * list_cap, count, list_cap);
-    if (lane == 0) { list_n[q] = ln; if (count > list_cap) atomicExch(overflow, 3); }
+    const int ln = warp_finish_list(out, q, count);
+    if (lane == 0) { out.list_n[q] = ln; if (count > out.list_cap) atomicExch(out.overflow, 3); }
 }
 
 // ---- resident tracking chain (TrackWithMotionModel-style glue between the reference functions) ----------------
@@ -1080,8 +1100,8 @@ void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_star
                         const ChainEdgesOut* edges) {
     if (lf.n <= 0) return;
     const bool pdl = chain_launch_pdl();
-    launch_kernel(search_last_collect_kernel, dim3((lf.n + 7) / 8), dim3(256), 0, st, pdl, f, cell_start, csr_idx, lf, prm, s.lists, s.list_cap, s.list_n, s.overflow);
-    launch_kernel(resolve_kernel, dim3(1), dim3(1024), (size_t)resolve_dyn_bytes(), st, pdl, 0, lf.n, (const int*)nullptr, f, s.lists, s.list_cap, s.list_n, lf.obs_pos, lf.angle, 0.f,
+    launch_kernel(search_last_collect_kernel, dim3((lf.n + 7) / 8), dim3(256), 0, st, pdl, f, cell_start, csr_idx, lf, prm, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow});
+    launch_kernel(resolve_kernel, dim3(1), dim3(1024), (size_t)resolve_dyn_bytes(), st, pdl, 0, lf.n, (const int*)nullptr, f, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow}, lf.obs_pos, lf.angle, 0.f,
                                        prm.check_orientation, kThHigh, (const float*)nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(),
                                        edges ? ChainEdgesDev{f.keys, f.uright, lf.xw, edges->exw, edges->eobs, edges->einfo, edges->est, edges->eidx, edges->n_edges} : ChainEdgesDev{}, ChainTlmDev{});
 }
@@ -1094,14 +1114,14 @@ void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_sta
     const int n_q_cta = (lp.n + 7) / 8, n_ho_cta = tail ? (tail->ring.cap + 255) / 256 : 0;
     const int n_cta = n_q_cta > n_ho_cta ? n_q_cta : n_ho_cta;
     const bool pdl = chain_launch_pdl();
-    launch_kernel(search_local_collect_kernel, dim3(n_cta), dim3(256), 0, st, pdl, f, cell_start, csr_idx, lp, prm, s.lists, s.list_cap, s.list_n, s.overflow, ho);
+    launch_kernel(search_local_collect_kernel, dim3(n_cta), dim3(256), 0, st, pdl, f, cell_start, csr_idx, lp, prm, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow}, ho);
     ChainEdgesDev ce{};
     ChainTlmDev tl{};
     if (tail) {
         ce = ChainEdgesDev{f.keys, f.uright, tail->last_xw, tail->edges.exw, tail->edges.eobs, tail->edges.einfo, tail->edges.est, tail->edges.eidx, tail->edges.n_edges};
         tl = ChainTlmDev{tail->match_last, tail->lq_xw, tail->ring.count, tail->n_local_matches};
     }
-    launch_kernel(resolve_kernel, dim3(1), dim3(1024), (size_t)resolve_dyn_bytes(), st, pdl, 1, lp.n, lp.n_dev, f, s.lists, s.list_cap, s.list_n, lp.obs_pos, (const float*)nullptr, prm.nn_ratio,
+    launch_kernel(resolve_kernel, dim3(1), dim3(1024), (size_t)resolve_dyn_bytes(), st, pdl, 1, lp.n, lp.n_dev, f, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow}, lp.obs_pos, (const float*)nullptr, prm.nn_ratio,
                                        0, kThHigh, (const float*)nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ce, tl);
 }
 
@@ -1110,17 +1130,17 @@ void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q
                        float nn_ratio, int keep_max, int check_orientation, const uint8_t* obs_pos, MatchScratch s, uint8_t* state, int* match,
                        int* n_matches) {
     if (n_q <= 0) return;
-    bow_collect_kernel<<<(n_q + 7) / 8, 256, 0, st>>>(n_q, q_feat, q_cbeg, q_cend, kf_desc, f_desc, f_node_feat, q_angle, f_angle, check_orientation, keep_max, s.lists, s.list_cap,
-                                                    s.list_n, s.overflow);
-    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(2, n_q, nullptr, f, s.lists, s.list_cap, s.list_n, obs_pos, q_angle, nn_ratio,
+    bow_collect_kernel<<<(n_q + 7) / 8, 256, 0, st>>>(n_q, q_feat, q_cbeg, q_cend, kf_desc, f_desc, f_node_feat, q_angle, f_angle, check_orientation, keep_max,
+                                                    ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow});
+    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(2, n_q, nullptr, f, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow}, obs_pos, q_angle, nn_ratio,
                                        check_orientation, 50 /* TH_LOW */, f_angle, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{}, ChainTlmDev{});
 }
 
 void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const RelocPointsDev& rp,
                          const SearchRelocParams& prm, const uint8_t* obs_pos, MatchScratch s, uint8_t* state, int* match, int* n_matches) {
     if (rp.n <= 0) return;
-    search_reloc_collect_kernel<<<(rp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, rp, prm, s.lists, s.list_cap, s.list_n, s.overflow);
-    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, rp.n, nullptr, f, s.lists, s.list_cap, s.list_n, obs_pos, rp.angle, 0.f,
+    search_reloc_collect_kernel<<<(rp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, rp, prm, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow});
+    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, rp.n, nullptr, f, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow}, obs_pos, rp.angle, 0.f,
                                        prm.check_orientation, prm.orb_dist, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{}, ChainTlmDev{});
 }
 

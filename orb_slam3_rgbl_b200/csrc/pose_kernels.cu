@@ -329,11 +329,13 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
     __shared__ __align__(8) unsigned long long xchg_mbar[2];
     __shared__ double s_tot[2];
     __shared__ float s_posef[7];
+    pdl_trigger();                        // the next kernel of the chain may be scheduled (it waits for this grid's completion itself)
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
     ClusterXchg xc{xchg_buf, xchg_mbar, rank, 0u};
     xc.init();
     cluster.sync();                       // every CTA's mbarriers are initialised before anyone sends
+    pdl_wait();                           // everything above is on-chip set-up and overlaps the tail of the previous kernel; global memory from here on
     __shared__ Se3d s_est, s_init, s_cand[kMaxTrials];
     __shared__ double s_cinv[kMaxTrials], s_lambda, s_ni, s_current, s_ini;
     __shared__ int s_cache_ok, s_nbad_lm, s_ok, s_cok[kMaxTrials], s_continue;
@@ -652,7 +654,7 @@ void launch_pose_optimize(cudaStream_t st, const PoseProblemDev& p, double* work
         static const cudaError_t opt_in = cudaFuncSetAttribute(pose_optimize_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         (void)opt_in;
     }
-    pose_optimize_kernel<<<kPoseCtas, kPoseThreads, 0, st>>>(p, work, level, outlier, pose_out, n_inliers, next ? *next : ChainPrepDev{});
+    launch_kernel(pose_optimize_kernel, dim3(kPoseCtas), dim3(kPoseThreads), 0, st, chain_launch_pdl(), p, work, level, outlier, pose_out, n_inliers, next ? *next : ChainPrepDev{});
 }
 
 }  // namespace rgbl

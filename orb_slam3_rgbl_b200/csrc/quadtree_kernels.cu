@@ -1,6 +1,7 @@
 // Device quad-tree distribution (one CTA per (frame, level)) + packing of the per-level survivor lists into the
 // per-frame SelKp list the describe kernel consumes.  Algorithm: quadtree_block.cuh.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -48,7 +49,13 @@ __global__ void __launch_bounds__(512) quadtree_kernel(const uint32_t* __restric
     }
     uint32_t* out = sel_lvl + (size_t)f * cap_kp + lvl_region[l];
     const int region_cap = lvl_region[l + 1] - lvl_region[l];
+#ifdef QT_TIMING
+    const long long qt_t0 = clock64();
+#endif
     const int m = qt::distribute(s, dense + off, n, lg.max_bx - lg.min_bx, lg.max_by - lg.min_by, lg.quota, g, out, region_cap, block_sort);
+#ifdef QT_TIMING
+    if (threadIdx.x == 0 && f == 0) printf("quadtree level %d: n=%d quota=%d selected=%d keys_on_chip=%d cycles=%lld\n", l, n, lg.quota, m, (int)(sizeof(qt::Shared) + key_bytes <= (size_t)dyn_bytes), clock64() - qt_t0);
+#endif
     if (threadIdx.x == 0) {
         if (m < 0 || m > region_cap) { atomicExch(status, 1); n_sel_lvl[f * RGBL_MAX_LEVELS + l] = 0; }
         else n_sel_lvl[f * RGBL_MAX_LEVELS + l] = m;

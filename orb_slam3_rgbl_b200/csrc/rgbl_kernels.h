@@ -121,12 +121,14 @@ struct RelocPointsDev { int n; const uint8_t* valid; const float* xw; const uint
 struct SearchRelocParams { float cur_pose[7]; float Ow[3]; float th; int orb_dist, check_orientation; };
 struct FrustumParams { float Rcw[9], tcw[3], Ow[3], cos_limit; };
 struct MatchScratch { unsigned long long* lists;      // 64-bit candidate entries (match_kernels.cu: MatchEntry)
-                       int list_cap; int* list_n; int* minq; int* choice; uint8_t* resolved; int* overflow; int* rounds; };
+                       int list_cap; int* list_n; int* minq; int* choice; uint8_t* resolved; int* overflow; int* rounds;
+                      uint16_t* slots;                 // per entry: its slot in the inverse list of its feature
+                      int* inv_cnt; };                 // per frame feature: entries so far; ZERO between launches (resolve_kernel clears what it read)
 
 void prepare_match_kernels();
 // true while the resident chain enqueues its kernels: the chain launchers then add the programmatic-stream-serialization attribute (PDL, see
 // pdl_wait in rgbl_device.cuh).  Thread-local, set and cleared by chain_begin (api_track.cu).
-bool& chain_launch_pdl();
+inline bool& chain_launch_pdl() { static thread_local bool on = false; return on; }
 // kernel launch with or without that attribute
 template <class... KArgs, class... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {

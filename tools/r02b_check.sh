@@ -25,6 +25,10 @@ except Exception as e:
     print("bench parse failed", e)
 EOF
 fi
+if [ "${AB_PDL:-0}" = "1" ]; then
+  RGBL_CHAIN_PDL=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-bow --multi-sequences 0 > "$out/bench_nopdl.json" 2>/dev/null
+  python -c "import json,sys; d=json.loads(open('$out/bench_nopdl.json').read().strip().splitlines()[-1]); print('RGBL_CHAIN_PDL=0: value', round(d['value'],1), 'chain us/frame', round(d['tracking_chain']['us_per_frame'],1))"
+fi
 RGBL_CHAIN_TIMING=1 timeout 300 python tools/run_chain_tlm.py 8 > "$out/chain_timing.log" 2>&1; echo "chain timing exit $?"; grep "chain timing" "$out/chain_timing.log" | tail -6
 if [ -f tools/dbg/librgbl_b200_dbg.so ]; then
   cp orb_slam3_rgbl_b200/librgbl_b200.so /tmp/librgbl_b200.so.keep

@@ -35,8 +35,8 @@ static int ensure_frame(Ctx* c, int n_frame) {
     GROW(t.keys, t.cap_keys, n_frame); GROW(t.uright, t.cap_uright, n_frame); GROW(t.desc, t.cap_desc, (size_t)n_frame * 32);
     GROW(t.csr_idx, t.cap_csr, n_frame); GROW(t.kp_cell, t.cap_kpcell, n_frame); GROW(t.state, t.cap_state, n_frame);
     GROW(t.match, t.cap_match, n_frame); GROW(t.minq, t.cap_minq, n_frame);
-    if ((size_t)n_frame > t.cap_inv_cnt) {                    // per-feature entry counters of the collect kernels: zero between launches
-        GROW(t.inv_cnt, t.cap_inv_cnt, n_frame);
+    if ((size_t)n_frame + 1 > t.cap_inv_cnt) {                // per-feature entry counters of the collect kernels + the entry total ([cap - 1]): zero between launches
+        GROW(t.inv_cnt, t.cap_inv_cnt, n_frame + 1);
         CU(cudaMemsetAsync(t.inv_cnt, 0, t.cap_inv_cnt * sizeof(int), c->st));
     }
     GROW(t.cell_start, t.cap_cellstart, kGridCols * kGridRows + 1);
@@ -47,6 +47,8 @@ static int ensure_frame(Ctx* c, int n_frame) {
 static int ensure_queries(Ctx* c, int n_q) {
     TrackBufs& t = c->trk;
     GROW(t.lists, t.cap_lists, (size_t)n_q * kMatchListCap); GROW(t.list_slots, t.cap_list_slots, (size_t)n_q * kMatchListCap); GROW(t.list_n, t.cap_listn, n_q);
+    GROW(t.dense, t.cap_dense, (size_t)n_q * kMatchListCap); GROW(t.dense_slot, t.cap_dense_slot, (size_t)n_q * kMatchListCap);
+    GROW(t.dense_q, t.cap_dense_q, (size_t)n_q * kMatchListCap); GROW(t.list_base, t.cap_list_base, n_q);
     GROW(t.choice, t.cap_choice, n_q); GROW(t.resolved, t.cap_resolved, n_q);
     GROW(t.q_u8a, t.cap_q_u8a, n_q); GROW(t.q_u8b, t.cap_q_u8b, n_q); GROW(t.q_desc, t.cap_q_desc, (size_t)n_q * 32);
     GROW(t.q_f3a, t.cap_q_f3a, (size_t)n_q * 3); GROW(t.q_f3b, t.cap_q_f3b, (size_t)n_q * 3);
@@ -87,7 +89,8 @@ static MatchScratch scratch(Ctx* c) {
     TrackBufs& t = c->trk;
     MatchScratch s;
     s.lists = t.lists; s.list_cap = kMatchListCap; s.list_n = t.list_n; s.minq = t.minq; s.choice = t.choice; s.resolved = t.resolved;
-    s.overflow = c->d_overflow; s.rounds = t.scalars + 2; s.slots = t.list_slots; s.inv_cnt = t.inv_cnt;
+    s.overflow = c->d_overflow; s.rounds = t.scalars + 2; s.slots = t.list_slots; s.inv_cnt = t.inv_cnt; s.total = t.inv_cnt + (t.cap_inv_cnt - 1);
+    s.dense = t.dense; s.dense_slot = t.dense_slot; s.dense_q = t.dense_q; s.base = t.list_base;
     return s;
 }
 

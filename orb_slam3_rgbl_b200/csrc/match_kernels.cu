@@ -42,7 +42,11 @@ __device__ __forceinline__ unsigned rotation_bin(float q_angle, float f_angle) {
 }
 // where a collect kernel writes the candidates of query q: entries + (parallel) the slot of each entry in its feature's inverse list
 struct ListOut {
-    MatchEntry* lists; uint16_t* slots; int list_cap; int* list_n;
+    MatchEntry* lists; uint16_t* slots; int list_cap; int* list_n;      // per-query staging lists (list_cap entries each) while a query's candidates are collected
+    // ... and the finished lists of ALL queries appended to one dense run (entry, slot, owning query): what the single-CTA resolution reads,
+    // coalesced - its share of the L2 bandwidth is one SM's, and 2-4 k scattered sectors cost it ~10 k cycles.  total = entries so far
+    // (zero between launches), base[q] = where query q's list starts.
+    MatchEntry* dense; uint16_t* dense_slot; int* dense_q; int* base; int* total;
     int* inv_cnt;                    // per frame feature: entries listing it so far (global atomics here, many CTAs: the single-CTA resolution
                                      // then builds its inverse index feature -> queries without any shared-memory atomic; zero between launches)
     int* overflow;
@@ -222,16 +226,25 @@ __device__ __forceinline__ int warp_finish_list(const ListOut& lo, int q, int co
     MatchEntry* __restrict__ list = lo.lists + (size_t)q * lo.list_cap;
     uint16_t* __restrict__ slots = lo.slots + (size_t)q * lo.list_cap;
     const int n = min(count, lo.list_cap);
-    if (n <= 1) return n;
-    if (n > 32) return n | kListUnsorted;
+    if (n == 0) return 0;
     const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) { base = atomicAdd(lo.total, n); lo.base[q] = base; }
+    base = __shfl_sync(0xffffffffu, base, 0);
     __syncwarp();                                       // the list was written by other lanes of this warp
+    if (n > 32) {                                       // left in scan order (flagged), copied as it is
+        for (int i = lane; i < n; i += 32) { lo.dense[base + i] = list[i]; lo.dense_slot[base + i] = slots[i]; lo.dense_q[base + i] = q; }
+        return n | kListUnsorted;
+    }
     const MatchEntry k = lane < n ? list[lane] : ~0ull;
     const uint16_t sl = lane < n ? slots[lane] : (uint16_t)0;
     int rank = 0;
     for (int j = 0; j < n; ++j) rank += (__shfl_sync(0xffffffffu, k, j) < k) ? 1 : 0;
     __syncwarp();
-    if (lane < n) { list[rank] = k; slots[rank] = sl; }
+    if (lane < n) {
+        list[rank] = k; slots[rank] = sl;               // the staging list stays valid (sorted): the global-memory fallback of the resolution reads it
+        lo.dense[base + rank] = k; lo.dense_slot[base + rank] = sl; lo.dense_q[base + rank] = q;
+    }
     return n;
 }
 
@@ -416,32 +429,11 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
 
     // ---- working set into shared memory: the rounds below are a chain of barriers around short dependent loads, so their
     // cost is the latency of those loads; with the candidate entries (key, feature, octave), the feature states and the
-    // proposal table on chip a round costs a few hundred cycles instead of several L2 round trips.  Exclusive scan of the
-    // list lengths -> entry offsets; falls back to the global-memory rounds when the problem does not fit.
-    const int per = (n_q + 1023) >> 10;
-    const int qb = min(n_q, tid * per), qe = min(n_q, qb + per);
-    int mine = 0;
-    for (int q = qb; q < qe; ++q) mine += list_n[q] & kListCountMask;
-    int incl = mine;
-    {
-        const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int v = s_wsum[lane], w = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-            s_wsum[lane] = w - v;
-            if (lane == 31) s_total = w;
-        }
-        __syncthreads();
-        incl += s_wsum[warp];
-    }
+    // lowest-lister table on chip a round costs a few hundred cycles instead of several L2 round trips.  Falls back to the global-memory
+    // rounds when the problem does not fit.
+    const int E = *lo.total;              // entries of all queries (appended to one dense run by the collect kernel); cleared below for the next launch
     RQ(1);
-    const int E = s_total;
-    const size_t need = (size_t)12 * (n_f + 1) + (size_t)4 * (n_q + 1) + (size_t)12 * (E + 4) + (size_t)12 * n_q + (size_t)n_f + (size_t)2 * n_q + 64;
+    const size_t need = (size_t)12 * (n_f + 1) + (size_t)4 * (n_q + 1) + (size_t)12 * (E + 4) + (size_t)12 * n_q + (size_t)n_f + (size_t)2 * n_q + (size_t)4 * n_q + 64;
     const bool on_chip = need <= (size_t)dyn_bytes;
     const bool orient = mode != 1 && check_orientation;
     int rounds = 0, nm_local = 0;          // nm_local: accepted minus rotation-rejected matches of this thread
@@ -454,26 +446,33 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         int* s_icur = s_ioff + n_f + 1;                  // per feature: entry count (from the collect kernel), later the lowest waiting lister
         int* s_iq = s_icur + n_f;
         int* s_match = s_iq + E + 4;
-        int* s_off = s_match + n_f;
-        int* s_choice = s_off + n_q + 1;
+        int* s_off = s_match + n_f;                      // query q's entries are s_ent[s_off[q] .. s_end[q])
+        int* s_end = s_off + n_q + 1;
+        int* s_choice = s_end + n_q;
         int* s_list = s_choice + n_q;                    // two compact lists of waiting queries
         uint8_t* s_state = reinterpret_cast<uint8_t*>(s_list + 2 * (size_t)n_q);
         uint8_t* s_res = s_state + n_f;    // bit 0: resolved, bit 1: the query's point has observations, bit 2: list not sorted by key
         uint8_t* s_bin = s_res + n_q;
         ch = s_choice; bins = s_bin; mt = s_match;
-        {
-            int o = incl - mine;
-            for (int q = qb; q < qe; ++q) { s_off[q] = o; o += list_n[q] & kListCountMask; }
-            if (tid == 1023) s_off[n_q] = E;
+        // The set-up below is a handful of phases separated by barriers; what it reads from global memory does not depend on any of them, so
+        // every load is ISSUED here, before the first barrier (the first 4 k entries of the dense run stay in registers until the inverse
+        // offsets exist): the whole set-up then pays two rounds of global latency (the total, everything else) instead of one per phase.
+        MatchEntry pe_[4]; int ps_[4], pq_[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int en = tid + u * 1024;
+            pe_[u] = (en < E) ? lo.dense[en] : 0ull; ps_[u] = (en < E) ? (int)lo.dense_slot[en] : 0; pq_[u] = (en < E) ? lo.dense_q[en] : 0;
         }
         for (int i = tid; i < n_f; i += 1024) { s_state[i] = state[i]; s_match[i] = -1; s_icur[i] = lo.inv_cnt[i]; lo.inv_cnt[i] = 0; }      // the counts are clean for the next launch
         if (tid < 4) s_ent[E + tid] = 0xffffffff00000000ull;     // padding: worst key, feature 0
-        __syncthreads();
         for (int q = tid; q < n_q; q += 1024) {
-            const bool empty = s_off[q + 1] == s_off[q];
-            s_res[q] = (uint8_t)((empty ? 1 : 0) | (obs_pos[q] ? 2 : 0) | ((list_n[q] & kListUnsorted) ? 4 : 0));
+            const int ln = list_n[q], cnt = ln & kListCountMask, b0 = lo.base[q];          // (base of an empty list is never used)
+            s_off[q] = b0; s_end[q] = b0 + cnt;
+            s_res[q] = (uint8_t)((cnt == 0 ? 1 : 0) | (obs_pos[q] ? 2 : 0) | ((ln & kListUnsorted) ? 4 : 0));
             s_choice[q] = -1;
         }
+        __syncthreads();                                     // everybody has read the entry total
+        if (tid == 0) *lo.total = 0;
         // ---- inverse index feature -> queries (who lists this feature), built WITHOUT shared-memory atomics: the collect kernels counted
         // the entries per feature with global atomics (many CTAs, negligible there) and gave every entry its slot; here a scan of the
         // counts and one pass over the entries.  (Shared atomics on scattered addresses retire at 2 cycles per lane: the first formulation's
@@ -498,36 +497,20 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             }
             __syncthreads();
             int o = incl_f - mine_f + s_wsum[warp];
-            for (int i = fb_; i < fe_; ++i) { s_ioff[i] = o; o += s_icur[i]; }
+            for (int i = fb_; i < fe_; ++i) { s_ioff[i] = o; o += s_icur[i]; s_icur[i] = -1; }      // the count is consumed: the slot becomes the 'lowest waiting lister' cache (-1 = unknown)
             if (tid == 1023) s_ioff[n_f] = o;
             __syncthreads();
         }
-        // one thread per ENTRY: the owning query is found by bisection of the offsets, the entry itself is ONE load (+ its slot) - the
-        // collect kernels already gathered feature index, octave and rotation bin; here, on a single SM, every dependent level of
-        // scattered global loads costs ~3 k cycles (measured: the three-level gather list -> csr -> keypoint was 9-15 k).
-        for (int en0 = tid; en0 < E; en0 += 4096) {
-            int qq[4]; MatchEntry ee[4]; int sl[4];
+        // one thread per ENTRY of the dense run: entry, slot and owning query are three coalesced loads
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int en = en0 + u * 1024;
-                int lo_ = 0, hi = n_q;                      // largest q with s_off[q] <= en
-                if (en < E) while (hi - lo_ > 1) { const int mid = (lo_ + hi) >> 1; if (s_off[mid] <= en) lo_ = mid; else hi = mid; }
-                qq[u] = lo_;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int en = en0 + u * 1024;
-                const size_t at = (size_t)qq[u] * list_cap + (en - s_off[qq[u]]);
-                ee[u] = (en < E) ? lists[at] : 0ull;
-                sl[u] = (en < E) ? (int)lo.slots[at] : 0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int en = en0 + u * 1024;
-                if (en >= E) continue;
-                s_ent[en] = ee[u];
-                s_iq[s_ioff[ent_ft(ee[u])] + sl[u]] = qq[u];
-            }
+        for (int u = 0; u < 4; ++u) {
+            const int en = tid + u * 1024;
+            if (en < E) { s_ent[en] = pe_[u]; s_iq[s_ioff[ent_ft(pe_[u])] + ps_[u]] = pq_[u]; }
+        }
+        for (int en = tid + 4096; en < E; en += 1024) {
+            const MatchEntry e = lo.dense[en];
+            s_ent[en] = e;
+            s_iq[s_ioff[ent_ft(e)] + lo.dense_slot[en]] = lo.dense_q[en];
         }
         __syncthreads();
         RQ(2);
@@ -538,21 +521,57 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         // until the query's turn, so if it is the lowest waiting lister of those two they are still its best two then and the decision
         // is final (tests/test_resolution_model.py checks this rule against the sequential loops).  With the list sorted by key the scan
         // stops at the second available entry; lists of more than 32 candidates (left in scan order) are read to the end.
-        int* s_minq = s_icur;                    // the scatter cursors are dead after the index is built
+        int* s_minq = s_icur;                    // the counts are dead after the index is built
+        // lowest-index query that still waits among the listers of ft (0x7fffffff: none).  The waiting set only shrinks, so a cached lister
+        // that still waits is still the lowest: the inverse list is walked again only when the cached one has become final (kDead: nobody
+        // waits for this feature any more, or it is taken for good).  Call only where nobody writes s_res concurrently.
+        constexpr int kDead = -2;
+        auto lowest_waiting = [&](int ft) -> int {
+            const int c = s_minq[ft];
+            if (c == kDead) return 0x7fffffff;
+            if (c >= 0 && !(s_res[c] & 1)) return c;
+            int m = 0x7fffffff;
+            const int e = s_ioff[ft + 1];
+            for (int k = s_ioff[ft]; k < e; ++k) { const int o = s_iq[k]; if (!(s_res[o] & 1)) m = min(m, o); }
+            s_minq[ft] = (m == 0x7fffffff) ? kDead : m;
+            return m;
+        };
         struct Pick { uint32_t best, best2; int lvl, lvl2, fb, fb2, bb; };
         auto pick = [&](int q) -> Pick {         // reads only
             Pick P{0xffffffffu, 0xffffffffu, -1, -1, -1, -1, 0};
-            const int e = s_off[q + 1];
+            const int k0 = s_off[q], e = s_end[q];
             if (!(s_res[q] & 4)) {
-                for (int k = s_off[q]; k < e; ++k) {
-                    const MatchEntry en = s_ent[k];
-                    const int ft = ent_ft(en);
-                    if (s_state[ft] == 1) continue;
-                    if (P.fb < 0) { P.best = ent_key(en); P.fb = ft; P.bb = ent_bin(en); P.lvl = ent_oc(en); if (mode == 0) break; }
-                    else { P.best2 = ent_key(en); P.fb2 = ft; P.lvl2 = ent_oc(en); break; }
+                // The first four entries at once, branch-free: the two best available candidates are almost always among them, and a
+                // data-dependent loop here makes the 32 lanes of a warp take 32 different paths (measured: ~4 k cycles per round for ANY
+                // number of waiting queries).  The loop below only continues where four entries were not enough.
+                MatchEntry en[4]; uint8_t st[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) en[u] = s_ent[k0 + u];                       // s_ent is padded: reading past a short list is harmless
+#pragma unroll
+                for (int u = 0; u < 4; ++u) st[u] = (k0 + u < e) ? s_state[ent_ft(en[u])] : (uint8_t)1;
+                int found = 0, first = e;                // first: position of the first available entry
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool av = st[u] != 1;
+                    if (av && found == 0) { P.best = ent_key(en[u]); P.fb = ent_ft(en[u]); P.bb = ent_bin(en[u]); P.lvl = ent_oc(en[u]); first = k0 + u; }
+                    if (av && found == 1) { P.best2 = ent_key(en[u]); P.fb2 = ent_ft(en[u]); P.lvl2 = ent_oc(en[u]); }
+                    found += av ? 1 : 0;
                 }
+                const int want = (mode == 0) ? 1 : 2;
+                for (int k = k0 + 4; found < want && k < e; ++k) {
+                    const MatchEntry x = s_ent[k];
+                    const int ft = ent_ft(x);
+                    if (s_state[ft] == 1) continue;
+                    if (found == 0) { P.best = ent_key(x); P.fb = ft; P.bb = ent_bin(x); P.lvl = ent_oc(x); first = k; }
+                    else { P.best2 = ent_key(x); P.fb2 = ft; P.lvl2 = ent_oc(x); }
+                    ++found;
+                }
+                // a taken feature stays taken: the entries before the first available one never matter again (the queries that wait
+                // longest are the contested ones, whose best candidates went to lower indices - without this they re-walk them every round)
+                if (first > k0) s_off[q] = first;
+                if (mode == 0) { P.best2 = 0xffffffffu; P.fb2 = -1; P.lvl2 = -1; }
             } else {
-                for (int k = s_off[q]; k < e; ++k) {
+                for (int k = k0; k < e; ++k) {
                     const MatchEntry en = s_ent[k];
                     const int ft = ent_ft(en);
                     if (s_state[ft] == 1) continue;
@@ -610,19 +629,24 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             __syncthreads();
             n_act = s_cnt[0];
         }
+#ifdef RESOLVE_DEBUG
+        long long tr_[24]; int na_[8]; int nr_ = 0;
+#endif
         while (n_act > 32) {
+#ifdef RESOLVE_DEBUG
+            if (nr_ < 8) { tr_[3 * nr_] = clock64(); na_[nr_] = n_act; }
+#endif
             const int* lst = s_list + (size_t)cur * n_q;
             int* lst_next = s_list + (size_t)(cur ^ 1) * n_q;
             if (tid == 0) s_cnt[cur ^ 1] = 0;
             for (int ft = tid; ft < n_f; ft += 1024) {           // phase A
-                int m = 0x7fffffff;
-                if (s_state[ft] != 1) {
-                    const int e = s_ioff[ft + 1];
-                    for (int k = s_ioff[ft]; k < e; ++k) { const int o = s_iq[k]; if (!(s_res[o] & 1)) m = min(m, o); }
-                }
-                s_minq[ft] = m;
+                if (s_minq[ft] == kDead) continue;
+                if (s_state[ft] == 1) s_minq[ft] = kDead; else (void)lowest_waiting(ft);
             }
             __syncthreads();
+#ifdef RESOLVE_DEBUG
+            if (nr_ < 8) tr_[3 * nr_ + 1] = clock64();
+#endif
             for (int i0 = 0; i0 < n_act; i0 += 1024) {           // phase B
                 const int i = i0 + tid;
                 const int q = i < n_act ? lst[i] : -1;
@@ -641,8 +665,14 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
             ++rounds;
             cur ^= 1;
             __syncthreads();
+#ifdef RESOLVE_DEBUG
+            if (nr_ < 8) { tr_[3 * nr_ + 2] = clock64(); ++nr_; }
+#endif
             n_act = s_cnt[cur];
         }
+#ifdef RESOLVE_DEBUG
+        if (tid == 0) for (int r_ = 0; r_ < nr_; ++r_) printf("  block round %d: waiting %d  phase A %lld  phase B %lld\n", r_, na_[r_], tr_[3 * r_ + 1] - tr_[3 * r_], tr_[3 * r_ + 2] - tr_[3 * r_ + 1]);
+#endif
         RQ(6);
 #ifdef RESOLVE_DEBUG
         dbg_block_rounds = rounds;
@@ -656,16 +686,7 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
                 Pick P{};
                 if (q >= 0) {
                     P = pick(q);
-                    bool blocked = false;
-                    if (P.fb >= 0) {
-                        const int e = s_ioff[P.fb + 1];
-                        for (int k = s_ioff[P.fb]; k < e; ++k) { const int o = s_iq[k]; blocked |= (o < q) && !(s_res[o] & 1); }
-                    }
-                    if (P.fb2 >= 0) {
-                        const int e = s_ioff[P.fb2 + 1];
-                        for (int k = s_ioff[P.fb2]; k < e; ++k) { const int o = s_iq[k]; blocked |= (o < q) && !(s_res[o] & 1); }
-                    }
-                    waiting = blocked;
+                    waiting = (P.fb >= 0 && lowest_waiting(P.fb) < q) || (P.fb2 >= 0 && lowest_waiting(P.fb2) < q);
                 }
                 __syncwarp();
                 if (q >= 0 && !waiting) { commit(q, P); q = -1; }
@@ -679,6 +700,8 @@ __global__ void __launch_bounds__(1024) resolve_kernel(int mode, int n_q, const 
         for (int i = tid; i < n_f; i += 1024) state[i] = s_state[i];
         __syncthreads();
     } else {
+    __syncthreads();
+    if (tid == 0) *lo.total = 0;
     for (int i = tid; i < n_f; i += 1024) { match[i] = -1; lo.inv_cnt[i] = 0; }
     for (int q = tid; q < n_q; q += 1024) { choice[q] = -1; resolved[q] = ((list_n[q] & kListCountMask) == 0); }
     __syncthreads();
@@ -1100,8 +1123,8 @@ void launch_search_last(cudaStream_t st, const FrameDev& f, const int* cell_star
                         const ChainEdgesOut* edges) {
     if (lf.n <= 0) return;
     const bool pdl = chain_launch_pdl();
-    launch_kernel(search_last_collect_kernel, dim3((lf.n + 7) / 8), dim3(256), 0, st, pdl, f, cell_start, csr_idx, lf, prm, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow});
-    launch_kernel(resolve_kernel, dim3(1), dim3(1024), (size_t)resolve_dyn_bytes(), st, pdl, 0, lf.n, (const int*)nullptr, f, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow}, lf.obs_pos, lf.angle, 0.f,
+    launch_kernel(search_last_collect_kernel, dim3((lf.n + 7) / 8), dim3(256), 0, st, pdl, f, cell_start, csr_idx, lf, prm, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.dense, s.dense_slot, s.dense_q, s.base, s.total, s.inv_cnt, s.overflow});
+    launch_kernel(resolve_kernel, dim3(1), dim3(1024), (size_t)resolve_dyn_bytes(), st, pdl, 0, lf.n, (const int*)nullptr, f, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.dense, s.dense_slot, s.dense_q, s.base, s.total, s.inv_cnt, s.overflow}, lf.obs_pos, lf.angle, 0.f,
                                        prm.check_orientation, kThHigh, (const float*)nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(),
                                        edges ? ChainEdgesDev{f.keys, f.uright, lf.xw, edges->exw, edges->eobs, edges->einfo, edges->est, edges->eidx, edges->n_edges} : ChainEdgesDev{}, ChainTlmDev{});
 }
@@ -1114,14 +1137,14 @@ void launch_search_local(cudaStream_t st, const FrameDev& f, const int* cell_sta
     const int n_q_cta = (lp.n + 7) / 8, n_ho_cta = tail ? (tail->ring.cap + 255) / 256 : 0;
     const int n_cta = n_q_cta > n_ho_cta ? n_q_cta : n_ho_cta;
     const bool pdl = chain_launch_pdl();
-    launch_kernel(search_local_collect_kernel, dim3(n_cta), dim3(256), 0, st, pdl, f, cell_start, csr_idx, lp, prm, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow}, ho);
+    launch_kernel(search_local_collect_kernel, dim3(n_cta), dim3(256), 0, st, pdl, f, cell_start, csr_idx, lp, prm, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.dense, s.dense_slot, s.dense_q, s.base, s.total, s.inv_cnt, s.overflow}, ho);
     ChainEdgesDev ce{};
     ChainTlmDev tl{};
     if (tail) {
         ce = ChainEdgesDev{f.keys, f.uright, tail->last_xw, tail->edges.exw, tail->edges.eobs, tail->edges.einfo, tail->edges.est, tail->edges.eidx, tail->edges.n_edges};
         tl = ChainTlmDev{tail->match_last, tail->lq_xw, tail->ring.count, tail->n_local_matches};
     }
-    launch_kernel(resolve_kernel, dim3(1), dim3(1024), (size_t)resolve_dyn_bytes(), st, pdl, 1, lp.n, lp.n_dev, f, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow}, lp.obs_pos, (const float*)nullptr, prm.nn_ratio,
+    launch_kernel(resolve_kernel, dim3(1), dim3(1024), (size_t)resolve_dyn_bytes(), st, pdl, 1, lp.n, lp.n_dev, f, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.dense, s.dense_slot, s.dense_q, s.base, s.total, s.inv_cnt, s.overflow}, lp.obs_pos, (const float*)nullptr, prm.nn_ratio,
                                        0, kThHigh, (const float*)nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ce, tl);
 }
 
@@ -1131,16 +1154,16 @@ void launch_search_bow(cudaStream_t st, const FrameDev& f, int n_q, const int* q
                        int* n_matches) {
     if (n_q <= 0) return;
     bow_collect_kernel<<<(n_q + 7) / 8, 256, 0, st>>>(n_q, q_feat, q_cbeg, q_cend, kf_desc, f_desc, f_node_feat, q_angle, f_angle, check_orientation, keep_max,
-                                                    ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow});
-    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(2, n_q, nullptr, f, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow}, obs_pos, q_angle, nn_ratio,
+                                                    ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.dense, s.dense_slot, s.dense_q, s.base, s.total, s.inv_cnt, s.overflow});
+    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(2, n_q, nullptr, f, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.dense, s.dense_slot, s.dense_q, s.base, s.total, s.inv_cnt, s.overflow}, obs_pos, q_angle, nn_ratio,
                                        check_orientation, 50 /* TH_LOW */, f_angle, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{}, ChainTlmDev{});
 }
 
 void launch_search_reloc(cudaStream_t st, const FrameDev& f, const int* cell_start, const int* csr_idx, const RelocPointsDev& rp,
                          const SearchRelocParams& prm, const uint8_t* obs_pos, MatchScratch s, uint8_t* state, int* match, int* n_matches) {
     if (rp.n <= 0) return;
-    search_reloc_collect_kernel<<<(rp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, rp, prm, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow});
-    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, rp.n, nullptr, f, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.inv_cnt, s.overflow}, obs_pos, rp.angle, 0.f,
+    search_reloc_collect_kernel<<<(rp.n + 7) / 8, 256, 0, st>>>(f, cell_start, csr_idx, rp, prm, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.dense, s.dense_slot, s.dense_q, s.base, s.total, s.inv_cnt, s.overflow});
+    resolve_kernel<<<1, 1024, resolve_dyn_bytes(), st>>>(0, rp.n, nullptr, f, ListOut{s.lists, s.slots, s.list_cap, s.list_n, s.dense, s.dense_slot, s.dense_q, s.base, s.total, s.inv_cnt, s.overflow}, obs_pos, rp.angle, 0.f,
                                        prm.check_orientation, prm.orb_dist, nullptr, state, s.minq, s.choice, s.resolved, match, n_matches, s.rounds, resolve_dyn_bytes(), ChainEdgesDev{}, ChainTlmDev{});
 }
 

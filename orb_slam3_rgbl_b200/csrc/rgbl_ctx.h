@@ -30,7 +30,10 @@ struct TrackBufs {
     int* scalars = nullptr; size_t cap_scalars = 0;
     unsigned long long* lists = nullptr; size_t cap_lists = 0;
     uint16_t* list_slots = nullptr; size_t cap_list_slots = 0;
-    int* inv_cnt = nullptr; size_t cap_inv_cnt = 0;
+    int* inv_cnt = nullptr; size_t cap_inv_cnt = 0;           // + 1: the entry total of the dense run (both zero between launches)
+    unsigned long long* dense = nullptr; size_t cap_dense = 0;
+    uint16_t* dense_slot = nullptr; size_t cap_dense_slot = 0;
+    int *dense_q = nullptr, *list_base = nullptr; size_t cap_dense_q = 0, cap_list_base = 0;
     int* list_n = nullptr; size_t cap_listn = 0;
     int* choice = nullptr; size_t cap_choice = 0;
     uint8_t* resolved = nullptr; size_t cap_resolved = 0;
@@ -67,7 +70,7 @@ struct TrackBufs {
     int *bw_i = nullptr; size_t cap_bw_i = 0;            // f_word | f_node | bow_word | fv_node | fv_start | fv_feature | scratch | counts
     double* bw_d = nullptr; size_t cap_bw_d = 0;         // f_weight | bow_value
     void release() {
-        void* all[] = {list_slots, inv_cnt, keys, uright, desc, csr_idx, kp_cell, cell_start, state, match, minq, scalars, lists, list_n, choice, resolved,
+        void* all[] = {list_slots, inv_cnt, dense, dense_slot, dense_q, list_base, keys, uright, desc, csr_idx, kp_cell, cell_start, state, match, minq, scalars, lists, list_n, choice, resolved,
                        q_u8a, q_u8b, q_desc, q_f3a, q_f3b, q_f[0], q_f[1], q_f[2], q_f[3], q_f[4], q_f[5], q_f[6], q_i, pose_work, ch_poses, ch_counts, e_xw, e_obs, e_info, e_st, e_lvl, e_out, e_idx,
                        s_kps, s_desc, s_depth, s_uright, s_nsel, b_cell_start, b_csr_idx, b_kp_cell, bw_i, bw_d,
                        c_kps, c_desc, c_depth, c_misc, r_valid, r_desc, r_xw, r_normal, r_min, r_max, lq_u8, lq_desc, lq_f, lq_i, match_local, lookback};

@@ -120,10 +120,13 @@ struct SearchLocalParams { float th, nn_ratio, th_far; int use_factor, far_point
 struct RelocPointsDev { int n; const uint8_t* valid; const float* xw; const uint8_t* desc; const float* angle; const float *mf_min, *mf_max; };
 struct SearchRelocParams { float cur_pose[7]; float Ow[3]; float th; int orb_dist, check_orientation; };
 struct FrustumParams { float Rcw[9], tcw[3], Ow[3], cos_limit; };
-struct MatchScratch { unsigned long long* lists;      // 64-bit candidate entries (match_kernels.cu: MatchEntry)
-                       int list_cap; int* list_n; int* minq; int* choice; uint8_t* resolved; int* overflow; int* rounds;
-                      uint16_t* slots;                 // per entry: its slot in the inverse list of its feature
-                      int* inv_cnt; };                 // per frame feature: entries so far; ZERO between launches (resolve_kernel clears what it read)
+struct MatchScratch {                 // device scratch of the matchers (match_kernels.cu)
+    unsigned long long* lists; uint16_t* slots; int list_cap; int* list_n;     // per-query staging lists: 64-bit entries (MatchEntry) + inverse-list slots
+    unsigned long long* dense; uint16_t* dense_slot; int* dense_q; int* base;   // all finished lists appended to one run, base[q] = start of query q
+    int* total;                      // entries in the run: ZERO between launches (resolve_kernel clears it)
+    int* inv_cnt;                    // per frame feature: entries listing it: ZERO between launches (resolve_kernel clears what it read)
+    int* minq; int* choice; uint8_t* resolved; int* overflow; int* rounds;
+};
 
 void prepare_match_kernels();
 // true while the resident chain enqueues its kernels: the chain launchers then add the programmatic-stream-serialization attribute (PDL, see

@@ -37,6 +37,34 @@ def se3f_inverse(pose):
     return q, se3f_rotate(q, nt)[0]
 
 
+def se3f_mul(a, b):
+    """Sophus::SE3f * SE3f (se3.hpp:304-308): (Ra Rb, ta + Ra tb).  SO3f * SO3f is the Hamilton product written out in so3.hpp:325-339,
+    evaluated left to right in float32, and its result goes through the SO3f(quaternion) constructor, which normalises (so3.hpp:481-487,
+    297-303: coeffs /= norm, Eigen's 4-term reduction (x2 + y2) + (z2 + w2)).  Poses are (qx, qy, qz, qw, tx, ty, tz) float32."""
+    ax, ay, az, aw = (f32(v) for v in a[:4]); bx, by, bz, bw = (f32(v) for v in b[:4])
+    w = f32(f32(f32(aw * bw) - f32(ax * bx)) - f32(ay * by)) - f32(az * bz)
+    x = f32(f32(f32(aw * bx) + f32(ax * bw)) + f32(ay * bz)) - f32(az * by)
+    y = f32(f32(f32(aw * by) + f32(ay * bw)) + f32(az * bx)) - f32(ax * bz)
+    z = f32(f32(f32(aw * bz) + f32(az * bw)) + f32(ax * by)) - f32(ay * bx)
+    q = np.array([x, y, z, w], f32)
+    length = np.sqrt(f32(f32(q[0] * q[0]) + f32(q[1] * q[1])) + f32(f32(q[2] * q[2]) + f32(q[3] * q[3])))
+    q = (q / f32(length)).astype(f32)
+    t = (np.asarray(a[4:7], f32) + se3f_rotate(np.asarray(a[:4], f32), np.asarray(b[4:7], f32)[None, :])[0]).astype(f32)
+    return np.concatenate([q, t]).astype(f32)
+
+
+def predict_pose(prev_pose, last_pose):
+    """Tracking::TrackWithMotionModel's initial pose mVelocity * mLastFrame.GetPose() (src/Tracking.cc:2904) with the constant-velocity
+    model mVelocity = Tcw(last) * Tcw(prev)^-1 (src/Tracking.cc:2243-2245).  prev_pose None (no velocity yet, the reference then tracks
+    against the reference key frame): the last pose itself."""
+    last_pose = np.asarray(last_pose, f32)
+    if prev_pose is None:
+        return last_pose
+    qi, ti = se3f_inverse(np.asarray(prev_pose, f32))
+    velocity = se3f_mul(last_pose, np.concatenate([qi, ti]).astype(f32))
+    return se3f_mul(velocity, last_pose)
+
+
 def quat_to_matrix_f32(q):
     """Eigen QuaternionBase::toRotationMatrix in float32 (Geometry/Quaternion.h)."""
     x, y, z, w = (f32(v) for v in q)
@@ -71,16 +99,17 @@ def oracle_chain(frames, sf, pose0, W, H, cam, th=15.0):
     for t in range(1, len(frames)):
         last, cur = frames[t - 1], frames[t]
         lp = poses[-1]
+        pred = predict_pose(poses[-2] if len(poses) >= 2 else None, lp)
         xw, ok = chain_unproject(last, lp, cam)
         fv = oracle.FrameView(*frame_view_args(cur, sf, W, H, cam))
-        nm, match = oracle.search_by_projection_last(fv, lp, lp, ok.astype(np.uint8), xw, last["d"], last["k"]["octave"], last["k"]["angle"],
+        nm, match = oracle.search_by_projection_last(fv, pred, lp, ok.astype(np.uint8), xw, last["d"], last["k"]["octave"], last["k"]["angle"],
                                                      np.ones(len(ok), np.uint8), th)
         m = np.nonzero(match >= 0)[0]
         obs = np.stack([cur["k"]["x"][m], cur["k"]["y"][m], cur["ur"][m]], 1).astype(f32)
         s = sf[cur["k"]["octave"][m]]
         inv_s2 = (f32(1.0) / (s * s).astype(f32)).astype(f32)
         st = (cur["ur"][m] >= 0).astype(np.uint8)
-        ni, pose, _ = oracle.pose_optimize(lp, xw[match[m]], obs, inv_s2, st, *cam)
+        ni, pose, _ = oracle.pose_optimize(pred, xw[match[m]], obs, inv_s2, st, *cam)
         poses.append(pose); nms.append(nm); nis.append(ni)
     return np.stack(poses), np.array(nms), np.array(nis)
 
@@ -119,17 +148,18 @@ def oracle_chain2(frames, sf, pose0, W, H, cam, K=3, th_last=15.0, th_local=3.0,
     next batch (continue_sequence).  -> (poses, n_matches, n_inliers, n_local_matches, n_inliers_first, state)"""
     if state is None:
         ring = [None] * max(K, 1); count = 0
-        last, last_pose = frames[0], np.asarray(pose0, f32)
+        last, last_pose, prev_pose = frames[0], np.asarray(pose0, f32), None
         poses, out = [last_pose], [(0, 0, 0, 0)]
         todo = frames[1:]
     else:
-        ring, count, last, last_pose = state["ring"], state["count"], state["last"], state["pose"]
+        ring, count, last, last_pose, prev_pose = state["ring"], state["count"], state["last"], state["pose"], state.get("prev_pose")
         poses, out = [], []
         todo = frames
     for cur in todo:
         xw, ok = chain_unproject(last, last_pose, cam)
+        pred = predict_pose(prev_pose, last_pose)                       # constant-velocity motion model
         fv = oracle.FrameView(*frame_view_args(cur, sf, W, H, cam))
-        nm, match = oracle.search_by_projection_last(fv, last_pose, last_pose, ok.astype(np.uint8), xw, last["d"], last["k"]["octave"], last["k"]["angle"],
+        nm, match = oracle.search_by_projection_last(fv, pred, last_pose, ok.astype(np.uint8), xw, last["d"], last["k"]["octave"], last["k"]["angle"],
                                                      np.ones(len(ok), np.uint8), th_last)
         m = np.nonzero(match >= 0)[0]
 
@@ -138,7 +168,7 @@ def oracle_chain2(frames, sf, pose0, W, H, cam, K=3, th_last=15.0, th_local=3.0,
             s = sf[cur["k"]["octave"][idx]]
             return pts, obs, (f32(1.0) / (s * s).astype(f32)).astype(f32), (cur["ur"][idx] >= 0).astype(np.uint8)
 
-        ni1, pose1, outl = oracle.pose_optimize(last_pose, *edges(m, xw[match[m]]), *cam)
+        ni1, pose1, outl = oracle.pose_optimize(pred, *edges(m, xw[match[m]]), *cam)
         if K == 0:
             pose2, ni2, nml = pose1, ni1, 0
         else:
@@ -160,8 +190,8 @@ def oracle_chain2(frames, sf, pose0, W, H, cam, K=3, th_last=15.0, th_local=3.0,
             ni2, pose2, _ = oracle.pose_optimize(pose1, *edges(idx, pts), *cam)
             ring[count % K] = local_points_of(last, last_pose, sf, cam); count += 1      # the last frame's points join the local map
         poses.append(pose2); out.append((nm, ni2, nml, ni1))
-        last, last_pose = cur, pose2
+        last, prev_pose, last_pose = cur, last_pose, pose2
     o = np.array(out, np.int64).reshape(-1, 4)
-    return np.stack(poses), o[:, 0], o[:, 1], o[:, 2], o[:, 3], dict(ring=ring, count=count, last=last, pose=last_pose)
+    return np.stack(poses), o[:, 0], o[:, 1], o[:, 2], o[:, 3], dict(ring=ring, count=count, last=last, pose=last_pose, prev_pose=prev_pose)
 
 

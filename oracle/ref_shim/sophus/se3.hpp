@@ -4,7 +4,7 @@
 //   SO3(quaternion) normalises: coeffs /= norm            so3.hpp:481-487, 297-303
 //   SO3(R) = Quaternion(R), no normalisation               so3.hpp:469-474
 //   SO3::inverse() = SO3(conjugate) (normalises again)     so3.hpp:229-231
-//   SO3 * SO3 explicit Hamilton product, no normalisation  so3.hpp:325-339 (operator*= normalises only through the ctor: not used here)
+//   SO3 * SO3 explicit Hamilton product -> SO3(quaternion) so3.hpp:325-339 (the product is handed to the normalising constructor, :481-487)
 //   SO3 * point = p + w*uv + vec x uv, uv = 2 (vec x p)    so3.hpp:358-367
 //   SE3(q, t), SE3(R, t), SE3(so3, t)                      se3.hpp:466-490
 //   SE3::inverse() = (invR, invR * (t * -1))               se3.hpp:208-211
@@ -40,7 +40,7 @@ public:
         return SO3(Eigen::Quaternion<T>(a.w() * b.w() - a.x() * b.x() - a.y() * b.y() - a.z() * b.z(),
                                         a.w() * b.x() + a.x() * b.w() + a.y() * b.z() - a.z() * b.y(),
                                         a.w() * b.y() + a.y() * b.w() + a.z() * b.x() - a.x() * b.z(),
-                                        a.w() * b.z() + a.z() * b.w() + a.x() * b.y() - a.y() * b.x()), Raw());
+                                        a.w() * b.z() + a.z() * b.w() + a.x() * b.y() - a.y() * b.x()));
     }
     template <class D> Vector3<T> operator*(const Eigen::MatrixBase<D>& p) const {
         const Vector3<T> qv = q_.vec();

@@ -521,12 +521,12 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
     TrackBufs& t = c->trk;
     const size_t tot = (size_t)nF * cap;
     GROW(t.pose_work, t.cap_pose_work, (size_t)cap * 3);
-    GROW(t.ch_poses, t.cap_ch_poses, (size_t)nF * 7 + 7); GROW(t.ch_counts, t.cap_ch_counts, n_counts);
+    GROW(t.ch_poses, t.cap_ch_poses, (size_t)nF * 7 + 14); GROW(t.ch_counts, t.cap_ch_counts, n_counts);      // poses | pose after TrackWithMotionModel | predicted pose
     GROW(t.e_xw, t.cap_e_xw, (size_t)cap * 3); GROW(t.e_obs, t.cap_e_obs, (size_t)cap * 3); GROW(t.e_info, t.cap_e_info, cap);
     GROW(t.e_st, t.cap_e_st, cap); GROW(t.e_lvl, t.cap_e_lvl, cap); GROW(t.e_out, t.cap_e_out, cap); GROW(t.e_idx, t.cap_e_idx, cap);
     // carried last frame of the sequence + the local map ring (persist across chains of this context)
     GROW(t.c_kps, t.cap_c_kps, cap); GROW(t.c_desc, t.cap_c_desc, (size_t)cap * 32); GROW(t.c_depth, t.cap_c_depth, cap);
-    GROW(t.c_misc, t.cap_c_misc, 16);                     // int n_sel | float pose[7] (as raw 32-bit words) | ring count
+    GROW(t.c_misc, t.cap_c_misc, 16);                     // int n_sel | float pose[7] (as raw 32-bit words) | ring count | float prev_pose[7]
     if (K > 0) {
         const size_t nr = (size_t)K * cap;
         if (cont && (t.cap_r_valid < nr)) { c->err = "local map ring missing"; return RGBL_E_INVALID; }
@@ -577,6 +577,8 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
     int* c_nsel = reinterpret_cast<int*>(t.c_misc);
     float* c_pose = reinterpret_cast<float*>(t.c_misc) + 1;
     int* r_count = reinterpret_cast<int*>(t.c_misc) + 8;
+    float* c_prev = reinterpret_cast<float*>(t.c_misc) + 9;      // pose of the frame before the carried one (valid: c->carry_prev_valid)
+    const bool prev_valid = cont && c->carry_prev_valid;
     int n_launches = 0;
     // Everything the chain does on the tracking stream.  It is captured ONCE per slot into a CUDA graph and
     // replayed: the launch commands then live in device memory, so the dependent-kernel sequence no longer fetches a command
@@ -586,6 +588,7 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
         n_launches = 0;
         float* poses = t.ch_poses;                 // frame k -> poses + 7 k
         float* pose_tmp = t.ch_poses + 7 * (size_t)nF;      // pose after TrackWithMotionModel (input of the second PoseOptimization)
+        float* pose_pred = pose_tmp + 7;                    // the motion model's pose of the frame being tracked (written when the previous frame's pose is final)
         CU(cudaMemsetAsync(t.ch_counts, 0, n_counts * sizeof(int), cs));
         if (!cont) {
             CU(cudaMemcpyAsync(poses, h_f, 7 * sizeof(float), cudaMemcpyHostToDevice, cs));
@@ -613,6 +616,11 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
             else { cp.kps = s_kps + (size_t)j * cap; cp.depth = s_depth + (size_t)j * cap; cp.n_ptr = s_nsel + j; }
             cp.fx = f.fx; cp.fy = f.fy; cp.cx = f.cx; cp.cy = f.cy; cp.mb = f.mb; cp.mono = mono; cp.cap = cap;
             cp.valid = t.q_u8a; cp.xw = t.q_f3a; cp.octave = t.q_i; cp.angle = t.q_f[0]; cp.obs_pos = t.q_u8b; cp.flags = d_flags; cp.state_clear = t.state;
+            // constant-velocity motion model: the pose of the frame before frame j (nullptr at the start of a sequence)
+            if (j >= 1) cp.prev_pose = poses + 7 * (size_t)(j - 1);
+            else if (j == 0) cp.prev_pose = cont ? c_pose : nullptr;
+            else cp.prev_pose = prev_valid ? c_prev : nullptr;
+            cp.pred_pose = pose_pred;
             return cp;
         };
         LocalRingDev ring{K, cap, t.r_valid, t.r_xw, t.r_normal, t.r_min, t.r_max, t.r_desc, r_count};
@@ -629,19 +637,19 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
             const float* last_pose = (k == 0) ? c_pose : poses + 7 * (size_t)(k - 1);
             const uint8_t* last_desc = (k == 0) ? t.c_desc : s_desc + (size_t)(k - 1) * cap * 32;
             if (tm) cudaEventRecord(tev[0], cs);
-            if (k == k0) { launch_chain_prep(cs, prep_of(k - 1), last_pose, last_pose); ++n_launches; }   // later frames: prepared by the previous pose kernel
+            if (k == k0) { launch_chain_prep(cs, prep_of(k - 1), last_pose); ++n_launches; }   // later frames: prepared by the previous pose kernel
             f.n = s_nsel + k; f.keys = s_kps + cu; f.uright = s_uright + cu; f.desc = s_desc + cu * 32;
             const int* cell_start = b_cell_start + (size_t)k * (kGridCols * kGridRows + 1);
             const int* csr_idx = b_csr_idx + cu;
             if (tm) cudaEventRecord(tev[1], cs);
             SearchLastParams prm{};
-            prm.th = th; prm.check_orientation = 1; prm.cur_pose_dev = last_pose; prm.flags_dev = d_flags;
+            prm.th = th; prm.check_orientation = 1; prm.cur_pose_dev = pose_pred; prm.flags_dev = d_flags;      // projected with the motion model's pose (src/Tracking.cc:2904)
             LastFrameDev lf{cap, t.q_u8a, t.q_f3a, last_desc, t.q_i, t.q_f[0], t.q_u8b};
             const ChainEdgesOut eo{t.e_xw, t.e_obs, t.e_info, t.e_st, t.e_idx, d_ne};
             launch_search_last(cs, f, cell_start, csr_idx, lf, prm, ms, t.state, t.match, d_nm + k, &eo); n_launches += 2;   // + edges of the matches
             if (tm) cudaEventRecord(tev[2], cs);
             PoseProblemDev p{};
-            p.n = 0; p.n_dev = d_ne; p.pose_in_dev = last_pose;
+            p.n = 0; p.n_dev = d_ne; p.pose_in_dev = pose_pred;
             p.xw = t.e_xw; p.obs = t.e_obs; p.inv_sigma2 = t.e_info; p.stereo = t.e_st;
             p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.bf = bf;
             const ChainPrepDev nxt = prep_of(k);
@@ -674,6 +682,9 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
         CU(cudaMemcpyAsync(t.c_desc, s_desc + lo * 32, (size_t)cap * 32, cudaMemcpyDeviceToDevice, cs));
         CU(cudaMemcpyAsync(t.c_depth, s_depth + lo, (size_t)cap * sizeof(float), cudaMemcpyDeviceToDevice, cs));
         CU(cudaMemcpyAsync(c_nsel, s_nsel + (nF - 1), sizeof(int), cudaMemcpyDeviceToDevice, cs));
+        // ... and the pose before it (motion model of the next chain's first frame): frame nF - 2, or the previously carried pose for a one-frame batch
+        if (nF >= 2) CU(cudaMemcpyAsync(c_prev, poses + 7 * (size_t)(nF - 2), 7 * sizeof(float), cudaMemcpyDeviceToDevice, cs));
+        else if (cont) CU(cudaMemcpyAsync(c_prev, c_pose, 7 * sizeof(float), cudaMemcpyDeviceToDevice, cs));
         CU(cudaMemcpyAsync(c_pose, poses + 7 * (size_t)(nF - 1), 7 * sizeof(float), cudaMemcpyDeviceToDevice, cs));
         if (chain_timing) c->chain_timing_ev = tev;
         CU(cudaGetLastError());
@@ -685,7 +696,7 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
     if (c->prof_on) CU(cudaEventRecord(c->ev_chain_b[slot], cs));
     if (chain_graphs && !chain_timing) {
         Ctx::ChainGraphKey key{};
-        key.nF = nF; key.cap = cap; key.mono = mono; key.cont = cont ? 1 : 0; key.K = K; key.th = th; key.th_local = P.th_local; key.nn_local = P.nn_ratio_local;
+        key.nF = nF; key.cap = cap; key.mono = mono; key.cont = cont ? 1 : 0; key.K = K; key.prev_valid = prev_valid ? 1 : 0; key.th = th; key.th_local = P.th_local; key.nn_local = P.nn_ratio_local;
         key.fx = fx; key.fy = fy; key.cx = cx; key.cy = cy; key.bf = bf; key.generation = c->scratch_generation;
         if (!c->chain_exec[slot] || std::memcmp(&key, &c->chain_key[slot], sizeof(key)) != 0) {
             if (c->chain_exec[slot]) { cudaGraphExecDestroy(c->chain_exec[slot]); c->chain_exec[slot] = nullptr; }
@@ -723,6 +734,7 @@ static int chain_begin(Ctx* c, const rgbl_chain_params& cp_) {
     c->chain_launches[slot] = n_launches;
     c->chain_pending += 1;
     c->chain_has_carry = true; c->carry_K = K; c->carry_cap = cap;
+    c->carry_prev_valid = (nF >= 2) || cont;
     return RGBL_OK;
 }
 

@@ -1083,9 +1083,9 @@ __global__ void __launch_bounds__(256) search_reloc_collect_kernel(FrameDev f, c
 // ---- resident tracking chain (TrackWithMotionModel-style glue between the reference functions) ----------------
 // Every keypoint of the last frame that has a LiDAR depth acts as a map point: Frame::UnprojectStereo
 // (src/Frame.cc:1137-1150) with the last pose, descriptor = the keypoint's own descriptor.
-__global__ void __launch_bounds__(256) chain_prep_kernel(ChainPrepDev cp, const float* __restrict__ last_pose, const float* __restrict__ cur_pose) {
+__global__ void __launch_bounds__(256) chain_prep_kernel(ChainPrepDev cp, const float* __restrict__ last_pose) {
     const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i == 0) chain_prep_flags(cp, last_pose, cur_pose);
+    if (i == 0) chain_prep_motion(cp, last_pose);
     float Rwc[9], Ow[3];
     chain_pose_matrices(last_pose, Rwc, Ow);
     if (i < cp.cap) chain_prep_item(cp, Rwc, Ow, i);
@@ -1175,8 +1175,8 @@ void launch_fuse_search(cudaStream_t st, const FrameDev& f, const int* cell_star
                                                   best_idx, best_dist);
 }
 
-void launch_chain_prep(cudaStream_t st, const ChainPrepDev& cp, const float* last_pose, const float* cur_pose) {
-    chain_prep_kernel<<<(cp.cap + 255) / 256, 256, 0, st>>>(cp, last_pose, cur_pose);
+void launch_chain_prep(cudaStream_t st, const ChainPrepDev& cp, const float* last_pose) {
+    chain_prep_kernel<<<(cp.cap + 255) / 256, 256, 0, st>>>(cp, last_pose);
 }
 
 void launch_frustum(cudaStream_t st, const FrameDev& f, const FrustumParams& prm, int n, const float* xw, const float* normal,

@@ -357,7 +357,7 @@ __global__ void __cluster_dims__(kPoseCtas, 1, 1) __launch_bounds__(kPoseThreads
         __syncthreads();                  // s_posef written by thread 0
         if (rank == 0 && tid < 7) pose_out[tid] = s_posef[tid];
         if (next.kps) {
-            if (rank == 0 && tid == 0) chain_prep_flags(next, s_posef, s_posef);
+            if (rank == 0 && tid == 0) chain_prep_motion(next, s_posef);
             float Rwc[9], Ow[3];
             chain_pose_matrices(s_posef, Rwc, Ow);
             for (int i = gtid; i < next.cap; i += kPoseStride) chain_prep_item(next, Rwc, Ow, i);

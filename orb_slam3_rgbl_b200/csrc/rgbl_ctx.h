@@ -168,6 +168,7 @@ struct Ctx {
     int chain_frames[2] = {}, chain_launches[2] = {}, chain_first[2] = {}, chain_graph_launches[2] = {};
     long chain_tracked_frames = 0;               // frames that went through the chain (frame 0 of a non-continuing chain is given, not tracked)
     bool chain_has_carry = false; int carry_K = 0, carry_cap = 0;
+    bool carry_prev_valid = false;               // the carried sequence also holds the pose BEFORE its last frame (constant-velocity motion model)
     int* h_chain_ovf = nullptr;                  // pinned, per slot: the two frame-construction overflow flags of the tracked batch
     unsigned long long scratch_generation = 1;   // bumped by every reallocation of this context's tracking scratch
     bool chain_timing_on = false, chain_graphs_on = true;   // RGBL_CHAIN_TIMING / RGBL_CHAIN_GRAPH, read at rgbl_create
@@ -177,7 +178,7 @@ struct Ctx {
     int* h_chain_i = nullptr;    // pinned, per slot: n_matches | n_inliers | n_local_matches | n_inliers_first | n_edges x2, flags[2], overflow, n_queries
     size_t h_chain_cap = 0;      // frames per slot
     // the chain of a slot as an instantiated CUDA graph (re-captured when any launch parameter or scratch pointer changes)
-    struct ChainGraphKey { int nF, cap, mono, cont, K; float th, th_local, nn_local, fx, fy, cx, cy, bf; unsigned long long generation; };
+    struct ChainGraphKey { int nF, cap, mono, cont, K, prev_valid; float th, th_local, nn_local, fx, fy, cx, cy, bf; unsigned long long generation; };
     cudaGraphExec_t chain_exec[2] = {};
     ChainGraphKey chain_key[2] = {};
     const void* chain_timing_ev = nullptr;   // RGBL_CHAIN_TIMING development aid

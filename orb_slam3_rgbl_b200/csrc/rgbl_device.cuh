@@ -168,6 +168,36 @@ __device__ __forceinline__ void se3f_inverse(const float* T, float qinv[4], floa
     se3f_rotate(qinv, nt, tinv);
 }
 
+// Sophus::SE3f * SE3f (Thirdparty/Sophus/sophus/se3.hpp:304-308): (Ra Rb, ta + Ra tb).  SO3f * SO3f is the Hamilton product written out in
+// so3.hpp:325-339, evaluated left to right in float32; its result goes through the SO3f(quaternion) constructor, which normalises
+// (so3.hpp:481-487, 297-303: coeffs /= norm).  Poses are (qx, qy, qz, qw, tx, ty, tz); out may not alias A or B.
+__device__ __forceinline__ void se3f_mul(const float* A, const float* B, float* out) {
+    const float ax = A[0], ay = A[1], az = A[2], aw = A[3], bx = B[0], by = B[1], bz = B[2], bw = B[3];
+    const float w = __fsub_rn(__fsub_rn(__fsub_rn(__fmul_rn(aw, bw), __fmul_rn(ax, bx)), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+    const float x = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(aw, bx), __fmul_rn(ax, bw)), __fmul_rn(ay, bz)), __fmul_rn(az, by));
+    const float y = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(aw, by), __fmul_rn(ay, bw)), __fmul_rn(az, bx)), __fmul_rn(ax, bz));
+    const float z = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(aw, bz), __fmul_rn(az, bw)), __fmul_rn(ax, by)), __fmul_rn(ay, bx));
+    const float length = sqrtf(eig_sum4(__fmul_rn(x, x), __fmul_rn(y, y), __fmul_rn(z, z), __fmul_rn(w, w)));
+    out[0] = __fdiv_rn(x, length); out[1] = __fdiv_rn(y, length); out[2] = __fdiv_rn(z, length); out[3] = __fdiv_rn(w, length);
+    float r[3];
+    se3f_rotate(A, B + 4, r);
+    out[4] = __fadd_rn(A[4], r[0]); out[5] = __fadd_rn(A[5], r[1]); out[6] = __fadd_rn(A[6], r[2]);
+}
+
+// Tracking::TrackWithMotionModel's initial pose mVelocity * mLastFrame.GetPose() (src/Tracking.cc:2904) with the constant-velocity model
+// mVelocity = Tcw(last) * Tcw(prev)^-1 (src/Tracking.cc:2243-2245).  prev == nullptr (no velocity yet): the last pose itself.
+__device__ __forceinline__ void predict_pose(const float* prev, const float* last, float* pred) {
+    if (!prev) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) pred[i] = last[i];
+        return;
+    }
+    float inv[7], vel[7];
+    se3f_inverse(prev, inv, inv + 4);
+    se3f_mul(last, inv, vel);
+    se3f_mul(vel, last, pred);
+}
+
 // Eigen QuaternionBase::toRotationMatrix (Geometry/Quaternion.h), float32, row-major R[9]
 __device__ __forceinline__ void quatf_to_matrix(const float q[4], float R[9]) {
     const float x = q[0], y = q[1], z = q[2], w = q[3];
@@ -251,9 +281,16 @@ struct ChainPrepDev {
     const rgbl_keypoint* kps; const float* depth; const int* n_ptr;      // kps == nullptr: disabled
     float fx, fy, cx, cy, mb; int mono, cap;
     uint8_t* valid; float* xw; int* octave; float* angle; uint8_t* obs_pos; int* flags; uint8_t* state_clear;
+    const float* prev_pose;          // pose of the frame BEFORE the one being prepared (nullptr: no velocity yet)
+    float* pred_pose;                // out: the motion model's pose for the next frame = where its search projects and its optimisation starts
 };
 
-__device__ __forceinline__ void chain_prep_flags(const ChainPrepDev& cp, const float* last_pose, const float* cur_pose) {
+// one thread: the next frame's predicted pose and the bForward / bBackward flags of its search (last_pose = the pose of the frame being prepared)
+__device__ __forceinline__ void chain_prep_motion(const ChainPrepDev& cp, const float* last_pose) {
+    float cur_pose[7];
+    predict_pose(cp.prev_pose, last_pose, cur_pose);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) cp.pred_pose[i] = cur_pose[i];
     // tlc = Tlw * (Tcw^-1).translation()
     float cinv[4], twc[3], r[3];
     se3f_inverse(cur_pose, cinv, twc);

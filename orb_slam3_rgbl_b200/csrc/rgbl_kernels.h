@@ -166,7 +166,7 @@ void launch_fuse_search(cudaStream_t st, const FrameDev& f, const int* cell_star
                         const float* Ow /*3, device*/, float th, int* best_idx, int* best_dist);
 // ChainPrepDev (rgbl_device.cuh): unprojection of one frame's LiDAR-depth keypoints with its pose = the map points of the next search
 struct ChainPrepDev;
-void launch_chain_prep(cudaStream_t st, const ChainPrepDev& cp, const float* last_pose, const float* cur_pose);
+void launch_chain_prep(cudaStream_t st, const ChainPrepDev& cp, const float* last_pose);
 void launch_frustum(cudaStream_t st, const FrameDev& f, const FrustumParams& prm, int n, const float* xw, const float* normal,
                     const float* mf_min, const float* mf_max, uint8_t* in_view, float* px, float* py, float* pxr, float* depth,
                     int* level, float* view_cos);

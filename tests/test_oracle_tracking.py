@@ -156,3 +156,32 @@ def test_fuse_search_oracle_vs_bruteforce(seq_frames):
             assert bd[i] == exp[1] and bi[i] in exp[0]
             checked += 1
     assert checked > 20
+
+
+def test_motion_model_pose_prediction():
+    """oracle.chain.se3f_mul / predict_pose restate Sophus::SE3f's product (Thirdparty/Sophus/sophus/se3.hpp:304-308, so3.hpp:325-339 + the
+    normalising quaternion constructor) and Tracking's constant-velocity model (src/Tracking.cc:2243-2245, 2904): group laws in float32
+    tolerance, unit quaternions, and exact extrapolation of a constant motion."""
+    from oracle import chain as OC
+    rng = np.random.default_rng(5)
+
+    def rand_pose():
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        return np.concatenate([q, rng.normal(size=3) * 3]).astype(np.float32)
+
+    def mat(p):
+        R = OC.quat_to_matrix_f32(p[:4]).astype(np.float64); T = np.eye(4); T[:3, :3] = R; T[:3, 3] = p[4:]
+        return T
+
+    for _ in range(50):
+        a, b = rand_pose(), rand_pose()
+        ab = OC.se3f_mul(a, b)
+        assert abs(np.linalg.norm(ab[:4].astype(np.float64)) - 1) < 2e-7
+        assert np.allclose(mat(ab), mat(a) @ mat(b), atol=2e-5)
+        qi, ti = OC.se3f_inverse(a)
+        assert np.allclose(mat(OC.se3f_mul(a, np.concatenate([qi, ti]).astype(np.float32))), np.eye(4), atol=2e-5)
+        # constant motion M: T1 = M T0, so the prediction for the next frame is M T1
+        M = rand_pose(); M[4:] *= 0.05; M[:3] *= 0.02; M[:4] /= np.linalg.norm(M[:4])
+        T0 = rand_pose(); T1 = OC.se3f_mul(M, T0)
+        assert np.allclose(mat(OC.predict_pose(T0, T1)), mat(M) @ mat(T1), atol=5e-5)
+    assert (OC.predict_pose(None, a) == a).all()

@@ -125,6 +125,7 @@ static int create(const rgbl_config* cfg, Ctx** out) {
             const int n_ini = (int)std::round(static_cast<float>(g.max_bx - g.min_bx) / (g.max_by - g.min_by));
             region[l + 1] = region[l] + std::max(g.quota + 3, 4 * n_ini);
             if (g.quota + 3 > 1024 || 4 * n_ini > 1024 || n_ini < 1 || n_ini > 64) fits = false;
+            c->qt_max_nodes = std::max(c->qt_max_nodes, std::max(g.quota + 3, 4 * n_ini));
         }
         int dev_smem = 0;
         cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
@@ -263,7 +264,7 @@ static int run_extract(Ctx* c, int n_frames, const std::function<void()>& aux_wo
         // Fully on-device keypoint distribution: no host round trip between FAST and describe.
         stage_begin(c, ST_QUADTREE, c->st);
         if (launch_quadtree(c->st, c->d_dense, c->d_level_cnt, c->d_frame_total, c->d_levels, nl, c->qt_scr, c->d_sel_lvl, c->d_n_sel_lvl,
-                            c->d_lvl_region, c->cap_kp, c->d_overflow + 1, c->d_sel, c->d_n_sel, n_frames) != 0) {
+                            c->d_lvl_region, c->cap_kp, c->d_overflow + 1, c->d_sel, c->d_n_sel, n_frames, c->qt_max_nodes) != 0) {
             c->err = "quad-tree kernel needs more shared memory than this device allows"; return RGBL_E_CUDA;
         }
         stage_end(c, ST_QUADTREE, c->st, 2);

@@ -164,39 +164,49 @@ QT_BIG void std_sort(SortItem* v, int n) {
 }
 
 // ---- shared-memory state of one tree ------------------------------------------------------------------
-struct NodeTable {
-    short ulx[kMaxNodes], uly[kMaxNodes], brx[kMaxNodes], bry[kMaxNodes];
-    int beg[kMaxNodes], end[kMaxNodes];
+// MAXN = node list capacity (needs quota + 3 <= MAXN and 4 * nIni <= MAXN): 1024 in general; 512 when every level of the context fits, which
+// halves this state (~56 KB) so that TWO trees are resident per SM - a tree is a chain of barrier-separated phases that leaves the SM idle
+// most of the time, and a batch is 8 trees per frame.
+template <int MAXN>
+struct NodeTableT {
+    short ulx[MAXN], uly[MAXN], brx[MAXN], bry[MAXN];
+    int beg[MAXN], end[MAXN];
 };
 
-struct Shared {
-    NodeTable tab[2];
+template <int MAXN>
+struct SharedT {
+    static constexpr int kNodes = MAXN;
+    NodeTableT<MAXN> tab[2];
     // per node of the current table
-    int cc[kMaxNodes][4];          // child key counts of a node that is being divided
-    short pushes[kMaxNodes];       // non-empty children (0 if the node is not divided this pass)
-    short proc[kMaxNodes];         // processing rank inside D (-1 = not divided)
-    int pushbase[kMaxNodes];       // exclusive prefix of pushes in processing order (indexed by processing rank)
-    int keepbase[kMaxNodes];       // exclusive prefix of "survives" flags in list order
-    short by_rank[kMaxNodes];      // node index by processing rank
-    SortItem open[2][kMaxNodes];   // expandable children: [cur] produced by the last pass, [1-cur] being built
-    int open_slot[kMaxNodes * 4];  // per push index: position in the next open list, or -1
+    int cc[MAXN][4];          // child key counts of a node that is being divided
+    short pushes[MAXN];       // non-empty children (0 if the node is not divided this pass)
+    short proc[MAXN];         // processing rank inside D (-1 = not divided)
+    int pushbase[MAXN];       // exclusive prefix of pushes in processing order (indexed by processing rank)
+    int keepbase[MAXN];       // exclusive prefix of "survives" flags in list order
+    short by_rank[MAXN];      // node index by processing rank
+    SortItem open[2][MAXN];   // expandable children: [cur] produced by the last pass, [1-cur] being built
+    int open_slot[MAXN * 4];  // per push index: position in the next open list, or -1
     int n_nodes, n_open, cur_tab, cur_open, n_div, total_push, n_keep, n_expand, scan_total, flag;
     int block_sort;                // 1: block_std_sort (prepared, not yet run on a GPU), 0: one-thread std_sort
     int root_cnt[kMaxRoots + 1];
     unsigned long long scan_carry[1024 + 32];
 };
+typedef SharedT<kMaxNodes> Shared;
+typedef NodeTableT<kMaxNodes> NodeTable;
 
 // global scratch of one tree (segments of the per-batch arrays)
+typedef unsigned short KeyIdx;               // key positions and node indices fit 16 bits (n < 65535 keys, <= 1024 nodes): 17 instead of 25 bytes per key
 struct Scratch {
-    int* perm_a; int* perm_b;                // key permutation (ping-pong)
-    int* node_a; int* node_b;                // node index of the key at each position (ping-pong)
+    KeyIdx* perm_a; KeyIdx* perm_b;          // key permutation (ping-pong)
+    KeyIdx* node_a; KeyIdx* node_b;          // node index of the key at each position (ping-pong)
     unsigned long long* scan;                // n + 1 packed quadrant counters
     unsigned char* quad;                     // quadrant of the key at each position (4 = not moving)
 };
 
 // Exclusive scan of packed counters a[0..n) -> a (exclusive), a[n] = total.  Block-parallel on the device:
 // per-thread chunks, warp shuffle scan of the chunk sums, then a scan of the <= 32 warp totals by warp 0.
-QT_BIG void scan_u64(unsigned long long* a, int n, Shared& s) {
+template <class SharedX>
+QT_BIG void scan_u64(unsigned long long* a, int n, SharedX& s) {
 #if QT_DEVICE
     const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     const int per = (n + nt - 1) / nt;
@@ -228,7 +238,8 @@ QT_BIG void scan_u64(unsigned long long* a, int n, Shared& s) {
 }
 
 // Exclusive scan of ints in shared memory (n <= 2 * blockDim), total returned through *total (shared).
-QT_BIG void scan_int(int* a, int n, int* total, Shared& s) {
+template <class SharedX>
+QT_BIG void scan_int(int* a, int n, int* total, SharedX& s) {
 #if QT_DEVICE
     const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     const int per = (n + nt - 1) / nt;
@@ -277,13 +288,14 @@ QT_BIG void scan_int(int* a, int n, int* total, Shared& s) {
 // divide passes.  depth_limit < 0: the reference's 2 * floor(log2 n).
 struct SortSeg { short first, last, depth, m; };
 
-QT_BIG void block_std_sort(Shared& s, SortItem* v, SortItem* tmp, int n, int depth_limit) {
+template <class SharedX>
+QT_BIG void block_std_sort(SharedX& s, SortItem* v, SortItem* tmp, int n, int depth_limit) {
     if (n <= 1) return;
     int* const scanbuf = &s.cc[0][0];                       // n + 1 packed flags / prefixes
     int* const posL = s.pushbase;                           // stoppers by rank, segment-relative slots
     int* const posR = s.keepbase;
-    SortSeg* const seg[2] = {reinterpret_cast<SortSeg*>(&s.cc[0][0] + kMaxNodes + 8), reinterpret_cast<SortSeg*>(&s.cc[0][0] + kMaxNodes + 8) + 128};
-    int* const ctl = &s.cc[0][0] + kMaxNodes + 8 + 512;     // [0] segments of this level, [1] of the next, [2] fallback flag
+    SortSeg* const seg[2] = {reinterpret_cast<SortSeg*>(&s.cc[0][0] + SharedX::kNodes + 8), reinterpret_cast<SortSeg*>(&s.cc[0][0] + SharedX::kNodes + 8) + 128};
+    int* const ctl = &s.cc[0][0] + SharedX::kNodes + 8 + 512;     // [0] segments of this level, [1] of the next, [2] fallback flag
     QT_FOR(i, n) tmp[i] = v[i];                             // saved input for the fallback
     QT_SINGLE {
         int lg = 0;
@@ -406,13 +418,14 @@ QT_FN int cand_s(unsigned int c) { return (int)(c >> 24); }
 // Divide the nodes marked in s.proc (processing rank >= 0, s.n_div of them, s.by_rank filled) and rebuild the list.
 // On exit: s.cur_tab flipped, s.n_nodes updated, s.open[1-cur_open] holds the new expandable children in push
 // order and s.cur_open is flipped; perm/node arrays flipped by the caller-visible flag `pp` (returns new value).
-QT_BIG int divide_pass(Shared& s, const unsigned int* cand, int n, Scratch g, int pp) {
-    NodeTable& T = s.tab[s.cur_tab];
-    NodeTable& U = s.tab[1 - s.cur_tab];
-    int* perm = pp ? g.perm_b : g.perm_a;
-    int* perm2 = pp ? g.perm_a : g.perm_b;
-    int* nod = pp ? g.node_b : g.node_a;
-    int* nod2 = pp ? g.node_a : g.node_b;
+template <class SharedX>
+QT_BIG int divide_pass(SharedX& s, const unsigned int* cand, int n, Scratch g, int pp) {
+    auto& T = s.tab[s.cur_tab];
+    auto& U = s.tab[1 - s.cur_tab];
+    KeyIdx* perm = pp ? g.perm_b : g.perm_a;
+    KeyIdx* perm2 = pp ? g.perm_a : g.perm_b;
+    KeyIdx* nod = pp ? g.node_b : g.node_a;
+    KeyIdx* nod2 = pp ? g.node_a : g.node_b;
     const int nn = s.n_nodes;
 
     // quadrant of every key that belongs to a divided node
@@ -524,7 +537,8 @@ QT_BIG int divide_pass(Shared& s, const unsigned int* cand, int n, Scratch g, in
 // Whole DistributeOctTree.  cand: n packed candidates (x, y relative to (minX, minY), reference order).
 // out: packed candidates of the survivors in the reference's output order.  Returns the count (or -1 if the
 // configuration exceeds the on-chip capacities; the caller then uses the host implementation).
-QT_FN int distribute(Shared& s, const unsigned int* cand, int n, int width, int height, int N, Scratch g,
+template <class SharedX>
+QT_FN int distribute(SharedX& s, const unsigned int* cand, int n, int width, int height, int N, Scratch g,
                      unsigned int* out, int out_cap, int block_sort = 0) {
     if (n <= 0) return 0;
     QT_SINGLE { s.block_sort = block_sort; }
@@ -533,7 +547,7 @@ QT_FN int distribute(Shared& s, const unsigned int* cand, int n, int width, int 
 #else
     const int n_ini = (int)std::round(static_cast<float>(width) / height);
 #endif
-    if (n_ini < 1 || n_ini > kMaxRoots || 4 * n_ini > kMaxNodes || N + 3 > kMaxNodes || n >= 65535) return -1;
+    if (n_ini < 1 || n_ini > kMaxRoots || 4 * n_ini > SharedX::kNodes || N + 3 > SharedX::kNodes || n >= 65535) return -1;
     const float hX = static_cast<float>(width) / n_ini;
 
     // ---- roots: stable bucket of the candidates by root index ----
@@ -563,7 +577,7 @@ QT_FN int distribute(Shared& s, const unsigned int* cand, int n, int width, int 
         QT_SYNC();
     }
     QT_SINGLE {
-        NodeTable& T = s.tab[0];
+        auto& T = s.tab[0];
         int m = 0, start = 0;
         for (int r = 0; r < n_ini; ++r) {
             const int c = s.root_cnt[r];
@@ -579,7 +593,7 @@ QT_FN int distribute(Shared& s, const unsigned int* cand, int n, int width, int 
     }
     QT_SYNC();
     {
-        const NodeTable& T = s.tab[0];
+        const auto& T = s.tab[0];
         const int m = s.n_nodes;
         QT_FOR(i, m) { for (int p = T.beg[i]; p < T.end[i]; ++p) g.node_a[p] = i; }
     }
@@ -589,7 +603,7 @@ QT_FN int distribute(Shared& s, const unsigned int* cand, int n, int width, int 
     for (;;) {
         const int prev = s.n_nodes;
         {   // full pass: D = every node with more than one key, processed in list order
-            const NodeTable& T = s.tab[s.cur_tab];
+            const auto& T = s.tab[s.cur_tab];
             if (s.block_sort) {              // the same compaction through a block scan of the flags
                 QT_FOR(i, prev) s.pushbase[i] = (T.end[i] - T.beg[i] > 1) ? 1 : 0;
                 QT_SYNC();
@@ -625,13 +639,13 @@ QT_FN int distribute(Shared& s, const unsigned int* cand, int n, int width, int 
                 QT_SYNC();
                 // child counts of every open node (they are all candidates for division)
                 {
-                    const NodeTable& T = s.tab[s.cur_tab];
+                    const auto& T = s.tab[s.cur_tab];
                     QT_FOR(i, prev2) s.proc[i] = -1;
                     QT_SYNC();
                     QT_FOR(k, n_open) { const int r = n_open - 1 - k; s.proc[s.open[s.cur_open][k].node] = (short)r; s.by_rank[r] = (short)s.open[s.cur_open][k].node; }
                     QT_SYNC();
                     // count non-empty children per open node with a direct scan of its (small) key segment
-                    int* perm = pp ? g.perm_b : g.perm_a;
+                    KeyIdx* perm = pp ? g.perm_b : g.perm_a;
                     QT_FOR(r, n_open) {
                         const int nd = s.by_rank[r];
                         const int hx = (T.brx[nd] - T.ulx[nd] + 1) >> 1, hy = (T.bry[nd] - T.uly[nd] + 1) >> 1;
@@ -687,8 +701,8 @@ QT_FN int distribute(Shared& s, const unsigned int* cand, int n, int width, int 
 
     // ---- best key per node, in list order (src/ORBextractor.cc:757-776) ----
     {
-        const NodeTable& T = s.tab[s.cur_tab];
-        const int* perm = pp ? g.perm_b : g.perm_a;
+        const auto& T = s.tab[s.cur_tab];
+        const KeyIdx* perm = pp ? g.perm_b : g.perm_a;
         const int m = s.n_nodes;
         QT_FOR(i, m) {
             unsigned int best = cand[perm[T.beg[i]]];

@@ -14,13 +14,15 @@
 
 namespace rgbl {
 
-__global__ void __launch_bounds__(512) quadtree_kernel(const uint32_t* __restrict__ dense, const int* __restrict__ level_cnt,
+template <int MAXN>
+__global__ void __launch_bounds__(512, MAXN <= 512 ? 2 : 1) quadtree_kernel(const uint32_t* __restrict__ dense, const int* __restrict__ level_cnt,
                                                        const int* __restrict__ frame_total, const LevelGeom* __restrict__ levels,
                                                        int n_levels, QtScratchDev scr, uint32_t* __restrict__ sel_lvl,
                                                        int* __restrict__ n_sel_lvl, const int* __restrict__ lvl_region,
                                                        int cap_kp, int* __restrict__ status, int dyn_bytes, int block_sort) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    qt::Shared& s = *reinterpret_cast<qt::Shared*>(smem_raw);
+    typedef qt::SharedT<MAXN> SharedX;
+    SharedX& s = *reinterpret_cast<SharedX*>(smem_raw);
     // level-major block order: with one CTA per SM (the key arrays take the whole shared memory) a batch is more than one wave, and a
     // level's run time grows with its candidate count - the long level-0 trees start first, the short ones fill the tail
     const int l = blockIdx.y, f = blockIdx.x;
@@ -31,17 +33,18 @@ __global__ void __launch_bounds__(512) quadtree_kernel(const uint32_t* __restric
     const LevelGeom lg = levels[l];
     qt::Scratch g;
     const int so = off + (f * n_levels + l);          // one extra scan slot per preceding tree
-    // The per-key arrays (two permutations, two node maps, packed scan counters, quadrants: 25 bytes per key) are walked by
+    // The per-key arrays (two permutations, two node maps as 16-bit indices, packed scan counters, quadrants: 17 bytes per key) are walked by
     // every subdivision pass with a dozen barrier-separated phases; in global memory each phase pays an L2 round trip.  They
     // live in the rest of the CTA's shared memory whenever the level's candidates fit (falls back to the global scratch).
-    const size_t key_bytes = (size_t)(n + 1) * 8 + (size_t)n * (4 * 4 + 1) + 64;
-    if (sizeof(qt::Shared) + key_bytes <= (size_t)dyn_bytes) {
-        unsigned char* base = smem_raw + ((sizeof(qt::Shared) + 15) & ~(size_t)15);
+    const size_t key_bytes = (size_t)(n + 1) * 8 + (size_t)(n + 1) * (4 * 2 + 1) + 64;
+    if (sizeof(SharedX) + key_bytes <= (size_t)dyn_bytes) {
+        unsigned char* base = smem_raw + ((sizeof(SharedX) + 15) & ~(size_t)15);
         g.scan = reinterpret_cast<unsigned long long*>(base); base += (size_t)(n + 1) * 8;
-        g.perm_a = reinterpret_cast<int*>(base); base += (size_t)n * 4;
-        g.perm_b = reinterpret_cast<int*>(base); base += (size_t)n * 4;
-        g.node_a = reinterpret_cast<int*>(base); base += (size_t)n * 4;
-        g.node_b = reinterpret_cast<int*>(base); base += (size_t)n * 4;
+        const size_t kb = ((size_t)n * sizeof(qt::KeyIdx) + 7) & ~(size_t)7;
+        g.perm_a = reinterpret_cast<qt::KeyIdx*>(base); base += kb;
+        g.perm_b = reinterpret_cast<qt::KeyIdx*>(base); base += kb;
+        g.node_a = reinterpret_cast<qt::KeyIdx*>(base); base += kb;
+        g.node_b = reinterpret_cast<qt::KeyIdx*>(base); base += kb;
         g.quad = base;
     } else {
         g.perm_a = scr.perm_a + off; g.perm_b = scr.perm_b + off; g.node_a = scr.node_a + off; g.node_b = scr.node_b + off;
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(512) quadtree_kernel(const uint32_t* __restric
 #endif
     const int m = qt::distribute(s, dense + off, n, lg.max_bx - lg.min_bx, lg.max_by - lg.min_by, lg.quota, g, out, region_cap, block_sort);
 #ifdef QT_TIMING
-    if (threadIdx.x == 0 && f == 0) printf("quadtree level %d: n=%d quota=%d selected=%d keys_on_chip=%d cycles=%lld\n", l, n, lg.quota, m, (int)(sizeof(qt::Shared) + key_bytes <= (size_t)dyn_bytes), clock64() - qt_t0);
+    if (threadIdx.x == 0 && f == 0) printf("quadtree level %d: n=%d quota=%d selected=%d keys_on_chip=%d cycles=%lld\n", l, n, lg.quota, m, (int)(sizeof(SharedX) + key_bytes <= (size_t)dyn_bytes), clock64() - qt_t0);
 #endif
     if (threadIdx.x == 0) {
         if (m < 0 || m > region_cap) { atomicExch(status, 1); n_sel_lvl[f * RGBL_MAX_LEVELS + l] = 0; }
@@ -83,35 +86,50 @@ __global__ void __launch_bounds__(256) sel_pack_kernel(const uint32_t* __restric
     if (threadIdx.x == 0) n_sel[f] = base;
 }
 
-int quadtree_smem_bytes() { return (int)sizeof(qt::Shared); }
+int quadtree_smem_bytes() { return (int)sizeof(qt::SharedT<512>); }
+
+// dynamic shared memory of one variant: everything an SM offers divided by the resident CTAs (tree state + the per-key arrays when they fit)
+template <int MAXN>
+static int quadtree_dyn_bytes(int ctas_per_sm) {
+    int dev = 0, optin = 0, per_sm = 0;
+    cudaFuncAttributes fa{};
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa, quadtree_kernel<MAXN>) != cudaSuccess) return -1;
+    int avail = optin - (int)fa.sharedSizeBytes - 256;
+    if (ctas_per_sm > 1) avail = std::min(avail, per_sm / ctas_per_sm - 1024 /* reserved per CTA */ - (int)fa.sharedSizeBytes - 256);
+    if (avail < (int)sizeof(qt::SharedT<MAXN>)) return -1;
+    if (cudaFuncSetAttribute(quadtree_kernel<MAXN>, cudaFuncAttributeMaxDynamicSharedMemorySize, avail) != cudaSuccess) return -1;
+    return avail;
+}
 
 int launch_quadtree(cudaStream_t st, const uint32_t* dense, const int* level_cnt, const int* frame_total, const LevelGeom* d_levels,
                     int n_levels, const QtScratchDev& scr, uint32_t* sel_lvl, int* n_sel_lvl, const int* lvl_region, int cap_kp,
-                    int* status, SelKp* sel, int* n_sel, int n_frames) {
-    // all the opt-in shared memory of an SM: the tree state + (when they fit) the per-key arrays of the level
-    static int dyn_bytes = 0;
-    if (!dyn_bytes) {
-        int dev = 0, optin = 0;
-        cudaFuncAttributes fa{};
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess ||
-            cudaFuncGetAttributes(&fa, quadtree_kernel) != cudaSuccess) return -1;
-        const int avail = optin - (int)fa.sharedSizeBytes - 256;
-        if (avail < (int)sizeof(qt::Shared)) return -1;
-        if (cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, avail) != cudaSuccess) return -1;
-        dyn_bytes = avail;
-    }
+                    int* status, SelKp* sel, int* n_sel, int n_frames, int max_nodes) {
+    // max_nodes = the largest node list any level of the context needs (max(quota + 3, 4 nIni)): <= 512 selects the half-size tree state
+    // with two CTAs per SM (RGBL_QT_TWO_PER_SM=0: one per SM with all the shared memory, as in round 1)
+    static const int two_per_sm = [] { const char* e = getenv("RGBL_QT_TWO_PER_SM"); return (e && e[0] == '0') ? 0 : 1; }();
+    static int dyn512 = 0, dyn1024 = 0;
+    const bool small = max_nodes <= 512;
+    int& dyn_bytes = small ? dyn512 : dyn1024;
+    if (!dyn_bytes) dyn_bytes = small ? quadtree_dyn_bytes<512>(two_per_sm ? 2 : 1) : quadtree_dyn_bytes<1024>(1);
+    if (dyn_bytes <= 0) return -1;
     // block-parallel std::sort of the budgeted expansion: measured on B200 in round 2 (0.44 -> 0.27 ms per 32 frames), the default;
     // RGBL_QT_BLOCK_SORT=0 selects the one-thread sort
     static const int block_sort = [] { const char* e = getenv("RGBL_QT_BLOCK_SORT"); return (e && e[0] == '0') ? 0 : 1; }();
-    quadtree_kernel<<<dim3(n_frames, n_levels), 512, dyn_bytes, st>>>(dense, level_cnt, frame_total, d_levels, n_levels, scr,
-                                                                   sel_lvl, n_sel_lvl, lvl_region, cap_kp, status, dyn_bytes, block_sort);
+    if (small)
+        quadtree_kernel<512><<<dim3(n_frames, n_levels), 512, dyn_bytes, st>>>(dense, level_cnt, frame_total, d_levels, n_levels, scr, sel_lvl, n_sel_lvl,
+                                                                             lvl_region, cap_kp, status, dyn_bytes, block_sort);
+    else
+        quadtree_kernel<1024><<<dim3(n_frames, n_levels), 512, dyn_bytes, st>>>(dense, level_cnt, frame_total, d_levels, n_levels, scr, sel_lvl, n_sel_lvl,
+                                                                              lvl_region, cap_kp, status, dyn_bytes, block_sort);
     sel_pack_kernel<<<n_frames, 256, 0, st>>>(sel_lvl, n_sel_lvl, lvl_region, n_levels, cap_kp, sel, n_sel);
     return 0;
 }
 
 // Host execution of the SAME block algorithm (phase-sequential): CPU validation of the device logic.
 int quadtree_block_host(const uint32_t* cand, int n, int width, int height, int N, uint32_t* out, int out_cap, int block_sort) {
-    std::vector<int> pa(n + 1), pb(n + 1), na(n + 1), nb(n + 1);
+    std::vector<qt::KeyIdx> pa(n + 1), pb(n + 1), na(n + 1), nb(n + 1);
     std::vector<unsigned long long> scan(n + 2);
     std::vector<unsigned char> quad(n + 1);
     qt::Scratch g{pa.data(), pb.data(), na.data(), nb.data(), scan.data(), quad.data()};

@@ -59,11 +59,11 @@ void launch_padded_level(cudaStream_t st, const uint8_t* pyr, size_t frame_strid
                          uint8_t* dst, int dst_pitch);
 
 // quadtree_kernels.cu
-struct QtScratchDev { int *perm_a, *perm_b, *node_a, *node_b; unsigned long long* scan; unsigned char* quad; };
+struct QtScratchDev { unsigned short *perm_a, *perm_b, *node_a, *node_b; unsigned long long* scan; unsigned char* quad; };      // 16-bit key / node indices (quadtree_block.cuh: KeyIdx)
 int quadtree_smem_bytes();
 int launch_quadtree(cudaStream_t st, const uint32_t* dense, const int* level_cnt, const int* frame_total, const LevelGeom* d_levels,
                     int n_levels, const QtScratchDev& scr, uint32_t* sel_lvl, int* n_sel_lvl, const int* lvl_region, int cap_kp,
-                    int* status, SelKp* sel, int* n_sel, int n_frames);
+                    int* status, SelKp* sel, int* n_sel, int n_frames, int max_nodes = 1024);      // max_nodes: largest max(quota + 3, 4 nIni) over the levels
 int quadtree_block_host(const uint32_t* cand, int n, int width, int height, int N, uint32_t* out, int out_cap, int block_sort = 0);
 
 // depth_kernels.cu

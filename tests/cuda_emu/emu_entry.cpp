@@ -73,14 +73,14 @@ int emu_quadtree(const int32_t* xys, int n, int w, int h, int n_desired, int32_t
     std::vector<uint32_t> dense(n + 1);
     for (int i = 0; i < n; ++i) dense[i] = pack_cand(xys[3 * i], xys[3 * i + 1], xys[3 * i + 2]);
     int level_cnt[RGBL_MAX_LEVELS] = {n}, frame_total = n, lvl_region[2] = {0, cap}, status = 0, n_sel = 0, n_sel_lvl[RGBL_MAX_LEVELS] = {0};
-    std::vector<int> pa(n + 8), pb(n + 8), na(n + 8), nb(n + 8);
+    std::vector<unsigned short> pa(n + 8), pb(n + 8), na(n + 8), nb(n + 8);
     std::vector<unsigned long long> scan(n + 16);
     std::vector<unsigned char> quad(n + 8);
     QtScratchDev scr{pa.data(), pb.data(), na.data(), nb.data(), scan.data(), quad.data()};
     std::vector<uint32_t> sel_lvl(cap + 8);
     std::vector<SelKp> sel(cap + 8);
     if (launch_quadtree(nullptr, dense.data(), level_cnt, &frame_total, &lg, 1, scr, sel_lvl.data(), n_sel_lvl, lvl_region, cap, &status,
-                        sel.data(), &n_sel, 1) != 0) return -100;
+                        sel.data(), &n_sel, 1, n_desired + 3 <= 512 ? 512 : 1024) != 0) return -100;
     if (status) return RGBL_E_CAPACITY;
     for (int i = 0; i < n_sel; ++i) { out_xys[3 * i] = sel[i].x; out_xys[3 * i + 1] = sel[i].y; out_xys[3 * i + 2] = sel[i].score; }
     return n_sel;
@@ -128,7 +128,7 @@ int emu_extract(const rgbl_orb_params* orb, const uint8_t* img, int width, int h
     }
     const int cap_kp = region[nl];
     const int n = frame_total;
-    std::vector<int> pa(n + nl + 8), pb(n + nl + 8), na(n + nl + 8), nb(n + nl + 8);
+    std::vector<unsigned short> pa(n + nl + 8), pb(n + nl + 8), na(n + nl + 8), nb(n + nl + 8);
     std::vector<unsigned long long> scan(n + nl + 16);
     std::vector<unsigned char> quad(n + nl + 8);
     QtScratchDev scr{pa.data(), pb.data(), na.data(), nb.data(), scan.data(), quad.data()};

@@ -479,7 +479,7 @@ def main():
                 "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": main_res["e2e"]["h2d_bytes_per_step"], "d2h_bytes_per_step": main_res["e2e"]["d2h_bytes_per_step"],
                         "ms_per_step": main_res["e2e"]["ms_per_step"], "steps": main_res["e2e"]["steps"]},
                 "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"], "roofline": roofline, "frame_construction": frame_construction, "kernels": kernels,
-                "tracking_chain": {"ms_per_step": chain_ms, "us_per_frame": 1e3 * chain_ms / T, "bound": "latency (serial in time; single-CTA resolution and FP64 LM kernels)",
+                "tracking_chain": {"ms_per_step": chain_ms, "us_per_frame": 1e3 * chain_ms / T, "bound": "latency (serial in time: 7 dependent kernels per frame - two candidate searches, two single-CTA resolutions, the frustum compaction, two FP64 LM solves on an 8-CTA cluster - chained by programmatic dependent launches inside a CUDA graph)",
                                    **main_res["tracking"]},
                 "per_rank_ms_per_step": {"min": float(min(rank_ms)), "max": float(max(rank_ms))},
                 "configs": side, "compute_bow": bow, "local_bundle_adjustment": lba,

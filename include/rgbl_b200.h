@@ -308,7 +308,9 @@ int rgbl_resident_compute_bow(rgbl_ctx* ctx, const rgbl_vocabulary* voc, int fra
 
 /* Resident tracking chain over the frames of the last batched call, entirely on the device: for t = 1..n-1
  * SearchByProjection(frame t, frame t-1, th) -> PoseOptimization, every LiDAR-depth keypoint of frame t-1 acting as a map
- * point (Frame::UnprojectStereo, src/Frame.cc:1137-1150, with the estimated pose of t-1; constant-pose motion model).
+ * point (Frame::UnprojectStereo, src/Frame.cc:1137-1150, with the estimated pose of t-1).  Frame t is searched and its optimisation
+ * started at the constant-velocity prediction mVelocity * Tcw(t-1), mVelocity = Tcw(t-1) * Tcw(t-2)^-1 (src/Tracking.cc:2904,
+ * 2243-2245; Sophus SE3f products); frame 1 of a sequence has no velocity yet and starts at the pose of frame 0.
  * This is harness glue around the two reference functions (Tracking::TrackWithMotionModel, src/Tracking.cc:2888-2981,
  * stays on the host in the drop-in).  poses_out[n][7], n_matches[n], n_inliers[n]; entry 0 = (pose0, 0, 0).           */
 int rgbl_resident_track(rgbl_ctx* ctx, const float pose0[7], float fx, float fy, float cx, float cy, float bf, float th, int mono,
@@ -325,15 +327,15 @@ int rgbl_resident_track_begin(rgbl_ctx* ctx, const float pose0[7], float fx, flo
 int rgbl_resident_track_end(rgbl_ctx* ctx, float* poses_out, int* n_matches, int* n_inliers);
 
 /* The full per-frame tracking path of the reference for an RGB-L frame, and batches that continue one sequence:
- *   TrackWithMotionModel (src/Tracking.cc:2888-2981): SearchByProjection(frame t, frame t-1, th_last) -> PoseOptimization -> outliers
- *     discarded;
+ *   TrackWithMotionModel (src/Tracking.cc:2888-2981): pose predicted by the constant-velocity model (:2904), SearchByProjection(frame t,
+ *     frame t-1, th_last) -> PoseOptimization -> outliers discarded;
  *   TrackLocalMap (src/Tracking.cc:2983-3050 with SearchLocalPoints :3377-3460), when local_map_frames = K > 0: Frame::isInFrustum over
  *     the local map, SearchByProjection(frame t, local points, th_local, nn_ratio_local) -> PoseOptimization on all map points.  The
  *     local map of this harness = the LiDAR-depth keypoints of the K frames before t-1, unprojected with their final poses, with
  *     MapPoint::UpdateNormalAndDepth's normal / scale-invariance distances for one observation (src/MapPoint.cc:437-490); it lives on
  *     the device as a ring (slot = frame counter mod K) and its points are searched in ring order.
  * continue_sequence != 0: frame 0 of this batch is tracked against the LAST frame of the previous chain of this context (keypoints,
- *   pose and local map stay in HBM), so consecutive batches form one sequence and every frame of the batch is tracked; pose0 is
+ *   pose, the pose before it - for the velocity - and local map stay in HBM), so consecutive batches form one sequence and every frame of the batch is tracked; pose0 is
  *   ignored.  continue_sequence == 0 starts a sequence: frame 0 gets pose0 and the local map is emptied.
  * th_last: 15 (7 for System::STEREO, src/Tracking.cc:2913-2917); th_local: 3 for RGB-L / RGB-D, else 1 (:3432-3436); nn_ratio_local 0.8. */
 typedef struct rgbl_chain_params {

@@ -197,7 +197,9 @@ def _ref_worker_init(cfg_key, seed):
 
 
 def _ref_worker_step(n_frames):
-    return _WORKER["cs"].advance(n_frames)
+    c0 = time.process_time()
+    n = _WORKER["cs"].advance(n_frames)
+    return n, time.process_time() - c0
 
 
 def run_reference(args, rank, world):
@@ -219,21 +221,32 @@ def run_reference(args, rank, world):
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_ref_worker_init, initargs=("_ref", 1000)) as pool:
         def step():
-            return sum(pool.map(_ref_worker_step, [frames_per_seq] * cores, chunksize=1))
+            r = pool.map(_ref_worker_step, [frames_per_seq] * cores, chunksize=1)
+            return sum(a for a, _ in r), sum(b for _, b in r)
         for _ in range(max(args.warmup, 1)):
             step()
         t0 = time.perf_counter()
-        frames = 0
+        frames, cpu_s = 0, 0.0
         for _ in range(args.steps):
-            frames += step()
+            a, b = step()
+            frames += a; cpu_s += b
         el = time.perf_counter() - t0
     fps = frames / el
+    # what the host actually gave the workers: CPU seconds they consumed per wall second (a container CPU quota or SMT siblings make this
+    # smaller than the number of processes), and the cgroup quota when there is one
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        quota = None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_string(cfg), "frames_per_step": frames_per_seq * cores, "sequences": cores, "frames_per_sequence_per_step": frames_per_seq},
-            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "cores_used": cores, "kind": "port",
-                             "sample": f"{cores} independent sequences (one process per core) x {frames_per_seq} frames per step x {args.steps} steps; oracle = scalar C++ "
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "cores_used": cores, "cores_effective": round(cpu_s / el, 2), "cgroup_cpu_quota": quota, "kind": "port",
+                             "sample": f"{cores} independent sequences (one process per hardware thread the scheduler offers) x {frames_per_seq} frames per step x {args.steps} steps; "
+                                       f"the workers consumed {cpu_s / el:.1f} CPU seconds per wall second; oracle = scalar C++ "
                                        "restatement pinned to the reference's own ORBextractor.cc / DepthModule.cc / ORBmatcher.cc / Optimizer::PoseOptimization + g2o "
                                        "(the reference itself needs OpenCV/Eigen/Pangolin/Boost and cannot be built here)"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -130,7 +130,8 @@ static int create(const rgbl_config* cfg, Ctx** out) {
         int dev_smem = 0;
         cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
         const char* env = getenv("RGBL_HOST_QUADTREE");
-        c->device_quadtree = fits && dev_smem >= quadtree_smem_bytes() && !(env && env[0] == '1');
+        c->qt_device_ok = fits && dev_smem >= quadtree_smem_bytes();
+        c->device_quadtree = c->qt_device_ok && !(env && env[0] == '1');
         CUF(dmalloc(&c->d_lvl_region, nl + 1));
         CUF(cudaMemcpy(c->d_lvl_region, region.data(), (nl + 1) * sizeof(int), cudaMemcpyHostToDevice));
         CUF(dmalloc(&c->d_sel_lvl, (size_t)B * c->cap_kp));
@@ -993,8 +994,8 @@ int rgbl_resident_download(rgbl_ctx* ctx, rgbl_keypoint* kps, uint8_t* desc, flo
 int rgbl_set_host_quadtree(rgbl_ctx* ctx, int on) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RGBL_E_INVALID;
-    if (!on) {
-        for (const LevelGeom& g : c->levels) if (g.quota + 3 > 1024) { c->err = "quota too large for the device quad-tree"; return RGBL_E_UNSUPPORTED; }
+    if (!on && !c->qt_device_ok) {       // the same test rgbl_create made: node capacity, root count and shared memory of every level
+        c->err = "this context's level geometry does not fit the device quad-tree (quota + 3 <= 1024, 1 <= nIni <= 64 per level)"; return RGBL_E_UNSUPPORTED;
     }
     c->device_quadtree = !on;
     return RGBL_OK;

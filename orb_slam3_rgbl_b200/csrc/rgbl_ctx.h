@@ -87,6 +87,7 @@ struct Ctx {
     size_t frame_bytes = 0;
     int n_cells = 0;
     int cap_kp = 0;              // keypoints per frame capacity (nfeatures + 3 per level)
+    bool qt_device_ok = false;   // the context's geometry fits the device quad-tree (every level: quota + 3 <= 1024, 1 <= nIni <= 64, shared memory)
     int qt_max_nodes = 0;        // largest node list of any level's quad-tree (selects the half-size tree state: two trees per SM)
     int dense_cap = 0;           // candidates per batch capacity
     std::string err;

@@ -231,6 +231,39 @@ def test_full_tracking_chain_continuous_sequence(K):
         assert got[2]["n_local_matches"].min() > 50          # the local map contributes matches once it holds frames
 
 
+def test_chain_is_the_same_with_and_without_programmatic_dependent_launches(monkeypatch):
+    """The chain's kernels are launched with the programmatic-stream-serialization attribute inside a CUDA graph (every kernel starts with
+    griddepcontrol.wait); RGBL_CHAIN_PDL=0 launches them the ordinary way and RGBL_CHAIN_GRAPH=0 without a graph.  Same inputs -> bitwise
+    the same poses and counts in all three modes, also for a second chain that continues the sequence (carried last frame, previous pose
+    for the motion model, local-map ring)."""
+    T = 4
+    seq = S.PlaneSequence(47, 2 * T + 1)
+    prm = F.make_depth_params(bf=S.KITTI_BF)
+    results = []
+    for env in ({}, {"RGBL_CHAIN_PDL": "0"}, {"RGBL_CHAIN_GRAPH": "0"}):
+        for k in ("RGBL_CHAIN_PDL", "RGBL_CHAIN_GRAPH"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c = F.Context(S.KITTI_W, S.KITTI_H, 2000, max_batch=T, max_points=seq.cloud(0).shape[1])      # the switches are read by rgbl_create
+        try:
+            out = []
+            for b in range(2):
+                ts = range(b * T, (b + 1) * T)
+                batch = F.RgblBatch(c, [seq.image(t) for t in ts], [seq.cloud(t) for t in ts], seq.P, prm, pinned=False)
+                batch.upload(); batch.process_resident()
+                batch.track_begin2(F.make_chain_params(seq.pose(0), *TD.CAM, th_last=15.0, continue_sequence=(b > 0), local_map_frames=2, th_local=3.0))
+                out.append(batch.track_end2())
+            results.append(out)
+        finally:
+            c.close()
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            for key in ("poses", "n_matches", "n_inliers", "n_local_matches", "n_inliers_first"):
+                assert (a[key] == b[key]).all(), key
+    assert results[0][1]["n_local_matches"].min() > 50
+
+
 def test_async_chain_overlapping_next_batch_is_identical():
     """rgbl_resident_track_begin/_end: the chain of batch A keeps running on its own stream (on its snapshot of A's frame
     outputs) while batch B is uploaded and processed in the same context; both chains must equal the synchronous results,

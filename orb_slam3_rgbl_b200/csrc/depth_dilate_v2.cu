@@ -1,12 +1,13 @@
-// Variant of depth_resolve_dilate_kernel (depth_kernels.cu; DepthModule::Upsample_InverseDilation, src/DepthModule.cc:230-274).
-// STATUS: validated on the CUDA-on-CPU shim against the oracle (tests/test_cuda_emu.py); not yet run on a GPU, therefore NOT
-// the default: RGBL_DILATE_V2=1 selects it (api.cu).
+// DepthModule::Upsample_InverseDilation (src/DepthModule.cc:230-274): the default kernel since round 2 (RGBL_DILATE_V2=0 selects
+// depth_resolve_dilate_kernel of depth_kernels.cu); validated on the CUDA-on-CPU shim and on the GPU against the oracle.
 //
-// Two changes, results identical by construction (max is exact and order-free):
+// Against that first kernel, results identical by construction (max is exact and order-free):
 //   * a tile whose staged window holds no LiDAR return skips the structuring-element loop: every in-image value of the inverted
 //     map is 0 there, so the output is 0 whatever the element is (most of the upper half of a KITTI frame);
 //   * the (dy, dx) taps are turned once per CTA into shared-memory offsets, so a tap costs two shared loads and one FMNMX
-//     instead of two constant-bank loads, the address arithmetic, one shared load and one FMNMX.
+//     instead of two constant-bank loads, the address arithmetic, one shared load and one FMNMX;
+//   * the 5x5 diamond (the element of the KITTI RGB-L settings, Examples/RGB-L/KITTI00-02.yaml) has its 13 taps compiled in: 13 loads
+//     with immediate offsets and a tree of (3-input) maxima instead of a 13-trip loop with an offset load per tap.
 #include <cfloat>
 
 #include "rgbl_device.cuh"
@@ -28,6 +29,7 @@ __device__ __forceinline__ float project_row2(const float* P, float x, float y, 
 struct DilateTaps2 { int n; int8_t dx[81], dy[81]; };
 }  // namespace
 
+template <int SHAPE /* 0: any element <= 9x9, 1: 5x5 diamond */>
 __global__ void __launch_bounds__(256) depth_resolve_dilate_v2_kernel(const float* __restrict__ pts, int pts_stride, const int* __restrict__ n_pts,
                                                                       DepthDev prm, DilateTaps2 taps, int W, int H,
                                                                       const uint32_t* __restrict__ idx_map, uint32_t stamp,
@@ -88,8 +90,15 @@ __global__ void __launch_bounds__(256) depth_resolve_dilate_v2_kernel(const floa
         const int r = ly + 8 * k, gy = y0 + r;
         if (gy >= H) break;
         const float* tp = &t[(r + HALO) * SP + lx + HALO];
-        float best = -FLT_MAX;
-        for (int q = 0; q < nt; ++q) best = fmaxf(best, tp[s_off[q]]);
+        float best;
+        if (SHAPE == 1) {
+            const float a0 = fmaxf(fmaxf(tp[-2 * SP], tp[-SP - 1]), tp[-SP]), a1 = fmaxf(fmaxf(tp[-SP + 1], tp[-2]), tp[-1]);
+            const float a2 = fmaxf(fmaxf(tp[0], tp[1]), tp[2]), a3 = fmaxf(fmaxf(tp[SP - 1], tp[SP]), tp[SP + 1]);
+            best = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), tp[2 * SP]);
+        } else {
+            best = -FLT_MAX;
+            for (int q = 0; q < nt; ++q) best = fmaxf(best, tp[s_off[q]]);
+        }
         const float o = __fsub_rn(M, best);
         processed[(size_t)frame * W * H + (size_t)gy * W + gx] = (o > thr) ? 0.f : o;
     }
@@ -103,8 +112,12 @@ void launch_depth_resolve_dilate_v2(cudaStream_t st, const float* pts, int pts_s
     for (int j = 0; j < prm.kv; ++j)
         for (int i = 0; i < prm.ku; ++i)
             if (prm.mask[j * prm.ku + i]) { taps.dx[taps.n] = (int8_t)(i - ax); taps.dy[taps.n] = (int8_t)(j - ay); ++taps.n; }
-    depth_resolve_dilate_v2_kernel<<<dim3((W + 31) / 32, (H + 31) / 32, n_frames), 256, 0, st>>>(pts, pts_stride, n_pts, prm, taps, W, H,
-                                                                                              idx_map, stamp, raw, processed);
+    static const int8_t kDiamond5[13][2] = {{0, -2}, {-1, -1}, {0, -1}, {1, -1}, {-2, 0}, {-1, 0}, {0, 0}, {1, 0}, {2, 0}, {-1, 1}, {0, 1}, {1, 1}, {0, 2}};      // (dx, dy) in mask order
+    bool diamond5 = prm.ku == 5 && prm.kv == 5 && taps.n == 13;
+    for (int q = 0; diamond5 && q < 13; ++q) diamond5 = taps.dx[q] == kDiamond5[q][0] && taps.dy[q] == kDiamond5[q][1];
+    const dim3 grid((W + 31) / 32, (H + 31) / 32, n_frames);
+    if (diamond5) depth_resolve_dilate_v2_kernel<1><<<grid, 256, 0, st>>>(pts, pts_stride, n_pts, prm, taps, W, H, idx_map, stamp, raw, processed);
+    else depth_resolve_dilate_v2_kernel<0><<<grid, 256, 0, st>>>(pts, pts_stride, n_pts, prm, taps, W, H, idx_map, stamp, raw, processed);
 }
 
 }  // namespace rgbl

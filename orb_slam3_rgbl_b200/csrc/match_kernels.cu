@@ -7,13 +7,16 @@
 //
 // The reference loops are sequential and greedy: a feature claimed by an earlier map point (with
 // Observations() > 0) is skipped by later ones, so results depend on iteration order.  Here the
-// distance work is data-parallel (one warp per query, __popc Hamming over the 64x48 grid's CSR
-// ranges) and the greedy order is reproduced afterwards by an exact "serial dictatorship" resolution:
-// in rounds, every unresolved query proposes its best still-available candidate and becomes final
-// as soon as no lower-indexed unresolved query can still take (any of) the candidates its decision
-// depends on.  The lowest unresolved query is always final, so the loop terminates; on real data a
-// handful of rounds suffice.  Candidate order (which decides ties) is the reference's: grid column,
-// then row, then keypoint index = ascending position in the column-major CSR.
+// distance work is data-parallel (collect kernels: one warp per query, __popc Hamming over the 64x48 grid's
+// CSR ranges; every query's candidates sorted by key and appended to one dense run) and the greedy order is
+// reproduced afterwards by an exact "serial dictatorship" resolution (resolve_kernel, one CTA, everything in
+// shared memory): in rounds, a waiting query becomes final as soon as it is the lowest-index waiting query
+// among those that list its best and its second-best available feature - the set of available features only
+// shrinks until its turn, so those two are then still its best two.  The lowest waiting query is always final,
+// so the loop terminates; on real data a handful of rounds suffice.  Candidate order (which decides ties) is the
+// reference's: grid column, then row, then keypoint index = ascending position in the column-major CSR.
+// tests/test_resolution_model.py checks the scheme against the sequential loops; DESIGN.md 5b has the measurements
+// that shaped the kernel (no shared-memory atomics per round, no data-dependent loops in the decision).
 #include <cfloat>
 
 #include "rgbl_device.cuh"

@@ -107,12 +107,25 @@ RGBL_HD void centroid_partial(int lane, const uint32_t* patch, int align, const 
 // lane <-> descriptor byte: 8 comparisons of rotated pattern pairs on the blurred window (:112-144)
 RGBL_HD int brief_byte(int lane, const uint32_t* win, int align, float a /*cos*/, float b /*sin*/, const int8_t* pattern) {
     const uint8_t* bytes = reinterpret_cast<const uint8_t*>(win);
+#if defined(__CUDA_ARCH__)
+    // the lane's 32 pattern bytes as two 16-byte loads (the kernel is bound by its load / shared-memory instruction queue: 2 instead of 32 LDG.U8)
+    const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(pattern + lane * 32)), p1 = __ldg(reinterpret_cast<const uint4*>(pattern + lane * 32) + 1);
+    const uint32_t pw[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#else
     const int8_t* pat = pattern + lane * 32;
+#endif
     int val = 0;
+#pragma unroll
     for (int j = 0; j < 8; ++j) {
         int t[2];
+#pragma unroll
         for (int e = 0; e < 2; ++e) {
+#if defined(__CUDA_ARCH__)
+            const uint32_t w = pw[j] >> (16 * e);                       // bytes 4 j + 2 e, + 1 of the lane's pattern row
+            const float px = (float)(int)(int8_t)(w & 0xffu), py = (float)(int)(int8_t)((w >> 8) & 0xffu);
+#else
             const float px = (float)pat[4 * j + 2 * e], py = (float)pat[4 * j + 2 * e + 1];
+#endif
 #if defined(__CUDA_ARCH__)
             const int rr = __float2int_rn(RGBL_FADD(RGBL_FMUL(px, b), RGBL_FMUL(py, a)));
             const int cc = __float2int_rn(RGBL_FSUB(RGBL_FMUL(px, a), RGBL_FMUL(py, b)));

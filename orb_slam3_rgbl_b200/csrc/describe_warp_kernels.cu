@@ -1,6 +1,6 @@
 // Staged variant of describe_kernel (describe_warp.cuh): kernel, launcher, host twin and its test hook.
-// STATUS: host twin validated against the oracle on the CPU (tests/test_host_abi.py); the device path has not been run on a
-// GPU yet and is therefore NOT the default: RGBL_DESCRIBE_STAGED=1 selects it (api.cu).
+// The default describe kernel since round 2 (RGBL_DESCRIBE_STAGED=0 selects describe_kernel of orb_kernels.cu); host twin checked against the oracle on
+// the CPU (tests/test_host_abi.py), device path on the CUDA-on-CPU shim and on the GPU.
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -17,7 +17,7 @@ namespace rgbl {
 static const int8_t h_pattern31[1024] = {
 #include "orb_pattern_31.inc"
 };
-__device__ const int8_t d_pattern31[1024] = {
+__device__ __align__(16) const int8_t d_pattern31[1024] = {
 #include "orb_pattern_31.inc"
 };
 

@@ -187,7 +187,7 @@ struct SharedT {
     SortItem open[2][MAXN];   // expandable children: [cur] produced by the last pass, [1-cur] being built
     int open_slot[MAXN * 4];  // per push index: position in the next open list, or -1
     int n_nodes, n_open, cur_tab, cur_open, n_div, total_push, n_keep, n_expand, scan_total, flag;
-    int block_sort;                // 1: block_std_sort (prepared, not yet run on a GPU), 0: one-thread std_sort
+    int block_sort;                // 1: block_std_sort (the default), 0: one-thread std_sort (RGBL_QT_BLOCK_SORT=0)
     int root_cnt[kMaxRoots + 1];
     unsigned long long scan_carry[1024 + 32];
 };

@@ -185,3 +185,29 @@ def test_motion_model_pose_prediction():
         T0 = rand_pose(); T1 = OC.se3f_mul(M, T0)
         assert np.allclose(mat(OC.predict_pose(T0, T1)), mat(M) @ mat(T1), atol=5e-5)
     assert (OC.predict_pose(None, a) == a).all()
+
+
+def test_oracle_chain_is_the_same_in_one_piece_and_in_batches():
+    """oracle.chain.oracle_chain2 is what the GPU chain tests and bench.py's CPU arms compare / time against.  Its `state` (last frame, its
+    pose, the pose before it for the constant-velocity prediction, the local-map ring and its frame counter) must carry a sequence from one
+    batch into the next exactly: 7 frames tracked in one call, in batches of 3 + 2 + 2, and one frame at a time give bitwise the same
+    poses and counts; and the prediction is used (the first optimisation of a frame starts closer to its result than the last pose is)."""
+    n = 7
+    seq = S.PlaneSequence(83, n + 1)
+    frames, sf = TD.extract_frames(seq, list(range(n)), nfeatures=1000)
+    whole = TD.oracle_chain2(frames, sf, seq.pose(0), K=2)
+    for cuts in ([3, 5], [1, 2, 3, 4, 5, 6]):
+        state, parts = None, []
+        for a, b in zip([0] + cuts, cuts + [n]):
+            out = TD.oracle_chain2(frames[a:b], sf, seq.pose(0), K=2, state=state)
+            state = out[-1]
+            parts.append(out[:-1])
+        for i in range(5):
+            got = np.concatenate([p[i] for p in parts])
+            assert got.shape == whole[i].shape and (got == whole[i]).all(), (cuts, i)
+    poses = whole[0]
+    from oracle import chain as OC
+    for t in range(2, n):
+        pred = OC.predict_pose(poses[t - 2], poses[t - 1])
+        assert np.abs(pred - poses[t]).max() < np.abs(poses[t - 1] - poses[t]).max(), t
+    assert whole[3][3:].min() > 20                     # the local map contributes matches once the ring holds frames
